@@ -1,0 +1,231 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference's own source
+(tests/golden/make_golden.py), plus independent-formulation checks of the restated GPy layer."""
+import contextlib
+import io
+import random
+
+import numpy as np
+import pytest
+
+from conftest import RANGES, load_golden
+from oracle import aq_oracle as aq
+from oracle import gpy_restated as G
+from oracle import mcts_oracle as mo
+from oracle.gpmodel_oracle import GPModelOracle, OnlineGPModelOracle
+
+RTOL = 1e-9          # oracle vs reference source: same numpy ops, so far tighter than the 1e-6 product bar
+
+
+def build_online(g):
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=float(g['noise']), dimension=2)
+    n0, k = int(g['n0']), int(g['k'])
+    m.add_data(g['X'][:n0], g['z'][:n0])
+    for a in range(int(g['appends'])):
+        s = n0 + a * k
+        m.add_data(g['X'][s:s + k], g['z'][s:s + k])
+    return m
+
+
+@pytest.mark.parametrize('name', ['online_gp_n05', 'online_gp_n1e4', 'online_gp_mid'])
+def test_online_gp_matches_reference(name):
+    g = load_golden(name)
+    m = build_online(g)
+    mu, var = m.predict_value(g['q'])
+    np.testing.assert_allclose(mu, g['mu'], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(var, g['var'], rtol=RTOL, atol=1e-9)
+    mu2, var2 = m.predict_value(g['q'], include_noise=False)
+    np.testing.assert_allclose(var2, g['var_nn'], rtol=RTOL, atol=1e-9)
+    muf, cov = m.predict_value(g['q'][:8], include_noise=True, full_cov=True)
+    np.testing.assert_allclose(cov, g['cov_fc'], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(m.woodbury_vector, g['alpha'], rtol=RTOL, atol=1e-9)
+    if 'winv' in g.files:
+        np.testing.assert_allclose(m.woodbury_inv, g['winv'], rtol=RTOL, atol=1e-9)
+
+
+def test_duplicate_rows_q4():
+    g = load_golden('online_gp_duplicates')
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    X, z = g['X'], g['z']
+    m.add_data(X[:22], z[:22])
+    for s in (22, 26):
+        m.add_data(X[s:s + 4], z[s:s + 4])
+        m.add_data(X[s:s + 4], z[s:s + 4])
+    mu, var = m.predict_value(g['q'])
+    np.testing.assert_allclose(mu, g['mu'], rtol=RTOL)
+    np.testing.assert_allclose(var, g['var'], rtol=RTOL)
+
+
+def test_gpy_wrapper_model():
+    g = load_golden('gpmodel_gpy')
+    m = GPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    mu0, var0 = m.predict_value(g['q'])
+    np.testing.assert_array_equal(mu0, g['mu0'])
+    np.testing.assert_array_equal(var0, g['var0'])
+    m.add_data(g['X'][:40], g['z'][:40])
+    m.add_data(g['X'][40:], g['z'][40:])
+    mu, var = m.predict_value(g['q'])
+    np.testing.assert_allclose(mu, g['mu'], rtol=RTOL)
+    np.testing.assert_allclose(var, g['var'], rtol=RTOL)
+    _, var_nn = m.predict_value(g['q'], include_noise=False)
+    np.testing.assert_allclose(var_nn, g['var_nn'], rtol=RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize('tag', ['n05', 'n1e4'])
+def test_rewards_match_reference(tag):
+    g = load_golden('rewards')
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=float(g[tag + '_noise']))
+    m.add_data(g[tag + '_X'], g[tag + '_z'])
+    paths, maxes, t = g[tag + '_paths'], g[tag + '_maxes'], int(g[tag + '_t'])
+    zmax = float(np.max(g[tag + '_z']))
+    tol = dict(rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose([aq.mean_UCB(t, p, m) for p in paths], g[tag + '_ucb'], **tol)
+    np.testing.assert_allclose(aq.mean_UCB(t, paths.reshape(-1, 3), m, FVECTOR=True), g[tag + '_ucb_f'], **tol)
+    np.testing.assert_allclose([aq.exp_improvement(t, p, m, param=[zmax]) for p in paths], g[tag + '_ei'], **tol)
+    np.testing.assert_allclose([aq.exp_improvement(t, p, m) for p in paths], g[tag + '_ei_default'], **tol)
+    got = np.array([aq.mves(t, p, m, (maxes, None, None)) for p in paths])
+    np.testing.assert_allclose(got, g[tag + '_mes'], equal_nan=True, **tol)
+    got = aq.mves(t, paths.reshape(-1, 3), m, (maxes, None, None), FVECTOR=True)
+    np.testing.assert_allclose(got, g[tag + '_mes_f'], equal_nan=True, **tol)
+    np.testing.assert_allclose([aq.info_gain(t, p, m) for p in paths], g[tag + '_ig'], rtol=1e-8, atol=1e-6)
+    np.testing.assert_allclose([aq.hotspot_info_UCB(t, p, m) for p in paths], g[tag + '_hot'], rtol=1e-8, atol=1e-6)
+    np.testing.assert_allclose(
+        [aq.naive(t, p, m, ((maxes, g[tag + '_max_locs'], None), 1.5)) for p in paths], g[tag + '_naive'], **tol)
+
+
+def test_rewards_without_data():
+    g = load_golden('rewards')
+    e = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    p = g['n05_paths'][0]
+    assert aq.mean_UCB(0, p, e) == float(g['empty_ucb']) == 1.0
+    np.testing.assert_array_equal(aq.mean_UCB(0, p, e, FVECTOR=True), g['empty_ucb_f'])
+    np.testing.assert_allclose(aq.info_gain(0, p, e), g['empty_ig'], rtol=1e-12)
+    assert aq.mves(0, p, e, (None, None, None)) == float(g['empty_mes']) == 1.0
+    np.testing.assert_allclose(aq.exp_improvement(0, p, e, param=[-1000]), g['empty_ei'], rtol=1e-12)
+
+
+@pytest.mark.parametrize('tag', ['lt', 'ge'])
+def test_sample_max_vals_matches_reference(tag):
+    """Same seed -> same W, b, eps, grid draws -> same maxima (both theta branches: N<F and N>=F)."""
+    g = load_golden('max_vals')
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(g[tag + '_X'], g[tag + '_z'])
+    np.random.seed(int(g[tag + '_seed']))
+    samples, locs, funcs = aq.sample_max_vals(m, t=0, nK=int(g[tag + '_nK']), nFeatures=int(g[tag + '_F']))
+    np.testing.assert_allclose(samples, g[tag + '_samples'], rtol=1e-7)
+    np.testing.assert_allclose(locs, g[tag + '_locs'], rtol=1e-6, atol=1e-6)
+    fvals = np.hstack([f(g[tag + '_probe']) for f in funcs])
+    np.testing.assert_allclose(fvals, g[tag + '_fvals'], rtol=1e-8, atol=1e-8)
+
+
+@pytest.mark.parametrize('tag,f_rew,tree_type', [('dpw_mean', 'mean', 'dpw'), ('dpw_mes', 'mes', 'dpw'),
+                                                 ('belief_mean', 'mean', 'belief'), ('dpw_ei', 'exp_improve', 'dpw')])
+def test_mcts_action_selection_matches_reference(tag, f_rew, tree_type):
+    g = load_golden('mcts')
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(g['X'], g['z'])
+    pg = mo.PathGeneratorOracle(6, 1.5, 0.05, 0.5, RANGES)
+    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement}[f_rew]
+    aq_param = float(np.max(g['z'])) if f_rew == 'exp_improve' else None
+    np.random.seed(77)
+    random.seed(78)
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+        mcts = mo.cMCTSOracle(int(g[tag + '_budget']), m, (5.0, 5.0, 0.3), 3, pg, fn, f_rew, 4, aq_param=aq_param,
+                              tree_type=tree_type)
+        res = mcts.choose_trajectory(t=4)
+    np.testing.assert_array_equal([c.nqueries for c in mcts.tree.root.children], g[tag + '_nq'])
+    np.testing.assert_allclose(np.array(res[0]), g[tag + '_action'], rtol=1e-12)
+    np.testing.assert_allclose([c.reward / c.nqueries for c in mcts.tree.root.children], g[tag + '_avg'], rtol=1e-7)
+
+
+def test_myopic_path_values():
+    g = load_golden('myopic')
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=1e-4)
+    m.add_data(g['X'], g['z'])
+    pg = mo.PathGeneratorOracle(15, 1.5, 0.05, 0.5, RANGES)
+    paths, _ = pg.get_path_set((4.0, 6.0, 1.1))
+    keys = sorted(paths.keys())
+    np.testing.assert_array_equal(keys, g['keys'])
+    np.testing.assert_allclose(np.array([pt for k in keys for pt in paths[k]]), g['pts'], rtol=1e-13)
+    vals = np.array([aq.mean_UCB(9, paths[k], m) for k in keys])
+    np.testing.assert_allclose(vals, g['vals'], rtol=1e-8)
+    assert keys[int(np.argmax(vals))] == int(g['best'])
+
+
+# ------------------------------------------------------------------ restated-GPy cross-checks (unpinned layer)
+def test_rbf_direct_formula():
+    rng = np.random.default_rng(0)
+    X, Y = rng.uniform(0, 10, (30, 2)), rng.uniform(0, 10, (17, 2))
+    k = G.RBF(2, variance=100.0, lengthscale=1.3)
+    d2 = ((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(k.K(X, Y), 100.0 * np.exp(-0.5 * d2 / 1.3 ** 2), rtol=1e-11)
+    Kxx = k.K(X)
+    assert np.all(np.diag(Kxx) == 100.0)
+    np.testing.assert_array_equal(k.Kdiag(X), np.full(30, 100.0))
+
+
+def test_pdinv_is_inverse_and_symmetric():
+    rng = np.random.default_rng(1)
+    X = rng.uniform(0, 10, (80, 2))
+    A = G.RBF(2, 100.0, 1.0).K(X) + 0.5 * np.eye(80)
+    Ai, L, Li, logdet = G.pdinv(A)
+    assert np.array_equal(Ai, Ai.T)
+    np.testing.assert_allclose(Ai @ A, np.eye(80), atol=1e-9)
+    np.testing.assert_allclose(L @ L.T, A, rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(Li @ L, np.eye(80), atol=1e-10)
+    np.testing.assert_allclose(logdet, np.linalg.slogdet(A)[1], rtol=1e-12)
+
+
+def test_inverse_form_vs_cholesky_form_and_longdouble():
+    """The two GP formulations agree at noise 0.5, and both agree with a
+    long-double evaluation of the same quadratic form."""
+    rng = np.random.default_rng(2)
+    X = rng.uniform(0, 10, (200, 2))
+    z = rng.normal(0, 10, (200, 1))
+    q = rng.uniform(0, 10, (50, 2))
+    on = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    on.add_data(X, z)
+    gm = GPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    gm.add_data(X, z)
+    mu1, v1 = on.predict_value(q)
+    mu2, v2 = gm.predict_value(q)
+    np.testing.assert_allclose(mu1, mu2, rtol=1e-9)
+    np.testing.assert_allclose(v1, v2, rtol=1e-8)
+    Kx = on.kern.K(X, q).astype(np.longdouble)
+    W = on.woodbury_inv.astype(np.longdouble)
+    v_ld = np.longdouble(100.0) - np.einsum('nm,nj,jm->m', Kx, W, Kx) + np.longdouble(0.5)
+    np.testing.assert_allclose(v1[:, 0], v_ld.astype(float), rtol=1e-9)
+
+
+def test_incremental_equals_from_scratch():
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 10, (120, 2))
+    z = rng.normal(0, 10, (120, 1))
+    a = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    a.add_data(X[:100], z[:100])
+    for s in range(100, 120, 4):
+        a.add_data(X[s:s + 4], z[s:s + 4])
+    b = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    b.add_data(X, z)
+    q = rng.uniform(0, 10, (40, 2))
+    np.testing.assert_allclose(a.predict_value(q)[0], b.predict_value(q)[0], rtol=1e-8)
+    np.testing.assert_allclose(a.predict_value(q)[1], b.predict_value(q)[1], rtol=1e-8)
+
+
+def test_analytic_cases():
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(np.array([[3.0, 4.0]]), np.array([[7.0]]))
+    mu, var = m.predict_value(np.array([[3.0, 4.0], [300.0, -200.0]]))
+    s2 = 0.5 + 1e-8
+    np.testing.assert_allclose(mu[0, 0], 100.0 / (100.0 + s2) * 7.0, rtol=1e-13)
+    np.testing.assert_allclose(var[0, 0], 100.0 - 100.0 ** 2 / (100.0 + s2) + 0.5, rtol=1e-10)
+    np.testing.assert_allclose(mu[1, 0], 0.0, atol=1e-300)
+    np.testing.assert_allclose(var[1, 0], 100.5, rtol=1e-15)
+
+
+def test_ctor_errors():
+    with pytest.raises(ValueError):
+        OnlineGPModelOracle(RANGES, 1.0, 100.0, dimension=4)
+    with pytest.raises(ValueError):
+        OnlineGPModelOracle(RANGES, 1.0, 100.0, kernel='matern')
+    with pytest.raises(ValueError):
+        OnlineGPModelOracle(RANGES, (1.0, 1.0), 100.0, dimension=3)
