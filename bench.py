@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- GP posterior mean+var queries/sec at N=4k observations (BASELINE.json metric).
+
+Workload (named in config.workload): BASELINE config 3 at N = 4096 observations x M = 2^20 query
+points per GPU, 10x10 Gaussian world, RBF l=1, variance 100, noise 0.5, FP64.  One "step" = one
+pass of the hot path (cross-covariance, posterior mean, posterior variance) over the M queries.
+
+  value      whole-job queries/s with the queries resident in HBM (device-timed, max over ranks)
+  e2e        the same metric through the drop-in API OnlineGPModel.predict_value(numpy) ->
+             numpy: pinned host buffers, H2D + D2H inside the timed region
+  roofline   the fused DMMA variance kernel: executed flops / its CUDA-event time, against the FP64
+             DGEMM rate of this GPU measured in the same run (cuBLAS via torch.matmul) -- the driver's
+             MEASURED_PEAKS.json holds only HBM and bf16 figures, so the FP64 denominator is
+             measured here by the same method (best of 5, CUDA events) and reported beside it
+  cpu_baseline  the oracle (numpy -> BLAS, all host threads) on a bounded sample of the same queries
+
+`--impl reference` times the reference's CPU path (the numpy oracle port: the reference is Python 2 +
+GPy and cannot run here) on the same config / metric.
+
+Multi-GPU (`torchrun ... bench.py --gpus N`): queries shard across ranks with no data-path collective
+(weak scaling: every rank owns M queries against the replicated belief); barrier + synchronize on both
+sides of the timed region, max over ranks.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_OBS = 4096
+M_QUERIES = 1 << 20
+RANGES = (0., 10., 0., 10.)
+NOISE = 0.5
+METRIC = 'gp_posterior_mean_var_queries_per_sec_at_N4096'
+UNIT = 'queries/s'
+
+
+def make_world(seed, n):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 10, (n, 2))
+    # a draw-like smooth field + sensor noise (synthetic Gaussian-environment data)
+    z = 10.0 * np.sin(0.7 * X[:, :1]) * np.cos(0.5 * X[:, 1:2]) + 3.0 * np.cos(1.3 * X[:, :1] + 0.4 * X[:, 1:2])
+    return X, z + rng.normal(0, np.sqrt(NOISE), (n, 1))
+
+
+def flops_per_query(n, mode='sym'):
+    """Executed flops of the variance GEMM per query: lower 128-tiles + diagonal tiles (sym) or all tiles."""
+    T = (n + 127) // 128
+    tiles = T * (T + 1) // 2 if mode == 'sym' else T * T
+    return 2.0 * tiles * 128 * 128
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_predict_rate(X, z, sample, repeats=1):
+    """The reference's CPU path (oracle port of OnlineGPModel.predict_value, gpmodel_library.py:303-328):
+    numpy -> BLAS with every host thread, queries chunked so the N x M temporaries stay < 2 GB."""
+    from oracle.gpmodel_oracle import OnlineGPModelOracle, predict_chunked
+    rng = np.random.default_rng(123)
+    q = rng.uniform(0, 10, (sample, 2))
+    m = OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=NOISE)
+    t0 = time.perf_counter()
+    m.add_data(X, z)
+    t_factor = time.perf_counter() - t0
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        predict_chunked(m, q, chunk=8192)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample / best, best, t_factor
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    X, z = make_world(0, N_OBS)
+    sample = 16384
+    cpu_predict_rate(X, z, 2048)                       # warm BLAS threads
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, _ = cpu_predict_rate(X, z, sample)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    cores = blas_threads()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'gp_predict N=4096 obs, FP64, 10x10 world RBF l=1 var=100 noise=0.5; each step a bounded '
+                               'sample of %d of the 2^20 queries' % sample, 'n_obs': N_OBS, 'queries_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d queries per step, numpy/BLAS port of gpmodel_library.py:303-328 (reference is '
+                                   'Python 2 + GPy: not runnable in this image)' % sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--queries', type=int, default=M_QUERIES, help='queries per GPU per step (default 2^20)')
+    ap.add_argument('--no-extras', action='store_true', help='skip cpu baseline / reward-path extras (profiling runs)')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from informative_path_planning_b200 import _lib as L
+    from informative_path_planning_b200 import aq_library as aq
+    from informative_path_planning_b200 import gpmodel_library as gp
+    from informative_path_planning_b200 import parallel
+
+    M = args.queries
+    X, z = make_world(0, N_OBS)
+    model = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=NOISE)
+    if world > 1:
+        parallel.add_data_replicated(model, X if rank == 0 else None, z if rank == 0 else None)
+    else:
+        model.add_data(X, z)
+    rng = np.random.default_rng(1000 + rank)
+    xq_host = torch.from_numpy(rng.uniform(0, 10, (M, 2))).pin_memory()
+    xq = xq_host.cuda()
+    kernels_per_step = 3 * ((M + 32767) // 32768)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return model.predict_device(xq)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.check(L.lib.ipp_profile_enable(1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        mean, var = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    tot_ms, launches = ctypes.c_double(0), ctypes.c_int64(0)
+    L.check(L.lib.ipp_profile_read(ctypes.byref(tot_ms), ctypes.byref(launches)))
+    L.check(L.lib.ipp_profile_enable(0))
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * M / (ms_step / 1e3)
+
+    # ---- end to end through the drop-in API (numpy in, numpy out; pinned host buffers)
+    xq_np = xq_host.numpy()
+    for _ in range(2):
+        model.predict_value(xq_np)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        mu_h, var_h = model.predict_value(xq_np)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * M * e2e_steps / float(dt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused DMMA variance kernel)
+    kernel_ms = tot_ms.value / max(1, launches.value)
+    chunk = min(M, 32768)
+    flops_launch = flops_per_query(N_OBS, 'sym') * chunk
+    achieved = flops_launch / (kernel_ms / 1e3) / 1e12 if kernel_ms > 0 else None
+    a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
+    b = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
+    best = None
+    for i in range(6):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        torch.matmul(a, b)
+        s1.record()
+        torch.cuda.synchronize()
+        if i:
+            ms = s0.elapsed_time(s1)
+            best = ms if best is None else min(best, ms)
+    del a, b
+    dgemm_tflops = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
+    roofline = {
+        'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tflops, 'unit': 'TFLOP/s',
+        'frac': (achieved / dgemm_tflops) if achieved else None, 'traffic': None,
+        'kernel': 'predict_var_kernel (FP64 DMMA.8x8x4, symmetric-half form: executed flops only)',
+        'kernel_ms': kernel_ms, 'kernel_launches_timed': int(launches.value), 'kernel_share_of_step': tot_ms.value / ms_total,
+        'flops_per_launch': flops_launch,
+        'peak_source': 'FP64 DGEMM 8192^3 via torch.matmul (cuBLAS), best of 5, CUDA events, measured in this run; '
+                       'MEASURED_PEAKS.json has no FP64 figure (hbm_gbs=%s of measured)' % hbm,
+    }
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': 'gp_predict N=4096 obs x M=2^20 queries per GPU (BASELINE config 3 at N=4k), FP64, 10x10 '
+                               'world RBF l=1 var=100 noise=0.5', 'n_obs': N_OBS, 'queries_per_gpu': M,
+                   'variance_form': 'W^-1 symmetric-half (IPP_VAR_WINV_SYM)',
+                   'l2': 'no flush: per step the kernels stream the 134 MB W^-1 and a 1.07 GB cross-covariance '
+                         'scratch, both larger than the 126 MB L2',
+                   'parallelism': 'queries sharded, belief replicated (dp%d)' % world},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(M * 2 * 8), 'd2h_bytes_per_step': int(M * 2 * 8)},
+        'gpu_launches': int(kernels_per_step * args.steps),
+        'clocks': clocks,
+        'roofline': roofline,
+    }
+
+    if not args.no_extras and world == 1:
+        # CPU baseline on a bounded sample (about 10-30 s of host work), rank 0 only
+        sample = 16384
+        cpu_predict_rate(X, z, 2048)
+        rate, dt_cpu, t_factor = cpu_predict_rate(X, z, sample, repeats=2)
+        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+                                'sample': '%d of the 2^20 queries, best of 2 (%.2f s); numpy/BLAS port of '
+                                          'gpmodel_library.py:303-328; factor+inverse at N=4096 took %.2f s'
+                                          % (sample, dt_cpu, t_factor),
+                                'host_cpus': os.cpu_count()}
+        # second half of the metric: MCTS reward evals/s (one eval = one path's scalar reward), config 5 shape
+        P, k = 65536, 20
+        prng = np.random.default_rng(7)
+        start = prng.uniform(1, 9, (P, 1, 2))
+        head = prng.uniform(-np.pi, np.pi, (P, 1))
+        steps_ = (np.arange(1, k + 1) * 0.5)[None, :]
+        pts = np.concatenate([start[:, :, 0] + steps_ * np.cos(head), start[:, :, 1] + steps_ * np.sin(head)], axis=0)
+        pts = np.clip(np.stack([pts[:P], pts[P:]], axis=-1).reshape(P * k, 2), 0.0, 10.0)
+        xp = L.to_device(pts)
+        offs = torch.arange(0, P * k + 1, k, dtype=torch.int64, device='cuda')
+        sqb = [float(np.sqrt(aq.ucb_beta(10)))]
+        maxes = L.to_device(np.linspace(25, 40, 100))
+        extras = {}
+        for name, kind, kw in (('ucb', L.REWARD_UCB, dict(params=sqb)), ('mes_S100', L.REWARD_MES, dict(maxes_d=maxes))):
+            model.reward_paths_device(kind, xp, offs, **kw)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(2):
+                model.reward_paths_device(kind, xp, offs, **kw)
+            r1.record()
+            torch.cuda.synchronize()
+            extras['reward_evals_per_s_' + name] = P * 2 / (r0.elapsed_time(r1) / 1e3)
+        extras['reward_workload'] = '%d paths x %d points, N=4096 (BASELINE config 5 shape on 1 GPU)' % (P, k)
+        line['extra'] = extras
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,162 @@
+/*
+ * ipp_b200.h -- C ABI of the B200 (sm_100a) reward-evaluation library, libipp_b200.so.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json's north_star:
+ * GP posterior prediction + acquisition scoring over the sample points of candidate
+ * paths.  The reference (expeditionary-robotics/informative-path-planning) is pure
+ * Python, so its "FFI" for this path is the set of numpy call sites listed beside
+ * each entry point below; the reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float64 / int32 / int64 data unless it is
+ *     marked "host";  matrices are row-major with an explicit leading dimension in
+ *     elements; leading dimensions and base addresses of matrices must be 16-byte
+ *     aligned (ld even);
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and
+ *     allocates nothing (callers own all workspace; sizes come from ipp_*_workspace);
+ *   - return value 0 = ok, otherwise an IPP_E_* code; ipp_last_error() gives the text
+ *     (thread-local).  No torch or C++ types cross this boundary.
+ */
+#ifndef IPP_B200_H
+#define IPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPP_OK            0
+#define IPP_E_INVALID     1   /* bad argument (shape, alignment, unsupported dimension) */
+#define IPP_E_CUDA        2   /* CUDA runtime error; text in ipp_last_error()           */
+#define IPP_E_NOTPD       3   /* reserved: factorisation status is reported through `info` on the device */
+
+#define IPP_MAX_DIM       3   /* RBF input dimension: 2 (isotropic) or 3 (space-time ARD) */
+
+/* kernel hyper-parameters: GPy.kern.RBF(variance, lengthscale[, ARD]) as built at
+ * gpmodel_library.py:65.  inv_lengthscale[d] = 1/l_d (isotropic: the same value D times). */
+typedef struct ipp_rbf {
+    int32_t dim;
+    double  variance;
+    double  inv_lengthscale[IPP_MAX_DIM];
+} ipp_rbf;
+
+/* reward kinds for ipp_reward_paths */
+#define IPP_REWARD_UCB    0   /* aq_library.py:82-114  mean_UCB                         */
+#define IPP_REWARD_EI     1   /* aq_library.py:556-582 exp_improvement                  */
+#define IPP_REWARD_MES    2   /* aq_library.py:281-337 mves                             */
+
+/* variance formulations for ipp_gp_predict */
+#define IPP_VAR_WINV_SYM  0   /* var = v - k^T W^-1 k, W^-1 symmetric: lower tiles x2 + diagonal tiles (N^2 flops/query) */
+#define IPP_VAR_WINV_FULL 1   /* var = v - sum((W^-T Kx) * Kx): every tile, the reference's literal formula (2 N^2)     */
+#define IPP_VAR_CHOL      2   /* var = v - |L^-1 k|^2 with the matrix operand = L^-1 (GPy's form; lower tiles only)     */
+
+const char* ipp_last_error(void);
+int  ipp_version(void);
+/* number of SMs the library will size persistent grids for on the current device */
+int  ipp_sm_count(void);
+
+/* ---- a1: RBF cross-covariance.  Replaces GPy kern.K(X, X2) at gpmodel_library.py:213,234,239,251,313,318
+ *      and aq_library.py:49,58,59.   out[i*ldo + j] = variance * exp(-0.5 * sum_d ((X1[i,d]-X2[j,d])/l_d)^2) */
+int ipp_rbf_cross(const ipp_rbf* kern, const double* X1, int64_t n1, const double* X2, int64_t n2,
+                  double* out, int64_t ldo, void* stream);
+
+/* ---- a2: OnlineGPModel.init_model, gpmodel_library.py:208-228 (GPy pdinv: Cholesky, inverse, symmetrify).
+ *      Builds A = K(X,X) + diag_add*I, factors it, and writes
+ *        winv  [N][ldw]   (K + diag_add I)^-1, exactly symmetric
+ *        linv  [N][ldw]   L^-1 (lower triangular, zeros above) -- may be NULL when not wanted
+ *        alpha [N]        winv @ z
+ *        logdet[1]        2 sum log diag L
+ *        info  [1] int32  0 = ok, j>0 = leading minor j not positive definite (LinAlgError in GPy's jitchol)
+ *      work: ipp_gp_factor_workspace(N) doubles.  diag_add = noise + 1e-8 at the reference call site. */
+int64_t ipp_gp_factor_workspace(int64_t N);
+int ipp_gp_factor(const ipp_rbf* kern, const double* X, const double* z, int64_t N, double diag_add,
+                  double* winv, double* linv, int64_t ldw, double* alpha, double* logdet, int32_t* info,
+                  double* work, void* stream);
+
+/* pdinv of an arbitrary dense SPD matrix A[N][lda] (GPy.util.linalg.pdinv, used by sample_max_vals'
+ * N >= F branch aq_library.py:197-200): A is overwritten by its lower Cholesky factor (entries above the
+ * diagonal inside 128-blocks are scratch); outputs as in ipp_gp_factor.  work: ipp_pdinv_workspace(N). */
+int64_t ipp_pdinv_workspace(int64_t N);
+int ipp_pdinv(double* A, int64_t N, int64_t lda, double* winv, double* linv, int64_t ldw,
+              double* logdet, int32_t* info, double* work, void* stream);
+
+/* ---- a4: OnlineGPModel.update_model, gpmodel_library.py:230-279 (block-inverse append of k points).
+ *      Reads winv_old [N][ldw_old], writes winv_new [(N+k)][ldw_new] and alpha_new [N+k] = winv_new @ z_all.
+ *      X_all/z_all hold the N old rows followed by the k new ones.  k <= IPP_APPEND_MAX_K.
+ *      work: ipp_gp_append_workspace(N, k) doubles.  info as in ipp_gp_factor (Schur block not PD). */
+#define IPP_APPEND_MAX_K 32
+int64_t ipp_gp_append_workspace(int64_t N, int64_t k);
+int ipp_gp_append(const ipp_rbf* kern, const double* X_all, const double* z_all, int64_t N, int64_t k,
+                  double diag_add, const double* winv_old, int64_t ldw_old,
+                  double* winv_new, int64_t ldw_new, double* alpha_new, int32_t* info,
+                  double* work, void* stream);
+
+/* ---- a3 (+a5): predict_value, gpmodel_library.py:303-328 (and GPy's Cholesky form for GPModel :82-103).
+ *      mean[m] = sum_n K(X, q_m)[n] alpha[n];  var[m] = variance - quadratic form (+ noise_add).
+ *      `mat` is W^-1 (IPP_VAR_WINV_*) or L^-1 (IPP_VAR_CHOL), [N][ldm].
+ *      work: ipp_gp_predict_workspace(N, M) doubles (cross-covariance chunk + partial sums). */
+int64_t ipp_gp_predict_workspace(int64_t N, int64_t M);
+int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                   const double* mat, int64_t ldm, int var_mode, double noise_add,
+                   const double* Xq, int64_t M, double* mean, double* var,
+                   double* work, void* stream);
+
+/* CUDA-event timing of the dominant kernel of ipp_gp_predict (the fused DMMA variance kernel), recorded on
+ * the launching stream.  enable(1) starts a fresh record; read() synchronises on the recorded events and
+ * returns the summed device time and the number of launches since enable/read.  Measurement only. */
+int ipp_profile_enable(int on);
+int ipp_profile_read(double* total_ms /* host */, int64_t* launches /* host */);
+
+/* full posterior covariance for a small batch (predict_value(full_cov=True), gpmodel_library.py:317-320):
+ *      cov[M][ldc] = K(q,q) - Kx^T W^-1 Kx + noise_add (added to EVERY entry, as the reference does). */
+int64_t ipp_gp_predict_cov_workspace(int64_t N, int64_t M);
+int ipp_gp_predict_cov(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                       const double* winv, int64_t ldm, double noise_add,
+                       const double* Xq, int64_t M, double* mean, double* cov, int64_t ldc,
+                       double* work, void* stream);
+
+/* ---- a7/a8/a9: per-path rewards from (mean, var) of the path's sample points.
+ *      path p owns points [offsets[p], offsets[p+1]).  params (host array of doubles):
+ *        UCB: params[0] = sqrt(beta_t)                     -> sum mu + sqrt(beta) sum |var|
+ *        EI : params[0] = eta                              -> x Phi(z) + sum|var| phi(z), x = sum(mu - eta), z = x/sum|var|
+ *        MES: maxes[S] on the DEVICE                       -> 2/S sum_i sum_p u(gamma_ip), gamma = (y*_i - mu)/var  (Q2)
+ *      point_out (may be NULL): per-point FVECTOR form, [M]. */
+int ipp_reward_paths(int kind, const double* mean, const double* var, const int64_t* offsets, int64_t P,
+                     const double* params_host, int n_params, const double* maxes_dev, int64_t S,
+                     double* reward, double* point_out, int64_t M, void* stream);
+
+/* ---- a11: random-Fourier-feature function samples on a grid + per-sample arg-max
+ *      (general_target aq_library.py:138-139 and the grid stage of global_maximization :475-479).
+ *      f_s(x) = sum_f theta[s][f] * cos(W_s[f] . x + b_s[f]); theta is pre-scaled by sqrt(2 variance / F).
+ *      shared_w != 0: one (W[F][D], b[F]) for all S samples; else W[S][F][D], b[S][F].
+ *      values (may be NULL): [S][G] function values.  max_val[S], arg_max[S] (first index of the max, like np.argmax).
+ *      work: ipp_rff_workspace(S, G) doubles. */
+int64_t ipp_rff_workspace(int64_t S, int64_t G);
+int ipp_rff_eval_argmax(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
+                        int shared_w, const double* grid, int64_t G, double* values,
+                        double* max_val, int64_t* arg_max, double* work, void* stream);
+/* feature matrix Z[F][ldz] = scale * cos(W X^T + b) (aq_library.py:171) */
+int ipp_rff_features(const double* W, const double* b, int64_t F, int D, const double* X, int64_t N,
+                     double scale, double* Z, int64_t ldz, void* stream);
+
+/* ---- building blocks exposed for tests and for info_gain (aq_library.py:34-80, Schur form):
+ *      C[M][ldc] (and/or Ct[N][ldct]) = alpha * A[M][K] * B[N][K]^T + beta * C      (FP64 DMMA) */
+int ipp_dgemm_nt(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                 double* Ct, int64_t ldct, void* stream);
+/* in-place lower Cholesky of A[N][lda] (entries above the diagonal inside 128-blocks are scratch),
+ * logdet = 2 sum log diag; info as above */
+int64_t ipp_potrf_workspace(int64_t N);
+int ipp_potrf_lower(double* A, int64_t N, int64_t lda, double* logdet, int32_t* info, double* work, void* stream);
+/* per-path log det of the k_p x k_p Schur blocks S_p = I + v Kqq_p - v^2 C_p^T Binv C_p  (info_gain) */
+int64_t ipp_info_gain_workspace(int64_t N, int64_t M);
+int ipp_info_gain_paths(const ipp_rbf* kern_v2 /* RBF with variance = v^2 */, const double* X, int64_t N,
+                        const double* binv /* (I + v K)^-1 */, int64_t ldb,
+                        const double* Xq, const int64_t* offsets, int64_t P, int64_t M,
+                        double* logdet_out, int32_t* info, double* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPP_B200_H */

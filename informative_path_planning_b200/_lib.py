@@ -1,0 +1,146 @@
+"""ctypes binding of libipp_b200.so (include/ipp_b200.h) + the torch plumbing around it.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only; every
+numerical step goes through the C ABI.  There is NO CPU fallback: importing this module
+without the built library, or calling into it without a CUDA device, raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libipp_b200.so')
+
+IPP_MAX_DIM = 3
+IPP_APPEND_MAX_K = 32
+REWARD_UCB, REWARD_EI, REWARD_MES = 0, 1, 2
+VAR_WINV_SYM, VAR_WINV_FULL, VAR_CHOL = 0, 1, 2
+
+
+class IppRbf(ctypes.Structure):
+    _fields_ = [('dim', ctypes.c_int32), ('variance', ctypes.c_double),
+                ('inv_lengthscale', ctypes.c_double * IPP_MAX_DIM)]
+
+
+class IppError(RuntimeError):
+    pass
+
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_D = ctypes.c_double
+_INT = ctypes.c_int
+_RBF = ctypes.POINTER(IppRbf)
+
+# name -> (restype, argtypes); must list every symbol include/ipp_b200.h declares
+SIGNATURES = {
+    'ipp_last_error': (ctypes.c_char_p, []),
+    'ipp_version': (_INT, []),
+    'ipp_sm_count': (_INT, []),
+    'ipp_rbf_cross': (_INT, [_RBF, _P, _I64, _P, _I64, _P, _I64, _P]),
+    'ipp_gp_factor_workspace': (_I64, [_I64]),
+    'ipp_gp_factor': (_INT, [_RBF, _P, _P, _I64, _D, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    'ipp_pdinv_workspace': (_I64, [_I64]),
+    'ipp_pdinv': (_INT, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P]),
+    'ipp_gp_append_workspace': (_I64, [_I64, _I64]),
+    'ipp_gp_append': (_INT, [_RBF, _P, _P, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _P, _P, _P]),
+    'ipp_gp_predict_workspace': (_I64, [_I64, _I64]),
+    'ipp_gp_predict': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _INT, _D, _P, _I64, _P, _P, _P, _P]),
+    'ipp_profile_enable': (_INT, [_INT]),
+    'ipp_profile_read': (_INT, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+    'ipp_gp_predict_cov_workspace': (_I64, [_I64, _I64]),
+    'ipp_gp_predict_cov': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _D, _P, _I64, _P, _P, _I64, _P, _P]),
+    'ipp_reward_paths': (_INT, [_INT, _P, _P, _P, _I64, _P, _INT, _P, _I64, _P, _P, _I64, _P]),
+    'ipp_rff_workspace': (_I64, [_I64, _I64]),
+    'ipp_rff_eval_argmax': (_INT, [_P, _P, _P, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
+    'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
+    'ipp_dgemm_nt': (_INT, [_I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, _P, _I64, _P]),
+    'ipp_potrf_workspace': (_I64, [_I64]),
+    'ipp_potrf_lower': (_INT, [_P, _I64, _I64, _P, _P, _P, _P]),
+    'ipp_info_gain_workspace': (_I64, [_I64, _I64]),
+    'ipp_info_gain_paths': (_INT, [_RBF, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _P, _P, _P, _P]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "informative_path_planning_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise IppError('libipp_b200 error %d: %s' % (rc, lib.ipp_last_error().decode('utf-8', 'replace')))
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise IppError('informative_path_planning_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def make_rbf(dim, variance, lengthscale):
+    k = IppRbf()
+    k.dim = int(dim)
+    k.variance = float(np.asarray(variance, dtype=float).reshape(-1)[0])
+    ls = np.asarray(lengthscale, dtype=float).reshape(-1)
+    for d in range(IPP_MAX_DIM):
+        if d < dim:
+            k.inv_lengthscale[d] = 1.0 / float(ls[d] if ls.size > 1 else ls[0])
+        else:
+            k.inv_lengthscale[d] = 0.0
+    return k
+
+
+_workspaces = {}
+
+
+def workspace(n_doubles, slot='main'):
+    """Grow-only float64 scratch on the current device.  Calls are stream-ordered on the current
+    stream, so successive library calls may reuse it."""
+    dev = device()
+    key = (dev.index, slot)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < n_doubles:
+        buf = None
+        _workspaces.pop(key, None)
+        buf = torch.empty(int(n_doubles), dtype=torch.float64, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+def to_device(a):
+    """numpy (any float layout) -> contiguous float64 CUDA tensor (through pinned memory for big arrays)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device(), dtype=torch.float64).contiguous()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    t = torch.from_numpy(a)
+    if t.numel() >= (1 << 16):
+        t = t.pin_memory()
+    return t.to(device(), non_blocking=True)

@@ -1,0 +1,435 @@
+"""Drop-in reward / acquisition callables (reference aq_library.py), CUDA-backed.
+
+Same call signatures as the reference -- f(time, xvals, robot_model, param=None[, FVECTOR=False]),
+always usable with keyword arguments (mcts_library.py:387-396, robot_library.py:200-202) -- and the
+same return types (numpy scalar, or an (M, 1) array with FVECTOR=True).  `robot_model` must be one of
+this package's GPModel / OnlineGPModel objects: the posterior, the acquisition closed forms and the
+per-path reduction run in one device pass through libipp_b200.so; there is no CPU path.
+
+Batched forms used by the planners (one GPU call for a whole set of candidate paths):
+  reward_paths(f_rew, time, paths, robot_model, param)  -> np.ndarray [P]
+
+Quirks of the reference kept on purpose: UCB/EI scale by the variance (Q1), MES divides
+by the variance and double-adds the utility (Q2), info_gain multiplies K by the variance again and
+scales by 2*pi*e (Q6), RFF weights use std sqrt(1/lengthscale) (Q7).
+"""
+import ctypes
+from functools import partial
+
+import numpy as np
+import scipy.optimize
+import torch
+
+from . import _lib as L
+from .gpmodel_library import GPModel
+
+_TWO_PI_E = 2 * np.pi * np.e
+
+
+def _require_model(robot_model):
+    if not isinstance(robot_model, GPModel):
+        raise TypeError('robot_model must be an informative_path_planning_b200 GPModel/OnlineGPModel '
+                        '(got %r); there is no CPU fallback' % type(robot_model))
+
+
+def _queries(time, xvals, robot_model):
+    """The reference's query construction (e.g. aq_library.py:84-91): columns 0,1 (+ time when D=3)."""
+    data = np.array(xvals, dtype=float)
+    x1 = data[:, 0]
+    x2 = data[:, 1]
+    if robot_model.dimension == 2:
+        return data, np.vstack([x1, x2]).T
+    return data, np.vstack([x1, x2, time * np.ones(len(x1))]).T
+
+
+def ucb_beta(time):
+    delta = 0.9
+    d = 20
+    pit = np.pi ** 2 * (time + 1) ** 2 / 6.
+    return 2 * np.log(d * pit / delta)
+
+
+def _single_path_offsets(k, dev):
+    return torch.tensor([0, k], dtype=torch.int64, device=dev)
+
+
+# ------------------------------------------------------------------------------------------ rewards
+def mean_UCB(time, xvals, robot_model, param=None, FVECTOR=False):
+    """reference aq_library.py:82-114"""
+    _require_model(robot_model)
+    data, queries = _queries(time, xvals, robot_model)
+    if robot_model.xvals is None:
+        return np.ones((data.shape[0], 1)) if FVECTOR else 1.0
+    xq = L.to_device(queries)
+    reward, points = robot_model.reward_paths_device(L.REWARD_UCB, xq, _single_path_offsets(xq.shape[0], xq.device),
+                                                     params=[np.sqrt(ucb_beta(time))], want_points=FVECTOR)
+    if FVECTOR:
+        return points.cpu().numpy().reshape(-1, 1)
+    return np.float64(reward.cpu().numpy()[0])
+
+
+def exp_improvement(time, xvals, robot_model, param=None):
+    """reference aq_library.py:556-582"""
+    _require_model(robot_model)
+    _, queries = _queries(time, xvals, robot_model)
+    eta = 0.5 if param is None else sum(param) / len(param)
+    xq = L.to_device(queries)
+    reward, _ = robot_model.reward_paths_device(L.REWARD_EI, xq, _single_path_offsets(xq.shape[0], xq.device),
+                                                params=[float(eta)])
+    return np.float64(reward.cpu().numpy()[0])
+
+
+def mves(time, xvals, robot_model, param, FVECTOR=False):
+    """reference aq_library.py:281-337"""
+    _require_model(robot_model)
+    maxes = param[0]
+    if maxes is None:
+        return np.ones((xvals.shape[0], 1)) if FVECTOR else 1.0
+    _, queries = _queries(time, xvals, robot_model)
+    xq = L.to_device(queries)
+    maxes_d = L.to_device(np.asarray(maxes, dtype=float).reshape(-1))
+    reward, points = robot_model.reward_paths_device(L.REWARD_MES, xq, _single_path_offsets(xq.shape[0], xq.device),
+                                                     maxes_d=maxes_d, want_points=True)
+    if FVECTOR:
+        # f_m = (sum_i u_mi + sum_i sum_m' u_m'i) / S  (the reference's "f += utility; f += sum(utility)")
+        pts = points.cpu().numpy().reshape(-1, 1)
+        return (pts + np.sum(pts)) / maxes_d.numel()
+    return np.float64(reward.cpu().numpy()[0])
+
+
+def _logdet_small_device(robot_model, queries, scale_variance):
+    """logdet(I + K2(q, q)) for the no-data branch of info_gain, on the device (k x k Cholesky)."""
+    v = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+    kern2 = L.make_rbf(robot_model.dimension, v * scale_variance, robot_model.lengthscale)
+    xq = L.to_device(queries)
+    k = xq.shape[0]
+    ld = L.round_up(k, 2)
+    A = torch.empty((k, ld), dtype=torch.float64, device=xq.device)
+    L.check(L.lib.ipp_rbf_cross(ctypes.byref(kern2), L.ptr(xq), k, L.ptr(xq), k, L.ptr(A), ld, L.stream_ptr()))
+    A[:, :k] += torch.eye(k, dtype=torch.float64, device=xq.device)
+    scal = torch.zeros(2, dtype=torch.float64, device=xq.device)
+    info = torch.zeros(1, dtype=torch.int32, device=xq.device)
+    work = L.workspace(L.lib.ipp_potrf_workspace(k), slot='potrf')
+    L.check(L.lib.ipp_potrf_lower(L.ptr(A), k, ld, L.ptr(scal), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('I + v K(q) is not positive definite')
+    return float(scal[0].item())
+
+
+def info_gain_paths(robot_model, queries, offsets):
+    """2*pi*e * (logdet(I + v K([X; q_p])) - logdet(I + v K(X))) for every path p, as one device pass
+    (Schur-complement form of reference aq_library.py:55-70)."""
+    kern2, binv, ld, _ = robot_model._info_gain_state()
+    xq = L.to_device(queries)
+    M, N = xq.shape[0], robot_model.n_obs
+    offs = torch.as_tensor(np.asarray(offsets, dtype=np.int64)).to(xq.device)
+    P = offs.shape[0] - 1
+    out = torch.empty(P, dtype=torch.float64, device=xq.device)
+    info = torch.zeros(1, dtype=torch.int32, device=xq.device)
+    work = L.workspace(L.lib.ipp_info_gain_workspace(N, M))
+    L.check(L.lib.ipp_info_gain_paths(ctypes.byref(kern2), L.ptr(robot_model._X_d), N, L.ptr(binv), ld, L.ptr(xq),
+                                      L.ptr(offs), P, M, L.ptr(out), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('info_gain: Schur block not positive definite (or path longer than 32 points)')
+    return _TWO_PI_E * out.cpu().numpy()
+
+
+def info_gain(time, xvals, robot_model, param=None):
+    """reference aq_library.py:34-80"""
+    _require_model(robot_model)
+    _, queries = _queries(time, xvals, robot_model)
+    if robot_model.xvals is None:
+        v = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+        return np.float64(0.5 * _logdet_small_device(robot_model, queries, v))
+    return np.float64(info_gain_paths(robot_model, queries, [0, queries.shape[0]])[0])
+
+
+def hotspot_info_UCB(time, xvals, robot_model, param=None):
+    """reference aq_library.py:117-135 (LAMBDA = 1)"""
+    return info_gain(time, xvals, robot_model) + mean_UCB(time, xvals, robot_model)
+
+
+def naive(time, xvals, robot_model, param, FVECTOR=False):
+    """reference aq_library.py:339-367 (pure geometry on a handful of points: host numpy, as in the reference)"""
+    _, max_locs, _ = param[0]
+    if max_locs is None:
+        return np.zeros((xvals.shape[0], 1)) if FVECTOR else 0.0
+    data = np.array(xvals, dtype=float)
+    f = np.zeros((data.shape[0], 1))
+    for i in range(max_locs.shape[0]):
+        dist = np.sqrt(np.square(data[:, 0] - max_locs[i][0]) + np.square(data[:, 1] - max_locs[i][1]))
+        f += (dist <= param[1]).astype(float).reshape(f.shape)
+    f = f / max_locs.shape[0]
+    return f if FVECTOR else np.sum(f)
+
+
+def naive_value(time, xvals, robot_model, param, FVECTOR=False):
+    """reference aq_library.py:369-413"""
+    max_vals, _, funcs = param[0]
+    if max_vals is None or funcs is None:
+        return np.zeros((xvals.shape[0], 1)) if FVECTOR else 0.0
+    data, queries = _queries(time, xvals, robot_model)
+    f = np.zeros((data.shape[0], 1))
+    for i in range(max_vals.shape[0]):
+        mean = funcs[i](queries)
+        f += (np.fabs(mean - max_vals[i][0]) <= param[1]).astype(float).reshape(f.shape)
+    f = f / float(max_vals.shape[0])
+    return f if FVECTOR else np.sum(f)
+
+
+# ------------------------------------------------------------------------------------------ batched rewards
+def flatten_paths(paths, dimension=2, time=0):
+    """paths: sequence of per-path point lists/arrays (k_p, >=2) -> (queries (M, D), offsets (P+1,) int64)."""
+    arrs = [np.asarray(p, dtype=float)[:, :2] for p in paths]
+    offsets = np.zeros(len(arrs) + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum([a.shape[0] for a in arrs])
+    q = np.vstack(arrs) if arrs else np.zeros((0, 2))
+    if dimension == 3:
+        q = np.hstack([q, time * np.ones((q.shape[0], 1))])
+    return q, offsets
+
+
+def reward_paths(f_rew, time, paths, robot_model, param=None, offsets=None):
+    """All candidate paths in ONE device call.  f_rew in {'mean', 'exp_improve', 'mes', 'info_gain',
+    'hotspot_info'}; `param` as the reference passes it to the matching callable.  `paths` is either a
+    sequence of point lists, or an (M, D) array together with `offsets`.  Returns float64 [P]; equals
+    [f(time, p, robot_model, param) for p in paths]."""
+    _require_model(robot_model)
+    if offsets is None:
+        queries, offsets = flatten_paths(paths, robot_model.dimension, time)
+    else:
+        queries = np.asarray(paths, dtype=float)
+        offsets = np.asarray(offsets, dtype=np.int64)
+    P = offsets.shape[0] - 1
+    if robot_model.xvals is None:
+        if f_rew in ('mean',):
+            return np.ones(P)
+        if f_rew in ('info_gain', 'hotspot_info', 'exp_improve'):
+            fn = {'info_gain': info_gain, 'exp_improve': exp_improvement}.get(f_rew)
+            if fn is None:
+                raise ValueError('hotspot_info needs observations (the reference fails here too)')
+            return np.array([fn(time, queries[offsets[p]:offsets[p + 1]], robot_model, param) for p in range(P)])
+    if f_rew == 'mes' and param[0] is None:
+        return np.ones(P)
+    if f_rew in ('info_gain', 'hotspot_info'):
+        ig = info_gain_paths(robot_model, queries, offsets)
+        if f_rew == 'info_gain':
+            return ig
+    xq = L.to_device(queries)
+    offs = torch.as_tensor(offsets).to(xq.device)
+    if f_rew in ('mean', 'hotspot_info'):
+        r, _ = robot_model.reward_paths_device(L.REWARD_UCB, xq, offs, params=[np.sqrt(ucb_beta(time))])
+        r = r.cpu().numpy()
+        return r + ig if f_rew == 'hotspot_info' else r
+    if f_rew == 'exp_improve':
+        eta = 0.5 if param is None else sum(param) / len(param)
+        r, _ = robot_model.reward_paths_device(L.REWARD_EI, xq, offs, params=[float(eta)])
+        return r.cpu().numpy()
+    if f_rew == 'mes':
+        maxes_d = L.to_device(np.asarray(param[0], dtype=float).reshape(-1))
+        r, _ = robot_model.reward_paths_device(L.REWARD_MES, xq, offs, maxes_d=maxes_d)
+        return r.cpu().numpy()
+    raise ValueError('unknown reward %r' % (f_rew,))
+
+
+# ------------------------------------------------------------------------------------------ max-value sampling
+class RFFTarget(object):
+    """One posterior function sample f(x) = theta^T sqrt(2 v / F) cos(W x^T + b) (reference general_target,
+    aq_library.py:138-139).  Calling it evaluates the sample on the device; `scalar`/`gradient` are the
+    closed forms SLSQP (host, as in the reference :527) needs for one point."""
+
+    def __init__(self, variance, nFeatures, W, theta, b):
+        self.variance, self.nFeatures = float(variance), int(nFeatures)
+        self.W, self.theta, self.b = W, theta, b
+        self.scale = np.sqrt(2.0 * self.variance / self.nFeatures)
+        self._dev = None
+
+    def _device_params(self):
+        if self._dev is None:
+            self._dev = (L.to_device(self.W), L.to_device(self.b.reshape(-1)),
+                         L.to_device((self.theta.reshape(-1) * self.scale)))
+        return self._dev
+
+    def eval_device(self, x_d, want_values=True):
+        """x_d: (G, D) CUDA tensor.  Returns (values[G] or None, max value, argmax index)."""
+        W_d, b_d, th_d = self._device_params()
+        G, D = x_d.shape
+        vals = torch.empty(G, dtype=torch.float64, device=x_d.device) if want_values else None
+        mx = torch.empty(1, dtype=torch.float64, device=x_d.device)
+        am = torch.empty(1, dtype=torch.int64, device=x_d.device)
+        work = L.workspace(L.lib.ipp_rff_workspace(1, G), slot='rff')
+        L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), self.nFeatures, 1, D, 0, L.ptr(x_d), G,
+                                          L.ptr(vals), L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
+        return vals, mx, am
+
+    def __call__(self, x):
+        x = np.asarray(x, dtype=float)
+        vals, _, _ = self.eval_device(L.to_device(x))
+        return vals.cpu().numpy().reshape(-1, 1)
+
+    # closed forms for the host optimiser (one point at a time)
+    def scalar(self, x):
+        d = self.W.shape[1]
+        return np.dot(self.theta.T * self.scale, np.cos(np.dot(self.W, x.reshape(1, d).T) + self.b)).T
+
+    def gradient(self, x):
+        d = self.W.shape[1]
+        return np.dot(self.theta.T * -self.scale, np.sin(np.dot(self.W, x.reshape((d, 1))) + self.b) * self.W)
+
+
+def general_target(x, robot_model, nFeatures, W, theta, b):
+    """reference aq_library.py:138-139 (device evaluation)."""
+    return RFFTarget(robot_model.variance, nFeatures, W, theta, b)(x)
+
+
+def _rff_theta(Z, zvals, noise_var, eps, nFeatures):
+    """Posterior weight draw (reference aq_library.py:177-206): small dense LAPACK on the host, as in the
+    reference (eig / inv / cholesky of an N x N or F x F matrix)."""
+    N = Z.shape[1]
+    if N < nFeatures:
+        Sigma = np.dot(Z.T, Z) + noise_var * np.eye(N)
+        mu = np.dot(np.dot(Z, np.linalg.inv(Sigma)), zvals)
+        D, U = np.linalg.eig(Sigma)
+        U = np.real(U)
+        D = np.real(np.reshape(D, (D.shape[0], 1)))
+        R = np.reciprocal(np.sqrt(D) * (np.sqrt(D) + np.sqrt(noise_var)))
+        return eps - np.dot(Z, np.dot(U, R * (np.dot(U.T, np.dot(Z.T, eps))))) + mu
+    Sigma = np.dot(Z, Z.T) / noise_var + np.eye(nFeatures)
+    Sigma = np.linalg.inv(Sigma)
+    mu = np.dot(np.dot(Sigma, Z), zvals) / noise_var
+    return mu + np.dot(np.linalg.cholesky(Sigma), eps)
+
+
+def rff_features(W, b, X_d, variance, nFeatures):
+    """Z = sqrt(2 v / F) cos(W X^T + b) on the device (reference aq_library.py:171) -> numpy (F, N)."""
+    F, D = W.shape
+    N = X_d.shape[0]
+    ldz = L.round_up(N, 2)
+    Z = torch.empty((F, ldz), dtype=torch.float64, device=X_d.device)
+    L.check(L.lib.ipp_rff_features(L.ptr(L.to_device(W)), L.ptr(L.to_device(b.reshape(-1))), F, D, L.ptr(X_d), N,
+                                   float(np.sqrt(2 * variance / nFeatures)), L.ptr(Z), ldz, L.stream_ptr()))
+    return Z[:, :N].cpu().numpy()
+
+
+def global_maximization(target, target_vector_n, target_grad, target_vector_gradient_n, ranges, guesses, visualize,
+                        filename, obstacles, f_rew, time=None):
+    """reference aq_library.py:444-553 without the plotting; the grid stage (:475-485) runs on the device
+    when `target` is an RFFTarget."""
+    gridSize = 300
+    bb = ((ranges[1] - ranges[0]) * 0.10, (ranges[3] - ranges[2]) * 0.10)
+    ranges = (ranges[0] + bb[0], ranges[1] - bb[0], ranges[2] + bb[1], ranges[3] - bb[1])
+    dim = guesses.shape[1]
+    x1 = np.random.uniform(ranges[0], ranges[1], size=gridSize)
+    x2 = np.random.uniform(ranges[2], ranges[3], size=gridSize)
+    x1, x2 = np.meshgrid(x1, x2, sparse=False, indexing='xy')
+    if dim == 2:
+        Xgrid_sample = np.vstack([x1.ravel(), x2.ravel()]).T
+        Xgrid = np.vstack([Xgrid_sample, guesses])
+    else:
+        Xgrid_sample = np.vstack([x1.ravel(), x2.ravel(), time * np.ones(len(x1.ravel()))]).T
+        Xgrid = Xgrid_sample
+    if isinstance(target, RFFTarget):
+        grid_d = L.to_device(Xgrid)
+        vals, _, am = target.eval_device(grid_d, want_values=True)
+        start = np.asarray(Xgrid[int(am.item()), :])
+        if start[0] < ranges[0] or start[0] > ranges[1] or start[1] < ranges[2] or start[1] > ranges[3]:
+            start = np.asarray(Xgrid_sample[int(torch.argmax(vals[:Xgrid_sample.shape[0]]).item()), :])
+    else:
+        y = target(Xgrid)
+        start = np.asarray(Xgrid[np.argmax(y), :])
+        if start[0] < ranges[0] or start[0] > ranges[1] or start[1] < ranges[2] or start[1] > ranges[3]:
+            start = np.asarray(Xgrid_sample[np.argmax(target(Xgrid_sample)), :])
+    if dim == 2:
+        bounds = ((ranges[0], ranges[1]), (ranges[2], ranges[3]))
+    else:
+        bounds = ((ranges[0], ranges[1]), (ranges[2], ranges[3]), (time, time))
+    res = scipy.optimize.minimize(fun=target_vector_n, x0=start, method='SLSQP', jac=target_vector_gradient_n,
+                                  bounds=bounds)
+    if not res['success']:
+        return 0, 0, 0, False
+    return res['x'], -res['fun'], res['jac'], True
+
+
+def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstacles=None, f_rew='mes'):
+    """reference aq_library.py:141-279.  Random draws come from the global np.random in the reference's
+    order (W, b, eps, then the grid draws of each optimisation attempt)."""
+    _require_model(robot_model)
+    if robot_model.xvals is None:
+        return None, None, None
+    d = robot_model.xvals.shape[1]
+    samples = np.zeros((nK, 1))
+    locs = np.zeros((nK, d))
+    funcs = []
+    delete_locs = []
+    variance = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+    for i in range(nK):
+        ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
+        W = np.random.normal(loc=0.0, scale=np.sqrt(1. / ls), size=(nFeatures, d))
+        b = 2 * np.pi * np.random.uniform(low=0.0, high=1.0, size=(nFeatures, 1))
+        Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
+        eps = np.random.normal(loc=0.0, scale=1.0, size=(nFeatures, 1))
+        try:
+            theta = _rff_theta(Z, robot_model.zvals, robot_model.noise, eps, nFeatures)
+        except Exception:
+            delete_locs.append(i)
+            continue
+        target = RFFTarget(variance, nFeatures, W, theta, b)
+        target_vector_n = lambda x, tg=target: -tg.scalar(x)
+        target_vector_gradient_n = lambda x, tg=target: -np.asarray(tg.gradient(x).reshape(d, ))
+        status = False
+        count = 0
+        while status is False and count < 5:
+            maxima, max_val, _, status = global_maximization(target, target_vector_n, target.gradient,
+                                                             target_vector_gradient_n, robot_model.ranges,
+                                                             robot_model.xvals, visualize, 't%s.nK%s' % (t, i),
+                                                             obstacles, f_rew=f_rew, time=t)
+            count += 1
+        if status is False:
+            delete_locs.append(i)
+            continue
+        samples[i] = np.array(max_val).reshape((1, 1))
+        funcs.append(target)
+        locs[i, :] = maxima.reshape((1, d))
+    samples = np.delete(samples, delete_locs, axis=0)
+    locs = np.delete(locs, delete_locs, axis=0)
+    if len(delete_locs) == nK:
+        samples[0] = np.max(robot_model.zvals) + 5.0 * np.sqrt(robot_model.noise)
+        locs[0, :] = robot_model.xvals[np.argmax(robot_model.zvals)]
+    return samples, locs, funcs
+
+
+def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
+    """Batched max-value sampling with ONE feature set shared by all nK posterior samples:
+    phi(grid) is evaluated once per grid point and contracted against all nK weight vectors in the same
+    kernel, followed by the per-sample arg-max.  Statistically the reference's sampler with a different
+    RNG stream; used for BASELINE config 4 (F=1000, S=100, 1M-point grid).
+    Returns (max_vals (nK,1), max_locs (nK,D), (W, b, Theta))."""
+    _require_model(robot_model)
+    rng = np.random.default_rng() if rng is None else rng
+    d = robot_model.xvals.shape[1]
+    variance = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+    ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
+    W = rng.normal(0.0, np.sqrt(1. / ls), size=(nFeatures, d))
+    b = 2 * np.pi * rng.uniform(0.0, 1.0, size=(nFeatures, 1))
+    Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
+    Theta = np.hstack([_rff_theta(Z, robot_model.zvals, robot_model.noise, rng.normal(size=(nFeatures, 1)), nFeatures)
+                       for _ in range(nK)])                              # (F, nK)
+    grid_d = grid if isinstance(grid, torch.Tensor) else L.to_device(grid)
+    mx, am = rff_eval_argmax_shared(W, b, Theta, variance, grid_d)
+    locs = grid_d[am].cpu().numpy()
+    return mx.cpu().numpy().reshape(-1, 1), locs, (W, b, Theta)
+
+
+def rff_eval_argmax_shared(W, b, Theta, variance, grid_d):
+    """max_g / argmax_g of f_s(x_g) for all samples s with shared features; device tensors out."""
+    F, D = W.shape
+    S = Theta.shape[1]
+    G = grid_d.shape[0]
+    scale = np.sqrt(2.0 * variance / F)
+    th_d = L.to_device(np.ascontiguousarray(Theta.T) * scale)            # [S][F]
+    mx = torch.empty(S, dtype=torch.float64, device=grid_d.device)
+    am = torch.empty(S, dtype=torch.int64, device=grid_d.device)
+    work = L.workspace(L.lib.ipp_rff_workspace(S, G), slot='rff')
+    L.check(L.lib.ipp_rff_eval_argmax(L.ptr(L.to_device(W)), L.ptr(L.to_device(b.reshape(-1))), L.ptr(th_d), F, S, D, 1,
+                                      L.ptr(grid_d), G, None, L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
+    return mx, am

@@ -1,0 +1,269 @@
+// a4: OnlineGPModel.update_model (gpmodel_library.py:230-279) -- block-inverse append of k <= 32 points.
+//
+//   Q = K(X_old, X_new) (N x k),  S = K(X_new, X_new)
+//   V  = P Q         (N x k)      Vt[j][a] = sum_i P[i][j] Q[i][a]   (= (R P)^T; equals V when P is symmetric)
+//   M  = pdinv(S - Vt^T Q + diag_add I)                               (:252-255)
+//   Pnew = P + (V M) Vt^T,  Qnew = -(V M),  Rnew = -M Vt^T,  Snew = M (:257-265)
+//   alpha = Wnew z                                                    (:273, full recompute like the reference)
+//
+// The reference evaluates Pnew as ((((P Q) M) R) P), an O(N^3) product; here the same four factors are
+// associated as (P Q M)(R P), O(N^2 k).  Every pass over the N x N inverse is a coalesced HBM stream
+// (read P twice for V / Vt, read P + write Pnew once, read Wnew once for alpha).
+#include "internal.cuh"
+
+namespace ipp {
+
+constexpr int KMAX = IPP_APPEND_MAX_K;
+
+// V[i][a] = sum_j P[i][j] Q[j][a]: one warp per row i
+__global__ void __launch_bounds__(256) append_pq_kernel(const double* __restrict__ P, int64_t ldp, int64_t N, int k,
+                                                        const double* __restrict__ Q, double* __restrict__ V) {
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= N) return;
+    double acc[KMAX];
+#pragma unroll
+    for (int a = 0; a < KMAX; ++a) acc[a] = 0.0;
+    const double* p = P + i * ldp;
+    for (int64_t j = lane; j < N; j += 32) {
+        const double pv = p[j];
+        const double* q = Q + j * KMAX;
+#pragma unroll
+        for (int a = 0; a < KMAX; ++a)
+            if (a < k) acc[a] = fma(pv, q[a], acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < KMAX; ++a) {
+        if (a < k) {
+            double s = acc[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) V[i * KMAX + a] = s;
+        }
+    }
+}
+
+// Vt[j][a] = sum_i P[i][j] Q[i][a]: block = 32 columns x 8 row phases, coalesced 256-byte row reads
+__global__ void __launch_bounds__(256) append_ptq_kernel(const double* __restrict__ P, int64_t ldp, int64_t N, int k,
+                                                         const double* __restrict__ Q, double* __restrict__ Vt) {
+    __shared__ double red[8][32][9];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+    double acc[KMAX];
+#pragma unroll
+    for (int a = 0; a < KMAX; ++a) acc[a] = 0.0;
+    if (j < N) {
+        for (int64_t i = ty; i < N; i += 8) {
+            const double pv = P[i * ldp + j];
+            const double* q = Q + i * KMAX;
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a)
+                if (a < k) acc[a] = fma(pv, q[a], acc[a]);
+        }
+    }
+    // reduce the 8 row phases, 8 columns of Vt at a time (keeps static shared memory under 48 KB)
+#pragma unroll
+    for (int ch = 0; ch < KMAX / 8; ++ch) {
+        if (ch * 8 < k) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) red[ty][tx][a] = acc[ch * 8 + a];
+            __syncthreads();
+            {
+                const int c = threadIdx.x >> 3, a = threadIdx.x & 7;      // 32 columns x 8 entries
+                const int64_t jj = (int64_t)blockIdx.x * 32 + c;
+                if (jj < N && ch * 8 + a < k) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int y = 0; y < 8; ++y) sum += red[y][c][a];
+                    Vt[jj * KMAX + ch * 8 + a] = sum;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// G[a][b] = sum_j Vt[j][a] Q[j][b]: one warp per (a, b)
+__global__ void __launch_bounds__(256) append_gram_kernel(const double* __restrict__ Vt, const double* __restrict__ Q,
+                                                          int64_t N, int k, double* __restrict__ G) {
+    const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= k * k) return;
+    const int a = pair / k, b = pair % k;
+    double s = 0.0;
+    for (int64_t j = lane; j < N; j += 32) s = fma(Vt[j * KMAX + a], Q[j * KMAX + b], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) G[a * KMAX + b] = s;
+}
+
+// M = pdinv(S - G + diag_add I) for a k x k block, with GPy's jitchol retries
+// (linalg.py: up to 5 retries with jitter mean(diag) * 1e-6 * 10^i).  One warp; lane = row.
+__global__ void __launch_bounds__(32) append_schur_inverse_kernel(const double* __restrict__ S, const double* __restrict__ G,
+                                                                  int k, double diag_add, double* __restrict__ Mout,
+                                                                  int32_t* info) {
+    __shared__ double a0[KMAX][KMAX + 1], a[KMAX][KMAX + 1], li[KMAX][KMAX + 1];
+    __shared__ int bad;
+    const int r = threadIdx.x;
+    for (int c = 0; c < k; ++c)
+        if (r < k) a0[r][c] = S[r * KMAX + c] - G[r * KMAX + c] + (r == c ? diag_add : 0.0);
+    __syncwarp();
+    double mean_diag = 0.0;
+    for (int c = 0; c < k; ++c) mean_diag += a0[c][c];
+    mean_diag /= k;
+    double jitter = 0.0;
+    int tries = 0;
+    for (;;) {
+        for (int c = 0; c < k; ++c)
+            if (r < k) a[r][c] = a0[r][c] + (r == c ? jitter : 0.0);
+        if (r == 0) bad = 0;
+        __syncwarp();
+        for (int j = 0; j < k; ++j) {
+            if (r == 0) {
+                double d = a[j][j];
+                if (!(d > 0.0)) { if (!bad) bad = j + 1; d = 1.0; }
+                a[j][j] = sqrt(d);
+            }
+            __syncwarp();
+            if (r > j && r < k) a[r][j] /= a[j][j];
+            __syncwarp();
+            if (r > j && r < k)
+                for (int c = j + 1; c <= r; ++c) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
+            __syncwarp();
+        }
+        if (!bad) break;
+        if (tries >= 5 || !(mean_diag > 0.0)) break;
+        jitter = (tries == 0) ? mean_diag * 1e-6 : jitter * 10.0;
+        ++tries;
+        __syncwarp();
+    }
+    if (bad) {
+        if (r == 0 && info && *info == 0) *info = bad;
+        // still emit something finite-shaped so downstream kernels do not fault
+    }
+    // Linv by forward substitution (lane = column), then Ai = Linv^T Linv, lower triangle mirrored
+    if (r < k) {
+        const int c = r;
+        for (int i = 0; i < c; ++i) li[i][c] = 0.0;
+        li[c][c] = 1.0 / a[c][c];
+        for (int i = c + 1; i < k; ++i) {
+            double s = 0.0;
+            for (int q = c; q < i; ++q) s = fma(a[i][q], li[q][c], s);
+            li[i][c] = -s / a[i][i];
+        }
+    }
+    __syncwarp();
+    if (r < k) {
+        for (int c = 0; c <= r; ++c) {
+            double s = 0.0;
+            for (int q = r; q < k; ++q) s = fma(li[q][r], li[q][c], s);
+            Mout[r * KMAX + c] = s;
+            Mout[c * KMAX + r] = s;
+        }
+    }
+}
+
+// VM[i][b] = sum_a V[i][a] M[a][b];  MVt[j][a] = sum_b M[a][b] Vt[j][b]
+__global__ void __launch_bounds__(256) append_apply_m_kernel(const double* __restrict__ V, const double* __restrict__ Vt,
+                                                             const double* __restrict__ Mm, int64_t N, int k,
+                                                             double* __restrict__ VM, double* __restrict__ MVt) {
+    __shared__ double m[KMAX][KMAX + 1];
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) m[idx / k][idx % k] = Mm[(idx / k) * KMAX + idx % k];
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * k) return;
+    const int64_t i = idx / k;
+    const int b = (int)(idx % k);
+    double s = 0.0, u = 0.0;
+    for (int a = 0; a < k; ++a) {
+        s = fma(V[i * KMAX + a], m[a][b], s);
+        u = fma(m[b][a], Vt[i * KMAX + a], u);
+    }
+    VM[i * KMAX + b] = s;
+    MVt[i * KMAX + b] = u;
+}
+
+// Wnew: 64 x 64 output tile per block; rank-k term from shared-memory panels
+__global__ void __launch_bounds__(256) append_update_kernel(const double* __restrict__ P, int64_t ldp, int64_t N, int k,
+                                                            const double* __restrict__ VM, const double* __restrict__ Vt,
+                                                            const double* __restrict__ MVt, const double* __restrict__ Mm,
+                                                            double* __restrict__ Wn, int64_t ldn) {
+    __shared__ double svm[64][KMAX + 1], svt[64][KMAX + 1];
+    const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
+    const int64_t NT = N + k;
+    for (int idx = threadIdx.x; idx < 64 * k; idx += blockDim.x) {
+        const int r = idx / k, a = idx % k;
+        svm[r][a] = (i0 + r < N) ? VM[(i0 + r) * KMAX + a] : 0.0;
+        svt[r][a] = (j0 + r < N) ? Vt[(j0 + r) * KMAX + a] : 0.0;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 columns x 4 row phases
+    const int64_t j = j0 + tx;
+    if (j >= NT) return;
+    for (int r = ty; r < 64; r += 4) {
+        const int64_t i = i0 + r;
+        if (i >= NT) break;
+        double v;
+        if (i < N && j < N) {
+            double s = 0.0;
+            for (int a = 0; a < k; ++a) s = fma(svm[r][a], svt[tx][a], s);
+            v = P[i * ldp + j] + s;
+        } else if (i < N) {
+            v = -VM[i * KMAX + (j - N)];                       // Qnew = -(P Q) M
+        } else if (j < N) {
+            v = -MVt[j * KMAX + (i - N)];                      // Rnew = -M (R P)
+        } else {
+            v = Mm[(i - N) * KMAX + (j - N)];                  // Snew = M
+        }
+        Wn[i * ldn + j] = v;
+    }
+}
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" int64_t ipp_gp_append_workspace(int64_t N, int64_t k) {
+    (void)k;
+    return 5 * (N + KMAX) * KMAX + 3 * KMAX * KMAX + 64;
+}
+
+extern "C" int ipp_gp_append(const ipp_rbf* kern, const double* X_all, const double* z_all, int64_t N, int64_t k,
+                             double diag_add, const double* winv_old, int64_t ldw_old,
+                             double* winv_new, int64_t ldw_new, double* alpha_new, int32_t* info,
+                             double* work, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(kern && X_all && winv_old && winv_new && work && info, "null pointer");
+    IPP_CHECK_ARG(N >= 1 && k >= 1 && k <= KMAX, "need N >= 1 and 1 <= k <= IPP_APPEND_MAX_K");
+    IPP_CHECK_ARG(ldw_old >= N && ldw_new >= N + k, "leading dimensions too small");
+    IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
+    const int D = kern->dim;
+    const double* Xnew = X_all + N * D;
+    double* Q = work;                          // [N][KMAX]
+    double* V = Q + (N + KMAX) * KMAX;
+    double* Vt = V + (N + KMAX) * KMAX;
+    double* VM = Vt + (N + KMAX) * KMAX;
+    double* MVt = VM + (N + KMAX) * KMAX;
+    double* S = MVt + (N + KMAX) * KMAX;       // [KMAX][KMAX]
+    double* G = S + KMAX * KMAX;
+    double* Mm = G + KMAX * KMAX;
+    IPP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    IPP_TRY(launch_rbf_cross(*kern, X_all, N, Xnew, k, Q, KMAX, s));
+    IPP_TRY(launch_rbf_cross(*kern, Xnew, k, Xnew, k, S, KMAX, s));
+    append_pq_kernel<<<(unsigned)((N + 7) / 8), 256, 0, s>>>(winv_old, ldw_old, N, (int)k, Q, V);
+    IPP_LAUNCH_CHECK();
+    append_ptq_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(winv_old, ldw_old, N, (int)k, Q, Vt);
+    IPP_LAUNCH_CHECK();
+    append_gram_kernel<<<(unsigned)((k * k + 7) / 8), 256, 0, s>>>(Vt, Q, N, (int)k, G);
+    IPP_LAUNCH_CHECK();
+    append_schur_inverse_kernel<<<1, 32, 0, s>>>(S, G, (int)k, diag_add, Mm, info);
+    IPP_LAUNCH_CHECK();
+    append_apply_m_kernel<<<(unsigned)((N * k + 255) / 256), 256, 0, s>>>(V, Vt, Mm, N, (int)k, VM, MVt);
+    IPP_LAUNCH_CHECK();
+    const int64_t NT = N + k;
+    dim3 grid((unsigned)((NT + 63) / 64), (unsigned)((NT + 63) / 64));
+    append_update_kernel<<<grid, 256, 0, s>>>(winv_old, ldw_old, N, (int)k, VM, Vt, MVt, Mm, winv_new, ldw_new);
+    IPP_LAUNCH_CHECK();
+    if (alpha_new && z_all) IPP_TRY(launch_gemv(winv_new, ldw_new, NT, NT, z_all, alpha_new, s));
+    return IPP_OK;
+}

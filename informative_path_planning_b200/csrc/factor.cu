@@ -1,0 +1,224 @@
+// a2: dense FP64 refresh of the belief (GPy pdinv restated on the device):
+//   A = K(X,X) + diag_add I  ->  L = chol(A)  ->  L^-1  ->  W^-1 = L^-T L^-1 (exactly symmetric)  ->  alpha = W^-1 z
+//
+// Right-looking blocked Cholesky, block 64: a single-CTA kernel factors the 64x64 diagonal block in
+// shared memory and also emits its triangular inverse; the panel solve (L21 = A21 * Ldd^-T) and the
+// trailing update (A22 -= L21 L21^T, lower tiles) are DMMA GEMMs.  The triangular inverse is built by
+// recursive doubling with GEMMs only (L^-1 and its transpose U are kept side by side so that every
+// product is of the K-major "NT" form the DMMA kernel wants):
+//   Linv21 = -Linv22 * (L21 * Linv11)
+// and W^-1 = U U^T is a lower-tile GEMM whose contraction starts at max(m0, n0), mirrored on store.
+#include "internal.cuh"
+#include "dgemm_dmma.cuh"
+
+namespace ipp {
+
+constexpr int NB = 64;
+constexpr int DIAG_SMEM = 2 * NB * (NB + 1) * 8;
+
+// Cholesky of the jb x jb lower block at A (leading dimension lda) + its inverse into dinv[64][64].
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t lda, int jb,
+                                                         double* __restrict__ dinv, double* logdet,
+                                                         int32_t* info, int j0) {
+    extern __shared__ double sm[];
+    double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    double (*li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+        const int r = idx >> 6, c = idx & 63;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
+        a[r][c] = v;
+        li[r][c] = 0.0;
+    }
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    for (int j = 0; j < jb; ++j) {
+        if (tid == 0) {
+            double d = a[j][j];
+            if (!(d > 0.0)) {            // also catches NaN, like LAPACK's dpotrf
+                if (bad == 0) bad = j + 1;
+                d = 1.0;
+            }
+            a[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double djj = a[j][j];
+        if (tid > j && tid < jb) a[tid][j] /= djj;
+        __syncthreads();
+        const int w = jb - j - 1;
+        for (int idx = tid; idx < w * w; idx += blockDim.x) {
+            const int i = j + 1 + idx / w, k = j + 1 + idx % w;
+            if (k <= i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+        }
+        __syncthreads();
+    }
+    // triangular inverse: thread c solves L x = e_c by forward substitution
+    if (tid < jb) {
+        const int c = tid;
+        li[c][c] = 1.0 / a[c][c];
+        for (int i = c + 1; i < jb; ++i) {
+            double s = 0.0;
+            for (int k = c; k < i; ++k) s = fma(a[i][k], li[k][c], s);
+            li[i][c] = -s / a[i][i];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r < jb && c <= r) A[(int64_t)r * lda + c] = a[r][c];
+        dinv[idx] = (r < jb && c <= r) ? li[r][c] : 0.0;
+    }
+    if (tid == 0) {
+        double s = 0.0;
+        for (int j = 0; j < jb; ++j) s += log(a[j][j]);
+        if (logdet) *logdet += 2.0 * s;
+        if (bad && info && *info == 0) *info = j0 + bad;
+    }
+}
+
+__global__ void init_factor_scalars_kernel(double* logdet, int32_t* info) {
+    if (logdet) *logdet = 0.0;
+    if (info) *info = 0;
+}
+
+int potrf_lower(double* A, int64_t N, int64_t lda, double* dinv, double* logdet, int32_t* info, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        IPP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+        configured = true;
+    }
+    init_factor_scalars_kernel<<<1, 1, 0, s>>>(logdet, info);
+    IPP_LAUNCH_CHECK();
+    for (int64_t j0 = 0, blk = 0; j0 < N; j0 += NB, ++blk) {
+        const int jb = (int)((N - j0) < NB ? (N - j0) : NB);
+        double* Ajj = A + j0 * lda + j0;
+        double* D = dinv + blk * NB * NB;
+        potrf_diag_kernel<<<1, 256, DIAG_SMEM, s>>>(Ajj, lda, jb, D, logdet, info, (int)j0);
+        IPP_LAUNCH_CHECK();
+        const int64_t rows = N - j0 - jb;
+        if (rows <= 0) break;
+        double* A21 = A + (j0 + jb) * lda + j0;
+        GemmArgs g{};                                   // L21 = A21 * Ldd^-T (in place)
+        g.A = A21; g.lda = lda; g.B = D; g.ldb = NB; g.C = A21; g.ldc = lda;
+        g.M = (int)rows; g.N = jb; g.K = jb; g.alpha = 1.0; g.beta = 0.0;
+        IPP_TRY(launch_gemm(g, s));
+        GemmArgs h{};                                   // A22 -= L21 L21^T on the lower tiles
+        h.A = A21; h.lda = lda; h.B = A21; h.ldb = lda; h.C = A + (j0 + jb) * lda + (j0 + jb); h.ldc = lda;
+        h.M = (int)rows; h.N = (int)rows; h.K = jb; h.alpha = -1.0; h.beta = 1.0; h.lower_only = 1;
+        IPP_TRY(launch_gemm(h, s));
+    }
+    return IPP_OK;
+}
+
+// A = K(X, X) + diag_add * I  (full matrix; the Cholesky reads the lower triangle)
+__global__ void add_diag_kernel(double* A, int64_t N, int64_t lda, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) A[i * lda + i] += v;
+}
+
+// scatter the 64x64 inverse diagonal blocks into Linv (lower) and U = Linv^T (upper)
+__global__ void place_diag_inverse_kernel(const double* __restrict__ dinv, int64_t N, double* __restrict__ Linv,
+                                          int64_t ldl, double* __restrict__ U, int64_t ld) {
+    const int64_t j0 = (int64_t)blockIdx.x * NB;
+    const double* D = dinv + (int64_t)blockIdx.x * NB * NB;
+    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+        const int r = idx >> 6, c = idx & 63;
+        if (j0 + r < N && j0 + c < N) {
+            Linv[(j0 + r) * ldl + j0 + c] = D[idx];
+            U[(j0 + c) * ld + j0 + r] = D[idx];
+        }
+    }
+}
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" int64_t ipp_potrf_workspace(int64_t N) { return ((N + NB - 1) / NB + 1) * NB * NB + 16; }
+
+extern "C" int ipp_potrf_lower(double* A, int64_t N, int64_t lda, double* logdet, int32_t* info, double* work,
+                               void* stream) {
+    IPP_CHECK_ARG(A && work && N >= 1 && lda >= N && lda % 2 == 0, "bad arguments");
+    IPP_CHECK_ARG(reinterpret_cast<uintptr_t>(A) % 16 == 0, "A must be 16-byte aligned");
+    return potrf_lower(A, N, lda, work, logdet, info, static_cast<cudaStream_t>(stream));
+}
+
+// pdinv of a dense SPD matrix already in device memory (lower triangle read, A overwritten by its factor)
+static int pdinv_device(double* Lf, int64_t N, int64_t lda, double* winv, double* linv, int64_t ldw,
+                        double* logdet, int32_t* info, double* work, cudaStream_t s) {
+    const int64_t ld = round_up(N, 16);
+    double* U = work;                     // Linv^T
+    double* Tt = U + N * ld;              // scratch for (L21 Linv11)^T
+    double* Li = Tt + N * ld;             // Linv when the caller does not want it
+    double* dinv = Li + N * ld;
+    double* Linv = linv ? linv : Li;
+    const int64_t ldl = linv ? ldw : ld;
+
+    IPP_TRY(potrf_lower(Lf, N, lda, dinv, logdet, info, s));
+    IPP_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * N * ldl, s));
+    IPP_CUDA(cudaMemsetAsync(U, 0, sizeof(double) * N * ld, s));
+    place_diag_inverse_kernel<<<(unsigned)((N + NB - 1) / NB), 256, 0, s>>>(dinv, N, Linv, ldl, U, ld);
+    IPP_LAUNCH_CHECK();
+    for (int64_t b = NB; b < N; b *= 2) {
+        for (int64_t r0 = 0; r0 + b < N; r0 += 2 * b) {
+            const int64_t b2 = (N - r0 - b) < b ? (N - r0 - b) : b;
+            GemmArgs g{};                               // Tt = (L21 * Linv11)^T  [b][b2]
+            g.A = Lf + (r0 + b) * lda + r0; g.lda = lda;
+            g.B = U + r0 * ld + r0; g.ldb = ld;
+            g.C = nullptr; g.Ct = Tt; g.ldct = ld;
+            g.M = (int)b2; g.N = (int)b; g.K = (int)b; g.alpha = 1.0; g.beta = 0.0;
+            IPP_TRY(launch_gemm(g, s));
+            GemmArgs h{};                               // Linv21 = -Linv22 * T, and its transpose into U
+            h.A = Linv + (r0 + b) * ldl + (r0 + b); h.lda = ldl;
+            h.B = Tt; h.ldb = ld;
+            h.C = Linv + (r0 + b) * ldl + r0; h.ldc = ldl;
+            h.Ct = U + r0 * ld + (r0 + b); h.ldct = ld;
+            h.M = (int)b2; h.N = (int)b; h.K = (int)b2; h.alpha = -1.0; h.beta = 0.0;
+            IPP_TRY(launch_gemm(h, s));
+        }
+    }
+    GemmArgs w{};                                       // W^-1 = U U^T, lower tiles, mirrored
+    w.A = U; w.lda = ld; w.B = U; w.ldb = ld; w.C = winv; w.ldc = ldw; w.Ct = winv; w.ldct = ldw;
+    w.M = (int)N; w.N = (int)N; w.K = (int)N; w.alpha = 1.0; w.beta = 0.0; w.lower_only = 1; w.k_from_max = 1;
+    IPP_TRY(launch_gemm(w, s));
+    return IPP_OK;
+}
+
+extern "C" int64_t ipp_pdinv_workspace(int64_t N) {
+    const int64_t ld = round_up(N > 0 ? N : 1, 16);
+    return 3 * N * ld + ipp_potrf_workspace(N) + 64;
+}
+
+extern "C" int ipp_pdinv(double* A, int64_t N, int64_t lda, double* winv, double* linv, int64_t ldw,
+                         double* logdet, int32_t* info, double* work, void* stream_) {
+    IPP_CHECK_ARG(A && winv && info && work, "null pointer");
+    IPP_CHECK_ARG(N >= 1 && N < (1LL << 30) && lda >= N && lda % 2 == 0 && ldw >= N && ldw % 2 == 0, "bad shape");
+    IPP_CHECK_ARG(reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(winv) % 16 == 0 &&
+                  (linv == nullptr || reinterpret_cast<uintptr_t>(linv) % 16 == 0), "matrices must be 16-byte aligned");
+    return pdinv_device(A, N, lda, winv, linv, ldw, logdet, info, work, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int64_t ipp_gp_factor_workspace(int64_t N) {
+    const int64_t ld = round_up(N > 0 ? N : 1, 16);
+    return N * ld + ipp_pdinv_workspace(N);
+}
+
+extern "C" int ipp_gp_factor(const ipp_rbf* kern, const double* X, const double* z, int64_t N, double diag_add,
+                             double* winv, double* linv, int64_t ldw, double* alpha, double* logdet, int32_t* info,
+                             double* work, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(kern && X && winv && work && info, "null pointer");
+    IPP_CHECK_ARG(N >= 1 && N < (1LL << 30), "bad N");
+    IPP_CHECK_ARG(ldw >= N && ldw % 2 == 0 && reinterpret_cast<uintptr_t>(winv) % 16 == 0, "winv: even ldw, 16-byte aligned");
+    IPP_CHECK_ARG(linv == nullptr || reinterpret_cast<uintptr_t>(linv) % 16 == 0, "linv must be 16-byte aligned");
+    const int64_t ld = round_up(N, 16);
+    double* Lf = work;                    // K + diag_add I, then its Cholesky factor (lower)
+    IPP_TRY(launch_rbf_cross(*kern, X, N, X, N, Lf, ld, s));
+    add_diag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(Lf, N, ld, diag_add);
+    IPP_LAUNCH_CHECK();
+    IPP_TRY(pdinv_device(Lf, N, ld, winv, linv, ldw, logdet, info, work + N * ld, s));
+    if (alpha && z) IPP_TRY(launch_gemv(winv, ldw, N, N, z, alpha, s));
+    return IPP_OK;
+}

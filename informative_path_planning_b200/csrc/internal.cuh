@@ -1,0 +1,78 @@
+// Internal declarations shared by the translation units of libipp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ipp_b200.h"
+
+namespace ipp {
+
+void set_error(const char* fmt, ...);
+int  sm_count();
+
+#define IPP_CHECK_ARG(cond, msg)                                                            \
+    do { if (!(cond)) { ::ipp::set_error("%s: %s", __func__, msg); return IPP_E_INVALID; } } while (0)
+
+#define IPP_CUDA(call)                                                                      \
+    do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                                \
+        ::ipp::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__));    \
+        return IPP_E_CUDA; } } while (0)
+
+#define IPP_LAUNCH_CHECK()                                                                  \
+    do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) {                    \
+        ::ipp::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__));\
+        return IPP_E_CUDA; } } while (0)
+
+#define IPP_TRY(call) do { int rc__ = (call); if (rc__ != IPP_OK) return rc__; } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ----- generic FP64 DMMA GEMM:  C (and/or Ct) = alpha * A[M][K] * B[N][K]^T + beta * C
+struct GemmArgs {
+    const double* A; const double* B; double* C; double* Ct;
+    int64_t lda, ldb, ldc, ldct;
+    int M, N, K;
+    double alpha, beta;
+    int lower_only;      // skip output tiles that lie strictly above the block diagonal
+    int k_from_max;      // contraction starts at max(m0, n0) (product of two upper-triangular-stored factors)
+    int k_to_min;        // contraction ends at min(m0, n0) + tile (product with lower-triangular operands)
+};
+int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+
+// ----- kernels used across files
+int launch_rbf_cross(const ipp_rbf& k, const double* X1, int64_t n1, const double* X2, int64_t n2,
+                     double* out, int64_t ldo, cudaStream_t s);
+// Kxt[m][n] = k(q_m, x_n) for a chunk of queries, plus mean[m] = sum_n Kxt[m][n] alpha[n] (alpha may be NULL)
+int launch_rbf_queries(const ipp_rbf& k, const double* X, int64_t N, const double* alpha,
+                       const double* Xq, int64_t M, double* Kxt, int64_t ldk, double* mean, cudaStream_t s);
+int launch_gemv(const double* A, int64_t lda, int64_t rows, int64_t cols, const double* x, double* y, cudaStream_t s);
+int potrf_lower(double* A, int64_t N, int64_t lda, double* dinv /* [ceil(N/64)][64*64] */, double* logdet,
+                int32_t* info, cudaStream_t s);
+
+struct RbfDev {
+    int dim;
+    double variance;
+    double il[IPP_MAX_DIM];
+};
+
+static inline RbfDev to_dev(const ipp_rbf& k) {
+    RbfDev d;
+    d.dim = k.dim;
+    d.variance = k.variance;
+    for (int i = 0; i < IPP_MAX_DIM; ++i) d.il[i] = i < k.dim ? k.inv_lengthscale[i] : 0.0;
+    return d;
+}
+
+template <int D>
+__device__ __forceinline__ double rbf_eval(const RbfDev& k, const double* a, const double* b) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double u = (a[d] - b[d]) * k.il[d];
+        r2 = fma(u, u, r2);
+    }
+    return k.variance * exp(-0.5 * r2);
+}
+
+
+}  // namespace ipp

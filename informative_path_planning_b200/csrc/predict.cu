@@ -1,0 +1,257 @@
+// a3 / a5: GP posterior mean and variance for a batch of query points.
+//
+//   mean[m] = sum_n k(q_m, x_n) alpha[n]                      (rbf_queries_kernel, fused with generation)
+//   var[m]  = variance - quad(m) + noise_add
+//     IPP_VAR_WINV_FULL  quad = sum_n (sum_j W[n][j] k_j) k_n            every 128x128 tile   (2 N^2 flop / query)
+//     IPP_VAR_WINV_SYM   same products, W symmetric: strictly-lower tiles counted twice,
+//                        diagonal tiles once                                                  (  N^2 flop / query)
+//     IPP_VAR_CHOL       quad = sum_n (sum_{j<=n} Linv[n][j] k_j)^2      lower tiles only     (  N^2 flop / query)
+//
+// The cross-covariance of one chunk of queries is materialised query-major (Kxt[m][n]) once, so the
+// exp is evaluated once per (m, n); the quadratic form is a DMMA GEMM  C[m][n] = sum_j Kxt[m][j] mat[n][j]
+// whose 128x128 output tile is never stored: the epilogue multiplies it with Kxt[m][n] (or squares it),
+// reduces over n with quad shuffles + a 4-warp shared-memory tree, and writes one partial per
+// (n-tile, m).  A persistent grid (one CTA per SM) pulls (n-tile, m-tile) items from an atomic
+// counter, heaviest n-tiles first.  A last pass adds the partials in a fixed order (deterministic).
+#include "internal.cuh"
+#include "dgemm_dmma.cuh"
+
+namespace ipp {
+
+struct PredictArgs {
+    const double* Kxt; int64_t ldk; int Mc;
+    const double* mat; int64_t ldm; int N;
+    int mode;
+    double* partial; int64_t ldp;
+    int* counter;
+    int T, Mtiles;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) predict_var_kernel(PredictArgs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_red[4][BM];
+    __shared__ int s_item;
+    const uint32_t smem_base = smem_u32(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 2) * WM, wn0 = (warp & 3) * WN;
+    const int total = p.T * p.Mtiles;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(p.counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int I = p.T - 1 - item / p.Mtiles;
+        const int m0 = (item % p.Mtiles) * BM, n0 = I * BN;
+        const int ndiag_end = (n0 + BN < p.N) ? (n0 + BN) : p.N;
+
+        double acc[MI][NI][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        if (p.mode == IPP_VAR_WINV_SYM) {
+            if (n0 > 0) {
+                gemm_mainloop(smem_base, p.Kxt, p.ldk, m0, p.Mc, p.mat, p.ldm, n0, p.N, 0, n0, acc, tid, wm0, wn0, g, t);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) { acc[i][j][0] *= 2.0; acc[i][j][1] *= 2.0; }
+            }
+            gemm_mainloop(smem_base, p.Kxt, p.ldk, m0, p.Mc, p.mat, p.ldm, n0, p.N, n0, ndiag_end, acc, tid, wm0, wn0, g, t);
+        } else if (p.mode == IPP_VAR_CHOL) {
+            gemm_mainloop(smem_base, p.Kxt, p.ldk, m0, p.Mc, p.mat, p.ldm, n0, p.N, 0, ndiag_end, acc, tid, wm0, wn0, g, t);
+        } else {
+            gemm_mainloop(smem_base, p.Kxt, p.ldk, m0, p.Mc, p.mat, p.ldm, n0, p.N, 0, p.N, acc, tid, wm0, wn0, g, t);
+        }
+
+        // fused epilogue: reduce the tile against Kxt[m][n0 .. n0+127] (or its own square) over n
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int row = m0 + wm0 + 8 * i + g;
+            double s = 0.0;
+            if (row < p.Mc) {
+                const double* kr = p.Kxt + (int64_t)row * p.ldk;
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    const int col = n0 + wn0 + 8 * j + 2 * t;
+                    if (p.mode == IPP_VAR_CHOL) {
+                        s = fma(acc[i][j][0], acc[i][j][0], s);
+                        s = fma(acc[i][j][1], acc[i][j][1], s);
+                    } else if (col + 1 < p.N) {
+                        const double2 kv = *reinterpret_cast<const double2*>(kr + col);
+                        s = fma(acc[i][j][0], kv.x, s);
+                        s = fma(acc[i][j][1], kv.y, s);
+                    } else if (col < p.N) {
+                        s = fma(acc[i][j][0], kr[col], s);
+                    }
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (t == 0) s_red[warp & 3][wm0 + 8 * i + g] = s;
+        }
+        __syncthreads();
+        if (tid < BM && m0 + tid < p.Mc)
+            p.partial[(int64_t)I * p.ldp + m0 + tid] = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
+        __syncthreads();
+    }
+}
+
+__global__ void predict_finalize_kernel(const double* __restrict__ partial, int64_t ldp, int T, int Mc,
+                                        double variance, double noise_add, double* __restrict__ var) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mc) return;
+    double q = 0.0;
+    for (int I = 0; I < T; ++I) q += partial[(int64_t)I * ldp + m];
+    var[m] = (variance - q) + noise_add;
+}
+
+__global__ void prior_fill_kernel(double* mean, double* var, int64_t M, double v) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) { mean[m] = 0.0; var[m] = v; }
+}
+
+__global__ void add_scalar_kernel(double* A, int64_t rows, int64_t cols, int64_t ld, double v) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < rows * cols) A[(idx / cols) * ld + idx % cols] += v;
+}
+
+constexpr int64_t PREDICT_CHUNK = 32768;
+
+// Optional CUDA-event timing of the dominant kernel (predict_var_kernel), on the launching stream.
+// Used by bench.py for the roofline figure; off by default (no events are recorded).
+constexpr int PROFILE_MAX = 8192;
+static bool g_profile = false;
+static cudaEvent_t g_ev[PROFILE_MAX][2];
+static int g_ev_made = 0, g_ev_used = 0;
+
+static void profile_mark(int which, cudaStream_t s) {
+    if (!g_profile || g_ev_used >= PROFILE_MAX) return;
+    if (which == 0 && g_ev_used >= g_ev_made) {
+        cudaEventCreate(&g_ev[g_ev_made][0]);
+        cudaEventCreate(&g_ev[g_ev_made][1]);
+        ++g_ev_made;
+    }
+    cudaEventRecord(g_ev[g_ev_used][which], s);
+    if (which == 1) ++g_ev_used;
+}
+
+static int64_t chunk_rows(int64_t M) { return M < PREDICT_CHUNK ? round_up(M, BM) : PREDICT_CHUNK; }
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" int64_t ipp_gp_predict_workspace(int64_t N, int64_t M) {
+    if (N <= 0 || M <= 0) return 16;
+    const int64_t ldk = round_up(N, 16), mc = chunk_rows(M), T = (N + BN - 1) / BN;
+    return mc * ldk + T * mc + 16;
+}
+
+extern "C" int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                              const double* mat, int64_t ldm, int var_mode, double noise_add,
+                              const double* Xq, int64_t M, double* mean, double* var,
+                              double* work, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(kern && Xq && mean && var, "null pointer");
+    IPP_CHECK_ARG(M >= 1, "need at least one query point");
+    IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
+    if (N == 0) {   // no observations: prior (gpmodel_library.py:310-311; noise is NOT added there)
+        prior_fill_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(mean, var, M, kern->variance);
+        IPP_LAUNCH_CHECK();
+        return IPP_OK;
+    }
+    IPP_CHECK_ARG(X && alpha && mat && work, "null pointer");
+    IPP_CHECK_ARG(var_mode >= 0 && var_mode <= 2, "bad var_mode");
+    IPP_CHECK_ARG(ldm >= N && ldm % 2 == 0 && reinterpret_cast<uintptr_t>(mat) % 16 == 0, "mat must be 16-byte aligned, ldm even");
+    IPP_CHECK_ARG(N < (1LL << 30), "N too large");
+    static bool configured = false;
+    if (!configured) {
+        IPP_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        configured = true;
+    }
+    const int64_t ldk = round_up(N, 16), mc_max = chunk_rows(M);
+    const int T = (int)((N + BN - 1) / BN);
+    double* Kxt = work;
+    double* partial = work + mc_max * ldk;
+    int* counter = reinterpret_cast<int*>(partial + (int64_t)T * mc_max);
+    const int grid = sm_count();
+    for (int64_t s = 0; s < M; s += mc_max) {
+        const int64_t mc = (M - s) < mc_max ? (M - s) : mc_max;
+        IPP_TRY(launch_rbf_queries(*kern, X, N, alpha, Xq + s * kern->dim, mc, Kxt, ldk, mean + s, stream));
+        IPP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        PredictArgs p;
+        p.Kxt = Kxt; p.ldk = ldk; p.Mc = (int)mc;
+        p.mat = mat; p.ldm = ldm; p.N = (int)N;
+        p.mode = var_mode;
+        p.partial = partial; p.ldp = mc_max;
+        p.counter = counter;
+        p.T = T; p.Mtiles = (int)((mc + BM - 1) / BM);
+        const int items = p.T * p.Mtiles;
+        profile_mark(0, stream);
+        predict_var_kernel<<<items < grid ? items : grid, GEMM_THREADS, GEMM_SMEM, stream>>>(p);
+        profile_mark(1, stream);
+        IPP_LAUNCH_CHECK();
+        predict_finalize_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, T, (int)mc,
+                                                                                 kern->variance, noise_add, var + s);
+        IPP_LAUNCH_CHECK();
+    }
+    return IPP_OK;
+}
+
+extern "C" int ipp_profile_enable(int on) {
+    g_profile = on != 0;
+    g_ev_used = 0;
+    return IPP_OK;
+}
+
+extern "C" int ipp_profile_read(double* total_ms, int64_t* launches) {
+    IPP_CHECK_ARG(total_ms && launches, "null pointer");
+    double sum = 0.0;
+    for (int i = 0; i < g_ev_used; ++i) {
+        IPP_CUDA(cudaEventSynchronize(g_ev[i][1]));
+        float ms = 0.f;
+        IPP_CUDA(cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = g_ev_used;
+    g_ev_used = 0;
+    return IPP_OK;
+}
+
+extern "C" int64_t ipp_gp_predict_cov_workspace(int64_t N, int64_t M) {
+    if (N <= 0 || M <= 0) return 16;
+    return 2 * round_up(M, 2) * round_up(N, 16) + 16;
+}
+
+extern "C" int ipp_gp_predict_cov(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                                  const double* winv, int64_t ldm, double noise_add,
+                                  const double* Xq, int64_t M, double* mean, double* cov, int64_t ldc,
+                                  double* work, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(kern && X && alpha && winv && Xq && mean && cov && work, "null pointer");
+    IPP_CHECK_ARG(N >= 1 && M >= 1 && M < (1 << 20), "bad shape");
+    IPP_CHECK_ARG(ldc >= M && ldc % 2 == 0, "ldc must be even and >= M");
+    const int64_t ldk = round_up(N, 16);
+    double* Kxt = work;
+    double* T1 = work + round_up(M, 2) * ldk;
+    IPP_TRY(launch_rbf_queries(*kern, X, N, alpha, Xq, M, Kxt, ldk, mean, stream));
+    GemmArgs g{};
+    g.A = Kxt; g.lda = ldk; g.B = winv; g.ldb = ldm; g.C = T1; g.ldc = ldk;
+    g.M = (int)M; g.N = (int)N; g.K = (int)N; g.alpha = 1.0; g.beta = 0.0;
+    IPP_TRY(launch_gemm(g, stream));                                   // T1 = Kx^T W^-1
+    IPP_TRY(launch_rbf_cross(*kern, Xq, M, Xq, M, cov, ldc, stream));  // K(q, q)
+    GemmArgs h{};
+    h.A = T1; h.lda = ldk; h.B = Kxt; h.ldb = ldk; h.C = cov; h.ldc = ldc;
+    h.M = (int)M; h.N = (int)M; h.K = (int)N; h.alpha = -1.0; h.beta = 1.0;
+    IPP_TRY(launch_gemm(h, stream));                                   // cov -= T1 Kx
+    if (noise_add != 0.0) {
+        add_scalar_kernel<<<(unsigned)((M * M + 255) / 256), 256, 0, stream>>>(cov, M, M, ldc, noise_add);
+        IPP_LAUNCH_CHECK();
+    }
+    return IPP_OK;
+}

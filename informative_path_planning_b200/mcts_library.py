@@ -1,0 +1,315 @@
+"""Tree search front-end (reference mcts_library.py:277-713) with the rewards on the GPU.
+
+The tree, its selection rules and its random-number consumption follow the reference exactly
+(SURVEY.md 8a row a12), so that on fixed seeds the same actions are chosen:
+  * DPW tree (`Tree`): widening exponent alpha = 3 / (10 (D - d) - 3); an existing child is re-used
+    iff d < D - 1 and floor(n^alpha) == floor((n - 1)^alpha), picked uniformly among the least visited
+    (after one discarded random.choice draw, reference :408); otherwise observations are simulated
+    from the PRIOR N(0, variance I) because belief.model is None for OnlineGPModel (:418-422) and are
+    appended TWICE (:426, :430);
+  * action choice Q/n + c sqrt(N^e_d / n), e_d = (1 - 3 / (10 (D - d))) / 2, first unvisited child wins,
+    exact ties broken with random.choice (:444-455);
+  * `BeliefTree`: Q/n + c sqrt(2 ln N / n), zero ("maximum likelihood") observations, random rollouts
+    below a not-yet-expanded node with np.random.randint(0, len - 1) (never the last action, :510);
+  * final action = most visited root child, ties -> random.choice (:707).
+
+Each rollout works on copy.copy(belief): an O(1) fork, because the device state of a belief is
+immutable and every append writes new buffers.
+
+Batching seam (`evaluate_root_actions`, `choose_myopic`): all candidate paths of a pose are scored by
+ONE call of aq_library.reward_paths instead of one predict per path (robot_library.py:175-203).
+"""
+import copy
+import random
+
+import numpy as np
+
+from . import aq_library as aqlib
+
+_PARAM_REWARDS = ('mes', 'maxs-mes', 'exp_improve', 'naive', 'naive_value')
+
+
+class Node(object):
+    def __init__(self, pose, parent, name, action=None, dense_path=None, zvals=None):
+        self.pose = pose
+        self.name = name
+        self.zvals = zvals
+        self.reward = 0.0
+        self.nqueries = 0
+        self.parent = parent
+        self.children = None
+        self.action = action
+        self.dense_path = dense_path if action is not None else None
+        if action is None:
+            self.node_type = 'B'
+            self.depth = 0 if parent is None else parent.depth + 1
+        else:
+            self.node_type = 'BA'
+            self.depth = parent.depth
+
+    def add_children(self, child_node):
+        if self.children is None:
+            self.children = []
+        self.children.append(child_node)
+
+    def print_self(self):
+        print(self.name)
+
+
+def _xobs(action):
+    obs = np.array(action)
+    return np.vstack([obs[:, 0], obs[:, 1]]).T
+
+
+class Tree(object):
+    def __init__(self, f_rew, f_aqu, belief, pose, path_generator, t, depth, param, c):
+        self.path_generator = path_generator
+        self.max_depth = depth
+        self.param = param
+        self.t = t
+        self.f_rew = f_rew
+        self.aquisition_function = f_aqu
+        self.c = c
+        self.root = Node(pose, parent=None, name='root')
+
+    def get_best_child(self):
+        return self.root.children[int(np.argmax([node.nqueries for node in self.root.children]))]
+
+    def backprop(self, leaf_node, reward):
+        node = leaf_node
+        while node is not None:
+            node.nqueries += 1
+            node.reward += reward
+            node = node.parent
+
+    def get_next_leaf(self, belief):
+        leaf, reward = self.leaf_helper(self.root, reward=0.0, belief=belief)
+        self.backprop(leaf, reward)
+
+    def action_reward(self, xobs, belief):
+        if self.f_rew in _PARAM_REWARDS:
+            return self.aquisition_function(time=self.t, xvals=xobs, robot_model=belief, param=self.param)
+        return self.aquisition_function(time=self.t, xvals=xobs, robot_model=belief)
+
+    def simulate_observation(self, xobs, belief):
+        n_points = xobs.shape[0]
+        if belief.model is None:
+            zobs = np.random.multivariate_normal(mean=np.zeros((n_points,)), cov=np.eye(n_points) * belief.variance)
+            return np.reshape(zobs, (n_points, 1))
+        return belief.posterior_samples(xobs, full_cov=False, size=1)
+
+    def _expand_action(self, node, reward, belief):
+        """One 'BA' step.  Returns (next belief node, accumulated reward)."""
+        xobs = _xobs(node.action)
+        r = self.action_reward(xobs, belief)
+        if node.children is not None:
+            alpha = 3.0 / (10.0 * (self.max_depth - node.depth) - 3.0)
+            nchild = len(node.children)
+            if node.depth < self.max_depth - 1 and np.floor(nchild ** alpha) == np.floor((nchild - 1) ** alpha):
+                random.choice(node.children)                                   # draw consumed, result unused
+                fewest = min(n.nqueries for n in node.children)
+                child = random.choice([n for n in node.children if n.nqueries == fewest])
+                belief.add_data(xobs, child.zvals)
+                return child, reward + r
+        zobs = self.simulate_observation(xobs, belief)
+        belief.add_data(xobs, zobs)
+        belief.add_data(xobs, zobs)
+        child = Node(pose=node.dense_path[-1], parent=node, name=node.name + '_belief' + str(node.depth + 1),
+                     zvals=zobs)
+        node.add_children(child)
+        return child, reward + r
+
+    def leaf_helper(self, current_node, reward, belief):
+        node = current_node
+        while True:
+            if node.node_type == 'B':
+                if node.depth == self.max_depth:
+                    return node, reward
+                if node.children is None:
+                    self.build_action_children(node)
+                if node.children is None:
+                    return node, reward
+                node = self.get_next_child(node)
+            else:
+                node, reward = self._expand_action(node, reward, belief)
+
+    def get_next_child(self, current_node):
+        vals = {}
+        e_d = 0.5 * (1.0 - (3.0 / (10.0 * (self.max_depth - current_node.depth))))
+        for child in current_node.children:
+            if child.nqueries == 0:
+                return child
+            vals[child] = child.reward / float(child.nqueries) + self.c * np.sqrt(
+                (float(current_node.nqueries) ** e_d) / float(child.nqueries))
+        top = max(vals.values())
+        return random.choice([key for key in vals.keys() if vals[key] == top])
+
+    def build_action_children(self, parent):
+        actions, dense_paths = self.path_generator.get_path_set(parent.pose)
+        if len(actions) == 0:
+            return
+        for i, action in enumerate(list(actions.keys())):
+            parent.add_children(Node(pose=parent.pose, parent=parent, name=parent.name + '_action' + str(i),
+                                     action=actions[action], dense_path=dense_paths[action]))
+
+    def count_leaves(self, node=None):
+        node = self.root if node is None else node
+        if node.children is None:
+            return 1
+        return sum(self.count_leaves(c) for c in node.children)
+
+
+class BeliefTree(Tree):
+    def mle_observation(self, xobs, belief):
+        if belief.model is None:
+            return np.zeros((xobs.shape[0], 1))
+        return belief.predict_value(xobs)[0]
+
+    def random_rollouts(self, current_node, reward, belief):
+        cur_depth = current_node.depth
+        pose = current_node.pose
+        while cur_depth <= self.max_depth:
+            actions, dense_paths = self.path_generator.get_path_set(pose)
+            keys = list(actions.keys())
+            if len(actions) <= 1:
+                return reward
+            a = np.random.randint(0, len(actions) - 1)
+            xobs = _xobs(actions[keys[a]])
+            r = self.action_reward(xobs, belief)
+            zobs = self.mle_observation(xobs, belief)
+            belief.add_data(xobs, zobs)
+            belief.add_data(xobs, zobs)
+            pose = dense_paths[keys[a]][-1]
+            reward += r
+            cur_depth += 1
+        return reward
+
+    def leaf_helper(self, current_node, reward, belief):
+        node = current_node
+        while True:
+            if node.node_type == 'B':
+                if node.depth == self.max_depth:
+                    return node, reward
+                if node.children is None:
+                    self.build_action_children(node)
+                if node.children is None:
+                    return node, reward
+                child, full_action_set = self.get_next_child(node)
+                if not full_action_set:
+                    return child, self.random_rollouts(node, reward, belief)
+                node = child
+            else:
+                xobs = _xobs(node.action)
+                r = self.action_reward(xobs, belief)
+                zobs = self.mle_observation(xobs, belief)
+                belief.add_data(xobs, zobs)
+                belief.add_data(xobs, zobs)
+                child = Node(pose=node.dense_path[-1], parent=node,
+                             name=node.name + '_belief' + str(node.depth + 1), zvals=zobs)
+                node.add_children(child)
+                node, reward = child, reward + r
+
+    def get_next_child(self, current_node):
+        vals = {}
+        for child in current_node.children:
+            if child.nqueries == 0:
+                return child, False
+            vals[child] = child.reward / float(child.nqueries) + self.c * np.sqrt(
+                2.0 * np.log(float(current_node.nqueries)) / float(child.nqueries))
+        top = max(vals.values())
+        return random.choice([key for key in vals.keys() if vals[key] == top]), True
+
+
+def exploration_constant(f_rew, tree_type):
+    """reference :645-660"""
+    if f_rew == 'mean':
+        return {'belief': 1000, 'dpw': 5000}.get(tree_type, 1.0)
+    if f_rew == 'exp_improve':
+        return 200
+    if f_rew == 'mes':
+        return {'belief': 1.0 / np.sqrt(2.0), 'dpw': 1.0}.get(tree_type, 1.0)
+    return 1.0
+
+
+class cMCTS(object):
+    """reference :636-713 (the legacy dict-tree base class MCTS :27-274 is not carried over)."""
+
+    def __init__(self, computation_budget, belief, initial_pose, rollout_length, path_generator,
+                 aquisition_function, f_rew, T, aq_param=None, use_cost=False, tree_type='dpw'):
+        self.GP = belief
+        self.cp = initial_pose
+        self.path_generator = path_generator
+        self.comp_budget = computation_budget
+        self.rl = rollout_length
+        self.tree = None
+        self.aquisition_function = aquisition_function
+        self.max_val = None
+        self.max_locs = None
+        self.target = None
+        self.current_max = aq_param
+        self.aq_param = aq_param
+        self.f_rew = f_rew
+        self.t = T
+        self.use_cost = use_cost
+        self.tree_type = tree_type
+        self.c = exploration_constant(f_rew, tree_type)
+
+    def choose_trajectory(self, t):
+        if self.f_rew == 'mes':
+            self.max_val, self.max_locs, self.target = aqlib.sample_max_vals(self.GP, t=t, visualize=True)
+            param = (self.max_val, self.max_locs, self.target)
+        elif self.f_rew == 'exp_improve':
+            param = [self.current_max]
+        elif self.f_rew in ('naive', 'naive_value'):
+            self.max_val, self.max_locs, self.target = aqlib.sample_max_vals(self.GP, t=t, nK=int(self.aq_param[0]),
+                                                                             visualize=True, f_rew=self.f_rew)
+            param = ((self.max_val, self.max_locs, self.target), self.aq_param[1])
+        else:
+            param = None
+        if self.tree_type == 'dpw':
+            tree_cls = Tree
+        elif self.tree_type == 'belief':
+            tree_cls = BeliefTree
+        else:
+            raise ValueError('Tree type must be one of either \'dpw\' or \'belief\'')
+        self.tree = tree_cls(self.f_rew, self.aquisition_function, self.GP, self.cp, self.path_generator, t,
+                             depth=self.rl, param=param, c=self.c)
+        for _ in range(self.comp_budget):
+            self.tree.get_next_leaf(copy.copy(self.GP))
+        most = max(n.nqueries for n in self.tree.root.children)
+        best_child = random.choice([node for node in self.tree.root.children if node.nqueries == most])
+        all_vals = {i: child.reward / float(child.nqueries) for i, child in enumerate(self.tree.root.children)}
+        paths, dense_paths = self.path_generator.get_path_set(self.cp)
+        return (best_child.action, best_child.dense_path, best_child.reward / float(best_child.nqueries), paths,
+                all_vals, self.max_locs, self.max_val, self.target)
+
+
+# ------------------------------------------------------------------------------------------ batched seams
+_F_REW_TO_BATCH = {'mean': 'mean', 'mes': 'mes', 'exp_improve': 'exp_improve', 'info_gain': 'info_gain',
+                   'hotspot_info': 'hotspot_info'}
+
+
+def evaluate_root_actions(belief, paths, f_rew, t, param=None):
+    """Score every candidate path of one pose in a single GPU call.  `paths`: dict key -> point list."""
+    keys = list(paths.keys())
+    values = aqlib.reward_paths(_F_REW_TO_BATCH[f_rew], t, [paths[k] for k in keys], belief, param)
+    return dict(zip(keys, values))
+
+
+def choose_myopic(belief, path_generator, pose, f_rew, t, param=None, use_cost=False):
+    """Robot.choose_trajectory's path loop (reference robot_library.py:173-208) with one batched reward
+    call.  Returns (sampling path, dense path, value, all paths, all values) or None."""
+    paths, true_paths = path_generator.get_path_set(pose)
+    if len(paths) == 0:
+        return None
+    value = evaluate_root_actions(belief, paths, f_rew, t, param)
+    if use_cost:
+        for k in list(value.keys()):
+            cost = float(path_generator.path_cost(true_paths[k]))
+            value[k] = value[k] / (cost if cost != 0.0 else 100.0)
+    try:
+        top = max(value.values())
+        best_key = np.random.choice([key for key in value.keys() if value[key] == top])
+        return paths[best_key], true_paths[best_key], value[best_key], paths, value
+    except Exception:
+        return None

@@ -1,0 +1,130 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, torch.distributed.
+
+The path shards naturally: query points and whole candidate paths are independent given the belief
+(X, alpha, W^-1).  So
+  * the belief is REPLICATED: a new observation is broadcast from the source rank (k x (D+1) doubles)
+    and every rank applies the same FP64 refresh / block append locally -- cheaper than shipping the
+    N x N inverse (134 MB at N=4096) and bit-identical across ranks because every rank runs the same
+    deterministic kernels on the same inputs; `mode='broadcast'` ships the factor instead;
+  * queries / paths are SHARDED contiguously (never splitting a path), with no data-path collective;
+  * per-path rewards are returned with one all_gather (64k paths x 8 B: latency-bound).
+Collectives run on NCCL over NVLink when the tensors are CUDA tensors and on gloo for the CPU tests
+of the host-side logic (the functions below never look at the device of what they move).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank, size):
+    """Contiguous, balanced [lo, hi) split of n items: the first n % size ranks get one extra."""
+    base, extra = divmod(int(n), int(size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_paths(offsets, rank, size):
+    """Whole paths only: rank r owns paths [plo, phi) and therefore points [offsets[plo], offsets[phi])."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    plo, phi = shard_bounds(offsets.shape[0] - 1, rank, size)
+    return plo, phi, int(offsets[plo]), int(offsets[phi])
+
+
+def _comm_device():
+    if dist.get_backend() == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def broadcast_array(a, src=0):
+    """Broadcast a float64 numpy array (None on non-source ranks) -> numpy array on every rank."""
+    rank, size = world()
+    if size == 1:
+        return np.asarray(a, dtype=np.float64)
+    dev = _comm_device()
+    shape = torch.zeros(4, dtype=torch.int64, device=dev)
+    if rank == src:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        shape[:a.ndim + 1] = torch.tensor([a.ndim] + list(a.shape), dtype=torch.int64)
+    dist.broadcast(shape, src)
+    ndim = int(shape[0])
+    dims = [int(s) for s in shape[1:1 + ndim]]
+    buf = torch.from_numpy(a).to(dev) if rank == src else torch.empty(dims, dtype=torch.float64, device=dev)
+    dist.broadcast(buf, src)
+    return buf.cpu().numpy()
+
+
+def add_data_replicated(model, xvals, zvals, src=0, mode='recompute'):
+    """model.add_data on every rank with the observation that only `src` holds.
+    mode='recompute': broadcast (xvals, zvals), every rank refreshes locally (default).
+    mode='broadcast': `src` refreshes, then W^-1 and alpha are broadcast (NCCL over NVLink)."""
+    rank, size = world()
+    xvals = broadcast_array(xvals, src)
+    zvals = broadcast_array(zvals, src)
+    if size == 1 or mode == 'recompute':
+        model.add_data(xvals, zvals)
+        return model
+    if mode != 'broadcast':
+        raise ValueError("mode must be 'recompute' or 'broadcast'")
+    if rank == src:
+        model.add_data(xvals, zvals)
+    else:
+        model.attach_state_shell(xvals, zvals)           # host arrays + empty device buffers of the right shape
+    for t in model.state_tensors():
+        dist.broadcast(t, src)
+    return model
+
+
+def gather_concat(local, counts):
+    """all_gather of ragged 1-D float64 tensors (counts[r] items from rank r) -> concatenated tensor."""
+    rank, size = world()
+    if size == 1:
+        return local
+    width = int(max(counts))
+    pad = torch.zeros(width, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    out = [torch.empty_like(pad) for _ in range(size)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:int(c)] for o, c in zip(out, counts)])
+
+
+def predict_sharded(model, xq):
+    """Posterior mean/var of (M, D) numpy queries: each rank predicts its contiguous slice on its GPU,
+    the slices are all-gathered.  Returns (mean (M,1), var (M,1)) on every rank."""
+    rank, size = world()
+    M = xq.shape[0]
+    lo, hi = shard_bounds(M, rank, size)
+    counts = [shard_bounds(M, r, size)[1] - shard_bounds(M, r, size)[0] for r in range(size)]
+    from . import _lib as L
+    mean, var = model.predict_device(L.to_device(xq[lo:hi])) if hi > lo else (
+        torch.empty(0, dtype=torch.float64, device=L.device()), torch.empty(0, dtype=torch.float64, device=L.device()))
+    mean, var = gather_concat(mean, counts), gather_concat(var, counts)
+    return mean.cpu().numpy().reshape(-1, 1), var.cpu().numpy().reshape(-1, 1)
+
+
+def reward_paths_sharded(model, f_rew, time, queries, offsets, param=None, reward_fn=None):
+    """Rewards of P paths, P/size whole paths per rank, one all_gather.  `reward_fn(f_rew, time, q, offs,
+    model, param) -> float64 [p]` defaults to aq_library.reward_paths (injected in the CPU tests)."""
+    rank, size = world()
+    offsets = np.asarray(offsets, dtype=np.int64)
+    P = offsets.shape[0] - 1
+    plo, phi, qlo, qhi = shard_paths(offsets, rank, size)
+    if reward_fn is None:
+        from . import aq_library as aq
+
+        def reward_fn(f, t, q, o, m, p):
+            return aq.reward_paths(f, t, q, m, p, offsets=o)
+    if phi > plo:
+        local = np.asarray(reward_fn(f_rew, time, queries[qlo:qhi], offsets[plo:phi + 1] - qlo, model, param), dtype=np.float64)
+    else:
+        local = np.zeros(0)
+    counts = [shard_bounds(P, r, size)[1] - shard_bounds(P, r, size)[0] for r in range(size)]
+    dev = _comm_device() if size > 1 else torch.device('cpu')
+    out = gather_concat(torch.from_numpy(local).to(dev), counts)
+    return out.cpu().numpy()

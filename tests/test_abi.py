@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ipp_b200.h declares; no compute calls."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, 'include', 'ipp_b200.h')
+LIBRARY = os.path.join(ROOT, 'informative_path_planning_b200', 'csrc', 'libipp_b200.so')
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(ipp_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(LIBRARY):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(LIBRARY)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_python_binding_covers_the_header():
+    from informative_path_planning_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    assert _lib.lib.ipp_version() == 100
+    # workspace queries are pure host arithmetic: safe without a device
+    assert _lib.lib.ipp_gp_predict_workspace(4096, 1 << 20) > 4096 * 32768
+    assert _lib.lib.ipp_gp_factor_workspace(1024) >= 4 * 1024 * 1024
+
+
+def test_struct_layout_matches_header():
+    from informative_path_planning_b200 import _lib
+    assert ctypes.sizeof(_lib.IppRbf) == 40          # int32 + pad, double, double[3]
+    k = _lib.make_rbf(2, 100.0, 1.0)
+    assert (k.dim, k.variance, k.inv_lengthscale[0], k.inv_lengthscale[1], k.inv_lengthscale[2]) == (2, 100.0, 1.0, 1.0, 0.0)
+    k3 = _lib.make_rbf(3, 4.0, (2.0, 4.0, 8.0))
+    assert list(k3.inv_lengthscale) == [0.5, 0.25, 0.125]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'informative_path_planning_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('np.random', ''), (f, 'product code must not reference oracle/')
+
+
+def test_reference_ctor_errors_without_gpu():
+    import pytest
+    from informative_path_planning_b200.gpmodel_library import OnlineGPModel
+    with pytest.raises(ValueError):
+        OnlineGPModel((0, 10, 0, 10), 1.0, 100.0, dimension=4)
+    with pytest.raises(ValueError):
+        OnlineGPModel((0, 10, 0, 10), 1.0, 100.0, kernel='matern')
+    with pytest.raises(ValueError):
+        OnlineGPModel((0, 10, 0, 10), (1.0, 1.0), 100.0, dimension=3)
+    m = OnlineGPModel((0, 10, 0, 10), 1.0, 100.0, noise=0.5)
+    assert m.xvals is None and m.zvals is None and m.model is None
+    import numpy as np
+    mu, var = m.predict_value(np.zeros((3, 2)))          # no data: prior, no device needed
+    assert mu.shape == (3, 1) and np.all(var == 100.0)
+    with pytest.raises(AssertionError):
+        m.predict_value(np.zeros((3, 3)))
+
+
+def test_paths_library_matches_oracle_generator():
+    import numpy as np
+    from informative_path_planning_b200.paths_library import Path_Generator, Dubins_Path_Generator, dubins_shortest_path
+    from oracle.mcts_oracle import PathGeneratorOracle
+    a = Path_Generator(15, 1.5, 0.05, 0.5, (0, 10, 0, 10)).get_path_set((4.0, 6.0, 1.1))[0]
+    b = PathGeneratorOracle(15, 1.5, 0.05, 0.5, (0, 10, 0, 10)).get_path_set((4.0, 6.0, 1.1))[0]
+    assert sorted(a) == sorted(b)
+    for k in a:
+        np.testing.assert_allclose(np.array(a[k]), np.array(b[k]))
+    # Dubins: straight-ahead goal is a straight line of the right length; every path ends near its goal
+    word, (t, p, q) = dubins_shortest_path((0, 0, 0), (4, 0, 0), 1.0)
+    assert abs(t + p + q - 4.0) < 1e-12
+    g = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, (0, 10, 0, 10))
+    paths, true_paths = g.get_path_set((5.0, 5.0, 0.3))
+    assert len(paths) >= 10
+    for k, pts in paths.items():
+        goal = g.goals[k]
+        end = true_paths[k][-1]
+        assert np.hypot(end[0] - goal[0], end[1] - goal[1]) < 0.5 + 1e-9      # samples every ss; the end point itself is excluded
+        steps = np.hypot(np.diff([c[0] for c in pts]), np.diff([c[1] for c in pts]))
+        assert np.all(steps < 0.5 + 1e-6)
