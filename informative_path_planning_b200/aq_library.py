@@ -306,9 +306,10 @@ def rff_features(W, b, X_d, variance, nFeatures):
     N = X_d.shape[0]
     ldz = L.round_up(N, 2)
     Z = torch.empty((F, ldz), dtype=torch.float64, device=X_d.device)
-    L.check(L.lib.ipp_rff_features(L.ptr(L.to_device(W)), L.ptr(L.to_device(b.reshape(-1))), F, D, L.ptr(X_d), N,
+    W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))     # keep both alive until the launch is enqueued
+    L.check(L.lib.ipp_rff_features(L.ptr(W_d), L.ptr(b_d), F, D, L.ptr(X_d), N,
                                    float(np.sqrt(2 * variance / nFeatures)), L.ptr(Z), ldz, L.stream_ptr()))
-    return Z[:, :N].cpu().numpy()
+    return np.ascontiguousarray(Z[:, :N].cpu().numpy())
 
 
 def global_maximization(target, target_vector_n, target_grad, target_vector_gradient_n, ranges, guesses, visualize,
@@ -430,6 +431,7 @@ def rff_eval_argmax_shared(W, b, Theta, variance, grid_d):
     mx = torch.empty(S, dtype=torch.float64, device=grid_d.device)
     am = torch.empty(S, dtype=torch.int64, device=grid_d.device)
     work = L.workspace(L.lib.ipp_rff_workspace(S, G), slot='rff')
-    L.check(L.lib.ipp_rff_eval_argmax(L.ptr(L.to_device(W)), L.ptr(L.to_device(b.reshape(-1))), L.ptr(th_d), F, S, D, 1,
+    W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))     # keep both alive until the launch is enqueued
+    L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, D, 1,
                                       L.ptr(grid_d), G, None, L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
     return mx, am
