@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libipp_b200.so')
+LIB_PATH = os.environ.get('IPP_B200_LIB') or os.path.join(_HERE, 'csrc', 'libipp_b200.so')   # env override: kernel-variant experiments
 
 IPP_MAX_DIM = 3
 IPP_APPEND_MAX_K = 32

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs p) {
     const uint32_t smem_base = smem_u32(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 2) * WM, wn0 = (warp & 3) * WN;
+    const int wm0 = (warp / Cfg::WARPS_N) * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
 
     int kbeg = 0, kend = p.K;
     if (p.k_from_max) kbeg = ((m0 > n0 ? m0 : n0) / BK) * BK;

@@ -25,16 +25,17 @@ struct PredictArgs {
     double* partial; int64_t ldp;
     int* counter;
     int T, Mtiles;
+    int GM;            // m-tiles per L2 group: a group's Kxt panel (GM * 128 rows) stays L2-resident during its n-tile sweep
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) predict_var_kernel(PredictArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_red[4][BM];
+    __shared__ double s_red[Cfg::WARPS_N][BM];
     __shared__ int s_item;
     const uint32_t smem_base = smem_u32(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 2) * WM, wn0 = (warp & 3) * WN;
+    const int wm0 = (warp / Cfg::WARPS_N) * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
     const int total = p.T * p.Mtiles;
 
     for (;;) {
@@ -42,8 +43,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) predict_var_kernel(PredictArg
         __syncthreads();
         const int item = s_item;
         if (item >= total) break;
-        const int I = p.T - 1 - item / p.Mtiles;
-        const int m0 = (item % p.Mtiles) * BM, n0 = I * BN;
+        // item -> (m-group, n-tile I heaviest first, m-tile within the group)
+        const int grp = item / (p.T * p.GM);
+        const int r = item - grp * p.T * p.GM;
+        const int gm = (p.Mtiles - grp * p.GM) < p.GM ? (p.Mtiles - grp * p.GM) : p.GM;
+        const int I = p.T - 1 - r / gm;
+        const int m0 = (grp * p.GM + r % gm) * BM, n0 = I * BN;
         const int ndiag_end = (n0 + BN < p.N) ? (n0 + BN) : p.N;
 
         double acc[MI][NI][2];
@@ -91,11 +96,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) predict_var_kernel(PredictArg
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (t == 0) s_red[warp & 3][wm0 + 8 * i + g] = s;
+            if (t == 0) s_red[warp % Cfg::WARPS_N][wm0 + 8 * i + g] = s;
         }
         __syncthreads();
-        if (tid < BM && m0 + tid < p.Mc)
-            p.partial[(int64_t)I * p.ldp + m0 + tid] = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
+        if (tid < BM && m0 + tid < p.Mc) {
+            double q = 0.0;
+#pragma unroll
+            for (int w = 0; w < Cfg::WARPS_N; ++w) q += s_red[w][tid];
+            p.partial[(int64_t)I * p.ldp + m0 + tid] = q;
+        }
         __syncthreads();
     }
 }
@@ -190,6 +199,13 @@ extern "C" int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, c
         p.partial = partial; p.ldp = mc_max;
         p.counter = counter;
         p.T = T; p.Mtiles = (int)((mc + BM - 1) / BM);
+        {
+            const int64_t panel = (int64_t)BM * ldk * 8;                 // bytes of one m-tile's Kxt panel
+            int64_t gm = (48LL << 20) / panel;                           // ~48 MB of the 126 MB L2 per group
+            if (gm < 1) gm = 1;
+            if (gm > p.Mtiles) gm = p.Mtiles;
+            p.GM = (int)gm;
+        }
         const int items = p.T * p.Mtiles;
         profile_mark(0, stream);
         predict_var_kernel<<<items < grid ? items : grid, GEMM_THREADS, GEMM_SMEM, stream>>>(p);
