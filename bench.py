@@ -30,6 +30,13 @@ import sys
 import threading
 import time
 
+# The CPU arm must use every host thread: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+# cripple the numpy/BLAS baseline.  Only rank 0 ever runs CPU work, so lift the limit there before numpy
+# (and its BLAS) is loaded.
+if os.environ.get('RANK', '0') == '0':
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -49,8 +49,42 @@ def ucb_beta(time):
     return 2 * np.log(d * pit / delta)
 
 
+_offsets_cache = {}
+
+
 def _single_path_offsets(k, dev):
-    return torch.tensor([0, k], dtype=torch.int64, device=dev)
+    """[0, k] as an int64 device tensor; cached (one tiny H2D per distinct k instead of one per call)."""
+    key = (int(k), dev.index)
+    t = _offsets_cache.get(key)
+    if t is None:
+        t = torch.tensor([0, k], dtype=torch.int64, device=dev)
+        _offsets_cache[key] = t
+    return t
+
+
+def reward_device(f_rew, time, xvals, robot_model, param=None):
+    """Scalar reward of one path as a 0-d CUDA tensor, WITHOUT a device->host sync (planner-internal:
+    the tree only needs the value when the rollout is back-propagated).  Returns None when the
+    reference's host-side early-outs apply (no data / no maxima), so the caller falls back to the
+    public callable."""
+    if robot_model.xvals is None:
+        return None
+    _, queries = _queries(time, xvals, robot_model)
+    xq = L.to_device(queries)
+    offs = _single_path_offsets(xq.shape[0], xq.device)
+    if f_rew == 'mean':
+        r, _ = robot_model.reward_paths_device(L.REWARD_UCB, xq, offs, params=[np.sqrt(ucb_beta(time))])
+    elif f_rew == 'exp_improve':
+        eta = 0.5 if param is None else sum(param) / len(param)
+        r, _ = robot_model.reward_paths_device(L.REWARD_EI, xq, offs, params=[float(eta)])
+    elif f_rew == 'mes':
+        if param[0] is None:
+            return None
+        maxes_d = param[0] if isinstance(param[0], torch.Tensor) else L.to_device(np.asarray(param[0], dtype=float).reshape(-1))
+        r, _ = robot_model.reward_paths_device(L.REWARD_MES, xq, offs, maxes_d=maxes_d)
+    else:
+        return None
+    return r[0]
 
 
 # ------------------------------------------------------------------------------------------ rewards

@@ -128,6 +128,79 @@ __global__ void add_scalar_kernel(double* A, int64_t rows, int64_t cols, int64_t
     if (idx < rows * cols) A[(idx / cols) * ld + idx % cols] += v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-batch path (M <= SMALL_M queries per pass): the planner's real call shape is k ~ 4 sample
+// points per path (paths_library.py:152-171), for which a 128-row DMMA tile is 97 % padding.  Here the
+// N x N operand is streamed ONCE across all SMs (HBM/L2-bound, N^2 * 8 B, half of it in the
+// symmetric / triangular forms): one warp per matrix row n, the <= 32 queries' cross-covariances are
+// accumulated in registers, t[n][m] = sum_j mat[n][j] Kxt[m][j], then reduced against Kxt[m][n] into
+// one partial per (CTA, m); a fixed-order finalize adds the partials.
+constexpr int SMALL_M = 32;
+constexpr int SMALL_ROWS_PER_CTA = 32;     // 8 warps x 4 rows
+
+template <int MT>      // MT = register tier (number of query accumulators per lane), M <= MT <= SMALL_M
+__global__ void __launch_bounds__(256) predict_var_small_kernel(const double* __restrict__ Kxt, int64_t ldk, int M,
+                                                                const double* __restrict__ mat, int64_t ldm, int N,
+                                                                int mode, double* __restrict__ partial) {
+    __shared__ double s_part[8][SMALL_M];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double cta_acc[MT];                 // lane 0 of each warp accumulates its rows' contributions
+#pragma unroll
+    for (int m = 0; m < MT; ++m) cta_acc[m] = 0.0;
+    // rows are dealt round-robin to CTAs so that the triangular forms (row n has n+1 terms) balance
+    for (int rr = warp; rr < SMALL_ROWS_PER_CTA; rr += 8) {
+        const int n = (int)blockIdx.x + rr * (int)gridDim.x;
+        if (n >= N) break;
+        const double* row = mat + (int64_t)n * ldm;
+        const int jend = (mode == IPP_VAR_WINV_FULL) ? N : (mode == IPP_VAR_CHOL ? n + 1 : n);
+        double acc[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+        for (int j = lane; j < jend; j += 32) {
+            const double w = row[j];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                if (m < M) acc[m] = fma(w, Kxt[(int64_t)m * ldk + j], acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            if (m < M) {
+                double t = acc[m];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) {
+                    const double kn = Kxt[(int64_t)m * ldk + n];
+                    double c;
+                    if (mode == IPP_VAR_CHOL) c = t * t;
+                    else if (mode == IPP_VAR_WINV_FULL) c = t * kn;
+                    else c = kn * fma(2.0, t, row[n] * kn);          // symmetric: 2 * strictly-lower + diagonal
+                    cta_acc[m] += c;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) s_part[warp][m] = cta_acc[m];
+    }
+    __syncthreads();
+    if (threadIdx.x < M) {
+        double q = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) q += s_part[w][threadIdx.x];
+        partial[(int64_t)blockIdx.x * SMALL_M + threadIdx.x] = q;
+    }
+}
+
+__global__ void predict_finalize_small_kernel(const double* __restrict__ partial, int nblocks, int M,
+                                              double variance, double noise_add, double* __restrict__ var) {
+    const int m = threadIdx.x;
+    if (m >= M) return;
+    double q = 0.0;
+    for (int b = 0; b < nblocks; ++b) q += partial[(int64_t)b * SMALL_M + m];
+    var[m] = (variance - q) + noise_add;
+}
+
 constexpr int64_t PREDICT_CHUNK = 32768;
 
 // Optional CUDA-event timing of the dominant kernel (predict_var_kernel), on the launching stream.
@@ -157,7 +230,7 @@ using namespace ipp;
 extern "C" int64_t ipp_gp_predict_workspace(int64_t N, int64_t M) {
     if (N <= 0 || M <= 0) return 16;
     const int64_t ldk = round_up(N, 16), mc = chunk_rows(M), T = (N + BN - 1) / BN;
-    return mc * ldk + T * mc + 16;
+    return mc * ldk + T * mc + N + 64;     // (+N: partials of the small-batch path)
 }
 
 extern "C" int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
@@ -184,6 +257,23 @@ extern "C" int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, c
     }
     const int64_t ldk = round_up(N, 16), mc_max = chunk_rows(M);
     const int T = (int)((N + BN - 1) / BN);
+    if (M <= 2 * SMALL_M) {                       // planner-sized batches: stream the operand once
+        double* Kxt_s = work;
+        double* part_s = work + (int64_t)round_up(M, BM) * ldk;
+        const int nblocks = (int)((N + SMALL_ROWS_PER_CTA - 1) / SMALL_ROWS_PER_CTA);
+        IPP_TRY(launch_rbf_queries(*kern, X, N, alpha, Xq, M, Kxt_s, ldk, mean, stream));
+        for (int64_t s0 = 0; s0 < M; s0 += SMALL_M) {
+            const int mm = (int)((M - s0) < SMALL_M ? (M - s0) : SMALL_M);
+            if (mm <= 8)
+                predict_var_small_kernel<8><<<nblocks, 256, 0, stream>>>(Kxt_s + s0 * ldk, ldk, mm, mat, ldm, (int)N, var_mode, part_s);
+            else
+                predict_var_small_kernel<SMALL_M><<<nblocks, 256, 0, stream>>>(Kxt_s + s0 * ldk, ldk, mm, mat, ldm, (int)N, var_mode, part_s);
+            IPP_LAUNCH_CHECK();
+            predict_finalize_small_kernel<<<1, SMALL_M, 0, stream>>>(part_s, nblocks, mm, kern->variance, noise_add, var + s0);
+            IPP_LAUNCH_CHECK();
+        }
+        return IPP_OK;
+    }
     double* Kxt = work;
     double* partial = work + mc_max * ldk;
     int* counter = reinterpret_cast<int*>(partial + (int64_t)T * mc_max);

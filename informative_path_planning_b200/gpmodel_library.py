@@ -109,6 +109,10 @@ class GPModel(object):
         self._linv_d = None        # [N][ld] L^-1 (GPy-form models only)
         self._ld = 0
         self._ig = None            # cached (binv, logdet_before) for info_gain
+        # Rollout forks may defer the "is the Schur block positive definite" read-back (a device->host
+        # sync per append) to one check per rollout: see defer_checks() / check_pending().
+        self._defer = False
+        self._pending_info = []
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -215,10 +219,25 @@ class GPModel(object):
     def train_kernel(self, xvals=None, zvals=None, kernel_file='kernel_model.npy'):
         raise NotImplementedError('GPy marginal-likelihood training is outside the accelerated hot path (SURVEY.md 8f rank 4)')
 
+    # ------------------------------------------------------------------ deferred status checks
+    def defer_checks(self, on=True):
+        """Planner-internal: postpone the per-append LinAlgError read-back; call check_pending() later."""
+        self._defer = bool(on)
+        return self
+
+    def check_pending(self):
+        """Raise numpy.linalg.LinAlgError if any append since the last check hit a non-PD Schur block."""
+        if self._pending_info:
+            bad = int(torch.stack(self._pending_info).max().item())
+            self._pending_info = []
+            if bad != 0:
+                raise np.linalg.LinAlgError('not positive definite, even with jitter.')
+
     # ------------------------------------------------------------------ copy semantics
     def __copy__(self):
         new = self.__class__.__new__(self.__class__)
         new.__dict__.update(self.__dict__)            # shares immutable device buffers: O(1) fork
+        new._pending_info = list(self._pending_info)
         if isinstance(self.model, _LegacyModelHandle):
             new.model = _LegacyModelHandle(new)
         return new
@@ -352,7 +371,9 @@ class OnlineGPModel(GPModel):
             L.check(L.lib.ipp_gp_append(ctypes.byref(self.kern._c), L.ptr(X_all), L.ptr(z_all), n_old, kb,
                                         self._diag_add(), L.ptr(winv), ld, L.ptr(w_new), ld_new, L.ptr(alpha),
                                         L.ptr(info), L.ptr(work), L.stream_ptr()))
-            if int(info.item()) != 0:
+            if self._defer:
+                self._pending_info.append(info)
+            elif int(info.item()) != 0:
                 raise np.linalg.LinAlgError('not positive definite, even with jitter.')
             winv, ld = w_new, ld_new
             done += kb

@@ -23,8 +23,10 @@ import copy
 import random
 
 import numpy as np
+import torch
 
 from . import aq_library as aqlib
+from .gpmodel_library import GPModel
 
 _PARAM_REWARDS = ('mes', 'maxs-mes', 'exp_improve', 'naive', 'naive_value')
 
@@ -70,6 +72,7 @@ class Tree(object):
         self.f_rew = f_rew
         self.aquisition_function = f_aqu
         self.c = c
+        self._maxes_d = None
         self.root = Node(pose, parent=None, name='root')
 
     def get_best_child(self):
@@ -87,9 +90,35 @@ class Tree(object):
         self.backprop(leaf, reward)
 
     def action_reward(self, xobs, belief):
+        """Reward of one action.  When the acquisition function is one of this package's own callables the
+        value stays on the device as a 0-d tensor (no host sync; the tree only needs it at back-propagation,
+        reference :352); otherwise the callable is invoked exactly as the reference does (:386-396)."""
+        fast = _FAST_REWARDS.get(self.aquisition_function)
+        if fast is not None and fast == self.f_rew and isinstance(belief, GPModel):
+            param = self.param
+            if fast == 'mes' and param is not None and param[0] is not None:
+                if self._maxes_d is None:
+                    self._maxes_d = aqlib.L.to_device(np.asarray(param[0], dtype=float).reshape(-1))
+                param = (self._maxes_d,) + tuple(param[1:])
+            r = aqlib.reward_device(fast, self.t, xobs, belief, param)
+            if r is not None:
+                return r
         if self.f_rew in _PARAM_REWARDS:
             return self.aquisition_function(time=self.t, xvals=xobs, robot_model=belief, param=self.param)
         return self.aquisition_function(time=self.t, xvals=xobs, robot_model=belief)
+
+    @staticmethod
+    def settle(reward, pending, belief):
+        """One device->host transfer for all the rewards of a rollout; summed in the reference's order
+        (reward + r level by level) so the float64 total is bit-identical to per-call accumulation."""
+        if pending:
+            dev = [r for r in pending if isinstance(r, torch.Tensor)]
+            host = iter(torch.stack(dev).cpu().numpy()) if dev else iter(())
+            for r in pending:
+                reward = reward + (next(host) if isinstance(r, torch.Tensor) else r)
+        if isinstance(belief, GPModel):
+            belief.check_pending()
+        return reward
 
     def simulate_observation(self, xobs, belief):
         n_points = xobs.shape[0]
@@ -98,10 +127,10 @@ class Tree(object):
             return np.reshape(zobs, (n_points, 1))
         return belief.posterior_samples(xobs, full_cov=False, size=1)
 
-    def _expand_action(self, node, reward, belief):
-        """One 'BA' step.  Returns (next belief node, accumulated reward)."""
+    def _expand_action(self, node, pending, belief):
+        """One 'BA' step: score the action, then extend the rollout's belief.  Returns the next belief node."""
         xobs = _xobs(node.action)
-        r = self.action_reward(xobs, belief)
+        pending.append(self.action_reward(xobs, belief))
         if node.children is not None:
             alpha = 3.0 / (10.0 * (self.max_depth - node.depth) - 3.0)
             nchild = len(node.children)
@@ -110,28 +139,32 @@ class Tree(object):
                 fewest = min(n.nqueries for n in node.children)
                 child = random.choice([n for n in node.children if n.nqueries == fewest])
                 belief.add_data(xobs, child.zvals)
-                return child, reward + r
+                return child
         zobs = self.simulate_observation(xobs, belief)
         belief.add_data(xobs, zobs)
         belief.add_data(xobs, zobs)
         child = Node(pose=node.dense_path[-1], parent=node, name=node.name + '_belief' + str(node.depth + 1),
                      zvals=zobs)
         node.add_children(child)
-        return child, reward + r
+        return child
 
     def leaf_helper(self, current_node, reward, belief):
         node = current_node
+        pending = []
+        if isinstance(belief, GPModel):
+            belief.defer_checks(True)
         while True:
             if node.node_type == 'B':
                 if node.depth == self.max_depth:
-                    return node, reward
+                    break
                 if node.children is None:
                     self.build_action_children(node)
                 if node.children is None:
-                    return node, reward
+                    break
                 node = self.get_next_child(node)
             else:
-                node, reward = self._expand_action(node, reward, belief)
+                node = self._expand_action(node, pending, belief)
+        return node, self.settle(reward, pending, belief)
 
     def get_next_child(self, current_node):
         vals = {}
@@ -165,49 +198,53 @@ class BeliefTree(Tree):
             return np.zeros((xobs.shape[0], 1))
         return belief.predict_value(xobs)[0]
 
-    def random_rollouts(self, current_node, reward, belief):
+    def random_rollouts(self, current_node, pending, belief):
         cur_depth = current_node.depth
         pose = current_node.pose
         while cur_depth <= self.max_depth:
             actions, dense_paths = self.path_generator.get_path_set(pose)
             keys = list(actions.keys())
             if len(actions) <= 1:
-                return reward
+                return
             a = np.random.randint(0, len(actions) - 1)
             xobs = _xobs(actions[keys[a]])
-            r = self.action_reward(xobs, belief)
+            pending.append(self.action_reward(xobs, belief))
             zobs = self.mle_observation(xobs, belief)
             belief.add_data(xobs, zobs)
             belief.add_data(xobs, zobs)
             pose = dense_paths[keys[a]][-1]
-            reward += r
             cur_depth += 1
-        return reward
 
     def leaf_helper(self, current_node, reward, belief):
         node = current_node
+        pending = []
+        if isinstance(belief, GPModel):
+            belief.defer_checks(True)
         while True:
             if node.node_type == 'B':
                 if node.depth == self.max_depth:
-                    return node, reward
+                    break
                 if node.children is None:
                     self.build_action_children(node)
                 if node.children is None:
-                    return node, reward
+                    break
                 child, full_action_set = self.get_next_child(node)
                 if not full_action_set:
-                    return child, self.random_rollouts(node, reward, belief)
+                    self.random_rollouts(node, pending, belief)
+                    node = child
+                    break
                 node = child
             else:
                 xobs = _xobs(node.action)
-                r = self.action_reward(xobs, belief)
+                pending.append(self.action_reward(xobs, belief))
                 zobs = self.mle_observation(xobs, belief)
                 belief.add_data(xobs, zobs)
                 belief.add_data(xobs, zobs)
                 child = Node(pose=node.dense_path[-1], parent=node,
                              name=node.name + '_belief' + str(node.depth + 1), zvals=zobs)
                 node.add_children(child)
-                node, reward = child, reward + r
+                node = child
+        return node, self.settle(reward, pending, belief)
 
     def get_next_child(self, current_node):
         vals = {}
@@ -218,6 +255,10 @@ class BeliefTree(Tree):
                 2.0 * np.log(float(current_node.nqueries)) / float(child.nqueries))
         top = max(vals.values())
         return random.choice([key for key in vals.keys() if vals[key] == top]), True
+
+
+# acquisition callables of this package that have a sync-free device form, by reward name
+_FAST_REWARDS = {aqlib.mean_UCB: 'mean', aqlib.mves: 'mes', aqlib.exp_improvement: 'exp_improve'}
 
 
 def exploration_constant(f_rew, tree_type):

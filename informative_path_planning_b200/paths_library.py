@@ -158,41 +158,86 @@ def _segment(q, length, kind):
     return (x + math.cos(th) * length, y + math.sin(th) * length, th)
 
 
+def _segment_vec(x, y, th, length, kind):
+    if kind == 'L':
+        return x + np.sin(th + length) - np.sin(th), y - np.cos(th + length) + np.cos(th), th + length
+    if kind == 'R':
+        return x - np.sin(th - length) + np.sin(th), y + np.cos(th - length) - np.cos(th), th - length
+    return x + np.cos(th) * length, y + np.sin(th) * length, th
+
+
 def dubins_sample_many(q0, word, params, rho, step):
-    """Configurations every `step` along the path (the `dubins` package's sample_many): [(x, y, heading)]."""
+    """Configurations every `step` along the path (the `dubins` package's sample_many), vectorised over the
+    arc-length samples: returns an (n, 3) array of (x, y, heading)."""
     total = sum(params) * rho
-    out = []
-    s = 0.0
-    while s < total:
-        tprime = s / rho
-        q = (0.0, 0.0, q0[2])
-        rem = tprime
-        for seg_len, kind in zip(params, word):
-            use = min(rem, seg_len)
-            q = _segment(q, use, kind)
-            rem -= use
-            if rem <= 0:
-                break
-        out.append((q[0] * rho + q0[0], q[1] * rho + q0[1], _mod2pi(q[2])))
-        s += step
+    n = int(math.ceil(total / step - 1e-12)) if total > 0 else 0
+    s = np.arange(n) * step
+    s = s[s < total]
+    rem = s / rho
+    x = np.zeros_like(rem)
+    y = np.zeros_like(rem)
+    th = np.full_like(rem, q0[2])
+    for seg_len, kind in zip(params, word):
+        use = np.clip(rem, 0.0, seg_len)
+        x, y, th = _segment_vec(x, y, th, use, kind)
+        rem = rem - use
+    out = np.empty((s.shape[0], 3))
+    out[:, 0] = x * rho + q0[0]
+    out[:, 1] = y * rho + q0[1]
+    out[:, 2] = th - 2.0 * math.pi * np.floor(th / (2.0 * math.pi))
     return out
 
 
 class Dubins_Path_Generator(Path_Generator):
-    """reference :141-189"""
+    """reference :141-189.  In the obstacle-free world the whole path set of a pose is produced by one native
+    call (ipp_dubins_path_set, the counterpart of the `dubins` C library the reference uses); obstacle worlds
+    keep the Python loop below, which is also the cross-check of the native code (tests/test_abi.py)."""
+
+    use_native = True
 
     def buffered_paths(self):
+        if self.use_native and isinstance(self.obstacle_world, FreeWorld) and len(self.goals) > 0:
+            return self._buffered_paths_native()
+        return self._buffered_paths_python()
+
+    def _buffered_paths_native(self):
+        import ctypes
+        from . import _lib as L
+        G = len(self.goals)
+        goals = np.ascontiguousarray(np.asarray(self.goals, dtype=np.float64).reshape(G, 3))
+        pose = np.ascontiguousarray(np.asarray(self.cp, dtype=np.float64).reshape(3))
+        ext = np.ascontiguousarray(np.asarray(self.extent, dtype=np.float64).reshape(4))
+        # longest shortest-Dubins path to a goal hl away: hl + a few turning circles
+        max_dense = int((self.hl + 8.0 * math.pi * self.tr) / (self.ss / 10)) + 16
+        max_samp = max_dense // 10 + 2
+        samp = np.empty((G, max_samp, 3))
+        dense = np.empty((G, max_dense, 3))
+        ns = np.zeros(G, dtype=np.int32)
+        nd = np.zeros(G, dtype=np.int32)
+        vp = ctypes.c_void_p
+        L.check(L.lib.ipp_dubins_path_set(pose.ctypes.data_as(vp), goals.ctypes.data_as(vp), G, float(self.tr),
+                                          float(self.ss / 10), 10, ext.ctypes.data_as(vp), float(3 * self.tr),
+                                          samp.ctypes.data_as(vp), ns.ctypes.data_as(vp), max_samp,
+                                          dense.ctypes.data_as(vp), nd.ctypes.data_as(vp), max_dense))
+        sampling_path, true_path = {}, {}
+        for i in range(G):
+            if ns[i] >= 2:
+                sampling_path[i] = [tuple(c) for c in samp[i, :ns[i]].tolist()]
+                true_path[i] = [tuple(c) for c in dense[i, :nd[i]].tolist()]
+        return sampling_path, true_path
+
+    def _buffered_paths_python(self):
         sampling_path, true_path = {}, {}
         ext, tr = self.extent, self.tr
+        free = isinstance(self.obstacle_world, FreeWorld)
         for i, goal in enumerate(self.goals):
             word, params = dubins_shortest_path(self.cp, goal, tr)
             fconfig = dubins_sample_many(self.cp, word, params, tr, self.ss / 10)
-            ftemp = []
-            for c in fconfig:
-                if ext[0] < c[0] < ext[1] and ext[2] < c[1] < ext[3] and not self.obstacle_world.in_obstacle((c[0], c[1]), buff=0.0):
-                    ftemp.append(c)
-                else:
-                    break
+            inside = (fconfig[:, 0] > ext[0]) & (fconfig[:, 0] < ext[1]) & (fconfig[:, 1] > ext[2]) & (fconfig[:, 1] < ext[3])
+            if not free:
+                inside &= ~np.array([self.obstacle_world.in_obstacle((c[0], c[1]), buff=0.0) for c in fconfig], dtype=bool)
+            stop = int(np.argmin(inside)) if not inside.all() else fconfig.shape[0]      # first violation ends the path
+            ftemp = [tuple(c) for c in fconfig[:stop].tolist()]
             try:
                 ttemp = ftemp[0::10]
                 for m, c in enumerate(ttemp):

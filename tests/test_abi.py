@@ -83,6 +83,16 @@ def test_paths_library_matches_oracle_generator():
     # Dubins: straight-ahead goal is a straight line of the right length; every path ends near its goal
     word, (t, p, q) = dubins_shortest_path((0, 0, 0), (4, 0, 0), 1.0)
     assert abs(t + p + q - 4.0) < 1e-12
+    # native (C, host) generator == Python generator, including the border-trimming quirk near the walls
+    for pose in ((5.0, 5.0, 0.3), (9.6, 9.5, 0.3), (0.4, 5.0, 3.0), (5.0, 0.2, -1.4), (9.9, 0.1, 2.0)):
+        a_gen = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, (0, 10, 0, 10))
+        b_gen = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, (0, 10, 0, 10))
+        b_gen.use_native = False
+        (pa, ta), (pb, tb) = a_gen.get_path_set(pose), b_gen.get_path_set(pose)
+        assert sorted(pa) == sorted(pb), pose
+        for k in pa:
+            np.testing.assert_allclose(np.array(pa[k]), np.array(pb[k]), rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(np.array(ta[k]), np.array(tb[k]), rtol=1e-12, atol=1e-12)
     g = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, (0, 10, 0, 10))
     paths, true_paths = g.get_path_set((5.0, 5.0, 0.3))
     assert len(paths) >= 10

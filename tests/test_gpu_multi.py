@@ -1,0 +1,77 @@
+"""GPU, 2 ranks over NCCL (skipped on a single-GPU box): replicated belief + sharded queries / paths give the
+same numbers as one GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import RANGES, ROOT
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _inputs():
+    rng = np.random.default_rng(42)
+    X = rng.uniform(0, 10, (500, 2))
+    z = 10 * np.sin(X[:, :1]) + rng.normal(0, 0.7, (500, 1))
+    q = rng.uniform(0, 10, (3001, 2))
+    lens = rng.integers(1, 9, 301)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    pts = rng.uniform(0.5, 9.5, (offs[-1], 2))
+    return X, z, q, pts, offs
+
+
+def _worker(rank, size, port, tmp):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=size, device_id=torch.device('cuda', rank))
+    from informative_path_planning_b200 import gpmodel_library as gp, parallel
+    X, z, q, pts, offs = _inputs()
+    out = {}
+    for mode in ('recompute', 'broadcast'):
+        m = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+        parallel.add_data_replicated(m, X[:480] if rank == 0 else None, z[:480] if rank == 0 else None, mode=mode)
+        parallel.add_data_replicated(m, X[480:] if rank == 0 else None, z[480:] if rank == 0 else None, mode=mode)
+        mu, var = parallel.predict_sharded(m, q)
+        out[mode + '_mu'], out[mode + '_var'] = mu, var
+        out[mode + '_ucb'] = parallel.reward_paths_sharded(m, 'mean', 5, pts, offs)
+        out[mode + '_mes'] = parallel.reward_paths_sharded(m, 'mes', 5, pts, offs, param=(np.array([[20.], [25.]]), None, None))
+    np.savez(os.path.join(tmp, 'rank%d.npz' % rank), **out)
+    dist.destroy_process_group()
+
+
+def test_two_ranks_match_one_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from informative_path_planning_b200 import aq_library as aq, gpmodel_library as gp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    X, z, q, pts, offs = _inputs()
+    m = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X[:480], z[:480])
+    m.add_data(X[480:], z[480:])
+    mu, var = m.predict_value(q)
+    ucb = aq.reward_paths('mean', 5, pts, m, offsets=offs)
+    mes = aq.reward_paths('mes', 5, pts, m, (np.array([[20.], [25.]]), None, None), offsets=offs)
+    r0, r1 = np.load(tmp_path / 'rank0.npz'), np.load(tmp_path / 'rank1.npz')
+    for k in r0.files:
+        np.testing.assert_array_equal(r0[k], r1[k])                  # every rank holds the same gathered result
+    for mode in ('recompute', 'broadcast'):
+        np.testing.assert_array_equal(r0[mode + '_mu'], mu)           # same kernels, same inputs: bit-identical
+        np.testing.assert_array_equal(r0[mode + '_var'], var)
+        np.testing.assert_allclose(r0[mode + '_ucb'], ucb, rtol=1e-12)
+        np.testing.assert_allclose(r0[mode + '_mes'], mes, rtol=1e-12)

@@ -1,0 +1,57 @@
+"""MCTS reward-evals/sec (BASELINE config 2 shape): dpw tree, horizon 5, 250 rollouts per planning step,
+Dubins-like straight fan paths (k~3 points), belief of N observations.  GPU-backed planner vs the CPU
+oracle planner on the same seeds (the reference prints 'Rollouts completed in ...s': mcts_library.py:689-700).
+One reward eval = one path's scalar acquisition value."""
+import contextlib, io, json, os, random, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+R = (0., 10., 0., 10.)
+
+def world(n, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 10, (n, 2))
+    z = 10 * np.sin(0.7 * X[:, :1]) * np.cos(0.5 * X[:, 1:]) + rng.normal(0, 0.7, (n, 1))
+    return X, z
+
+class CountingFn(object):
+    def __init__(self, fn): self.fn, self.n = fn, 0
+    def __call__(self, **kw):
+        self.n += 1
+        return self.fn(**kw)
+
+def run(kind, n_obs, f_rew, budget=250, depth=5):
+    X, z = world(n_obs)
+    if kind == 'gpu':
+        from informative_path_planning_b200 import aq_library as aq, gpmodel_library as gp, mcts_library as mc
+        from informative_path_planning_b200.paths_library import Dubins_Path_Generator as PG
+        model = gp.OnlineGPModel(R, 1.0, 100.0, noise=0.5); cls = mc.cMCTS
+    else:
+        from oracle import aq_oracle as aq, mcts_oracle as mc
+        from oracle.gpmodel_oracle import OnlineGPModelOracle
+        from informative_path_planning_b200.paths_library import Dubins_Path_Generator as PG
+        model = OnlineGPModelOracle(R, 1.0, 100.0, noise=0.5); cls = mc.cMCTSOracle
+    model.add_data(X, z)
+    pg = PG(15, 1.5, 0.05, 0.5, R)
+    fn = CountingFn({'mean': aq.mean_UCB, 'mes': aq.mves}[f_rew])
+    np.random.seed(5); random.seed(6)
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+        m = cls(budget, model, (5.0, 5.0, 0.3), depth, pg, fn, f_rew, 3, tree_type='dpw')
+        if f_rew == 'mes':      # max-value sampling timed separately
+            t0 = time.perf_counter(); m.choose_trajectory(t=3); dt = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter(); m.choose_trajectory(t=3); dt = time.perf_counter() - t0
+    nq = [c.nqueries for c in m.tree.root.children]
+    return {'kind': kind, 'n_obs': n_obs, 'f_rew': f_rew, 'seconds': dt, 'rollouts_per_s': budget / dt,
+            'reward_evals': fn.n, 'reward_evals_per_s': fn.n / dt, 'root_visits': nq}
+
+if __name__ == '__main__':
+    out = []
+    for n_obs in (100, 900):
+        for kind in ('gpu', 'cpu'):
+            if kind == 'gpu': run(kind, n_obs, 'mean', budget=20)      # warm-up (module load, allocator)
+            r = run(kind, n_obs, 'mean'); out.append(r); print(json.dumps(r))
+    same = out[0]['root_visits'] == out[1]['root_visits'], out[2]['root_visits'] == out[3]['root_visits']
+    print('same root visit counts (gpu vs cpu planner):', same)
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(out, open('gpurun_out/mcts_bench.json', 'w'), indent=1)
