@@ -330,6 +330,46 @@ def main():
             torch.cuda.synchronize()
             extras['reward_evals_per_s_' + name] = P * 2 / (r0.elapsed_time(r1) / 1e3)
         extras['reward_workload'] = '%d paths x %d points, N=4096 (BASELINE config 5 shape on 1 GPU)' % (P, k)
+        # tree search (BASELINE config 2 shape): dpw, horizon 5, 250 rollouts, Dubins fan, N=900 observations;
+        # GPU-backed planner vs the CPU oracle planner on the same seeds (identical visit counts expected)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import bench_mcts
+            bench_mcts.run('gpu', 900, 'mean', budget=20)
+            g_ = bench_mcts.run('gpu', 900, 'mean')
+            c_ = bench_mcts.run('cpu', 900, 'mean')
+            extras['mcts_N900_dpw_ucb'] = {
+                'reward_evals_per_s': g_['reward_evals_per_s'], 'rollouts_per_s': g_['rollouts_per_s'],
+                'cpu_reward_evals_per_s': c_['reward_evals_per_s'], 'cpu_rollouts_per_s': c_['rollouts_per_s'],
+                'same_root_visit_counts': g_['root_visits'] == c_['root_visits']}
+        except Exception as e:      # measurement extra only
+            extras['mcts_N900_dpw_ucb'] = {'error': repr(e)}
+        # max-value sampling (BASELINE config 4): F=1000 shared features x S=100 samples on a 2^20-point grid
+        try:
+            F_, S_, G_ = 1000, 100, 1 << 20
+            r4 = np.random.default_rng(4)
+            W4 = r4.normal(size=(F_, 2)); b4 = 2 * np.pi * r4.uniform(size=(F_, 1)); T4 = r4.normal(size=(F_, S_))
+            g1 = r4.uniform(1, 9, 1024); g2 = r4.uniform(1, 9, 1024)
+            gx, gy = np.meshgrid(g1, g2)
+            grid_d = L.to_device(np.vstack([gx.ravel(), gy.ravel()]).T)
+            aq.rff_eval_argmax_shared(W4, b4, T4, 100.0, grid_d)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            aq.rff_eval_argmax_shared(W4, b4, T4, 100.0, grid_d)
+            r1.record()
+            torch.cuda.synchronize()
+            ms4 = r0.elapsed_time(r1)
+            gs = 1 << 15
+            sub = np.vstack([gx.ravel(), gy.ravel()]).T[:gs]
+            t0 = time.perf_counter()
+            vals = (T4.T * np.sqrt(2 * 100.0 / F_)) @ np.cos(W4 @ sub.T + b4)
+            vals.argmax(axis=1)
+            dt4 = time.perf_counter() - t0
+            extras['rff_F1000_S100_G2^20'] = {'ms': ms4, 'grid_points_per_s': G_ / (ms4 / 1e3),
+                                              'cpu_grid_points_per_s': gs / dt4, 'cpu_sample': '%d grid points, numpy' % gs}
+        except Exception as e:
+            extras['rff_F1000_S100_G2^20'] = {'error': repr(e)}
         line['extra'] = extras
     print(json.dumps(line))
     if world > 1:

@@ -441,3 +441,92 @@ def test_full_size_properties(pkg):
     mu_o, var_o = o.predict_value(xq[:512].cpu().numpy())
     np.testing.assert_allclose(mean[:512].cpu().numpy().reshape(-1, 1), mu_o, rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(var[:512].cpu().numpy().reshape(-1, 1), var_o, rtol=RTOL)
+
+
+# ------------------------------------------------------------------ more edge cases
+@pytest.mark.parametrize('M', [1, 7, 8, 9, 32, 33, 64, 65, 128, 129])
+def test_small_batch_path_equals_tile_path(pkg, M):
+    """The streaming small-batch kernel (M <= 64) and the DMMA tile kernel give the same posterior."""
+    _, gpo, _ = _oracle()
+    rng = np.random.default_rng(M)
+    X, z = world(rng, 777, 0.5)
+    d = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    d.add_data(X, z)
+    o.add_data(X, z)
+    q = rng.uniform(0, 10, (M, 2))
+    mu_d, var_d = d.predict_value(q)
+    mu_o, var_o = o.predict_value(q)
+    np.testing.assert_allclose(mu_d, mu_o, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(var_d, var_o, rtol=RTOL)
+    big = np.vstack([q, rng.uniform(0, 10, (200, 2))])               # same points through the tile kernel
+    np.testing.assert_allclose(d.predict_value(big)[1][:M], var_d, rtol=1e-9)
+    g = pkg.GPModel(RANGES, 1.0, 100.0, noise=0.5)                   # Cholesky form, small path
+    g.add_data(X, z)
+    np.testing.assert_allclose(g.predict_value(q)[1], var_o, rtol=RTOL)
+
+
+def test_space_time_kernel_d3(pkg):
+    """D = 3 ARD path (gpmodel_library.py:55-59): time column appended by the rewards (aq_library.py:43-44)."""
+    aqo, gpo, _ = _oracle()
+    rng = np.random.default_rng(33)
+    X = np.hstack([rng.uniform(0, 10, (150, 2)), rng.integers(0, 20, (150, 1)).astype(float)])
+    z = rng.normal(0, 5, (150, 1))
+    ls = (1.0, 1.0, 10.0)
+    d = pkg.OnlineGPModel(RANGES, ls, 100.0, noise=0.5, dimension=3)
+    o = gpo.OnlineGPModelOracle(RANGES, ls, 100.0, noise=0.5, dimension=3)
+    d.add_data(X[:140], z[:140]); o.add_data(X[:140], z[:140])
+    d.add_data(X[140:], z[140:]); o.add_data(X[140:], z[140:])
+    q = np.hstack([rng.uniform(0, 10, (90, 2)), np.full((90, 1), 12.0)])
+    np.testing.assert_allclose(d.predict_value(q)[0], o.predict_value(q)[0], rtol=RTOL, atol=1e-8)
+    np.testing.assert_allclose(d.predict_value(q)[1], o.predict_value(q)[1], rtol=RTOL)
+    path = rng.uniform(1, 9, (5, 3))
+    np.testing.assert_allclose(pkg.aq_library.mean_UCB(time=12, xvals=path, robot_model=d),
+                               aqo.mean_UCB(12, path, o), rtol=RTOL)
+    with pytest.raises(AssertionError):
+        d.predict_value(q[:, :2])
+
+
+def test_linalg_error_on_indefinite_append(pkg):
+    """A Schur block that is not positive definite even with GPy's jitter ladder raises LinAlgError."""
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=-60.0)           # negative 'noise' makes K + noise I indefinite
+    with pytest.raises(np.linalg.LinAlgError):
+        m.add_data(np.array([[1.0, 1.0], [1.2, 1.0], [5.0, 5.0]]), np.zeros((3, 1)))
+    ok = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    ok.add_data(np.array([[1.0, 1.0], [5.0, 5.0]]), np.zeros((2, 1)))
+    ok.noise = -150.0
+    with pytest.raises(np.linalg.LinAlgError):
+        ok.add_data(np.array([[1.0, 1.1]]), np.zeros((1, 1)))
+
+
+def test_rff_per_sample_features_and_values(pkg):
+    """Per-sample (W, b) mode of ipp_rff_eval_argmax (the reference's sampling scheme) incl. the values output."""
+    L = pkg._lib
+    rng = np.random.default_rng(8)
+    F, S, G = 50, 3, 1000
+    W, b, th = rng.normal(size=(S, F, 2)), rng.uniform(0, 6.28, (S, F)), rng.normal(size=(S, F))
+    grid = rng.uniform(0, 10, (G, 2))
+    W_d, b_d, th_d, g_d = L.to_device(W), L.to_device(b), L.to_device(th), L.to_device(grid)
+    vals = torch.empty((S, G), dtype=torch.float64, device='cuda')
+    mx = torch.empty(S, dtype=torch.float64, device='cuda')
+    am = torch.empty(S, dtype=torch.int64, device='cuda')
+    work = torch.empty(L.lib.ipp_rff_workspace(S, G), dtype=torch.float64, device='cuda')
+    L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, 2, 0, L.ptr(g_d), G, L.ptr(vals), L.ptr(mx),
+                                      L.ptr(am), L.ptr(work), L.stream_ptr()))
+    want = np.stack([th[s] @ np.cos(W[s] @ grid.T + b[s][:, None]) for s in range(S)])
+    np.testing.assert_allclose(vals.cpu().numpy(), want, rtol=1e-10, atol=1e-10)
+    np.testing.assert_array_equal(am.cpu().numpy(), want.argmax(1))
+
+
+def test_big_block_append_splits(pkg):
+    """k > IPP_APPEND_MAX_K is applied as consecutive blocks of <= 32 points (same posterior as the oracle's one block)."""
+    _, gpo, _ = _oracle()
+    rng = np.random.default_rng(77)
+    X, z = world(rng, 190, 0.5)
+    d = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    d.add_data(X[:100], z[:100]); o.add_data(X[:100], z[:100])
+    d.add_data(X[100:], z[100:]); o.add_data(X[100:], z[100:])      # 90 points at once
+    q = rng.uniform(0, 10, (50, 2))
+    np.testing.assert_allclose(d.predict_value(q)[0], o.predict_value(q)[0], rtol=RTOL, atol=1e-8)
+    np.testing.assert_allclose(d.predict_value(q)[1], o.predict_value(q)[1], rtol=RTOL)
