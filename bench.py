@@ -120,6 +120,26 @@ def cpu_predict_rate(X, z, sample, repeats=1):
     return sample / best, best, t_factor
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of predict_var_kernel, from the committed
+    `ncu --set full` capture of this kernel (profiles/, newest round first); None if no capture is present."""
+    import csv
+    import glob
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*ncu_full_predict_var_kernel.csv')), reverse=True):
+        try:
+            tot = 0.0
+            for r in csv.reader(open(path)):
+                if r and r[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                    vals = [float(v) for v in r[2:]]
+                    tot += scale[r[1]] * sum(vals) / len(vals)
+            if tot > 0:
+                return tot, os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -270,9 +290,12 @@ def main():
     dgemm_tflops = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
+    traffic, traffic_src = ncu_traffic_bytes()
+    if chunk != 32768:
+        traffic, traffic_src = None, None          # the capture is of a full 32768-query launch
     roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tflops, 'unit': 'TFLOP/s',
-        'frac': (achieved / dgemm_tflops) if achieved else None, 'traffic': None,
+        'frac': (achieved / dgemm_tflops) if achieved else None, 'traffic': traffic, 'traffic_source': traffic_src,
         'kernel': 'predict_var_kernel (FP64 DMMA.8x8x4, symmetric-half form: executed flops only)',
         'kernel_ms': kernel_ms, 'kernel_launches_timed': int(launches.value), 'kernel_share_of_step': tot_ms.value / ms_total,
         'flops_per_launch': flops_launch,

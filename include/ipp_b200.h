@@ -131,8 +131,10 @@ int ipp_reward_paths(int kind, const double* mean, const double* var, const int6
  *      f_s(x) = sum_f theta[s][f] * cos(W_s[f] . x + b_s[f]); theta is pre-scaled by sqrt(2 variance / F).
  *      shared_w != 0: one (W[F][D], b[F]) for all S samples; else W[S][F][D], b[S][F].
  *      values (may be NULL): [S][G] function values.  max_val[S], arg_max[S] (first index of the max, like np.argmax).
- *      work: ipp_rff_workspace(S, G) doubles. */
-int64_t ipp_rff_workspace(int64_t S, int64_t G);
+ *      Shared features with S >= 8 run as phi(grid) Theta^T on the FP64 tensor path with the arg-max fused into the
+ *      GEMM epilogue; otherwise a SIMT kernel (per-sample features are cos-bound, no contraction to share).
+ *      work: ipp_rff_workspace(F, S, G, shared_w) doubles. */
+int64_t ipp_rff_workspace(int64_t F, int64_t S, int64_t G, int shared_w);
 int ipp_rff_eval_argmax(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
                         int shared_w, const double* grid, int64_t G, double* values,
                         double* max_val, int64_t* arg_max, double* work, void* stream);

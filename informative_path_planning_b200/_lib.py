@@ -53,7 +53,7 @@ SIGNATURES = {
     'ipp_gp_predict_cov_workspace': (_I64, [_I64, _I64]),
     'ipp_gp_predict_cov': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _D, _P, _I64, _P, _P, _I64, _P, _P]),
     'ipp_reward_paths': (_INT, [_INT, _P, _P, _P, _I64, _P, _INT, _P, _I64, _P, _P, _I64, _P]),
-    'ipp_rff_workspace': (_I64, [_I64, _I64]),
+    'ipp_rff_workspace': (_I64, [_I64, _I64, _I64, _INT]),
     'ipp_rff_eval_argmax': (_INT, [_P, _P, _P, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
     'ipp_dgemm_nt': (_INT, [_I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, _P, _I64, _P]),

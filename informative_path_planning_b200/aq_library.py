@@ -291,7 +291,7 @@ class RFFTarget(object):
         vals = torch.empty(G, dtype=torch.float64, device=x_d.device) if want_values else None
         mx = torch.empty(1, dtype=torch.float64, device=x_d.device)
         am = torch.empty(1, dtype=torch.int64, device=x_d.device)
-        work = L.workspace(L.lib.ipp_rff_workspace(1, G), slot='rff')
+        work = L.workspace(L.lib.ipp_rff_workspace(self.nFeatures, 1, G, 0), slot='rff')
         L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), self.nFeatures, 1, D, 0, L.ptr(x_d), G,
                                           L.ptr(vals), L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
         return vals, mx, am
@@ -464,7 +464,7 @@ def rff_eval_argmax_shared(W, b, Theta, variance, grid_d):
     th_d = L.to_device(np.ascontiguousarray(Theta.T) * scale)            # [S][F]
     mx = torch.empty(S, dtype=torch.float64, device=grid_d.device)
     am = torch.empty(S, dtype=torch.int64, device=grid_d.device)
-    work = L.workspace(L.lib.ipp_rff_workspace(S, G), slot='rff')
+    work = L.workspace(L.lib.ipp_rff_workspace(F, S, G, 1), slot='rff')
     W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))     # keep both alive until the launch is enqueued
     L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, D, 1,
                                       L.ptr(grid_d), G, None, L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))

@@ -510,7 +510,7 @@ def test_rff_per_sample_features_and_values(pkg):
     vals = torch.empty((S, G), dtype=torch.float64, device='cuda')
     mx = torch.empty(S, dtype=torch.float64, device='cuda')
     am = torch.empty(S, dtype=torch.int64, device='cuda')
-    work = torch.empty(L.lib.ipp_rff_workspace(S, G), dtype=torch.float64, device='cuda')
+    work = torch.empty(L.lib.ipp_rff_workspace(F, S, G, 0), dtype=torch.float64, device='cuda')
     L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, 2, 0, L.ptr(g_d), G, L.ptr(vals), L.ptr(mx),
                                       L.ptr(am), L.ptr(work), L.stream_ptr()))
     want = np.stack([th[s] @ np.cos(W[s] @ grid.T + b[s][:, None]) for s in range(S)])
@@ -530,3 +530,27 @@ def test_big_block_append_splits(pkg):
     q = rng.uniform(0, 10, (50, 2))
     np.testing.assert_allclose(d.predict_value(q)[0], o.predict_value(q)[0], rtol=RTOL, atol=1e-8)
     np.testing.assert_allclose(d.predict_value(q)[1], o.predict_value(q)[1], rtol=RTOL)
+
+
+@pytest.mark.parametrize('F,S,G', [(101, 130, 40000), (200, 8, 129), (1000, 100, 4096), (37, 3, 700)])
+def test_rff_shared_gemm_path_values_and_argmax(pkg, F, S, G):
+    """Shared-feature max-value sampling as phi(grid) Theta^T on the DMMA path with the arg-max fused into the
+    epilogue (S >= 8; S = 3 stays on the SIMT kernel): odd F, S spanning two 128-column tiles, a grid spanning
+    two Phi chunks, and the optional values output -- against numpy (general_target, aq_library.py:138-139)."""
+    L = pkg._lib
+    rng = np.random.default_rng(F + S)
+    W, b, th = rng.normal(size=(F, 2)), rng.uniform(0, 6.28, F), rng.normal(size=(S, F))
+    grid = rng.uniform(0, 10, (G, 2))
+    W_d, b_d, th_d, g_d = L.to_device(W), L.to_device(b), L.to_device(th), L.to_device(grid)
+    vals = torch.empty((S, G), dtype=torch.float64, device='cuda')
+    mx = torch.empty(S, dtype=torch.float64, device='cuda')
+    am = torch.empty(S, dtype=torch.int64, device='cuda')
+    work = torch.empty(L.lib.ipp_rff_workspace(F, S, G, 1), dtype=torch.float64, device='cuda')
+    want = th @ np.cos(W @ grid.T + b[:, None])
+    for v in (vals, None):
+        mx.zero_(); am.zero_()
+        L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, 2, 1, L.ptr(g_d), G, L.ptr(v),
+                                          L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
+        np.testing.assert_array_equal(am.cpu().numpy(), want.argmax(1))
+        np.testing.assert_allclose(mx.cpu().numpy(), want.max(1), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(vals.cpu().numpy(), want, rtol=1e-10, atol=1e-9)
