@@ -360,11 +360,15 @@ def main():
             import bench_mcts
             bench_mcts.run('gpu', 900, 'mean', budget=20)
             g_ = bench_mcts.run('gpu', 900, 'mean')
+            bench_mcts.run('gpu', 900, 'mean', budget=20, fuse=False)
+            p_ = bench_mcts.run('gpu', 900, 'mean', fuse=False)
             c_ = bench_mcts.run('cpu', 900, 'mean')
             extras['mcts_N900_dpw_ucb'] = {
                 'reward_evals_per_s': g_['reward_evals_per_s'], 'rollouts_per_s': g_['rollouts_per_s'],
+                'per_level_calls_reward_evals_per_s': p_['reward_evals_per_s'],
                 'cpu_reward_evals_per_s': c_['reward_evals_per_s'], 'cpu_rollouts_per_s': c_['rollouts_per_s'],
-                'same_root_visit_counts': g_['root_visits'] == c_['root_visits']}
+                'same_root_visit_counts': g_['root_visits'] == c_['root_visits'] == p_['root_visits'],
+                'note': 'one device call per rollout (ipp_rollout_rewards) vs one reward + two add_data per level'}
         except Exception as e:      # measurement extra only
             extras['mcts_N900_dpw_ucb'] = {'error': repr(e)}
         # max-value sampling (BASELINE config 4): F=1000 shared features x S=100 samples on a 2^20-point grid

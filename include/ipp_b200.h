@@ -82,7 +82,8 @@ int ipp_pdinv(double* A, int64_t N, int64_t lda, double* winv, double* linv, int
               double* logdet, int32_t* info, double* work, void* stream);
 
 /* ---- a4: OnlineGPModel.update_model, gpmodel_library.py:230-279 (block-inverse append of k points).
- *      Reads winv_old [N][ldw_old], writes winv_new [(N+k)][ldw_new] and alpha_new [N+k] = winv_new @ z_all.
+ *      Reads winv_old [N][ldw_old] (must be symmetric, as ipp_gp_factor / ipp_gp_append produce it), writes
+ *      winv_new [(N+k)][ldw_new] (bitwise symmetric) and alpha_new [N+k] = winv_new @ z_all.
  *      X_all/z_all hold the N old rows followed by the k new ones.  k <= IPP_APPEND_MAX_K.
  *      work: ipp_gp_append_workspace(N, k) doubles.  info as in ipp_gp_factor (Schur block not PD). */
 #define IPP_APPEND_MAX_K 32
@@ -125,6 +126,29 @@ int ipp_gp_predict_cov(const ipp_rbf* kern, const double* X, int64_t N, const do
 int ipp_reward_paths(int kind, const double* mean, const double* var, const int64_t* offsets, int64_t P,
                      const double* params_host, int n_params, const double* maxes_dev, int64_t S,
                      double* reward, double* point_out, int64_t M, void* stream);
+
+/* ---- a12 (batching seam): all rewards of ONE tree-search rollout in a single call.
+ *      Replaces, per rollout, the L reward calls and the <= 2 L add_data calls that Tree.leaf_helper /
+ *      BeliefTree.leaf_helper make on a per-rollout copy of the belief (mcts_library.py:383-430, :570-609).
+ *      Level l scores its sample points under the belief = base + the observation blocks of levels < l, each
+ *      appended reps[l'] times (2 for a newly created child -- the reference adds it twice, :426 & :430 -- 1 for a
+ *      re-used child, :413).  The base belief (X, alpha, winv) is NOT modified.
+ *        pts  [M][D], zobs [M]   device; level l owns rows [offsets[l], offsets[l+1]);  M = offsets[L]
+ *        offsets[L+1], reps[L]   host int32
+ *        kind / params_host / maxes_dev / S as in ipp_reward_paths;  reward [L] device
+ *        noise_pred   added to every predictive variance (predict_value(include_noise=True): the model's noise)
+ *        diag_add     noise + 1e-8, the diagonal added to each appended block (gpmodel_library.py:254)
+ *        info [1]     0 = ok, l+1 = level l's block was not positive definite (caller falls back to add_data)
+ *      work: ipp_rollout_workspace(N, M) doubles. */
+#define IPP_ROLLOUT_MAX_POINTS 128
+#define IPP_ROLLOUT_MAX_LEVELS 32
+int64_t ipp_rollout_workspace(int64_t N, int64_t M);
+int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                        const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                        int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
+                        const double* pts, const double* zobs, const int32_t* offsets_host,
+                        const int32_t* reps_host, int L, double* reward, int32_t* info,
+                        double* work, void* stream);
 
 /* ---- a11: random-Fourier-feature function samples on a grid + per-sample arg-max
  *      (general_target aq_library.py:138-139 and the grid stage of global_maximization :475-479).

@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get('IPP_B200_LIB') or os.path.join(_HERE, 'csrc', 'libipp
 
 IPP_MAX_DIM = 3
 IPP_APPEND_MAX_K = 32
+IPP_ROLLOUT_MAX_POINTS = 128
+IPP_ROLLOUT_MAX_LEVELS = 32
 REWARD_UCB, REWARD_EI, REWARD_MES = 0, 1, 2
 VAR_WINV_SYM, VAR_WINV_FULL, VAR_CHOL = 0, 1, 2
 
@@ -53,6 +55,9 @@ SIGNATURES = {
     'ipp_gp_predict_cov_workspace': (_I64, [_I64, _I64]),
     'ipp_gp_predict_cov': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _D, _P, _I64, _P, _P, _I64, _P, _P]),
     'ipp_reward_paths': (_INT, [_INT, _P, _P, _P, _I64, _P, _INT, _P, _I64, _P, _P, _I64, _P]),
+    'ipp_rollout_workspace': (_I64, [_I64, _I64]),
+    'ipp_rollout_rewards': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _D, _D, _INT, _P, _INT, _P, _I64, _P, _P, _P, _P, _INT, _P, _P,
+                                   _P, _P]),
     'ipp_rff_workspace': (_I64, [_I64, _I64, _I64, _INT]),
     'ipp_rff_eval_argmax': (_INT, [_P, _P, _P, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),

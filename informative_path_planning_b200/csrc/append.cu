@@ -1,14 +1,16 @@
 // a4: OnlineGPModel.update_model (gpmodel_library.py:230-279) -- block-inverse append of k <= 32 points.
 //
-//   Q = K(X_old, X_new) (N x k),  S = K(X_new, X_new)
-//   V  = P Q         (N x k)      Vt[j][a] = sum_i P[i][j] Q[i][a]   (= (R P)^T; equals V when P is symmetric)
-//   M  = pdinv(S - Vt^T Q + diag_add I)                               (:252-255)
-//   Pnew = P + (V M) Vt^T,  Qnew = -(V M),  Rnew = -M Vt^T,  Snew = M (:257-265)
+//   Q = K(X_old, X_new) (N x k),  S = K(X_new, X_new),  P = the current inverse (symmetric), R = Q^T
+//   V  = P Q         (N x k)                                          (= (R P)^T because P is symmetric)
+//   M  = pdinv(S - V^T Q + diag_add I) = Li^T Li                      (:252-255; Li = inverse Cholesky factor)
+//   Pnew = P + V M V^T,  Qnew = -(V M),  Rnew = Qnew^T,  Snew = M     (:257-265)
 //   alpha = Wnew z                                                    (:273, full recompute like the reference)
 //
-// The reference evaluates Pnew as ((((P Q) M) R) P), an O(N^3) product; here the same four factors are
-// associated as (P Q M)(R P), O(N^2 k).  Every pass over the N x N inverse is a coalesced HBM stream
-// (read P twice for V / Vt, read P + write Pnew once, read Wnew once for alpha).
+// The reference evaluates Pnew as ((((P Q) M) R) P), an O(N^3) product; here the same factors are associated
+// as U U^T with U = V Li^T (N x k), O(N^2 k), which makes Pnew EXACTLY symmetric (fma(U_ia, U_ja, s) commutes),
+// like pdinv's symmetrified output: the symmetric-half variance form of predict (IPP_VAR_WINV_SYM) relies on
+// it -- an asymmetry of 1e-11 in W^-1 is amplified by |k*|^2 ~ 1e4 into the posterior variance.  Every pass over
+// the N x N inverse is a coalesced HBM stream (read P for V, read P + write Pnew, read Wnew once for alpha).
 #include "internal.cuh"
 
 namespace ipp {
@@ -43,47 +45,7 @@ __global__ void __launch_bounds__(256) append_pq_kernel(const double* __restrict
     }
 }
 
-// Vt[j][a] = sum_i P[i][j] Q[i][a]: block = 32 columns x 8 row phases, coalesced 256-byte row reads
-__global__ void __launch_bounds__(256) append_ptq_kernel(const double* __restrict__ P, int64_t ldp, int64_t N, int k,
-                                                         const double* __restrict__ Q, double* __restrict__ Vt) {
-    __shared__ double red[8][32][9];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
-    double acc[KMAX];
-#pragma unroll
-    for (int a = 0; a < KMAX; ++a) acc[a] = 0.0;
-    if (j < N) {
-        for (int64_t i = ty; i < N; i += 8) {
-            const double pv = P[i * ldp + j];
-            const double* q = Q + i * KMAX;
-#pragma unroll
-            for (int a = 0; a < KMAX; ++a)
-                if (a < k) acc[a] = fma(pv, q[a], acc[a]);
-        }
-    }
-    // reduce the 8 row phases, 8 columns of Vt at a time (keeps static shared memory under 48 KB)
-#pragma unroll
-    for (int ch = 0; ch < KMAX / 8; ++ch) {
-        if (ch * 8 < k) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a) red[ty][tx][a] = acc[ch * 8 + a];
-            __syncthreads();
-            {
-                const int c = threadIdx.x >> 3, a = threadIdx.x & 7;      // 32 columns x 8 entries
-                const int64_t jj = (int64_t)blockIdx.x * 32 + c;
-                if (jj < N && ch * 8 + a < k) {
-                    double sum = 0.0;
-#pragma unroll
-                    for (int y = 0; y < 8; ++y) sum += red[y][c][a];
-                    Vt[jj * KMAX + ch * 8 + a] = sum;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// G[a][b] = sum_j Vt[j][a] Q[j][b]: one warp per (a, b)
+// G[a][b] = sum_j V[j][a] Q[j][b]: one warp per (a, b)
 __global__ void __launch_bounds__(256) append_gram_kernel(const double* __restrict__ Vt, const double* __restrict__ Q,
                                                           int64_t N, int k, double* __restrict__ G) {
     const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -101,7 +63,7 @@ __global__ void __launch_bounds__(256) append_gram_kernel(const double* __restri
 // (linalg.py: up to 5 retries with jitter mean(diag) * 1e-6 * 10^i).  One warp; lane = row.
 __global__ void __launch_bounds__(32) append_schur_inverse_kernel(const double* __restrict__ S, const double* __restrict__ G,
                                                                   int k, double diag_add, double* __restrict__ Mout,
-                                                                  int32_t* info) {
+                                                                  double* __restrict__ Liout, int32_t* info) {
     __shared__ double a0[KMAX][KMAX + 1], a[KMAX][KMAX + 1], li[KMAX][KMAX + 1];
     __shared__ int bad;
     const int r = threadIdx.x;
@@ -160,41 +122,43 @@ __global__ void __launch_bounds__(32) append_schur_inverse_kernel(const double* 
             Mout[r * KMAX + c] = s;
             Mout[c * KMAX + r] = s;
         }
+        for (int c = 0; c < k; ++c) Liout[r * KMAX + c] = li[r][c];
     }
 }
 
-// VM[i][b] = sum_a V[i][a] M[a][b];  MVt[j][a] = sum_b M[a][b] Vt[j][b]
-__global__ void __launch_bounds__(256) append_apply_m_kernel(const double* __restrict__ V, const double* __restrict__ Vt,
+// U[i][a] = sum_b V[i][b] Li[a][b]  (U = V Li^T, so V M V^T = U U^T);  VM[i][b] = sum_a V[i][a] M[a][b]
+__global__ void __launch_bounds__(256) append_apply_m_kernel(const double* __restrict__ V, const double* __restrict__ Li,
                                                              const double* __restrict__ Mm, int64_t N, int k,
-                                                             double* __restrict__ VM, double* __restrict__ MVt) {
-    __shared__ double m[KMAX][KMAX + 1];
-    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) m[idx / k][idx % k] = Mm[(idx / k) * KMAX + idx % k];
+                                                             double* __restrict__ U, double* __restrict__ VM) {
+    __shared__ double m[KMAX][KMAX + 1], li[KMAX][KMAX + 1];
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+        m[idx / k][idx % k] = Mm[(idx / k) * KMAX + idx % k];
+        li[idx / k][idx % k] = Li[(idx / k) * KMAX + idx % k];
+    }
     __syncthreads();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * k) return;
     const int64_t i = idx / k;
     const int b = (int)(idx % k);
     double s = 0.0, u = 0.0;
-    for (int a = 0; a < k; ++a) {
-        s = fma(V[i * KMAX + a], m[a][b], s);
-        u = fma(m[b][a], Vt[i * KMAX + a], u);
-    }
+    for (int a = 0; a < k; ++a) s = fma(V[i * KMAX + a], m[a][b], s);
+    for (int a = 0; a <= b; ++a) u = fma(V[i * KMAX + a], li[b][a], u);       // Li is lower triangular
     VM[i * KMAX + b] = s;
-    MVt[i * KMAX + b] = u;
+    U[i * KMAX + b] = u;
 }
 
-// Wnew: 64 x 64 output tile per block; rank-k term from shared-memory panels
+// Wnew: 64 x 64 output tile per block; rank-k term U U^T from shared-memory panels (bitwise symmetric)
 __global__ void __launch_bounds__(256) append_update_kernel(const double* __restrict__ P, int64_t ldp, int64_t N, int k,
-                                                            const double* __restrict__ VM, const double* __restrict__ Vt,
-                                                            const double* __restrict__ MVt, const double* __restrict__ Mm,
+                                                            const double* __restrict__ U, const double* __restrict__ VM,
+                                                            const double* __restrict__ Mm,
                                                             double* __restrict__ Wn, int64_t ldn) {
-    __shared__ double svm[64][KMAX + 1], svt[64][KMAX + 1];
+    __shared__ double sui[64][KMAX + 1], suj[64][KMAX + 1];
     const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
     const int64_t NT = N + k;
     for (int idx = threadIdx.x; idx < 64 * k; idx += blockDim.x) {
         const int r = idx / k, a = idx % k;
-        svm[r][a] = (i0 + r < N) ? VM[(i0 + r) * KMAX + a] : 0.0;
-        svt[r][a] = (j0 + r < N) ? Vt[(j0 + r) * KMAX + a] : 0.0;
+        sui[r][a] = (i0 + r < N) ? U[(i0 + r) * KMAX + a] : 0.0;
+        suj[r][a] = (j0 + r < N) ? U[(j0 + r) * KMAX + a] : 0.0;
     }
     __syncthreads();
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 columns x 4 row phases
@@ -206,12 +170,12 @@ __global__ void __launch_bounds__(256) append_update_kernel(const double* __rest
         double v;
         if (i < N && j < N) {
             double s = 0.0;
-            for (int a = 0; a < k; ++a) s = fma(svm[r][a], svt[tx][a], s);
-            v = P[i * ldp + j] + s;
+            for (int a = 0; a < k; ++a) s = fma(sui[r][a], suj[tx][a], s);
+            v = P[i * ldp + j] + s;                            // P bitwise symmetric in => Wnew bitwise symmetric out
         } else if (i < N) {
             v = -VM[i * KMAX + (j - N)];                       // Qnew = -(P Q) M
         } else if (j < N) {
-            v = -MVt[j * KMAX + (i - N)];                      // Rnew = -M (R P)
+            v = -VM[j * KMAX + (i - N)];                       // Rnew = Qnew^T
         } else {
             v = Mm[(i - N) * KMAX + (j - N)];                  // Snew = M
         }
@@ -225,7 +189,7 @@ using namespace ipp;
 
 extern "C" int64_t ipp_gp_append_workspace(int64_t N, int64_t k) {
     (void)k;
-    return 5 * (N + KMAX) * KMAX + 3 * KMAX * KMAX + 64;
+    return 5 * (N + KMAX) * KMAX + 4 * KMAX * KMAX + 64;
 }
 
 extern "C" int ipp_gp_append(const ipp_rbf* kern, const double* X_all, const double* z_all, int64_t N, int64_t k,
@@ -241,28 +205,27 @@ extern "C" int ipp_gp_append(const ipp_rbf* kern, const double* X_all, const dou
     const double* Xnew = X_all + N * D;
     double* Q = work;                          // [N][KMAX]
     double* V = Q + (N + KMAX) * KMAX;
-    double* Vt = V + (N + KMAX) * KMAX;
-    double* VM = Vt + (N + KMAX) * KMAX;
-    double* MVt = VM + (N + KMAX) * KMAX;
+    double* U = V + (N + KMAX) * KMAX;
+    double* VM = U + (N + KMAX) * KMAX;
+    double* MVt = VM + (N + KMAX) * KMAX;      // (spare panel)
     double* S = MVt + (N + KMAX) * KMAX;       // [KMAX][KMAX]
     double* G = S + KMAX * KMAX;
     double* Mm = G + KMAX * KMAX;
+    double* Li = Mm + KMAX * KMAX;
     IPP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
     IPP_TRY(launch_rbf_cross(*kern, X_all, N, Xnew, k, Q, KMAX, s));
     IPP_TRY(launch_rbf_cross(*kern, Xnew, k, Xnew, k, S, KMAX, s));
     append_pq_kernel<<<(unsigned)((N + 7) / 8), 256, 0, s>>>(winv_old, ldw_old, N, (int)k, Q, V);
     IPP_LAUNCH_CHECK();
-    append_ptq_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(winv_old, ldw_old, N, (int)k, Q, Vt);
+    append_gram_kernel<<<(unsigned)((k * k + 7) / 8), 256, 0, s>>>(V, Q, N, (int)k, G);
     IPP_LAUNCH_CHECK();
-    append_gram_kernel<<<(unsigned)((k * k + 7) / 8), 256, 0, s>>>(Vt, Q, N, (int)k, G);
+    append_schur_inverse_kernel<<<1, 32, 0, s>>>(S, G, (int)k, diag_add, Mm, Li, info);
     IPP_LAUNCH_CHECK();
-    append_schur_inverse_kernel<<<1, 32, 0, s>>>(S, G, (int)k, diag_add, Mm, info);
-    IPP_LAUNCH_CHECK();
-    append_apply_m_kernel<<<(unsigned)((N * k + 255) / 256), 256, 0, s>>>(V, Vt, Mm, N, (int)k, VM, MVt);
+    append_apply_m_kernel<<<(unsigned)((N * k + 255) / 256), 256, 0, s>>>(V, Li, Mm, N, (int)k, U, VM);
     IPP_LAUNCH_CHECK();
     const int64_t NT = N + k;
     dim3 grid((unsigned)((NT + 63) / 64), (unsigned)((NT + 63) / 64));
-    append_update_kernel<<<grid, 256, 0, s>>>(winv_old, ldw_old, N, (int)k, VM, Vt, MVt, Mm, winv_new, ldw_new);
+    append_update_kernel<<<grid, 256, 0, s>>>(winv_old, ldw_old, N, (int)k, U, VM, Mm, winv_new, ldw_new);
     IPP_LAUNCH_CHECK();
     if (alpha_new && z_all) IPP_TRY(launch_gemv(winv_new, ldw_new, NT, NT, z_all, alpha_new, s));
     return IPP_OK;

@@ -1,0 +1,231 @@
+// a12 batching seam: every reward of ONE tree-search rollout in a single call.
+//
+// Reference flow (mcts_library.py:354-442 Tree.leaf_helper, :499-621 BeliefTree): at level l the rollout
+// scores the k_l sample points of its action under the belief = base belief + the simulated observations
+// of levels < l, then appends its own observation block once (re-used child, :413) or twice (new child,
+// :426 & :430).  Each append is an O(N^2 k) block-inverse update of the N x N matrix and each reward an
+// O(N^2 k) predict -- although the rollout only ever looks at <= ~40 points.
+//
+// Here the N x N work is done ONCE per rollout against the (immutable) base belief:
+//   m0 = K(P, X) alpha,   C0 = K(P, P) - K(P, X) W^-1 K(X, P)          P = all sample points of the rollout
+// and the per-level beliefs are obtained by conditioning the small joint Gaussian (m, C) over P on the noisy
+// block observations, which is the same posterior the reference reaches through update_model
+// (gpmodel_library.py:230-279: Schur block M = (S - R P^-1 Q + (noise + 1e-8) I)^-1 is exactly
+// (C[B,B] + (noise + 1e-8) I)^-1 here):
+//   A = C[B,B] + diag_add I = L L^T;  H = C[:,B] L^-T;  u = L^-1 (y_B - m_B);  m += H u;  C -= H H^T
+// repeated `reps[l]` times for the same block.  One CTA, everything in shared memory.
+#include "internal.cuh"
+
+namespace ipp {
+
+// shared with rewards.cu (same closed forms; kept textually identical so both paths agree bit for bit)
+__device__ __forceinline__ double ro_norm_cdf(double a) {
+    const double x = a * 0.70710678118654752440;
+    const double z = fabs(x);
+    if (z < 0.70710678118654752440) return 0.5 + 0.5 * erf(x);
+    double y = 0.5 * erfc(z);
+    if (x > 0) y = 1.0 - y;
+    return y;
+}
+__device__ __forceinline__ double ro_norm_pdf(double x) { return exp(-(x * x) / 2.0) / 2.50662827463100050242; }
+__device__ __forceinline__ double ro_mes_utility(double ymax, double mu, double var) {
+    const double gamma = (ymax - mu) / var;
+    const double pdf = ro_norm_pdf(gamma), cdf = ro_norm_cdf(gamma);
+    return gamma * pdf / (2.0 * cdf) - log(cdf);
+}
+
+constexpr int RO_MAX_POINTS = IPP_ROLLOUT_MAX_POINTS;
+constexpr int RO_MAX_BLOCK = IPP_APPEND_MAX_K;
+constexpr int RO_MAX_LEVELS = IPP_ROLLOUT_MAX_LEVELS;
+constexpr int RO_THREADS = 256;
+
+struct RolloutArgs {
+    const double* mean0;        // [M]
+    const double* cov0;         // [M][ldc]
+    int64_t ldc;
+    const double* zobs;         // [M]
+    int M, L;
+    int offsets[RO_MAX_LEVELS + 1];
+    int reps[RO_MAX_LEVELS];
+    int kind;
+    double p0;                  // UCB: sqrt(beta); EI: eta
+    const double* maxes; int S; // MES
+    double noise_pred;          // added to the predictive variance (predict_value include_noise=True)
+    double diag_add;            // noise + 1e-8 on the Schur block
+    double* reward;             // [L]
+    int32_t* info;              // 0 ok; l + 1: level l's block was not positive definite
+};
+
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(RolloutArgs p) {
+    extern __shared__ __align__(16) double sm[];
+    const int M = p.M, ldc = M + 1;
+    double* C = sm;                              // [M][M+1]
+    double* m = C + (size_t)M * ldc;             // [M]
+    double* H = m + M;                           // [M][RO_MAX_BLOCK + 1]
+    double* A = H + (size_t)M * (RO_MAX_BLOCK + 1);   // [RO_MAX_BLOCK][RO_MAX_BLOCK + 1]
+    double* u = A + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1);   // [RO_MAX_BLOCK]
+    double* red = u + RO_MAX_BLOCK;              // [RO_THREADS / 32][2]
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int HL = RO_MAX_BLOCK + 1, AL = RO_MAX_BLOCK + 1;
+
+    for (int idx = tid; idx < M * M; idx += RO_THREADS) C[(idx / M) * ldc + idx % M] = p.cov0[(int64_t)(idx / M) * p.ldc + idx % M];
+    for (int i = tid; i < M; i += RO_THREADS) m[i] = p.mean0[i];
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+
+    for (int l = 0; l < p.L; ++l) {
+        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
+        // ---- reward of level l from (m, diag C + noise) of its points
+        double s0 = 0.0, s1 = 0.0;
+        if (p.kind == IPP_REWARD_MES) {
+            for (int idx = tid; idx < kb * p.S; idx += RO_THREADS) {
+                const int q = b0 + idx / p.S;
+                s0 += ro_mes_utility(p.maxes[idx % p.S], m[q], C[q * ldc + q] + p.noise_pred);
+            }
+        } else {
+            for (int q = b0 + tid; q < b0 + kb; q += RO_THREADS) {
+                s0 += (p.kind == IPP_REWARD_EI) ? (m[q] - p.p0) : m[q];
+                s1 += fabs(C[q * ldc + q] + p.noise_pred);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane == 0) { red[2 * warp] = s0; red[2 * warp + 1] = s1; }
+        __syncthreads();
+        if (tid == 0) {
+            s0 = s1 = 0.0;
+            for (int w = 0; w < RO_THREADS / 32; ++w) { s0 += red[2 * w]; s1 += red[2 * w + 1]; }
+            double r;
+            if (p.kind == IPP_REWARD_UCB) {
+                r = s0 + p.p0 * s1;
+            } else if (p.kind == IPP_REWARD_EI) {
+                const double z = s0 / s1;
+                const double big_phi = 0.5 * (1.0 + erf(z / 1.41421356237309504880));
+                const double small_phi = 1.0 / 2.50662827463100050242 * exp(-(z * z) / 2.0);
+                r = s0 * big_phi + s1 * small_phi;
+            } else {
+                r = 2.0 * s0 / (double)p.S;
+            }
+            p.reward[l] = r;
+        }
+        if (l == p.L - 1) break;                  // the last level's observation is never looked at again
+        // ---- condition (m, C) on the block observation, reps[l] times; only rows >= b0 are read later
+        for (int rep = 0; rep < p.reps[l]; ++rep) {
+            __syncthreads();
+            for (int idx = tid; idx < kb * kb; idx += RO_THREADS) {
+                const int a = idx / kb, b = idx % kb;
+                A[a * AL + b] = C[(b0 + a) * ldc + b0 + b] + (a == b ? p.diag_add : 0.0);
+            }
+            if (tid < kb) u[tid] = p.zobs[b0 + tid] - m[b0 + tid];
+            __syncthreads();
+            if (warp == 0) {                      // lower Cholesky of A (kb <= 32): lane = row
+                for (int j = 0; j < kb; ++j) {
+                    double d = A[j * AL + j];
+                    if (!(d > 0.0)) { if (lane == 0) s_bad = l + 1; d = 1.0; }
+                    d = sqrt(d);
+                    __syncwarp();
+                    if (lane == j) A[j * AL + j] = d;
+                    if (lane > j && lane < kb) A[lane * AL + j] /= d;
+                    __syncwarp();
+                    if (lane > j && lane < kb)
+                        for (int c = j + 1; c <= lane; ++c) A[lane * AL + c] -= A[lane * AL + j] * A[c * AL + j];
+                    __syncwarp();
+                }
+                if (lane == 0) {                  // u = L^-1 (y_B - m_B)
+                    for (int a = 0; a < kb; ++a) {
+                        double v = u[a];
+                        for (int c = 0; c < a; ++c) v -= A[a * AL + c] * u[c];
+                        u[a] = v / A[a * AL + a];
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = b0 + tid; i < M; i += RO_THREADS) {      // H[i] = L^-1 C[B, i]  (forward substitution)
+                double dm = 0.0;
+                for (int a = 0; a < kb; ++a) {
+                    double v = C[i * ldc + b0 + a];
+                    for (int c = 0; c < a; ++c) v -= A[a * AL + c] * H[i * HL + c];
+                    v /= A[a * AL + a];
+                    H[i * HL + a] = v;
+                    dm = fma(v, u[a], dm);
+                }
+                m[i] += dm;
+            }
+            __syncthreads();
+            const int R = M - b0;
+            for (int idx = tid; idx < R * R; idx += RO_THREADS) {
+                const int i = b0 + idx / R, j = b0 + idx % R;
+                double s = 0.0;
+                for (int a = 0; a < kb; ++a) s = fma(H[i * HL + a], H[j * HL + a], s);
+                C[i * ldc + j] -= s;
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) *p.info = s_bad;
+}
+
+static size_t rollout_smem(int M) {
+    return sizeof(double) * ((size_t)M * (M + 1) + M + (size_t)M * (RO_MAX_BLOCK + 1) + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1) +
+                             RO_MAX_BLOCK + 2 * (RO_THREADS / 32));
+}
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
+    if (M <= 0) return 16;
+    const int64_t ldc = round_up(M, 2);
+    return ipp_gp_predict_cov_workspace(N, M) + M * ldc + round_up(M, 2) + 16;
+}
+
+extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                                   const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                                   int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
+                                   const double* pts, const double* zobs, const int32_t* offsets_host,
+                                   const int32_t* reps_host, int L, double* reward, int32_t* info,
+                                   double* work, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(kern && pts && zobs && offsets_host && reps_host && reward && info && work, "null pointer");
+    IPP_CHECK_ARG(L >= 1 && L <= RO_MAX_LEVELS, "1 <= levels <= IPP_ROLLOUT_MAX_LEVELS");
+    IPP_CHECK_ARG(kind == IPP_REWARD_UCB || kind == IPP_REWARD_EI || kind == IPP_REWARD_MES, "unknown reward kind");
+    IPP_CHECK_ARG(N >= 1 && X && alpha && winv, "needs a belief with data (the reference's no-data early-outs stay with the caller)");
+    const int M = offsets_host[L];
+    IPP_CHECK_ARG(offsets_host[0] == 0 && M >= 1 && M <= RO_MAX_POINTS, "1 <= points <= IPP_ROLLOUT_MAX_POINTS");
+    RolloutArgs p;
+    for (int l = 0; l < L; ++l) {
+        const int kb = offsets_host[l + 1] - offsets_host[l];
+        IPP_CHECK_ARG(kb >= 1 && kb <= RO_MAX_BLOCK, "each level needs 1..IPP_APPEND_MAX_K points");
+        IPP_CHECK_ARG(reps_host[l] >= 0 && reps_host[l] <= 4, "reps must be 0..4");
+        p.offsets[l] = offsets_host[l];
+        p.reps[l] = reps_host[l];
+    }
+    p.offsets[L] = M;
+    p.p0 = 0.0;
+    if (kind == IPP_REWARD_MES) IPP_CHECK_ARG(maxes_dev && S >= 1, "MES needs the sampled maxima");
+    else { IPP_CHECK_ARG(params_host && n_params >= 1, "need params[0]"); p.p0 = params_host[0]; }
+
+    const int64_t ldc = round_up(M, 2);
+    double* cov0 = work;
+    double* mean0 = cov0 + (int64_t)M * ldc;
+    double* sub = mean0 + round_up(M, 2);
+    IPP_TRY(ipp_gp_predict_cov(kern, X, N, alpha, winv, ldw, 0.0, pts, M, mean0, cov0, ldc, sub, stream_));
+    p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc; p.zobs = zobs;
+    p.M = M; p.L = L; p.kind = kind; p.maxes = maxes_dev; p.S = (int)S;
+    p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;
+    static bool configured = false;
+    if (!configured) {
+        IPP_CUDA(cudaFuncSetAttribute(rollout_condition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)rollout_smem(RO_MAX_POINTS)));
+        configured = true;
+    }
+    rollout_condition_kernel<<<1, RO_THREADS, rollout_smem(M), stream>>>(p);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}

@@ -285,6 +285,39 @@ class GPModel(object):
                                        L.ptr(reward), L.ptr(points), M, L.stream_ptr()))
         return reward, points
 
+    def rollout_rewards(self, kind, levels, params=None, maxes_d=None):
+        """Every reward of one tree-search rollout in ONE device call (ipp_rollout_rewards): `levels` is the
+        rollout's list of (query points (k_l, D), simulated observations (k_l, 1), times the block is appended
+        afterwards).  This belief is the base and is not modified.  Returns (rewards ndarray [L], info int);
+        info != 0 means a block was not positive definite and the caller must replay through add_data."""
+        D = self.dimension
+        L_ = len(levels)
+        offsets = (ctypes.c_int32 * (L_ + 1))()
+        reps = (ctypes.c_int32 * L_)()
+        M = 0
+        for i, (xq, _, r) in enumerate(levels):
+            M += xq.shape[0]
+            offsets[i + 1] = M
+            reps[i] = r
+        host = np.empty(M * (D + 1))
+        host[:M * D] = np.concatenate([np.asarray(xq, dtype=float).reshape(-1) for xq, _, _ in levels])
+        host[M * D:] = np.concatenate([np.asarray(z, dtype=float).reshape(-1) for _, z, _ in levels])
+        buf = torch.from_numpy(host).to(L.device(), non_blocking=False)
+        out = torch.empty(L_ + 1, dtype=torch.float64, device=buf.device)
+        N = self.n_obs
+        work = L.workspace(L.lib.ipp_rollout_workspace(N, M), slot='rollout')
+        par = (ctypes.c_double * 1)(float(params[0]) if params is not None else 0.0)
+        S = 0 if maxes_d is None else int(maxes_d.numel())
+        base = buf.data_ptr()
+        L.check(L.lib.ipp_rollout_rewards(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
+                                          L.ptr(self._winv_d), self._ld, float(self.noise), self._diag_add(), kind,
+                                          par, 1, L.ptr(maxes_d), S, ctypes.c_void_p(base),
+                                          ctypes.c_void_p(base + 8 * M * D), offsets, reps, L_,
+                                          L.ptr(out), ctypes.c_void_p(out.data_ptr() + 8 * L_), L.ptr(work),
+                                          L.stream_ptr()))
+        res = out.cpu().numpy()
+        return res[:L_], int(res[L_:].view(np.int32)[0])
+
     # multi-GPU replication by broadcasting the refreshed state (parallel.add_data_replicated)
     def state_tensors(self):
         return [t for t in (self._X_d, self._z_d, self._alpha_d, self._winv_d, self._linv_d) if t is not None]

@@ -16,6 +16,15 @@ The tree, its selection rules and its random-number consumption follow the refer
 Each rollout works on copy.copy(belief): an O(1) fork, because the device state of a belief is
 immutable and every append writes new buffers.
 
+Rollout batching (the north-star seam "hand each rollout's batched query points to the GPU in one call"):
+within a rollout the tree walk never looks at a reward -- child selection uses statistics of EARLIER
+rollouts, paths depend on poses only, and the simulated observations are prior draws / zeros because
+belief.model is None (:418-422, :598-601).  So the walk first records (sample points, observation,
+1-or-2 appends) per level, consuming the random streams in the reference's order, and then ONE call
+(GPModel.rollout_rewards -> ipp_rollout_rewards) returns every level's reward under the belief that level
+would have seen.  The sequential path (one reward + up to two add_data per level) remains for beliefs
+with a GPy-style model handle, foreign acquisition callables, empty beliefs and non-PD fallbacks.
+
 Batching seam (`evaluate_root_actions`, `choose_myopic`): all candidate paths of a pose are scored by
 ONE call of aq_library.reward_paths instead of one predict per path (robot_library.py:175-203).
 """
@@ -64,6 +73,8 @@ def _xobs(action):
 
 
 class Tree(object):
+    FUSE_ROLLOUTS = True       # default of .fuse_rollouts: score each rollout with one device call when possible
+
     def __init__(self, f_rew, f_aqu, belief, pose, path_generator, t, depth, param, c):
         self.path_generator = path_generator
         self.max_depth = depth
@@ -73,6 +84,8 @@ class Tree(object):
         self.aquisition_function = f_aqu
         self.c = c
         self._maxes_d = None
+        self.reward_evals = 0                       # one eval = one path's scalar reward (the benchmark's unit)
+        self.fuse_rollouts = self.FUSE_ROLLOUTS     # False forces the per-level reward / add_data path
         self.root = Node(pose, parent=None, name='root')
 
     def get_best_child(self):
@@ -93,6 +106,7 @@ class Tree(object):
         """Reward of one action.  When the acquisition function is one of this package's own callables the
         value stays on the device as a 0-d tensor (no host sync; the tree only needs it at back-propagation,
         reference :352); otherwise the callable is invoked exactly as the reference does (:386-396)."""
+        self.reward_evals += 1
         fast = _FAST_REWARDS.get(self.aquisition_function)
         if fast is not None and fast == self.f_rew and isinstance(belief, GPModel):
             param = self.param
@@ -106,6 +120,57 @@ class Tree(object):
         if self.f_rew in _PARAM_REWARDS:
             return self.aquisition_function(time=self.t, xvals=xobs, robot_model=belief, param=self.param)
         return self.aquisition_function(time=self.t, xvals=xobs, robot_model=belief)
+
+    # ---------------------------------------------------------------- fused rollouts
+    def _fused_kind(self, belief):
+        """Reward kind + parameters when the whole rollout can be scored by one device call, else None."""
+        if not self.fuse_rollouts:
+            return None
+        fast = _FAST_REWARDS.get(self.aquisition_function)
+        if fast is None or fast != self.f_rew or not isinstance(belief, GPModel):
+            return None
+        if belief.model is not None or belief.xvals is None or belief._winv_d is None:
+            return None
+        if fast == 'mean':
+            return aqlib.L.REWARD_UCB, [np.sqrt(aqlib.ucb_beta(self.t))], None
+        if fast == 'exp_improve':
+            eta = 0.5 if self.param is None else sum(self.param) / len(self.param)
+            return aqlib.L.REWARD_EI, [float(np.asarray(eta, dtype=float).reshape(-1)[0])], None
+        if self.param is None or self.param[0] is None:
+            return None
+        if self._maxes_d is None:
+            self._maxes_d = aqlib.L.to_device(np.asarray(self.param[0], dtype=float).reshape(-1))
+        return aqlib.L.REWARD_MES, None, self._maxes_d
+
+    def _replay(self, levels, pending, belief):
+        """The reference's per-level sequence for recorded levels (fallback of the fused path)."""
+        for xobs, zobs, reps in levels:
+            pending.append(self.action_reward(xobs, belief))
+            for _ in range(reps):
+                belief.add_data(xobs, zobs)
+
+    def settle_fused(self, reward, levels, belief, fused):
+        """Score the recorded levels with one device call; rewards are added level by level like settle()."""
+        if not levels:
+            return reward
+        kind, params, maxes_d = fused
+        n_pts = sum(x.shape[0] for x, _, _ in levels)
+        ok = (len(levels) <= aqlib.L.IPP_ROLLOUT_MAX_LEVELS and n_pts <= aqlib.L.IPP_ROLLOUT_MAX_POINTS
+              and max(x.shape[0] for x, _, _ in levels) <= aqlib.L.IPP_APPEND_MAX_K)
+        if ok:
+            queries = [(aqlib._queries(self.t, x, belief)[1], z, r) for x, z, r in levels]
+            vals, info = belief.rollout_rewards(kind, queries, params=params, maxes_d=maxes_d)
+            ok = info == 0
+            if ok:
+                self.reward_evals += len(levels)
+        if not ok:
+            pending = []
+            belief.defer_checks(True)
+            self._replay(levels, pending, belief)
+            return self.settle(reward, pending, belief)
+        for r in vals:
+            reward = reward + r
+        return reward
 
     @staticmethod
     def settle(reward, pending, belief):
@@ -127,9 +192,12 @@ class Tree(object):
             return np.reshape(zobs, (n_points, 1))
         return belief.posterior_samples(xobs, full_cov=False, size=1)
 
-    def _expand_action(self, node, pending, belief):
-        """One 'BA' step: score the action, then extend the rollout's belief.  Returns the next belief node."""
+    def _expand_action(self, node, pending, belief, levels=None):
+        """One 'BA' step: score the action, then extend the rollout's belief.  Returns the next belief node.
+        With `levels` (fused rollouts) the step is only recorded: (points, observation, number of appends)."""
         xobs = _xobs(node.action)
+        if levels is not None:
+            return self._record_action(node, xobs, belief, levels)
         pending.append(self.action_reward(xobs, belief))
         if node.children is not None:
             alpha = 3.0 / (10.0 * (self.max_depth - node.depth) - 3.0)
@@ -148,9 +216,29 @@ class Tree(object):
         node.add_children(child)
         return child
 
+    def _record_action(self, node, xobs, belief, levels):
+        """_expand_action without device work: same branches, same random draws, in the same order."""
+        if node.children is not None:
+            alpha = 3.0 / (10.0 * (self.max_depth - node.depth) - 3.0)
+            nchild = len(node.children)
+            if node.depth < self.max_depth - 1 and np.floor(nchild ** alpha) == np.floor((nchild - 1) ** alpha):
+                random.choice(node.children)
+                fewest = min(n.nqueries for n in node.children)
+                child = random.choice([n for n in node.children if n.nqueries == fewest])
+                levels.append((xobs, child.zvals, 1))
+                return child
+        zobs = self.simulate_observation(xobs, belief)
+        levels.append((xobs, zobs, 2))
+        child = Node(pose=node.dense_path[-1], parent=node, name=node.name + '_belief' + str(node.depth + 1),
+                     zvals=zobs)
+        node.add_children(child)
+        return child
+
     def leaf_helper(self, current_node, reward, belief):
         node = current_node
         pending = []
+        fused = self._fused_kind(belief)
+        levels = [] if fused is not None else None
         if isinstance(belief, GPModel):
             belief.defer_checks(True)
         while True:
@@ -163,7 +251,9 @@ class Tree(object):
                     break
                 node = self.get_next_child(node)
             else:
-                node = self._expand_action(node, pending, belief)
+                node = self._expand_action(node, pending, belief, levels)
+        if fused is not None:
+            return node, self.settle_fused(reward, levels, belief, fused)
         return node, self.settle(reward, pending, belief)
 
     def get_next_child(self, current_node):
@@ -198,7 +288,7 @@ class BeliefTree(Tree):
             return np.zeros((xobs.shape[0], 1))
         return belief.predict_value(xobs)[0]
 
-    def random_rollouts(self, current_node, pending, belief):
+    def random_rollouts(self, current_node, pending, belief, levels=None):
         cur_depth = current_node.depth
         pose = current_node.pose
         while cur_depth <= self.max_depth:
@@ -208,16 +298,21 @@ class BeliefTree(Tree):
                 return
             a = np.random.randint(0, len(actions) - 1)
             xobs = _xobs(actions[keys[a]])
-            pending.append(self.action_reward(xobs, belief))
-            zobs = self.mle_observation(xobs, belief)
-            belief.add_data(xobs, zobs)
-            belief.add_data(xobs, zobs)
+            if levels is not None:
+                levels.append((xobs, self.mle_observation(xobs, belief), 2))
+            else:
+                pending.append(self.action_reward(xobs, belief))
+                zobs = self.mle_observation(xobs, belief)
+                belief.add_data(xobs, zobs)
+                belief.add_data(xobs, zobs)
             pose = dense_paths[keys[a]][-1]
             cur_depth += 1
 
     def leaf_helper(self, current_node, reward, belief):
         node = current_node
         pending = []
+        fused = self._fused_kind(belief)
+        levels = [] if fused is not None else None
         if isinstance(belief, GPModel):
             belief.defer_checks(True)
         while True:
@@ -230,20 +325,26 @@ class BeliefTree(Tree):
                     break
                 child, full_action_set = self.get_next_child(node)
                 if not full_action_set:
-                    self.random_rollouts(node, pending, belief)
+                    self.random_rollouts(node, pending, belief, levels)
                     node = child
                     break
                 node = child
             else:
                 xobs = _xobs(node.action)
-                pending.append(self.action_reward(xobs, belief))
-                zobs = self.mle_observation(xobs, belief)
-                belief.add_data(xobs, zobs)
-                belief.add_data(xobs, zobs)
+                if levels is not None:
+                    zobs = self.mle_observation(xobs, belief)
+                    levels.append((xobs, zobs, 2))
+                else:
+                    pending.append(self.action_reward(xobs, belief))
+                    zobs = self.mle_observation(xobs, belief)
+                    belief.add_data(xobs, zobs)
+                    belief.add_data(xobs, zobs)
                 child = Node(pose=node.dense_path[-1], parent=node,
                              name=node.name + '_belief' + str(node.depth + 1), zvals=zobs)
                 node.add_children(child)
                 node = child
+        if fused is not None:
+            return node, self.settle_fused(reward, levels, belief, fused)
         return node, self.settle(reward, pending, belief)
 
     def get_next_child(self, current_node):
