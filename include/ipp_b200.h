@@ -103,7 +103,22 @@ int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, const double
                    const double* Xq, int64_t M, double* mean, double* var,
                    double* work, void* stream);
 
-/* CUDA-event timing of the dominant kernel of ipp_gp_predict (the fused DMMA variance kernel), recorded on
+/* ---- a3, 3xTF32 mode (BASELINE config 3 "FP64 vs 3xTF32"): the variance in GPy's Cholesky form,
+ *      var = variance - |Linv k|^2, on the tcgen05 tensor cores (kind::tf32, TMA-staged operands, TMEM
+ *      accumulators).  Operands are split once as a = hi + lo (two TF32 numbers) and the contraction is
+ *      hi*hi + hi*lo + lo*hi with FP32 accumulation; the mean stays FP64.  Variance error ~1e-6 of the PRIOR
+ *      variance (FP32 operand representation), not 1e-6 of the posterior variance: see DESIGN.md.
+ *        ipp_tf32_split: A[rows][lda] (double) -> hi, lo [rows][ldf] (float), columns >= cols zeroed;
+ *        linv_hi / linv_lo: the split of Linv [N][ldl] (lower triangular, zeros above), ldl % 4 == 0;
+ *      work: ipp_gp_predict_tf32_workspace(N, M) doubles. */
+int ipp_tf32_split(const double* A, int64_t rows, int64_t cols, int64_t lda, float* hi, float* lo, int64_t ldf,
+                   void* stream);
+int64_t ipp_gp_predict_tf32_workspace(int64_t N, int64_t M);
+int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                        const float* linv_hi, const float* linv_lo, int64_t ldl, double noise_add,
+                        const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
+
+/* CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 (the fused DMMA variance kernel), recorded on
  * the launching stream.  enable(1) starts a fresh record; read() synchronises on the recorded events and
  * returns the summed device time and the number of launches since enable/read.  Measurement only. */
 int ipp_profile_enable(int on);

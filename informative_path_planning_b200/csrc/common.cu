@@ -46,7 +46,47 @@ int launch_gemv(const double* A, int64_t lda, int64_t rows, int64_t cols, const 
     return IPP_OK;
 }
 
+// Optional CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 (the fused variance
+// kernels), recorded on the launching stream.  Used by bench.py for the roofline figure; off by default.
+constexpr int PROFILE_MAX = 8192;
+static bool g_profile = false;
+static cudaEvent_t g_ev[PROFILE_MAX][2];
+static int g_ev_made = 0, g_ev_used = 0;
+
+void profile_mark(int which, cudaStream_t s) {
+    if (!g_profile || g_ev_used >= PROFILE_MAX) return;
+    if (which == 0 && g_ev_used >= g_ev_made) {
+        cudaEventCreate(&g_ev[g_ev_made][0]);
+        cudaEventCreate(&g_ev[g_ev_made][1]);
+        ++g_ev_made;
+    }
+    cudaEventRecord(g_ev[g_ev_used][which], s);
+    if (which == 1) ++g_ev_used;
+}
+
 }  // namespace ipp
+
+extern "C" int ipp_profile_enable(int on) {
+    ipp::g_profile = on != 0;
+    ipp::g_ev_used = 0;
+    return IPP_OK;
+}
+
+extern "C" int ipp_profile_read(double* total_ms, int64_t* launches) {
+    using namespace ipp;
+    IPP_CHECK_ARG(total_ms && launches, "null pointer");
+    double sum = 0.0;
+    for (int i = 0; i < g_ev_used; ++i) {
+        IPP_CUDA(cudaEventSynchronize(g_ev[i][1]));
+        float ms = 0.f;
+        IPP_CUDA(cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = g_ev_used;
+    g_ev_used = 0;
+    return IPP_OK;
+}
 
 extern "C" const char* ipp_last_error(void) { return ipp::g_err; }
 extern "C" int ipp_version(void) { return 100; }

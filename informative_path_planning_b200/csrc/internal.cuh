@@ -9,6 +9,7 @@ namespace ipp {
 
 void set_error(const char* fmt, ...);
 int  sm_count();
+void profile_mark(int which, cudaStream_t s);      // CUDA-event bracket of the dominant kernel (ipp_profile_*)
 
 #define IPP_CHECK_ARG(cond, msg)                                                            \
     do { if (!(cond)) { ::ipp::set_error("%s: %s", __func__, msg); return IPP_E_INVALID; } } while (0)

@@ -203,24 +203,6 @@ __global__ void predict_finalize_small_kernel(const double* __restrict__ partial
 
 constexpr int64_t PREDICT_CHUNK = 32768;
 
-// Optional CUDA-event timing of the dominant kernel (predict_var_kernel), on the launching stream.
-// Used by bench.py for the roofline figure; off by default (no events are recorded).
-constexpr int PROFILE_MAX = 8192;
-static bool g_profile = false;
-static cudaEvent_t g_ev[PROFILE_MAX][2];
-static int g_ev_made = 0, g_ev_used = 0;
-
-static void profile_mark(int which, cudaStream_t s) {
-    if (!g_profile || g_ev_used >= PROFILE_MAX) return;
-    if (which == 0 && g_ev_used >= g_ev_made) {
-        cudaEventCreate(&g_ev[g_ev_made][0]);
-        cudaEventCreate(&g_ev[g_ev_made][1]);
-        ++g_ev_made;
-    }
-    cudaEventRecord(g_ev[g_ev_used][which], s);
-    if (which == 1) ++g_ev_used;
-}
-
 static int64_t chunk_rows(int64_t M) { return M < PREDICT_CHUNK ? round_up(M, BM) : PREDICT_CHUNK; }
 
 }  // namespace ipp
@@ -305,27 +287,6 @@ extern "C" int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, c
                                                                                  kern->variance, noise_add, var + s);
         IPP_LAUNCH_CHECK();
     }
-    return IPP_OK;
-}
-
-extern "C" int ipp_profile_enable(int on) {
-    g_profile = on != 0;
-    g_ev_used = 0;
-    return IPP_OK;
-}
-
-extern "C" int ipp_profile_read(double* total_ms, int64_t* launches) {
-    IPP_CHECK_ARG(total_ms && launches, "null pointer");
-    double sum = 0.0;
-    for (int i = 0; i < g_ev_used; ++i) {
-        IPP_CUDA(cudaEventSynchronize(g_ev[i][1]));
-        float ms = 0.f;
-        IPP_CUDA(cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]));
-        sum += ms;
-    }
-    *total_ms = sum;
-    *launches = g_ev_used;
-    g_ev_used = 0;
     return IPP_OK;
 }
 

@@ -109,6 +109,8 @@ class GPModel(object):
         self._linv_d = None        # [N][ld] L^-1 (GPy-form models only)
         self._ld = 0
         self._ig = None            # cached (binv, logdet_before) for info_gain
+        self._tf32 = None          # cached (linv_hi, linv_lo, ld) float32 split of L^-1 for the 3xTF32 predict
+        self.predict_precision = 'fp64'   # 'tf32x3': batched predicts run on the tcgen05 path (see predict_device)
         # Rollout forks may defer the "is the Schur block positive definite" read-back (a device->host
         # sync per append) to one check per rollout: see defer_checks() / check_pending().
         self._defer = False
@@ -152,6 +154,7 @@ class GPModel(object):
         self._winv_d, self._linv_d, self._alpha_d, self._ld = winv, linv, alpha, ld
         self._logdet = scal
         self._ig = None
+        self._tf32 = None
 
     def _predict_core(self, xq_d, include_noise, mode, mat):
         M = xq_d.shape[0]
@@ -262,12 +265,59 @@ class GPModel(object):
     def _var_operand(self):
         return L.VAR_CHOL, self._linv_d
 
-    def predict_device(self, xq_d, include_noise=True):
-        """(M, D) float64 CUDA tensor -> (mean[M], var[M]) CUDA tensors; no host transfer."""
+    def _tf32_operand(self):
+        """(hi, lo, ld): float32 split of L^-1 of the current belief, built on first use after every refresh /
+        append (L^-1 itself comes from a device refactorisation when the model only carries W^-1)."""
+        if self._tf32 is None:
+            N, dev = self.n_obs, L.device()
+            linv = self._linv_d
+            if linv is None:
+                ld = L.round_up(N, 16)
+                winv = torch.empty((N, ld), dtype=torch.float64, device=dev)
+                linv = torch.empty((N, ld), dtype=torch.float64, device=dev)
+                alpha = torch.empty(N, dtype=torch.float64, device=dev)
+                scal = torch.zeros(2, dtype=torch.float64, device=dev)
+                info = torch.zeros(1, dtype=torch.int32, device=dev)
+                work = L.workspace(L.lib.ipp_gp_factor_workspace(N))
+                L.check(L.lib.ipp_gp_factor(ctypes.byref(self.kern._c), L.ptr(self._X_d), L.ptr(self._z_d), N,
+                                            self._diag_add(), L.ptr(winv), L.ptr(linv), ld, L.ptr(alpha), L.ptr(scal),
+                                            L.ptr(info), L.ptr(work), L.stream_ptr()))
+                if int(info.item()) != 0:
+                    raise np.linalg.LinAlgError('not positive definite (3xTF32 operand refresh)')
+                lda = ld
+            else:
+                lda = self._ld
+            ldl = L.round_up(N, 32)
+            hi = torch.empty((N, ldl), dtype=torch.float32, device=dev)
+            lo = torch.empty((N, ldl), dtype=torch.float32, device=dev)
+            L.check(L.lib.ipp_tf32_split(L.ptr(linv), N, N, lda, L.ptr(hi), L.ptr(lo), ldl, L.stream_ptr()))
+            self._tf32 = (hi, lo, ldl)
+        return self._tf32
+
+    def _predict_tf32(self, xq_d, include_noise):
+        M, N = xq_d.shape[0], self.n_obs
+        hi, lo, ldl = self._tf32_operand()
+        mean = torch.empty(M, dtype=torch.float64, device=xq_d.device)
+        var = torch.empty(M, dtype=torch.float64, device=xq_d.device)
+        work = L.workspace(L.lib.ipp_gp_predict_tf32_workspace(N, M), slot='tf32')
+        L.check(L.lib.ipp_gp_predict_tf32(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
+                                          L.ptr(hi), L.ptr(lo), ldl, float(self.noise) if include_noise else 0.0,
+                                          L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
+        return mean, var
+
+    def predict_device(self, xq_d, include_noise=True, precision=None):
+        """(M, D) float64 CUDA tensor -> (mean[M], var[M]) CUDA tensors; no host transfer.
+        precision: 'fp64' (FP64 DMMA, reference parity) or 'tf32x3' (tcgen05, split operands); default = the
+        model's .predict_precision.  Small batches always use the FP64 path (they are bandwidth-bound)."""
         if self.n_obs == 0:
             M = xq_d.shape[0]
             return (torch.zeros(M, dtype=torch.float64, device=xq_d.device),
                     torch.full((M,), float(self.variance), dtype=torch.float64, device=xq_d.device))
+        precision = self.predict_precision if precision is None else precision
+        if precision not in ('fp64', 'tf32x3'):
+            raise ValueError("precision must be 'fp64' or 'tf32x3'")
+        if precision == 'tf32x3' and xq_d.shape[0] > 64:
+            return self._predict_tf32(xq_d.contiguous(), include_noise)
         mode, mat = self._var_operand()
         return self._predict_core(xq_d.contiguous(), include_noise, mode, mat)
 
@@ -412,6 +462,8 @@ class OnlineGPModel(GPModel):
             done += kb
         self._X_d, self._z_d, self._winv_d, self._alpha_d, self._ld = X_all, z_all, winv, alpha, ld
         self._ig = None
+        self._tf32 = None
+        self._linv_d = None
 
     def add_data(self, xvals, zvals):                         # reference :281-301
         if self.xvals is None:
@@ -431,7 +483,7 @@ class OnlineGPModel(GPModel):
             return np.zeros((n_points, 1)), np.ones((n_points, 1)) * self.variance
         if full_cov:
             return self._predict_full_cov(xvals, include_noise, float(self.noise), diagonal_only=False)
-        mean, var = self._predict_core(L.to_device(xvals), include_noise, L.VAR_WINV_SYM, self._winv_d)
+        mean, var = self.predict_device(L.to_device(xvals), include_noise)     # FP64 unless .predict_precision says otherwise
         return mean.cpu().numpy().reshape(-1, 1), var.cpu().numpy().reshape(-1, 1)
 
     def posterior_samples(self, xvals, size=10, full_cov=True):           # reference :331-364

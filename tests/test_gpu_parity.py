@@ -646,3 +646,30 @@ def test_mcts_fused_rollouts_same_choices_as_per_level_path(pkg, f_rew, tree_typ
     np.testing.assert_array_equal(out[True][1], out[False][1])
     np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-8)
     assert m.n_obs == 120
+
+
+@pytest.mark.parametrize('N,M', [(333, 130), (1000, 5000), (2048, 33000)])
+def test_predict_tf32x3_mode_against_fp64_mode(pkg, N, M):
+    """3xTF32 mode (tcgen05 kind::tf32, Cholesky form, split operands) against the FP64 mode on the same belief.
+    The mean is computed in FP64 in both.  The variance carries the FP32 representation error of the operands
+    amplified by the cancellation variance - |Linv k|^2: bounded here relative to the PRIOR
+    variance (1e-5 * variance) and, at noise 0.5, to 2e-3 of the posterior variance (typically ~5e-5)."""
+    rng = np.random.default_rng(N)
+    X, z = world(rng, N, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    q = rng.uniform(0, 10, (M, 2))
+    mu64, var64 = m.predict_value(q)
+    m.predict_precision = 'tf32x3'
+    mu32, var32 = m.predict_value(q)
+    np.testing.assert_allclose(mu32, mu64, rtol=1e-9, atol=1e-9)
+    err = np.abs(var32 - var64)
+    assert err.max() <= 1e-5 * 100.0, err.max()
+    assert (err / var64).max() <= 2e-3, (err / var64).max()
+    assert np.median(err / var64) <= 2e-4
+    # appended data invalidates the split operand
+    m.add_data(np.array([[5.0, 5.0], [2.5, 7.5]]), np.array([[1.0], [2.0]]))
+    v_a = m.predict_value(q[:200])[1]
+    m.predict_precision = 'fp64'
+    v_b = m.predict_value(q[:200])[1]
+    assert np.abs(v_a - v_b).max() <= 1e-3
