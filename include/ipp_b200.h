@@ -110,12 +110,14 @@ int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, const double
  *      variance (FP32 operand representation), not 1e-6 of the posterior variance: see DESIGN.md.
  *        ipp_tf32_split: A[rows][lda] (double) -> hi, lo [rows][ldf] (float), columns >= cols zeroed;
  *        linv_hi / linv_lo: the split of Linv [N][ldl] (lower triangular, zeros above), ldl % 4 == 0;
+ *        acc_kblocks: 32-wide k-blocks accumulated inside the tensor core (truncating FP32) before the epilogue
+ *        takes the chunk over into round-to-nearest register sums; 1 = most accurate, large = fastest;
  *      work: ipp_gp_predict_tf32_workspace(N, M) doubles. */
 int ipp_tf32_split(const double* A, int64_t rows, int64_t cols, int64_t lda, float* hi, float* lo, int64_t ldf,
                    void* stream);
 int64_t ipp_gp_predict_tf32_workspace(int64_t N, int64_t M);
 int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                        const float* linv_hi, const float* linv_lo, int64_t ldl, double noise_add,
+                        const float* linv_hi, const float* linv_lo, int64_t ldl, int acc_kblocks, double noise_add,
                         const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
 
 /* CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 (the fused DMMA variance kernel), recorded on

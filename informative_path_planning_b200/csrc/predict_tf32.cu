@@ -8,14 +8,17 @@
 //   * rbf_queries_tf32_kernel  cross-covariance chunk Kxt[m][j] generated in FP64 (one exp per pair), stored
 //                              query-major as (hi, lo); the posterior mean is accumulated in FP64 there;
 //   * predict_var_tf32_kernel  D[m][n] = sum_j Kxt[m][j] Linv[n][j] as tcgen05.mma.kind::tf32, 128 x 128
-//                              tiles, operands staged by TMA (SWIZZLE_128B, 3 x 64 KB stages), accumulator
-//                              in TMEM (2 x 128 columns, double buffered).  Warp-specialised persistent CTA:
-//                              warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue
-//                              (tcgen05.ld 32x32b: thread = query row; squares summed in FP64; the tile is
-//                              never stored).  Lower-triangular Linv: n-tile I contracts k < 128 (I + 1) only.
-// Accuracy (measured, tests/test_gpu_parity.py): mean as in FP64 mode; variance error <= ~3e-6 of the prior
-// variance (the FP32 representation of the operands bounds it), i.e. not a replacement for the
-// FP64 mode where 1e-6 relative variance is required.
+//                              tiles, operands staged by TMA (SWIZZLE_128B, 3 x 64 KB stages), accumulators
+//                              in TMEM (4 x 128 columns).  Warp-specialised persistent CTA: warp 0 = TMA
+//                              producer, warp 1 = MMA issuer (one thread), warps 2-9 = epilogue (tcgen05.ld
+//                              32x32b: thread = query row x 64 columns; the tile is never stored).
+//                              Lower-triangular Linv: n-tile I contracts k < 128 (I + 1) only.
+// Accumulation: rows of Linv oscillate, so |terms| / |result| ~ 1e3 in this contraction and the tensor core's
+// truncating FP32 accumulator is the dominant error when it runs over the whole K (measured at N = 4096: 1.2e-2 of
+// the posterior variance).  The MMA therefore accumulates only `acc_kblocks` k-blocks of 32 per TMEM buffer and the
+// epilogue sums the chunks in registers with round-to-nearest FP32 adds, overlapped with the next chunks' MMAs
+// (acc_kblocks = 1: 7.7e-4 max / 2e-4 median of the posterior variance, 15 % slower than unchunked).
+// Not a replacement for the FP64 mode where 1e-6 relative variance is required.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "internal.cuh"
@@ -27,9 +30,11 @@ constexpr int T_STAGES = 3;
 constexpr int T_TILE_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int T_STAGE_BYTES = 4 * T_TILE_BYTES;      // A hi, A lo, B hi, B lo
 constexpr int T_SMEM = T_STAGES * T_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int T_THREADS = 192;
+constexpr int T_EPI_WARPS = 8;                       // two per TMEM lane quarter, 64 accumulator columns each
+constexpr int T_THREADS = 64 + 32 * T_EPI_WARPS;
 constexpr int T_ACC_COLS = 128;                      // FP32 accumulator columns per tile
-constexpr int T_TMEM_COLS = 256;                     // two accumulators
+constexpr int T_NBUF = 4;                            // TMEM accumulator buffers (chunk pipeline MMA -> epilogue)
+constexpr int T_TMEM_COLS = T_NBUF * T_ACC_COLS;     // 512 = all of TMEM (one CTA per SM)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 128, M = 128
 constexpr uint32_t T_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 
@@ -93,8 +98,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct Tf32Args {
-    double* partial; int64_t ldp;      // [T][ldp] per-(n-tile, query) partial sums of squares
+    double* partial; int64_t ldp;      // [2 T][ldp] per-(n-tile, column half, query) partial sums of squares
     int Mc, N, T, Mtiles, GM;
+    int KC;                            // k-blocks (of 32) accumulated inside the tensor core before the epilogue takes over
 };
 
 // item -> (n-tile I heaviest first inside an L2-sized group of GM m-tiles, m-tile); identical in all three roles
@@ -120,13 +126,13 @@ predict_var_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-B alignment
     const uint32_t bars = tiles + T_STAGES * T_STAGE_BYTES;              // 8-byte mbarriers
     const uint32_t full0 = bars, empty0 = bars + 8 * T_STAGES;
-    const uint32_t tfull0 = bars + 16 * T_STAGES, tempty0 = tfull0 + 16;
-    const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t tfull0 = bars + 16 * T_STAGES, tempty0 = tfull0 + 8 * T_NBUF;
+    const uint32_t tmem_slot = tempty0 + 8 * T_NBUF;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        for (int a = 0; a < T_NBUF; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 32 * T_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -162,56 +168,74 @@ predict_var_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         }
     } else if (warp == 1) {
         if (lane == 0) {                                                 // ===== MMA issuer (single thread)
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, buf = 0, buf_phase = 0;
             int m0, I, kblocks;
             for (int it = 0; tf32_item(p, it, m0, I, kblocks); ++it) {
-                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);             // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d = tmem_base + acc * T_ACC_COLS;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);
+                for (int kb0 = 0; kb0 < kblocks; kb0 += p.KC) {          // one accumulation chunk per TMEM buffer
+                    const int kb1 = (kb0 + p.KC < kblocks) ? kb0 + p.KC : kblocks;
+                    mbar_wait(tempty0 + 8 * buf, buf_phase ^ 1);         // epilogue has drained this buffer
                     tc_fence_after();
-                    const uint32_t base = tiles + stage * T_STAGE_BYTES;
-                    const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + T_TILE_BYTES);
-                    const uint64_t b_hi = make_desc(base + 2 * T_TILE_BYTES), b_lo = make_desc(base + 3 * T_TILE_BYTES);
+                    const uint32_t d = tmem_base + buf * T_ACC_COLS;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t base = tiles + stage * T_STAGE_BYTES;
+                        const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + T_TILE_BYTES);
+                        const uint64_t b_hi = make_desc(base + 2 * T_TILE_BYTES), b_lo = make_desc(base + 3 * T_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TBK / 8; ++k) {                  // UMMA_K = 8 TF32 = 32 B: +2 in 16-B units
-                        const uint64_t adv = (uint64_t)(2 * k);
-                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, (kb | k) != 0);
-                        tc_mma_tf32(d, a_hi + adv, b_lo + adv, 1);
-                        tc_mma_tf32(d, a_hi + adv, b_hi + adv, 1);
+                        for (int k = 0; k < TBK / 8; ++k) {              // UMMA_K = 8 TF32 = 32 B: +2 in 16-B units
+                            const uint64_t adv = (uint64_t)(2 * k);
+                            tc_mma_tf32(d, a_lo + adv, b_hi + adv, (kb != kb0) || k != 0);
+                            tc_mma_tf32(d, a_hi + adv, b_lo + adv, 1);
+                            tc_mma_tf32(d, a_hi + adv, b_hi + adv, 1);
+                        }
+                        tc_commit(empty0 + 8 * stage);                   // frees the stage when these MMAs retire
+                        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(empty0 + 8 * stage);                       // frees the stage when these MMAs retire
-                    if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+                    tc_commit(tfull0 + 8 * buf);                         // chunk complete -> epilogue
+                    if (++buf == T_NBUF) { buf = 0; buf_phase ^= 1; }
                 }
-                tc_commit(tfull0 + 8 * acc);                             // accumulator complete -> epilogue
             }
         }
     } else {                                                             // ===== epilogue warps 2..5
+        // The tensor core accumulates in FP32 with truncation; over a long contraction with heavy cancellation
+        // (rows of Linv oscillate) that error dominates.  So the MMA only accumulates KC k-blocks per TMEM buffer
+        // and the chunks are summed here in registers with round-to-nearest FP32 adds (thread = query row,
+        // 128 columns), overlapped with the MMAs of the next chunks.
         const int quarter = warp & 3;                                    // TMEM lanes 32 * (warp % 4) ...
+        const int half = (warp - 2) >> 2;                                // accumulator columns [64 half, 64 half + 64)
+        constexpr int HC = T_ACC_COLS / 2;
+        uint32_t buf = 0, buf_phase = 0;
         int m0, I, kblocks;
         for (int it = 0; tf32_item(p, it, m0, I, kblocks); ++it) {
-            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * T_ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-            double q = 0.0;
-#pragma unroll 1
-            for (int c = 0; c < T_ACC_COLS / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
+            float acc[HC];
+#pragma unroll
+            for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+            for (int kb0 = 0; kb0 < kblocks; kb0 += p.KC) {
+                mbar_wait(tfull0 + 8 * buf, buf_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + buf * T_ACC_COLS + half * HC + ((uint32_t)(quarter * 32) << 16);
+                uint32_t r0[32], r1[32];
+                tmem_ld32(taddr, r0);
+                tmem_ld32(taddr + 32, r1);
                 tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * buf);                          // buffer is in registers: hand it back early
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const double v = (double)__uint_as_float(r[i]);
-                    q = fma(v, v, q);
+                    acc[i] += __uint_as_float(r0[i]);
+                    acc[32 + i] += __uint_as_float(r1[i]);
                 }
+                if (++buf == T_NBUF) { buf = 0; buf_phase ^= 1; }
             }
-            tc_fence_before();
-            mbar_arrive(tempty0 + 8 * acc);
+            double q = 0.0;
+#pragma unroll
+            for (int i = 0; i < HC; ++i) {
+                const double v = (double)acc[i];
+                q = fma(v, v, q);
+            }
             const int row = m0 + quarter * 32 + lane;
-            if (row < p.Mc) p.partial[(int64_t)I * p.ldp + row] = q;
+            if (row < p.Mc) p.partial[(int64_t)(2 * I + half) * p.ldp + row] = q;
         }
     }
     tc_fence_before();
@@ -349,16 +373,17 @@ extern "C" int ipp_tf32_split(const double* A, int64_t rows, int64_t cols, int64
 extern "C" int64_t ipp_gp_predict_tf32_workspace(int64_t N, int64_t M) {
     if (N <= 0 || M <= 0) return 16;
     const int64_t ldf = round_up(N, 32), mc = tf32_chunk_rows(M), T = (N + TBN - 1) / TBN;
-    return mc * ldf /* hi + lo floats */ + T * mc + 64;
+    return mc * ldf /* hi + lo floats */ + 2 * T * mc + 64;
 }
 
 extern "C" int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                                   const float* linv_hi, const float* linv_lo, int64_t ldl, double noise_add,
-                                   const double* Xq, int64_t M, double* mean, double* var,
+                                   const float* linv_hi, const float* linv_lo, int64_t ldl, int acc_kblocks,
+                                   double noise_add, const double* Xq, int64_t M, double* mean, double* var,
                                    double* work, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(kern && X && alpha && linv_hi && linv_lo && Xq && mean && var && work, "null pointer");
     IPP_CHECK_ARG(N >= 1 && M >= 1 && N < (1LL << 30), "bad shape");
+    IPP_CHECK_ARG(acc_kblocks >= 1, "acc_kblocks >= 1");
     IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
     IPP_CHECK_ARG(ldl >= N && ldl % 4 == 0 && reinterpret_cast<uintptr_t>(linv_hi) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(linv_lo) % 16 == 0, "linv_hi/lo must be 16-byte aligned with ldl % 4 == 0");
@@ -398,13 +423,14 @@ extern "C" int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t
             if (gm > p.Mtiles) gm = p.Mtiles;
             p.GM = (int)gm;
         }
+        p.KC = acc_kblocks;
         const int items = p.T * p.Mtiles;
         profile_mark(0, stream);
         predict_var_tf32_kernel<<<items < grid ? items : grid, T_THREADS, T_SMEM, stream>>>(map_a_hi, map_a_lo, map_b_hi,
                                                                                             map_b_lo, p);
         profile_mark(1, stream);
         IPP_LAUNCH_CHECK();
-        predict_finalize_tf32_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, T, (int)mc,
+        predict_finalize_tf32_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, 2 * T, (int)mc,
                                                                                       kern->variance, noise_add, var + s);
         IPP_LAUNCH_CHECK();
     }

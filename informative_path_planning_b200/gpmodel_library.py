@@ -111,6 +111,7 @@ class GPModel(object):
         self._ig = None            # cached (binv, logdet_before) for info_gain
         self._tf32 = None          # cached (linv_hi, linv_lo, ld) float32 split of L^-1 for the 3xTF32 predict
         self.predict_precision = 'fp64'   # 'tf32x3': batched predicts run on the tcgen05 path (see predict_device)
+        self.tf32_acc_kblocks = 1         # tensor-core accumulation chunk of the 3xTF32 path (1 = most accurate)
         # Rollout forks may defer the "is the Schur block positive definite" read-back (a device->host
         # sync per append) to one check per rollout: see defer_checks() / check_pending().
         self._defer = False
@@ -301,7 +302,8 @@ class GPModel(object):
         var = torch.empty(M, dtype=torch.float64, device=xq_d.device)
         work = L.workspace(L.lib.ipp_gp_predict_tf32_workspace(N, M), slot='tf32')
         L.check(L.lib.ipp_gp_predict_tf32(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                          L.ptr(hi), L.ptr(lo), ldl, float(self.noise) if include_noise else 0.0,
+                                          L.ptr(hi), L.ptr(lo), ldl, int(self.tf32_acc_kblocks),
+                                          float(self.noise) if include_noise else 0.0,
                                           L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
         return mean, var
 
