@@ -67,6 +67,25 @@ class Node(object):
         print(self.name)
 
 
+_prior_transforms = {}
+
+
+def _prior_draw(k, variance):
+    """np.random.multivariate_normal(zeros(k), eye(k) * variance) (reference mcts_library.py:418-422), bit for bit
+    and consuming the same global random stream, without the per-call SVD + PSD check: numpy's legacy sampler is
+    standard_normal(k) @ (sqrt(s)[:, None] * v) with (u, s, v) = svd(cov), which for a fixed (k, variance) is one
+    constant k x k matrix."""
+    key = (int(k), float(variance))
+    tr = _prior_transforms.get(key)
+    if tr is None:
+        _, s, v = np.linalg.svd(np.eye(k) * float(variance))
+        tr = _prior_transforms[key] = np.sqrt(s)[:, None] * v
+    x = np.random.standard_normal((k,)).reshape(-1, k)
+    x = np.dot(x, tr)
+    x += np.zeros((k,))
+    return x.reshape(k)
+
+
 def _xobs(action):
     obs = np.array(action)
     return np.vstack([obs[:, 0], obs[:, 1]]).T
@@ -188,8 +207,7 @@ class Tree(object):
     def simulate_observation(self, xobs, belief):
         n_points = xobs.shape[0]
         if belief.model is None:
-            zobs = np.random.multivariate_normal(mean=np.zeros((n_points,)), cov=np.eye(n_points) * belief.variance)
-            return np.reshape(zobs, (n_points, 1))
+            return np.reshape(_prior_draw(n_points, belief.variance), (n_points, 1))
         return belief.posterior_samples(xobs, full_cov=False, size=1)
 
     def _expand_action(self, node, pending, belief, levels=None):
@@ -268,7 +286,8 @@ class Tree(object):
         return random.choice([key for key in vals.keys() if vals[key] == top])
 
     def build_action_children(self, parent):
-        actions, dense_paths = self.path_generator.get_path_set(parent.pose)
+        lazy = getattr(self.path_generator, 'get_path_set_lazy', None)     # same paths, dense ones materialised on demand
+        actions, dense_paths = lazy(parent.pose) if lazy is not None else self.path_generator.get_path_set(parent.pose)
         if len(actions) == 0:
             return
         for i, action in enumerate(list(actions.keys())):
@@ -422,7 +441,10 @@ class cMCTS(object):
         best_child = random.choice([node for node in self.tree.root.children if node.nqueries == most])
         all_vals = {i: child.reward / float(child.nqueries) for i, child in enumerate(self.tree.root.children)}
         paths, dense_paths = self.path_generator.get_path_set(self.cp)
-        return (best_child.action, best_child.dense_path, best_child.reward / float(best_child.nqueries), paths,
+        best_dense = best_child.dense_path
+        if hasattr(best_dense, 'tolist'):
+            best_dense = best_dense.tolist()                  # the reference returns a list of (x, y, heading) tuples
+        return (best_child.action, best_dense, best_child.reward / float(best_child.nqueries), paths,
                 all_vals, self.max_locs, self.max_val, self.target)
 
 

@@ -27,6 +27,31 @@ class FreeWorld(object):
         return []
 
 
+class LazyPath(object):
+    """A dense path kept as an (n, 3) array and turned into the reference's tuples on access.  The tree search
+    only ever looks at dense_path[-1] (the pose of the next belief node) for all but the chosen action, so
+    building ~100 tuples per candidate path per expanded node is wasted host time."""
+
+    __slots__ = ('arr',)
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __len__(self):
+        return self.arr.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [tuple(c) for c in self.arr[i].tolist()]
+        return tuple(self.arr[i].tolist())
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def tolist(self):
+        return [tuple(c) for c in self.arr.tolist()]
+
+
 class Path_Generator(object):
     def __init__(self, frontier_size, horizon_length, turning_radius, sample_step, extent, obstacle_world=None):
         self.fs = frontier_size
@@ -40,17 +65,24 @@ class Path_Generator(object):
         self.obstacle_world = FreeWorld() if obstacle_world is None else obstacle_world
 
     def generate_frontier_points(self):
-        """reference :44-83"""
+        """reference :44-83 (plain-float arithmetic: this runs once per expanded tree node)"""
         goals = []
-        for a in np.linspace(-2.35, 2.35, self.fs):
-            x = self.hl * np.cos(self.cp[2] + a) + self.cp[0]
-            y = self.hl * np.sin(self.cp[2] + a) + self.cp[1]
-            p = self.cp[2] + a
-            if np.linalg.norm([self.cp[0] - x, self.cp[1] - y]) <= self.tr:
+        angles = self.__dict__.get('_angles')
+        if angles is None or len(angles) != self.fs:
+            angles = self._angles = [float(a) for a in np.linspace(-2.35, 2.35, self.fs)]
+        cx, cy, ch = float(self.cp[0]), float(self.cp[1]), float(self.cp[2])
+        hl, tr = self.hl, self.tr
+        x_lo, x_hi = self.extent[0] + 3 * tr, self.extent[1] - 3 * tr
+        y_lo, y_hi = self.extent[2] + 3 * tr, self.extent[3] - 3 * tr
+        for a in angles:
+            p = ch + a
+            x = hl * math.cos(p) + cx
+            y = hl * math.sin(p) + cy
+            if math.sqrt((cx - x) * (cx - x) + (cy - y) * (cy - y)) <= tr:
                 continue
-            if x > self.extent[1] - 3 * self.tr or x < self.extent[0] + 3 * self.tr:
+            if x > x_hi or x < x_lo:
                 continue
-            if y > self.extent[3] - 3 * self.tr or y < self.extent[2] + 3 * self.tr:
+            if y > y_hi or y < y_lo:
                 continue
             goals.append((x, y, p))
         goals.append(self.cp)
@@ -195,12 +227,20 @@ class Dubins_Path_Generator(Path_Generator):
 
     use_native = True
 
-    def buffered_paths(self):
+    def buffered_paths(self, lazy=False):
         if self.use_native and isinstance(self.obstacle_world, FreeWorld) and len(self.goals) > 0:
-            return self._buffered_paths_native()
+            return self._buffered_paths_native(lazy)
         return self._buffered_paths_python()
 
-    def _buffered_paths_native(self):
+    def get_path_set_lazy(self, current_pose):
+        """get_path_set for the tree search: dense paths come back as LazyPath views (same values)."""
+        self.cp = current_pose
+        self.generate_frontier_points()
+        coords, true_coords = self.buffered_paths(lazy=True)
+        self.samples = coords
+        return coords, true_coords
+
+    def _buffered_paths_native(self, lazy=False):
         import ctypes
         from . import _lib as L
         G = len(self.goals)
@@ -223,7 +263,7 @@ class Dubins_Path_Generator(Path_Generator):
         for i in range(G):
             if ns[i] >= 2:
                 sampling_path[i] = [tuple(c) for c in samp[i, :ns[i]].tolist()]
-                true_path[i] = [tuple(c) for c in dense[i, :nd[i]].tolist()]
+                true_path[i] = LazyPath(dense[i, :nd[i]]) if lazy else [tuple(c) for c in dense[i, :nd[i]].tolist()]
         return sampling_path, true_path
 
     def _buffered_paths_python(self):

@@ -102,3 +102,33 @@ def test_paths_library_matches_oracle_generator():
         assert np.hypot(end[0] - goal[0], end[1] - goal[1]) < 0.5 + 1e-9      # samples every ss; the end point itself is excluded
         steps = np.hypot(np.diff([c[0] for c in pts]), np.diff([c[1] for c in pts]))
         assert np.all(steps < 0.5 + 1e-6)
+
+
+def test_prior_draw_is_numpys_multivariate_normal_bit_for_bit():
+    """The planner's fast prior sampler must consume np.random exactly like the reference's
+    np.random.multivariate_normal(zeros(k), eye(k) * variance) call (mcts_library.py:418-422)."""
+    import numpy as np
+    from informative_path_planning_b200 import mcts_library as mc
+    for k in (1, 3, 4, 7, 20):
+        for var in (100.0, 2.5):
+            np.random.seed(5)
+            want = [np.random.multivariate_normal(mean=np.zeros((k,)), cov=np.eye(k) * var) for _ in range(4)]
+            after_want = np.random.random()
+            np.random.seed(5)
+            got = [mc._prior_draw(k, var) for _ in range(4)]
+            after_got = np.random.random()
+            assert all(np.array_equal(a, b) for a, b in zip(want, got))
+            assert after_want == after_got
+
+
+def test_lazy_dense_paths_equal_eager_ones():
+    import numpy as np
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    for pose in ((5.0, 5.0, 0.3), (9.6, 9.5, 0.3), (0.4, 5.0, 3.0)):
+        g = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, (0, 10, 0, 10))
+        pa, ta = g.get_path_set(pose)
+        pb, tb = g.get_path_set_lazy(pose)
+        assert pa == pb and sorted(ta) == sorted(tb)
+        for k in ta:
+            assert ta[k] == tb[k].tolist() == list(tb[k]) and ta[k][-1] == tb[k][-1] and len(ta[k]) == len(tb[k])
+            assert ta[k][2:5] == tb[k][2:5]
