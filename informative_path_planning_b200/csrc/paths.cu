@@ -77,16 +77,24 @@ extern "C" int ipp_dubins_path_set(const double* pose, const double* goals, int 
         const double total = best_len * rho;
         double* dg = dense + (size_t)gi * max_dense * 3;
         int nd = 0;
+        // state at the start of each of the three segments (a fully traversed segment always contributes the same
+        // increment, so it is evaluated once per path instead of once per sample: 2 trig calls per sample, not 12)
+        double sx[4], sy[4], sth[4];
+        sx[0] = 0; sy[0] = 0; sth[0] = pose[2];
+        for (int k = 0; k < 3; ++k) {
+            sx[k + 1] = sx[k]; sy[k + 1] = sy[k]; sth[k + 1] = sth[k];
+            segment(sx[k + 1], sy[k + 1], sth[k + 1], w[best].len[k] < 0 ? 0 : w[best].len[k], w[best].kinds[k]);
+        }
         for (int si = 0; nd < max_dense; ++si) {
             const double s = si * dense_step;
             if (!(s < total)) break;
-            double rem = s / rho, x = 0, y = 0, th = pose[2];
-            for (int k = 0; k < 3; ++k) {
-                double use = rem < w[best].len[k] ? rem : w[best].len[k];
-                if (use < 0) use = 0;
-                segment(x, y, th, use, w[best].kinds[k]);
-                rem -= use;
-            }
+            double rem = s / rho;
+            int k = 0;
+            while (k < 2 && !(rem < w[best].len[k])) { rem -= (w[best].len[k] < 0 ? 0 : w[best].len[k]); ++k; }
+            double x = sx[k], y = sy[k], th = sth[k];
+            double use = rem < w[best].len[k] ? rem : w[best].len[k];
+            if (use < 0) use = 0;
+            segment(x, y, th, use, w[best].kinds[k]);
             const double cx = x * rho + pose[0], cy = y * rho + pose[1];
             if (!(cx > extent[0] && cx < extent[1] && cy > extent[2] && cy < extent[3])) break;
             dg[3 * nd] = cx; dg[3 * nd + 1] = cy; dg[3 * nd + 2] = mod2pi(th);

@@ -170,6 +170,65 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
     if (tid == 0) *p.info = s_bad;
 }
 
+// ---- base posterior over the rollout's M <= 128 points.  A 128-row DMMA tile would be > 80 % padding here and only
+// N / 128 CTAs would stream the N x N operand (measured 130 us per GEMM at N = 900), so the two contractions are
+// bandwidth-shaped SIMT kernels over all SMs instead:
+//   T1[m][n] = sum_j W[n][j] Kxt[m][j]          one warp per row n of W^-1 (the only N^2 traffic), <= 32 m per pass
+//   C0[m][m'] = Kqq[m][m'] - sum_n T1[m][n] Kxt[m'][n]   one warp per (m, m' <= m), mirrored
+__global__ void __launch_bounds__(256) rollout_tw_kernel(const double* __restrict__ W, int64_t ldw, int N,
+                                                         const double* __restrict__ Kxt, int64_t ldk, int M,
+                                                         double* __restrict__ T1) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const double* row = W + (int64_t)n * ldw;
+    for (int m0 = 0; m0 < M; m0 += 32) {
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+        const int mm = (M - m0) < 32 ? (M - m0) : 32;
+        for (int j = lane; j < N; j += 32) {
+            const double w = row[j];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < mm) acc[i] = fma(w, Kxt[(int64_t)(m0 + i) * ldk + j], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (i < mm) {
+                double t = acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) T1[(int64_t)(m0 + i) * ldk + n] = t;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const double* __restrict__ pts,
+                                                          const double* __restrict__ T1, const double* __restrict__ Kxt,
+                                                          int64_t ldk, int N, int M, double* __restrict__ cov, int64_t ldc) {
+    const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= M * (M + 1) / 2) return;
+    int a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);           // pair = a (a + 1) / 2 + b, b <= a
+    while (a * (a + 1) / 2 > pair) --a;
+    while ((a + 1) * (a + 2) / 2 <= pair) ++a;
+    const int b = pair - a * (a + 1) / 2;
+    const double* t = T1 + (int64_t)a * ldk;
+    const double* kx = Kxt + (int64_t)b * ldk;
+    double s = 0.0;
+    for (int n = lane; n < N; n += 32) s = fma(t[n], kx[n], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double kqq = (D == 2) ? rbf_eval<2>(k, pts + 2 * a, pts + 2 * b) : rbf_eval<3>(k, pts + 3 * a, pts + 3 * b);
+        const double v = kqq - s;
+        cov[(int64_t)a * ldc + b] = v;
+        cov[(int64_t)b * ldc + a] = v;
+    }
+}
+
 static size_t rollout_smem(int M) {
     return sizeof(double) * ((size_t)M * (M + 1) + M + (size_t)M * (RO_MAX_BLOCK + 1) + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1) +
                              RO_MAX_BLOCK + 2 * (RO_THREADS / 32));
@@ -182,7 +241,7 @@ using namespace ipp;
 extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
     if (M <= 0) return 16;
     const int64_t ldc = round_up(M, 2);
-    return ipp_gp_predict_cov_workspace(N, M) + M * ldc + round_up(M, 2) + 16;
+    return 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
 }
 
 extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
@@ -215,7 +274,18 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
     double* cov0 = work;
     double* mean0 = cov0 + (int64_t)M * ldc;
     double* sub = mean0 + round_up(M, 2);
-    IPP_TRY(ipp_gp_predict_cov(kern, X, N, alpha, winv, ldw, 0.0, pts, M, mean0, cov0, ldc, sub, stream_));
+    {
+        const int64_t ldk = round_up(N, 16);
+        double* Kxt = sub;
+        double* T1 = sub + (int64_t)M * ldk;
+        IPP_TRY(launch_rbf_queries(*kern, X, N, alpha, pts, M, Kxt, ldk, mean0, stream));
+        rollout_tw_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(winv, ldw, (int)N, Kxt, ldk, M, T1);
+        IPP_LAUNCH_CHECK();
+        const int pairs = M * (M + 1) / 2;
+        rollout_cov_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
+                                                                          (int)N, M, cov0, ldc);
+        IPP_LAUNCH_CHECK();
+    }
     p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc; p.zobs = zobs;
     p.M = M; p.L = L; p.kind = kind; p.maxes = maxes_dev; p.S = (int)S;
     p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;

@@ -14,7 +14,7 @@ for N in [int(a) for a in (sys.argv[1:] or ['333', '1024', '2048', '4096', '8192
     m = pkg.OnlineGPModel(R, 1.0, 100.0, noise=0.5)
     m.add_data(X, z)
     m.tf32_acc_kblocks = KC
-    M = 1 << 20
+    M = int(os.environ.get('M', str(1 << 20)))
     q = L.to_device(rng.uniform(0, 10, (M, 2)))
     res = {'N': N, 'M': M, 'acc_kblocks': KC}
     for prec in ('fp64', 'tf32x3'):
