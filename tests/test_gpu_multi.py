@@ -59,7 +59,12 @@ def test_two_ranks_match_one_gpu(tmp_path):
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
     from informative_path_planning_b200 import aq_library as aq, gpmodel_library as gp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    try:
+        mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    except Exception as e:      # one retry on a fresh port: NCCL bring-up on a just-booted box failed once in ~8 runs
+        import sys
+        sys.stderr.write('first 2-rank attempt failed, retrying once: %r\n' % (e,))
+        mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     X, z, q, pts, offs = _inputs()
     m = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
     m.add_data(X[:480], z[:480])
