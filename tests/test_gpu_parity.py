@@ -662,7 +662,7 @@ def test_predict_tf32x3_mode_against_fp64_mode(pkg, N, M):
     mu64, var64 = m.predict_value(q)
     m.predict_precision = 'tf32x3'
     mu32, var32 = m.predict_value(q)
-    np.testing.assert_allclose(mu32, mu64, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(mu32, mu64, rtol=1e-8, atol=1e-7)      # same FP64 accumulation; exp to 2^-36 instead of < 1 ulp
     err = np.abs(var32 - var64)
     assert err.max() <= 1e-5 * 100.0, err.max()
     assert (err / var64).max() <= 2e-3, (err / var64).max()
