@@ -397,6 +397,35 @@ def main():
                                               'cpu_grid_points_per_s': gs / dt4, 'cpu_sample': '%d grid points, numpy' % gs}
         except Exception as e:
             extras['rff_F1000_S100_G2^20'] = {'error': repr(e)}
+        # config 5 with the candidate paths generated on the device: 65536 (pose, goal) pairs ->
+        # shortest Dubins curves sampled / trimmed like the reference generator -> ragged points -> UCB rewards
+        try:
+            from informative_path_planning_b200.paths_library import dubins_paths_device, ragged_points
+            r5 = np.random.default_rng(5)
+            P5 = 65536
+            poses5 = np.column_stack([r5.uniform(1, 9, P5), r5.uniform(1, 9, P5), r5.uniform(-np.pi, np.pi, P5)])
+            ang5 = poses5[:, 2] + r5.uniform(-2.35, 2.35, P5)
+            goals5 = np.column_stack([poses5[:, 0] + 3.0 * np.cos(ang5), poses5[:, 1] + 3.0 * np.sin(ang5), ang5])
+            poses5_d, goals5_d = L.to_device(poses5), L.to_device(goals5)
+
+            def pipeline():
+                s_d, c_d, _ = dubins_paths_device(poses5_d, goals5_d, 0.3, 0.5, RANGES)
+                pts_d, offs_d, _ = ragged_points(s_d, c_d)
+                rew, _ = model.reward_paths_device(L.REWARD_UCB, pts_d, offs_d, params=sqb)
+                return pts_d.shape[0], offs_d.shape[0] - 1, rew
+            pipeline()
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(); dubins_paths_device(poses5_d, goals5_d, 0.3, 0.5, RANGES); g1.record()
+            r0.record(); n_pts, n_paths, _ = pipeline(); r1.record()
+            torch.cuda.synchronize()
+            extras['dubins_on_device_N4096'] = {
+                'pairs': P5, 'kept_paths': int(n_paths), 'points': int(n_pts), 'path_generation_ms': g0.elapsed_time(g1),
+                'generate_plus_ucb_ms': r0.elapsed_time(r1), 'reward_evals_per_s': n_paths / (r0.elapsed_time(r1) / 1e3),
+                'note': 'shortest Dubins curves (goal 3.0 ahead, rho 0.3, samples every 0.5, border-trimmed), FP64 rewards'}
+        except Exception as e:
+            extras['dubins_on_device_N4096'] = {'error': repr(e)}
         # BASELINE config 3, second arm: 3xTF32 mode (tcgen05 kind::tf32, Cholesky form) on the same belief / queries
         try:
             mu64, var64 = model.predict_device(xq)

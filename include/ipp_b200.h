@@ -209,6 +209,14 @@ int ipp_dubins_path_set(const double* pose, const double* goals, int G, double r
                         double* samp, int* samp_count, int max_samp,
                         double* dense, int* dense_count, int max_dense);
 
+/* ---- 8f (caller side), device form for large batches (BASELINE config 5: 64k candidate paths): one thread per
+ *      independent (start pose, goal pose) pair, same closed forms and trimming as ipp_dubins_path_set.
+ *      poses[P][3], goals[P][3], samp[P][max_samp][3], counts[P] (int32, 0 = dropped), end_pose[P][3] (may be NULL;
+ *      the last kept configuration = pose of the next belief node) are DEVICE pointers; extent[4] is host. */
+int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P, double rho, double dense_step,
+                            int keep_every, const double* extent_host, double border,
+                            double* samp, int32_t* counts, int max_samp, double* end_pose, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,4 +1,7 @@
-// Host-side (CPU, no kernel) Dubins path-set generation: the native counterpart of the `dubins` C library
+// Dubins candidate paths.  (1) Host-side (CPU, no kernel) path-set generation for one pose; (2) the same generator as a
+// CUDA kernel for large batches of independent (pose, goal) pairs (BASELINE config 5: 64k candidate paths), one
+// thread per path, sharing the closed forms below through __host__ __device__ functions.
+// (1): the native counterpart of the `dubins` C library
 // the reference calls from paths_library.py:141-175 (dubins.shortest_path + path.sample_many), plus the
 // border trimming of Dubins_Path_Generator.buffered_paths for the obstacle-free world.
 // Classical six-word closed form (LSL, RSR, LSR, RSL, RLR, LRL; Shkel & Lumelsky 2001).
@@ -7,40 +10,145 @@
 
 namespace {
 
-const double TWO_PI = 6.283185307179586476925286766559;
+#define TWO_PI 6.283185307179586476925286766559
 
-inline double mod2pi(double t) { return t - TWO_PI * floor(t / TWO_PI); }
+__host__ __device__ inline double mod2pi(double t) { return t - TWO_PI * floor(t / TWO_PI); }
 
 struct Word { int kinds[3]; double len[3]; bool ok; };   // kind: 0 = L, 1 = S, 2 = R
 
-void all_words(double alpha, double beta, double d, Word out[6]) {
+__host__ __device__ inline Word make_word(int k0, int k1, int k2, double a, double b, double c) {
+    Word w;
+    w.kinds[0] = k0; w.kinds[1] = k1; w.kinds[2] = k2;
+    w.len[0] = a; w.len[1] = b; w.len[2] = c;
+    w.ok = true;
+    return w;
+}
+
+__host__ __device__ void all_words(double alpha, double beta, double d, Word out[6]) {
     const double sa = sin(alpha), sb = sin(beta), ca = cos(alpha), cb = cos(beta), cab = cos(alpha - beta);
     for (int i = 0; i < 6; ++i) out[i].ok = false;
     double p2, tmp, p, t;
     p2 = 2 + d * d - 2 * cab + 2 * d * (sa - sb);                                   // LSL
     if (p2 >= 0) { tmp = atan2(cb - ca, d + sa - sb);
-        out[0] = {{0, 1, 0}, {mod2pi(-alpha + tmp), sqrt(p2), mod2pi(beta - tmp)}, true}; }
+        out[0] = make_word(0, 1, 0, mod2pi(-alpha + tmp), sqrt(p2), mod2pi(beta - tmp)); }
     p2 = 2 + d * d - 2 * cab + 2 * d * (sb - sa);                                   // RSR
     if (p2 >= 0) { tmp = atan2(ca - cb, d - sa + sb);
-        out[1] = {{2, 1, 2}, {mod2pi(alpha - tmp), sqrt(p2), mod2pi(-beta + tmp)}, true}; }
+        out[1] = make_word(2, 1, 2, mod2pi(alpha - tmp), sqrt(p2), mod2pi(-beta + tmp)); }
     p2 = -2 + d * d + 2 * cab + 2 * d * (sa + sb);                                  // LSR
     if (p2 >= 0) { p = sqrt(p2); tmp = atan2(-ca - cb, d + sa + sb) - atan2(-2.0, p);
-        out[2] = {{0, 1, 2}, {mod2pi(-alpha + tmp), p, mod2pi(-mod2pi(beta) + tmp)}, true}; }
+        out[2] = make_word(0, 1, 2, mod2pi(-alpha + tmp), p, mod2pi(-mod2pi(beta) + tmp)); }
     p2 = d * d - 2 + 2 * cab - 2 * d * (sa + sb);                                   // RSL
     if (p2 >= 0) { p = sqrt(p2); tmp = atan2(ca + cb, d - sa - sb) - atan2(2.0, p);
-        out[3] = {{2, 1, 0}, {mod2pi(alpha - tmp), p, mod2pi(beta - tmp)}, true}; }
+        out[3] = make_word(2, 1, 0, mod2pi(alpha - tmp), p, mod2pi(beta - tmp)); }
     tmp = (6.0 - d * d + 2 * cab + 2 * d * (sa - sb)) / 8.0;                        // RLR
     if (fabs(tmp) <= 1) { p = mod2pi(TWO_PI - acos(tmp)); t = mod2pi(alpha - atan2(ca - cb, d - sa + sb) + p / 2.0);
-        out[4] = {{2, 0, 2}, {t, p, mod2pi(alpha - beta - t + p)}, true}; }
+        out[4] = make_word(2, 0, 2, t, p, mod2pi(alpha - beta - t + p)); }
     tmp = (6.0 - d * d + 2 * cab + 2 * d * (sb - sa)) / 8.0;                        // LRL
     if (fabs(tmp) <= 1) { p = mod2pi(TWO_PI - acos(tmp)); t = mod2pi(-alpha - atan2(ca - cb, d + sa - sb) + p / 2.0);
-        out[5] = {{0, 2, 0}, {t, p, mod2pi(mod2pi(beta) - alpha - t + p)}, true}; }
+        out[5] = make_word(0, 2, 0, t, p, mod2pi(mod2pi(beta) - alpha - t + p)); }
 }
 
-inline void segment(double& x, double& y, double& th, double len, int kind) {
+__host__ __device__ inline void segment(double& x, double& y, double& th, double len, int kind) {
     if (kind == 0) { x += sin(th + len) - sin(th); y += -cos(th + len) + cos(th); th += len; }
     else if (kind == 2) { x += -sin(th - len) + sin(th); y += cos(th - len) - cos(th); th -= len; }
     else { x += cos(th) * len; y += sin(th) * len; }
+}
+
+
+// One (pose, goal) pair.  dense (may be NULL on the device path): every configuration; samp: the kept ones.
+// Returns the number of kept samples (0 = path dropped); *dense_n = number of dense configurations of the true path;
+// end[3] = its last configuration (the pose of the next belief node).
+__host__ __device__ int dubins_one(const double* pose, const double* q1, double rho, double dense_step, int keep_every,
+                                   const double* extent, double border, double* sg, int max_samp,
+                                   double* dg, int max_dense, int* dense_n, double* end) {
+    const double dx = q1[0] - pose[0], dy = q1[1] - pose[1];
+    const double D = hypot(dx, dy), d = D / rho;
+    const double theta = D > 0 ? mod2pi(atan2(dy, dx)) : 0.0;
+    const double alpha = mod2pi(pose[2] - theta), beta = mod2pi(q1[2] - theta);
+    Word w[6];
+    all_words(alpha, beta, d, w);
+    int best = -1;
+    double best_len = 0;
+    for (int i = 0; i < 6; ++i) {
+        if (!w[i].ok) continue;
+        const double L = w[i].len[0] + w[i].len[1] + w[i].len[2];
+        if (best < 0 || L < best_len) { best = i; best_len = L; }
+    }
+    *dense_n = 0;
+    if (best < 0) return 0;
+    const Word wb = w[best];
+    const double total = best_len * rho;
+    // state at the start of each of the three segments (a fully traversed segment always contributes the same
+    // increment, so it is evaluated once per path instead of once per sample: 2 trig calls per sample, not 12)
+    double sx[4], sy[4], sth[4];
+    sx[0] = 0; sy[0] = 0; sth[0] = pose[2];
+    for (int k = 0; k < 3; ++k) {
+        sx[k + 1] = sx[k]; sy[k + 1] = sy[k]; sth[k + 1] = sth[k];
+        segment(sx[k + 1], sy[k + 1], sth[k + 1], wb.len[k] < 0 ? 0 : wb.len[k], wb.kinds[k]);
+    }
+    // dense sweep: cut at the first configuration outside the open extent; every keep_every-th one is a sample
+    // candidate, trimmed by the reference's loop (python: `ttemp = ttemp[0:m-1]`, including its negative-index quirk)
+    int nd = 0, orig = 0, cur = 0;
+    bool trimmed_any = false;
+    for (int si = 0; nd < max_dense; ++si) {
+        const double s = si * dense_step;
+        if (!(s < total)) break;
+        double rem = s / rho;
+        int k = 0;
+        while (k < 2 && !(rem < wb.len[k])) { rem -= (wb.len[k] < 0 ? 0 : wb.len[k]); ++k; }
+        double x = sx[k], y = sy[k], th = sth[k];
+        double use = rem < wb.len[k] ? rem : wb.len[k];
+        if (use < 0) use = 0;
+        segment(x, y, th, use, wb.kinds[k]);
+        const double cx = x * rho + pose[0], cy = y * rho + pose[1];
+        if (!(cx > extent[0] && cx < extent[1] && cy > extent[2] && cy < extent[3])) break;
+        const double cth = mod2pi(th);
+        if (dg) { dg[3 * nd] = cx; dg[3 * nd + 1] = cy; dg[3 * nd + 2] = cth; }
+        if (nd % keep_every == 0 && orig < max_samp) {
+            sg[3 * orig] = cx; sg[3 * orig + 1] = cy; sg[3 * orig + 2] = cth;
+            ++orig;
+        }
+        ++nd;
+    }
+    (void)trimmed_any;
+    cur = orig;
+    for (int m = 0; m < orig; ++m) {
+        const double* c = sg + 3 * m;
+        if (c[0] <= extent[0] + border || c[0] >= extent[1] - border || c[1] <= extent[2] + border || c[1] >= extent[3] - border) {
+            int stop = m - 1;                       // python: ttemp = ttemp[0:m-1]
+            if (stop < 0) stop = cur + stop;        // negative stop counts from the end
+            if (stop < 0) stop = 0;
+            if (stop < cur) cur = stop;
+        }
+    }
+    if (cur < 2) return 0;
+    // true_path = ftemp[0 : ftemp.index(ttemp[-1]) + 1]: first dense configuration equal to the last kept one
+    const double* last = sg + 3 * (cur - 1);
+    int idx = (cur - 1) * keep_every;
+    if (dg) {
+        for (int i = 0; i < idx; ++i)
+            if (dg[3 * i] == last[0] && dg[3 * i + 1] == last[1] && dg[3 * i + 2] == last[2]) { idx = i; break; }
+    }
+    *dense_n = idx + 1;
+    if (end) { end[0] = last[0]; end[1] = last[1]; end[2] = last[2]; }
+    return cur;
+}
+
+__global__ void dubins_paths_kernel(const double* __restrict__ poses, const double* __restrict__ goals, int64_t P,
+                                    double rho, double dense_step, int keep_every, double e0, double e1, double e2,
+                                    double e3, double border, double* __restrict__ samp, int32_t* __restrict__ counts,
+                                    int max_samp, double* __restrict__ end_pose) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double extent[4] = {e0, e1, e2, e3};
+    const double pose[3] = {poses[3 * p], poses[3 * p + 1], poses[3 * p + 2]};
+    const double goal[3] = {goals[3 * p], goals[3 * p + 1], goals[3 * p + 2]};
+    int dense_n = 0;
+    double end[3] = {pose[0], pose[1], pose[2]};
+    const int n = dubins_one(pose, goal, rho, dense_step, keep_every, extent, border, samp + p * max_samp * 3, max_samp,
+                             nullptr, 1 << 30, &dense_n, end);
+    counts[p] = n;
+    if (end_pose) { end_pose[3 * p] = end[0]; end_pose[3 * p + 1] = end[1]; end_pose[3 * p + 2] = end[2]; }
 }
 
 }  // namespace
@@ -57,75 +165,26 @@ extern "C" int ipp_dubins_path_set(const double* pose, const double* goals, int 
     IPP_CHECK_ARG(pose && goals && extent && samp && samp_count && dense && dense_count, "null pointer");
     IPP_CHECK_ARG(G >= 0 && rho > 0 && dense_step > 0 && keep_every >= 1 && max_samp >= 2 && max_dense >= 2, "bad argument");
     for (int gi = 0; gi < G; ++gi) {
-        const double* q1 = goals + 3 * gi;
-        const double dx = q1[0] - pose[0], dy = q1[1] - pose[1];
-        const double D = hypot(dx, dy), d = D / rho;
-        const double theta = D > 0 ? mod2pi(atan2(dy, dx)) : 0.0;
-        const double alpha = mod2pi(pose[2] - theta), beta = mod2pi(q1[2] - theta);
-        Word w[6];
-        all_words(alpha, beta, d, w);
-        int best = -1;
-        double best_len = 0;
-        for (int i = 0; i < 6; ++i) {
-            if (!w[i].ok) continue;
-            const double L = w[i].len[0] + w[i].len[1] + w[i].len[2];
-            if (best < 0 || L < best_len) { best = i; best_len = L; }
-        }
-        samp_count[gi] = 0;
-        dense_count[gi] = 0;
-        if (best < 0) continue;
-        const double total = best_len * rho;
-        double* dg = dense + (size_t)gi * max_dense * 3;
-        int nd = 0;
-        // state at the start of each of the three segments (a fully traversed segment always contributes the same
-        // increment, so it is evaluated once per path instead of once per sample: 2 trig calls per sample, not 12)
-        double sx[4], sy[4], sth[4];
-        sx[0] = 0; sy[0] = 0; sth[0] = pose[2];
-        for (int k = 0; k < 3; ++k) {
-            sx[k + 1] = sx[k]; sy[k + 1] = sy[k]; sth[k + 1] = sth[k];
-            segment(sx[k + 1], sy[k + 1], sth[k + 1], w[best].len[k] < 0 ? 0 : w[best].len[k], w[best].kinds[k]);
-        }
-        for (int si = 0; nd < max_dense; ++si) {
-            const double s = si * dense_step;
-            if (!(s < total)) break;
-            double rem = s / rho;
-            int k = 0;
-            while (k < 2 && !(rem < w[best].len[k])) { rem -= (w[best].len[k] < 0 ? 0 : w[best].len[k]); ++k; }
-            double x = sx[k], y = sy[k], th = sth[k];
-            double use = rem < w[best].len[k] ? rem : w[best].len[k];
-            if (use < 0) use = 0;
-            segment(x, y, th, use, w[best].kinds[k]);
-            const double cx = x * rho + pose[0], cy = y * rho + pose[1];
-            if (!(cx > extent[0] && cx < extent[1] && cy > extent[2] && cy < extent[3])) break;
-            dg[3 * nd] = cx; dg[3 * nd + 1] = cy; dg[3 * nd + 2] = mod2pi(th);
-            ++nd;
-        }
-        // ttemp = ftemp[0::keep_every], trimmed by the reference's loop
-        int orig = (nd + keep_every - 1) / keep_every;
-        if (orig > max_samp) orig = max_samp;
-        int cur = orig;
-        for (int m = 0; m < orig; ++m) {
-            const double* c = dg + 3 * (m * keep_every);
-            if (c[0] <= extent[0] + border || c[0] >= extent[1] - border || c[1] <= extent[2] + border || c[1] >= extent[3] - border) {
-                int stop = m - 1;                       // python: ttemp = ttemp[0:m-1]
-                if (stop < 0) stop = cur + stop;        // negative stop counts from the end
-                if (stop < 0) stop = 0;
-                if (stop < cur) cur = stop;
-            }
-        }
-        if (cur < 2) continue;
-        double* sg = samp + (size_t)gi * max_samp * 3;
-        for (int m = 0; m < cur; ++m) {
-            const double* c = dg + 3 * (m * keep_every);
-            sg[3 * m] = c[0]; sg[3 * m + 1] = c[1]; sg[3 * m + 2] = c[2];
-        }
-        samp_count[gi] = cur;
-        // true_path = ftemp[0 : ftemp.index(ttemp[-1]) + 1]: first dense configuration equal to the last kept one
-        const double* last = sg + 3 * (cur - 1);
-        int idx = (cur - 1) * keep_every;
-        for (int i = 0; i < idx; ++i)
-            if (dg[3 * i] == last[0] && dg[3 * i + 1] == last[1] && dg[3 * i + 2] == last[2]) { idx = i; break; }
-        dense_count[gi] = idx + 1;
+        int dn = 0;
+        samp_count[gi] = dubins_one(pose, goals + 3 * gi, rho, dense_step, keep_every, extent, border,
+                                    samp + (size_t)gi * max_samp * 3, max_samp, dense + (size_t)gi * max_dense * 3,
+                                    max_dense, &dn, nullptr);
+        dense_count[gi] = dn;
     }
+    return IPP_OK;
+}
+
+// ---- 8f rank 2: the same generator on the device, one thread per (pose, goal) pair.
+extern "C" int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P, double rho, double dense_step,
+                                       int keep_every, const double* extent_host, double border,
+                                       double* samp, int32_t* counts, int max_samp, double* end_pose, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(poses && goals && extent_host && samp && counts, "null pointer");
+    IPP_CHECK_ARG(P >= 0 && rho > 0 && dense_step > 0 && keep_every >= 1 && max_samp >= 2, "bad argument");
+    if (P == 0) return IPP_OK;
+    dubins_paths_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(poses, goals, P, rho, dense_step, keep_every,
+                                                                   extent_host[0], extent_host[1], extent_host[2],
+                                                                   extent_host[3], border, samp, counts, max_samp, end_pose);
+    IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

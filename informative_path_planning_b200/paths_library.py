@@ -295,3 +295,36 @@ class Dubins_Path_Generator(Path_Generator):
         coords, true_coords = self.buffered_paths()
         self.samples = coords
         return coords, true_coords
+
+
+def dubins_paths_device(poses, goals, turning_radius, sample_step, extent, max_samples=32):
+    """Batched candidate-path generation on the GPU (BASELINE config 5): one Dubins path per (pose, goal) row with the
+    reference generator's sampling (dense step ss/10, every 10th kept) and border trimming (paths_library.py:147-175).
+    poses, goals: (P, 3) arrays or CUDA tensors.  Returns CUDA tensors (samples (P, max_samples, 3), counts (P,) int32,
+    end_poses (P, 3)); counts[p] == 0 means the path was dropped (fewer than 2 samples survive)."""
+    import ctypes
+    import torch
+    from . import _lib as L
+    poses_d, goals_d = L.to_device(poses), L.to_device(goals)
+    P = poses_d.shape[0]
+    samp = torch.empty((P, max_samples, 3), dtype=torch.float64, device=poses_d.device)
+    counts = torch.empty(P, dtype=torch.int32, device=poses_d.device)
+    end = torch.empty((P, 3), dtype=torch.float64, device=poses_d.device)
+    ext = (ctypes.c_double * 4)(*[float(e) for e in extent])
+    L.check(L.lib.ipp_dubins_paths_device(L.ptr(poses_d), L.ptr(goals_d), P, float(turning_radius), float(sample_step) / 10,
+                                          10, ext, float(3 * turning_radius), L.ptr(samp), L.ptr(counts), int(max_samples),
+                                          L.ptr(end), L.stream_ptr()))
+    return samp, counts, end
+
+
+def ragged_points(samp, counts):
+    """(samples, counts) of dubins_paths_device -> (points (M, 2) of the kept paths, offsets (P_kept + 1,) int64,
+    indices of the kept paths): the layout reward_paths_device takes.  torch indexing = plumbing, no numerics."""
+    import torch
+    keep = counts > 0
+    c = counts[keep].to(torch.int64)
+    mask = torch.arange(samp.shape[1], device=samp.device)[None, :] < c[:, None]
+    pts = samp[keep][mask][:, :2].contiguous()
+    offsets = torch.zeros(c.numel() + 1, dtype=torch.int64, device=samp.device)
+    offsets[1:] = torch.cumsum(c, 0)
+    return pts, offsets, torch.nonzero(keep).reshape(-1)

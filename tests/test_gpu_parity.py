@@ -673,3 +673,39 @@ def test_predict_tf32x3_mode_against_fp64_mode(pkg, N, M):
     m.predict_precision = 'fp64'
     v_b = m.predict_value(q[:200])[1]
     assert np.abs(v_a - v_b).max() <= 1e-3
+
+
+def test_dubins_paths_on_device_match_host_generator(pkg):
+    """ipp_dubins_paths_device (one thread per (pose, goal)) against the host generator (itself checked against the
+    Python restatement of paths_library.py:147-175 in test_abi): same kept-sample counts, same points, same end pose,
+    including poses near the walls where the trimming quirk bites; then rewards of the ragged result."""
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator, dubins_paths_device, ragged_points
+    rng = np.random.default_rng(21)
+    poses, goals, want = [], [], []
+    for _ in range(60):
+        pose = (float(rng.uniform(0.3, 9.7)), float(rng.uniform(0.3, 9.7)), float(rng.uniform(-np.pi, np.pi)))
+        g = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES)
+        paths, true_paths = g.get_path_set(pose)
+        for i, goal in enumerate(g.goals):
+            poses.append(pose); goals.append(goal)
+            want.append((paths.get(i), true_paths[i][-1] if i in true_paths else None))
+    samp, counts, end = dubins_paths_device(np.array(poses), np.array(goals), 0.05, 0.5, RANGES)
+    samp, counts, end = samp.cpu().numpy(), counts.cpu().numpy(), end.cpu().numpy()
+    assert len(want) > 700 and (counts == 0).sum() > 10 and (counts > 0).sum() > 500
+    for p, (pts, last) in enumerate(want):
+        if pts is None:
+            assert counts[p] == 0, p
+            continue
+        assert counts[p] == len(pts), (p, counts[p], len(pts))
+        np.testing.assert_allclose(samp[p, :counts[p]], np.array(pts), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(end[p], np.array(last), rtol=1e-12, atol=1e-12)
+    # ragged layout -> one reward call for all kept paths
+    X, z = world(rng, 200, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    s_d, c_d, _ = dubins_paths_device(np.array(poses), np.array(goals), 0.05, 0.5, RANGES)
+    pts_d, offs_d, kept = ragged_points(s_d, c_d)
+    r, _ = m.reward_paths_device(pkg._lib.REWARD_UCB, pts_d, offs_d, params=[np.sqrt(pkg.aq_library.ucb_beta(3))])
+    kept = kept.cpu().numpy()
+    ref = np.array([pkg.aq_library.mean_UCB(time=3, xvals=np.array(want[p][0]), robot_model=m) for p in kept[:40]])
+    np.testing.assert_allclose(r.cpu().numpy()[:40], ref, rtol=1e-10)
