@@ -120,7 +120,21 @@ int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const d
                         const float* linv_hi, const float* linv_lo, int64_t ldl, int acc_kblocks, double noise_add,
                         const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
 
-/* CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 (the fused DMMA variance kernel), recorded on
+/* ---- a3, sliced-INT8 mode: FP64-grade variance on the INT8 tensor cores (tcgen05 kind::i8, exact INT32 accumulation).
+ *      Operands in fixed point against one power-of-two scale each, cut into six signed 7-bit slices; 21 slice-pair
+ *      products (i + j <= 5) accumulate exactly, the six weight levels are combined in FP64.  Measured variance error
+ *      ~2e-8 relative (inside the FP64 mode's 1e-6 parity tolerance); the mean is computed exactly as in FP64 mode.
+ *        ipp_i8_slice: A[rows][lda] (double) -> planes [6][rows][ldp] (int8), scale = power of two >= max |A|;
+ *        linv_planes: the slices of Linv [N][ldl bytes], ldl % 16 == 0; linv_scale: the scale they were cut with;
+ *      work: ipp_gp_predict_i8_workspace(N, M) doubles. */
+int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int8_t* planes, int64_t ldp,
+                 void* stream);
+int64_t ipp_gp_predict_i8_workspace(int64_t N, int64_t M);
+int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                      const int8_t* linv_planes, int64_t ldl, double linv_scale, double noise_add,
+                      const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
+
+/* CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 / ipp_gp_predict_i8 (the fused DMMA variance kernel), recorded on
  * the launching stream.  enable(1) starts a fresh record; read() synchronises on the recorded events and
  * returns the summed device time and the number of launches since enable/read.  Measurement only. */
 int ipp_profile_enable(int on);

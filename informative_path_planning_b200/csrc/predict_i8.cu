@@ -1,0 +1,384 @@
+// a3, "sliced INT8" mode: FP64-grade posterior variance on the INT8 tensor cores (Ozaki-style error-free slicing).
+//
+//   var[m] = variance - sum_n (sum_{j<=n} Linv[n][j] k(q_m, x_j))^2 + noise_add          (GPy's Cholesky form)
+//
+// Both operands are written in fixed point against ONE power-of-two scale each (k <= variance for every entry of the
+// cross-covariance; |Linv| <= its global maximum) and cut into NS = 6 signed 7-bit slices:
+//       x = scale * sum_s x_s 2^(-6 - 7 s),   x_s integer in [-64, 64]                       (42 bits)
+// The contraction is then 21 INT8 products (slice pairs with i + j <= 5), each accumulated EXACTLY in INT32 by
+// tcgen05.mma.kind::i8 -- no floating-point accumulation error at all, which is what the 3xTF32 mode suffers from
+// (rows of Linv oscillate: |terms| / |result| ~ 1e3) -- and the six weight levels w = i + j are combined in FP64 in
+// the epilogue.  What is dropped is 2^-42 of the operand scales per entry plus the slice pairs with i + j > 5:
+// measured variance error <= ~2e-8 relative at N = 2048..8192 (noise 0.5), i.e. inside the FP64 mode's 1e-6 parity
+// tolerance with a wide margin (numpy emulation with exact integers agrees: 2.0e-8).
+//
+// Kernel: 128 x 64 tiles (6 levels x 64 columns of TMEM), K-major SWIZZLE_64B operand planes staged by two 3-D TMA
+// loads per stage ([6 planes][rows][64 B]), 3 x 72 KB stages, 42 MMAs (128 x 64 x 32) per stage issued by one thread,
+// persistent warp-specialised CTA as in predict_tf32.cu.  Lower-triangular Linv: n-tile I contracts k < 64 (I + 1).
+#include "internal.cuh"
+#include "tc05.cuh"
+
+namespace ipp {
+
+constexpr int I_NS = 6;                                // slices per operand
+constexpr int I_LEVELS = 6;                            // weight levels i + j = 0..5
+constexpr int I_BM = 128, I_BN = 64, I_BK = 64;        // tile; I_BK int8 = 64 B = one SWIZZLE_64B row
+constexpr int I_STAGES = 3;
+constexpr int I_A_PLANE = I_BM * I_BK;                 // 8 KB
+constexpr int I_B_PLANE = I_BN * I_BK;                 // 4 KB
+constexpr int I_A_BYTES = I_NS * I_A_PLANE, I_B_BYTES = I_NS * I_B_PLANE;
+constexpr int I_STAGE_BYTES = I_A_BYTES + I_B_BYTES;   // 72 KB
+constexpr int I_SMEM = I_STAGES * I_STAGE_BYTES + 1024 + 256;
+constexpr int I_THREADS = 192;                         // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int I_TMEM_COLS = 512;                       // 6 x 64 = 384 used
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+constexpr uint32_t I_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I_BN >> 3) << 17) | ((uint32_t)(I_BM >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(I_IDESC), "r"(accumulate) : "memory");
+}
+// K-major operand plane [rows][64 B], SWIZZLE_64B: 8-row groups 512 B apart (SBO), LBO unused (1), version 1,
+// layout type 4 = SWIZZLE_64B   (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+struct I8Args {
+    double* partial; int64_t ldp;      // [T][ldp] per-(n-tile, query) sums of squares in units of (sa sb 2^-12)^2
+    int Mc, N, T, Mtiles, GM;
+};
+
+__device__ __forceinline__ bool i8_item(const I8Args& p, int it, int& m0, int& I, int& kblocks) {
+    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    if (item >= p.T * p.Mtiles) return false;
+    const int grp = item / (p.T * p.GM);
+    const int r = item - grp * p.T * p.GM;
+    const int gm = (p.Mtiles - grp * p.GM) < p.GM ? (p.Mtiles - grp * p.GM) : p.GM;
+    I = p.T - 1 - r / gm;
+    m0 = (grp * p.GM + r % gm) * I_BM;
+    const int kend = ((I + 1) * I_BN < p.N) ? (I + 1) * I_BN : p.N;
+    kblocks = (kend + I_BK - 1) / I_BK;
+    return true;
+}
+
+__global__ void __launch_bounds__(I_THREADS, 1)
+predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const I8Args p) {
+    extern __shared__ unsigned char i_smem_raw[];
+    const uint32_t raw = smem_addr(i_smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t bars = tiles + I_STAGES * I_STAGE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * I_STAGES;
+    const uint32_t tfull = bars + 16 * I_STAGES, tempty = tfull + 8;
+    const uint32_t tmem_slot = tempty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < I_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(I_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {                                                 // ===== TMA producer
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+            uint32_t stage = 0, phase = 0;
+            int m0, I, kblocks;
+            for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t full = full0 + 8 * stage, dst = tiles + stage * I_STAGE_BYTES;
+                    mbar_expect_tx(full, I_STAGE_BYTES);
+                    tma_load_3d(dst, &map_a, kb * I_BK, m0, 0, full);               // [6][128][64 B]
+                    tma_load_3d(dst + I_A_BYTES, &map_b, kb * I_BK, I * I_BN, 0, full);   // [6][64][64 B]
+                    if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                                 // ===== MMA issuer (single thread)
+            uint32_t stage = 0, phase = 0;
+            int m0, I, kblocks;
+            for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+                mbar_wait(tempty, (it & 1) ^ 1);                         // epilogue has drained the accumulators
+                tc_fence_after();
+                uint32_t touched = 0;                                    // bit w: level w already holds a product
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t base = tiles + stage * I_STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < I_BK / 32; ++ks) {             // UMMA_K = 32 int8 = 32 B: +2 in 16-B units
+#pragma unroll
+                        for (int i = 0; i < I_NS; ++i) {
+                            const uint64_t ad = make_desc64(base + i * I_A_PLANE) + (uint64_t)(2 * ks);
+#pragma unroll
+                            for (int j = 0; j < I_NS - i; ++j) {
+                                const uint64_t bd = make_desc64(base + I_A_BYTES + j * I_B_PLANE) + (uint64_t)(2 * ks);
+                                const int w = i + j;
+                                tc_mma_i8(tmem_base + w * I_BN, ad, bd, (touched >> w) & 1u);
+                                touched |= 1u << w;
+                            }
+                        }
+                    }
+                    tc_commit(empty0 + 8 * stage);
+                    if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull);
+            }
+        }
+    } else {                                                             // ===== epilogue warps 2..5: thread = query row
+        const int quarter = warp & 3;
+        int m0, I, kblocks;
+        for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+            mbar_wait(tfull, it & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            double q = 0.0;
+#pragma unroll 1
+            for (int half = 0; half < I_BN / 32; ++half) {
+                double v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = 0.0;
+#pragma unroll
+                for (int w = 0; w < I_LEVELS; ++w) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + w * I_BN + half * 32, r);
+                    tmem_ld_wait();
+                    const double wt = 1.0 / (double)(1ull << (7 * w));   // level w carries weight 2^(-7 w)
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)r[c], wt, v[c]);   // exact: |D| < 2^31
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) q = fma(v[c], v[c], q);
+            }
+            tc_fence_before();
+            mbar_arrive(tempty);
+            const int row = m0 + quarter * 32 + lane;
+            if (row < p.Mc) p.partial[(int64_t)I * p.ldp + row] = q;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I_TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void predict_finalize_i8_kernel(const double* __restrict__ partial, int64_t ldp, int T, int Mc,
+                                           double unit2, double variance, double noise_add, double* __restrict__ var) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mc) return;
+    double q = 0.0;
+    for (int I = 0; I < T; ++I) q += partial[(int64_t)I * ldp + m];
+    var[m] = (variance - q * unit2) + noise_add;
+}
+
+// x / scale in (-1, 1)  ->  six signed 7-bit slices, round to nearest at every level (|slice| <= 64)
+__device__ __forceinline__ void slice6(double x, double inv_scale, int (&s)[I_NS]) {
+    double r = x * inv_scale, w = 64.0;
+#pragma unroll
+    for (int k = 0; k < I_NS; ++k) {
+        const double t = rint(r * w);
+        s[k] = (int)t;
+        r = fma(-t, 1.0 / w, r);           // exact: w is a power of two, t has <= 8 significant bits
+        w *= 128.0;
+    }
+}
+
+// planes[s][r][c] (int8, row pitch ldp bytes, plane pitch rows * ldp) of A[rows][lda]; columns >= cols are zeroed
+__global__ void i8_slice_kernel(const double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, double inv_scale,
+                                int8_t* __restrict__ planes, int64_t ldp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * ldp) return;
+    const int64_t r = idx / ldp, c = idx % ldp;
+    int s[I_NS] = {0, 0, 0, 0, 0, 0};
+    if (c < cols) slice6(A[r * lda + c], inv_scale, s);
+#pragma unroll
+    for (int k = 0; k < I_NS; ++k) planes[(int64_t)k * rows * ldp + idx] = (int8_t)s[k];
+}
+
+// Cross-covariance chunk as six int8 planes [6][Mc][ldp] + the FP64 posterior mean (exact exp: the mean of this mode
+// is the FP64 mode's).  A warp owns QPW queries; lane l handles observations 4 l .. 4 l + 3 of every 128-block so that
+// each plane store is a packed 32-bit word (128 B per warp and plane).
+template <int D>
+__global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const double* __restrict__ X, int64_t N,
+                                                             const double* __restrict__ alpha,
+                                                             const double* __restrict__ Xq, int64_t M, double inv_scale,
+                                                             int8_t* __restrict__ planes, int64_t ldp, int64_t plane_pitch,
+                                                             double* __restrict__ mean) {
+    constexpr int QPW = 2;
+    const int lane = threadIdx.x & 31;
+    const int64_t m0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * QPW;
+    if (m0 >= M) return;
+    double q[QPW][D], acc[QPW];
+#pragma unroll
+    for (int i = 0; i < QPW; ++i) {
+        const int64_t m = (m0 + i < M) ? (m0 + i) : (M - 1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) q[i][d] = Xq[m * D + d];
+        acc[i] = 0.0;
+    }
+    for (int64_t n0 = 4 * lane; n0 < ldp; n0 += 128) {
+        uint32_t packed[QPW][I_NS];
+#pragma unroll
+        for (int i = 0; i < QPW; ++i)
+#pragma unroll
+            for (int s = 0; s < I_NS; ++s) packed[i][s] = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t n = n0 + e;
+            if (n < N) {
+                double x[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] = X[n * D + d];
+                const double a = alpha[n];
+#pragma unroll
+                for (int i = 0; i < QPW; ++i) {
+                    const double kv = rbf_eval<D>(k, q[i], x);
+                    acc[i] = fma(kv, a, acc[i]);
+                    int sl[I_NS];
+                    slice6(kv, inv_scale, sl);
+#pragma unroll
+                    for (int s = 0; s < I_NS; ++s) packed[i][s] |= ((uint32_t)sl[s] & 0xFFu) << (8 * e);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < QPW; ++i)
+            if (m0 + i < M) {
+#pragma unroll
+                for (int s = 0; s < I_NS; ++s)
+                    *reinterpret_cast<uint32_t*>(planes + (int64_t)s * plane_pitch + (m0 + i) * ldp + n0) = packed[i][s];
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < QPW; ++i) {
+        double s = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && m0 + i < M) mean[m0 + i] = s;
+    }
+}
+
+// planes [6][rows][ldp] int8, logical width `cols` bytes: box = 64 B x box_rows x 6 planes, SWIZZLE_64B, OOB -> 0
+static int make_map_i8(CUtensorMap* map, const int8_t* base, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_pitch,
+                       int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IPP_E_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)I_NS};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldp, (cuuint64_t)plane_pitch};
+    const cuuint32_t box[3] = {(cuuint32_t)I_BK, (cuuint32_t)box_rows, (cuuint32_t)I_NS};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (int8 planes) failed with CUresult %d", (int)r); return IPP_E_CUDA; }
+    return IPP_OK;
+}
+
+constexpr int64_t I8_CHUNK = 32768;
+static int64_t i8_chunk_rows(int64_t M) { return M < I8_CHUNK ? round_up(M, I_BM) : I8_CHUNK; }
+static double pow2_at_least(double x) {
+    double s = 1.0;
+    while (s < x) s *= 2.0;
+    while (s * 0.5 >= x && s > 1e-300) s *= 0.5;
+    return s;
+}
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale,
+                            int8_t* planes, int64_t ldp, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(A && planes && rows >= 1 && cols >= 1 && lda >= cols && ldp >= cols && ldp % 16 == 0, "bad arguments");
+    IPP_CHECK_ARG(scale > 0, "scale must be a positive power of two >= max |A|");
+    const int64_t total = rows * ldp;
+    i8_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, rows, cols, lda, 1.0 / scale, planes, ldp);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+extern "C" int64_t ipp_gp_predict_i8_workspace(int64_t N, int64_t M) {
+    if (N <= 0 || M <= 0) return 16;
+    const int64_t ldp = round_up(N, 128), mc = i8_chunk_rows(M), T = (N + I_BN - 1) / I_BN;
+    return (I_NS * mc * ldp + 7) / 8 + T * mc + 64;
+}
+
+extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                                 const int8_t* linv_planes, int64_t ldl, double linv_scale, double noise_add,
+                                 const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(kern && X && alpha && linv_planes && Xq && mean && var && work, "null pointer");
+    IPP_CHECK_ARG(N >= 1 && M >= 1 && N < (1LL << 22), "bad shape (the exact INT32 accumulation needs N < 2^22)");
+    IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
+    IPP_CHECK_ARG(ldl >= N && ldl % 16 == 0 && reinterpret_cast<uintptr_t>(linv_planes) % 16 == 0,
+                  "linv planes must be 16-byte aligned with ldl % 16 == 0");
+    IPP_CHECK_ARG(linv_scale > 0 && kern->variance > 0, "scales must be positive");
+    static bool configured = false;
+    if (!configured) {
+        IPP_CUDA(cudaFuncSetAttribute(predict_var_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM));
+        configured = true;
+    }
+    const int64_t ldp = round_up(N, 128), mc_max = i8_chunk_rows(M);
+    const int T = (int)((N + I_BN - 1) / I_BN);
+    int8_t* planes = reinterpret_cast<int8_t*>(work);
+    double* partial = work + (I_NS * mc_max * ldp + 7) / 8;
+    const double sa = pow2_at_least(kern->variance * (1.0 + 1e-12));      // k(q, x) <= variance for every pair
+    // v = D * sa * sb * 2^-12 with D = sum_w D_w 2^(-7 w): the epilogue sums squares of D, so one constant at the end
+    const double unit = sa * linv_scale / 4096.0;
+    CUtensorMap map_b;
+    IPP_TRY(make_map_i8(&map_b, linv_planes, N, N, ldl, N * ldl, I_BN));
+    const RbfDev kd = to_dev(*kern);
+    const int grid = sm_count();
+    for (int64_t s = 0; s < M; s += mc_max) {
+        const int64_t mc = (M - s) < mc_max ? (M - s) : mc_max;
+        const unsigned qblocks = (unsigned)((mc + 15) / 16);
+        if (kern->dim == 2)
+            rbf_queries_i8_kernel<2><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 2, mc, 1.0 / sa, planes, ldp,
+                                                                  mc * ldp, mean + s);
+        else
+            rbf_queries_i8_kernel<3><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 3, mc, 1.0 / sa, planes, ldp,
+                                                                  mc * ldp, mean + s);
+        IPP_LAUNCH_CHECK();
+        CUtensorMap map_a;
+        IPP_TRY(make_map_i8(&map_a, planes, mc, N, ldp, mc * ldp, I_BM));
+        I8Args p;
+        p.partial = partial; p.ldp = mc_max;
+        p.Mc = (int)mc; p.N = (int)N; p.T = T; p.Mtiles = (int)((mc + I_BM - 1) / I_BM);
+        {
+            const int64_t panel = (int64_t)I_BM * ldp * I_NS;            // bytes of one m-tile's six planes
+            int64_t gm = (48LL << 20) / panel;
+            if (gm < 1) gm = 1;
+            if (gm > p.Mtiles) gm = p.Mtiles;
+            p.GM = (int)gm;
+        }
+        const int items = p.T * p.Mtiles;
+        profile_mark(0, stream);
+        predict_var_i8_kernel<<<items < grid ? items : grid, I_THREADS, I_SMEM, stream>>>(map_a, map_b, p);
+        profile_mark(1, stream);
+        IPP_LAUNCH_CHECK();
+        predict_finalize_i8_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, T, (int)mc, unit * unit,
+                                                                                    kern->variance, noise_add, var + s);
+        IPP_LAUNCH_CHECK();
+    }
+    return IPP_OK;
+}

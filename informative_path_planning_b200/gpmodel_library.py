@@ -110,6 +110,7 @@ class GPModel(object):
         self._ld = 0
         self._ig = None            # cached (binv, logdet_before) for info_gain
         self._tf32 = None          # cached (linv_hi, linv_lo, ld) float32 split of L^-1 for the 3xTF32 predict
+        self._i8 = None            # cached (planes, ld, scale) int8 slices of L^-1 for the sliced-INT8 predict
         self.predict_precision = 'fp64'   # 'tf32x3': batched predicts run on the tcgen05 path (see predict_device)
         self.tf32_acc_kblocks = 1         # tensor-core accumulation chunk of the 3xTF32 path (1 = most accurate)
         # Rollout forks may defer the "is the Schur block positive definite" read-back (a device->host
@@ -156,6 +157,7 @@ class GPModel(object):
         self._logdet = scal
         self._ig = None
         self._tf32 = None
+        self._i8 = None
 
     def _predict_core(self, xq_d, include_noise, mode, mat):
         M = xq_d.shape[0]
@@ -266,28 +268,55 @@ class GPModel(object):
     def _var_operand(self):
         return L.VAR_CHOL, self._linv_d
 
+    def _linv_for_tensor_modes(self):
+        """(L^-1 [N][ld] float64 CUDA tensor, ld) of the current belief; a device refactorisation when the model only
+        carries W^-1 (OnlineGPModel after init / appends)."""
+        if self._linv_d is not None:
+            return self._linv_d, self._ld
+        N, dev = self.n_obs, L.device()
+        ld = L.round_up(N, 16)
+        winv = torch.empty((N, ld), dtype=torch.float64, device=dev)
+        linv = torch.empty((N, ld), dtype=torch.float64, device=dev)
+        alpha = torch.empty(N, dtype=torch.float64, device=dev)
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        work = L.workspace(L.lib.ipp_gp_factor_workspace(N))
+        L.check(L.lib.ipp_gp_factor(ctypes.byref(self.kern._c), L.ptr(self._X_d), L.ptr(self._z_d), N,
+                                    self._diag_add(), L.ptr(winv), L.ptr(linv), ld, L.ptr(alpha), L.ptr(scal),
+                                    L.ptr(info), L.ptr(work), L.stream_ptr()))
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError('not positive definite (tensor-mode operand refresh)')
+        return linv, ld
+
+    def _i8_operand(self):
+        """(planes [6][N][ld] int8, ld, scale): six signed 7-bit slices of L^-1 against one power-of-two scale."""
+        if self._i8 is None:
+            N, dev = self.n_obs, L.device()
+            linv, lda = self._linv_for_tensor_modes()
+            scale = 2.0 ** int(np.ceil(np.log2(float(linv[:, :N].abs().max().item()) * (1.0 + 1e-12))))
+            ldl = L.round_up(N, 128)
+            planes = torch.empty((6, N, ldl), dtype=torch.int8, device=dev)
+            L.check(L.lib.ipp_i8_slice(L.ptr(linv), N, N, lda, scale, L.ptr(planes), ldl, L.stream_ptr()))
+            self._i8 = (planes, ldl, scale)
+        return self._i8
+
+    def _predict_i8(self, xq_d, include_noise):
+        M, N = xq_d.shape[0], self.n_obs
+        planes, ldl, scale = self._i8_operand()
+        mean = torch.empty(M, dtype=torch.float64, device=xq_d.device)
+        var = torch.empty(M, dtype=torch.float64, device=xq_d.device)
+        work = L.workspace(L.lib.ipp_gp_predict_i8_workspace(N, M), slot='i8')
+        L.check(L.lib.ipp_gp_predict_i8(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
+                                        L.ptr(planes), ldl, scale, float(self.noise) if include_noise else 0.0,
+                                        L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
+        return mean, var
+
     def _tf32_operand(self):
         """(hi, lo, ld): float32 split of L^-1 of the current belief, built on first use after every refresh /
-        append (L^-1 itself comes from a device refactorisation when the model only carries W^-1)."""
+        append."""
         if self._tf32 is None:
             N, dev = self.n_obs, L.device()
-            linv = self._linv_d
-            if linv is None:
-                ld = L.round_up(N, 16)
-                winv = torch.empty((N, ld), dtype=torch.float64, device=dev)
-                linv = torch.empty((N, ld), dtype=torch.float64, device=dev)
-                alpha = torch.empty(N, dtype=torch.float64, device=dev)
-                scal = torch.zeros(2, dtype=torch.float64, device=dev)
-                info = torch.zeros(1, dtype=torch.int32, device=dev)
-                work = L.workspace(L.lib.ipp_gp_factor_workspace(N))
-                L.check(L.lib.ipp_gp_factor(ctypes.byref(self.kern._c), L.ptr(self._X_d), L.ptr(self._z_d), N,
-                                            self._diag_add(), L.ptr(winv), L.ptr(linv), ld, L.ptr(alpha), L.ptr(scal),
-                                            L.ptr(info), L.ptr(work), L.stream_ptr()))
-                if int(info.item()) != 0:
-                    raise np.linalg.LinAlgError('not positive definite (3xTF32 operand refresh)')
-                lda = ld
-            else:
-                lda = self._ld
+            linv, lda = self._linv_for_tensor_modes()
             ldl = L.round_up(N, 32)
             hi = torch.empty((N, ldl), dtype=torch.float32, device=dev)
             lo = torch.empty((N, ldl), dtype=torch.float32, device=dev)
@@ -309,17 +338,20 @@ class GPModel(object):
 
     def predict_device(self, xq_d, include_noise=True, precision=None):
         """(M, D) float64 CUDA tensor -> (mean[M], var[M]) CUDA tensors; no host transfer.
-        precision: 'fp64' (FP64 DMMA, reference parity) or 'tf32x3' (tcgen05, split operands); default = the
-        model's .predict_precision.  Small batches always use the FP64 path (they are bandwidth-bound)."""
+        precision: 'fp64' (FP64 DMMA), 'i8x6' (tcgen05 kind::i8 on six 7-bit slices per operand, exact integer
+        accumulation: FP64-grade, ~2e-8 relative variance error) or 'tf32x3' (tcgen05 kind::tf32, split operands,
+        ~2e-4); default = the model's .predict_precision.  Small batches always use the FP64 path (bandwidth-bound)."""
         if self.n_obs == 0:
             M = xq_d.shape[0]
             return (torch.zeros(M, dtype=torch.float64, device=xq_d.device),
                     torch.full((M,), float(self.variance), dtype=torch.float64, device=xq_d.device))
         precision = self.predict_precision if precision is None else precision
-        if precision not in ('fp64', 'tf32x3'):
-            raise ValueError("precision must be 'fp64' or 'tf32x3'")
+        if precision not in ('fp64', 'tf32x3', 'i8x6'):
+            raise ValueError("precision must be 'fp64', 'i8x6' or 'tf32x3'")
         if precision == 'tf32x3' and xq_d.shape[0] > 64:
             return self._predict_tf32(xq_d.contiguous(), include_noise)
+        if precision == 'i8x6' and xq_d.shape[0] > 64:
+            return self._predict_i8(xq_d.contiguous(), include_noise)
         mode, mat = self._var_operand()
         return self._predict_core(xq_d.contiguous(), include_noise, mode, mat)
 
@@ -465,6 +497,7 @@ class OnlineGPModel(GPModel):
         self._X_d, self._z_d, self._winv_d, self._alpha_d, self._ld = X_all, z_all, winv, alpha, ld
         self._ig = None
         self._tf32 = None
+        self._i8 = None
         self._linv_d = None
 
     def add_data(self, xvals, zvals):                         # reference :281-301

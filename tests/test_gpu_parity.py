@@ -720,3 +720,35 @@ def test_dubins_paths_on_device_match_host_generator(pkg):
     s_h, c_h = s_d.cpu().numpy(), c_d.cpu().numpy()
     ref = np.array([pkg.aq_library.mean_UCB(time=3, xvals=s_h[p, :c_h[p]], robot_model=m) for p in kept[:40]])
     np.testing.assert_allclose(r.cpu().numpy()[:40], ref, rtol=1e-8)      # tile path vs small-batch path: summation order
+
+
+@pytest.mark.parametrize('N,M,noise', [(333, 130, 0.5), (1000, 5000, 0.5), (2048, 33000, 0.5), (700, 3000, 1e-4)])
+def test_predict_i8x6_mode_is_fp64_grade(pkg, N, M, noise):
+    """Sliced-INT8 mode (tcgen05 kind::i8, six 7-bit slices per operand, exact INT32 accumulation) against the FP64
+    mode and the oracle: the FP64 mode's own parity tolerance (1e-6 relative at noise 0.5; 1e-6 of the prior variance
+    at noise 1e-4) holds with a wide margin, ragged N / M included."""
+    _, gpo, _ = _oracle()
+    rng = np.random.default_rng(N + 1)
+    X, z = world(rng, N, noise)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=noise)
+    m.add_data(X, z)
+    q = rng.uniform(0, 10, (M, 2))
+    mu64, var64 = m.predict_value(q)
+    m.predict_precision = 'i8x6'
+    mu8, var8 = m.predict_value(q)
+    np.testing.assert_allclose(mu8, mu64, rtol=1e-12, atol=1e-11)
+    if noise == 0.5:
+        np.testing.assert_allclose(var8, var64, rtol=2e-7)
+        o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=noise)
+        o.add_data(X, z)
+        mu_o, var_o = o.predict_value(q[:400])
+        np.testing.assert_allclose(var8[:400], var_o, rtol=RTOL)
+        np.testing.assert_allclose(mu8[:400], mu_o, rtol=RTOL, atol=1e-8)
+    else:
+        assert np.abs(var8 - var64).max() <= 1e-6 * 100.0
+    # appended data invalidates the sliced operand
+    m.add_data(np.array([[5.0, 5.0], [2.5, 7.5]]), np.array([[1.0], [2.0]]))
+    v_a = m.predict_value(q[:200])[1]
+    m.predict_precision = 'fp64'
+    v_b = m.predict_value(q[:200])[1]
+    np.testing.assert_allclose(v_a, v_b, rtol=2e-7 if noise == 0.5 else 1e-2, atol=0 if noise == 0.5 else 1e-4)

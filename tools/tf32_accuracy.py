@@ -1,4 +1,5 @@
-"""3xTF32 vs FP64 predict: variance error statistics and throughput by N (BASELINE config 3 sweep)."""
+"""Tensor-mode (3xTF32 or sliced INT8, env MODE=tf32x3|i8x6) vs FP64 predict: variance error statistics and throughput
+by N (BASELINE config 3 sweep)."""
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -7,6 +8,7 @@ from informative_path_planning_b200 import _lib as L
 R = (0., 10., 0., 10.)
 out = []
 KC = int(os.environ.get('KC', '1'))
+MODE = os.environ.get('MODE', 'tf32x3')
 for N in [int(a) for a in (sys.argv[1:] or ['333', '1024', '2048', '4096', '8192'])]:
     rng = np.random.default_rng(N)
     X = rng.uniform(0, 10, (N, 2))
@@ -17,7 +19,7 @@ for N in [int(a) for a in (sys.argv[1:] or ['333', '1024', '2048', '4096', '8192
     M = int(os.environ.get('M', str(1 << 20)))
     q = L.to_device(rng.uniform(0, 10, (M, 2)))
     res = {'N': N, 'M': M, 'acc_kblocks': KC}
-    for prec in ('fp64', 'tf32x3'):
+    for prec in ('fp64', MODE):
         mu, var = m.predict_device(q, precision=prec)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,13 +31,16 @@ for N in [int(a) for a in (sys.argv[1:] or ['333', '1024', '2048', '4096', '8192
         res[prec + '_ms'] = ms
         res[prec + '_queries_per_s'] = M / ms * 1e3
         res[prec] = (mu.cpu().numpy(), var.cpu().numpy())
-    (mu64, v64), (mu32, v32) = res.pop('fp64'), res.pop('tf32x3')
+    (mu64, v64), (mu32, v32) = res.pop('fp64'), res.pop(MODE)
     err = np.abs(v32 - v64)
     res.update(mean_max_abs_diff=float(np.abs(mu32 - mu64).max()), var_abs_err_max=float(err.max()), var_abs_err_median=float(np.median(err)),
                var_rel_err_max=float((err / v64).max()), var_rel_err_median=float(np.median(err / v64)),
-               var_err_over_prior_max=float(err.max() / 100.0), bias=float(np.mean(v32 - v64)), speedup=res['fp64_ms'] / res['tf32x3_ms'])
+               var_err_over_prior_max=float(err.max() / 100.0), bias=float(np.mean(v32 - v64)), speedup=res['fp64_ms'] / res[MODE + '_ms'])
     T = (N + 127) // 128
-    res['tf32_executed_tflops'] = 3 * 2.0 * 128 * 128 * T * (T + 1) / 2 * M / (res['tf32x3_ms'] / 1e3) / 1e12
+    T64 = (N + 63) // 64
+    res['mode'] = MODE
+    res['tf32_executed_tflops'] = 3 * 2.0 * 128 * 128 * T * (T + 1) / 2 * M / (res[MODE + '_ms'] / 1e3) / 1e12 if MODE == 'tf32x3' else None
+    res['i8_executed_tops'] = 21 * 2.0 * 64 * 64 * T64 * (T64 + 1) / 2 * M / (res[MODE + '_ms'] / 1e3) / 1e12 if MODE == 'i8x6' else None
     print(json.dumps(res)); out.append(res)
 os.makedirs('gpurun_out', exist_ok=True)
-json.dump(out, open('gpurun_out/tf32_sweep.json', 'w'), indent=1)
+json.dump(out, open('gpurun_out/%s_sweep.json' % ('tf32' if MODE == 'tf32x3' else 'i8'), 'w'), indent=1)
