@@ -93,53 +93,62 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-    if (warp == 0) {
-        if (lane == 0) {                                                 // ===== TMA producer
+    if (warp == 0) {                                                     // ===== TMA producer (converged warp, one elected lane issues)
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-            uint32_t stage = 0, phase = 0;
-            int m0, I, kblocks;
-            for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        }
+        uint32_t stage = 0, phase = 0;
+        int m0, I, kblocks;
+        for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (elect_one()) {
                     const uint32_t full = full0 + 8 * stage, dst = tiles + stage * I_STAGE_BYTES;
                     mbar_expect_tx(full, I_STAGE_BYTES);
                     tma_load_3d(dst, &map_a, kb * I_BK, m0, 0, full);               // [6][128][64 B]
                     tma_load_3d(dst + I_A_BYTES, &map_b, kb * I_BK, I * I_BN, 0, full);   // [6][64][64 B]
-                    if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                                 // ===== MMA issuer (single thread)
-            uint32_t stage = 0, phase = 0;
-            int m0, I, kblocks;
-            for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
-                mbar_wait(tempty, (it & 1) ^ 1);                         // epilogue has drained the accumulators
+    } else if (warp == 1) {                                              // ===== MMA issuer (converged warp, one elected lane issues)
+        uint32_t stage = 0, phase = 0;
+        int m0, I, kblocks;
+        for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+            mbar_wait(tempty, (it & 1) ^ 1);                             // epilogue has drained the accumulators
+            tc_fence_after();
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-                uint32_t touched = 0;                                    // bit w: level w already holds a product
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t base = tiles + stage * I_STAGE_BYTES;
+                    const uint32_t fresh = (kb == 0) ? 0u : 1u;          // first k-block of the tile overwrites the levels
+                    uint64_t ad[I_NS], bd[I_NS];
+#pragma unroll
+                    for (int i = 0; i < I_NS; ++i) {
+                        ad[i] = make_desc64(base + i * I_A_PLANE);
+                        bd[i] = make_desc64(base + I_A_BYTES + i * I_B_PLANE);
+                    }
 #pragma unroll
                     for (int ks = 0; ks < I_BK / 32; ++ks) {             // UMMA_K = 32 int8 = 32 B: +2 in 16-B units
 #pragma unroll
                         for (int i = 0; i < I_NS; ++i) {
-                            const uint64_t ad = make_desc64(base + i * I_A_PLANE) + (uint64_t)(2 * ks);
 #pragma unroll
                             for (int j = 0; j < I_NS - i; ++j) {
-                                const uint64_t bd = make_desc64(base + I_A_BYTES + j * I_B_PLANE) + (uint64_t)(2 * ks);
-                                const int w = i + j;
-                                tc_mma_i8(tmem_base + w * I_BN, ad, bd, (touched >> w) & 1u);
-                                touched |= 1u << w;
+                                // level w = i + j: its first product of the tile is (i = 0, j = w) of ks = 0
+                                const uint32_t accumulate = (ks == 0 && i == 0) ? fresh : 1u;
+                                tc_mma_i8(tmem_base + (i + j) * I_BN, ad[i] + (uint64_t)(2 * ks), bd[j] + (uint64_t)(2 * ks),
+                                          accumulate);
                             }
                         }
                     }
                     tc_commit(empty0 + 8 * stage);
-                    if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == kblocks - 1) tc_commit(tfull);
                 }
-                tc_commit(tfull);
+                __syncwarp();
+                if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {                                                             // ===== epilogue warps 2..5: thread = query row

@@ -98,40 +98,43 @@ predict_var_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-    if (warp == 0) {
-        if (lane == 0) {                                                 // ===== TMA producer
+    if (warp == 0) {                                                     // ===== TMA producer (one elected lane issues)
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
-            uint32_t stage = 0, phase = 0;
-            int m0, I, kblocks;
-            for (int it = 0; tf32_item(p, it, m0, I, kblocks); ++it) {
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        }
+        uint32_t stage = 0, phase = 0;
+        int m0, I, kblocks;
+        for (int it = 0; tf32_item(p, it, m0, I, kblocks); ++it) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (elect_one()) {
                     const uint32_t full = full0 + 8 * stage, dst = tiles + stage * T_STAGE_BYTES;
                     mbar_expect_tx(full, T_STAGE_BYTES);
                     tma_load_2d(dst, &map_a_hi, kb * TBK, m0, full);
                     tma_load_2d(dst + T_TILE_BYTES, &map_a_lo, kb * TBK, m0, full);
                     tma_load_2d(dst + 2 * T_TILE_BYTES, &map_b_hi, kb * TBK, I * TBN, full);
                     tma_load_2d(dst + 3 * T_TILE_BYTES, &map_b_lo, kb * TBK, I * TBN, full);
-                    if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                                 // ===== MMA issuer (single thread)
-            uint32_t stage = 0, phase = 0, buf = 0, buf_phase = 0;
-            int m0, I, kblocks;
-            for (int it = 0; tf32_item(p, it, m0, I, kblocks); ++it) {
-                for (int kb0 = 0; kb0 < kblocks; kb0 += p.KC) {          // one accumulation chunk per TMEM buffer
-                    const int kb1 = (kb0 + p.KC < kblocks) ? kb0 + p.KC : kblocks;
-                    mbar_wait(tempty0 + 8 * buf, buf_phase ^ 1);         // epilogue has drained this buffer
+    } else if (warp == 1) {                                              // ===== MMA issuer (one elected lane issues)
+        uint32_t stage = 0, phase = 0, buf = 0, buf_phase = 0;
+        int m0, I, kblocks;
+        for (int it = 0; tf32_item(p, it, m0, I, kblocks); ++it) {
+            for (int kb0 = 0; kb0 < kblocks; kb0 += p.KC) {              // one accumulation chunk per TMEM buffer
+                const int kb1 = (kb0 + p.KC < kblocks) ? kb0 + p.KC : kblocks;
+                mbar_wait(tempty0 + 8 * buf, buf_phase ^ 1);             // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * T_ACC_COLS;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + buf * T_ACC_COLS;
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(full0 + 8 * stage, phase);
-                        tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t base = tiles + stage * T_STAGE_BYTES;
                         const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + T_TILE_BYTES);
                         const uint64_t b_hi = make_desc(base + 2 * T_TILE_BYTES), b_lo = make_desc(base + 3 * T_TILE_BYTES);
@@ -143,11 +146,12 @@ predict_var_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                             tc_mma_tf32(d, a_hi + adv, b_hi + adv, 1);
                         }
                         tc_commit(empty0 + 8 * stage);                   // frees the stage when these MMAs retire
-                        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+                        if (kb == kb1 - 1) tc_commit(tfull0 + 8 * buf);  // chunk complete -> epilogue
                     }
-                    tc_commit(tfull0 + 8 * buf);                         // chunk complete -> epilogue
-                    if (++buf == T_NBUF) { buf = 0; buf_phase ^= 1; }
+                    __syncwarp();
+                    if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (++buf == T_NBUF) { buf = 0; buf_phase ^= 1; }
             }
         }
     } else {                                                             // ===== epilogue warps 2..5

@@ -9,6 +9,19 @@ namespace ipp {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a converged warp (elect.sync).  tcgen05.mma / TMA are uniform-datapath instructions: issued under
+// `if (elect_one())` inside warp-uniform control flow they compile to straight UTC*MMA / UTMALDG, whereas under a
+// divergent `lane == 0` branch the compiler wraps every one of them in an ELECT / BRA.U.ANY loop (~5 extra issue
+// slots per MMA, which made the single MMA thread issue-bound at N = 64).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
