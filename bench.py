@@ -500,7 +500,7 @@ def main():
             del a8, b8
             i8_peak = (2.0 * 8192 ** 3 / (best8 / 1e3) / 1e12) if best8 else None
             T64 = (N_OBS + 63) // 64
-            ops8 = 21 * 2.0 * 128 * 64 * (T64 * (T64 + 1) / 2) * (min(M, 32768) / 128.0)
+            ops8 = 21 * 2.0 * 128 * 64 * 64 * (T64 * (T64 + 1) / 2) * (min(M, 32768) / 128.0)   # 21 products x tiles x k-blocks of 64
             kern_tops = ops8 / (k_ms.value / max(1, k_n.value) / 1e3) / 1e12
             err = (var8 - var64).abs()
             extras['i8x6_N4096'] = {

@@ -9,6 +9,8 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__ops_path_tensor_src_fp64.sum', 'sm__ops_path_tensor_src_fp64.sum.per_second',
         'sm__ops_path_tensor_src_fp64.sum.peak_sustained_elapsed.per_second',
         'sm__ops_path_tensor_src_tf32_dst_fp32.sum', 'sm__ops_path_tensor_src_tf32_dst_fp32.sum.per_second',
+        'sm__ops_path_tensor_src_int8.sum', 'sm__ops_path_tensor_src_int8.sum.per_second',
+        'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
