@@ -76,4 +76,39 @@ __device__ __forceinline__ double rbf_eval(const RbfDev& k, const double* a, con
 }
 
 
+// exp(x) for x <= 0 to ~2^-36 relative (degree-9 Taylor after Cody-Waite reduction): used by the tensor-core modes
+// (3xTF32: operands rounded to 22 bits; sliced INT8: 42-bit fixed point, tolerance 1e-6), where libdevice's < 1 ulp exp
+// (about twice the FP64-pipe instructions) buys nothing.  The FP64 DMMA mode keeps the exact exp.
+__device__ __forceinline__ double exp_neg_fast(double x) {
+    if (x < -700.0) return 0.0;
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);      // n = rint(x log2 e) in the low word
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double f = fma(nf, -6.93147180369123816490e-01, x);
+    f = fma(nf, -1.90821492927058770002e-10, f);
+    double p = 2.7557319223985893e-06;                                       // 1/9!
+    p = fma(p, f, 2.4801587301587302e-05);
+    p = fma(p, f, 1.9841269841269841e-04);
+    p = fma(p, f, 1.3888888888888889e-03);
+    p = fma(p, f, 8.3333333333333332e-03);
+    p = fma(p, f, 4.1666666666666664e-02);
+    p = fma(p, f, 1.6666666666666666e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));   // p in [0.70, 1.42]: exact scaling by 2^n
+}
+
+template <int D>
+__device__ __forceinline__ double rbf_eval_fast(const RbfDev& k, const double* a, const double* b) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double u = (a[d] - b[d]) * k.il[d];
+        r2 = fma(u, u, r2);
+    }
+    return k.variance * exp_neg_fast(-0.5 * r2);
+}
+
+
 }  // namespace ipp

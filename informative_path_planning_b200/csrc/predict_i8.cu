@@ -49,7 +49,7 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
 }
 
 struct I8Args {
-    double* partial; int64_t ldp;      // [T][ldp] per-(n-tile, query) sums of squares in units of (sa sb 2^-12)^2
+    double* partial; int64_t ldp;      // [T][ldp] per-(n-tile, query) sums of squares in units of (sa sb 2^-13)^2
     int Mc, N, T, Mtiles, GM;
 };
 
@@ -223,9 +223,10 @@ __global__ void i8_slice_kernel(const double* __restrict__ A, int64_t rows, int6
     for (int k = 0; k < I_NS; ++k) planes[(int64_t)k * rows * ldp + idx] = (int8_t)s[k];
 }
 
-// Cross-covariance chunk as six int8 planes [6][Mc][ldp] + the FP64 posterior mean (exact exp: the mean of this mode
-// is the FP64 mode's).  A warp owns QPW queries; lane l handles observations 4 l .. 4 l + 3 of every 128-block so that
-// each plane store is a packed 32-bit word (128 B per warp and plane).
+// Cross-covariance chunk as six int8 planes [6][Mc][ldp] + the FP64 posterior mean.  k >= 0, so its 42-bit fixed-point
+// value is cut into plain base-128 digits in [0, 127] with integer shifts (the signed round-to-nearest slicing of
+// slice6 costs as many FP64-pipe instructions as the exp itself).  A warp owns QPW queries; lane l handles observations
+// 4 l .. 4 l + 3 of every 128-block so that each plane store is a packed 32-bit word (128 B per warp and plane).
 template <int D>
 __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const double* __restrict__ X, int64_t N,
                                                              const double* __restrict__ alpha,
@@ -260,12 +261,14 @@ __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const dou
                 const double a = alpha[n];
 #pragma unroll
                 for (int i = 0; i < QPW; ++i) {
-                    const double kv = rbf_eval<D>(k, q[i], x);
+                    const double kv = rbf_eval<D>(k, q[i], x);              // exact exp: the mean of this mode is the FP64 mode's
                     acc[i] = fma(kv, a, acc[i]);
-                    int sl[I_NS];
-                    slice6(kv, inv_scale, sl);
+                    // kv / scale in [0, 1)  ->  X = rint(. 2^42) <= 2^42;  digit s = bits [42 - 7 (s + 1), 42 - 7 s)
+                    unsigned long long X = (unsigned long long)__double2ll_rn(kv * inv_scale * 4398046511104.0);
+                    if (X > 4398046511103ull) X = 4398046511103ull;
 #pragma unroll
-                    for (int s = 0; s < I_NS; ++s) packed[i][s] |= ((uint32_t)sl[s] & 0xFFu) << (8 * e);
+                    for (int s = 0; s < I_NS; ++s)
+                        packed[i][s] |= (uint32_t)((X >> (7 * (I_NS - 1 - s))) & 127ull) << (8 * e);
                 }
             }
         }
@@ -337,7 +340,7 @@ extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N
                                  const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(kern && X && alpha && linv_planes && Xq && mean && var && work, "null pointer");
-    IPP_CHECK_ARG(N >= 1 && M >= 1 && N < (1LL << 22), "bad shape (the exact INT32 accumulation needs N < 2^22)");
+    IPP_CHECK_ARG(N >= 1 && M >= 1 && N <= 40000, "bad shape (exact INT32 accumulation: 6 pairs x 127 x 64 x N < 2^31)");
     IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
     IPP_CHECK_ARG(ldl >= N && ldl % 16 == 0 && reinterpret_cast<uintptr_t>(linv_planes) % 16 == 0,
                   "linv planes must be 16-byte aligned with ldl % 16 == 0");
@@ -352,8 +355,9 @@ extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N
     int8_t* planes = reinterpret_cast<int8_t*>(work);
     double* partial = work + (I_NS * mc_max * ldp + 7) / 8;
     const double sa = pow2_at_least(kern->variance * (1.0 + 1e-12));      // k(q, x) <= variance for every pair
-    // v = D * sa * sb * 2^-12 with D = sum_w D_w 2^(-7 w): the epilogue sums squares of D, so one constant at the end
-    const double unit = sa * linv_scale / 4096.0;
+    // v = D * sa * sb * 2^-13 with D = sum_w D_w 2^(-7 w): the epilogue sums squares of D, so one constant at the end
+    // (cross-covariance digits carry 2^(-7 - 7 s), Linv slices 2^(-6 - 7 s): 2^-13 in front of level 0)
+    const double unit = sa * linv_scale / 8192.0;
     CUtensorMap map_b;
     IPP_TRY(make_map_i8(&map_b, linv_planes, N, N, ldl, N * ldl, I_BN));
     const RbfDev kd = to_dev(*kern);

@@ -441,6 +441,13 @@ def test_full_size_properties(pkg):
     mu_o, var_o = o.predict_value(xq[:512].cpu().numpy())
     np.testing.assert_allclose(mean[:512].cpu().numpy().reshape(-1, 1), mu_o, rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(var[:512].cpu().numpy().reshape(-1, 1), var_o, rtol=RTOL)
+    # (6) the tensor modes at full size: sliced INT8 inside the FP64 tolerance on every query, 3xTF32 inside its bound
+    mean8, var8 = m.predict_device(xq, precision='i8x6')
+    torch.testing.assert_close(mean8, mean, rtol=1e-9, atol=1e-9)
+    torch.testing.assert_close(var8, var, rtol=2e-7, atol=0)
+    np.testing.assert_allclose(var8[:512].cpu().numpy().reshape(-1, 1), var_o, rtol=RTOL)
+    mean32, var32 = m.predict_device(xq, precision='tf32x3')
+    assert float(((var32 - var).abs() / var).max()) < 2e-3 and float((mean32 - mean).abs().max()) < 1e-6
 
 
 # ------------------------------------------------------------------ more edge cases
