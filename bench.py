@@ -352,6 +352,20 @@ def main():
             r1.record()
             torch.cuda.synchronize()
             extras['reward_evals_per_s_' + name] = P * 2 / (r0.elapsed_time(r1) / 1e3)
+        model.predict_precision = 'i8x6'           # the same reward call with the posterior on the INT8 tensor path
+        try:
+            model.reward_paths_device(L.REWARD_UCB, xp, offs, params=sqb)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(2):
+                model.reward_paths_device(L.REWARD_UCB, xp, offs, params=sqb)
+            r1.record()
+            torch.cuda.synchronize()
+            extras['reward_evals_per_s_ucb_i8x6'] = P * 2 / (r0.elapsed_time(r1) / 1e3)
+        except Exception as e:
+            extras['reward_evals_per_s_ucb_i8x6'] = repr(e)
+        model.predict_precision = 'fp64'
         extras['reward_workload'] = '%d paths x %d points, N=4096 (BASELINE config 5 shape on 1 GPU)' % (P, k)
         # tree search (BASELINE config 2 shape): dpw, horizon 5, 250 rollouts, Dubins fan, N=900 observations;
         # GPU-backed planner vs the CPU oracle planner on the same seeds (identical visit counts expected)

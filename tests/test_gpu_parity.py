@@ -492,6 +492,14 @@ def test_space_time_kernel_d3(pkg):
                                aqo.mean_UCB(12, path, o), rtol=RTOL)
     with pytest.raises(AssertionError):
         d.predict_value(q[:, :2])
+    # the tensor modes carry D = 3 too (their cross-covariance generators are templated on the dimension)
+    mu_o, var_o = o.predict_value(q)
+    for prec, tol in (('i8x6', RTOL), ('tf32x3', 2e-3)):
+        d.predict_precision = prec
+        mu_t, var_t = d.predict_value(q)
+        np.testing.assert_allclose(mu_t, mu_o, rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(var_t, var_o, rtol=tol)
+    d.predict_precision = 'fp64'
 
 
 def test_linalg_error_on_indefinite_append(pkg):
@@ -655,7 +663,7 @@ def test_mcts_fused_rollouts_same_choices_as_per_level_path(pkg, f_rew, tree_typ
     assert m.n_obs == 120
 
 
-@pytest.mark.parametrize('N,M', [(333, 130), (1000, 5000), (2048, 33000)])
+@pytest.mark.parametrize('N,M', [(9, 70), (333, 130), (1000, 5000), (2048, 33000)])
 def test_predict_tf32x3_mode_against_fp64_mode(pkg, N, M):
     """3xTF32 mode (tcgen05 kind::tf32, Cholesky form, split operands) against the FP64 mode on the same belief.
     The mean is computed in FP64 in both.  The variance carries the FP32 representation error of the operands
@@ -729,7 +737,7 @@ def test_dubins_paths_on_device_match_host_generator(pkg):
     np.testing.assert_allclose(r.cpu().numpy()[:40], ref, rtol=1e-8)      # tile path vs small-batch path: summation order
 
 
-@pytest.mark.parametrize('N,M,noise', [(333, 130, 0.5), (1000, 5000, 0.5), (2048, 33000, 0.5), (700, 3000, 1e-4)])
+@pytest.mark.parametrize('N,M,noise', [(9, 70, 0.5), (64, 65, 0.5), (333, 130, 0.5), (1000, 5000, 0.5), (2048, 33000, 0.5), (700, 3000, 1e-4)])
 def test_predict_i8x6_mode_is_fp64_grade(pkg, N, M, noise):
     """Sliced-INT8 mode (tcgen05 kind::i8, six 7-bit slices per operand, exact INT32 accumulation) against the FP64
     mode and the oracle: the FP64 mode's own parity tolerance (1e-6 relative at noise 0.5; 1e-6 of the prior variance
