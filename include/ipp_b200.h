@@ -124,14 +124,16 @@ int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const d
  *      Operands in fixed point against one power-of-two scale each, cut into six signed 7-bit slices; 21 slice-pair
  *      products (i + j <= 5) accumulate exactly, the six weight levels are combined in FP64.  Measured variance error
  *      ~2e-8 relative (inside the FP64 mode's 1e-6 parity tolerance); the mean is computed exactly as in FP64 mode.
- *        ipp_i8_slice: A[rows][lda] (double) -> planes [6][rows][ldp] (int8), scale = power of two >= max |A|;
- *        linv_planes: the slices of Linv [N][ldl bytes], ldl % 16 == 0; linv_scale: the scale they were cut with;
+ *      n_slices = 6: 42-bit operands, 21 products, 128 x 64 tiles ("i8x6", the FP64-grade setting above);
+ *      n_slices = 5: 35-bit operands, 15 products, 128 x 96 tiles ("i8x5": ~2e-6 relative variance error, ~1.7x faster).
+ *        ipp_i8_slice: A[rows][lda] (double) -> planes [n_slices][rows][ldp] (int8), scale = power of two >= max |A|;
+ *        linv_planes: the slices of Linv [N][ldl bytes], ldl % 16 == 0; linv_scale / n_slices: what they were cut with;
  *      work: ipp_gp_predict_i8_workspace(N, M) doubles. */
-int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int8_t* planes, int64_t ldp,
-                 void* stream);
+int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int n_slices, int8_t* planes,
+                 int64_t ldp, void* stream);
 int64_t ipp_gp_predict_i8_workspace(int64_t N, int64_t M);
 int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                      const int8_t* linv_planes, int64_t ldl, double linv_scale, double noise_add,
+                      const int8_t* linv_planes, int64_t ldl, double linv_scale, int n_slices, double noise_add,
                       const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
 
 /* CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 / ipp_gp_predict_i8 (the fused DMMA variance kernel), recorded on

@@ -20,26 +20,35 @@
 
 namespace ipp {
 
-constexpr int I_NS = 6;                                // slices per operand
-constexpr int I_LEVELS = 6;                            // weight levels i + j = 0..5
-constexpr int I_BM = 128, I_BN = 64, I_BK = 64;        // tile; I_BK int8 = 64 B = one SWIZZLE_64B row
+constexpr int I_BM = 128, I_BK = 64;                   // tile rows; I_BK int8 = 64 B = one SWIZZLE_64B row
 constexpr int I_STAGES = 3;
-constexpr int I_A_PLANE = I_BM * I_BK;                 // 8 KB
-constexpr int I_B_PLANE = I_BN * I_BK;                 // 4 KB
-constexpr int I_A_BYTES = I_NS * I_A_PLANE, I_B_BYTES = I_NS * I_B_PLANE;
-constexpr int I_STAGE_BYTES = I_A_BYTES + I_B_BYTES;   // 72 KB
-constexpr int I_SMEM = I_STAGES * I_STAGE_BYTES + 1024 + 256;
 constexpr int I_THREADS = 192;                         // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int I_TMEM_COLS = 512;                       // 6 x 64 = 384 used
-// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
-constexpr uint32_t I_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I_BN >> 3) << 17) | ((uint32_t)(I_BM >> 4) << 24);
+constexpr int I_TMEM_COLS = 512;
+constexpr int I_MAX_NS = 6;
 
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// Two instantiations: NS slices per operand (= number of weight levels i + j = 0..NS-1, products NS (NS + 1) / 2) and the
+// widest tile whose NS INT32 accumulators fit the 512 TMEM columns:
+//   <6, 64>  42-bit operands, 21 products, 6 x 64 = 384 columns   ("i8x6": ~4e-8 relative variance error, FP64-grade)
+//   <5, 96>  35-bit operands, 15 products, 5 x 96 = 480 columns   ("i8x5": ~2e-6; fewer products AND a wider MMA, i.e.
+//            fewer shared-memory bytes per MAC -- faster and 400x more accurate than the 3xTF32 mode)
+template <int NS_, int BN_>
+struct I8Cfg {
+    static constexpr int NS = NS_, BN = BN_;
+    static constexpr int A_PLANE = I_BM * I_BK, B_PLANE = BN_ * I_BK;
+    static constexpr int A_BYTES = NS_ * A_PLANE, B_BYTES = NS_ * B_PLANE;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = I_STAGES * STAGE_BYTES + 1024 + 256;
+    // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = BN, M = 128
+    static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(I_BM >> 4) << 24);
+    static_assert(NS_ * BN_ <= I_TMEM_COLS && BN_ % 32 == 0 && NS_ <= I_MAX_NS, "accumulators must fit TMEM");
+};
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(I_IDESC), "r"(accumulate) : "memory");
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major operand plane [rows][64 B], SWIZZLE_64B: 8-row groups 512 B apart (SBO), LBO unused (1), version 1,
 // layout type 4 = SWIZZLE_64B   (cute::UMMA::SmemDescriptor)
@@ -53,6 +62,7 @@ struct I8Args {
     int Mc, N, T, Mtiles, GM;
 };
 
+template <int BN>
 __device__ __forceinline__ bool i8_item(const I8Args& p, int it, int& m0, int& I, int& kblocks) {
     const int item = (int)blockIdx.x + it * (int)gridDim.x;
     if (item >= p.T * p.Mtiles) return false;
@@ -61,13 +71,16 @@ __device__ __forceinline__ bool i8_item(const I8Args& p, int it, int& m0, int& I
     const int gm = (p.Mtiles - grp * p.GM) < p.GM ? (p.Mtiles - grp * p.GM) : p.GM;
     I = p.T - 1 - r / gm;
     m0 = (grp * p.GM + r % gm) * I_BM;
-    const int kend = ((I + 1) * I_BN < p.N) ? (I + 1) * I_BN : p.N;
+    const int kend = ((I + 1) * BN < p.N) ? (I + 1) * BN : p.N;      // rows of this n-tile are zero beyond their diagonal
     kblocks = (kend + I_BK - 1) / I_BK;
     return true;
 }
 
+template <class C>
 __global__ void __launch_bounds__(I_THREADS, 1)
 predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const I8Args p) {
+    constexpr int I_NS = C::NS, I_BN = C::BN, I_A_PLANE = C::A_PLANE, I_B_PLANE = C::B_PLANE, I_A_BYTES = C::A_BYTES;
+    constexpr int I_STAGE_BYTES = C::STAGE_BYTES, I_LEVELS = C::NS;
     extern __shared__ unsigned char i_smem_raw[];
     const uint32_t raw = smem_addr(i_smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;
@@ -100,7 +113,7 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         uint32_t stage = 0, phase = 0;
         int m0, I, kblocks;
-        for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+        for (int it = 0; i8_item<I_BN>(p, it, m0, I, kblocks); ++it) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 if (elect_one()) {
@@ -116,7 +129,7 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     } else if (warp == 1) {                                              // ===== MMA issuer (converged warp, one elected lane issues)
         uint32_t stage = 0, phase = 0;
         int m0, I, kblocks;
-        for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+        for (int it = 0; i8_item<I_BN>(p, it, m0, I, kblocks); ++it) {
             mbar_wait(tempty, (it & 1) ^ 1);                             // epilogue has drained the accumulators
             tc_fence_after();
             for (int kb = 0; kb < kblocks; ++kb) {
@@ -140,7 +153,7 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                                 // level w = i + j: its first product of the tile is (i = 0, j = w) of ks = 0
                                 const uint32_t accumulate = (ks == 0 && i == 0) ? fresh : 1u;
                                 tc_mma_i8(tmem_base + (i + j) * I_BN, ad[i] + (uint64_t)(2 * ks), bd[j] + (uint64_t)(2 * ks),
-                                          accumulate);
+                                          C::IDESC, accumulate);
                             }
                         }
                     }
@@ -154,7 +167,7 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     } else {                                                             // ===== epilogue warps 2..5: thread = query row
         const int quarter = warp & 3;
         int m0, I, kblocks;
-        for (int it = 0; i8_item(p, it, m0, I, kblocks); ++it) {
+        for (int it = 0; i8_item<I_BN>(p, it, m0, I, kblocks); ++it) {
             mbar_wait(tfull, it & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -199,11 +212,12 @@ __global__ void predict_finalize_i8_kernel(const double* __restrict__ partial, i
     var[m] = (variance - q * unit2) + noise_add;
 }
 
-// x / scale in (-1, 1)  ->  six signed 7-bit slices, round to nearest at every level (|slice| <= 64)
-__device__ __forceinline__ void slice6(double x, double inv_scale, int (&s)[I_NS]) {
+// x / scale in (-1, 1)  ->  ns signed 7-bit slices, round to nearest at every level (|slice| <= 64)
+__device__ __forceinline__ void slice_signed(double x, double inv_scale, int ns, int (&s)[I_MAX_NS]) {
     double r = x * inv_scale, w = 64.0;
 #pragma unroll
-    for (int k = 0; k < I_NS; ++k) {
+    for (int k = 0; k < I_MAX_NS; ++k) {
+        if (k >= ns) { s[k] = 0; continue; }
         const double t = rint(r * w);
         s[k] = (int)t;
         r = fma(-t, 1.0 / w, r);           // exact: w is a power of two, t has <= 8 significant bits
@@ -213,21 +227,22 @@ __device__ __forceinline__ void slice6(double x, double inv_scale, int (&s)[I_NS
 
 // planes[s][r][c] (int8, row pitch ldp bytes, plane pitch rows * ldp) of A[rows][lda]; columns >= cols are zeroed
 __global__ void i8_slice_kernel(const double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, double inv_scale,
-                                int8_t* __restrict__ planes, int64_t ldp) {
+                                int ns, int8_t* __restrict__ planes, int64_t ldp) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * ldp) return;
     const int64_t r = idx / ldp, c = idx % ldp;
-    int s[I_NS] = {0, 0, 0, 0, 0, 0};
-    if (c < cols) slice6(A[r * lda + c], inv_scale, s);
+    int s[I_MAX_NS] = {0, 0, 0, 0, 0, 0};
+    if (c < cols) slice_signed(A[r * lda + c], inv_scale, ns, s);
 #pragma unroll
-    for (int k = 0; k < I_NS; ++k) planes[(int64_t)k * rows * ldp + idx] = (int8_t)s[k];
+    for (int k = 0; k < I_MAX_NS; ++k)
+        if (k < ns) planes[(int64_t)k * rows * ldp + idx] = (int8_t)s[k];
 }
 
-// Cross-covariance chunk as six int8 planes [6][Mc][ldp] + the FP64 posterior mean.  k >= 0, so its 42-bit fixed-point
+// Cross-covariance chunk as NS int8 planes [NS][Mc][ldp] + the FP64 posterior mean.  k >= 0, so its 7 NS-bit fixed-point
 // value is cut into plain base-128 digits in [0, 127] with integer shifts (the signed round-to-nearest slicing of
-// slice6 costs as many FP64-pipe instructions as the exp itself).  A warp owns QPW queries; lane l handles observations
+// slice_signed costs as many FP64-pipe instructions as the exp itself).  A warp owns QPW queries; lane l handles observations
 // 4 l .. 4 l + 3 of every 128-block so that each plane store is a packed 32-bit word (128 B per warp and plane).
-template <int D>
+template <int D, int I_NS>
 __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const double* __restrict__ X, int64_t N,
                                                              const double* __restrict__ alpha,
                                                              const double* __restrict__ Xq, int64_t M, double inv_scale,
@@ -263,9 +278,10 @@ __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const dou
                 for (int i = 0; i < QPW; ++i) {
                     const double kv = rbf_eval<D>(k, q[i], x);              // exact exp: the mean of this mode is the FP64 mode's
                     acc[i] = fma(kv, a, acc[i]);
-                    // kv / scale in [0, 1)  ->  X = rint(. 2^42) <= 2^42;  digit s = bits [42 - 7 (s + 1), 42 - 7 s)
-                    unsigned long long X = (unsigned long long)__double2ll_rn(kv * inv_scale * 4398046511104.0);
-                    if (X > 4398046511103ull) X = 4398046511103ull;
+                    // kv / scale in [0, 1)  ->  X = rint(. 2^(7 NS));  digit s = bits [7 (NS - 1 - s), 7 (NS - s))
+                    constexpr unsigned long long TOP = 1ull << (7 * I_NS);
+                    unsigned long long X = (unsigned long long)__double2ll_rn(kv * inv_scale * (double)TOP);
+                    if (X > TOP - 1) X = TOP - 1;
 #pragma unroll
                     for (int s = 0; s < I_NS; ++s)
                         packed[i][s] |= (uint32_t)((X >> (7 * (I_NS - 1 - s))) & 127ull) << (8 * e);
@@ -289,9 +305,9 @@ __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const dou
     }
 }
 
-// planes [6][rows][ldp] int8, logical width `cols` bytes: box = 64 B x box_rows x 6 planes, SWIZZLE_64B, OOB -> 0
+// planes [ns][rows][ldp] int8, logical width `cols` bytes: box = 64 B x box_rows x ns planes, SWIZZLE_64B, OOB -> 0
 static int make_map_i8(CUtensorMap* map, const int8_t* base, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_pitch,
-                       int box_rows) {
+                       int box_rows, int I_NS) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IPP_E_CUDA; }
     const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)I_NS};
@@ -318,25 +334,86 @@ static double pow2_at_least(double x) {
 
 using namespace ipp;
 
-extern "C" int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale,
+extern "C" int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int n_slices,
                             int8_t* planes, int64_t ldp, void* stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(A && planes && rows >= 1 && cols >= 1 && lda >= cols && ldp >= cols && ldp % 16 == 0, "bad arguments");
     IPP_CHECK_ARG(scale > 0, "scale must be a positive power of two >= max |A|");
+    IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6");
     const int64_t total = rows * ldp;
-    i8_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, rows, cols, lda, 1.0 / scale, planes, ldp);
+    i8_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, rows, cols, lda, 1.0 / scale, n_slices, planes, ldp);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
 
 extern "C" int64_t ipp_gp_predict_i8_workspace(int64_t N, int64_t M) {
     if (N <= 0 || M <= 0) return 16;
-    const int64_t ldp = round_up(N, 128), mc = i8_chunk_rows(M), T = (N + I_BN - 1) / I_BN;
-    return (I_NS * mc * ldp + 7) / 8 + T * mc + 64;
+    const int64_t ldp = round_up(N, 128), mc = i8_chunk_rows(M), T = (N + 63) / 64;       // sized for the 6-slice layout
+    return (I_MAX_NS * mc * ldp + 7) / 8 + T * mc + 64;
 }
 
+namespace ipp {
+
+template <class C>
+static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha, const int8_t* linv_planes,
+                           int64_t ldl, double linv_scale, double noise_add, const double* Xq, int64_t M, double* mean,
+                           double* var, double* work, cudaStream_t stream) {
+    constexpr int NS = C::NS, BN = C::BN;
+    static bool configured = false;
+    if (!configured) {
+        IPP_CUDA(cudaFuncSetAttribute(predict_var_i8_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    const int64_t ldp = round_up(N, 128), mc_max = i8_chunk_rows(M);
+    const int T = (int)((N + BN - 1) / BN);
+    int8_t* planes = reinterpret_cast<int8_t*>(work);
+    double* partial = work + (I_MAX_NS * mc_max * ldp + 7) / 8;
+    const double sa = pow2_at_least(kern->variance * (1.0 + 1e-12));      // k(q, x) <= variance for every pair
+    // v = D * sa * sb * 2^-13 with D = sum_w D_w 2^(-7 w): the epilogue sums squares of D, so one constant at the end
+    // (cross-covariance digits carry 2^(-7 - 7 s), Linv slices 2^(-6 - 7 s): 2^-13 in front of level 0)
+    const double unit = sa * linv_scale / 8192.0;
+    CUtensorMap map_b;
+    IPP_TRY(make_map_i8(&map_b, linv_planes, N, N, ldl, N * ldl, BN, NS));
+    const RbfDev kd = to_dev(*kern);
+    const int grid = sm_count();
+    for (int64_t s = 0; s < M; s += mc_max) {
+        const int64_t mc = (M - s) < mc_max ? (M - s) : mc_max;
+        const unsigned qblocks = (unsigned)((mc + 15) / 16);
+        if (kern->dim == 2)
+            rbf_queries_i8_kernel<2, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 2, mc, 1.0 / sa, planes, ldp,
+                                                                      mc * ldp, mean + s);
+        else
+            rbf_queries_i8_kernel<3, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 3, mc, 1.0 / sa, planes, ldp,
+                                                                      mc * ldp, mean + s);
+        IPP_LAUNCH_CHECK();
+        CUtensorMap map_a;
+        IPP_TRY(make_map_i8(&map_a, planes, mc, N, ldp, mc * ldp, I_BM, NS));
+        I8Args p;
+        p.partial = partial; p.ldp = mc_max;
+        p.Mc = (int)mc; p.N = (int)N; p.T = T; p.Mtiles = (int)((mc + I_BM - 1) / I_BM);
+        {
+            const int64_t panel = (int64_t)I_BM * ldp * NS;              // bytes of one m-tile's planes
+            int64_t gm = (48LL << 20) / panel;
+            if (gm < 1) gm = 1;
+            if (gm > p.Mtiles) gm = p.Mtiles;
+            p.GM = (int)gm;
+        }
+        const int items = p.T * p.Mtiles;
+        profile_mark(0, stream);
+        predict_var_i8_kernel<C><<<items < grid ? items : grid, I_THREADS, C::SMEM, stream>>>(map_a, map_b, p);
+        profile_mark(1, stream);
+        IPP_LAUNCH_CHECK();
+        predict_finalize_i8_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, T, (int)mc, unit * unit,
+                                                                                    kern->variance, noise_add, var + s);
+        IPP_LAUNCH_CHECK();
+    }
+    return IPP_OK;
+}
+
+}  // namespace ipp
+
 extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                                 const int8_t* linv_planes, int64_t ldl, double linv_scale, double noise_add,
+                                 const int8_t* linv_planes, int64_t ldl, double linv_scale, int n_slices, double noise_add,
                                  const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(kern && X && alpha && linv_planes && Xq && mean && var && work, "null pointer");
@@ -345,53 +422,8 @@ extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N
     IPP_CHECK_ARG(ldl >= N && ldl % 16 == 0 && reinterpret_cast<uintptr_t>(linv_planes) % 16 == 0,
                   "linv planes must be 16-byte aligned with ldl % 16 == 0");
     IPP_CHECK_ARG(linv_scale > 0 && kern->variance > 0, "scales must be positive");
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(predict_var_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM));
-        configured = true;
-    }
-    const int64_t ldp = round_up(N, 128), mc_max = i8_chunk_rows(M);
-    const int T = (int)((N + I_BN - 1) / I_BN);
-    int8_t* planes = reinterpret_cast<int8_t*>(work);
-    double* partial = work + (I_NS * mc_max * ldp + 7) / 8;
-    const double sa = pow2_at_least(kern->variance * (1.0 + 1e-12));      // k(q, x) <= variance for every pair
-    // v = D * sa * sb * 2^-13 with D = sum_w D_w 2^(-7 w): the epilogue sums squares of D, so one constant at the end
-    // (cross-covariance digits carry 2^(-7 - 7 s), Linv slices 2^(-6 - 7 s): 2^-13 in front of level 0)
-    const double unit = sa * linv_scale / 8192.0;
-    CUtensorMap map_b;
-    IPP_TRY(make_map_i8(&map_b, linv_planes, N, N, ldl, N * ldl, I_BN));
-    const RbfDev kd = to_dev(*kern);
-    const int grid = sm_count();
-    for (int64_t s = 0; s < M; s += mc_max) {
-        const int64_t mc = (M - s) < mc_max ? (M - s) : mc_max;
-        const unsigned qblocks = (unsigned)((mc + 15) / 16);
-        if (kern->dim == 2)
-            rbf_queries_i8_kernel<2><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 2, mc, 1.0 / sa, planes, ldp,
-                                                                  mc * ldp, mean + s);
-        else
-            rbf_queries_i8_kernel<3><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 3, mc, 1.0 / sa, planes, ldp,
-                                                                  mc * ldp, mean + s);
-        IPP_LAUNCH_CHECK();
-        CUtensorMap map_a;
-        IPP_TRY(make_map_i8(&map_a, planes, mc, N, ldp, mc * ldp, I_BM));
-        I8Args p;
-        p.partial = partial; p.ldp = mc_max;
-        p.Mc = (int)mc; p.N = (int)N; p.T = T; p.Mtiles = (int)((mc + I_BM - 1) / I_BM);
-        {
-            const int64_t panel = (int64_t)I_BM * ldp * I_NS;            // bytes of one m-tile's six planes
-            int64_t gm = (48LL << 20) / panel;
-            if (gm < 1) gm = 1;
-            if (gm > p.Mtiles) gm = p.Mtiles;
-            p.GM = (int)gm;
-        }
-        const int items = p.T * p.Mtiles;
-        profile_mark(0, stream);
-        predict_var_i8_kernel<<<items < grid ? items : grid, I_THREADS, I_SMEM, stream>>>(map_a, map_b, p);
-        profile_mark(1, stream);
-        IPP_LAUNCH_CHECK();
-        predict_finalize_i8_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, T, (int)mc, unit * unit,
-                                                                                    kern->variance, noise_add, var + s);
-        IPP_LAUNCH_CHECK();
-    }
-    return IPP_OK;
+    IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6 (the count linv_planes was cut with)");
+    if (n_slices == 6)
+        return predict_i8_impl<I8Cfg<6, 64>>(kern, X, N, alpha, linv_planes, ldl, linv_scale, noise_add, Xq, M, mean, var, work, stream);
+    return predict_i8_impl<I8Cfg<5, 96>>(kern, X, N, alpha, linv_planes, ldl, linv_scale, noise_add, Xq, M, mean, var, work, stream);
 }

@@ -767,3 +767,22 @@ def test_predict_i8x6_mode_is_fp64_grade(pkg, N, M, noise):
     m.predict_precision = 'fp64'
     v_b = m.predict_value(q[:200])[1]
     np.testing.assert_allclose(v_a, v_b, rtol=2e-7 if noise == 0.5 else 1e-2, atol=0 if noise == 0.5 else 1e-4)
+
+
+@pytest.mark.parametrize('N,M', [(9, 70), (100, 200), (333, 130), (1000, 5000), (2048, 33000)])
+def test_predict_i8x5_mode(pkg, N, M):
+    """Five-slice INT8 mode (35-bit operands, 15 products, 128 x 96 tiles): the fast tensor mode.  Mean as in FP64 mode;
+    variance within 2e-5 relative of the FP64 mode (measured ~2e-6) -- two orders inside the 1e-4 the north star allows
+    its reduced-precision mode, ragged N (n-tiles of 96 against k-blocks of 64) included."""
+    rng = np.random.default_rng(N + 5)
+    X, z = world(rng, N, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    q = rng.uniform(0, 10, (M, 2))
+    mu64, var64 = m.predict_value(q)
+    m.predict_precision = 'i8x5'
+    mu5, var5 = m.predict_value(q)
+    np.testing.assert_allclose(mu5, mu64, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(var5, var64, rtol=2e-5)
+    m.predict_precision = 'i8x6'                      # both slice counts cached side by side
+    np.testing.assert_allclose(m.predict_value(q)[1], var64, rtol=2e-7)

@@ -40,7 +40,12 @@ for N in [int(a) for a in (sys.argv[1:] or ['333', '1024', '2048', '4096', '8192
     T64 = (N + 63) // 64
     res['mode'] = MODE
     res['tf32_executed_tflops'] = 3 * 2.0 * 128 * 128 * T * (T + 1) / 2 * M / (res[MODE + '_ms'] / 1e3) / 1e12 if MODE == 'tf32x3' else None
-    res['i8_executed_tops'] = 21 * 2.0 * 64 * 64 * T64 * (T64 + 1) / 2 * M / (res[MODE + '_ms'] / 1e3) / 1e12 if MODE == 'i8x6' else None
+    if MODE in ('i8x6', 'i8x5'):
+        ns, bn = (6, 64) if MODE == 'i8x6' else (5, 96)
+        kblocks = sum(-(-min((I + 1) * bn, N) // 64) for I in range(-(-N // bn)))
+        res['i8_executed_tops'] = ns * (ns + 1) / 2 * 2.0 * 128 * bn * 64 * kblocks * (M / 128) / (res[MODE + '_ms'] / 1e3) / 1e12
+    else:
+        res['i8_executed_tops'] = None
     print(json.dumps(res)); out.append(res)
 os.makedirs('gpurun_out', exist_ok=True)
-json.dump(out, open('gpurun_out/%s_sweep.json' % ('tf32' if MODE == 'tf32x3' else 'i8'), 'w'), indent=1)
+json.dump(out, open('gpurun_out/%s_sweep.json' % MODE, 'w'), indent=1)
