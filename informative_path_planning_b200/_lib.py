@@ -154,6 +154,31 @@ def to_device(a):
         return a.to(device=device(), dtype=torch.float64).contiguous()
     a = np.ascontiguousarray(a, dtype=np.float64)
     t = torch.from_numpy(a)
-    if t.numel() >= (1 << 16):
-        t = t.pin_memory()
-    return t.to(device(), non_blocking=True)
+    if t.numel() < (1 << 21):
+        return t.to(device())                        # < 16 MB: a pageable copy beats pinning a fresh buffer (~5 ms per cudaHostAlloc)
+    return _staged_upload(t)
+
+
+_staging = {}
+
+
+def _staged_upload(t):
+    """Large host array -> device through a reused pinned staging buffer (grow-only, two slots, each guarded by the
+    event of its last DMA so a slot is never overwritten while the copy engine still reads it)."""
+    dev = device()
+    st = _staging.setdefault(dev.index, {'bufs': [None, None], 'events': [None, None], 'next': 0})
+    i = st['next']
+    st['next'] = 1 - i
+    if st['events'][i] is not None:
+        st['events'][i].synchronize()
+    buf = st['bufs'][i]
+    if buf is None or buf.numel() < t.numel():
+        buf = torch.empty(t.numel(), dtype=torch.float64).pin_memory()
+        st['bufs'][i] = buf
+    view = buf[:t.numel()].view(t.shape)
+    view.copy_(t)
+    out = view.to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    st['events'][i] = ev
+    return out
