@@ -20,6 +20,9 @@
 
 namespace ipp {
 
+#ifndef IPP_I8_COLLECTOR
+#define IPP_I8_COLLECTOR 1
+#endif
 constexpr int I_BM = 128, I_BK = 64;                   // tile rows; I_BK int8 = 64 B = one SWIZZLE_64B row
 constexpr int I_STAGES = 3;
 constexpr int I_THREADS = 192;                         // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
@@ -43,12 +46,28 @@ struct I8Cfg {
     static_assert(NS_ * BN_ <= I_TMEM_COLS && BN_ % 32 == 0 && NS_ <= I_MAX_NS, "accumulators must fit TMEM");
 };
 
+// COLL: use of the tensor core's A-operand collector buffer.  Consecutive MMAs that share their A slice (one slice of
+// the cross-covariance against every Linv slice j <= NS - 1 - i) keep it in the collector instead of re-reading 4 KB of
+// shared memory each time -- SS-mode operand reads were the limiter of this kernel (6 KB per 32-clk MMA at N = 64).
+//   0 = discard (default), 1 = fill (first of a run), 2 = use, 3 = lastuse          (SASS: .A_KEEP / .A_REUSE)
+template <int COLL>
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if (COLL == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (COLL == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (COLL == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major operand plane [rows][64 B], SWIZZLE_64B: 8-row groups 512 B apart (SBO), LBO unused (1), version 1,
 // layout type 4 = SWIZZLE_64B   (cute::UMMA::SmemDescriptor)
@@ -152,8 +171,13 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             for (int j = 0; j < I_NS - i; ++j) {
                                 // level w = i + j: its first product of the tile is (i = 0, j = w) of ks = 0
                                 const uint32_t accumulate = (ks == 0 && i == 0) ? fresh : 1u;
-                                tc_mma_i8(tmem_base + (i + j) * I_BN, ad[i] + (uint64_t)(2 * ks), bd[j] + (uint64_t)(2 * ks),
-                                          C::IDESC, accumulate);
+                                const uint32_t dcol = tmem_base + (i + j) * I_BN;
+                                const uint64_t a = ad[i] + (uint64_t)(2 * ks), b = bd[j] + (uint64_t)(2 * ks);
+                                constexpr bool kReuse = IPP_I8_COLLECTOR != 0;
+                                if (!kReuse || I_NS - i == 1) tc_mma_i8<0>(dcol, a, b, C::IDESC, accumulate);
+                                else if (j == 0) tc_mma_i8<1>(dcol, a, b, C::IDESC, accumulate);
+                                else if (j == I_NS - i - 1) tc_mma_i8<3>(dcol, a, b, C::IDESC, accumulate);
+                                else tc_mma_i8<2>(dcol, a, b, C::IDESC, accumulate);
                             }
                         }
                     }
