@@ -126,14 +126,17 @@ int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const d
  *      ~2e-8 relative (inside the FP64 mode's 1e-6 parity tolerance); the mean is computed exactly as in FP64 mode.
  *      n_slices = 6: 42-bit operands, 21 products, 128 x 64 tiles ("i8x6", the FP64-grade setting above);
  *      n_slices = 5: 35-bit operands, 15 products, 128 x 96 tiles ("i8x5": ~2e-6 relative variance error, ~1.7x faster).
- *        ipp_i8_slice: A[rows][lda] (double) -> planes [n_slices][rows][ldp] (int8), scale = power of two >= max |A|;
- *        linv_planes: the slices of Linv [N][ldl bytes], ldl % 16 == 0; linv_scale / n_slices: what they were cut with;
+ *        ipp_i8_slice: A[rows][lda] (double) -> ipp_i8_slice_bytes(rows, cols, n_slices) bytes of int8 "tiles": the slices
+ *        laid out as the kernel's shared-memory stage images ([row tile][k-block of 64][slice][tile rows][64 B], 64-byte
+ *        swizzle applied), so a stage is one contiguous bulk copy; scale = power of two >= max |A|;
+ *        linv_tiles: that layout of Linv; linv_scale / n_slices: what it was cut with;
  *      work: ipp_gp_predict_i8_workspace(N, M) doubles. */
-int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int n_slices, int8_t* planes,
-                 int64_t ldp, void* stream);
+int64_t ipp_i8_slice_bytes(int64_t rows, int64_t cols, int n_slices);
+int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int n_slices, int8_t* tiles,
+                 void* stream);
 int64_t ipp_gp_predict_i8_workspace(int64_t N, int64_t M);
 int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                      const int8_t* linv_planes, int64_t ldl, double linv_scale, int n_slices, double noise_add,
+                      const int8_t* linv_tiles, double linv_scale, int n_slices, double noise_add,
                       const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
 
 /* CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 / ipp_gp_predict_i8 (the fused DMMA variance kernel), recorded on

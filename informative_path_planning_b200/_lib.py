@@ -53,9 +53,10 @@ SIGNATURES = {
     'ipp_tf32_split': (_INT, [_P, _I64, _I64, _I64, _P, _P, _I64, _P]),
     'ipp_gp_predict_tf32_workspace': (_I64, [_I64, _I64]),
     'ipp_gp_predict_tf32': (_INT, [_RBF, _P, _I64, _P, _P, _P, _I64, _INT, _D, _P, _I64, _P, _P, _P, _P]),
-    'ipp_i8_slice': (_INT, [_P, _I64, _I64, _I64, _D, _INT, _P, _I64, _P]),
+    'ipp_i8_slice_bytes': (_I64, [_I64, _I64, _INT]),
+    'ipp_i8_slice': (_INT, [_P, _I64, _I64, _I64, _D, _INT, _P, _P]),
     'ipp_gp_predict_i8_workspace': (_I64, [_I64, _I64]),
-    'ipp_gp_predict_i8': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _D, _INT, _D, _P, _I64, _P, _P, _P, _P]),
+    'ipp_gp_predict_i8': (_INT, [_RBF, _P, _I64, _P, _P, _D, _INT, _D, _P, _I64, _P, _P, _P, _P]),
     'ipp_profile_enable': (_INT, [_INT]),
     'ipp_profile_read': (_INT, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     'ipp_gp_predict_cov_workspace': (_I64, [_I64, _I64]),

@@ -12,9 +12,13 @@
 // measured variance error <= ~2e-8 relative at N = 2048..8192 (noise 0.5), i.e. inside the FP64 mode's 1e-6 parity
 // tolerance with a wide margin (numpy emulation with exact integers agrees: 2.0e-8).
 //
-// Kernel: 128 x 64 tiles (6 levels x 64 columns of TMEM), K-major SWIZZLE_64B operand planes staged by two 3-D TMA
-// loads per stage ([6 planes][rows][64 B]), 3 x 72 KB stages, 42 MMAs (128 x 64 x 32) per stage issued by one thread,
-// persistent warp-specialised CTA as in predict_tf32.cu.  Lower-triangular Linv: n-tile I contracts k < 64 (I + 1).
+// Kernel: 128 x 64 tiles (6 levels x 64 columns of TMEM), 3 x 72 KB stages, 42 MMAs (128 x 64 x 32) per stage issued by
+// one thread, persistent warp-specialised CTA as in predict_tf32.cu.  Lower-triangular Linv: n-tile I contracts
+// k < 64 (I + 1).
+// Operand layout: the generators write the planes ALREADY in the shared-memory image of a stage -- tile-major
+// [row tile][k-block of 64][plane][rows][64 B] with the SWIZZLE_64B chunk permutation applied (16-byte chunk c of row r
+// lives at chunk c ^ ((r >> 1) & 3)) -- so a stage is two contiguous 1-D bulk copies (48 + 24 KB at 6 x 64) instead of
+// 1152 64-byte tensor-map rows; with tensor maps the TMA request rate (~2.2 clk per 64-byte row) capped the kernel.
 #include "internal.cuh"
 #include "tc05.cuh"
 
@@ -77,9 +81,15 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
 }
 
 struct I8Args {
+    const int8_t* a_tiles;             // [Mtiles][KB][NS][128][64 B]   cross-covariance digits (swizzled stage images)
+    const int8_t* b_tiles;             // [T][KB][NS][BN][64 B]         Linv slices
+    int KB;                            // k-blocks of 64 in a row: ceil(N / 64)
     double* partial; int64_t ldp;      // [T][ldp] per-(n-tile, query) sums of squares in units of (sa sb 2^-13)^2
     int Mc, N, T, Mtiles, GM;
 };
+
+// byte offset of element (row r of its tile, k) inside a [rows][64 B] SWIZZLE_64B plane of a k-block
+__host__ __device__ __forceinline__ int swz64(int r, int kk) { return r * 64 + ((((kk >> 4) ^ (r >> 1)) & 3) << 4) + (kk & 15); }
 
 template <int BN>
 __device__ __forceinline__ bool i8_item(const I8Args& p, int it, int& m0, int& I, int& kblocks) {
@@ -97,7 +107,7 @@ __device__ __forceinline__ bool i8_item(const I8Args& p, int it, int& m0, int& I
 
 template <class C>
 __global__ void __launch_bounds__(I_THREADS, 1)
-predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const I8Args p) {
+predict_var_i8_kernel(const I8Args p) {
     constexpr int I_NS = C::NS, I_BN = C::BN, I_A_PLANE = C::A_PLANE, I_B_PLANE = C::B_PLANE, I_A_BYTES = C::A_BYTES;
     constexpr int I_STAGE_BYTES = C::STAGE_BYTES, I_LEVELS = C::NS;
     extern __shared__ unsigned char i_smem_raw[];
@@ -126,10 +136,6 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {                                                     // ===== TMA producer (converged warp, one elected lane issues)
-        if (elect_one()) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        }
         uint32_t stage = 0, phase = 0;
         int m0, I, kblocks;
         for (int it = 0; i8_item<I_BN>(p, it, m0, I, kblocks); ++it) {
@@ -138,8 +144,8 @@ predict_var_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (elect_one()) {
                     const uint32_t full = full0 + 8 * stage, dst = tiles + stage * I_STAGE_BYTES;
                     mbar_expect_tx(full, I_STAGE_BYTES);
-                    tma_load_3d(dst, &map_a, kb * I_BK, m0, 0, full);               // [6][128][64 B]
-                    tma_load_3d(dst + I_A_BYTES, &map_b, kb * I_BK, I * I_BN, 0, full);   // [6][64][64 B]
+                    bulk_load(dst, p.a_tiles + ((int64_t)(m0 / I_BM) * p.KB + kb) * I_A_BYTES, I_A_BYTES, full);
+                    bulk_load(dst + I_A_BYTES, p.b_tiles + ((int64_t)I * p.KB + kb) * C::B_BYTES, C::B_BYTES, full);
                 }
                 __syncwarp();
                 if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
@@ -249,17 +255,20 @@ __device__ __forceinline__ void slice_signed(double x, double inv_scale, int ns,
     }
 }
 
-// planes[s][r][c] (int8, row pitch ldp bytes, plane pitch rows * ldp) of A[rows][lda]; columns >= cols are zeroed
+// tiles[row tile][k-block][slice][bn][64 B] of A[rows][lda] (swizzled stage images); rows >= `rows` and columns >= `cols`
+// of the padded extent are zeroed
 __global__ void i8_slice_kernel(const double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, double inv_scale,
-                                int ns, int8_t* __restrict__ planes, int64_t ldp) {
+                                int ns, int bn, int64_t KB, int64_t rows_pad, int8_t* __restrict__ tiles) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * ldp) return;
-    const int64_t r = idx / ldp, c = idx % ldp;
+    if (idx >= rows_pad * KB * 64) return;
+    const int64_t r = idx / (KB * 64), c = idx % (KB * 64);
     int s[I_MAX_NS] = {0, 0, 0, 0, 0, 0};
-    if (c < cols) slice_signed(A[r * lda + c], inv_scale, ns, s);
+    if (r < rows && c < cols) slice_signed(A[r * lda + c], inv_scale, ns, s);
+    const int64_t tile = r / bn, kb = c / 64;
+    const int64_t base = ((tile * KB + kb) * ns) * ((int64_t)bn * 64) + swz64((int)(r % bn), (int)(c % 64));
 #pragma unroll
     for (int k = 0; k < I_MAX_NS; ++k)
-        if (k < ns) planes[(int64_t)k * rows * ldp + idx] = (int8_t)s[k];
+        if (k < ns) tiles[base + (int64_t)k * bn * 64] = (int8_t)s[k];
 }
 
 // Cross-covariance chunk as NS int8 planes [NS][Mc][ldp] + the FP64 posterior mean.  k >= 0, so its 7 NS-bit fixed-point
@@ -270,7 +279,7 @@ template <int D, int I_NS>
 __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const double* __restrict__ X, int64_t N,
                                                              const double* __restrict__ alpha,
                                                              const double* __restrict__ Xq, int64_t M, double inv_scale,
-                                                             int8_t* __restrict__ planes, int64_t ldp, int64_t plane_pitch,
+                                                             int8_t* __restrict__ tiles, int64_t KB,
                                                              double* __restrict__ mean) {
     constexpr int QPW = 2;
     const int lane = threadIdx.x & 31;
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const dou
         for (int d = 0; d < D; ++d) q[i][d] = Xq[m * D + d];
         acc[i] = 0.0;
     }
-    for (int64_t n0 = 4 * lane; n0 < ldp; n0 += 128) {
+    for (int64_t n0 = 4 * lane; n0 < KB * 64; n0 += 128) {
         uint32_t packed[QPW][I_NS];
 #pragma unroll
         for (int i = 0; i < QPW; ++i)
@@ -317,7 +326,8 @@ __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const dou
             if (m0 + i < M) {
 #pragma unroll
                 for (int s = 0; s < I_NS; ++s)
-                    *reinterpret_cast<uint32_t*>(planes + (int64_t)s * plane_pitch + (m0 + i) * ldp + n0) = packed[i][s];
+                    *reinterpret_cast<uint32_t*>(tiles + ((((m0 + i) / I_BM) * KB + n0 / 64) * I_NS + s) * (int64_t)(I_BM * 64) +
+                                                 swz64((int)((m0 + i) % I_BM), (int)(n0 % 64))) = packed[i][s];
             }
     }
 #pragma unroll
@@ -327,22 +337,6 @@ __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const dou
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0 && m0 + i < M) mean[m0 + i] = s;
     }
-}
-
-// planes [ns][rows][ldp] int8, logical width `cols` bytes: box = 64 B x box_rows x ns planes, SWIZZLE_64B, OOB -> 0
-static int make_map_i8(CUtensorMap* map, const int8_t* base, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_pitch,
-                       int box_rows, int I_NS) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IPP_E_CUDA; }
-    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)I_NS};
-    const cuuint64_t strides[2] = {(cuuint64_t)ldp, (cuuint64_t)plane_pitch};
-    const cuuint32_t box[3] = {(cuuint32_t)I_BK, (cuuint32_t)box_rows, (cuuint32_t)I_NS};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (int8 planes) failed with CUresult %d", (int)r); return IPP_E_CUDA; }
-    return IPP_OK;
 }
 
 constexpr int64_t I8_CHUNK = 32768;
@@ -358,29 +352,39 @@ static double pow2_at_least(double x) {
 
 using namespace ipp;
 
+static int bn_of(int n_slices) { return n_slices == 6 ? 64 : 96; }
+
+extern "C" int64_t ipp_i8_slice_bytes(int64_t rows, int64_t cols, int n_slices) {
+    if (rows <= 0 || cols <= 0 || (n_slices != 5 && n_slices != 6)) return 0;
+    const int64_t bn = bn_of(n_slices);
+    return round_up(rows, bn) * ((cols + 63) / 64) * 64 * n_slices;
+}
+
 extern "C" int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t lda, double scale, int n_slices,
-                            int8_t* planes, int64_t ldp, void* stream_) {
+                            int8_t* tiles, void* stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
-    IPP_CHECK_ARG(A && planes && rows >= 1 && cols >= 1 && lda >= cols && ldp >= cols && ldp % 16 == 0, "bad arguments");
+    IPP_CHECK_ARG(A && tiles && rows >= 1 && cols >= 1 && lda >= cols, "bad arguments");
+    IPP_CHECK_ARG(reinterpret_cast<uintptr_t>(tiles) % 16 == 0, "tiles must be 16-byte aligned");
     IPP_CHECK_ARG(scale > 0, "scale must be a positive power of two >= max |A|");
     IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6");
-    const int64_t total = rows * ldp;
-    i8_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, rows, cols, lda, 1.0 / scale, n_slices, planes, ldp);
+    const int bn = bn_of(n_slices);
+    const int64_t KB = (cols + 63) / 64, rows_pad = round_up(rows, bn), total = rows_pad * KB * 64;
+    i8_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, rows, cols, lda, 1.0 / scale, n_slices, bn, KB, rows_pad, tiles);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
 
 extern "C" int64_t ipp_gp_predict_i8_workspace(int64_t N, int64_t M) {
     if (N <= 0 || M <= 0) return 16;
-    const int64_t ldp = round_up(N, 128), mc = i8_chunk_rows(M), T = (N + 63) / 64;       // sized for the 6-slice layout
-    return (I_MAX_NS * mc * ldp + 7) / 8 + T * mc + 64;
+    const int64_t KB = (N + 63) / 64, mc = i8_chunk_rows(M), T = (N + 63) / 64;           // sized for the 6-slice layout
+    return (I_MAX_NS * mc * KB * 64 + 7) / 8 + T * mc + 64;
 }
 
 namespace ipp {
 
 template <class C>
-static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha, const int8_t* linv_planes,
-                           int64_t ldl, double linv_scale, double noise_add, const double* Xq, int64_t M, double* mean,
+static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha, const int8_t* linv_tiles,
+                           double linv_scale, double noise_add, const double* Xq, int64_t M, double* mean,
                            double* var, double* work, cudaStream_t stream) {
     constexpr int NS = C::NS, BN = C::BN;
     static bool configured = false;
@@ -388,35 +392,30 @@ static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, cons
         IPP_CUDA(cudaFuncSetAttribute(predict_var_i8_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
-    const int64_t ldp = round_up(N, 128), mc_max = i8_chunk_rows(M);
+    const int64_t KB = (N + 63) / 64, mc_max = i8_chunk_rows(M);
     const int T = (int)((N + BN - 1) / BN);
-    int8_t* planes = reinterpret_cast<int8_t*>(work);
-    double* partial = work + (I_MAX_NS * mc_max * ldp + 7) / 8;
+    int8_t* tiles = reinterpret_cast<int8_t*>(work);
+    double* partial = work + (I_MAX_NS * mc_max * KB * 64 + 7) / 8;
     const double sa = pow2_at_least(kern->variance * (1.0 + 1e-12));      // k(q, x) <= variance for every pair
     // v = D * sa * sb * 2^-13 with D = sum_w D_w 2^(-7 w): the epilogue sums squares of D, so one constant at the end
     // (cross-covariance digits carry 2^(-7 - 7 s), Linv slices 2^(-6 - 7 s): 2^-13 in front of level 0)
     const double unit = sa * linv_scale / 8192.0;
-    CUtensorMap map_b;
-    IPP_TRY(make_map_i8(&map_b, linv_planes, N, N, ldl, N * ldl, BN, NS));
     const RbfDev kd = to_dev(*kern);
     const int grid = sm_count();
     for (int64_t s = 0; s < M; s += mc_max) {
         const int64_t mc = (M - s) < mc_max ? (M - s) : mc_max;
         const unsigned qblocks = (unsigned)((mc + 15) / 16);
         if (kern->dim == 2)
-            rbf_queries_i8_kernel<2, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 2, mc, 1.0 / sa, planes, ldp,
-                                                                      mc * ldp, mean + s);
+            rbf_queries_i8_kernel<2, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 2, mc, 1.0 / sa, tiles, KB, mean + s);
         else
-            rbf_queries_i8_kernel<3, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 3, mc, 1.0 / sa, planes, ldp,
-                                                                      mc * ldp, mean + s);
+            rbf_queries_i8_kernel<3, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 3, mc, 1.0 / sa, tiles, KB, mean + s);
         IPP_LAUNCH_CHECK();
-        CUtensorMap map_a;
-        IPP_TRY(make_map_i8(&map_a, planes, mc, N, ldp, mc * ldp, I_BM, NS));
         I8Args p;
+        p.a_tiles = tiles; p.b_tiles = linv_tiles; p.KB = (int)KB;
         p.partial = partial; p.ldp = mc_max;
         p.Mc = (int)mc; p.N = (int)N; p.T = T; p.Mtiles = (int)((mc + I_BM - 1) / I_BM);
         {
-            const int64_t panel = (int64_t)I_BM * ldp * NS;              // bytes of one m-tile's planes
+            const int64_t panel = (int64_t)I_BM * KB * 64 * NS;          // bytes of one m-tile's planes
             int64_t gm = (48LL << 20) / panel;
             if (gm < 1) gm = 1;
             if (gm > p.Mtiles) gm = p.Mtiles;
@@ -424,7 +423,7 @@ static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, cons
         }
         const int items = p.T * p.Mtiles;
         profile_mark(0, stream);
-        predict_var_i8_kernel<C><<<items < grid ? items : grid, I_THREADS, C::SMEM, stream>>>(map_a, map_b, p);
+        predict_var_i8_kernel<C><<<items < grid ? items : grid, I_THREADS, C::SMEM, stream>>>(p);
         profile_mark(1, stream);
         IPP_LAUNCH_CHECK();
         predict_finalize_i8_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(partial, mc_max, T, (int)mc, unit * unit,
@@ -437,17 +436,17 @@ static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, cons
 }  // namespace ipp
 
 extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                                 const int8_t* linv_planes, int64_t ldl, double linv_scale, int n_slices, double noise_add,
+                                 const int8_t* linv_tiles, double linv_scale, int n_slices, double noise_add,
                                  const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    IPP_CHECK_ARG(kern && X && alpha && linv_planes && Xq && mean && var && work, "null pointer");
+    IPP_CHECK_ARG(kern && X && alpha && linv_tiles && Xq && mean && var && work, "null pointer");
     IPP_CHECK_ARG(N >= 1 && M >= 1 && N <= 40000, "bad shape (exact INT32 accumulation: 6 pairs x 127 x 64 x N < 2^31)");
     IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
-    IPP_CHECK_ARG(ldl >= N && ldl % 16 == 0 && reinterpret_cast<uintptr_t>(linv_planes) % 16 == 0,
-                  "linv planes must be 16-byte aligned with ldl % 16 == 0");
+    IPP_CHECK_ARG(reinterpret_cast<uintptr_t>(linv_tiles) % 16 == 0 && reinterpret_cast<uintptr_t>(work) % 16 == 0,
+                  "linv tiles and work must be 16-byte aligned");
     IPP_CHECK_ARG(linv_scale > 0 && kern->variance > 0, "scales must be positive");
-    IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6 (the count linv_planes was cut with)");
+    IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6 (the count linv_tiles was cut with)");
     if (n_slices == 6)
-        return predict_i8_impl<I8Cfg<6, 64>>(kern, X, N, alpha, linv_planes, ldl, linv_scale, noise_add, Xq, M, mean, var, work, stream);
-    return predict_i8_impl<I8Cfg<5, 96>>(kern, X, N, alpha, linv_planes, ldl, linv_scale, noise_add, Xq, M, mean, var, work, stream);
+        return predict_i8_impl<I8Cfg<6, 64>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
+    return predict_i8_impl<I8Cfg<5, 96>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
 }

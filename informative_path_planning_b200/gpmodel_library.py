@@ -289,27 +289,27 @@ class GPModel(object):
         return linv, ld
 
     def _i8_operand(self, ns):
-        """(planes [ns][N][ld] int8, ld, scale): ns signed 7-bit slices of L^-1 against one power-of-two scale."""
+        """(tiles, scale): ns signed 7-bit slices of L^-1 against one power-of-two scale, in the kernel's stage-image
+        layout (ipp_i8_slice)."""
         if self._i8 is None:
             self._i8 = {}
         if ns not in self._i8:
             N, dev = self.n_obs, L.device()
             linv, lda = self._linv_for_tensor_modes()
             scale = 2.0 ** int(np.ceil(np.log2(float(linv[:, :N].abs().max().item()) * (1.0 + 1e-12))))
-            ldl = L.round_up(N, 128)
-            planes = torch.empty((ns, N, ldl), dtype=torch.int8, device=dev)
-            L.check(L.lib.ipp_i8_slice(L.ptr(linv), N, N, lda, scale, ns, L.ptr(planes), ldl, L.stream_ptr()))
-            self._i8[ns] = (planes, ldl, scale)
+            tiles = torch.empty(int(L.lib.ipp_i8_slice_bytes(N, N, ns)), dtype=torch.int8, device=dev)
+            L.check(L.lib.ipp_i8_slice(L.ptr(linv), N, N, lda, scale, ns, L.ptr(tiles), L.stream_ptr()))
+            self._i8[ns] = (tiles, scale)
         return self._i8[ns]
 
     def _predict_i8(self, xq_d, include_noise, ns=6):
         M, N = xq_d.shape[0], self.n_obs
-        planes, ldl, scale = self._i8_operand(ns)
+        tiles, scale = self._i8_operand(ns)
         mean = torch.empty(M, dtype=torch.float64, device=xq_d.device)
         var = torch.empty(M, dtype=torch.float64, device=xq_d.device)
         work = L.workspace(L.lib.ipp_gp_predict_i8_workspace(N, M), slot='i8')
         L.check(L.lib.ipp_gp_predict_i8(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                        L.ptr(planes), ldl, scale, ns, float(self.noise) if include_noise else 0.0,
+                                        L.ptr(tiles), scale, ns, float(self.noise) if include_noise else 0.0,
                                         L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
         return mean, var
 
