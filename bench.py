@@ -120,13 +120,13 @@ def cpu_predict_rate(X, z, sample, repeats=1):
     return sample / best, best, t_factor
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of predict_var_kernel, from the committed
+def ncu_traffic_bytes(kernel='predict_var_kernel'):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture of this kernel (profiles/, newest round first); None if no capture is present."""
     import csv
     import glob
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
-    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*ncu_full_predict_var_kernel.csv')), reverse=True):
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*ncu_full_%s.csv' % kernel)), reverse=True):
         try:
             tot = 0.0
             for r in csv.reader(open(path)):
@@ -186,6 +186,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--queries', type=int, default=M_QUERIES, help='queries per GPU per step (default 2^20)')
     ap.add_argument('--no-extras', action='store_true', help='skip cpu baseline / reward-path extras (profiling runs)')
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'i8x6'],
+                    help="arithmetic of the timed path: 'fp64' = FP64 DMMA (default, the headline); 'i8x6' = FP64-grade "
+                         "sliced-INT8 tcgen05 path (same 1e-6 parity tolerance, ~3.8x the rate)")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -221,6 +224,8 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    model.predict_precision = args.precision        # also steers predict_value (the e2e leg)
 
     def step():
         return model.predict_device(xq)
@@ -272,15 +277,23 @@ def main():
     # ---- roofline of the dominant kernel (fused DMMA variance kernel)
     kernel_ms = tot_ms.value / max(1, launches.value)
     chunk = min(M, 32768)
-    flops_launch = flops_per_query(N_OBS, 'sym') * chunk
+    if args.precision == 'fp64':
+        flops_launch = flops_per_query(N_OBS, 'sym') * chunk
+        a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
+        b = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
+        mm = torch.matmul
+    else:                                           # 21 slice-pair products x 128 x 64 tiles x k-blocks of 64, lower-triangular
+        T64 = (N_OBS + 63) // 64
+        flops_launch = 21 * 2.0 * 128 * 64 * 64 * (T64 * (T64 + 1) / 2) * (chunk / 128.0)
+        a = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
+        b = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
+        mm = torch._int_mm
     achieved = flops_launch / (kernel_ms / 1e3) / 1e12 if kernel_ms > 0 else None
-    a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
-    b = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
     best = None
     for i in range(6):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        torch.matmul(a, b)
+        mm(a, b)
         s1.record()
         torch.cuda.synchronize()
         if i:
@@ -290,26 +303,31 @@ def main():
     dgemm_tflops = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
-    traffic, traffic_src = ncu_traffic_bytes()
+    traffic, traffic_src = ncu_traffic_bytes('predict_var_kernel' if args.precision == 'fp64' else 'predict_var_i8_kernel')
     if chunk != 32768:
         traffic, traffic_src = None, None          # the capture is of a full 32768-query launch
+    fp64 = args.precision == 'fp64' 
     roofline = {
-        'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tflops, 'unit': 'TFLOP/s',
+        'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tflops, 'unit': 'TFLOP/s' if fp64 else 'TOP/s',
         'frac': (achieved / dgemm_tflops) if achieved else None, 'traffic': traffic, 'traffic_source': traffic_src,
-        'kernel': 'predict_var_kernel (FP64 DMMA.8x8x4, symmetric-half form: executed flops only)',
+        'kernel': 'predict_var_kernel (FP64 DMMA.8x8x4, symmetric-half form: executed flops only)' if fp64 else
+                  'predict_var_i8_kernel<6 slices, 128x64> (tcgen05.mma kind::i8, 21 slice-pair products: executed INT8 ops only)',
         'kernel_ms': kernel_ms, 'kernel_launches_timed': int(launches.value), 'kernel_share_of_step': tot_ms.value / ms_total,
         'flops_per_launch': flops_launch,
-        'peak_source': 'FP64 DGEMM 8192^3 via torch.matmul (cuBLAS), best of 5, CUDA events, measured in this run; '
-                       'MEASURED_PEAKS.json has no FP64 figure (hbm_gbs=%s of measured)' % hbm,
+        'peak_source': ('FP64 DGEMM 8192^3 via torch.matmul (cuBLAS)' if fp64 else 'INT8 GEMM 8192^3 via torch._int_mm (cuBLAS)') +
+                       ', best of 5, CUDA events, measured in this run; MEASURED_PEAKS.json has no %s figure '
+                       '(hbm_gbs=%s of measured)' % ('FP64' if fp64 else 'INT8', hbm),
     }
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64' if fp64 else 'i8 (6 x 7-bit slices per f64 operand, exact i32 accumulation, f64 combine; f64 mean)',
         'data': 'synthetic',
-        'config': {'workload': 'gp_predict N=4096 obs x M=2^20 queries per GPU (BASELINE config 3 at N=4k), FP64, 10x10 '
-                               'world RBF l=1 var=100 noise=0.5', 'n_obs': N_OBS, 'queries_per_gpu': M,
-                   'variance_form': 'W^-1 symmetric-half (IPP_VAR_WINV_SYM)',
+        'config': {'workload': 'gp_predict N=4096 obs x M=2^20 queries per GPU (BASELINE config 3 at N=4k), %s, 10x10 '
+                               'world RBF l=1 var=100 noise=0.5' % ('FP64' if fp64 else 'FP64-grade sliced INT8'),
+                   'n_obs': N_OBS, 'queries_per_gpu': M,
+                   'variance_form': 'W^-1 symmetric-half (IPP_VAR_WINV_SYM)' if fp64 else 'Cholesky form |L^-1 k|^2 (i8x6)',
                    'l2': 'no flush: per step the kernels stream the 134 MB W^-1 and a 1.07 GB cross-covariance '
                          'scratch, both larger than the 126 MB L2',
                    'parallelism': 'queries sharded, belief replicated (dp%d)' % world},
@@ -319,6 +337,8 @@ def main():
         'roofline': roofline,
     }
 
+    model.predict_precision = 'fp64'                # the extras below name their precision explicitly
+    ms_fp64 = ms_step if fp64 else None
     if not args.no_extras and world == 1:
         # CPU baseline on a bounded sample (about 10-30 s of host work), rank 0 only
         sample = 16384
@@ -472,7 +492,7 @@ def main():
             kern_tf = flops32 / (k_ms.value / max(1, k_n.value) / 1e3) / 1e12
             err = (var32 - var64).abs()
             extras['tf32x3_N4096'] = {
-                'queries_per_s': M / (ms32 / 1e3), 'ms_per_step': ms32, 'speedup_vs_fp64_mode': ms_step / ms32,
+                'queries_per_s': M / (ms32 / 1e3), 'ms_per_step': ms32, 'speedup_vs_fp64_mode': (ms_fp64 / ms32) if ms_fp64 else None,
                 'acc_kblocks': int(model.tf32_acc_kblocks),
                 'kernel': 'predict_var_tf32_kernel (tcgen05.mma kind::tf32, TMA, TMEM; 3 products per MAC executed)',
                 'kernel_ms': k_ms.value / max(1, k_n.value), 'kernel_tflops_executed': kern_tf,
@@ -521,7 +541,7 @@ def main():
                 kern_tops = ops8 / (k_ms.value / max(1, k_n.value) / 1e3) / 1e12
                 err = (var8 - var64).abs()
                 extras[prec + '_N4096'] = {
-                    'queries_per_s': M / (ms8 / 1e3), 'ms_per_step': ms8, 'speedup_vs_fp64_mode': ms_step / ms8,
+                    'queries_per_s': M / (ms8 / 1e3), 'ms_per_step': ms8, 'speedup_vs_fp64_mode': (ms_fp64 / ms8) if ms_fp64 else None,
                     'kernel': 'predict_var_i8_kernel<%d slices, 128x%d tiles> (tcgen05.mma kind::i8, 3-D TMA, TMEM; %d slice-pair '
                               'products per MAC executed)' % (ns, bn, n_prod),
                     'kernel_ms': k_ms.value / max(1, k_n.value), 'kernel_int8_tops_executed': kern_tops,
