@@ -173,35 +173,60 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
 // ---- base posterior over the rollout's M <= 128 points.  A 128-row DMMA tile would be > 80 % padding here and only
 // N / 128 CTAs would stream the N x N operand (measured 130 us per GEMM at N = 900), so the two contractions are
 // bandwidth-shaped SIMT kernels over all SMs instead:
-//   T1[m][n] = sum_j W[n][j] Kxt[m][j]          one warp per row n of W^-1 (the only N^2 traffic), <= 32 m per pass
+//   T1[m][n] = sum_j W[n][j] Kxt[m][j]          two rows n of W^-1 per warp (the only N^2 traffic), <= 32 m per pass
 //   C0[m][m'] = Kqq[m][m'] - sum_n T1[m][n] Kxt[m'][n]   one warp per (m, m' <= m), mirrored
+constexpr int TW_ROWS_PER_WARP = 2, TW_JC = 128;
 __global__ void __launch_bounds__(256) rollout_tw_kernel(const double* __restrict__ W, int64_t ldw, int N,
                                                          const double* __restrict__ Kxt, int64_t ldk, int M,
                                                          double* __restrict__ T1) {
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const double* row = W + (int64_t)n * ldw;
+    // Block = 16 rows of W^-1 (2 per warp); the cross-covariance rows of <= 32 points are staged in shared memory in
+    // j-chunks and shared by all 16 rows (at N = 4096 the M x N panel does not fit L1: the untiled version re-streamed
+    // it from L2 once per row -- 2.7 GB per call, 1.8 ms; this one reads it once per block).
+    __shared__ double sK[32][TW_JC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = (blockIdx.x * 8 + warp) * TW_ROWS_PER_WARP;
     for (int m0 = 0; m0 < M; m0 += 32) {
-        double acc[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
         const int mm = (M - m0) < 32 ? (M - m0) : 32;
-        for (int j = lane; j < N; j += 32) {
-            const double w = row[j];
+        double acc[TW_ROWS_PER_WARP][32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i < mm) acc[i] = fma(w, Kxt[(int64_t)(m0 + i) * ldk + j], acc[i]);
-        }
+        for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (i < mm) {
-                double t = acc[i];
+            for (int i = 0; i < 32; ++i) acc[r][i] = 0.0;
+        for (int j0 = 0; j0 < N; j0 += TW_JC) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < mm * TW_JC; idx += 256) {
+                const int m = idx / TW_JC, jj = idx % TW_JC;
+                sK[m][jj] = (j0 + jj < N) ? Kxt[(int64_t)(m0 + m) * ldk + j0 + jj] : 0.0;
+            }
+            __syncthreads();
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                if (lane == 0) T1[(int64_t)(m0 + i) * ldk + n] = t;
+            for (int c = 0; c < TW_JC / 32; ++c) {
+                const int jj = lane + 32 * c, j = j0 + jj;
+                double w[TW_ROWS_PER_WARP];
+#pragma unroll
+                for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
+                    w[r] = (j < N && n0 + r < N) ? W[(int64_t)(n0 + r) * ldw + j] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < mm) {
+                        const double kv = sK[i][jj];
+#pragma unroll
+                        for (int r = 0; r < TW_ROWS_PER_WARP; ++r) acc[r][i] = fma(w[r], kv, acc[r][i]);
+                    }
+                }
             }
         }
+#pragma unroll
+        for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i < mm) {
+                    double t = acc[r][i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0 && n0 + r < N) T1[(int64_t)(m0 + i) * ldk + n0 + r] = t;
+                }
+            }
     }
 }
 
@@ -279,7 +304,7 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
         double* Kxt = sub;
         double* T1 = sub + (int64_t)M * ldk;
         IPP_TRY(launch_rbf_queries(*kern, X, N, alpha, pts, M, Kxt, ldk, mean0, stream));
-        rollout_tw_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(winv, ldw, (int)N, Kxt, ldk, M, T1);
+        rollout_tw_kernel<<<(unsigned)((N + 15) / 16), 256, 0, stream>>>(winv, ldw, (int)N, Kxt, ldk, M, T1);
         IPP_LAUNCH_CHECK();
         const int pairs = M * (M + 1) / 2;
         rollout_cov_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
