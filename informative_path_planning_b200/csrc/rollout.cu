@@ -175,46 +175,107 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
 // bandwidth-shaped SIMT kernels over all SMs instead:
 //   T1[m][n] = sum_j W[n][j] Kxt[m][j]          two rows n of W^-1 per warp (the only N^2 traffic), <= 32 m per pass
 //   C0[m][m'] = Kqq[m][m'] - sum_n T1[m][n] Kxt[m'][n]   one warp per (m, m' <= m), mirrored
-constexpr int TW_ROWS_PER_WARP = 2, TW_JC = 128;
-__global__ void __launch_bounds__(256) rollout_tw_kernel(const double* __restrict__ W, int64_t ldw, int N,
-                                                         const double* __restrict__ Kxt, int64_t ldk, int M,
-                                                         double* __restrict__ T1) {
+// Cross-covariance rows of the rollout's M <= 128 points: thread = observation n (coalesced stores along n), loop over
+// the points; the general query kernel maps 4 queries to a warp and would keep 5 warps busy for M = 20.
+template <int D>
+__global__ void __launch_bounds__(256) rollout_rbf_kernel(RbfDev k, const double* __restrict__ X, int N,
+                                                          const double* __restrict__ pts, int M,
+                                                          double* __restrict__ Kxt, int64_t ldk) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double x[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = X[(int64_t)n * D + d];
+    for (int m = 0; m < M; ++m) {
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) q[d] = pts[m * D + d];
+        Kxt[(int64_t)m * ldk + n] = rbf_eval<D>(k, q, x);
+    }
+}
+
+// mean0[m] = sum_n Kxt[m][n] alpha[n]: one warp per point, fixed summation order
+__global__ void __launch_bounds__(256) rollout_mean_kernel(const double* __restrict__ Kxt, int64_t ldk, int N, int M,
+                                                           const double* __restrict__ alpha, double* __restrict__ mean0) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    double s = 0.0;
+    for (int n = lane; n < N; n += 32) s = fma(Kxt[(int64_t)m * ldk + n], alpha[n], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) mean0[m] = s;
+}
+
+constexpr int TW_ROWS_PER_WARP = 2, TW_JC = 256, TW_WARPS = 8;
+constexpr int TW_SMEM = 2 * 32 * TW_JC * 8;                 // two tile buffers of [32 points][256 j] doubles = 128 KB
+
+__device__ __forceinline__ void tw_cp16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+
+__global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const double* __restrict__ W, int64_t ldw, int N,
+                                                                      const double* __restrict__ Kxt, int64_t ldk, int M,
+                                                                      double* __restrict__ T1) {
     // Block = 16 rows of W^-1 (2 per warp); the cross-covariance rows of <= 32 points are staged in shared memory in
-    // j-chunks and shared by all 16 rows (at N = 4096 the M x N panel does not fit L1: the untiled version re-streamed
-    // it from L2 once per row -- 2.7 GB per call, 1.8 ms; this one reads it once per block).
-    __shared__ double sK[32][TW_JC];
+    // j-chunks shared by all 16 rows (at N = 4096 the M x N panel does not fit L1: the untiled version re-streamed it
+    // from L2 once per row -- 2.7 GB per call, 1.8 ms).  The chunks arrive by cp.async, double buffered: a plain
+    // load-store loop serialised ~20 L2 latencies per chunk and kept the kernel at 0.45 ms.
+    extern __shared__ __align__(16) double tw_smem[];
+    const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(tw_smem));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = (blockIdx.x * 8 + warp) * TW_ROWS_PER_WARP;
+    const int n0 = (blockIdx.x * TW_WARPS + warp) * TW_ROWS_PER_WARP;
     for (int m0 = 0; m0 < M; m0 += 32) {
         const int mm = (M - m0) < 32 ? (M - m0) : 32;
+        auto load_tile = [&](int buf, int j0) {
+            for (int idx = threadIdx.x; idx < mm * (TW_JC / 2); idx += 32 * TW_WARPS) {
+                const int m = idx / (TW_JC / 2), jj = 2 * (idx % (TW_JC / 2));
+                const int left = N - (j0 + jj);
+                const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);             // zero-fill beyond the N valid columns
+                const double* src = Kxt + (int64_t)(m0 + m) * ldk + (bytes ? j0 + jj : 0);
+                tw_cp16(s_base + (uint32_t)(((buf * 32 + m) * TW_JC + jj) * 8), src, bytes);
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
         double acc[TW_ROWS_PER_WARP][32];
 #pragma unroll
         for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[r][i] = 0.0;
+        int buf = 0;
+        load_tile(0, 0);
         for (int j0 = 0; j0 < N; j0 += TW_JC) {
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < mm * TW_JC; idx += 256) {
-                const int m = idx / TW_JC, jj = idx % TW_JC;
-                sK[m][jj] = (j0 + jj < N) ? Kxt[(int64_t)(m0 + m) * ldk + j0 + jj] : 0.0;
-            }
-            __syncthreads();
+            // this chunk's rows of W^-1 first (independent of the tile), then wait for the tile
+            double w[TW_JC / 32][TW_ROWS_PER_WARP];
 #pragma unroll
             for (int c = 0; c < TW_JC / 32; ++c) {
-                const int jj = lane + 32 * c, j = j0 + jj;
-                double w[TW_ROWS_PER_WARP];
+                const int j = j0 + lane + 32 * c;
 #pragma unroll
                 for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
-                    w[r] = (j < N && n0 + r < N) ? W[(int64_t)(n0 + r) * ldw + j] : 0.0;
+                    w[c][r] = (j < N && n0 + r < N) ? W[(int64_t)(n0 + r) * ldw + j] : 0.0;
+            }
+            if (j0 + TW_JC < N) {
+                load_tile(buf ^ 1, j0 + TW_JC);
+                asm volatile("cp.async.wait_group 1;\n" ::);
+            } else {
+                asm volatile("cp.async.wait_group 0;\n" ::);
+            }
+            __syncthreads();
+            const double* sK = tw_smem + (size_t)buf * 32 * TW_JC;
+#pragma unroll
+            for (int c = 0; c < TW_JC / 32; ++c) {
+                const int jj = lane + 32 * c;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     if (i < mm) {
-                        const double kv = sK[i][jj];
+                        const double kv = sK[i * TW_JC + jj];
 #pragma unroll
-                        for (int r = 0; r < TW_ROWS_PER_WARP; ++r) acc[r][i] = fma(w[r], kv, acc[r][i]);
+                        for (int r = 0; r < TW_ROWS_PER_WARP; ++r) acc[r][i] = fma(w[c][r], kv, acc[r][i]);
                     }
                 }
             }
+            __syncthreads();
+            buf ^= 1;
         }
 #pragma unroll
         for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
@@ -227,6 +288,7 @@ __global__ void __launch_bounds__(256) rollout_tw_kernel(const double* __restric
                     if (lane == 0 && n0 + r < N) T1[(int64_t)(m0 + i) * ldk + n0 + r] = t;
                 }
             }
+        __syncthreads();
     }
 }
 
@@ -303,8 +365,20 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
         const int64_t ldk = round_up(N, 16);
         double* Kxt = sub;
         double* T1 = sub + (int64_t)M * ldk;
-        IPP_TRY(launch_rbf_queries(*kern, X, N, alpha, pts, M, Kxt, ldk, mean0, stream));
-        rollout_tw_kernel<<<(unsigned)((N + 15) / 16), 256, 0, stream>>>(winv, ldw, (int)N, Kxt, ldk, M, T1);
+        const RbfDev kd = to_dev(*kern);
+        if (kern->dim == 2) rollout_rbf_kernel<2><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
+        else rollout_rbf_kernel<3><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
+        IPP_LAUNCH_CHECK();
+        rollout_mean_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(Kxt, ldk, (int)N, M, alpha, mean0);
+        IPP_LAUNCH_CHECK();
+        static bool tw_configured = false;
+        if (!tw_configured) {
+            IPP_CUDA(cudaFuncSetAttribute(rollout_tw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+            tw_configured = true;
+        }
+        constexpr int rows_per_block = TW_WARPS * TW_ROWS_PER_WARP;
+        rollout_tw_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 32 * TW_WARPS, TW_SMEM, stream>>>(
+            winv, ldw, (int)N, Kxt, ldk, M, T1);
         IPP_LAUNCH_CHECK();
         const int pairs = M * (M + 1) / 2;
         rollout_cov_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
