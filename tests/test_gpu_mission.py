@@ -157,3 +157,29 @@ def test_nonmyopic_mission_same_actions_every_step(pkg, f_rew, tree_type):
     q = rng.uniform(0, 10, (200, 2))
     np.testing.assert_allclose(d.predict_value(q)[0], o.predict_value(q)[0], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(d.predict_value(q)[1], o.predict_value(q)[1], rtol=1e-6)
+
+
+def test_environment_world_matches_oracle_built_world(pkg):
+    """envmodel_library.Environment (reference :27-260): the same seed gives the same Gaussian world whether the GP
+    underneath is the device GPModel or the oracle's GPy restatement (prior draw at one grid point, then one joint
+    posterior sample of the remaining NUM_PTS^2 - 1 points through np.random.multivariate_normal), the maximum sits
+    inside the 5 % border, and sample_value adds ONE scalar noise draw to the whole batch (Q9)."""
+    from informative_path_planning_b200.envmodel_library import Environment
+    from oracle.gpmodel_oracle import GPModelOracle
+    ranges = (0., 10., 0., 10.)
+    dev = Environment(ranges, 12, 100.0, 1.0, noise=0.5, seed=3, dim=2)
+    ora = Environment(ranges, 12, 100.0, 1.0, noise=0.5, seed=3, dim=2, gp_cls=GPModelOracle)
+    assert dev.GP.xvals.shape == (144, 2) and dev.GP.zvals.shape == (144, 1)
+    np.testing.assert_allclose(dev.GP.xvals, ora.GP.xvals)
+    # the joint draw goes through an SVD of the 143 x 143 posterior covariance: continuous, not bit-stable
+    np.testing.assert_allclose(dev.GP.zvals, ora.GP.zvals, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(dev.max_loc, ora.max_loc)
+    assert 0.5 <= dev.max_loc[0] <= 9.5 and 0.5 <= dev.max_loc[1] <= 9.5
+    q = np.random.default_rng(0).uniform(0, 10, (7, 2))
+    np.random.seed(9)
+    a = dev.sample_value(q)
+    np.random.seed(9)
+    b = ora.sample_value(q)
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-4)
+    mean = dev.GP.predict_value(q, include_noise=False)[0]
+    assert np.ptp(a - mean) < 1e-9                                   # one scalar noise value for all seven points
