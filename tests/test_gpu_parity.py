@@ -786,3 +786,24 @@ def test_predict_i8x5_mode(pkg, N, M):
     np.testing.assert_allclose(var5, var64, rtol=2e-5)
     m.predict_precision = 'i8x6'                      # both slice counts cached side by side
     np.testing.assert_allclose(m.predict_value(q)[1], var64, rtol=2e-7)
+
+
+@pytest.mark.parametrize('variance,lengthscale,noise', [(1.0, 0.5, 0.01), (1000.0, 2.0, 5.0), (7.3, 1.3, 0.2), (100.0, 1.0, 0.5)])
+def test_precision_modes_across_hyperparameters(pkg, variance, lengthscale, noise):
+    """The fixed-point scales of the INT8 modes (power of two >= variance, power of two >= max |L^-1|) and the TF32
+    split must follow the kernel hyper-parameters: every mode against the oracle on non-default worlds."""
+    _, gpo, _ = _oracle()
+    rng = np.random.default_rng(int(variance * 10) + 3)
+    N, M = 500, 700
+    X = rng.uniform(0, 10, (N, 2))
+    z = np.sqrt(variance) * np.sin(0.9 * X[:, :1]) * np.cos(0.7 * X[:, 1:]) + rng.normal(0, np.sqrt(noise), (N, 1))
+    d = pkg.OnlineGPModel(RANGES, lengthscale, variance, noise=noise)
+    o = gpo.OnlineGPModelOracle(RANGES, lengthscale, variance, noise=noise)
+    d.add_data(X, z); o.add_data(X, z)
+    q = rng.uniform(0, 10, (M, 2))
+    mu_o, var_o = o.predict_value(q)
+    for prec, tol in (('fp64', RTOL), ('i8x6', RTOL), ('i8x5', 1e-4), ('tf32x3', 5e-3)):
+        d.predict_precision = prec
+        mu, var = d.predict_value(q)
+        np.testing.assert_allclose(mu, mu_o, rtol=RTOL, atol=1e-7 * np.sqrt(variance), err_msg=prec)
+        np.testing.assert_allclose(var, var_o, rtol=tol, err_msg=prec)
