@@ -334,16 +334,69 @@ def _rff_theta(Z, zvals, noise_var, eps, nFeatures):
     return mu + np.dot(np.linalg.cholesky(Sigma), eps)
 
 
-def rff_features(W, b, X_d, variance, nFeatures):
-    """Z = sqrt(2 v / F) cos(W X^T + b) on the device (reference aq_library.py:171) -> numpy (F, N)."""
+def rff_features_device(W, b, X_d, variance, nFeatures):
+    """Z = sqrt(2 v / F) cos(W X^T + b) on the device (reference aq_library.py:171) -> CUDA tensor (F, ld) with ld even."""
     F, D = W.shape
     N = X_d.shape[0]
     ldz = L.round_up(N, 2)
-    Z = torch.empty((F, ldz), dtype=torch.float64, device=X_d.device)
+    Z = torch.zeros((F, ldz), dtype=torch.float64, device=X_d.device)
     W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))     # keep both alive until the launch is enqueued
     L.check(L.lib.ipp_rff_features(L.ptr(W_d), L.ptr(b_d), F, D, L.ptr(X_d), N,
                                    float(np.sqrt(2 * variance / nFeatures)), L.ptr(Z), ldz, L.stream_ptr()))
-    return np.ascontiguousarray(Z[:, :N].cpu().numpy())
+    return Z
+
+
+def rff_features(W, b, X_d, variance, nFeatures):
+    """rff_features_device -> numpy (F, N)."""
+    return np.ascontiguousarray(rff_features_device(W, b, X_d, variance, nFeatures)[:, :X_d.shape[0]].cpu().numpy())
+
+
+def _gemm_nt(A, B, M, N, K, alpha=1.0, C=None, beta=0.0):
+    """C[M][ldc] = alpha A[M][K] B[N][K]^T + beta C through the library's FP64 DMMA GEMM (row-major CUDA tensors)."""
+    ldc = L.round_up(N, 2)
+    if C is None:
+        C = torch.empty((M, ldc), dtype=torch.float64, device=A.device)
+    L.check(L.lib.ipp_dgemm_nt(M, N, K, float(alpha), L.ptr(A), A.stride(0), L.ptr(B), B.stride(0), float(beta),
+                               L.ptr(C), C.stride(0), None, 0, L.stream_ptr()))
+    return C
+
+
+def rff_theta_batch_device(Z_d, N, zvals, noise_var, eps):
+    """All S posterior weight draws of the N >= F branch (reference aq_library.py:195-200) in one device pass:
+    Sigma = (Z Z^T / s2 + I)^-1, m = Sigma Z z / s2, Theta[:, s] = m + chol(Sigma) eps[:, s].  The reference redoes the
+    F x F inverse and Cholesky for every sample although only eps changes; here they are shared (FP64 DMMA GEMMs,
+    ipp_pdinv, ipp_potrf_lower).  eps: (F, S) numpy.  Returns Theta as a (F, S) numpy array."""
+    F, S = eps.shape
+    dev = Z_d.device
+    ld = L.round_up(F, 16)
+    A = torch.zeros((F, ld), dtype=torch.float64, device=dev)
+    _gemm_nt(Z_d, Z_d, F, F, N, alpha=1.0 / noise_var, C=A)
+    A.diagonal().add_(1.0)                                     # + I (plumbing: F adds)
+    Sigma = torch.zeros((F, ld), dtype=torch.float64, device=dev)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = L.workspace(L.lib.ipp_pdinv_workspace(F), slot='pdinv')
+    L.check(L.lib.ipp_pdinv(L.ptr(A), F, ld, L.ptr(Sigma), None, ld, L.ptr(scal), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('Z Z^T / noise + I is not positive definite')
+    zrow = torch.zeros((1, Z_d.stride(0)), dtype=torch.float64, device=dev)
+    zrow[0, :N] = L.to_device(np.asarray(zvals, dtype=float).reshape(-1))
+    Zz = _gemm_nt(Z_d, zrow, F, 1, N)                           # (F, 2): column 0 = Z z
+    zz_row = torch.zeros((1, ld), dtype=torch.float64, device=dev)
+    zz_row[0, :F] = Zz[:, 0]
+    m = _gemm_nt(Sigma, zz_row, F, 1, F, alpha=1.0 / noise_var)  # (F, 2): column 0 = Sigma Z z / s2
+    Cf = Sigma.clone()
+    work = L.workspace(L.lib.ipp_potrf_workspace(F), slot='potrf')
+    L.check(L.lib.ipp_potrf_lower(L.ptr(Cf), F, ld, L.ptr(scal), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('posterior weight covariance is not positive definite')
+    Cf[:, :F].tril_()                                           # entries above the diagonal are factorisation scratch
+    Et = torch.zeros((S, ld), dtype=torch.float64, device=dev)
+    Et[:, :F] = L.to_device(np.ascontiguousarray(eps.T))
+    Theta = torch.zeros((F, L.round_up(S, 2)), dtype=torch.float64, device=dev)
+    Theta[:, :S] = m[:, :1]                                     # broadcast m, then += chol(Sigma) eps
+    _gemm_nt(Cf, Et, F, S, F, C=Theta, beta=1.0)
+    return Theta[:, :S].cpu().numpy()
 
 
 def global_maximization(target, target_vector_n, target_grad, target_vector_gradient_n, ranges, guesses, visualize,
@@ -446,9 +499,15 @@ def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
     ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
     W = rng.normal(0.0, np.sqrt(1. / ls), size=(nFeatures, d))
     b = 2 * np.pi * rng.uniform(0.0, 1.0, size=(nFeatures, 1))
-    Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
-    Theta = np.hstack([_rff_theta(Z, robot_model.zvals, robot_model.noise, rng.normal(size=(nFeatures, 1)), nFeatures)
-                       for _ in range(nK)])                              # (F, nK)
+    N = robot_model.xvals.shape[0]
+    eps = np.hstack([rng.normal(size=(nFeatures, 1)) for _ in range(nK)])      # same draws, same order as one-by-one
+    if N >= nFeatures:
+        Z_d = rff_features_device(W, b, robot_model._X_d, variance, nFeatures)
+        Theta = rff_theta_batch_device(Z_d, N, robot_model.zvals, float(robot_model.noise), eps)
+    else:
+        Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
+        Theta = np.hstack([_rff_theta(Z, robot_model.zvals, robot_model.noise, eps[:, s:s + 1], nFeatures)
+                           for s in range(nK)])                                # (F, nK)
     grid_d = grid if isinstance(grid, torch.Tensor) else L.to_device(grid)
     mx, am = rff_eval_argmax_shared(W, b, Theta, variance, grid_d)
     locs = grid_d[am].cpu().numpy()

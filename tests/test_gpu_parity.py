@@ -807,3 +807,25 @@ def test_precision_modes_across_hyperparameters(pkg, variance, lengthscale, nois
         mu, var = d.predict_value(q)
         np.testing.assert_allclose(mu, mu_o, rtol=RTOL, atol=1e-7 * np.sqrt(variance), err_msg=prec)
         np.testing.assert_allclose(var, var_o, rtol=tol, err_msg=prec)
+
+
+def test_rff_theta_batch_on_device_matches_reference_formula(pkg):
+    """Posterior weight draws of the N >= F branch (aq_library.py:195-200) for all samples in one device pass (shared
+    F x F inverse + Cholesky) against the reference's per-sample numpy formula, and the full shared-feature sampler."""
+    aq, L = pkg.aq_library, pkg._lib
+    rng = np.random.default_rng(17)
+    N, F, S = 700, 150, 9
+    X, z = world(rng, N, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    W = rng.normal(size=(F, 2)); b = 2 * np.pi * rng.uniform(size=(F, 1))
+    eps = rng.normal(size=(F, S))
+    Z_d = aq.rff_features_device(W, b, m._X_d, 100.0, F)
+    got = aq.rff_theta_batch_device(Z_d, N, z, 0.5, eps)
+    Z = aq.rff_features(W, b, m._X_d, 100.0, F)
+    want = np.hstack([aq._rff_theta(Z, z, 0.5, eps[:, s:s + 1], F) for s in range(S)])
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
+    grid = rng.uniform(1, 9, (5000, 2))
+    mx, locs, _ = aq.sample_max_vals_shared(m, grid, nK=6, nFeatures=F, rng=np.random.default_rng(5))
+    assert mx.shape == (6, 1) and locs.shape == (6, 2) and np.all(np.isfinite(mx))
+    assert np.all(mx.ravel() > z.max() - 15.0)                 # sampled maxima sit near / above the observed maximum
