@@ -222,7 +222,8 @@ int ipp_info_gain_paths(const ipp_rbf* kern_v2 /* RBF with variance = v^2 */, co
  *      C library calls + trimming loop of Dubins_Path_Generator.buffered_paths (paths_library.py:147-175),
  *      obstacle-free world.  All pointers are host memory.  pose[3], goals[G][3], extent[4];
  *      samp[G][max_samp][3] / samp_count[G]: kept sample points (0 = path dropped);
- *      dense[G][max_dense][3] / dense_count[G]: dense path up to the last kept point. */
+ *      dense[G][max_dense][3] / dense_count[G]: dense path up to the last kept point; dense may be NULL (the tree search
+ *      only needs the kept samples and the end pose: interior paths then evaluate one configuration in keep_every). */
 int ipp_dubins_path_set(const double* pose, const double* goals, int G, double rho, double dense_step,
                         int keep_every, const double* extent, double border,
                         double* samp, int* samp_count, int max_samp,

@@ -89,8 +89,14 @@ __host__ __device__ int dubins_one(const double* pose, const double* q1, double 
     // dense sweep: cut at the first configuration outside the open extent; every keep_every-th one is a sample
     // candidate, trimmed by the reference's loop (python: `ttemp = ttemp[0:m-1]`, including its negative-index quirk)
     int nd = 0, orig = 0, cur = 0;
-    bool trimmed_any = false;
-    for (int si = 0; nd < max_dense; ++si) {
+    // When the dense configurations are not asked for (dg == NULL) and the whole curve provably stays inside the extent
+    // (start pose farther from every wall than the path is long), only every keep_every-th configuration -- the sample
+    // candidates -- needs evaluating: each one is a closed form of its own arc length, so the values are identical.
+    const double margin = total + 1e-9;
+    const bool interior = pose[0] - extent[0] > margin && extent[1] - pose[0] > margin &&
+                          pose[1] - extent[2] > margin && extent[3] - pose[1] > margin;
+    const int stride = (dg == nullptr && interior) ? keep_every : 1;
+    for (int si = 0; nd < max_dense; si += stride, nd += stride - 1) {
         const double s = si * dense_step;
         if (!(s < total)) break;
         double rem = s / rho;
@@ -104,13 +110,12 @@ __host__ __device__ int dubins_one(const double* pose, const double* q1, double 
         if (!(cx > extent[0] && cx < extent[1] && cy > extent[2] && cy < extent[3])) break;
         const double cth = mod2pi(th);
         if (dg) { dg[3 * nd] = cx; dg[3 * nd + 1] = cy; dg[3 * nd + 2] = cth; }
-        if (nd % keep_every == 0 && orig < max_samp) {
+        if (si % keep_every == 0 && orig < max_samp) {
             sg[3 * orig] = cx; sg[3 * orig + 1] = cy; sg[3 * orig + 2] = cth;
             ++orig;
         }
         ++nd;
     }
-    (void)trimmed_any;
     cur = orig;
     for (int m = 0; m < orig; ++m) {
         const double* c = sg + 3 * m;
@@ -162,13 +167,13 @@ extern "C" int ipp_dubins_path_set(const double* pose, const double* goals, int 
                                    int keep_every, const double* extent, double border,
                                    double* samp, int* samp_count, int max_samp,
                                    double* dense, int* dense_count, int max_dense) {
-    IPP_CHECK_ARG(pose && goals && extent && samp && samp_count && dense && dense_count, "null pointer");
+    IPP_CHECK_ARG(pose && goals && extent && samp && samp_count && dense_count, "null pointer");
     IPP_CHECK_ARG(G >= 0 && rho > 0 && dense_step > 0 && keep_every >= 1 && max_samp >= 2 && max_dense >= 2, "bad argument");
     for (int gi = 0; gi < G; ++gi) {
         int dn = 0;
         samp_count[gi] = dubins_one(pose, goals + 3 * gi, rho, dense_step, keep_every, extent, border,
-                                    samp + (size_t)gi * max_samp * 3, max_samp, dense + (size_t)gi * max_dense * 3,
-                                    max_dense, &dn, nullptr);
+                                    samp + (size_t)gi * max_samp * 3, max_samp,
+                                    dense ? dense + (size_t)gi * max_dense * 3 : nullptr, max_dense, &dn, nullptr);
         dense_count[gi] = dn;
     }
     return IPP_OK;

@@ -28,28 +28,33 @@ class FreeWorld(object):
 
 
 class LazyPath(object):
-    """A dense path kept as an (n, 3) array and turned into the reference's tuples on access.  The tree search
-    only ever looks at dense_path[-1] (the pose of the next belief node) for all but the chosen action, so
-    building ~100 tuples per candidate path per expanded node is wasted host time."""
+    """A dense path that is only materialised on demand.  The tree search only ever looks at dense_path[-1] (the pose
+    of the next belief node) for all but the chosen action, so the ~30-100 dense configurations per candidate path per
+    expanded node are neither computed nor turned into tuples unless somebody asks: `end` is the last configuration,
+    `factory()` produces the whole list of (x, y, heading) tuples."""
 
-    __slots__ = ('arr',)
+    __slots__ = ('end', 'factory', '_items')
 
-    def __init__(self, arr):
-        self.arr = arr
+    def __init__(self, end, factory):
+        self.end = end
+        self.factory = factory
+        self._items = None
+
+    def tolist(self):
+        if self._items is None:
+            self._items = self.factory()
+        return self._items
 
     def __len__(self):
-        return self.arr.shape[0]
+        return len(self.tolist())
 
     def __getitem__(self, i):
-        if isinstance(i, slice):
-            return [tuple(c) for c in self.arr[i].tolist()]
-        return tuple(self.arr[i].tolist())
+        if i == -1:
+            return self.end
+        return self.tolist()[i]
 
     def __iter__(self):
         return iter(self.tolist())
-
-    def tolist(self):
-        return [tuple(c) for c in self.arr.tolist()]
 
 
 class Path_Generator(object):
@@ -268,17 +273,42 @@ class Dubins_Path_Generator(Path_Generator):
         nb['pose'][:] = self.cp
         P = nb['ptr']
         L.check(L.lib.ipp_dubins_path_set(P['pose'], P['goals'], G, float(self.tr), float(self.ss / 10), 10, P['ext'],
-                                          float(3 * self.tr), P['samp'], P['ns'], nb['max_samp'], P['dense'], P['nd'],
-                                          nb['max_dense']))
-        ns, nd = nb['ns'][:G].tolist(), nb['nd'][:G].tolist()
+                                          float(3 * self.tr), P['samp'], P['ns'], nb['max_samp'],
+                                          None if lazy else P['dense'], P['nd'], nb['max_dense']))
+        ns = nb['ns'][:G].tolist()
         samp = nb['samp'].tolist()
-        dense = nb['dense']
         sampling_path, true_path = {}, {}
+        if lazy:
+            pose, goals = self.cp, list(self.goals)
+            for i in range(G):
+                if ns[i] >= 2:
+                    pts = [tuple(c) for c in samp[i][:ns[i]]]
+                    sampling_path[i] = pts
+                    true_path[i] = LazyPath(pts[-1], lambda pose=pose, goal=goals[i]: self._dense_for(pose, goal))
+            return sampling_path, true_path
+        nd, dense = nb['nd'][:G].tolist(), nb['dense']
         for i in range(G):
             if ns[i] >= 2:
                 sampling_path[i] = [tuple(c) for c in samp[i][:ns[i]]]
-                true_path[i] = LazyPath(dense[i, :nd[i]].copy()) if lazy else [tuple(c) for c in dense[i, :nd[i]].tolist()]
+                true_path[i] = [tuple(c) for c in dense[i, :nd[i]].tolist()]
         return sampling_path, true_path
+
+    def _dense_for(self, pose, goal):
+        """Dense path of ONE (pose, goal) pair on demand (LazyPath.factory): own small buffers, generator state untouched."""
+        import ctypes
+        from . import _lib as L
+        max_dense = int((self.hl + 8.0 * math.pi * self.tr) / (self.ss / 10)) + 16
+        max_samp = max_dense // 10 + 2
+        samp, dense = np.empty((1, max_samp, 3)), np.empty((1, max_dense, 3))
+        ns, nd = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        pose_a, goal_a = np.asarray(pose, dtype=np.float64).copy(), np.asarray(goal, dtype=np.float64).reshape(1, 3).copy()
+        ext = np.asarray(self.extent, dtype=np.float64).copy()
+        vp = ctypes.c_void_p
+        L.check(L.lib.ipp_dubins_path_set(pose_a.ctypes.data_as(vp), goal_a.ctypes.data_as(vp), 1, float(self.tr),
+                                          float(self.ss / 10), 10, ext.ctypes.data_as(vp), float(3 * self.tr),
+                                          samp.ctypes.data_as(vp), ns.ctypes.data_as(vp), max_samp,
+                                          dense.ctypes.data_as(vp), nd.ctypes.data_as(vp), max_dense))
+        return [tuple(c) for c in dense[0, :int(nd[0])].tolist()]
 
     def _buffered_paths_python(self):
         sampling_path, true_path = {}, {}
