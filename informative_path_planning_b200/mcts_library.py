@@ -477,3 +477,30 @@ def choose_myopic(belief, path_generator, pose, f_rew, t, param=None, use_cost=F
         return paths[best_key], true_paths[best_key], value[best_key], paths, value
     except Exception:
         return None
+
+
+_grid_cache = {}
+
+
+def predict_max(belief, ranges, t=0, time=0):
+    """Robot.predict_max (reference robot_library.py:222-254): location and value of the posterior-mean maximum over the
+    100 x 100 grid of the world -- one batched device predict (the grid stays resident on the device between steps)."""
+    if belief.xvals is None:
+        return np.array([0., 0.]), 0.
+    key = (tuple(float(r) for r in ranges), int(belief.dimension), float(time) if belief.dimension == 3 else 0.0,
+           torch.cuda.current_device())
+    entry = _grid_cache.get(key)
+    if entry is None:
+        x1, x2 = np.meshgrid(np.linspace(ranges[0], ranges[1], 100), np.linspace(ranges[2], ranges[3], 100),
+                             sparse=False, indexing='xy')
+        if belief.dimension == 2:
+            data = np.vstack([x1.ravel(), x2.ravel()]).T
+        else:
+            data = np.vstack([x1.ravel(), x2.ravel(), time * np.ones(len(x1.ravel()))]).T
+        if len(_grid_cache) > 8:
+            _grid_cache.clear()
+        entry = _grid_cache[key] = (data, aqlib.L.to_device(data))
+    data, data_d = entry
+    mean, _ = belief.predict_device(data_d, precision='fp64')
+    top = torch.argmax(mean)                         # first index of the maximum, like np.argmax
+    return data[int(top.item()), :], float(mean[top].item())

@@ -183,3 +183,21 @@ def test_environment_world_matches_oracle_built_world(pkg):
     np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-4)
     mean = dev.GP.predict_value(q, include_noise=False)[0]
     assert np.ptp(a - mean) < 1e-9                                   # one scalar noise value for all seven points
+
+
+def test_predict_max_matches_reference_loop(pkg):
+    """Robot.predict_max (robot_library.py:222-254): arg-max of the posterior mean over the 100 x 100 grid."""
+    from informative_path_planning_b200 import mcts_library as mc
+    from oracle.gpmodel_oracle import OnlineGPModelOracle
+    d, o = _models(pkg, 0.5)
+    assert mc.predict_max(d, RANGES)[1] == 0.
+    rng = np.random.default_rng(8)
+    x = rng.uniform(0, 10, (60, 2))
+    z = field(x) + rng.normal(0, 0.7, (60, 1))
+    d.add_data(x, z); o.add_data(x, z)
+    loc, val = mc.predict_max(d, RANGES)
+    x1, x2 = np.meshgrid(np.linspace(0, 10, 100), np.linspace(0, 10, 100), sparse=False, indexing='xy')
+    data = np.vstack([x1.ravel(), x2.ravel()]).T
+    obs, _ = o.predict_value(data)
+    np.testing.assert_allclose(loc, data[np.argmax(obs), :])
+    np.testing.assert_allclose(val, np.max(obs), rtol=1e-9)
