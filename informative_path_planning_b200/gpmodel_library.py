@@ -123,8 +123,12 @@ class GPModel(object):
     def n_obs(self):
         return 0 if self.xvals is None else int(self.xvals.shape[0])
 
+    def _noise_var(self):
+        """Likelihood variance the regression actually uses (the legacy ipp_library model overrides it: GPy default 1.0)."""
+        return float(self.noise)
+
     def _diag_add(self):
-        return float(self.noise) + 1e-8
+        return self._noise_var() + 1e-8
 
     def _factor(self, want_linv):
         """Full FP64 refresh on the device, with GPy jitchol's retry ladder (linalg.py: jitter =
@@ -167,7 +171,7 @@ class GPModel(object):
         N = self.n_obs
         work = L.workspace(L.lib.ipp_gp_predict_workspace(N, M))
         L.check(L.lib.ipp_gp_predict(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                     L.ptr(mat), self._ld, mode, float(self.noise) if include_noise else 0.0,
+                                     L.ptr(mat), self._ld, mode, self._noise_var() if include_noise else 0.0,
                                      L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
         return mean, var
 
@@ -178,7 +182,7 @@ class GPModel(object):
     def _predict_chol(self, xvals, include_noise, full_cov=False):
         xvals = np.asarray(xvals, dtype=float)
         if full_cov:
-            return self._predict_full_cov(xvals, include_noise, float(self.noise), diagonal_only=True)
+            return self._predict_full_cov(xvals, include_noise, self._noise_var(), diagonal_only=True)
         mean, var = self._predict_core(L.to_device(xvals), include_noise, L.VAR_CHOL, self._linv_d)
         return mean.cpu().numpy().reshape(-1, 1), var.cpu().numpy().reshape(-1, 1)
 
@@ -309,7 +313,7 @@ class GPModel(object):
         var = torch.empty(M, dtype=torch.float64, device=xq_d.device)
         work = L.workspace(L.lib.ipp_gp_predict_i8_workspace(N, M), slot='i8')
         L.check(L.lib.ipp_gp_predict_i8(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                        L.ptr(tiles), scale, ns, float(self.noise) if include_noise else 0.0,
+                                        L.ptr(tiles), scale, ns, self._noise_var() if include_noise else 0.0,
                                         L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
         return mean, var
 
@@ -334,7 +338,7 @@ class GPModel(object):
         work = L.workspace(L.lib.ipp_gp_predict_tf32_workspace(N, M), slot='tf32')
         L.check(L.lib.ipp_gp_predict_tf32(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
                                           L.ptr(hi), L.ptr(lo), ldl, int(self.tf32_acc_kblocks),
-                                          float(self.noise) if include_noise else 0.0,
+                                          self._noise_var() if include_noise else 0.0,
                                           L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
         return mean, var
 
@@ -396,7 +400,7 @@ class GPModel(object):
         S = 0 if maxes_d is None else int(maxes_d.numel())
         base = buf.data_ptr()
         L.check(L.lib.ipp_rollout_rewards(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                          L.ptr(self._winv_d), self._ld, float(self.noise), self._diag_add(), kind,
+                                          L.ptr(self._winv_d), self._ld, self._noise_var(), self._diag_add(), kind,
                                           par, 1, L.ptr(maxes_d), S, ctypes.c_void_p(base),
                                           ctypes.c_void_p(base + 8 * M * D), offsets, reps, L_,
                                           L.ptr(out), ctypes.c_void_p(out.data_ptr() + 8 * L_), L.ptr(work),
@@ -519,7 +523,7 @@ class OnlineGPModel(GPModel):
         if self.xvals is None:
             return np.zeros((n_points, 1)), np.ones((n_points, 1)) * self.variance
         if full_cov:
-            return self._predict_full_cov(xvals, include_noise, float(self.noise), diagonal_only=False)
+            return self._predict_full_cov(xvals, include_noise, self._noise_var(), diagonal_only=False)
         mean, var = self.predict_device(L.to_device(xvals), include_noise)     # FP64 unless .predict_precision says otherwise
         return mean.cpu().numpy().reshape(-1, 1), var.cpu().numpy().reshape(-1, 1)
 

@@ -829,3 +829,42 @@ def test_rff_theta_batch_on_device_matches_reference_formula(pkg):
     mx, locs, _ = aq.sample_max_vals_shared(m, grid, nK=6, nFeatures=F, rng=np.random.default_rng(5))
     assert mx.shape == (6, 1) and locs.shape == (6, 2) and np.all(np.isfinite(mx))
     assert np.all(mx.ravel() > z.max() - 15.0)                 # sampled maxima sit near / above the observed maximum
+
+
+def test_legacy_ipp_library_call_sites(pkg):
+    """The monolith's call sites (reference ipp_library.py): GPModel runs with GPy's default likelihood variance 1.0 and
+    ignores .noise (:145); its mves is the same utility as aq_library.mves summed once (half of it, Q2/Q3); its
+    MCTS.get_reward scores the concatenated samples of a whole sequence in one call."""
+    aqo, gpo, _ = _oracle()
+    from informative_path_planning_b200 import ipp_library as ipp
+    rng = np.random.default_rng(2)
+    X, z = world(rng, 80, 0.5)
+    d = ipp.GPModel(RANGES, 1.0, 100.0, noise=0.0001)
+    o = gpo.GPModelOracle(RANGES, 1.0, 100.0, noise=1.0)            # what GPRegression(X, Y, kern) amounts to
+    q = rng.uniform(0, 10, (40, 2))
+    mu0, var0 = d.predict_value(q)
+    assert np.all(mu0 == 0) and np.all(var0 == 100.0)
+    assert abs(ipp.mean_UCB(3, q[:5], d) - np.sqrt(aqo.ucb_beta(3)) * 500.0) < 1e-9      # no data: scores the prior
+    d.add_data(X[:50], z[:50]); o.add_data(X[:50], z[:50])
+    d.add_data(X[50:], z[50:]); o.add_data(X[50:], z[50:])
+    mu_d, var_d = d.predict_value(q)
+    mu_o, var_o = o.predict_value(q, include_noise=True)
+    np.testing.assert_allclose(mu_d, mu_o, rtol=RTOL, atol=1e-8)
+    np.testing.assert_allclose(var_d, var_o, rtol=RTOL)
+    assert d.noise == 0.0001 and d.dim == 2
+    d.add_data_and_temp_model(q[:3], np.zeros((3, 1)))
+    o2 = gpo.GPModelOracle(RANGES, 1.0, 100.0, noise=1.0)
+    o2.add_data(np.vstack([X, q[:3]]), np.vstack([z, np.zeros((3, 1))]))
+    np.testing.assert_allclose(d.predict_value(q[5:9], TEMP=True)[1], o2.predict_value(q[5:9])[1], rtol=RTOL)
+    np.testing.assert_allclose(d.predict_value(q[5:9])[1], var_o[5:9], rtol=RTOL)        # the model itself is untouched
+    maxes = np.array([[30.0], [35.0]])
+    path = rng.uniform(1, 9, (6, 3))
+    mean, var = o.predict_value(path[:, :2])
+    want = sum(np.sum(ipp.entropy_of_n(var) - ipp.entropy_of_tn(None, m, mean, var)) for m in maxes.ravel()) / 2
+    np.testing.assert_allclose(ipp.mves(3, path, d, (maxes, None, None)), want, rtol=1e-6)
+    np.testing.assert_allclose(ipp.mves(3, path, d, (maxes, None, None)), 0.5 * pkg.aq_library.mves(3, path, d, (maxes, None, None)))
+    seq = [[tuple(p) for p in path[:3]], [tuple(p) for p in path[3:]]]
+    got = ipp.sequence_reward(ipp.mean_UCB, 'mean', 3, seq, d)
+    np.testing.assert_allclose(got, aqo.mean_UCB(3, path, o), rtol=RTOL)
+    with pytest.raises(ValueError):
+        ipp.GPModel(RANGES, 1.0, 100.0, dimension=3)
