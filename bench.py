@@ -551,7 +551,7 @@ def main():
                 err = (var8 - var64).abs()
                 extras[prec + '_N4096'] = {
                     'queries_per_s': M / (ms8 / 1e3), 'ms_per_step': ms8, 'speedup_vs_fp64_mode': (ms_fp64 / ms8) if ms_fp64 else None,
-                    'kernel': 'predict_var_i8_kernel<%d slices, 128x%d tiles> (tcgen05.mma kind::i8, 3-D TMA, TMEM; %d slice-pair '
+                    'kernel': 'predict_var_i8_kernel<%d slices, 128x%d tiles> (tcgen05.mma kind::i8, bulk-copied stage images, TMEM; %d slice-pair '
                               'products per MAC executed)' % (ns, bn, n_prod),
                     'kernel_ms': k_ms.value / max(1, k_n.value), 'kernel_int8_tops_executed': kern_tops,
                     'cublas_int8_tops_measured': i8_peak, 'frac_of_cublas_int8': (kern_tops / i8_peak) if i8_peak else None,
