@@ -186,9 +186,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--queries', type=int, default=M_QUERIES, help='queries per GPU per step (default 2^20)')
     ap.add_argument('--no-extras', action='store_true', help='skip cpu baseline / reward-path extras (profiling runs)')
-    ap.add_argument('--precision', default='fp64', choices=['fp64', 'i8x6'],
-                    help="arithmetic of the timed path: 'fp64' = FP64 DMMA (default, the headline); 'i8x6' = FP64-grade "
-                         "sliced-INT8 tcgen05 path (same 1e-6 parity tolerance, ~3.8x the rate)")
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'i8x7', 'i8x6'],
+                    help="arithmetic of the timed path: 'fp64' = FP64 DMMA (default, the headline); 'i8x7' / 'i8x6' = sliced-INT8 "
+                         "tcgen05 path with 49- / 42-bit operands and exact integer accumulation (i8x7 is closer to an "
+                         "extended-precision solve than the FP64 path itself; ~3x / ~3.8x the rate)")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -282,9 +283,10 @@ def main():
         a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
         b = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
         mm = torch.matmul
-    else:                                           # 21 slice-pair products x 128 x 64 tiles x k-blocks of 64, lower-triangular
+    else:                                           # 28 / 21 slice-pair products x 128 x 64 tiles x k-blocks of 64, lower-triangular
         T64 = (N_OBS + 63) // 64
-        flops_launch = 21 * 2.0 * 128 * 64 * 64 * (T64 * (T64 + 1) / 2) * (chunk / 128.0)
+        n_prod = 28 if args.precision == 'i8x7' else 21
+        flops_launch = n_prod * 2.0 * 128 * 64 * 64 * (T64 * (T64 + 1) / 2) * (chunk / 128.0)
         a = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
         b = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
         mm = torch._int_mm
@@ -311,7 +313,8 @@ def main():
         'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tflops, 'unit': 'TFLOP/s' if fp64 else 'TOP/s',
         'frac': (achieved / dgemm_tflops) if achieved else None, 'traffic': traffic, 'traffic_source': traffic_src,
         'kernel': 'predict_var_kernel (FP64 DMMA.8x8x4, symmetric-half form: executed flops only)' if fp64 else
-                  'predict_var_i8_kernel<6 slices, 128x64> (tcgen05.mma kind::i8, 21 slice-pair products: executed INT8 ops only)',
+                  'predict_var_i8_kernel<%s slices, 128x64> (tcgen05.mma kind::i8, %d slice-pair products: executed INT8 ops only)'
+                  % (args.precision[-1], n_prod),
         'kernel_ms': kernel_ms, 'kernel_launches_timed': int(launches.value), 'kernel_share_of_step': tot_ms.value / ms_total,
         'flops_per_launch': flops_launch,
         'peak_source': ('FP64 DGEMM 8192^3 via torch.matmul (cuBLAS)' if fp64 else 'INT8 GEMM 8192^3 via torch._int_mm (cuBLAS)') +
@@ -322,12 +325,13 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64' if fp64 else 'i8 (6 x 7-bit slices per f64 operand, exact i32 accumulation, f64 combine; f64 mean)',
+        'dtype': 'f64' if fp64 else 'i8 (%s x 7-bit slices per f64 operand, exact i32 accumulation, f64 combine; f64 mean)'
+                 % args.precision[-1],
         'data': 'synthetic',
         'config': {'workload': 'gp_predict N=4096 obs x M=2^20 queries per GPU (BASELINE config 3 at N=4k), %s, 10x10 '
-                               'world RBF l=1 var=100 noise=0.5' % ('FP64' if fp64 else 'FP64-grade sliced INT8'),
+                               'world RBF l=1 var=100 noise=0.5' % ('FP64' if fp64 else 'sliced INT8 (%s)' % args.precision),
                    'n_obs': N_OBS, 'queries_per_gpu': M,
-                   'variance_form': 'W^-1 symmetric-half (IPP_VAR_WINV_SYM)' if fp64 else 'Cholesky form |L^-1 k|^2 (i8x6)',
+                   'variance_form': 'W^-1 symmetric-half (IPP_VAR_WINV_SYM)' if fp64 else 'Cholesky form |L^-1 k|^2 (%s)' % args.precision,
                    'l2': 'no flush: per step the kernels stream the 134 MB W^-1 and a 1.07 GB cross-covariance '
                          'scratch, both larger than the 126 MB L2',
                    'parallelism': 'queries sharded, belief replicated (dp%d)' % world},
@@ -528,7 +532,7 @@ def main():
             i8_peak = 2.0 * 8192 ** 3 / (best8 / 1e3) / 1e12
         except Exception:
             i8_peak = None
-        for prec, ns, bn in (('i8x6', 6, 64), ('i8x5', 5, 96)):
+        for prec, ns, bn in (('i8x7', 7, 64), ('i8x6', 6, 64), ('i8x5', 5, 96)):
             try:
                 mu64, var64 = model.predict_device(xq)
                 model.predict_device(xq, precision=prec)
@@ -558,9 +562,12 @@ def main():
                     'fp64_equivalent_tflops': kern_tops / n_prod,
                     'mean_max_abs_diff_vs_fp64': float((mu8 - mu64).abs().max()),
                     'var_rel_err_max': float((err / var64).max()), 'var_rel_err_median': float((err / var64).median()),
-                    'note': ('FP64-grade: exact integer accumulation, 42-bit fixed-point operands; passes the FP64 mode parity tests '
-                             '(tests/test_gpu_parity.py::test_predict_i8x6_mode_is_fp64_grade); headline stays FP64 DMMA') if ns == 6 else
-                            'fast tensor mode: 35-bit operands; the reduced-precision arm that replaces 3xTF32 (faster and ~200x more accurate)'}
+                    'note': {7: 'FP64-equivalent: 49-bit fixed-point operands, exact integer accumulation; 1e-10 from an extended-'
+                                'precision solve where the FP64 DMMA mode is 2e-9 (profiles/r1i_check_large_N4096.json)',
+                             6: 'FP64-grade: 42-bit operands; passes the FP64 mode parity tests '
+                                '(tests/test_gpu_parity.py::test_predict_i8x6_mode_is_fp64_grade); headline stays FP64 DMMA',
+                             5: 'fast tensor mode: 35-bit operands; the reduced-precision arm that replaces 3xTF32 (faster and '
+                                '~200x more accurate)'}[ns]}
             except Exception as e:
                 extras[prec + '_N4096'] = {'error': repr(e)}
         line['extra'] = extras

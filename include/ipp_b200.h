@@ -124,6 +124,7 @@ int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const d
  *      Operands in fixed point against one power-of-two scale each, cut into six signed 7-bit slices; 21 slice-pair
  *      products (i + j <= 5) accumulate exactly, the six weight levels are combined in FP64.  Measured variance error
  *      ~2e-8 relative (inside the FP64 mode's 1e-6 parity tolerance); the mean is computed exactly as in FP64 mode.
+ *      n_slices = 7: 49-bit operands, 28 products, 128 x 64 tiles ("i8x7": ~3e-10, FP64-equivalent for this path);
  *      n_slices = 6: 42-bit operands, 21 products, 128 x 64 tiles ("i8x6", the FP64-grade setting above);
  *      n_slices = 5: 35-bit operands, 15 products, 128 x 96 tiles ("i8x5": ~2e-6 relative variance error, ~1.7x faster).
  *        ipp_i8_slice: A[rows][lda] (double) -> ipp_i8_slice_bytes(rows, cols, n_slices) bytes of int8 "tiles": the slices

@@ -28,23 +28,25 @@ namespace ipp {
 #define IPP_I8_COLLECTOR 1
 #endif
 constexpr int I_BM = 128, I_BK = 64;                   // tile rows; I_BK int8 = 64 B = one SWIZZLE_64B row
-constexpr int I_STAGES = 3;
 constexpr int I_THREADS = 192;                         // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int I_TMEM_COLS = 512;
-constexpr int I_MAX_NS = 6;
+constexpr int I_MAX_NS = 7;
 
-// Two instantiations: NS slices per operand (= number of weight levels i + j = 0..NS-1, products NS (NS + 1) / 2) and the
-// widest tile whose NS INT32 accumulators fit the 512 TMEM columns:
-//   <6, 64>  42-bit operands, 21 products, 6 x 64 = 384 columns   ("i8x6": ~4e-8 relative variance error, FP64-grade)
-//   <5, 96>  35-bit operands, 15 products, 5 x 96 = 480 columns   ("i8x5": ~2e-6; fewer products AND a wider MMA, i.e.
-//            fewer shared-memory bytes per MAC -- faster and 400x more accurate than the 3xTF32 mode)
-template <int NS_, int BN_>
+// Three instantiations: NS slices per operand (= number of weight levels i + j = 0..NS-1, products NS (NS + 1) / 2), the
+// widest tile whose NS INT32 accumulators fit the 512 TMEM columns, and as many stages as fit shared memory:
+//   <7, 64, 2>  49-bit operands, 28 products, 7 x 64 = 448 columns   ("i8x7": ~3e-10 relative variance error -- below the
+//               FP64 DMMA mode's own summation-order deviation from the oracle; FP64-equivalent for this path)
+//   <6, 64, 3>  42-bit operands, 21 products, 6 x 64 = 384 columns   ("i8x6": ~4e-8, FP64-grade: inside the 1e-6 tolerance)
+//   <5, 96, 3>  35-bit operands, 15 products, 5 x 96 = 480 columns   ("i8x5": ~4e-6; fewer products AND a wider MMA --
+//               faster and 200x more accurate than the 3xTF32 mode)
+template <int NS_, int BN_, int STAGES_>
 struct I8Cfg {
-    static constexpr int NS = NS_, BN = BN_;
+    static constexpr int NS = NS_, BN = BN_, STAGES = STAGES_;
     static constexpr int A_PLANE = I_BM * I_BK, B_PLANE = BN_ * I_BK;
     static constexpr int A_BYTES = NS_ * A_PLANE, B_BYTES = NS_ * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM = I_STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM = STAGES_ * STAGE_BYTES + 1024 + 256;
+    static_assert(SMEM <= 232448, "stages must fit the 227 KB of shared memory");
     // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = BN, M = 128
     static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(I_BM >> 4) << 24);
     static_assert(NS_ * BN_ <= I_TMEM_COLS && BN_ % 32 == 0 && NS_ <= I_MAX_NS, "accumulators must fit TMEM");
@@ -109,7 +111,7 @@ template <class C>
 __global__ void __launch_bounds__(I_THREADS, 1)
 predict_var_i8_kernel(const I8Args p) {
     constexpr int I_NS = C::NS, I_BN = C::BN, I_A_PLANE = C::A_PLANE, I_B_PLANE = C::B_PLANE, I_A_BYTES = C::A_BYTES;
-    constexpr int I_STAGE_BYTES = C::STAGE_BYTES, I_LEVELS = C::NS;
+    constexpr int I_STAGE_BYTES = C::STAGE_BYTES, I_LEVELS = C::NS, I_STAGES = C::STAGES;
     extern __shared__ unsigned char i_smem_raw[];
     const uint32_t raw = smem_addr(i_smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;
@@ -262,7 +264,7 @@ __global__ void i8_slice_kernel(const double* __restrict__ A, int64_t rows, int6
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows_pad * KB * 64) return;
     const int64_t r = idx / (KB * 64), c = idx % (KB * 64);
-    int s[I_MAX_NS] = {0, 0, 0, 0, 0, 0};
+    int s[I_MAX_NS] = {0, 0, 0, 0, 0, 0, 0};
     if (r < rows && c < cols) slice_signed(A[r * lda + c], inv_scale, ns, s);
     const int64_t tile = r / bn, kb = c / 64;
     const int64_t base = ((tile * KB + kb) * ns) * ((int64_t)bn * 64) + swz64((int)(r % bn), (int)(c % 64));
@@ -352,10 +354,11 @@ static double pow2_at_least(double x) {
 
 using namespace ipp;
 
-static int bn_of(int n_slices) { return n_slices == 6 ? 64 : 96; }
+static int bn_of(int n_slices) { return n_slices == 5 ? 96 : 64; }
+static bool ns_ok(int n_slices) { return n_slices >= 5 && n_slices <= 7; }
 
 extern "C" int64_t ipp_i8_slice_bytes(int64_t rows, int64_t cols, int n_slices) {
-    if (rows <= 0 || cols <= 0 || (n_slices != 5 && n_slices != 6)) return 0;
+    if (rows <= 0 || cols <= 0 || !ns_ok(n_slices)) return 0;
     const int64_t bn = bn_of(n_slices);
     return round_up(rows, bn) * ((cols + 63) / 64) * 64 * n_slices;
 }
@@ -366,7 +369,7 @@ extern "C" int ipp_i8_slice(const double* A, int64_t rows, int64_t cols, int64_t
     IPP_CHECK_ARG(A && tiles && rows >= 1 && cols >= 1 && lda >= cols, "bad arguments");
     IPP_CHECK_ARG(reinterpret_cast<uintptr_t>(tiles) % 16 == 0, "tiles must be 16-byte aligned");
     IPP_CHECK_ARG(scale > 0, "scale must be a positive power of two >= max |A|");
-    IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6");
+    IPP_CHECK_ARG(ns_ok(n_slices), "n_slices must be 5, 6 or 7");
     const int bn = bn_of(n_slices);
     const int64_t KB = (cols + 63) / 64, rows_pad = round_up(rows, bn), total = rows_pad * KB * 64;
     i8_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, rows, cols, lda, 1.0 / scale, n_slices, bn, KB, rows_pad, tiles);
@@ -445,8 +448,11 @@ extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N
     IPP_CHECK_ARG(reinterpret_cast<uintptr_t>(linv_tiles) % 16 == 0 && reinterpret_cast<uintptr_t>(work) % 16 == 0,
                   "linv tiles and work must be 16-byte aligned");
     IPP_CHECK_ARG(linv_scale > 0 && kern->variance > 0, "scales must be positive");
-    IPP_CHECK_ARG(n_slices == 5 || n_slices == 6, "n_slices must be 5 or 6 (the count linv_tiles was cut with)");
+    IPP_CHECK_ARG(ns_ok(n_slices), "n_slices must be 5, 6 or 7 (the count linv_tiles was cut with)");
+    IPP_CHECK_ARG(N <= 37000 || n_slices < 7, "n_slices = 7 needs N <= 37000 (exact INT32 accumulation of 7 pairs per level)");
+    if (n_slices == 7)
+        return predict_i8_impl<I8Cfg<7, 64, 2>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
     if (n_slices == 6)
-        return predict_i8_impl<I8Cfg<6, 64>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
-    return predict_i8_impl<I8Cfg<5, 96>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
+        return predict_i8_impl<I8Cfg<6, 64, 3>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
+    return predict_i8_impl<I8Cfg<5, 96, 3>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
 }

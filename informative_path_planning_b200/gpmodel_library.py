@@ -345,18 +345,19 @@ class GPModel(object):
     def predict_device(self, xq_d, include_noise=True, precision=None):
         """(M, D) float64 CUDA tensor -> (mean[M], var[M]) CUDA tensors; no host transfer.
         precision: 'fp64' (FP64 DMMA), 'i8x6' (tcgen05 kind::i8 on six 7-bit slices per operand, exact integer
-        accumulation: FP64-grade, ~4e-8 relative variance error), 'i8x5' (five slices, 15 products on wider tiles:
+        accumulation: FP64-grade, ~4e-8 relative variance error), 'i8x7' (seven slices, 28 products: ~3e-10, below the
+        FP64 DMMA mode's own round-off against the oracle), 'i8x5' (five slices, 15 products on wider tiles:
         ~2e-6, faster) or 'tf32x3' (tcgen05 kind::tf32, split operands, ~2e-4); default = the model's .predict_precision.  Small batches always use the FP64 path (bandwidth-bound)."""
         if self.n_obs == 0:
             M = xq_d.shape[0]
             return (torch.zeros(M, dtype=torch.float64, device=xq_d.device),
                     torch.full((M,), float(self.variance), dtype=torch.float64, device=xq_d.device))
         precision = self.predict_precision if precision is None else precision
-        if precision not in ('fp64', 'tf32x3', 'i8x6', 'i8x5'):
-            raise ValueError("precision must be 'fp64', 'i8x6', 'i8x5' or 'tf32x3'")
+        if precision not in ('fp64', 'tf32x3', 'i8x7', 'i8x6', 'i8x5'):
+            raise ValueError("precision must be 'fp64', 'i8x7', 'i8x6', 'i8x5' or 'tf32x3'")
         if precision == 'tf32x3' and xq_d.shape[0] > 64:
             return self._predict_tf32(xq_d.contiguous(), include_noise)
-        if precision in ('i8x6', 'i8x5') and xq_d.shape[0] > 64:
+        if precision in ('i8x7', 'i8x6', 'i8x5') and xq_d.shape[0] > 64:
             return self._predict_i8(xq_d.contiguous(), include_noise, ns=int(precision[-1]))
         mode, mat = self._var_operand()
         return self._predict_core(xq_d.contiguous(), include_noise, mode, mat)

@@ -494,7 +494,7 @@ def test_space_time_kernel_d3(pkg):
         d.predict_value(q[:, :2])
     # the tensor modes carry D = 3 too (their cross-covariance generators are templated on the dimension)
     mu_o, var_o = o.predict_value(q)
-    for prec, tol in (('i8x6', RTOL), ('tf32x3', 2e-3)):
+    for prec, tol in (('i8x7', RTOL), ('i8x6', RTOL), ('tf32x3', 2e-3)):
         d.predict_precision = prec
         mu_t, var_t = d.predict_value(q)
         np.testing.assert_allclose(mu_t, mu_o, rtol=RTOL, atol=1e-7)
@@ -802,7 +802,7 @@ def test_precision_modes_across_hyperparameters(pkg, variance, lengthscale, nois
     d.add_data(X, z); o.add_data(X, z)
     q = rng.uniform(0, 10, (M, 2))
     mu_o, var_o = o.predict_value(q)
-    for prec, tol in (('fp64', RTOL), ('i8x6', RTOL), ('i8x5', 1e-4), ('tf32x3', 5e-3)):
+    for prec, tol in (('fp64', RTOL), ('i8x7', RTOL), ('i8x6', RTOL), ('i8x5', 1e-4), ('tf32x3', 5e-3)):
         d.predict_precision = prec
         mu, var = d.predict_value(q)
         np.testing.assert_allclose(mu, mu_o, rtol=RTOL, atol=1e-7 * np.sqrt(variance), err_msg=prec)
@@ -868,3 +868,23 @@ def test_legacy_ipp_library_call_sites(pkg):
     np.testing.assert_allclose(got, aqo.mean_UCB(3, path, o), rtol=RTOL)
     with pytest.raises(ValueError):
         ipp.GPModel(RANGES, 1.0, 100.0, dimension=3)
+
+
+@pytest.mark.parametrize('N,M', [(9, 70), (333, 130), (2048, 33000)])
+def test_predict_i8x7_mode_is_fp64_equivalent(pkg, N, M):
+    """Seven-slice INT8 mode (49-bit operands, 28 products): its deviation from the FP64 DMMA mode (asserted <= 2e-8
+    relative; measured ~1e-9) is of the order of that mode's own summation-order round-off against the oracle."""
+    _, gpo, _ = _oracle()
+    rng = np.random.default_rng(N + 7)
+    X, z = world(rng, N, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    q = rng.uniform(0, 10, (M, 2))
+    mu64, var64 = m.predict_value(q)
+    m.predict_precision = 'i8x7'
+    mu7, var7 = m.predict_value(q)
+    np.testing.assert_allclose(mu7, mu64, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(var7, var64, rtol=2e-8)
+    o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    o.add_data(X, z)
+    np.testing.assert_allclose(var7[:300], o.predict_value(q[:300])[1], rtol=RTOL)

@@ -40,8 +40,8 @@ for N in [int(a) for a in (sys.argv[1:] or ['333', '1024', '2048', '4096', '8192
     T64 = (N + 63) // 64
     res['mode'] = MODE
     res['tf32_executed_tflops'] = 3 * 2.0 * 128 * 128 * T * (T + 1) / 2 * M / (res[MODE + '_ms'] / 1e3) / 1e12 if MODE == 'tf32x3' else None
-    if MODE in ('i8x6', 'i8x5'):
-        ns, bn = (6, 64) if MODE == 'i8x6' else (5, 96)
+    if MODE in ('i8x7', 'i8x6', 'i8x5'):
+        ns, bn = {'i8x7': (7, 64), 'i8x6': (6, 64), 'i8x5': (5, 96)}[MODE]
         kblocks = sum(-(-min((I + 1) * bn, N) // 64) for I in range(-(-N // bn)))
         res['i8_executed_tops'] = ns * (ns + 1) / 2 * 2.0 * 128 * bn * 64 * kblocks * (M / 128) / (res[MODE + '_ms'] / 1e3) / 1e12
     else:
