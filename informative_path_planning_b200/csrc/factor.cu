@@ -84,11 +84,7 @@ __global__ void init_factor_scalars_kernel(double* logdet, int32_t* info) {
 }
 
 int potrf_lower(double* A, int64_t N, int64_t lda, double* dinv, double* logdet, int32_t* info, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-        configured = true;
-    }
+    IPP_OPT_IN_SMEM(potrf_diag_kernel, DIAG_SMEM);
     init_factor_scalars_kernel<<<1, 1, 0, s>>>(logdet, info);
     IPP_LAUNCH_CHECK();
     for (int64_t j0 = 0, blk = 0; j0 < N; j0 += NB, ++blk) {

@@ -63,11 +63,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     IPP_CHECK_ARG(g.C == nullptr || ((g.ldc % 2 == 0) && (reinterpret_cast<uintptr_t>(g.C) % 16 == 0)),
                   "C must be 16-byte aligned with even ldc");
     IPP_CHECK_ARG(g.C != nullptr || g.beta == 0.0, "beta != 0 needs C");
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        configured = true;
-    }
+    IPP_OPT_IN_SMEM(dgemm_nt_kernel, GEMM_SMEM);
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, 1);
     dgemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g);
     IPP_LAUNCH_CHECK();

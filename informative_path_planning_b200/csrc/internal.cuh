@@ -28,6 +28,19 @@ void profile_mark(int which, cudaStream_t s);      // CUDA-event bracket of the 
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) setting: remember it per device so
+// that one process driving several GPUs configures every one of them (a plain function-static flag would not).
+#define IPP_OPT_IN_SMEM(kernel, bytes)                                                                   \
+    do {                                                                                                 \
+        static bool done__[64] = {};                                                                     \
+        int dev__ = 0;                                                                                   \
+        IPP_CUDA(cudaGetDevice(&dev__));                                                                 \
+        if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                \
+            IPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                          \
+        }                                                                                                \
+    } while (0)
+
 // ----- generic FP64 DMMA GEMM:  C (and/or Ct) = alpha * A[M][K] * B[N][K]^T + beta * C
 struct GemmArgs {
     const double* A; const double* B; double* C; double* Ct;

@@ -232,11 +232,7 @@ extern "C" int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, c
     IPP_CHECK_ARG(var_mode >= 0 && var_mode <= 2, "bad var_mode");
     IPP_CHECK_ARG(ldm >= N && ldm % 2 == 0 && reinterpret_cast<uintptr_t>(mat) % 16 == 0, "mat must be 16-byte aligned, ldm even");
     IPP_CHECK_ARG(N < (1LL << 30), "N too large");
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        configured = true;
-    }
+    IPP_OPT_IN_SMEM(predict_var_kernel, GEMM_SMEM);
     const int64_t ldk = round_up(N, 16), mc_max = chunk_rows(M);
     const int T = (int)((N + BN - 1) / BN);
     if (M <= 2 * SMALL_M) {                       // planner-sized batches: stream the operand once

@@ -35,7 +35,7 @@ constexpr int I_MAX_NS = 7;
 // Three instantiations: NS slices per operand (= number of weight levels i + j = 0..NS-1, products NS (NS + 1) / 2), the
 // widest tile whose NS INT32 accumulators fit the 512 TMEM columns, and as many stages as fit shared memory:
 //   <7, 64, 2>  49-bit operands, 28 products, 7 x 64 = 448 columns   ("i8x7": ~3e-10 relative variance error -- below the
-//               FP64 DMMA mode's own summation-order deviation from the oracle; FP64-equivalent for this path)
+//               FP64 DMMA mode's own deviation from an extended-precision solve; FP64-equivalent for this path)
 //   <6, 64, 3>  42-bit operands, 21 products, 6 x 64 = 384 columns   ("i8x6": ~4e-8, FP64-grade: inside the 1e-6 tolerance)
 //   <5, 96, 3>  35-bit operands, 15 products, 5 x 96 = 480 columns   ("i8x5": ~4e-6; fewer products AND a wider MMA --
 //               faster and 200x more accurate than the 3xTF32 mode)
@@ -390,11 +390,7 @@ static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, cons
                            double linv_scale, double noise_add, const double* Xq, int64_t M, double* mean,
                            double* var, double* work, cudaStream_t stream) {
     constexpr int NS = C::NS, BN = C::BN;
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(predict_var_i8_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        configured = true;
-    }
+    IPP_OPT_IN_SMEM(predict_var_i8_kernel<C>, C::SMEM);
     const int64_t KB = (N + 63) / 64, mc_max = i8_chunk_rows(M);
     const int T = (int)((N + BN - 1) / BN);
     int8_t* tiles = reinterpret_cast<int8_t*>(work);

@@ -328,11 +328,7 @@ extern "C" int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t
     IPP_CHECK_ARG(kern->dim == 2 || kern->dim == 3, "dimension must be 2 or 3");
     IPP_CHECK_ARG(ldl >= N && ldl % 4 == 0 && reinterpret_cast<uintptr_t>(linv_hi) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(linv_lo) % 16 == 0, "linv_hi/lo must be 16-byte aligned with ldl % 4 == 0");
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(predict_var_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
-        configured = true;
-    }
+    IPP_OPT_IN_SMEM(predict_var_tf32_kernel, T_SMEM);
     const int64_t ldf = round_up(N, 32), mc_max = tf32_chunk_rows(M);
     const int T = (int)((N + TBN - 1) / TBN);
     float* Khi = reinterpret_cast<float*>(work);

@@ -269,11 +269,7 @@ extern "C" int ipp_rff_eval_argmax(const double* W, const double* b, const doubl
     IPP_CHECK_ARG(F >= 1 && S >= 1 && G >= 1 && F < (1 << 30) && S < (1 << 30), "bad shape");
     IPP_CHECK_ARG(D == 2 || D == 3, "dimension must be 2 or 3");
     if (rff_use_gemm(S, shared_w)) {
-        static bool configured = false;
-        if (!configured) {
-            IPP_CUDA(cudaFuncSetAttribute(rff_gemm_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-            configured = true;
-        }
+        IPP_OPT_IN_SMEM(rff_gemm_argmax_kernel, GEMM_SMEM);
         const int64_t ldf = round_up(F, 16), gc_max = rff_chunk_rows(G);
         const int nparts = (int)((G + BM - 1) / BM);
         double* Phi = work;

@@ -371,11 +371,7 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
         IPP_LAUNCH_CHECK();
         rollout_mean_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(Kxt, ldk, (int)N, M, alpha, mean0);
         IPP_LAUNCH_CHECK();
-        static bool tw_configured = false;
-        if (!tw_configured) {
-            IPP_CUDA(cudaFuncSetAttribute(rollout_tw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
-            tw_configured = true;
-        }
+        IPP_OPT_IN_SMEM(rollout_tw_kernel, TW_SMEM);
         constexpr int rows_per_block = TW_WARPS * TW_ROWS_PER_WARP;
         rollout_tw_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 32 * TW_WARPS, TW_SMEM, stream>>>(
             winv, ldw, (int)N, Kxt, ldk, M, T1);
@@ -388,12 +384,7 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
     p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc; p.zobs = zobs;
     p.M = M; p.L = L; p.kind = kind; p.maxes = maxes_dev; p.S = (int)S;
     p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA(cudaFuncSetAttribute(rollout_condition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)rollout_smem(RO_MAX_POINTS)));
-        configured = true;
-    }
+    IPP_OPT_IN_SMEM(rollout_condition_kernel, (int)rollout_smem(RO_MAX_POINTS));
     rollout_condition_kernel<<<1, RO_THREADS, rollout_smem(M), stream>>>(p);
     IPP_LAUNCH_CHECK();
     return IPP_OK;

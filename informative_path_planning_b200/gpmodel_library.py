@@ -346,7 +346,7 @@ class GPModel(object):
         """(M, D) float64 CUDA tensor -> (mean[M], var[M]) CUDA tensors; no host transfer.
         precision: 'fp64' (FP64 DMMA), 'i8x6' (tcgen05 kind::i8 on six 7-bit slices per operand, exact integer
         accumulation: FP64-grade, ~4e-8 relative variance error), 'i8x7' (seven slices, 28 products: ~3e-10, below the
-        FP64 DMMA mode's own round-off against the oracle), 'i8x5' (five slices, 15 products on wider tiles:
+        FP64 DMMA mode's own round-off against an extended-precision solve), 'i8x5' (five slices, 15 products on wider tiles:
         ~2e-6, faster) or 'tf32x3' (tcgen05 kind::tf32, split operands, ~2e-4); default = the model's .predict_precision.  Small batches always use the FP64 path (bandwidth-bound)."""
         if self.n_obs == 0:
             M = xq_d.shape[0]
