@@ -56,6 +56,22 @@ class _RBFKern(object):
         ret[:] = self.variance
         return ret
 
+    # GPy parameter-array view: kern[:] = [variance, lengthscale(s)]  (gpmodel_library.py:144, 180)
+    def _params(self):
+        ls = np.asarray(self.lengthscale, dtype=float).reshape(-1)
+        n_ls = self.input_dim if self.ARD else 1
+        return np.concatenate([[float(np.asarray(self.variance, dtype=float).reshape(-1)[0])], ls[:n_ls]])
+
+    def __getitem__(self, key):
+        return self._params()[key]
+
+    def __setitem__(self, key, value):
+        p = self._params()
+        p[key] = np.asarray(value, dtype=float).reshape(-1) if np.ndim(value) else float(value)
+        self.variance = float(p[0])
+        self.lengthscale = tuple(float(v) for v in p[1:]) if self.ARD else float(p[1])
+        self._c = L.make_rbf(self.input_dim, self.variance, self.lengthscale)
+
 
 class _LegacyModelHandle(object):
     """Stands in for the GPy GPRegression object the reference keeps in `.model`: callers only
@@ -223,11 +239,55 @@ class GPModel(object):
     def posterior_samples(self, xvals, size=10, full_cov=True):
         return self.model.posterior_samples_f(xvals, size, full_cov=full_cov)
 
+    def _refresh_after_kernel_change(self):
+        if self.xvals is not None:
+            self._factor(want_linv=self._linv_d is not None)
+
     def load_kernel(self, kernel_file='kernel_model.npy'):
-        raise NotImplementedError('GPy hyper-parameter files are outside the accelerated hot path (SURVEY.md 8f rank 4)')
+        """reference :134-147: kern[:] = [variance, lengthscale(s)] from a .npy file (the model's own .variance /
+        .lengthscale attributes are left alone, as in the reference)."""
+        import os
+        if not os.path.isfile(kernel_file):
+            raise ValueError('Failed to load kernel. Kernel parameter file not found.')
+        self.kern[:] = np.load(kernel_file)
+        self._refresh_after_kernel_change()
+
+    def log_marginal_likelihood(self):
+        """Exact GP log marginal likelihood of the current data under the current kernel, from the device factorisation:
+        -0.5 z^T alpha - 0.5 logdet(K + (noise + 1e-8) I) - N/2 log(2 pi)."""
+        N = self.n_obs
+        quad = float(torch.dot(self._z_d, self._alpha_d).item())
+        return -0.5 * quad - 0.5 * float(self._logdet[0].item()) - 0.5 * N * np.log(2.0 * np.pi)
 
     def train_kernel(self, xvals=None, zvals=None, kernel_file='kernel_model.npy'):
-        raise NotImplementedError('GPy marginal-likelihood training is outside the accelerated hot path (SURVEY.md 8f rank 4)')
+        """reference :149-185: optimise (variance, lengthscale) on the model's data with the noise fixed, save kern[:] to
+        `kernel_file`, adopt the values.  Same objective as GPy's (exact log marginal likelihood; every evaluation is one
+        device factorisation), L-BFGS-B on the log-parameters with 2 random restarts; GPy's own restart randomisation
+        (un-vendored, unpinned) is not reproduced, so trained values agree with GPy's to optimiser tolerance, not bitwise."""
+        import scipy.optimize
+        if self.xvals is None or self.zvals is None:
+            raise ValueError('Failed to train kernel. No training data provided.')
+        want_linv = self._linv_d is not None
+
+        def objective(logp):
+            try:
+                self.kern[:] = np.exp(np.clip(logp, -20.0, 20.0))
+                self._factor(want_linv=want_linv)
+                val = -self.log_marginal_likelihood()
+            except np.linalg.LinAlgError:
+                return 1e25
+            return val if np.isfinite(val) else 1e25
+
+        start = np.log(self.kern[:])
+        best = None
+        for x0 in [start] + [np.random.normal(size=start.shape) for _ in range(2)]:
+            res = scipy.optimize.minimize(objective, x0, method='L-BFGS-B', options={'maxiter': 60})
+            if best is None or res.fun < best.fun:
+                best = res
+        objective(best.x)                                      # leave the model factored at the optimum
+        np.save(kernel_file, self.kern[:])
+        self.lengthscale = self.kern.lengthscale
+        self.variance = self.kern.variance
 
     # ------------------------------------------------------------------ deferred status checks
     def defer_checks(self, on=True):
