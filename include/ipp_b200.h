@@ -103,7 +103,8 @@ int ipp_gp_predict(const ipp_rbf* kern, const double* X, int64_t N, const double
                    const double* Xq, int64_t M, double* mean, double* var,
                    double* work, void* stream);
 
-/* ---- a3, 3xTF32 mode (BASELINE config 3 "FP64 vs 3xTF32"): the variance in GPy's Cholesky form,
+/* ---- a3, 3xTF32 mode (predict_value, gpmodel_library.py:303-328; BASELINE config 3 "FP64 vs 3xTF32"): the variance in
+ *      GPy's Cholesky form,
  *      var = variance - |Linv k|^2, on the tcgen05 tensor cores (kind::tf32, TMA-staged operands, TMEM
  *      accumulators).  Operands are split once as a = hi + lo (two TF32 numbers) and the contraction is
  *      hi*hi + hi*lo + lo*hi with FP32 accumulation; the mean stays FP64.  Variance error ~1e-6 of the PRIOR
@@ -120,7 +121,8 @@ int ipp_gp_predict_tf32(const ipp_rbf* kern, const double* X, int64_t N, const d
                         const float* linv_hi, const float* linv_lo, int64_t ldl, int acc_kblocks, double noise_add,
                         const double* Xq, int64_t M, double* mean, double* var, double* work, void* stream);
 
-/* ---- a3, sliced-INT8 mode: FP64-grade variance on the INT8 tensor cores (tcgen05 kind::i8, exact INT32 accumulation).
+/* ---- a3, sliced-INT8 mode (predict_value, gpmodel_library.py:303-328; GPy's Cholesky form of :82-103): FP64-grade
+ *      variance on the INT8 tensor cores (tcgen05 kind::i8, exact INT32 accumulation).
  *      Operands in fixed point against one power-of-two scale each, cut into six signed 7-bit slices; 21 slice-pair
  *      products (i + j <= 5) accumulate exactly, the six weight levels are combined in FP64.  Measured variance error
  *      ~2e-8 relative (inside the FP64 mode's 1e-6 parity tolerance); the mean is computed exactly as in FP64 mode.
