@@ -8,6 +8,7 @@ Drop-in for the reward-evaluation hot path of expeditionary-robotics/informative
   paths_library   : Path_Generator, Dubins_Path_Generator (restated without the `dubins` C library)
   ipp_library     : the legacy monolith's GPModel / rewards / get_reward seam
   envmodel_library: Environment (Gaussian world synthesis + sample_value)
+  evaluation_library: Evaluation (per-step metrics; regret sweeps over all candidate paths as batched device calls)
   parallel        : query / path sharding across the GPUs of one box (torch.distributed, NCCL)
 
 All numerics run in libipp_b200.so (hand-written CUDA for sm_100a, csrc/) behind the C ABI in

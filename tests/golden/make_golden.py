@@ -190,6 +190,46 @@ def case_myopic(gp, aq, pl):
                         offsets=offs, best=np.array(keys[int(np.argmax(vals))]))
 
 
+def case_evaluation(gp, aq, pl, ev):
+    """Evaluation.update_metrics (evaluation_library.py:262-314) for three evaluation rewards on one planning step:
+    a 10 x 10 gridded world model, a 36-observation robot belief, the 15-path frontier set of one pose."""
+    import types
+    rng = np.random.default_rng(77)
+    g = np.linspace(0.5, 9.5, 10)
+    gx, gy = np.meshgrid(g, g)
+    Xw = np.vstack([gx.ravel(), gy.ravel()]).T
+    zw = 10.0 * np.sin(0.7 * Xw[:, :1]) * np.cos(0.5 * Xw[:, 1:2]) + 3.0 * np.cos(1.3 * Xw[:, :1] + 0.4 * Xw[:, 1:2])
+    wm = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    wm.add_data(Xw, zw)
+    w = types.SimpleNamespace(dim=2, GP=wm, x1min=0., x1max=10., x2min=0., x2max=10.)
+    X, z = world(rng, 36, 1e-4)
+    m = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    m.add_data(X, z)
+    pg = pl.Path_Generator(15, 1.5, 0.05, 0.5, RANGES)
+    paths, true_paths = pg.get_path_set((4.0, 6.0, 1.1))
+    keys = sorted(paths.keys())
+    sel = paths[keys[11]]
+    max_loc = np.array([6.1, 2.2, 0.0])
+    max_val = 11.5
+    out = dict(Xw=Xw, zw=zw, X=X, z=z, keys=np.array(keys), sel=np.array(sel), max_loc=max_loc, max_val=max_val,
+               pts=np.array([pt for k in keys for pt in paths[k]]),
+               offsets=np.cumsum([0] + [len(paths[k]) for k in keys]))
+    names = ['simple_regret', 'sample_regret_loc', 'sample_regret_val', 'max_loc_error', 'max_val_error',
+             'instant_regret', 'max_val_regret', 'mes_reward_robot', 'mes_reward_omni', 'info_gain_reward', 'MSE',
+             'hotspot_error']
+    for rf in ('mean', 'hotspot_info', 'info_gain'):
+        with quiet():
+            e = ev.Evaluation(w, rf)
+        np.random.seed(5)
+        e.update_metrics(3, m, paths, sel, value=1.25, max_loc=max_loc, max_val=max_val,
+                         params=[7.0, (1.0, 2.0), None, None], dist=4.5)
+        out['metrics_' + rf] = np.array([float(e.metrics[n][3]) for n in names])
+        r, vs, vm = e.inst_regret(3, paths, sel, m)
+        out['regret_' + rf] = np.array([r, vs, vm], dtype=float)
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, 'evaluation.npz'), **out)
+
+
 def main():
     import tempfile
     os.chdir(tempfile.mkdtemp())          # the reference's visualize=True branches mkdir ./figures
@@ -206,6 +246,7 @@ def main():
     case_max_vals(gp, aq)
     case_mcts(gp, aq, mc, pl)
     case_myopic(gp, aq, pl)
+    case_evaluation(gp, aq, pl, ref_loader.load('evaluation_library'))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -201,3 +201,69 @@ def test_predict_max_matches_reference_loop(pkg):
     obs, _ = o.predict_value(data)
     np.testing.assert_allclose(loc, data[np.argmax(obs), :])
     np.testing.assert_allclose(val, np.max(obs), rtol=1e-9)
+
+
+# ------------------------------------------------------------------ metrics caller (evaluation_library.Evaluation)
+def _evaluation_case(pkg, g):
+    import types
+    wm = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    wm.add_data(g['Xw'], g['zw'])
+    w = types.SimpleNamespace(dim=2, GP=wm, x1min=0., x1max=10., x2min=0., x2max=10.)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    m.add_data(g['X'], g['z'])
+    offs = g['offsets']
+    paths = {int(k): [tuple(p) for p in g['pts'][offs[i]:offs[i + 1]]] for i, k in enumerate(g['keys'])}
+    return w, m, paths, [tuple(p) for p in g['sel']]
+
+
+@pytest.mark.parametrize('rf', ['mean', 'hotspot_info', 'info_gain'])
+def test_evaluation_update_metrics_golden(pkg, rf):
+    """One Evaluation.update_metrics step against the reference source's own output (tests/golden/evaluation.npz):
+    both regret sweeps are one batched device call each, the MSE / hotspot probes consume np.random identically."""
+    from conftest import load_golden
+    from informative_path_planning_b200.evaluation_library import Evaluation
+    g = load_golden('evaluation')
+    w, m, paths, sel = _evaluation_case(pkg, g)
+    e = Evaluation(w, rf)
+    np.random.seed(5)
+    e.update_metrics(3, m, paths, sel, value=1.25, max_loc=g['max_loc'], max_val=float(g['max_val']),
+                     params=[7.0, (1.0, 2.0), None, None], dist=4.5)
+    for name, want in zip(g['names'], g['metrics_' + rf]):
+        np.testing.assert_allclose(e.metrics[str(name)][3], want, rtol=1e-6, atol=1e-7, err_msg=str(name))
+    np.testing.assert_allclose(np.array(e.inst_regret(3, paths, sel, m), dtype=float), g['regret_' + rf], rtol=1e-6)
+    assert e.metrics['star_obs_0'][3] == -1. and e.metrics['distance_traveled'][3] == 4.5
+    assert e.metrics['robot_location_a'][3] == sel[0][2] and e.metrics['aquisition_function'][3] == 1.25
+
+
+def test_evaluation_batched_sweep_equals_per_path_calls(pkg, tmp_path):
+    """reward_all == [f_rew(p) for p in paths] for every GP-backed evaluation reward, with and without robot
+    observations; the CSV writer lays rows out as the reference's plot_metrics.  ('naive' / 'naive_value' only ever
+    get the -1 sentinels in update_metrics; their f_rew indexes a 1-D max_loc as 2-D in the reference and raises.)"""
+    from conftest import load_golden
+    from informative_path_planning_b200.evaluation_library import Evaluation
+    g = load_golden('evaluation')
+    w, m, paths, sel = _evaluation_case(pkg, g)
+    empty = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    plist = [paths[k] for k in sorted(paths)]
+    for rf in ('mean', 'mes', 'exp_improve', 'hotspot_info', 'info_gain'):
+        e = Evaluation(w, rf)
+        for model in (m, empty):
+            if rf == 'hotspot_info' and model is empty:
+                continue
+            batched = e.reward_all(3, plist, model)
+            single = np.array([e.f_rew(time=3, xvals=np.array(p), robot_model=model) for p in plist], dtype=float)
+            np.testing.assert_allclose(batched, single, rtol=1e-9, atol=1e-9, err_msg=rf)
+    with pytest.raises(ValueError):
+        Evaluation(w, 'no_such_reward')
+    e = Evaluation(w, 'mean')
+    for t in range(3):
+        np.random.seed(t)
+        e.update_metrics(t, m, paths, sel, value=0.5 * t, max_loc=g['max_loc'], max_val=float(g['max_val']),
+                         params=[7.0, (1.0, 2.0), [1.0, 2.0, 3.0], [(0, 1), (2, 3), (4, 5)]], dist=float(t))
+    out = e.plot_metrics(str(tmp_path))
+    rows = np.loadtxt(out + '/metrics.csv')
+    assert rows.shape == (21, 3)
+    np.testing.assert_allclose(rows[0], [0, 1, 2])
+    np.testing.assert_allclose(rows[2], np.cumsum([0.0, 0.5, 1.0]))
+    np.testing.assert_allclose(rows[10], np.cumsum([e.metrics['instant_regret'][t] for t in range(3)]))
+    assert np.loadtxt(out + '/stars.csv').shape == (9, 3)

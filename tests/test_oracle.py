@@ -229,3 +229,30 @@ def test_ctor_errors():
         OnlineGPModelOracle(RANGES, 1.0, 100.0, kernel='matern')
     with pytest.raises(ValueError):
         OnlineGPModelOracle(RANGES, (1.0, 1.0), 100.0, dimension=3)
+
+
+def _evaluation_case(g, model_cls, ev_cls):
+    import types
+    wm = model_cls(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    wm.add_data(g['Xw'], g['zw'])
+    w = types.SimpleNamespace(dim=2, GP=wm, x1min=0., x1max=10., x2min=0., x2max=10.)
+    m = model_cls(RANGES, 1.0, 100.0, noise=1e-4, dimension=2)
+    m.add_data(g['X'], g['z'])
+    offs = g['offsets']
+    paths = {int(k): [tuple(p) for p in g['pts'][offs[i]:offs[i + 1]]] for i, k in enumerate(g['keys'])}
+    sel = [tuple(p) for p in g['sel']]
+    return w, m, paths, sel, {rf: ev_cls(w, rf) for rf in ('mean', 'hotspot_info', 'info_gain')}
+
+
+@pytest.mark.parametrize('rf', ['mean', 'hotspot_info', 'info_gain'])
+def test_evaluation_metrics_match_reference(rf):
+    """Evaluation.update_metrics' prediction-dependent entries (evaluation_library.py:262-314)."""
+    from oracle.evaluation_oracle import EvaluationOracle
+    g = load_golden('evaluation')
+    w, m, paths, sel, evs = _evaluation_case(g, OnlineGPModelOracle, EvaluationOracle)
+    e = evs[rf]
+    np.random.seed(5)
+    got = e.step_metrics(3, m, paths, sel, g['max_loc'], float(g['max_val']))
+    for name, want in zip(g['names'], g['metrics_' + rf]):
+        np.testing.assert_allclose(got[str(name)], want, rtol=1e-7, atol=1e-9, err_msg=str(name))
+    np.testing.assert_allclose(np.array(e.inst_regret(3, paths, sel, m), dtype=float), g['regret_' + rf], rtol=1e-8)
