@@ -221,23 +221,46 @@ int ipp_info_gain_paths(const ipp_rbf* kern_v2 /* RBF with variance = v^2 */, co
                         const double* Xq, const int64_t* offsets, int64_t P, int64_t M,
                         double* logdet_out, int32_t* info, double* work, void* stream);
 
+/* ---- 8f (caller side): obstacle worlds (reference obstacles.py:26-195).  Every world of the reference is a union of
+ *      axis-aligned boxes, each optionally with a box-shaped hole (the inside of BugTrap, the opening of ChannelWorld):
+ *        in_obstacle((x, y), buff) = OR_b [ x > outer[0]-buff && x < outer[1]+buff && y > outer[2]-buff && y < outer[3]+buff
+ *                                           && !(has_hole && x >= hole[0]+hole_buff[0]*buff && x <= hole[1]+hole_buff[1]*buff
+ *                                                         && y >= hole[2]+hole_buff[2]*buff && y <= hole[3]+hole_buff[3]*buff) ]
+ *      (BlockWorld.in_obstacle :58-75, BugTrap.in_obstacle :145-163, ChannelWorld.in_obstacle :189-193; +-INFINITY for an
+ *      unbounded side).  The comparisons and the order of the floating-point operations are the reference's. */
+#define IPP_MAX_OBSTACLES 16
+typedef struct {
+    double outer[4];       /* x0, x1, y0, y1 (open box, grown by buff) */
+    double hole[4];        /* x0, x1, y0, y1 (closed box), used when has_hole != 0 */
+    double hole_buff[4];   /* -1, 0 or +1: how buff moves each hole edge */
+    int32_t has_hole;
+    int32_t reserved;
+} ipp_obstacle_box;
+
 /* ---- 8f (caller side): Dubins candidate paths on the HOST (no kernel) -- native replacement of the `dubins`
- *      C library calls + trimming loop of Dubins_Path_Generator.buffered_paths (paths_library.py:147-175),
- *      obstacle-free world.  All pointers are host memory.  pose[3], goals[G][3], extent[4];
+ *      C library calls + trimming loop of Dubins_Path_Generator.buffered_paths (paths_library.py:147-175).
+ *      All pointers are host memory.  pose[3], goals[G][3], extent[4];
+ *      obstacles[n_obstacles] (may be NULL / 0 = FreeWorld): the dense sweep stops at the first configuration inside an
+ *      obstacle (buff 0), a kept sample within `border` of an obstacle trims like one within `border` of the extent
+ *      (the reference passes buff = 3 * turning radius = border for both);
  *      samp[G][max_samp][3] / samp_count[G]: kept sample points (0 = path dropped);
  *      dense[G][max_dense][3] / dense_count[G]: dense path up to the last kept point; dense may be NULL (the tree search
- *      only needs the kept samples and the end pose: interior paths then evaluate one configuration in keep_every). */
+ *      only needs the kept samples and the end pose: interior paths of an obstacle-free world then evaluate one
+ *      configuration in keep_every). */
 int ipp_dubins_path_set(const double* pose, const double* goals, int G, double rho, double dense_step,
                         int keep_every, const double* extent, double border,
+                        const ipp_obstacle_box* obstacles, int n_obstacles,
                         double* samp, int* samp_count, int max_samp,
                         double* dense, int* dense_count, int max_dense);
 
 /* ---- 8f (caller side), device form for large batches (BASELINE config 5: 64k candidate paths): one thread per
  *      independent (start pose, goal pose) pair, same closed forms and trimming as ipp_dubins_path_set.
  *      poses[P][3], goals[P][3], samp[P][max_samp][3], counts[P] (int32, 0 = dropped), end_pose[P][3] (may be NULL;
- *      the last kept configuration = pose of the next belief node) are DEVICE pointers; extent[4] is host. */
+ *      the last kept configuration = pose of the next belief node) are DEVICE pointers; extent[4] and
+ *      obstacles[n_obstacles <= IPP_MAX_OBSTACLES] are host (passed to the kernel by value). */
 int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P, double rho, double dense_step,
                             int keep_every, const double* extent_host, double border,
+                            const ipp_obstacle_box* obstacles_host, int n_obstacles,
                             double* samp, int32_t* counts, int max_samp, double* end_pose, void* stream);
 
 #ifdef __cplusplus

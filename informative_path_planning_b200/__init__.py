@@ -6,6 +6,7 @@ Drop-in for the reward-evaluation hot path of expeditionary-robotics/informative
                     sample_max_vals, global_maximization, general_target  (+ batched reward_paths)
   mcts_library    : cMCTS, Tree, BeliefTree, Node    (tree logic on the host, rewards on the GPU)
   paths_library   : Path_Generator, Dubins_Path_Generator (restated without the `dubins` C library)
+  obstacles       : FreeWorld, BlockWorld, BugTrap, ChannelWorld (in_obstacle + box lists for the native path generators)
   ipp_library     : the legacy monolith's GPModel / rewards / get_reward seam
   envmodel_library: Environment (Gaussian world synthesis + sample_value)
   evaluation_library: Evaluation (per-step metrics; regret sweeps over all candidate paths as batched device calls)

@@ -72,8 +72,8 @@ SIGNATURES = {
     'ipp_potrf_workspace': (_I64, [_I64]),
     'ipp_potrf_lower': (_INT, [_P, _I64, _I64, _P, _P, _P, _P]),
     'ipp_info_gain_workspace': (_I64, [_I64, _I64]),
-    'ipp_dubins_path_set': (_INT, [_P, _P, _INT, _D, _D, _INT, _P, _D, _P, _P, _INT, _P, _P, _INT]),
-    'ipp_dubins_paths_device': (_INT, [_P, _P, _I64, _D, _D, _INT, _P, _D, _P, _P, _INT, _P, _P]),
+    'ipp_dubins_path_set': (_INT, [_P, _P, _INT, _D, _D, _INT, _P, _D, _P, _INT, _P, _P, _INT, _P, _P, _INT]),
+    'ipp_dubins_paths_device': (_INT, [_P, _P, _I64, _D, _D, _INT, _P, _D, _P, _INT, _P, _P, _INT, _P, _P]),
     'ipp_info_gain_paths': (_INT, [_RBF, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _P, _P, _P, _P]),
 }
 

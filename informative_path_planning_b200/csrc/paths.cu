@@ -3,7 +3,7 @@
 // thread per path, sharing the closed forms below through __host__ __device__ functions.
 // (1): the native counterpart of the `dubins` C library
 // the reference calls from paths_library.py:141-175 (dubins.shortest_path + path.sample_many), plus the
-// border trimming of Dubins_Path_Generator.buffered_paths for the obstacle-free world.
+// border / obstacle trimming of Dubins_Path_Generator.buffered_paths (obstacle worlds as box-with-hole lists).
 // Classical six-word closed form (LSL, RSR, LSR, RSL, RLR, LRL; Shkel & Lumelsky 2001).
 #include <math.h>
 #include "internal.cuh"
@@ -55,12 +55,28 @@ __host__ __device__ inline void segment(double& x, double& y, double& th, double
 }
 
 
+struct ObstacleSet { ipp_obstacle_box box[IPP_MAX_OBSTACLES]; int n; };
+
+// reference obstacles.py:58-75 / :145-163 / :189-193 in the box-with-hole form of include/ipp_b200.h
+__host__ __device__ inline bool in_obstacle(const ipp_obstacle_box* obs, int n, double x, double y, double buff) {
+    for (int i = 0; i < n; ++i) {
+        const ipp_obstacle_box& b = obs[i];
+        if (x > b.outer[0] - buff && x < b.outer[1] + buff && y > b.outer[2] - buff && y < b.outer[3] + buff) {
+            if (b.has_hole && x >= b.hole[0] + b.hole_buff[0] * buff && x <= b.hole[1] + b.hole_buff[1] * buff &&
+                y >= b.hole[2] + b.hole_buff[2] * buff && y <= b.hole[3] + b.hole_buff[3] * buff)
+                continue;
+            return true;
+        }
+    }
+    return false;
+}
+
 // One (pose, goal) pair.  dense (may be NULL on the device path): every configuration; samp: the kept ones.
 // Returns the number of kept samples (0 = path dropped); *dense_n = number of dense configurations of the true path;
 // end[3] = its last configuration (the pose of the next belief node).
 __host__ __device__ int dubins_one(const double* pose, const double* q1, double rho, double dense_step, int keep_every,
-                                   const double* extent, double border, double* sg, int max_samp,
-                                   double* dg, int max_dense, int* dense_n, double* end) {
+                                   const double* extent, double border, const ipp_obstacle_box* obs, int n_obs,
+                                   double* sg, int max_samp, double* dg, int max_dense, int* dense_n, double* end) {
     const double dx = q1[0] - pose[0], dy = q1[1] - pose[1];
     const double D = hypot(dx, dy), d = D / rho;
     const double theta = D > 0 ? mod2pi(atan2(dy, dx)) : 0.0;
@@ -95,9 +111,12 @@ __host__ __device__ int dubins_one(const double* pose, const double* q1, double 
     const double margin = total + 1e-9;
     const bool interior = pose[0] - extent[0] > margin && extent[1] - pose[0] > margin &&
                           pose[1] - extent[2] > margin && extent[3] - pose[1] > margin;
-    const int stride = (dg == nullptr && interior) ? keep_every : 1;
+    const int stride = (dg == nullptr && interior && n_obs == 0) ? keep_every : 1;
+    // arc length advances by repeated addition, as the `dubins` library's sample_many does (x += stepSize while
+    // x < length): whether the configuration AT the path's end is sampled is decided by the same rounding
+    double s = 0.0;
     for (int si = 0; nd < max_dense; si += stride, nd += stride - 1) {
-        const double s = si * dense_step;
+        if (si) for (int a = 0; a < stride; ++a) s += dense_step;
         if (!(s < total)) break;
         double rem = s / rho;
         int k = 0;
@@ -108,6 +127,7 @@ __host__ __device__ int dubins_one(const double* pose, const double* q1, double 
         segment(x, y, th, use, wb.kinds[k]);
         const double cx = x * rho + pose[0], cy = y * rho + pose[1];
         if (!(cx > extent[0] && cx < extent[1] && cy > extent[2] && cy < extent[3])) break;
+        if (n_obs && in_obstacle(obs, n_obs, cx, cy, 0.0)) break;
         const double cth = mod2pi(th);
         if (dg) { dg[3 * nd] = cx; dg[3 * nd + 1] = cy; dg[3 * nd + 2] = cth; }
         if (si % keep_every == 0 && orig < max_samp) {
@@ -119,7 +139,8 @@ __host__ __device__ int dubins_one(const double* pose, const double* q1, double 
     cur = orig;
     for (int m = 0; m < orig; ++m) {
         const double* c = sg + 3 * m;
-        if (c[0] <= extent[0] + border || c[0] >= extent[1] - border || c[1] <= extent[2] + border || c[1] >= extent[3] - border) {
+        if (c[0] <= extent[0] + border || c[0] >= extent[1] - border || c[1] <= extent[2] + border || c[1] >= extent[3] - border ||
+            (n_obs && in_obstacle(obs, n_obs, c[0], c[1], border))) {
             int stop = m - 1;                       // python: ttemp = ttemp[0:m-1]
             if (stop < 0) stop = cur + stop;        // negative stop counts from the end
             if (stop < 0) stop = 0;
@@ -141,7 +162,8 @@ __host__ __device__ int dubins_one(const double* pose, const double* q1, double 
 
 __global__ void dubins_paths_kernel(const double* __restrict__ poses, const double* __restrict__ goals, int64_t P,
                                     double rho, double dense_step, int keep_every, double e0, double e1, double e2,
-                                    double e3, double border, double* __restrict__ samp, int32_t* __restrict__ counts,
+                                    double e3, double border, const __grid_constant__ ObstacleSet obs,
+                                    double* __restrict__ samp, int32_t* __restrict__ counts,
                                     int max_samp, double* __restrict__ end_pose) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
@@ -150,8 +172,8 @@ __global__ void dubins_paths_kernel(const double* __restrict__ poses, const doub
     const double goal[3] = {goals[3 * p], goals[3 * p + 1], goals[3 * p + 2]};
     int dense_n = 0;
     double end[3] = {pose[0], pose[1], pose[2]};
-    const int n = dubins_one(pose, goal, rho, dense_step, keep_every, extent, border, samp + p * max_samp * 3, max_samp,
-                             nullptr, 1 << 30, &dense_n, end);
+    const int n = dubins_one(pose, goal, rho, dense_step, keep_every, extent, border, obs.box, obs.n,
+                             samp + p * max_samp * 3, max_samp, nullptr, 1 << 30, &dense_n, end);
     counts[p] = n;
     if (end_pose) { end_pose[3 * p] = end[0]; end_pose[3 * p + 1] = end[1]; end_pose[3 * p + 2] = end[2]; }
 }
@@ -165,14 +187,16 @@ __global__ void dubins_paths_kernel(const double* __restrict__ poses, const doub
 // dense_count[g] then is meaningless.  Arrays are host memory: samp [G][max_samp][3], dense [G][max_dense][3].
 extern "C" int ipp_dubins_path_set(const double* pose, const double* goals, int G, double rho, double dense_step,
                                    int keep_every, const double* extent, double border,
+                                   const ipp_obstacle_box* obstacles, int n_obstacles,
                                    double* samp, int* samp_count, int max_samp,
                                    double* dense, int* dense_count, int max_dense) {
     IPP_CHECK_ARG(pose && goals && extent && samp && samp_count && dense_count, "null pointer");
     IPP_CHECK_ARG(G >= 0 && rho > 0 && dense_step > 0 && keep_every >= 1 && max_samp >= 2 && max_dense >= 2, "bad argument");
+    IPP_CHECK_ARG(n_obstacles >= 0 && (n_obstacles == 0 || obstacles), "bad obstacle list");
     for (int gi = 0; gi < G; ++gi) {
         int dn = 0;
         samp_count[gi] = dubins_one(pose, goals + 3 * gi, rho, dense_step, keep_every, extent, border,
-                                    samp + (size_t)gi * max_samp * 3, max_samp,
+                                    obstacles, n_obstacles, samp + (size_t)gi * max_samp * 3, max_samp,
                                     dense ? dense + (size_t)gi * max_dense * 3 : nullptr, max_dense, &dn, nullptr);
         dense_count[gi] = dn;
     }
@@ -182,14 +206,20 @@ extern "C" int ipp_dubins_path_set(const double* pose, const double* goals, int 
 // ---- 8f rank 2: the same generator on the device, one thread per (pose, goal) pair.
 extern "C" int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P, double rho, double dense_step,
                                        int keep_every, const double* extent_host, double border,
+                                       const ipp_obstacle_box* obstacles_host, int n_obstacles,
                                        double* samp, int32_t* counts, int max_samp, double* end_pose, void* stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(poses && goals && extent_host && samp && counts, "null pointer");
     IPP_CHECK_ARG(P >= 0 && rho > 0 && dense_step > 0 && keep_every >= 1 && max_samp >= 2, "bad argument");
+    IPP_CHECK_ARG(n_obstacles >= 0 && n_obstacles <= IPP_MAX_OBSTACLES && (n_obstacles == 0 || obstacles_host),
+                  "bad obstacle list (at most IPP_MAX_OBSTACLES boxes)");
     if (P == 0) return IPP_OK;
+    ObstacleSet obs;
+    obs.n = n_obstacles;
+    for (int i = 0; i < n_obstacles; ++i) obs.box[i] = obstacles_host[i];
     dubins_paths_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(poses, goals, P, rho, dense_step, keep_every,
                                                                    extent_host[0], extent_host[1], extent_host[2],
-                                                                   extent_host[3], border, samp, counts, max_samp, end_pose);
+                                                                   extent_host[3], border, obs, samp, counts, max_samp, end_pose);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

@@ -13,7 +13,7 @@ import logging
 import numpy as np
 
 from .gpmodel_library import GPModel
-from .paths_library import FreeWorld
+from .obstacles import FreeWorld
 
 logger = logging.getLogger('robot')
 

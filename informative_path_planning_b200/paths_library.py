@@ -7,24 +7,14 @@ Dubins_Path_Generator  reference :141-189  shortest Dubins curves to the frontie
 
 The Dubins solver below is the classical six-word closed form (LSL, LSR, RSL, RSR, RLR, LRL; Shkel & Lumelsky
 2001), the algorithm the `dubins` package wraps; shortest word wins.  Obstacle worlds are the reference's
-FreeWorld contract: any object with in_obstacle(point, buff) -> bool.
+FreeWorld contract: any object with in_obstacle(point, buff) -> bool; the worlds of this package's obstacles.py also
+expose boxes(), which keeps them on the native / device generators.
 """
 import math
 
 import numpy as np
 
-
-class FreeWorld(object):
-    """reference obstacles.py:16-24"""
-
-    def __init__(self):
-        self.obstacles = []
-
-    def in_obstacle(self, point, buff=0.1):
-        return False
-
-    def get_obstacles(self):
-        return []
+from .obstacles import FreeWorld, box_array  # noqa: F401  (FreeWorld re-exported: reference paths_library uses obs.FreeWorld)
 
 
 class LazyPath(object):
@@ -209,8 +199,9 @@ def dubins_sample_many(q0, word, params, rho, step):
     """Configurations every `step` along the path (the `dubins` package's sample_many), vectorised over the
     arc-length samples: returns an (n, 3) array of (x, y, heading)."""
     total = sum(params) * rho
-    n = int(math.ceil(total / step - 1e-12)) if total > 0 else 0
-    s = np.arange(n) * step
+    n = int(math.ceil(total / step)) + 2 if total > 0 else 0
+    # x += step while x < length, as the library does: the accumulated rounding decides whether the end point is sampled
+    s = np.concatenate([[0.0], np.cumsum(np.full(max(n - 1, 0), float(step)))])[:n]
     s = s[s < total]
     rem = s / rho
     x = np.zeros_like(rem)
@@ -228,14 +219,25 @@ def dubins_sample_many(q0, word, params, rho, step):
 
 
 class Dubins_Path_Generator(Path_Generator):
-    """reference :141-189.  In the obstacle-free world the whole path set of a pose is produced by one native
-    call (ipp_dubins_path_set, the counterpart of the `dubins` C library the reference uses); obstacle worlds
-    keep the Python loop below, which is also the cross-check of the native code (tests/test_abi.py)."""
+    """reference :141-189.  The whole path set of a pose is produced by one native call (ipp_dubins_path_set, the
+    counterpart of the `dubins` C library the reference uses) for every obstacle world that can state itself as a
+    box list (obstacles.py: FreeWorld, BlockWorld, BugTrap, ChannelWorld); any other duck-typed world keeps the
+    Python loop below, which is also the cross-check of the native code (tests/test_abi.py)."""
 
     use_native = True
 
+    def _obstacle_boxes(self):
+        """(ctypes box array or None, count) of the obstacle world, or None when it cannot be stated as boxes."""
+        cached = self.__dict__.get('_boxes')
+        if cached is not None and cached[0] is self.obstacle_world:
+            return cached[1]
+        fn = getattr(self.obstacle_world, 'boxes', None)
+        out = box_array(fn()) if callable(fn) else None
+        self._boxes = (self.obstacle_world, out)
+        return out
+
     def buffered_paths(self, lazy=False):
-        if self.use_native and isinstance(self.obstacle_world, FreeWorld) and len(self.goals) > 0:
+        if self.use_native and len(self.goals) > 0 and self._obstacle_boxes() is not None:
             return self._buffered_paths_native(lazy)
         return self._buffered_paths_python()
 
@@ -272,8 +274,9 @@ class Dubins_Path_Generator(Path_Generator):
         nb['goals'][:G] = self.goals
         nb['pose'][:] = self.cp
         P = nb['ptr']
+        boxes, n_boxes = self._obstacle_boxes()
         L.check(L.lib.ipp_dubins_path_set(P['pose'], P['goals'], G, float(self.tr), float(self.ss / 10), 10, P['ext'],
-                                          float(3 * self.tr), P['samp'], P['ns'], nb['max_samp'],
+                                          float(3 * self.tr), boxes, n_boxes, P['samp'], P['ns'], nb['max_samp'],
                                           None if lazy else P['dense'], P['nd'], nb['max_dense']))
         ns = nb['ns'][:G].tolist()
         samp = nb['samp'].tolist()
@@ -304,9 +307,10 @@ class Dubins_Path_Generator(Path_Generator):
         pose_a, goal_a = np.asarray(pose, dtype=np.float64).copy(), np.asarray(goal, dtype=np.float64).reshape(1, 3).copy()
         ext = np.asarray(self.extent, dtype=np.float64).copy()
         vp = ctypes.c_void_p
+        boxes, n_boxes = self._obstacle_boxes()
         L.check(L.lib.ipp_dubins_path_set(pose_a.ctypes.data_as(vp), goal_a.ctypes.data_as(vp), 1, float(self.tr),
                                           float(self.ss / 10), 10, ext.ctypes.data_as(vp), float(3 * self.tr),
-                                          samp.ctypes.data_as(vp), ns.ctypes.data_as(vp), max_samp,
+                                          boxes, n_boxes, samp.ctypes.data_as(vp), ns.ctypes.data_as(vp), max_samp,
                                           dense.ctypes.data_as(vp), nd.ctypes.data_as(vp), max_dense))
         return [tuple(c) for c in dense[0, :int(nd[0])].tolist()]
 
@@ -341,9 +345,10 @@ class Dubins_Path_Generator(Path_Generator):
         return coords, true_coords
 
 
-def dubins_paths_device(poses, goals, turning_radius, sample_step, extent, max_samples=32):
+def dubins_paths_device(poses, goals, turning_radius, sample_step, extent, max_samples=32, obstacle_world=None):
     """Batched candidate-path generation on the GPU (BASELINE config 5): one Dubins path per (pose, goal) row with the
-    reference generator's sampling (dense step ss/10, every 10th kept) and border trimming (paths_library.py:147-175).
+    reference generator's sampling (dense step ss/10, every 10th kept) and border / obstacle trimming
+    (paths_library.py:147-175); obstacle_world: None or a world with boxes() (obstacles.py, at most 16 boxes).
     poses, goals: (P, 3) arrays or CUDA tensors.  Returns CUDA tensors (samples (P, max_samples, 3), counts (P,) int32,
     end_poses (P, 3)); counts[p] == 0 means the path was dropped (fewer than 2 samples survive)."""
     import ctypes
@@ -355,8 +360,11 @@ def dubins_paths_device(poses, goals, turning_radius, sample_step, extent, max_s
     counts = torch.empty(P, dtype=torch.int32, device=poses_d.device)
     end = torch.empty((P, 3), dtype=torch.float64, device=poses_d.device)
     ext = (ctypes.c_double * 4)(*[float(e) for e in extent])
+    if obstacle_world is not None and not callable(getattr(obstacle_world, 'boxes', None)):
+        raise TypeError('dubins_paths_device needs an obstacle world with boxes() (informative_path_planning_b200.obstacles)')
+    boxes, n_boxes = box_array(obstacle_world.boxes()) if obstacle_world is not None else (None, 0)
     L.check(L.lib.ipp_dubins_paths_device(L.ptr(poses_d), L.ptr(goals_d), P, float(turning_radius), float(sample_step) / 10,
-                                          10, ext, float(3 * turning_radius), L.ptr(samp), L.ptr(counts), int(max_samples),
+                                          10, ext, float(3 * turning_radius), boxes, n_boxes, L.ptr(samp), L.ptr(counts), int(max_samples),
                                           L.ptr(end), L.stream_ptr()))
     return samp, counts, end
 

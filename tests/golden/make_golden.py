@@ -230,6 +230,66 @@ def case_evaluation(gp, aq, pl, ev):
     np.savez_compressed(os.path.join(HERE, 'evaluation.npz'), **out)
 
 
+def case_obstacles(ob, pl):
+    """obstacles.py in_obstacle predicates (:58-75, :145-163, :189-193) on random points and buffers -- including points
+    placed exactly on the (buffered) edges -- and Dubins_Path_Generator.buffered_paths (paths_library.py:147-175)
+    in a block world.  `dubins` is absent: the reference loop runs on the restated closed-form solver through a small
+    adapter with the dubins package's two calls."""
+    rng = np.random.default_rng(9)
+    ext = [0., 10., 0., 10.]
+    with quiet():
+        worlds = {'block': ob.BlockWorld(ext, num_blocks=3, dim_blocks=(2., 1.5), centers=[(3., 3.), (7., 6.5), (2.5, 8.)]),
+                  'trap_left': ob.BugTrap(ext, (3., 3.), 2., 0.5, 2., 'left'),
+                  'trap_right': ob.BugTrap(ext, (7., 6.), 1.5, 0.25, 3., 'right'),
+                  'channel': ob.ChannelWorld(ext, (5., 4.), 3., 2.)}
+    pts = rng.uniform(-1, 11, (3000, 2))
+    edges = np.array([1.5, 2.0, 2.25, 2.5, 3.0, 3.5, 3.75, 4.0, 4.5, 5.0, 5.25, 5.5, 5.75, 6.0, 6.5, 6.75, 7.0, 7.25, 7.5,
+                      8.0, 8.75, 0.0, 10.0])
+    grid = np.array([(a, b) for a in edges for b in edges])
+    pts = np.vstack([pts, grid])
+    buffs = np.array([0.0, 0.1, 0.25, 0.5, 1.5])
+    out = dict(pts=pts, buffs=buffs)
+    for name, w in worlds.items():
+        out[name] = np.array([[bool(w.in_obstacle((p[0], p[1]), buff=b)) for p in pts] for b in buffs])
+
+    import types
+    from informative_path_planning_b200 import paths_library as mine      # closed-form solver only (host numpy)
+
+    class _Path(object):
+        def __init__(self, q0, q1, rho):
+            self.q0, self.rho = q0, rho
+            self.word, self.params = mine.dubins_shortest_path(q0, q1, rho)
+
+        def sample_many(self, step):
+            cfg = mine.dubins_sample_many(self.q0, self.word, self.params, self.rho, step)
+            return [tuple(c) for c in cfg.tolist()], None
+
+    saved = pl.dubins
+    pl.dubins = types.SimpleNamespace(shortest_path=_Path)
+    try:
+        poses = [(1.2, 1.0, 0.3), (4.6, 2.4, 1.9), (5.2, 5.1, 2.6), (8.6, 8.2, 4.0), (2.2, 6.0, 1.2), (6.0, 3.3, 5.5)]
+        out['poses'] = np.array(poses)
+        for name in ('block', 'trap_left', 'channel'):
+            with quiet():
+                pg = pl.Dubins_Path_Generator(15, 1.5, 0.05, 0.5, ext, worlds[name])
+            for pi, pose in enumerate(poses):
+                with quiet():
+                    paths, true_paths = pg.get_path_set(pose)
+                ns = np.zeros(len(pg.goals), dtype=np.int64)
+                nd = np.zeros(len(pg.goals), dtype=np.int64)
+                flat = []
+                for i in range(len(pg.goals)):
+                    if i in paths:
+                        ns[i], nd[i] = len(paths[i]), len(true_paths[i])
+                        flat.extend(paths[i])
+                tag = 'dubins_%s_%d_' % (name, pi)
+                out[tag + 'ns'], out[tag + 'nd'] = ns, nd
+                out[tag + 'pts'] = np.array(flat).reshape(-1, 3)
+    finally:
+        pl.dubins = saved
+    np.savez_compressed(os.path.join(HERE, 'obstacles.npz'), **out)
+
+
 def main():
     import tempfile
     os.chdir(tempfile.mkdtemp())          # the reference's visualize=True branches mkdir ./figures
@@ -247,6 +307,7 @@ def main():
     case_mcts(gp, aq, mc, pl)
     case_myopic(gp, aq, pl)
     case_evaluation(gp, aq, pl, ref_loader.load('evaluation_library'))
+    case_obstacles(ref_loader.load('obstacles'), pl)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

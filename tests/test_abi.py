@@ -132,3 +132,72 @@ def test_lazy_dense_paths_equal_eager_ones():
         for k in ta:
             assert ta[k] == tb[k].tolist() == list(tb[k]) and ta[k][-1] == tb[k][-1] and len(ta[k]) == len(tb[k])
             assert ta[k][2:5] == tb[k][2:5]
+
+
+def _golden_worlds():
+    from informative_path_planning_b200 import obstacles as ob
+    ext = [0., 10., 0., 10.]
+    return {'block': ob.BlockWorld(ext, num_blocks=3, dim_blocks=(2., 1.5), centers=[(3., 3.), (7., 6.5), (2.5, 8.)]),
+            'trap_left': ob.BugTrap(ext, (3., 3.), 2., 0.5, 2., 'left'),
+            'trap_right': ob.BugTrap(ext, (7., 6.), 1.5, 0.25, 3., 'right'),
+            'channel': ob.ChannelWorld(ext, (5., 4.), 3., 2.)}
+
+
+def test_obstacle_worlds_match_reference_predicates():
+    """in_obstacle of every world, and the box-with-hole list the native generators evaluate, against the reference
+    source's own answers (tests/golden/obstacles.npz: random points + points exactly on the buffered edges)."""
+    import numpy as np
+    from conftest import load_golden
+    from informative_path_planning_b200 import obstacles as ob
+    g = load_golden('obstacles')
+    for name, w in _golden_worlds().items():
+        boxes = w.boxes()
+        for bi, buff in enumerate(g['buffs']):
+            got = np.array([w.in_obstacle((p[0], p[1]), buff=float(buff)) for p in g['pts']])
+            via_boxes = np.array([ob.in_boxes(boxes, p, float(buff)) for p in g['pts']])
+            assert np.array_equal(got, g[name][bi]), (name, buff)
+            assert np.array_equal(via_boxes, g[name][bi]), (name, buff)
+    assert ctypes.sizeof(ob.IppObstacleBox) == 104
+    free = ob.FreeWorld()
+    assert free.boxes() == [] and not free.in_obstacle((1, 1)) and free.get_obstacles() == []
+    np.random.seed(3)
+    a = ob.BlockWorld([0., 10., 0., 10.], num_blocks=2)
+    np.random.seed(3)
+    want = [tuple(10 * np.random.random_sample(2)) for _ in range(2)]
+    np.testing.assert_allclose(np.array(a.get_centers()), np.array(want))
+
+
+def test_native_dubins_path_sets_in_obstacle_worlds():
+    """ipp_dubins_path_set with an obstacle list == the reference's trimming loop (golden: the reference source run on
+    the closed-form solver) == this package's Python loop; lazy dense paths agree as well."""
+    import numpy as np
+    from conftest import load_golden
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    g = load_golden('obstacles')
+    worlds = _golden_worlds()
+    for name in ('block', 'trap_left', 'channel'):
+        for pi, pose in enumerate(g['poses']):
+            pose = tuple(float(v) for v in pose)
+            nat = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], worlds[name])
+            py = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], worlds[name])
+            py.use_native = False
+            (pa, ta), (pb, tb) = nat.get_path_set(pose), py.get_path_set(pose)
+            tag = 'dubins_%s_%d_' % (name, pi)
+            ns, nd, flat = g[tag + 'ns'], g[tag + 'nd'], g[tag + 'pts']
+            assert sorted(pa) == sorted(pb) == [i for i in range(len(ns)) if ns[i] > 0], (name, pose)
+            off = 0
+            for k in sorted(pa):
+                assert len(pa[k]) == ns[k] and len(ta[k]) == len(tb[k]) == nd[k], (name, pose, k)
+                np.testing.assert_allclose(np.array(pa[k]), flat[off:off + ns[k]], rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(np.array(pa[k]), np.array(pb[k]), rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(np.array(ta[k]), np.array(tb[k]), rtol=1e-12, atol=1e-12)
+                off += ns[k]
+            pl_, tl_ = nat.get_path_set_lazy(pose)
+            assert pl_ == pa and all(tl_[k].tolist() == ta[k] for k in ta)
+
+    class Duck(object):                          # a world without boxes() keeps working through the Python loop
+        def in_obstacle(self, point, buff=0.1):
+            return worlds['block'].in_obstacle(point, buff)
+    duck = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], Duck())
+    ref = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], worlds['block'])
+    assert duck.get_path_set((4.6, 2.4, 1.9))[0].keys() == ref.get_path_set((4.6, 2.4, 1.9))[0].keys()

@@ -690,23 +690,19 @@ def test_predict_tf32x3_mode_against_fp64_mode(pkg, N, M):
     assert np.abs(v_a - v_b).max() <= 1e-3
 
 
-def test_dubins_paths_on_device_match_host_generator(pkg):
-    """ipp_dubins_paths_device (one thread per (pose, goal)) against the host generator (itself checked against the
-    Python restatement of paths_library.py:147-175 in test_abi): same kept-sample counts, same points, same end pose,
-    including poses near the walls where the trimming quirk bites; then rewards of the ragged result."""
-    from informative_path_planning_b200.paths_library import Dubins_Path_Generator, dubins_paths_device, ragged_points
-    rng = np.random.default_rng(21)
+def _device_vs_host_paths(world_obj, seed, n_poses=60):
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator, dubins_paths_device
+    rng = np.random.default_rng(seed)
     poses, goals, want = [], [], []
-    for _ in range(60):
+    for _ in range(n_poses):
         pose = (float(rng.uniform(0.3, 9.7)), float(rng.uniform(0.3, 9.7)), float(rng.uniform(-np.pi, np.pi)))
-        g = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES)
+        g = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES, world_obj)
         paths, true_paths = g.get_path_set(pose)
         for i, goal in enumerate(g.goals):
             poses.append(pose); goals.append(goal)
             want.append((paths.get(i), true_paths[i][-1] if i in true_paths else None))
-    samp, counts, end = dubins_paths_device(np.array(poses), np.array(goals), 0.05, 0.5, RANGES)
+    samp, counts, end = dubins_paths_device(np.array(poses), np.array(goals), 0.05, 0.5, RANGES, obstacle_world=world_obj)
     samp, counts, end = samp.cpu().numpy(), counts.cpu().numpy(), end.cpu().numpy()
-    assert len(want) > 700 and (counts == 0).sum() > 10 and (counts > 0).sum() > 500
     ties = 0
     for p, (pts, last) in enumerate(want):
         n_host = 0 if pts is None else len(pts)
@@ -724,6 +720,38 @@ def test_dubins_paths_on_device_match_host_generator(pkg):
         np.testing.assert_allclose(samp[p, :counts[p]], np.array(pts), rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(end[p], np.array(last), rtol=1e-12, atol=1e-12)
     assert ties <= len(want) // 12            # at most the straight-ahead goal of each pose (1 in 15)
+    return poses, goals, counts
+
+
+@pytest.mark.parametrize('kind', ['block', 'trap_left', 'trap_right', 'channel'])
+def test_dubins_paths_on_device_in_obstacle_worlds(pkg, kind):
+    """The device generator trims against the reference's obstacle worlds (obstacles.py:58-75, :145-163, :189-193 as
+    box-with-hole lists) exactly as the host generator does -- which test_abi pins to the reference's own trimming loop
+    -- and drops clearly more paths than the free world."""
+    from informative_path_planning_b200 import obstacles as ob
+    from informative_path_planning_b200.paths_library import dubins_paths_device
+    ext = list(RANGES)
+    w = {'block': lambda: ob.BlockWorld(ext, num_blocks=3, dim_blocks=(2., 1.5), centers=[(3., 3.), (7., 6.5), (2.5, 8.)]),
+         'trap_left': lambda: ob.BugTrap(ext, (3., 3.), 2., 0.5, 2., 'left'),
+         'trap_right': lambda: ob.BugTrap(ext, (7., 6.), 1.5, 0.25, 3., 'right'),
+         'channel': lambda: ob.ChannelWorld(ext, (5., 4.), 3., 2.)}[kind]()
+    poses, goals, counts = _device_vs_host_paths(w, seed=33)
+    _, free_counts, _ = dubins_paths_device(np.array(poses), np.array(goals), 0.05, 0.5, RANGES)
+    free_counts = free_counts.cpu().numpy()
+    assert (counts > free_counts).sum() == 0 and (counts < free_counts).sum() > 20
+    many = ob.BlockWorld(ext, num_blocks=17, centers=[(0.5 * i, 1.0) for i in range(17)])
+    with pytest.raises(pkg._lib.IppError):
+        dubins_paths_device(np.array(poses[:4]), np.array(goals[:4]), 0.05, 0.5, RANGES, obstacle_world=many)
+
+
+def test_dubins_paths_on_device_match_host_generator(pkg):
+    """ipp_dubins_paths_device (one thread per (pose, goal)) against the host generator (itself checked against the
+    Python restatement of paths_library.py:147-175 in test_abi): same kept-sample counts, same points, same end pose,
+    including poses near the walls where the trimming quirk bites; then rewards of the ragged result."""
+    from informative_path_planning_b200.paths_library import dubins_paths_device, ragged_points
+    poses, goals, counts = _device_vs_host_paths(None, seed=21)
+    assert len(poses) > 700 and (counts == 0).sum() > 10 and (counts > 0).sum() > 500
+    rng = np.random.default_rng(21)
     # ragged layout -> one reward call for all kept paths
     X, z = world(rng, 200, 0.5)
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
