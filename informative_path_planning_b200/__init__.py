@@ -9,6 +9,7 @@ Drop-in for the reward-evaluation hot path of expeditionary-robotics/informative
   obstacles       : FreeWorld, BlockWorld, BugTrap, ChannelWorld (in_obstacle + box lists for the native path generators)
   ipp_library     : the legacy monolith's GPModel / rewards / get_reward seam
   envmodel_library: Environment (Gaussian world synthesis + sample_value)
+  robot_library   : Robot (mission loop: predict_max, myopic choice in one device call or cMCTS, observe, append)
   evaluation_library: Evaluation (per-step metrics; regret sweeps over all candidate paths as batched device calls)
   parallel        : query / path sharding across the GPUs of one box (torch.distributed, NCCL)
 

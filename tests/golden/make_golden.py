@@ -290,6 +290,57 @@ def case_obstacles(ob, pl):
     np.savez_compressed(os.path.join(HERE, 'obstacles.npz'), **out)
 
 
+from mission_spec import (MISSION_METRICS, MISSIONS, mission_kwargs, mission_obstacles,  # noqa: E402
+                          mission_sample_world, mission_world)
+
+
+def case_missions(gp, pl, ob, ev, rb):
+    """Robot.planner (robot_library.py:256-337) of the reference source, metrics by its Evaluation: whole seeded
+    missions -- myopic and tree search, straight fan and Dubins (the absent `dubins` package replaced by the closed-form
+    solver adapter), free and obstacle worlds.  Recorded: the pose after every step, the final belief data, the
+    per-step metrics."""
+    import types
+    from informative_path_planning_b200 import paths_library as mine
+
+    class _Path(object):
+        def __init__(self, q0, q1, rho):
+            self.q0, self.rho = q0, rho
+            self.word, self.params = mine.dubins_shortest_path(q0, q1, rho)
+
+        def sample_many(self, step):
+            cfg = mine.dubins_sample_many(self.q0, self.word, self.params, self.rho, step)
+            return [tuple(c) for c in cfg.tolist()], None
+
+    saved = pl.dubins
+    pl.dubins = types.SimpleNamespace(shortest_path=_Path)
+    out = {}
+    try:
+        for name, spec in MISSIONS.items():
+            with quiet():
+                world_obs = mission_obstacles(ob, spec[4])
+                e = ev.Evaluation(mission_world(gp.OnlineGPModel), spec[0])
+                np.random.seed(11)
+                random.seed(12)
+                r = rb.Robot(**mission_kwargs(name, e, world_obs, mission_sample_world))
+                locs = []
+                orig = r.collect_observations
+
+                def spy(xobs, orig=orig, r=r, locs=locs):
+                    orig(xobs)
+                    locs.append(np.array(xobs[-1], dtype=float))
+                r.collect_observations = spy
+                with np.errstate(all='ignore'):
+                    r.planner(T=spec[5])
+            out[name + '_locs'] = np.array(locs)
+            out[name + '_end'] = np.array([float(v) for v in r.loc])
+            out[name + '_X'] = r.GP.xvals
+            out[name + '_z'] = r.GP.zvals
+            out[name + '_metrics'] = np.array([[float(e.metrics[n][t]) for n in MISSION_METRICS] for t in range(spec[5])])
+    finally:
+        pl.dubins = saved
+    np.savez_compressed(os.path.join(HERE, 'missions.npz'), **out)
+
+
 def main():
     import tempfile
     os.chdir(tempfile.mkdtemp())          # the reference's visualize=True branches mkdir ./figures
@@ -308,6 +359,7 @@ def main():
     case_myopic(gp, aq, pl)
     case_evaluation(gp, aq, pl, ref_loader.load('evaluation_library'))
     case_obstacles(ref_loader.load('obstacles'), pl)
+    case_missions(gp, pl, ref_loader.load('obstacles'), ref_loader.load('evaluation_library'), ref_loader.load('robot_library'))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

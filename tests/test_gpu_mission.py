@@ -267,3 +267,49 @@ def test_evaluation_batched_sweep_equals_per_path_calls(pkg, tmp_path):
     np.testing.assert_allclose(rows[2], np.cumsum([0.0, 0.5, 1.0]))
     np.testing.assert_allclose(rows[10], np.cumsum([e.metrics['instant_regret'][t] for t in range(3)]))
     assert np.loadtxt(out + '/stars.csv').shape == (9, 3)
+
+
+# ------------------------------------------------------------------ whole missions of the reference's Robot
+@pytest.mark.parametrize('name', ['myopic_mean_fan', 'myopic_mean_dubins_blocks', 'myopic_mes_fan', 'nonmyopic_mean_dpw',
+                                  'nonmyopic_mean_belief_dubins'])
+def test_robot_mission_reproduces_reference_run(pkg, name, tmp_path, monkeypatch):
+    """robot_library.Robot.planner + evaluation_library.Evaluation on the device against the SAME seeded mission run by
+    the reference's own Robot / Evaluation source (tests/golden/missions.npz): the pose after every step, every
+    observation (so the random streams stay in lock-step), and the per-step metrics."""
+    import os
+    import sys
+    from conftest import GOLDEN, load_golden
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import mission_spec as ms
+    from informative_path_planning_b200 import obstacles as ob
+    from informative_path_planning_b200.evaluation_library import Evaluation
+    from informative_path_planning_b200.robot_library import Robot
+    g = load_golden('missions')
+    spec = ms.MISSIONS[name]
+    monkeypatch.chdir(tmp_path)                                   # planner writes ./figures/<f_rew>/robot_model.csv
+    e = Evaluation(ms.mission_world(pkg.OnlineGPModel), spec[0])
+    np.random.seed(11)
+    random.seed(12)
+    r = Robot(**ms.mission_kwargs(name, e, ms.mission_obstacles(ob, spec[4]), ms.mission_sample_world))
+    locs = []
+    orig = r.collect_observations
+
+    def spy(xobs):
+        orig(xobs)
+        locs.append(np.array(xobs[-1], dtype=float))
+    r.collect_observations = spy
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+        r.planner(T=spec[5])
+    np.testing.assert_allclose(np.array(locs), g[name + '_locs'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(np.array([float(v) for v in r.loc]), g[name + '_end'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.GP.xvals, g[name + '_X'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.GP.zvals, g[name + '_z'], rtol=1e-9, atol=1e-9)
+    got = np.array([[float(e.metrics[n][t]) for n in ms.MISSION_METRICS] for t in range(spec[5])])
+    np.testing.assert_allclose(got, g[name + '_metrics'], rtol=2e-5, atol=1e-5)
+    assert os.path.exists(os.path.join('figures', spec[0], 'robot_model.csv'))
+    x1, x2, mean_grid, var_grid = r.visualize_world_model(screen=False)
+    assert mean_grid.shape == (100, 100) and np.isfinite(mean_grid).all() and (var_grid > 0).all()
+    if spec[0] == 'mean':
+        _, _, reward_grid = r.visualize_reward(t=3)
+        assert reward_grid.shape == (100, 100) and np.isfinite(reward_grid).all()
