@@ -415,18 +415,22 @@ class cMCTS(object):
         self.tree_type = tree_type
         self.c = exploration_constant(f_rew, tree_type)
 
-    def choose_trajectory(self, t):
+    def reward_param(self, t):
+        """The acquisition parameter of this planning step (reference :668-679); for MES / the naive rewards this draws
+        the max-value samples."""
         if self.f_rew == 'mes':
             self.max_val, self.max_locs, self.target = aqlib.sample_max_vals(self.GP, t=t, visualize=True)
-            param = (self.max_val, self.max_locs, self.target)
-        elif self.f_rew == 'exp_improve':
-            param = [self.current_max]
-        elif self.f_rew in ('naive', 'naive_value'):
+            return (self.max_val, self.max_locs, self.target)
+        if self.f_rew == 'exp_improve':
+            return [self.current_max]
+        if self.f_rew in ('naive', 'naive_value'):
             self.max_val, self.max_locs, self.target = aqlib.sample_max_vals(self.GP, t=t, nK=int(self.aq_param[0]),
                                                                              visualize=True, f_rew=self.f_rew)
-            param = ((self.max_val, self.max_locs, self.target), self.aq_param[1])
-        else:
-            param = None
+            return ((self.max_val, self.max_locs, self.target), self.aq_param[1])
+        return None
+
+    def search(self, t, param, budget=None):
+        """Build the tree and run `budget` rollouts (reference :681-695); returns the root's children."""
         if self.tree_type == 'dpw':
             tree_cls = Tree
         elif self.tree_type == 'belief':
@@ -435,17 +439,25 @@ class cMCTS(object):
             raise ValueError('Tree type must be one of either \'dpw\' or \'belief\'')
         self.tree = tree_cls(self.f_rew, self.aquisition_function, self.GP, self.cp, self.path_generator, t,
                              depth=self.rl, param=param, c=self.c)
-        for _ in range(self.comp_budget):
+        for _ in range(self.comp_budget if budget is None else budget):
             self.tree.get_next_leaf(copy.copy(self.GP))
-        most = max(n.nqueries for n in self.tree.root.children)
-        best_child = random.choice([node for node in self.tree.root.children if node.nqueries == most])
-        all_vals = {i: child.reward / float(child.nqueries) for i, child in enumerate(self.tree.root.children)}
+        return self.tree.root.children
+
+    def result(self, best_child, all_vals):
+        """The tuple choose_trajectory returns (reference :709-713)."""
         paths, dense_paths = self.path_generator.get_path_set(self.cp)
         best_dense = best_child.dense_path
         if hasattr(best_dense, 'tolist'):
             best_dense = best_dense.tolist()                  # the reference returns a list of (x, y, heading) tuples
-        return (best_child.action, best_dense, best_child.reward / float(best_child.nqueries), paths,
+        return (best_child.action, best_dense, all_vals[self.tree.root.children.index(best_child)], paths,
                 all_vals, self.max_locs, self.max_val, self.target)
+
+    def choose_trajectory(self, t):
+        children = self.search(t, self.reward_param(t))
+        most = max(n.nqueries for n in children)
+        best_child = random.choice([node for node in children if node.nqueries == most])
+        all_vals = {i: child.reward / float(child.nqueries) for i, child in enumerate(children)}
+        return self.result(best_child, all_vals)
 
 
 # ------------------------------------------------------------------------------------------ batched seams

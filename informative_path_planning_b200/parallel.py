@@ -128,3 +128,50 @@ def reward_paths_sharded(model, f_rew, time, queries, offsets, param=None, rewar
     dev = _comm_device() if size > 1 else torch.device('cpu')
     out = gather_concat(torch.from_numpy(local).to(dev), counts)
     return out.cpu().numpy()
+
+
+def mcts_root_parallel(mcts, t, seed=None):
+    """Root-parallel tree search for one planning step (rollouts per rank).
+
+    Every rank holds the replicated belief and runs its OWN tree (mcts_library.cMCTS.search) on its GPU with
+    computation_budget / world_size rollouts and its own random stream; the root statistics (visit count and reward
+    sum per root action: <= 16 x 2 doubles) are summed with ONE all_reduce and every rank picks the same action: most
+    visits, ties by mean reward, then by index.  The candidate paths of the root pose are deterministic, so the root
+    actions line up across ranks.  The acquisition parameter (MES max-value samples) is drawn from an identically
+    seeded stream on every rank, so it is the same everywhere without shipping the sampled functions.
+
+    This is a different search from the reference's single sequential tree (the ranks do not see each other's
+    statistics while searching), so it is an opt-in mode; with world_size 1 it IS mcts.choose_trajectory(t).
+    Returns the tuple of cMCTS.choose_trajectory."""
+    import random
+    rank, size = world()
+    if size == 1:
+        return mcts.choose_trajectory(t)
+    dev = _comm_device()
+    if seed is None:                                             # agree on a seed: rank 0 draws it
+        s = torch.tensor([np.random.randint(0, 2 ** 31 - 1) if rank == 0 else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(s, 0)
+        seed = int(s.item())
+    np.random.seed(seed % (2 ** 32))
+    random.seed(seed)
+    param = mcts.reward_param(t)                                 # same draws on every rank
+    np.random.seed((seed + 7919 * (rank + 1)) % (2 ** 32))
+    random.seed(seed + 7919 * (rank + 1))
+    lo, hi = shard_bounds(mcts.comp_budget, rank, size)
+    children = mcts.search(t, param, budget=hi - lo)
+    stats = torch.tensor([[float(c.nqueries), float(c.reward)] for c in children], dtype=torch.float64, device=dev)
+    count = torch.tensor([stats.shape[0]], dtype=torch.int64, device=dev)
+    lo_c, hi_c = count.clone(), count.clone()
+    dist.all_reduce(lo_c, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_c, op=dist.ReduceOp.MAX)
+    if int(lo_c.item()) != int(hi_c.item()):
+        raise RuntimeError('root actions differ across ranks (%d vs %d): the belief or the path generator is not '
+                           'replicated' % (int(lo_c.item()), int(hi_c.item())))
+    mcts.local_root_stats = stats.cpu().numpy().copy()
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    stats = stats.cpu().numpy()
+    visits, sums = stats[:, 0], stats[:, 1]
+    means = np.where(visits > 0, sums / np.maximum(visits, 1.0), 0.0)
+    order = sorted(range(len(children)), key=lambda i: (-visits[i], -means[i], i))
+    mcts.root_stats = stats
+    return mcts.result(children[order[0]], {i: float(means[i]) for i in range(len(children))})

@@ -50,6 +50,21 @@ def _worker(rank, size, port, tmp):
         out[mode + '_mu'], out[mode + '_var'] = mu, var
         out[mode + '_ucb'] = parallel.reward_paths_sharded(m, 'mean', 5, pts, offs)
         out[mode + '_mes'] = parallel.reward_paths_sharded(m, 'mes', 5, pts, offs, param=(np.array([[20.], [25.]]), None, None))
+    # root-parallel tree search (config 2 sharding): replicated belief, budget split, one all_reduce of root statistics
+    import contextlib
+    import io
+    from informative_path_planning_b200 import aq_library as aq, mcts_library as mc
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    pg = Dubins_Path_Generator(9, 1.5, 0.05, 0.5, RANGES)
+    for f_rew, fn in (('mean', aq.mean_UCB), ('mes', aq.mves)):
+        planner = mc.cMCTS(41, m, (5.0, 5.0, 0.3), 3, pg, fn, f_rew, 4, tree_type='dpw')
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            res = parallel.mcts_root_parallel(planner, 4, seed=77)
+        out['mcts_' + f_rew + '_action'] = np.array(res[0])
+        out['mcts_' + f_rew + '_global'] = planner.root_stats
+        np.save(os.path.join(tmp, 'mcts_%s_local%d.npy' % (f_rew, rank)), planner.local_root_stats)
+        if f_rew == 'mes':
+            out['mcts_mes_maxes'] = np.asarray(res[6])
     np.savez(os.path.join(tmp, 'rank%d.npz' % rank), **out)
     dist.destroy_process_group()
 
@@ -80,3 +95,10 @@ def test_two_ranks_match_one_gpu(tmp_path):
         np.testing.assert_array_equal(r0[mode + '_var'], var)
         np.testing.assert_allclose(r0[mode + '_ucb'], ucb, rtol=1e-12)
         np.testing.assert_allclose(r0[mode + '_mes'], mes, rtol=1e-12)
+    for f_rew in ('mean', 'mes'):
+        l0, l1 = np.load(tmp_path / ('mcts_%s_local0.npy' % f_rew)), np.load(tmp_path / ('mcts_%s_local1.npy' % f_rew))
+        g = r0['mcts_' + f_rew + '_global']
+        np.testing.assert_allclose(l0 + l1, g, rtol=1e-12)
+        assert l0[:, 0].sum() == 21 and l1[:, 0].sum() == 20 and not np.array_equal(l0, l1)
+        assert r0['mcts_' + f_rew + '_action'].shape[1] == 3
+    assert r0['mcts_mes_maxes'].shape == (3, 1)                       # same max-value samples on both ranks (checked above)

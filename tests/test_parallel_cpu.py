@@ -74,3 +74,59 @@ def test_gloo_world_size_2(tmp_path):
     np.testing.assert_allclose(r0[:P], r0[P:2 * P])
     np.testing.assert_array_equal(r0[2 * P:2 * P + 12], np.arange(12.0))
     np.testing.assert_array_equal(r0[2 * P + 12:], [0.0, 1.0, 1.0])
+
+
+def _mcts_worker(rank, size, port, tmp):
+    import contextlib
+    import io
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200 import parallel
+    from informative_path_planning_b200.paths_library import Path_Generator
+    from oracle import aq_oracle
+    from oracle.gpmodel_oracle import OnlineGPModelOracle
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 10, (30, 2))
+    z = np.sin(X[:, :1]) * 5 + rng.normal(0, 0.5, (30, 1))
+    m = OnlineGPModelOracle((0., 10., 0., 10.), 1.0, 100.0, noise=0.5, dimension=2)      # the replicated belief
+    m.add_data(X, z)
+    pg = Path_Generator(8, 1.5, 0.05, 0.5, (0., 10., 0., 10.))
+    out = {}
+    for f_rew, fn in (('mean', aq_oracle.mean_UCB), ('mes', aq_oracle.mves)):
+        planner = mc.cMCTS(31, m, (5., 5., 0.3), 3, pg, fn, f_rew, 2, tree_type='dpw')
+        if f_rew == 'mes':                            # host stand-in for the device max-value sampler: counts its draws
+            planner.reward_param = lambda t, planner=planner: (np.random.uniform(20, 30, (3, 1)), None, None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = parallel.mcts_root_parallel(planner, 2, seed=123 if f_rew == 'mean' else None)
+        out[f_rew + '_action'] = np.array(res[0])
+        out[f_rew + '_value'] = np.array([res[2]])
+        out[f_rew + '_all'] = np.array([res[4][i] for i in range(len(res[4]))])
+        out[f_rew + '_local'] = planner.local_root_stats
+        out[f_rew + '_global'] = planner.root_stats
+        out[f_rew + '_param'] = np.zeros(1) if planner.tree.param is None else np.asarray(planner.tree.param[0])
+    np.savez(os.path.join(tmp, 'mcts%d.npz' % rank), **out)
+    dist.destroy_process_group()
+
+
+def test_root_parallel_tree_search_gloo(tmp_path):
+    """parallel.mcts_root_parallel on 2 ranks: the rollout budget is split, each rank searches its own tree with its own
+    random stream, the root statistics are summed by one all_reduce and both ranks return the same action."""
+    port = _free_port()
+    mp.spawn(_mcts_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / 'mcts0.npz'), np.load(tmp_path / 'mcts1.npz')
+    for f_rew in ('mean', 'mes'):
+        for key in ('_action', '_value', '_all', '_global', '_param'):
+            np.testing.assert_array_equal(a[f_rew + key], b[f_rew + key])
+        np.testing.assert_allclose(a[f_rew + '_local'] + b[f_rew + '_local'], a[f_rew + '_global'])
+        assert a[f_rew + '_local'][:, 0].sum() == 16 and b[f_rew + '_local'][:, 0].sum() == 15      # 31 rollouts split
+        assert not np.array_equal(a[f_rew + '_local'], b[f_rew + '_local'])                      # different streams
+        g = a[f_rew + '_global']
+        means = g[:, 1] / g[:, 0]
+        best = sorted(range(len(g)), key=lambda i: (-g[i, 0], -means[i], i))[0]          # most visits, then mean reward
+        assert a[f_rew + '_value'][0] == means[best]
+        np.testing.assert_allclose(a[f_rew + '_all'], means)
+    assert a['mes_param'].shape == (3, 1)
