@@ -263,6 +263,67 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
                             const ipp_obstacle_box* obstacles_host, int n_obstacles,
                             double* samp, int32_t* counts, int max_samp, double* end_pose, void* stream);
 
+/* ---- a12 / 8f rank 1: one whole planning step of the DPW tree search on the host side of the library -- the walk,
+ *      the progressive widening, the Dubins candidate sets, the simulated observations and the random draws of
+ *      Tree.get_next_leaf / leaf_helper / get_next_child (mcts_library.py:347-455) in native code, with ONE
+ *      ipp_rollout_rewards launch sequence + one stream synchronisation per rollout.  Replaces the Python interpreter on
+ *      the per-rollout critical path; the search it performs is the SAME search: both random streams the reference
+ *      consumes are continued bit for bit --
+ *        py_rng: CPython's `random` Mersenne Twister (random.getstate(): 624 words + index); random.choice(seq) is
+ *                seq[_randbelow(len(seq))], getrandbits(bit_length(n)) = genrand_uint32() >> (32 - k) redrawn while >= n;
+ *        np_rng: numpy's legacy global RandomState (np.random.get_state(): 624 words, pos, has_gauss, cached_gaussian);
+ *                standard_normal = the polar method over genrand_res53 pairs with the second variate cached --
+ *      and written back, so the caller's interpreter continues the streams where the search stopped.
+ *      Simulated observations are prior draws z_i = gauss_i * prior_scale[k][i] (np.random.multivariate_normal(0,
+ *      variance I_k), mcts_library.py:418-422, whose SVD transform of a scaled identity is a constant diagonal).
+ *      Candidate paths: frontier goals pose + horizon (cos, sin)(heading + angles[i]) (paths_library.py:44-83) joined by
+ *      shortest Dubins curves, sampled and trimmed as ipp_dubins_path_set does.
+ *      status[0]: 0 = done; 1 = a rollout could not be scored in one call (block not positive definite, or more than
+ *      IPP_ROLLOUT_MAX_POINTS / LEVELS) -- nothing is written back and the caller must run its own search from the
+ *      unchanged random states.  root_goal / root_visits / root_reward [frontier_size + 1]: the root's action children in
+ *      creation order (goal index, visit count, reward sum); n_root[0] of them.  reward_evals[0]: path rewards scored.
+ *      stage_host: PINNED host scratch, stage_dev: device scratch, each >= IPP_TREE_STAGE_DOUBLES doubles;
+ *      work: ipp_rollout_workspace(N, IPP_ROLLOUT_MAX_POINTS) doubles on the device. */
+#define IPP_TREE_STAGE_DOUBLES (IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1) + IPP_ROLLOUT_MAX_LEVELS + 16)
+typedef struct {
+    uint32_t key[624];
+    int32_t pos;
+    int32_t has_gauss;     /* numpy only */
+    double gauss;          /* numpy only */
+} ipp_mt_state;
+typedef struct {
+    int32_t budget;        /* rollouts */
+    int32_t max_depth;     /* rollout_length */
+    int32_t kind;          /* IPP_REWARD_UCB / EI / MES */
+    int32_t frontier_size;
+    int32_t keep_every;    /* 10 */
+    int32_t n_obstacles;
+    double c;              /* exploration constant (mcts_library.py:645-660) */
+    double reward_param;   /* sqrt(beta_t) or eta */
+    double time;           /* third query column when the kernel has 3 dimensions */
+    double horizon, turning_radius, dense_step, border;
+    double extent[4];
+    const double* angles;             /* [frontier_size] host */
+    const ipp_obstacle_box* obstacles;/* [n_obstacles] host, may be NULL */
+    const double* prior_scale;        /* [IPP_APPEND_MAX_K + 1][IPP_APPEND_MAX_K] host */
+} ipp_tree_params;
+int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
+                        const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                        const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                        const double* maxes_dev, int64_t S,
+                        ipp_mt_state* py_rng, ipp_mt_state* np_rng,
+                        double* stage_host, double* stage_dev, double* work,
+                        int32_t* n_root, int32_t* root_goal, int64_t* root_visits, double* root_reward,
+                        int64_t* reward_evals, int32_t* status, void* stream);
+/* test hooks for the two generators (host only, no device): out[i] = random.choice(range(ns[i])) /
+ * out[i] = np.random.standard_normal() continued from the given state, which is advanced. */
+int ipp_rng_py_choices(ipp_mt_state* py_rng, const int32_t* ns, int count, int32_t* out);
+int ipp_rng_np_normals(ipp_mt_state* np_rng, int count, double* out);
+/* test hook: the candidate path set of one pose as the tree search builds it (host only): goals kept by the frontier
+ * rule, then ipp_dubins_path_set; returns per kept path its goal index, sample count and samples [..][max_samp][3]. */
+int ipp_tree_path_set(const ipp_tree_params* prm, const double* pose, int32_t* n_paths, int32_t* goal_index,
+                      int32_t* samp_count, double* samp, int max_samp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,53 @@ class IppRbf(ctypes.Structure):
                 ('inv_lengthscale', ctypes.c_double * IPP_MAX_DIM)]
 
 
+class IppMtState(ctypes.Structure):
+    """MT19937 state of CPython's `random` or numpy's legacy global RandomState (include/ipp_b200.h: ipp_mt_state)."""
+    _fields_ = [('key', ctypes.c_uint32 * 624), ('pos', ctypes.c_int32), ('has_gauss', ctypes.c_int32),
+                ('gauss', ctypes.c_double)]
+
+
+class IppTreeParams(ctypes.Structure):
+    _fields_ = [('budget', ctypes.c_int32), ('max_depth', ctypes.c_int32), ('kind', ctypes.c_int32),
+                ('frontier_size', ctypes.c_int32), ('keep_every', ctypes.c_int32), ('n_obstacles', ctypes.c_int32),
+                ('c', ctypes.c_double), ('reward_param', ctypes.c_double), ('time', ctypes.c_double),
+                ('horizon', ctypes.c_double), ('turning_radius', ctypes.c_double), ('dense_step', ctypes.c_double),
+                ('border', ctypes.c_double), ('extent', ctypes.c_double * 4),
+                ('angles', ctypes.c_void_p), ('obstacles', ctypes.c_void_p), ('prior_scale', ctypes.c_void_p)]
+
+
+IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 32 + 16
+
+
+def py_rng_state():
+    """CPython `random` state -> IppMtState (and the trailing gauss_next, which the search never touches)."""
+    import random
+    version, internal, gauss_next = random.getstate()
+    st = IppMtState()
+    st.key[:] = internal[:624]
+    st.pos = internal[624]
+    return st, (version, gauss_next)
+
+
+def set_py_rng_state(st, extra):
+    import random
+    random.setstate((extra[0], tuple(st.key) + (int(st.pos),), extra[1]))
+
+
+def np_rng_state():
+    """numpy legacy global RandomState -> IppMtState."""
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    st = IppMtState()
+    ctypes.memmove(st.key, np.ascontiguousarray(key, dtype=np.uint32).ctypes.data, 624 * 4)
+    st.pos, st.has_gauss, st.gauss = int(pos), int(has_gauss), float(cached)
+    return st
+
+
+def set_np_rng_state(st):
+    key = np.frombuffer(bytes(st.key), dtype=np.uint32).copy()
+    np.random.set_state(('MT19937', key, int(st.pos), int(st.has_gauss), float(st.gauss)))
+
+
 class IppError(RuntimeError):
     pass
 
@@ -74,6 +121,12 @@ SIGNATURES = {
     'ipp_info_gain_workspace': (_I64, [_I64, _I64]),
     'ipp_dubins_path_set': (_INT, [_P, _P, _INT, _D, _D, _INT, _P, _D, _P, _INT, _P, _P, _INT, _P, _P, _INT]),
     'ipp_dubins_paths_device': (_INT, [_P, _P, _I64, _D, _D, _INT, _P, _D, _P, _INT, _P, _P, _INT, _P, _P]),
+    'ipp_tree_search_dpw': (_INT, [ctypes.POINTER(IppTreeParams), _P, _RBF, _P, _I64, _P, _P, _I64, _D, _D, _P, _I64,
+                                   ctypes.POINTER(IppMtState), ctypes.POINTER(IppMtState), _P, _P, _P, _P, _P, _P, _P, _P,
+                                   _P, _P]),
+    'ipp_rng_py_choices': (_INT, [ctypes.POINTER(IppMtState), _P, _INT, _P]),
+    'ipp_rng_np_normals': (_INT, [ctypes.POINTER(IppMtState), _INT, _P]),
+    'ipp_tree_path_set': (_INT, [ctypes.POINTER(IppTreeParams), _P, _P, _P, _P, _P, _INT]),
     'ipp_info_gain_paths': (_INT, [_RBF, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _P, _P, _P, _P]),
 }
 

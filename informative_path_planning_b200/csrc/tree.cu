@@ -1,0 +1,361 @@
+// Native DPW tree search for one planning step (include/ipp_b200.h: ipp_tree_search_dpw).
+//
+// What runs here is the host side of the reference's Tree (mcts_library.py:314-488): get_next_leaf / leaf_helper (the
+// walk), get_next_child (DPW-UCT), build_action_children (frontier goals + Dubins candidate paths, shared with
+// paths.cu through dubins.cuh), the progressive-widening rule and the simulated prior observations of the 'BA' step,
+// and backprop -- with the two random streams the reference consumes (CPython's `random`, numpy's legacy global
+// RandomState) continued bit for bit, so that the search is the one the interpreter would have run.  Rewards: one
+// ipp_rollout_rewards launch sequence per rollout (rollout.cu), inputs staged through pinned memory, one stream
+// synchronisation per rollout (back-propagation needs the value before the next selection).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "dubins.cuh"
+#include "internal.cuh"
+
+namespace {
+
+using namespace ipp_dubins;
+
+// ---- MT19937, the generator under both `random` and numpy's legacy RandomState
+struct Mt {
+    uint32_t* mt;
+    int32_t* pos;
+    void regen() {
+        const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAG = 0x9908b0dfu;
+        int kk = 0;
+        uint32_t y;
+        for (; kk < 624 - 397; ++kk) {
+            y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+        }
+        for (; kk < 623; ++kk) {
+            y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+        }
+        y = (mt[623] & UPPER) | (mt[0] & LOWER);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+        *pos = 0;
+    }
+    uint32_t next() {
+        if (*pos >= 624) regen();
+        uint32_t y = mt[(*pos)++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+};
+
+// random.choice(seq) -> index: seq[_randbelow(len(seq))], _randbelow_with_getrandbits (CPython Lib/random.py)
+inline int py_choice(Mt& g, int n) {
+    int k = 0;
+    for (unsigned v = (unsigned)n; v; v >>= 1) ++k;          // n.bit_length()
+    uint32_t r = g.next() >> (32 - k);
+    while (r >= (uint32_t)n) r = g.next() >> (32 - k);
+    return (int)r;
+}
+
+// numpy legacy: random_standard_normal of the global RandomState = legacy_gauss (polar method, cached second variate)
+inline double np_double(Mt& g) {
+    const int32_t a = (int32_t)(g.next() >> 5), b = (int32_t)(g.next() >> 6);
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+inline double np_gauss(Mt& g, ipp_mt_state* st) {
+    if (st->has_gauss) {
+        const double t = st->gauss;
+        st->has_gauss = 0;
+        st->gauss = 0.0;
+        return t;
+    }
+    double f, x1, x2, r2;
+    do {
+        x1 = 2.0 * np_double(g) - 1.0;
+        x2 = 2.0 * np_double(g) - 1.0;
+        r2 = x1 * x1 + x2 * x2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    f = sqrt(-2.0 * log(r2) / r2);
+    st->gauss = f * x1;
+    st->has_gauss = 1;
+    return f * x2;
+}
+
+// ---- candidate paths of one pose: Path_Generator.generate_frontier_points (paths_library.py:44-83) + buffered_paths
+struct PathSet {
+    std::vector<int32_t> goal;       // goal index of each kept path
+    std::vector<int32_t> count;      // kept samples
+    std::vector<double> samp;        // [path][max_samp][3]
+    int max_samp = 0;
+};
+
+int path_limits(const ipp_tree_params& p, int* max_samp) {
+    const double longest = p.horizon + 8.0 * 3.14159265358979323846 * p.turning_radius;   // hl + a few turning circles
+    const int max_dense = (int)(longest / p.dense_step) + 16;
+    *max_samp = max_dense / p.keep_every + 2;
+    return max_dense;
+}
+
+void build_path_set(const ipp_tree_params& p, const double* cp, PathSet& out) {
+    const int fs = p.frontier_size;
+    std::vector<double> goals((size_t)(fs + 1) * 3);
+    int G = 0;
+    const double cx = cp[0], cy = cp[1], ch = cp[2], hl = p.horizon, tr = p.turning_radius;
+    const double x_lo = p.extent[0] + 3 * tr, x_hi = p.extent[1] - 3 * tr;
+    const double y_lo = p.extent[2] + 3 * tr, y_hi = p.extent[3] - 3 * tr;
+    for (int i = 0; i < fs; ++i) {
+        const double a = ch + p.angles[i];
+        const double x = hl * cos(a) + cx, y = hl * sin(a) + cy;
+        if (sqrt((cx - x) * (cx - x) + (cy - y) * (cy - y)) <= tr) continue;
+        if (x > x_hi || x < x_lo) continue;
+        if (y > y_hi || y < y_lo) continue;
+        goals[3 * G] = x; goals[3 * G + 1] = y; goals[3 * G + 2] = a;
+        ++G;
+    }
+    goals[3 * G] = cx; goals[3 * G + 1] = cy; goals[3 * G + 2] = ch;       // the pose itself closes the goal list
+    ++G;
+    int max_samp = 0;
+    const int max_dense = path_limits(p, &max_samp);
+    out.max_samp = max_samp;
+    out.goal.clear(); out.count.clear(); out.samp.clear();
+    std::vector<double> tmp((size_t)max_samp * 3);
+    for (int gi = 0; gi < G; ++gi) {
+        int dn = 0;
+        const int n = dubins_one(cp, &goals[3 * gi], tr, p.dense_step, p.keep_every, p.extent, p.border, p.obstacles,
+                                 p.n_obstacles, tmp.data(), max_samp, nullptr, max_dense, &dn, nullptr);
+        if (n < 2) continue;
+        out.goal.push_back(gi);
+        out.count.push_back(n);
+        out.samp.insert(out.samp.end(), tmp.begin(), tmp.end());
+    }
+}
+
+// ---- the tree
+struct Node {
+    bool action = false;            // 'BA' (an action of its parent belief node) or 'B'
+    bool has_children = false;      // python: children is not None
+    int depth = 0;
+    int parent = -1;
+    int goal = -1;                  // action nodes: goal index in the parent's path set
+    int k = 0;                      // action nodes: sample points; belief nodes: length of zvals
+    size_t data = 0;                // action nodes: offset of samp[k][3] in the pool; belief nodes: offset of zvals[k]
+    double pose[3] = {0, 0, 0};
+    double end[3] = {0, 0, 0};      // action nodes: last kept sample (pose of the belief children)
+    int64_t nq = 0;
+    double reward = 0.0;
+    std::vector<int> children;
+};
+
+bool valid_params(const ipp_tree_params* p) {
+    return p && p->angles && p->prior_scale && p->budget >= 0 && p->max_depth >= 1 && p->frontier_size >= 1 &&
+           p->keep_every >= 1 && p->turning_radius > 0 && p->dense_step > 0 && p->n_obstacles >= 0 &&
+           p->n_obstacles <= IPP_MAX_OBSTACLES && (p->n_obstacles == 0 || p->obstacles);
+}
+
+}  // namespace
+
+extern "C" int ipp_rng_py_choices(ipp_mt_state* py_rng, const int32_t* ns, int count, int32_t* out) {
+    IPP_CHECK_ARG(py_rng && ns && out && count >= 0, "bad argument");
+    Mt g{py_rng->key, &py_rng->pos};
+    for (int i = 0; i < count; ++i) {
+        IPP_CHECK_ARG(ns[i] >= 1, "choice from an empty sequence");
+        out[i] = py_choice(g, ns[i]);
+    }
+    return IPP_OK;
+}
+
+extern "C" int ipp_rng_np_normals(ipp_mt_state* np_rng, int count, double* out) {
+    IPP_CHECK_ARG(np_rng && out && count >= 0, "bad argument");
+    Mt g{np_rng->key, &np_rng->pos};
+    for (int i = 0; i < count; ++i) out[i] = np_gauss(g, np_rng);
+    return IPP_OK;
+}
+
+extern "C" int ipp_tree_path_set(const ipp_tree_params* prm, const double* pose, int32_t* n_paths, int32_t* goal_index,
+                                 int32_t* samp_count, double* samp, int max_samp) {
+    IPP_CHECK_ARG(valid_params(prm) && pose && n_paths && goal_index && samp_count && samp, "bad argument");
+    PathSet ps;
+    build_path_set(*prm, pose, ps);
+    IPP_CHECK_ARG(max_samp >= ps.max_samp, "max_samp too small");
+    *n_paths = (int32_t)ps.goal.size();
+    for (size_t i = 0; i < ps.goal.size(); ++i) {
+        goal_index[i] = ps.goal[i];
+        samp_count[i] = ps.count[i];
+        memcpy(samp + i * (size_t)max_samp * 3, &ps.samp[i * (size_t)ps.max_samp * 3], sizeof(double) * 3 * ps.count[i]);
+    }
+    return IPP_OK;
+}
+
+extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
+                                   const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                                   const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                                   const double* maxes_dev, int64_t S,
+                                   ipp_mt_state* py_rng, ipp_mt_state* np_rng,
+                                   double* stage_host, double* stage_dev, double* work,
+                                   int32_t* n_root, int32_t* root_goal, int64_t* root_visits, double* root_reward,
+                                   int64_t* reward_evals, int32_t* status, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(valid_params(prm), "bad tree parameters");
+    IPP_CHECK_ARG(root_pose && kern && X && alpha && winv && py_rng && np_rng && stage_host && stage_dev && work, "null pointer");
+    IPP_CHECK_ARG(n_root && root_goal && root_visits && root_reward && reward_evals && status, "null output pointer");
+    IPP_CHECK_ARG(N >= 1 && (kern->dim == 2 || kern->dim == 3), "needs a belief with data, 2 or 3 input dimensions");
+    IPP_CHECK_ARG(prm->kind == IPP_REWARD_UCB || prm->kind == IPP_REWARD_EI || prm->kind == IPP_REWARD_MES, "unknown reward kind");
+    const ipp_tree_params& P = *prm;
+    const int D = kern->dim;
+    // work on copies of the generators: they are only written back when the whole search succeeded
+    ipp_mt_state py = *py_rng, np = *np_rng;
+    Mt gpy{py.key, &py.pos}, gnp{np.key, &np.pos};
+
+    std::vector<Node> nodes;
+    nodes.reserve((size_t)P.budget * (2 * P.max_depth + 2) + 64);
+    std::vector<double> pool;
+    pool.reserve(1 << 16);
+    PathSet ps;
+    nodes.emplace_back();
+    memcpy(nodes[0].pose, root_pose, sizeof(double) * 3);
+
+    struct Level { int node; size_t z; int k; int reps; };
+    std::vector<Level> levels;
+    std::vector<int> ties;
+    int64_t evals = 0;
+    *status = 0;
+    double* h_in = stage_host;                                                   // [M][D] points, then [M] observations
+    double* h_out = stage_host + IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1);      // [L] rewards + info
+    double* d_in = stage_dev;
+    double* d_out = stage_dev + IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1);
+    const double params_host[1] = {P.reward_param};
+
+    for (int it = 0; it < P.budget; ++it) {
+        // ---- leaf_helper: walk down, recording the (points, observation, appends) of every action step
+        levels.clear();
+        int cur = 0;
+        while (true) {
+            if (!nodes[cur].action) {
+                if (nodes[cur].depth == P.max_depth) break;
+                if (!nodes[cur].has_children) {                                   // build_action_children
+                    build_path_set(P, nodes[cur].pose, ps);
+                    for (size_t i = 0; i < ps.goal.size(); ++i) {
+                        Node a;
+                        a.action = true;
+                        a.depth = nodes[cur].depth;
+                        a.parent = cur;
+                        a.goal = ps.goal[i];
+                        a.k = ps.count[i];
+                        a.data = pool.size();
+                        const double* sp = &ps.samp[i * (size_t)ps.max_samp * 3];
+                        pool.insert(pool.end(), sp, sp + 3 * a.k);
+                        memcpy(a.pose, nodes[cur].pose, sizeof(double) * 3);
+                        memcpy(a.end, sp + 3 * (a.k - 1), sizeof(double) * 3);
+                        nodes[cur].children.push_back((int)nodes.size());
+                        nodes.push_back(a);
+                    }
+                    nodes[cur].has_children = !ps.goal.empty();
+                }
+                if (!nodes[cur].has_children) break;
+                // get_next_child: first unvisited child, else DPW-UCT with exact-equality ties -> random.choice
+                const Node& b = nodes[cur];
+                const double e_d = 0.5 * (1.0 - (3.0 / (10.0 * (P.max_depth - b.depth))));
+                int pick = -1;
+                double top = 0.0;
+                ties.clear();
+                for (int ci : b.children) {
+                    const Node& ch = nodes[ci];
+                    if (ch.nq == 0) { pick = ci; break; }
+                    const double v = ch.reward / (double)ch.nq + P.c * sqrt(pow((double)b.nq, e_d) / (double)ch.nq);
+                    if (ties.empty() || v > top) { top = v; ties.clear(); ties.push_back(ci); }
+                    else if (v == top) ties.push_back(ci);
+                }
+                if (pick < 0) pick = ties[py_choice(gpy, (int)ties.size())];
+                cur = pick;
+            } else {
+                // _record_action: re-use a child (progressive widening) or simulate a new observation
+                Node& a = nodes[cur];
+                int child = -1;
+                if (a.has_children) {
+                    const double al = 3.0 / (10.0 * (P.max_depth - a.depth) - 3.0);
+                    const int nchild = (int)a.children.size();
+                    if (a.depth < P.max_depth - 1 && floor(pow((double)nchild, al)) == floor(pow((double)(nchild - 1), al))) {
+                        py_choice(gpy, nchild);                                    // draw consumed, result unused (:408)
+                        int64_t fewest = nodes[a.children[0]].nq;
+                        for (int ci : a.children) if (nodes[ci].nq < fewest) fewest = nodes[ci].nq;
+                        ties.clear();
+                        for (int ci : a.children) if (nodes[ci].nq == fewest) ties.push_back(ci);
+                        child = ties[py_choice(gpy, (int)ties.size())];
+                        levels.push_back({cur, nodes[child].data, a.k, 1});
+                    }
+                }
+                if (child < 0) {
+                    if (a.k > IPP_APPEND_MAX_K) { *status = 1; return IPP_OK; }
+                    Node bnode;
+                    bnode.depth = a.depth + 1;
+                    bnode.parent = cur;
+                    bnode.k = a.k;
+                    bnode.data = pool.size();
+                    memcpy(bnode.pose, a.end, sizeof(double) * 3);
+                    const double* sc = P.prior_scale + (size_t)a.k * IPP_APPEND_MAX_K;
+                    for (int i = 0; i < a.k; ++i) pool.push_back(np_gauss(gnp, &np) * sc[i]);
+                    child = (int)nodes.size();
+                    levels.push_back({cur, bnode.data, a.k, 2});
+                    nodes.push_back(bnode);                                        // may move `a`: not used below
+                    nodes[cur].children.push_back(child);
+                    nodes[cur].has_children = true;
+                }
+                cur = child;
+            }
+        }
+        // ---- settle: all rewards of the rollout in one device pass
+        double reward = 0.0;
+        const int L = (int)levels.size();
+        if (L > 0) {
+            int M = 0;
+            for (const Level& lv : levels) M += lv.k;
+            if (L > IPP_ROLLOUT_MAX_LEVELS || M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }
+            int32_t offsets[IPP_ROLLOUT_MAX_LEVELS + 1], reps[IPP_ROLLOUT_MAX_LEVELS];
+            int row = 0;
+            for (int l = 0; l < L; ++l) {
+                const Node& a = nodes[levels[l].node];
+                offsets[l] = row;
+                reps[l] = levels[l].reps;
+                for (int i = 0; i < a.k; ++i, ++row) {
+                    h_in[(size_t)row * D] = pool[a.data + 3 * i];
+                    h_in[(size_t)row * D + 1] = pool[a.data + 3 * i + 1];
+                    if (D == 3) h_in[(size_t)row * D + 2] = P.time;
+                    h_in[(size_t)M * D + row] = pool[levels[l].z + i];
+                }
+            }
+            offsets[L] = M;
+            IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * (D + 1), cudaMemcpyHostToDevice, stream));
+            const int rc = ipp_rollout_rewards(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
+                                               maxes_dev, S, d_in, d_in + (size_t)M * D, offsets, reps, L, d_out,
+                                               reinterpret_cast<int32_t*>(d_out + L), work, stream_);
+            if (rc != IPP_OK) return rc;
+            IPP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * (size_t)(L + 1), cudaMemcpyDeviceToHost, stream));
+            IPP_CUDA(cudaStreamSynchronize(stream));
+            int32_t info;
+            memcpy(&info, h_out + L, sizeof(int32_t));
+            if (info != 0) { *status = 1; return IPP_OK; }
+            for (int l = 0; l < L; ++l) reward = reward + h_out[l];
+            evals += L;
+        }
+        // ---- backprop
+        for (int n = cur; n >= 0; n = nodes[n].parent) {
+            nodes[n].nq += 1;
+            nodes[n].reward += reward;
+        }
+    }
+
+    const Node& root = nodes[0];
+    *n_root = (int32_t)root.children.size();
+    for (size_t i = 0; i < root.children.size(); ++i) {
+        const Node& ch = nodes[root.children[i]];
+        root_goal[i] = ch.goal;
+        root_visits[i] = ch.nq;
+        root_reward[i] = ch.reward;
+    }
+    *reward_evals = evals;
+    *py_rng = py;
+    *np_rng = np;
+    return IPP_OK;
+}

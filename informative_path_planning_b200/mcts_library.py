@@ -86,6 +86,28 @@ def _prior_draw(k, variance):
     return x.reshape(k)
 
 
+_native_stage = {}
+_prior_scales = {}
+
+
+def _prior_scale_table(variance):
+    """[33][32] table d with _prior_draw(k, variance)[i] == standard_normal_i * d[k][i]: the SVD transform of a scaled
+    identity is a constant diagonal (checked, else None and the interpreter keeps the search)."""
+    key = float(np.asarray(variance, dtype=float).reshape(-1)[0])
+    if key not in _prior_scales:
+        kmax = aqlib.L.IPP_APPEND_MAX_K
+        table = np.zeros((kmax + 1, kmax), dtype=np.float64)
+        for k in range(1, kmax + 1):
+            _, s, v = np.linalg.svd(np.eye(k) * key)
+            tr = np.sqrt(s)[:, None] * v
+            if np.count_nonzero(tr - np.diag(np.diag(tr))) != 0:
+                table = None
+                break
+            table[k, :k] = np.diag(tr)
+        _prior_scales[key] = table
+    return _prior_scales[key]
+
+
 def _xobs(action):
     obs = np.array(action)
     return np.vstack([obs[:, 0], obs[:, 1]]).T
@@ -429,6 +451,8 @@ class cMCTS(object):
             return ((self.max_val, self.max_locs, self.target), self.aq_param[1])
         return None
 
+    NATIVE_SEARCH = True       # dpw tree + Dubins generator + a fused reward: run the whole search in libipp_b200.so
+
     def search(self, t, param, budget=None):
         """Build the tree and run `budget` rollouts (reference :681-695); returns the root's children."""
         if self.tree_type == 'dpw':
@@ -439,9 +463,94 @@ class cMCTS(object):
             raise ValueError('Tree type must be one of either \'dpw\' or \'belief\'')
         self.tree = tree_cls(self.f_rew, self.aquisition_function, self.GP, self.cp, self.path_generator, t,
                              depth=self.rl, param=param, c=self.c)
-        for _ in range(self.comp_budget if budget is None else budget):
+        budget = self.comp_budget if budget is None else budget
+        self.native_search_used = False
+        if self.NATIVE_SEARCH and tree_cls is Tree and self._search_native(t, budget):
+            self.native_search_used = True
+            return self.tree.root.children
+        for _ in range(budget):
             self.tree.get_next_leaf(copy.copy(self.GP))
         return self.tree.root.children
+
+    def _search_native(self, t, budget):
+        """The same search by ipp_tree_search_dpw (csrc/tree.cu): walk, widening, candidate paths, simulated
+        observations and both random streams in native code, one device pass + one synchronisation per rollout.
+        Returns False -- with nothing consumed from the random streams -- when the configuration is not covered
+        (other generators / rewards, no data yet) or a rollout needs the per-level fallback."""
+        import ctypes
+        from .paths_library import Dubins_Path_Generator
+        L = aqlib.L
+        pg, belief, tree = self.path_generator, self.GP, self.tree
+        if type(pg) is not Dubins_Path_Generator or not pg.use_native or not isinstance(belief, GPModel):
+            return False
+        boxes = pg._obstacle_boxes()
+        if boxes is None or boxes[1] > 16:
+            return False
+        fused = tree._fused_kind(belief)
+        scale = _prior_scale_table(belief.variance)
+        if fused is None or scale is None or belief.dimension not in (2, 3):
+            return False
+        kind, params, maxes_d = fused
+        pose = np.array([float(v) for v in self.cp], dtype=np.float64)
+        if pose.shape[0] != 3:
+            return False
+        angles = np.ascontiguousarray(np.linspace(-2.35, 2.35, pg.fs), dtype=np.float64)
+        prm = L.IppTreeParams()
+        prm.budget, prm.max_depth, prm.kind = int(budget), int(self.rl), int(kind)
+        prm.frontier_size, prm.keep_every, prm.n_obstacles = int(pg.fs), 10, int(boxes[1])
+        prm.c = float(self.c)
+        prm.reward_param = float(params[0]) if params is not None else 0.0
+        prm.time = float(t)
+        prm.horizon, prm.turning_radius = float(pg.hl), float(pg.tr)
+        prm.dense_step, prm.border = float(pg.ss / 10), float(3 * pg.tr)
+        prm.extent[:] = [float(e) for e in pg.extent]
+        prm.angles = angles.ctypes.data
+        prm.obstacles = ctypes.cast(boxes[0], ctypes.c_void_p).value if boxes[1] else None
+        prm.prior_scale = scale.ctypes.data
+        dev = L.device()
+        stage = _native_stage.get(dev.index)
+        if stage is None:
+            stage = _native_stage[dev.index] = (torch.empty(L.IPP_TREE_STAGE_DOUBLES, dtype=torch.float64).pin_memory(),
+                                                torch.empty(L.IPP_TREE_STAGE_DOUBLES, dtype=torch.float64, device=dev))
+        N = belief.n_obs
+        work = L.workspace(L.lib.ipp_rollout_workspace(N, L.IPP_ROLLOUT_MAX_POINTS), slot='rollout')
+        G = int(pg.fs) + 1
+        n_root = np.zeros(1, dtype=np.int32)
+        root_goal = np.zeros(G, dtype=np.int32)
+        root_visits = np.zeros(G, dtype=np.int64)
+        root_reward = np.zeros(G, dtype=np.float64)
+        evals = np.zeros(1, dtype=np.int64)
+        status = np.zeros(1, dtype=np.int32)
+        py_state, py_extra = L.py_rng_state()
+        np_state = L.np_rng_state()
+        vp = ctypes.c_void_p
+        S = 0 if maxes_d is None else int(maxes_d.numel())
+        L.check(L.lib.ipp_tree_search_dpw(
+            ctypes.byref(prm), pose.ctypes.data_as(vp), ctypes.byref(belief.kern._c), L.ptr(belief._X_d), N,
+            L.ptr(belief._alpha_d), L.ptr(belief._winv_d), belief._ld, belief._noise_var(), belief._diag_add(),
+            L.ptr(maxes_d), S, ctypes.byref(py_state), ctypes.byref(np_state), L.ptr(stage[0]), L.ptr(stage[1]),
+            L.ptr(work), n_root.ctypes.data_as(vp), root_goal.ctypes.data_as(vp), root_visits.ctypes.data_as(vp),
+            root_reward.ctypes.data_as(vp), evals.ctypes.data_as(vp), status.ctypes.data_as(vp), L.stream_ptr()))
+        if int(status[0]) != 0:
+            return False
+        L.set_py_rng_state(py_state, py_extra)
+        L.set_np_rng_state(np_state)
+        paths, dense_paths = pg.get_path_set_lazy(self.cp)
+        keys = list(paths.keys())
+        n = int(n_root[0])
+        if keys != [int(g) for g in root_goal[:n]]:
+            raise RuntimeError('native tree search and the path generator disagree on the root actions')
+        root = tree.root
+        for i, key in enumerate(keys):
+            child = Node(pose=root.pose, parent=root, name=root.name + '_action' + str(i), action=paths[key],
+                         dense_path=dense_paths[key])
+            child.nqueries = int(root_visits[i])
+            child.reward = float(root_reward[i])
+            root.add_children(child)
+        root.nqueries = int(budget)
+        root.reward = float(np.sum(root_reward[:n]))
+        tree.reward_evals = int(evals[0])
+        return True
 
     def result(self, best_child, all_vals):
         """The tuple choose_trajectory returns (reference :709-713)."""

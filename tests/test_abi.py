@@ -201,3 +201,73 @@ def test_native_dubins_path_sets_in_obstacle_worlds():
     duck = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], Duck())
     ref = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], worlds['block'])
     assert duck.get_path_set((4.6, 2.4, 1.9))[0].keys() == ref.get_path_set((4.6, 2.4, 1.9))[0].keys()
+
+
+def test_native_random_streams_continue_pythons_and_numpys():
+    """The tree search's generators (csrc/tree.cu) against the interpreters': random.choice and
+    np.random.standard_normal continued bit for bit from an arbitrary state (cached Gaussian included), and the state
+    handed back continues the interpreter's stream."""
+    import random
+    import numpy as np
+    from informative_path_planning_b200 import _lib as L
+    vp = ctypes.c_void_p
+    random.seed(123)
+    [random.random() for _ in range(7)]
+    st, extra = L.py_rng_state()
+    ns = np.random.default_rng(0).integers(1, 70, 6000).astype(np.int32)
+    ns[:40] = np.arange(1, 41)
+    out = np.zeros(ns.size, dtype=np.int32)
+    L.check(L.lib.ipp_rng_py_choices(ctypes.byref(st), ns.ctypes.data_as(vp), int(ns.size), out.ctypes.data_as(vp)))
+    want = np.array([random.choice(range(int(n))) for n in ns])
+    assert np.array_equal(out, want)
+    nxt = [random.random(), random.choice([3, 4, 5])]
+    L.set_py_rng_state(st, extra)
+    assert [random.random(), random.choice([3, 4, 5])] == nxt
+    for warm in (0, 3):                                   # 3: an odd number of draws leaves a cached second variate
+        np.random.seed(77)
+        np.random.standard_normal(warm)
+        st = L.np_rng_state()
+        assert st.has_gauss == warm % 2
+        got = np.zeros(10001)
+        L.check(L.lib.ipp_rng_np_normals(ctypes.byref(st), 10001, got.ctypes.data_as(vp)))
+        assert np.array_equal(got, np.random.standard_normal(10001))
+        nxt = np.random.standard_normal(5)
+        L.set_np_rng_state(st)
+        assert np.array_equal(np.random.standard_normal(5), nxt)
+
+
+def test_native_tree_path_sets_equal_the_generators():
+    """ipp_tree_path_set (frontier rule + Dubins sets inside the native tree search) == Dubins_Path_Generator
+    .get_path_set, bit for bit, in free and obstacle worlds, at interior poses and against the walls."""
+    import numpy as np
+    from informative_path_planning_b200 import _lib as L
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200.obstacles import box_array
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    vp = ctypes.c_void_p
+    rng = np.random.default_rng(4)
+    worlds = _golden_worlds()
+    for world in (None, worlds['block'], worlds['trap_left'], worlds['channel']):
+        pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, [0., 10., 0., 10.], world)
+        boxes, nb = box_array(pg.obstacle_world.boxes())
+        angles = np.ascontiguousarray(np.linspace(-2.35, 2.35, 15))
+        scale = mc._prior_scale_table(100.0)
+        prm = L.IppTreeParams()
+        prm.budget, prm.max_depth, prm.kind, prm.frontier_size, prm.keep_every, prm.n_obstacles = 1, 3, 0, 15, 10, nb
+        prm.horizon, prm.turning_radius, prm.dense_step, prm.border = 1.5, 0.05, float(0.5 / 10), float(3 * 0.05)
+        prm.extent[:] = [0., 10., 0., 10.]
+        prm.angles, prm.prior_scale = angles.ctypes.data, scale.ctypes.data
+        prm.obstacles = ctypes.cast(boxes, vp).value if nb else None
+        for _ in range(40):
+            pose = (float(rng.uniform(0.2, 9.8)), float(rng.uniform(0.2, 9.8)), float(rng.uniform(-4, 4)))
+            paths, _ = pg.get_path_set(pose)
+            n = np.zeros(1, dtype=np.int32)
+            goal = np.zeros(16, dtype=np.int32)
+            cnt = np.zeros(16, dtype=np.int32)
+            samp = np.zeros((16, 16, 3))
+            pose_a = np.array(pose)
+            L.check(L.lib.ipp_tree_path_set(ctypes.byref(prm), pose_a.ctypes.data_as(vp), n.ctypes.data_as(vp),
+                                            goal.ctypes.data_as(vp), cnt.ctypes.data_as(vp), samp.ctypes.data_as(vp), 16))
+            assert list(paths.keys()) == goal[:n[0]].tolist(), pose
+            for i, key in enumerate(paths):
+                assert np.array_equal(np.array(paths[key]), samp[i, :cnt[i]]), (pose, key)

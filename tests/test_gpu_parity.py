@@ -951,3 +951,64 @@ def test_train_and_load_kernel(pkg, tmp_path):
     assert m2.variance == 100.0                                  # the reference's load_kernel leaves the attributes alone
     with pytest.raises(ValueError):
         m2.load_kernel(str(tmp_path / 'missing.npy'))
+
+
+@pytest.mark.parametrize('f_rew,world_kind,n_obs,budget,depth', [
+    ('mean', 'free', 40, 120, 5), ('mean', 'block', 300, 250, 5), ('mes', 'free', 150, 250, 5),
+    ('exp_improve', 'channel', 90, 150, 4), ('mean', 'free', 1200, 60, 3)])
+def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n_obs, budget, depth):
+    """ipp_tree_search_dpw (the whole DPW search in native code) against the Python Tree on the same seeds: identical
+    visit counts, bit-identical reward sums, the same chosen action -- and the interpreter's two random streams are left
+    exactly where the Python search leaves them."""
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200 import obstacles as ob
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    aq = pkg.aq_library
+    ext = list(RANGES)
+    w = {'free': None, 'block': ob.BlockWorld(ext, num_blocks=2, dim_blocks=(1.5, 1.5), centers=[(6.5, 5.0), (4.0, 7.0)]),
+         'channel': ob.ChannelWorld(ext, (6.5, 5.0), 3., 0.6)}[world_kind]
+    rng = np.random.default_rng(n_obs)
+    X, z = world(rng, n_obs, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement}[f_rew]
+    res = {}
+    for native in (True, False):
+        pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES, w)
+        np.random.seed(21); random.seed(22)
+        np.random.standard_normal(1)                             # leave a cached Gaussian in numpy's state
+        planner = mc.cMCTS(budget, m, (5.2, 4.6, 0.7), depth, pg, fn, f_rew, 6,
+                           aq_param=float(np.max(z)) if f_rew == 'exp_improve' else None, tree_type='dpw')
+        planner.NATIVE_SEARCH = native
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            out = planner.choose_trajectory(t=6)
+        assert planner.native_search_used == native
+        kids = planner.tree.root.children
+        res[native] = (out, [c.nqueries for c in kids], [c.reward for c in kids], planner.tree.reward_evals,
+                       random.random(), np.random.standard_normal(3), [c.action for c in kids])
+    a, b = res[True], res[False]
+    assert a[1] == b[1] and sum(a[1]) == budget
+    assert a[2] == b[2]                                           # same kernels on the same inputs, summed in the same order
+    assert a[3] == b[3] and a[4] == b[4] and np.array_equal(a[5], b[5])
+    assert a[6] == b[6]
+    assert a[0][0] == b[0][0] and a[0][1] == b[0][1] and a[0][2] == b[0][2] and a[0][4] == b[0][4]
+
+
+def test_native_tree_search_steps_aside_when_not_covered(pkg):
+    """Straight-fan generator, belief tree, no data yet: the interpreter keeps the search (and the native path says so)."""
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator, Path_Generator
+    aq = pkg.aq_library
+    rng = np.random.default_rng(0)
+    X, z = world(rng, 30, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    empty = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    cases = [(m, Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw'), (m, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'belief'),
+             (empty, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw')]
+    for model, pg, tree_type in cases:
+        np.random.seed(1); random.seed(2)
+        planner = mc.cMCTS(12, model, (5.0, 5.0, 0.2), 3, pg, aq.mean_UCB, 'mean', 2, tree_type=tree_type)
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            out = planner.choose_trajectory(t=2)
+        assert not planner.native_search_used and len(out) == 8

@@ -20,13 +20,14 @@ class CountingFn(object):
         self.n += 1
         return self.fn(**kw)
 
-def run(kind, n_obs, f_rew, budget=250, depth=5, fuse=True):
+def run(kind, n_obs, f_rew, budget=250, depth=5, fuse=True, native=True):
     X, z = world(n_obs)
     if kind == 'gpu':
         from informative_path_planning_b200 import aq_library as aq, gpmodel_library as gp, mcts_library as mc
         from informative_path_planning_b200.paths_library import Dubins_Path_Generator as PG
         model = gp.OnlineGPModel(R, 1.0, 100.0, noise=0.5); cls = mc.cMCTS
         mc.Tree.FUSE_ROLLOUTS = fuse
+        mc.cMCTS.NATIVE_SEARCH = native and fuse
     else:
         from oracle import aq_oracle as aq, mcts_oracle as mc
         from oracle.gpmodel_oracle import OnlineGPModelOracle
@@ -42,7 +43,7 @@ def run(kind, n_obs, f_rew, budget=250, depth=5, fuse=True):
         t0 = time.perf_counter(); m.choose_trajectory(t=3); dt = time.perf_counter() - t0
     nq = [c.nqueries for c in m.tree.root.children]
     n_evals = fn.n if kind == 'cpu' else m.tree.reward_evals
-    return {'kind': kind if kind == 'cpu' else ('gpu_fused' if fuse else 'gpu_per_level'), 'n_obs': n_obs, 'f_rew': f_rew,
+    return {'kind': kind if kind == 'cpu' else (('gpu_native' if native else 'gpu_fused') if fuse else 'gpu_per_level'), 'n_obs': n_obs, 'f_rew': f_rew,
             'seconds': dt, 'rollouts_per_s': budget / dt, 'reward_evals': n_evals, 'reward_evals_per_s': n_evals / dt,
             'root_visits': nq}
 
@@ -51,17 +52,18 @@ if __name__ == '__main__':
     for n_obs in (100, 900, 4096):
         for f_rew in ('mean', 'mes'):
             rows = []
-            for kind, fuse in (('gpu', True), ('gpu', False), ('cpu', True)):
+            for kind, fuse, native in (('gpu', True, True), ('gpu', True, False), ('gpu', False, False), ('cpu', True, False)):
                 if kind == 'cpu' and n_obs > 900:
                     continue                                        # minutes of host time per planning step
-                if kind == 'gpu': run(kind, n_obs, f_rew, budget=20, fuse=fuse)      # warm-up (module load, allocator)
+                if kind == 'gpu': run(kind, n_obs, f_rew, budget=20, fuse=fuse, native=native)      # warm-up (module load, allocator)
                 reps = 3 if kind == 'gpu' else 1                     # a planning step is ~0.15 s: best of 3 against host jitter
-                r = min((run(kind, n_obs, f_rew, fuse=fuse) for _ in range(reps)), key=lambda x: x['seconds'])
+                r = min((run(kind, n_obs, f_rew, fuse=fuse, native=native) for _ in range(reps)), key=lambda x: x['seconds'])
                 rows.append(r); print(json.dumps(r))
             gpu_rows = [r for r in rows if r['kind'] != 'cpu']
-            print('same root visit counts, fused vs per-level device planner:', gpu_rows[0]['root_visits'] == gpu_rows[1]['root_visits'])
-            if f_rew == 'mean' and len(rows) == 3:      # (mes: the host planners draw their maxima through different optimiser paths)
-                print('same root visit counts, device vs CPU oracle planner:', rows[0]['root_visits'] == rows[2]['root_visits'])
+            print('same root visit counts, native vs interpreter (fused) vs per-level device planner:',
+                  gpu_rows[0]['root_visits'] == gpu_rows[1]['root_visits'] == gpu_rows[2]['root_visits'])
+            if f_rew == 'mean' and len(rows) == 4:      # (mes: the host planners draw their maxima through different optimiser paths)
+                print('same root visit counts, device vs CPU oracle planner:', rows[0]['root_visits'] == rows[3]['root_visits'])
             out += rows
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(out, open('gpurun_out/mcts_bench.json', 'w'), indent=1)
