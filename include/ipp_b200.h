@@ -315,6 +315,9 @@ int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
                         double* stage_host, double* stage_dev, double* work,
                         int32_t* n_root, int32_t* root_goal, int64_t* root_visits, double* root_reward,
                         int64_t* reward_evals, int32_t* status, void* stream);
+/* where the last ipp_tree_search_dpw spent its wall time: the tree walk (selection, candidate paths, draws) and the
+ * device pass (staging + launches + synchronisation), microseconds summed over the rollouts */
+int ipp_tree_last_timing(double* walk_us, double* device_us);
 /* test hooks for the two generators (host only, no device): out[i] = random.choice(range(ns[i])) /
  * out[i] = np.random.standard_normal() continued from the given state, which is advanced. */
 int ipp_rng_py_choices(ipp_mt_state* py_rng, const int32_t* ns, int count, int32_t* out);

@@ -124,6 +124,7 @@ SIGNATURES = {
     'ipp_tree_search_dpw': (_INT, [ctypes.POINTER(IppTreeParams), _P, _RBF, _P, _I64, _P, _P, _I64, _D, _D, _P, _I64,
                                    ctypes.POINTER(IppMtState), ctypes.POINTER(IppMtState), _P, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _P]),
+    'ipp_tree_last_timing': (_INT, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'ipp_rng_py_choices': (_INT, [ctypes.POINTER(IppMtState), _P, _INT, _P]),
     'ipp_rng_np_normals': (_INT, [ctypes.POINTER(IppMtState), _INT, _P]),
     'ipp_tree_path_set': (_INT, [ctypes.POINTER(IppTreeParams), _P, _P, _P, _P, _P, _INT]),

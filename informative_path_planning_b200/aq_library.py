@@ -400,7 +400,7 @@ def rff_theta_batch_device(Z_d, N, zvals, noise_var, eps):
 
 
 def global_maximization(target, target_vector_n, target_grad, target_vector_gradient_n, ranges, guesses, visualize,
-                        filename, obstacles, f_rew, time=None):
+                        filename, obstacles, f_rew, time=None, guesses_d=None):
     """reference aq_library.py:444-553 without the plotting; the grid stage (:475-485) runs on the device
     when `target` is an RFFTarget."""
     gridSize = 300
@@ -409,20 +409,35 @@ def global_maximization(target, target_vector_n, target_grad, target_vector_grad
     dim = guesses.shape[1]
     x1 = np.random.uniform(ranges[0], ranges[1], size=gridSize)
     x2 = np.random.uniform(ranges[2], ranges[3], size=gridSize)
-    x1, x2 = np.meshgrid(x1, x2, sparse=False, indexing='xy')
-    if dim == 2:
-        Xgrid_sample = np.vstack([x1.ravel(), x2.ravel()]).T
-        Xgrid = np.vstack([Xgrid_sample, guesses])
-    else:
-        Xgrid_sample = np.vstack([x1.ravel(), x2.ravel(), time * np.ones(len(x1.ravel()))]).T
-        Xgrid = Xgrid_sample
     if isinstance(target, RFFTarget):
-        grid_d = L.to_device(Xgrid)
-        vals, _, am = target.eval_device(grid_d, want_values=True)
-        start = np.asarray(Xgrid[int(am.item()), :])
+        # the 300 x 300 meshgrid (+ the data points as extra guesses when dim == 2) is assembled on the device from the
+        # 600 drawn coordinates (torch indexing = plumbing); row g = (x1[g % 300], x2[g // 300]) as np.meshgrid 'xy' ravels
+        ax = L.to_device(np.concatenate([x1, x2]))
+        G0 = gridSize * gridSize
+        cols = [ax[:gridSize].repeat(gridSize), ax[gridSize:].repeat_interleave(gridSize)]
+        if dim != 2:
+            cols.append(torch.full((G0,), float(time), dtype=torch.float64, device=ax.device))
+        grid_d = torch.stack(cols, dim=1)
+        guesses_d = guesses_d if guesses_d is not None else L.to_device(guesses)
+        if dim == 2:
+            grid_d = torch.cat([grid_d, guesses_d[:, :2]], dim=0)
+        vals, _, am = target.eval_device(grid_d.contiguous(), want_values=True)
+
+        def point(g):
+            if g < G0:
+                return np.array([x1[g % gridSize], x2[g // gridSize]] + ([float(time)] if dim != 2 else []))
+            return np.asarray(guesses[g - G0, :], dtype=float)
+        start = point(int(am.item()))
         if start[0] < ranges[0] or start[0] > ranges[1] or start[1] < ranges[2] or start[1] > ranges[3]:
-            start = np.asarray(Xgrid_sample[int(torch.argmax(vals[:Xgrid_sample.shape[0]]).item()), :])
+            start = point(int(torch.argmax(vals[:G0]).item()))
     else:
+        x1, x2 = np.meshgrid(x1, x2, sparse=False, indexing='xy')
+        if dim == 2:
+            Xgrid_sample = np.vstack([x1.ravel(), x2.ravel()]).T
+            Xgrid = np.vstack([Xgrid_sample, guesses])
+        else:
+            Xgrid_sample = np.vstack([x1.ravel(), x2.ravel(), time * np.ones(len(x1.ravel()))]).T
+            Xgrid = Xgrid_sample
         y = target(Xgrid)
         start = np.asarray(Xgrid[np.argmax(y), :])
         if start[0] < ranges[0] or start[0] > ranges[1] or start[1] < ranges[2] or start[1] > ranges[3]:
@@ -450,14 +465,19 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
     funcs = []
     delete_locs = []
     variance = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+    N_obs = robot_model.xvals.shape[0]
     for i in range(nK):
         ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
         W = np.random.normal(loc=0.0, scale=np.sqrt(1. / ls), size=(nFeatures, d))
         b = 2 * np.pi * np.random.uniform(low=0.0, high=1.0, size=(nFeatures, 1))
-        Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
+        Z_d = rff_features_device(W, b, robot_model._X_d, variance, nFeatures)
         eps = np.random.normal(loc=0.0, scale=1.0, size=(nFeatures, 1))
         try:
-            theta = _rff_theta(Z, robot_model.zvals, robot_model.noise, eps, nFeatures)
+            if N_obs >= nFeatures:      # F x F inverse + Cholesky on the device (:195-200); Z never leaves it
+                theta = rff_theta_batch_device(Z_d, N_obs, robot_model.zvals, robot_model.noise, eps)
+            else:                       # N x N eigendecomposition (:177-187): small dense LAPACK on the host
+                Z = np.ascontiguousarray(Z_d[:, :N_obs].cpu().numpy())
+                theta = _rff_theta(Z, robot_model.zvals, robot_model.noise, eps, nFeatures)
         except Exception:
             delete_locs.append(i)
             continue
@@ -470,7 +490,8 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
             maxima, max_val, _, status = global_maximization(target, target_vector_n, target.gradient,
                                                              target_vector_gradient_n, robot_model.ranges,
                                                              robot_model.xvals, visualize, 't%s.nK%s' % (t, i),
-                                                             obstacles, f_rew=f_rew, time=t)
+                                                             obstacles, f_rew=f_rew, time=t,
+                                                             guesses_d=robot_model._X_d)
             count += 1
         if status is False:
             delete_locs.append(i)

@@ -124,4 +124,15 @@ __device__ __forceinline__ double rbf_eval_fast(const RbfDev& k, const double* a
 }
 
 
+// ---- rollout.cu <-> tree.cu: one rollout's launch sequence with the points passed by value and a host-visible
+// completion word (see rollout_launch in rollout.cu)
+constexpr int RO_INLINE_POINTS = 96;                                          // 96 * 4 doubles = 3 KB of kernel parameters
+struct RolloutInline { double v[RO_INLINE_POINTS * (IPP_MAX_DIM + 1)]; };     // [M][D] points, then [M] observations
+int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                   const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                   int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
+                   double* pts, double* zobs, const RolloutInline* inline_pts, const int32_t* offsets_host,
+                   const int32_t* reps_host, int L, double* reward, int32_t* info,
+                   unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream);
+
 }  // namespace ipp

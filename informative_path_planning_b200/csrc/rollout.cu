@@ -12,8 +12,9 @@
 // block observations, which is the same posterior the reference reaches through update_model
 // (gpmodel_library.py:230-279: Schur block M = (S - R P^-1 Q + (noise + 1e-8) I)^-1 is exactly
 // (C[B,B] + (noise + 1e-8) I)^-1 here):
-//   A = C[B,B] + diag_add I = L L^T;  H = C[:,B] L^-T;  u = L^-1 (y_B - m_B);  m += H u;  C -= H H^T
-// repeated `reps[l]` times for the same block.  One CTA, everything in shared memory.
+//   A = C[B,B] + (diag_add / reps[l]) I = L L^T;  H = C[:,B] L^-T;  u = L^-1 (y_B - m_B);  m += H u;  C -= H H^T
+// (the same block appended reps[l] times = one conditioning with the noise divided by reps[l]).  One CTA, everything
+// in shared memory.
 #include "internal.cuh"
 
 namespace ipp {
@@ -54,6 +55,8 @@ struct RolloutArgs {
     double diag_add;            // noise + 1e-8 on the Schur block
     double* reward;             // [L]
     int32_t* info;              // 0 ok; l + 1: level l's block was not positive definite
+    unsigned int* done;         // optional (host-mapped): set to done_seq after reward / info are visible system-wide
+    unsigned int done_seq;
 };
 
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(RolloutArgs p) {
@@ -64,7 +67,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
     double* H = m + M;                           // [M][RO_MAX_BLOCK + 1]
     double* A = H + (size_t)M * (RO_MAX_BLOCK + 1);   // [RO_MAX_BLOCK][RO_MAX_BLOCK + 1]
     double* u = A + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1);   // [RO_MAX_BLOCK]
-    double* red = u + RO_MAX_BLOCK;              // [RO_THREADS / 32][2]
+    double* rd = u + RO_MAX_BLOCK;               // [RO_MAX_BLOCK] reciprocal diagonal of the Cholesky factor
+    double* red = rd + RO_MAX_BLOCK;             // [RO_THREADS / 32][2]
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int HL = RO_MAX_BLOCK + 1, AL = RO_MAX_BLOCK + 1;
@@ -113,23 +117,26 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
             p.reward[l] = r;
         }
         if (l == p.L - 1) break;                  // the last level's observation is never looked at again
-        // ---- condition (m, C) on the block observation, reps[l] times; only rows >= b0 are read later
-        for (int rep = 0; rep < p.reps[l]; ++rep) {
+        // ---- condition (m, C) on the block observation; only rows >= b0 are read later.  Appending the SAME noisy
+        // block r times (the reference's double add_data, Q4) is one conditioning on that observation with the noise
+        // divided by r: r independent readings that all equal y are one reading of y with variance diag_add / r.
+        if (p.reps[l] > 0) {
+            const double dadd = p.diag_add / (double)p.reps[l];
             __syncthreads();
             for (int idx = tid; idx < kb * kb; idx += RO_THREADS) {
                 const int a = idx / kb, b = idx % kb;
-                A[a * AL + b] = C[(b0 + a) * ldc + b0 + b] + (a == b ? p.diag_add : 0.0);
+                A[a * AL + b] = C[(b0 + a) * ldc + b0 + b] + (a == b ? dadd : 0.0);
             }
             if (tid < kb) u[tid] = p.zobs[b0 + tid] - m[b0 + tid];
             __syncthreads();
-            if (warp == 0) {                      // lower Cholesky of A (kb <= 32): lane = row
+            if (warp == 0) {                      // lower Cholesky of A (kb <= 32): lane = row; rd[j] = 1 / L[j][j]
                 for (int j = 0; j < kb; ++j) {
                     double d = A[j * AL + j];
                     if (!(d > 0.0)) { if (lane == 0) s_bad = l + 1; d = 1.0; }
-                    d = sqrt(d);
+                    const double r = 1.0 / sqrt(d);
                     __syncwarp();
-                    if (lane == j) A[j * AL + j] = d;
-                    if (lane > j && lane < kb) A[lane * AL + j] /= d;
+                    if (lane == j) rd[j] = r;
+                    if (lane > j && lane < kb) A[lane * AL + j] *= r;
                     __syncwarp();
                     if (lane > j && lane < kb)
                         for (int c = j + 1; c <= lane; ++c) A[lane * AL + c] -= A[lane * AL + j] * A[c * AL + j];
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
                     for (int a = 0; a < kb; ++a) {
                         double v = u[a];
                         for (int c = 0; c < a; ++c) v -= A[a * AL + c] * u[c];
-                        u[a] = v / A[a * AL + a];
+                        u[a] = v * rd[a];
                     }
                 }
             }
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
                 for (int a = 0; a < kb; ++a) {
                     double v = C[i * ldc + b0 + a];
                     for (int c = 0; c < a; ++c) v -= A[a * AL + c] * H[i * HL + c];
-                    v /= A[a * AL + a];
+                    v *= rd[a];
                     H[i * HL + a] = v;
                     dm = fma(v, u[a], dm);
                 }
@@ -167,7 +174,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
         __syncthreads();
     }
     __syncthreads();
-    if (tid == 0) *p.info = s_bad;
+    if (tid == 0) {
+        *p.info = s_bad;
+        if (p.done) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(p.done) = p.done_seq;
+        }
+    }
 }
 
 // ---- base posterior over the rollout's M <= 128 points.  A 128-row DMMA tile would be > 80 % padding here and only
@@ -194,17 +207,28 @@ __global__ void __launch_bounds__(256) rollout_rbf_kernel(RbfDev k, const double
     }
 }
 
-// mean0[m] = sum_n Kxt[m][n] alpha[n]: one warp per point, fixed summation order
-__global__ void __launch_bounds__(256) rollout_mean_kernel(const double* __restrict__ Kxt, int64_t ldk, int N, int M,
-                                                           const double* __restrict__ alpha, double* __restrict__ mean0) {
-    const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (m >= M) return;
-    double s = 0.0;
-    for (int n = lane; n < N; n += 32) s = fma(Kxt[(int64_t)m * ldk + n], alpha[n], s);
+// Same, with the rollout's points and observations arriving BY VALUE in the kernel parameters (no host-to-device copy
+// on the critical path of a rollout): block 0 also stores them to device scratch for the kernels that follow.
+template <int D>
+__global__ void __launch_bounds__(256) rollout_rbf_inline_kernel(RbfDev k, const double* __restrict__ X, int N,
+                                                                 const __grid_constant__ RolloutInline pp, int M,
+                                                                 double* __restrict__ pts_out, double* __restrict__ zobs_out,
+                                                                 double* __restrict__ Kxt, int64_t ldk) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < M * D; i += blockDim.x) pts_out[i] = pp.v[i];
+        for (int i = threadIdx.x; i < M; i += blockDim.x) zobs_out[i] = pp.v[M * D + i];
+    }
+    if (n >= N) return;
+    double x[D];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) mean0[m] = s;
+    for (int d = 0; d < D; ++d) x[d] = X[(int64_t)n * D + d];
+    for (int m = 0; m < M; ++m) {
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) q[d] = pp.v[m * D + d];
+        Kxt[(int64_t)m * ldk + n] = rbf_eval<D>(k, q, x);
+    }
 }
 
 constexpr int TW_ROWS_PER_WARP = 2, TW_JC = 256, TW_WARPS = 8;
@@ -292,12 +316,25 @@ __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const doub
     }
 }
 
+// C0[a][b] for the M (M + 1) / 2 pairs b <= a, then mean0[m] = sum_n Kxt[m][n] alpha[n] for M more "pairs": one warp per
+// dot product of length N, fixed summation order.
 __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const double* __restrict__ pts,
                                                           const double* __restrict__ T1, const double* __restrict__ Kxt,
-                                                          int64_t ldk, int N, int M, double* __restrict__ cov, int64_t ldc) {
+                                                          int64_t ldk, int N, int M, double* __restrict__ cov, int64_t ldc,
+                                                          const double* __restrict__ alpha, double* __restrict__ mean0) {
     const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (pair >= M * (M + 1) / 2) return;
+    const int pairs = M * (M + 1) / 2;
+    if (pair >= pairs + M) return;
+    if (pair >= pairs) {
+        const int mi = pair - pairs;
+        double s = 0.0;
+        for (int n = lane; n < N; n += 32) s = fma(Kxt[(int64_t)mi * ldk + n], alpha[n], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) mean0[mi] = s;
+        return;
+    }
     int a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);           // pair = a (a + 1) / 2 + b, b <= a
     while (a * (a + 1) / 2 > pair) --a;
     while ((a + 1) * (a + 2) / 2 <= pair) ++a;
@@ -318,7 +355,7 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
 
 static size_t rollout_smem(int M) {
     return sizeof(double) * ((size_t)M * (M + 1) + M + (size_t)M * (RO_MAX_BLOCK + 1) + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1) +
-                             RO_MAX_BLOCK + 2 * (RO_THREADS / 32));
+                             2 * RO_MAX_BLOCK + 2 * (RO_THREADS / 32));
 }
 
 }  // namespace ipp
@@ -331,19 +368,25 @@ extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
     return 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
 }
 
-extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
-                                   const double* winv, int64_t ldw, double noise_pred, double diag_add,
-                                   int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
-                                   const double* pts, const double* zobs, const int32_t* offsets_host,
-                                   const int32_t* reps_host, int L, double* reward, int32_t* info,
-                                   double* work, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+namespace ipp {
+
+// One rollout's launch sequence.  inline_pts != NULL: the [M][D] points followed by the [M] observations are passed by
+// value to the first kernel, which also writes them to pts / zobs (device scratch); else pts / zobs already hold them.
+// done != NULL: a host-mapped word the last kernel sets to done_seq once reward[] and info[] (then usually host-mapped
+// too) are visible to the host.
+int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                   const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                   int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
+                   double* pts, double* zobs, const RolloutInline* inline_pts, const int32_t* offsets_host,
+                   const int32_t* reps_host, int L, double* reward, int32_t* info,
+                   unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream) {
     IPP_CHECK_ARG(kern && pts && zobs && offsets_host && reps_host && reward && info && work, "null pointer");
     IPP_CHECK_ARG(L >= 1 && L <= RO_MAX_LEVELS, "1 <= levels <= IPP_ROLLOUT_MAX_LEVELS");
     IPP_CHECK_ARG(kind == IPP_REWARD_UCB || kind == IPP_REWARD_EI || kind == IPP_REWARD_MES, "unknown reward kind");
     IPP_CHECK_ARG(N >= 1 && X && alpha && winv, "needs a belief with data (the reference's no-data early-outs stay with the caller)");
     const int M = offsets_host[L];
     IPP_CHECK_ARG(offsets_host[0] == 0 && M >= 1 && M <= RO_MAX_POINTS, "1 <= points <= IPP_ROLLOUT_MAX_POINTS");
+    IPP_CHECK_ARG(!inline_pts || M <= RO_INLINE_POINTS, "too many points for the by-value form");
     RolloutArgs p;
     for (int l = 0; l < L; ++l) {
         const int kb = offsets_host[l + 1] - offsets_host[l];
@@ -366,26 +409,44 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
         double* Kxt = sub;
         double* T1 = sub + (int64_t)M * ldk;
         const RbfDev kd = to_dev(*kern);
-        if (kern->dim == 2) rollout_rbf_kernel<2><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
-        else rollout_rbf_kernel<3><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
-        IPP_LAUNCH_CHECK();
-        rollout_mean_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(Kxt, ldk, (int)N, M, alpha, mean0);
+        const unsigned nb = (unsigned)((N + 255) / 256);
+        if (inline_pts) {
+            if (kern->dim == 2) rollout_rbf_inline_kernel<2><<<nb, 256, 0, stream>>>(kd, X, (int)N, *inline_pts, M, pts, zobs, Kxt, ldk);
+            else rollout_rbf_inline_kernel<3><<<nb, 256, 0, stream>>>(kd, X, (int)N, *inline_pts, M, pts, zobs, Kxt, ldk);
+        } else {
+            if (kern->dim == 2) rollout_rbf_kernel<2><<<nb, 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
+            else rollout_rbf_kernel<3><<<nb, 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
+        }
         IPP_LAUNCH_CHECK();
         IPP_OPT_IN_SMEM(rollout_tw_kernel, TW_SMEM);
         constexpr int rows_per_block = TW_WARPS * TW_ROWS_PER_WARP;
         rollout_tw_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 32 * TW_WARPS, TW_SMEM, stream>>>(
             winv, ldw, (int)N, Kxt, ldk, M, T1);
         IPP_LAUNCH_CHECK();
-        const int pairs = M * (M + 1) / 2;
+        const int pairs = M * (M + 1) / 2 + M;                  // covariance pairs + the M mean dot products
         rollout_cov_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
-                                                                          (int)N, M, cov0, ldc);
+                                                                          (int)N, M, cov0, ldc, alpha, mean0);
         IPP_LAUNCH_CHECK();
     }
     p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc; p.zobs = zobs;
     p.M = M; p.L = L; p.kind = kind; p.maxes = maxes_dev; p.S = (int)S;
     p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;
+    p.done = done; p.done_seq = done_seq;
     IPP_OPT_IN_SMEM(rollout_condition_kernel, (int)rollout_smem(RO_MAX_POINTS));
     rollout_condition_kernel<<<1, RO_THREADS, rollout_smem(M), stream>>>(p);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
+}
+
+}  // namespace ipp
+
+extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
+                                   const double* winv, int64_t ldw, double noise_pred, double diag_add,
+                                   int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
+                                   const double* pts, const double* zobs, const int32_t* offsets_host,
+                                   const int32_t* reps_host, int L, double* reward, int32_t* info,
+                                   double* work, void* stream_) {
+    return rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, kind, params_host, n_params, maxes_dev, S,
+                          const_cast<double*>(pts), const_cast<double*>(zobs), nullptr, offsets_host, reps_host, L,
+                          reward, info, nullptr, 0u, work, static_cast<cudaStream_t>(stream_));
 }

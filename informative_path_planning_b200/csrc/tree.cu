@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "dubins.cuh"
@@ -154,7 +155,19 @@ bool valid_params(const ipp_tree_params* p) {
            p->n_obstacles <= IPP_MAX_OBSTACLES && (p->n_obstacles == 0 || p->obstacles);
 }
 
+double g_walk_us = 0.0, g_device_us = 0.0;      // host-side split of the last search (ipp_tree_last_timing)
+inline double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 }  // namespace
+
+extern "C" int ipp_tree_last_timing(double* walk_us, double* device_us) {
+    IPP_CHECK_ARG(walk_us && device_us, "null pointer");
+    *walk_us = g_walk_us;
+    *device_us = g_device_us;
+    return IPP_OK;
+}
 
 extern "C" int ipp_rng_py_choices(ipp_mt_state* py_rng, const int32_t* ns, int count, int32_t* out) {
     IPP_CHECK_ARG(py_rng && ns && out && count >= 0, "bad argument");
@@ -226,8 +239,30 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     double* d_in = stage_dev;
     double* d_out = stage_dev + IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1);
     const double params_host[1] = {P.reward_param};
+    // zero-copy form: the pinned staging buffer as the device sees it (same memory; unified addressing normally makes
+    // the two pointers equal).  If the buffer is not mapped, the copy + synchronise form below is used instead.
+    double* h_flag = h_out + IPP_ROLLOUT_MAX_LEVELS + 8;
+    double* m_out = nullptr;
+    unsigned int* m_flag = nullptr;
+    bool zero_copy = false;
+    {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, stage_host, 0) == cudaSuccess && dp) {
+            m_out = static_cast<double*>(dp) + (h_out - stage_host);
+            m_flag = reinterpret_cast<unsigned int*>(static_cast<double*>(dp) + (h_flag - stage_host));
+            zero_copy = true;
+        } else {
+            cudaGetLastError();                                                  // clear the sticky "not mapped" error
+        }
+    }
+    static unsigned int seq_base = 0;                                            // completion words never repeat a value
+    unsigned int seq = (seq_base += 1u << 20);
+    *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
+    ipp::RolloutInline inl;
 
+    double walk_us = 0.0, device_us = 0.0;
     for (int it = 0; it < P.budget; ++it) {
+        const double t_walk = now_us();
         // ---- leaf_helper: walk down, recording the (points, observation, appends) of every action step
         levels.clear();
         int cur = 0;
@@ -306,6 +341,8 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             }
         }
         // ---- settle: all rewards of the rollout in one device pass
+        const double t_dev = now_us();
+        walk_us += t_dev - t_walk;
         double reward = 0.0;
         const int L = (int)levels.size();
         if (L > 0) {
@@ -313,32 +350,55 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             for (const Level& lv : levels) M += lv.k;
             if (L > IPP_ROLLOUT_MAX_LEVELS || M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }
             int32_t offsets[IPP_ROLLOUT_MAX_LEVELS + 1], reps[IPP_ROLLOUT_MAX_LEVELS];
+            const bool fast = zero_copy && M <= ipp::RO_INLINE_POINTS;
+            double* in = fast ? inl.v : h_in;
             int row = 0;
             for (int l = 0; l < L; ++l) {
                 const Node& a = nodes[levels[l].node];
                 offsets[l] = row;
                 reps[l] = levels[l].reps;
                 for (int i = 0; i < a.k; ++i, ++row) {
-                    h_in[(size_t)row * D] = pool[a.data + 3 * i];
-                    h_in[(size_t)row * D + 1] = pool[a.data + 3 * i + 1];
-                    if (D == 3) h_in[(size_t)row * D + 2] = P.time;
-                    h_in[(size_t)M * D + row] = pool[levels[l].z + i];
+                    in[(size_t)row * D] = pool[a.data + 3 * i];
+                    in[(size_t)row * D + 1] = pool[a.data + 3 * i + 1];
+                    if (D == 3) in[(size_t)row * D + 2] = P.time;
+                    in[(size_t)M * D + row] = pool[levels[l].z + i];
                 }
             }
             offsets[L] = M;
-            IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * (D + 1), cudaMemcpyHostToDevice, stream));
-            const int rc = ipp_rollout_rewards(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
-                                               maxes_dev, S, d_in, d_in + (size_t)M * D, offsets, reps, L, d_out,
-                                               reinterpret_cast<int32_t*>(d_out + L), work, stream_);
-            if (rc != IPP_OK) return rc;
-            IPP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * (size_t)(L + 1), cudaMemcpyDeviceToHost, stream));
-            IPP_CUDA(cudaStreamSynchronize(stream));
             int32_t info;
+            if (fast) {
+                // points by value in the kernel parameters, rewards + info written straight into the pinned buffer, completion
+                // word polled by this thread: no copies and no driver synchronisation on the rollout's critical path
+                ++seq;
+                const int rc = ipp::rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
+                                                   maxes_dev, S, d_in, d_in + (size_t)M * D, &inl, offsets, reps, L, m_out,
+                                                   reinterpret_cast<int32_t*>(m_out + L), m_flag, seq, work, stream);
+                if (rc != IPP_OK) return rc;
+                const double t_spin = now_us();
+                for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int*>(h_flag) != seq; ++spins) {
+                    if ((spins & 0xffff) == 0xffff && now_us() - t_spin > 5e6) {          // 5 s: something is wrong on the device
+                        IPP_CUDA(cudaStreamSynchronize(stream));
+                        if (*reinterpret_cast<volatile unsigned int*>(h_flag) == seq) break;
+                        ::ipp::set_error("%s: rollout %d never completed", __func__, it);
+                        return IPP_E_CUDA;
+                    }
+                }
+                __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            } else {
+                IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * (D + 1), cudaMemcpyHostToDevice, stream));
+                const int rc = ipp::rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
+                                                   maxes_dev, S, d_in, d_in + (size_t)M * D, nullptr, offsets, reps, L, d_out,
+                                                   reinterpret_cast<int32_t*>(d_out + L), nullptr, 0u, work, stream);
+                if (rc != IPP_OK) return rc;
+                IPP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * (size_t)(L + 1), cudaMemcpyDeviceToHost, stream));
+                IPP_CUDA(cudaStreamSynchronize(stream));
+            }
             memcpy(&info, h_out + L, sizeof(int32_t));
             if (info != 0) { *status = 1; return IPP_OK; }
             for (int l = 0; l < L; ++l) reward = reward + h_out[l];
             evals += L;
         }
+        device_us += now_us() - t_dev;
         // ---- backprop
         for (int n = cur; n >= 0; n = nodes[n].parent) {
             nodes[n].nq += 1;
@@ -355,6 +415,8 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         root_reward[i] = ch.reward;
     }
     *reward_evals = evals;
+    g_walk_us = walk_us;
+    g_device_us = device_us;
     *py_rng = py;
     *np_rng = np;
     return IPP_OK;
