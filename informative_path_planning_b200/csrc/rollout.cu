@@ -64,14 +64,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
     const int M = p.M, ldc = M + 1;
     double* C = sm;                              // [M][M+1]
     double* m = C + (size_t)M * ldc;             // [M]
-    double* H = m + M;                           // [M][RO_MAX_BLOCK + 1]
-    double* A = H + (size_t)M * (RO_MAX_BLOCK + 1);   // [RO_MAX_BLOCK][RO_MAX_BLOCK + 1]
-    double* u = A + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1);   // [RO_MAX_BLOCK]
-    double* rd = u + RO_MAX_BLOCK;               // [RO_MAX_BLOCK] reciprocal diagonal of the Cholesky factor
-    double* red = rd + RO_MAX_BLOCK;             // [RO_THREADS / 32][2]
+    double* H = m + M;                           // [M + 1][RO_MAX_BLOCK + 1]; row M = the block's residual y_B - m_B
+    double* red = H + (size_t)(M + 1) * (RO_MAX_BLOCK + 1);   // [RO_THREADS / 32][2]
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int HL = RO_MAX_BLOCK + 1, AL = RO_MAX_BLOCK + 1;
+    constexpr int HL = RO_MAX_BLOCK + 1;
 
     for (int idx = tid; idx < M * M; idx += RO_THREADS) C[(idx / M) * ldc + idx % M] = p.cov0[(int64_t)(idx / M) * p.ldc + idx % M];
     for (int i = tid; i < M; i += RO_THREADS) m[i] = p.mean0[i];
@@ -121,50 +118,40 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
         // block r times (the reference's double add_data, Q4) is one conditioning on that observation with the noise
         // divided by r: r independent readings that all equal y are one reading of y with variance diag_add / r.
         if (p.reps[l] > 0) {
+            // Right-looking elimination of the panel [C[b0:, B] + dadd I ; (y_B - m_B)^T] by all threads: after column a,
+            // H[i][a] = (L^-1 C[B, i])_a for every remaining point i and H[M][a] = u_a = (L^-1 (y_B - m_B))_a -- the
+            // Cholesky factor of the block, the forward substitutions of every row and of the residual in one sweep
+            // (kb steps of rsqrt + scale + rank-1 update instead of three dependent triangular loops).
             const double dadd = p.diag_add / (double)p.reps[l];
+            const int R = M - b0;
             __syncthreads();
-            for (int idx = tid; idx < kb * kb; idx += RO_THREADS) {
-                const int a = idx / kb, b = idx % kb;
-                A[a * AL + b] = C[(b0 + a) * ldc + b0 + b] + (a == b ? dadd : 0.0);
+            for (int idx = tid; idx < R * kb; idx += RO_THREADS) {
+                const int i = idx / kb, a = idx % kb;
+                H[(b0 + i) * HL + a] = C[(b0 + i) * ldc + b0 + a] + (i == a ? dadd : 0.0);
             }
-            if (tid < kb) u[tid] = p.zobs[b0 + tid] - m[b0 + tid];
+            if (tid < kb) H[M * HL + tid] = p.zobs[b0 + tid] - m[b0 + tid];
             __syncthreads();
-            if (warp == 0) {                      // lower Cholesky of A (kb <= 32): lane = row; rd[j] = 1 / L[j][j]
-                for (int j = 0; j < kb; ++j) {
-                    double d = A[j * AL + j];
-                    if (!(d > 0.0)) { if (lane == 0) s_bad = l + 1; d = 1.0; }
-                    const double r = 1.0 / sqrt(d);
-                    __syncwarp();
-                    if (lane == j) rd[j] = r;
-                    if (lane > j && lane < kb) A[lane * AL + j] *= r;
-                    __syncwarp();
-                    if (lane > j && lane < kb)
-                        for (int c = j + 1; c <= lane; ++c) A[lane * AL + c] -= A[lane * AL + j] * A[c * AL + j];
-                    __syncwarp();
+            for (int a = 0; a < kb; ++a) {
+                const double piv = H[(b0 + a) * HL + a];
+                __syncthreads();
+                if (!(piv > 0.0) && tid == 0) s_bad = l + 1;
+                const double d = piv > 0.0 ? rsqrt(piv) : 1.0;
+                for (int i = b0 + tid; i <= M; i += RO_THREADS)
+                    H[i * HL + a] = (i < b0 + a) ? 0.0 : H[i * HL + a] * d;
+                __syncthreads();
+                const int rest = kb - a - 1;
+                for (int idx = tid; idx < (R + 1) * rest; idx += RO_THREADS) {
+                    const int i = b0 + idx / rest, c = a + 1 + idx % rest;
+                    H[i * HL + c] = fma(-H[i * HL + a], H[(b0 + c) * HL + a], H[i * HL + c]);
                 }
-                if (lane == 0) {                  // u = L^-1 (y_B - m_B)
-                    for (int a = 0; a < kb; ++a) {
-                        double v = u[a];
-                        for (int c = 0; c < a; ++c) v -= A[a * AL + c] * u[c];
-                        u[a] = v * rd[a];
-                    }
-                }
+                __syncthreads();
             }
-            __syncthreads();
-            for (int i = b0 + tid; i < M; i += RO_THREADS) {      // H[i] = L^-1 C[B, i]  (forward substitution)
+            for (int i = b0 + tid; i < M; i += RO_THREADS) {      // m += H u
                 double dm = 0.0;
-                for (int a = 0; a < kb; ++a) {
-                    double v = C[i * ldc + b0 + a];
-                    for (int c = 0; c < a; ++c) v -= A[a * AL + c] * H[i * HL + c];
-                    v *= rd[a];
-                    H[i * HL + a] = v;
-                    dm = fma(v, u[a], dm);
-                }
+                for (int a = 0; a < kb; ++a) dm = fma(H[i * HL + a], H[M * HL + a], dm);
                 m[i] += dm;
             }
-            __syncthreads();
-            const int R = M - b0;
-            for (int idx = tid; idx < R * R; idx += RO_THREADS) {
+            for (int idx = tid; idx < R * R; idx += RO_THREADS) {  // C -= H H^T
                 const int i = b0 + idx / R, j = b0 + idx % R;
                 double s = 0.0;
                 for (int a = 0; a < kb; ++a) s = fma(H[i * HL + a], H[j * HL + a], s);
@@ -231,7 +218,8 @@ __global__ void __launch_bounds__(256) rollout_rbf_inline_kernel(RbfDev k, const
     }
 }
 
-constexpr int TW_ROWS_PER_WARP = 2, TW_JC = 256, TW_WARPS = 8;
+constexpr int TW_ROWS_PER_WARP = 4, TW_JC = 256, TW_WARPS = 8, TW_PTS = 16;
+constexpr int TW_ROWS_PER_BLOCK = (TW_WARPS / 2) * TW_ROWS_PER_WARP;       // two warps (point halves) share a row group
 constexpr int TW_SMEM = 2 * 32 * TW_JC * 8;                 // two tile buffers of [32 points][256 j] doubles = 128 KB
 
 __device__ __forceinline__ void tw_cp16(uint32_t dst, const void* src, int src_bytes) {
@@ -241,16 +229,21 @@ __device__ __forceinline__ void tw_cp16(uint32_t dst, const void* src, int src_b
 __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const double* __restrict__ W, int64_t ldw, int N,
                                                                       const double* __restrict__ Kxt, int64_t ldk, int M,
                                                                       double* __restrict__ T1) {
-    // Block = 16 rows of W^-1 (2 per warp); the cross-covariance rows of <= 32 points are staged in shared memory in
-    // j-chunks shared by all 16 rows (at N = 4096 the M x N panel does not fit L1: the untiled version re-streamed it
-    // from L2 once per row -- 2.7 GB per call, 1.8 ms).  The chunks arrive by cp.async, double buffered: a plain
-    // load-store loop serialised ~20 L2 latencies per chunk and kept the kernel at 0.45 ms.
+    // Block = 16 rows of W^-1; the cross-covariance rows of <= 32 points are staged in shared memory in j-chunks shared
+    // by all 16 rows (at N = 4096 the M x N panel does not fit L1: the untiled version re-streamed it from L2 once per
+    // row -- 2.7 GB per call, 1.8 ms).  The chunks arrive by cp.async, double buffered: a plain load-store loop
+    // serialised ~20 L2 latencies per chunk and kept the kernel at 0.45 ms.
+    // Warp = 4 rows x one HALF of the points: every staged value read from shared memory feeds 4 FMAs (the 2-row x
+    // all-points layout fed 2 and was bound by shared-memory bandwidth, not by the FP64 pipe or HBM).
     extern __shared__ __align__(16) double tw_smem[];
     const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(tw_smem));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = (blockIdx.x * TW_WARPS + warp) * TW_ROWS_PER_WARP;
+    const int half_id = warp & 1;
+    const int n0 = (blockIdx.x * (TW_WARPS / 2) + (warp >> 1)) * TW_ROWS_PER_WARP;
     for (int m0 = 0; m0 < M; m0 += 32) {
         const int mm = (M - m0) < 32 ? (M - m0) : 32;
+        const int half = (mm + 1) >> 1;                                   // points of this warp: [i0, i1)
+        const int i0 = half_id * half, i1 = (i0 + half) < mm ? (i0 + half) : mm;
         auto load_tile = [&](int buf, int j0) {
             for (int idx = threadIdx.x; idx < mm * (TW_JC / 2); idx += 32 * TW_WARPS) {
                 const int m = idx / (TW_JC / 2), jj = 2 * (idx % (TW_JC / 2));
@@ -261,11 +254,11 @@ __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const doub
             }
             asm volatile("cp.async.commit_group;\n" ::);
         };
-        double acc[TW_ROWS_PER_WARP][32];
+        double acc[TW_ROWS_PER_WARP][TW_PTS];
 #pragma unroll
         for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[r][i] = 0.0;
+            for (int i = 0; i < TW_PTS; ++i) acc[r][i] = 0.0;
         int buf = 0;
         load_tile(0, 0);
         for (int j0 = 0; j0 < N; j0 += TW_JC) {
@@ -285,13 +278,13 @@ __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const doub
                 asm volatile("cp.async.wait_group 0;\n" ::);
             }
             __syncthreads();
-            const double* sK = tw_smem + (size_t)buf * 32 * TW_JC;
+            const double* sK = tw_smem + (size_t)buf * 32 * TW_JC + (size_t)i0 * TW_JC;
 #pragma unroll
             for (int c = 0; c < TW_JC / 32; ++c) {
                 const int jj = lane + 32 * c;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i < mm) {
+                for (int i = 0; i < TW_PTS; ++i) {
+                    if (i0 + i < i1) {
                         const double kv = sK[i * TW_JC + jj];
 #pragma unroll
                         for (int r = 0; r < TW_ROWS_PER_WARP; ++r) acc[r][i] = fma(w[c][r], kv, acc[r][i]);
@@ -304,16 +297,31 @@ __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const doub
 #pragma unroll
         for (int r = 0; r < TW_ROWS_PER_WARP; ++r)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (i < mm) {
+            for (int i = 0; i < TW_PTS; ++i) {
+                if (i0 + i < i1) {
                     double t = acc[r][i];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                    if (lane == 0 && n0 + r < N) T1[(int64_t)(m0 + i) * ldk + n0 + r] = t;
+                    if (lane == 0 && n0 + r < N) T1[(int64_t)(m0 + i0 + i) * ldk + n0 + r] = t;
                 }
             }
         __syncthreads();
     }
+}
+
+// One lane's share of a length-N dot product with 8 independent accumulators: 16 loads in flight per lane instead of a
+// dependent load -> fma chain (one L2 round trip per 32 elements: 34 us for the covariance pass at N = 4096).
+__device__ __forceinline__ double warp_dot(const double* __restrict__ a, const double* __restrict__ b, int N, int lane) {
+    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int n = lane;
+    for (; n + 7 * 32 < N; n += 8 * 32) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] = fma(a[n + 32 * u], b[n + 32 * u], s[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 7; ++u)
+        if (n + 32 * u < N) s[u] = fma(a[n + 32 * u], b[n + 32 * u], s[u]);
+    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
 // C0[a][b] for the M (M + 1) / 2 pairs b <= a, then mean0[m] = sum_n Kxt[m][n] alpha[n] for M more "pairs": one warp per
@@ -328,8 +336,7 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
     if (pair >= pairs + M) return;
     if (pair >= pairs) {
         const int mi = pair - pairs;
-        double s = 0.0;
-        for (int n = lane; n < N; n += 32) s = fma(Kxt[(int64_t)mi * ldk + n], alpha[n], s);
+        double s = warp_dot(Kxt + (int64_t)mi * ldk, alpha, N, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) mean0[mi] = s;
@@ -341,8 +348,7 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
     const int b = pair - a * (a + 1) / 2;
     const double* t = T1 + (int64_t)a * ldk;
     const double* kx = Kxt + (int64_t)b * ldk;
-    double s = 0.0;
-    for (int n = lane; n < N; n += 32) s = fma(t[n], kx[n], s);
+    double s = warp_dot(t, kx, N, lane);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
@@ -354,8 +360,7 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
 }
 
 static size_t rollout_smem(int M) {
-    return sizeof(double) * ((size_t)M * (M + 1) + M + (size_t)M * (RO_MAX_BLOCK + 1) + RO_MAX_BLOCK * (RO_MAX_BLOCK + 1) +
-                             2 * RO_MAX_BLOCK + 2 * (RO_THREADS / 32));
+    return sizeof(double) * ((size_t)M * (M + 1) + M + (size_t)(M + 1) * (RO_MAX_BLOCK + 1) + 2 * (RO_THREADS / 32));
 }
 
 }  // namespace ipp
@@ -419,7 +424,7 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         }
         IPP_LAUNCH_CHECK();
         IPP_OPT_IN_SMEM(rollout_tw_kernel, TW_SMEM);
-        constexpr int rows_per_block = TW_WARPS * TW_ROWS_PER_WARP;
+        constexpr int rows_per_block = TW_ROWS_PER_BLOCK;
         rollout_tw_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 32 * TW_WARPS, TW_SMEM, stream>>>(
             winv, ldw, (int)N, Kxt, ldk, M, T1);
         IPP_LAUNCH_CHECK();
