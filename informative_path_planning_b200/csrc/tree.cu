@@ -99,9 +99,9 @@ int path_limits(const ipp_tree_params& p, int* max_samp) {
     return max_dense;
 }
 
-void build_path_set(const ipp_tree_params& p, const double* cp, PathSet& out) {
+// goals[(fs + 1) * 3] -> number of goals (the pose itself closes the list)
+int frontier_goals(const ipp_tree_params& p, const double* cp, double* goals) {
     const int fs = p.frontier_size;
-    std::vector<double> goals((size_t)(fs + 1) * 3);
     int G = 0;
     const double cx = cp[0], cy = cp[1], ch = cp[2], hl = p.horizon, tr = p.turning_radius;
     const double x_lo = p.extent[0] + 3 * tr, x_hi = p.extent[1] - 3 * tr;
@@ -115,18 +115,30 @@ void build_path_set(const ipp_tree_params& p, const double* cp, PathSet& out) {
         goals[3 * G] = x; goals[3 * G + 1] = y; goals[3 * G + 2] = a;
         ++G;
     }
-    goals[3 * G] = cx; goals[3 * G + 1] = cy; goals[3 * G + 2] = ch;       // the pose itself closes the goal list
-    ++G;
+    goals[3 * G] = cx; goals[3 * G + 1] = cy; goals[3 * G + 2] = ch;
+    return G + 1;
+}
+
+// kept samples of the path pose -> goal (0 = dropped); samp[max_samp][3]
+inline int goal_path(const ipp_tree_params& p, const double* cp, const double* goal, double* samp, int max_samp,
+                     int max_dense) {
+    int dn = 0;
+    const int n = dubins_one(cp, goal, p.turning_radius, p.dense_step, p.keep_every, p.extent, p.border, p.obstacles,
+                             p.n_obstacles, samp, max_samp, nullptr, max_dense, &dn, nullptr);
+    return n < 2 ? 0 : n;
+}
+
+void build_path_set(const ipp_tree_params& p, const double* cp, PathSet& out) {
+    std::vector<double> goals((size_t)(p.frontier_size + 1) * 3);
+    const int G = frontier_goals(p, cp, goals.data());
     int max_samp = 0;
     const int max_dense = path_limits(p, &max_samp);
     out.max_samp = max_samp;
     out.goal.clear(); out.count.clear(); out.samp.clear();
     std::vector<double> tmp((size_t)max_samp * 3);
     for (int gi = 0; gi < G; ++gi) {
-        int dn = 0;
-        const int n = dubins_one(cp, &goals[3 * gi], tr, p.dense_step, p.keep_every, p.extent, p.border, p.obstacles,
-                                 p.n_obstacles, tmp.data(), max_samp, nullptr, max_dense, &dn, nullptr);
-        if (n < 2) continue;
+        const int n = goal_path(p, cp, &goals[3 * gi], tmp.data(), max_samp, max_dense);
+        if (n == 0) continue;
         out.goal.push_back(gi);
         out.count.push_back(n);
         out.samp.insert(out.samp.end(), tmp.begin(), tmp.end());
@@ -147,6 +159,10 @@ struct Node {
     int64_t nq = 0;
     double reward = 0.0;
     std::vector<int> children;
+    // belief nodes: candidate actions are materialised one goal at a time (see expand_one)
+    int n_goals = -1;               // -1: frontier goals not generated yet
+    int g_next = 0;                 // next goal whose path has not been tried
+    size_t goals = 0;               // offset of goals[n_goals][3] in the pool
 };
 
 bool valid_params(const ipp_tree_params* p) {
@@ -225,7 +241,6 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     nodes.reserve((size_t)P.budget * (2 * P.max_depth + 2) + 64);
     std::vector<double> pool;
     pool.reserve(1 << 16);
-    PathSet ps;
     nodes.emplace_back();
     memcpy(nodes[0].pose, root_pose, sizeof(double) * 3);
 
@@ -260,6 +275,44 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
     ipp::RolloutInline inl;
 
+    int max_samp = 0;
+    const int max_dense = path_limits(P, &max_samp);
+    std::vector<double> tmp_path((size_t)max_samp * 3);
+    std::vector<int> incomplete;                                                  // belief nodes with goals still to try
+    // try the next goal of belief node b; true when it produced an action child
+    auto expand_one = [&](int b) -> bool {
+        const int gi = nodes[b].g_next++;
+        double pose[3], goal[3];
+        memcpy(pose, nodes[b].pose, sizeof(pose));
+        memcpy(goal, &pool[nodes[b].goals + 3 * (size_t)gi], sizeof(goal));
+        const int n = goal_path(P, pose, goal, tmp_path.data(), max_samp, max_dense);
+        if (n == 0) return false;
+        Node a;
+        a.action = true;
+        a.depth = nodes[b].depth;
+        a.parent = b;
+        a.goal = gi;
+        a.k = n;
+        a.data = pool.size();
+        pool.insert(pool.end(), tmp_path.begin(), tmp_path.begin() + 3 * n);
+        memcpy(a.pose, pose, sizeof(pose));
+        memcpy(a.end, &tmp_path[3 * (size_t)(n - 1)], sizeof(double) * 3);
+        nodes[b].children.push_back((int)nodes.size());
+        nodes[b].has_children = true;
+        nodes.push_back(a);
+        return true;
+    };
+    // one deferred path (most recently visited node first); false when nothing is left to do
+    auto complete_some = [&]() -> bool {
+        while (!incomplete.empty()) {
+            const int b = incomplete.back();
+            if (nodes[b].g_next >= nodes[b].n_goals) { incomplete.pop_back(); continue; }
+            expand_one(b);
+            return true;
+        }
+        return false;
+    };
+
     double walk_us = 0.0, device_us = 0.0;
     for (int it = 0; it < P.budget; ++it) {
         const double t_walk = now_us();
@@ -269,38 +322,35 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         while (true) {
             if (!nodes[cur].action) {
                 if (nodes[cur].depth == P.max_depth) break;
-                if (!nodes[cur].has_children) {                                   // build_action_children
-                    build_path_set(P, nodes[cur].pose, ps);
-                    for (size_t i = 0; i < ps.goal.size(); ++i) {
-                        Node a;
-                        a.action = true;
-                        a.depth = nodes[cur].depth;
-                        a.parent = cur;
-                        a.goal = ps.goal[i];
-                        a.k = ps.count[i];
-                        a.data = pool.size();
-                        const double* sp = &ps.samp[i * (size_t)ps.max_samp * 3];
-                        pool.insert(pool.end(), sp, sp + 3 * a.k);
-                        memcpy(a.pose, nodes[cur].pose, sizeof(double) * 3);
-                        memcpy(a.end, sp + 3 * (a.k - 1), sizeof(double) * 3);
-                        nodes[cur].children.push_back((int)nodes.size());
-                        nodes.push_back(a);
-                    }
-                    nodes[cur].has_children = !ps.goal.empty();
+                // build_action_children + get_next_child.  The reference builds all candidate paths of a node at once and
+                // then takes the first unvisited child; here the paths are tried one goal at a time, in the same order, so a
+                // fresh node costs one Dubins path on the walk instead of sixteen -- the rest are completed while the host
+                // waits for the device (complete_some), and the choice is the same: every built child before the first
+                // unvisited one has been visited, and UCT only runs once all goals have been tried.
+                if (nodes[cur].n_goals < 0) {
+                    nodes[cur].goals = pool.size();
+                    pool.resize(pool.size() + (size_t)(P.frontier_size + 1) * 3);
+                    nodes[cur].n_goals = frontier_goals(P, nodes[cur].pose, &pool[nodes[cur].goals]);
+                    incomplete.push_back(cur);
                 }
-                if (!nodes[cur].has_children) break;
-                // get_next_child: first unvisited child, else DPW-UCT with exact-equality ties -> random.choice
-                const Node& b = nodes[cur];
-                const double e_d = 0.5 * (1.0 - (3.0 / (10.0 * (P.max_depth - b.depth))));
                 int pick = -1;
-                double top = 0.0;
-                ties.clear();
-                for (int ci : b.children) {
-                    const Node& ch = nodes[ci];
-                    if (ch.nq == 0) { pick = ci; break; }
-                    const double v = ch.reward / (double)ch.nq + P.c * sqrt(pow((double)b.nq, e_d) / (double)ch.nq);
-                    if (ties.empty() || v > top) { top = v; ties.clear(); ties.push_back(ci); }
-                    else if (v == top) ties.push_back(ci);
+                for (int ci : nodes[cur].children)
+                    if (nodes[ci].nq == 0) { pick = ci; break; }
+                while (pick < 0 && nodes[cur].g_next < nodes[cur].n_goals)
+                    if (expand_one(cur)) pick = nodes[cur].children.back();
+                if (pick < 0 && nodes[cur].children.empty()) break;                // no feasible action: python children None
+                if (pick < 0) {
+                    // DPW-UCT over all children, exact-equality ties -> random.choice
+                    const Node& b = nodes[cur];
+                    const double e_d = 0.5 * (1.0 - (3.0 / (10.0 * (P.max_depth - b.depth))));
+                    double top = 0.0;
+                    ties.clear();
+                    for (int ci : b.children) {
+                        const Node& ch = nodes[ci];
+                        const double v = ch.reward / (double)ch.nq + P.c * sqrt(pow((double)b.nq, e_d) / (double)ch.nq);
+                        if (ties.empty() || v > top) { top = v; ties.clear(); ties.push_back(ci); }
+                        else if (v == top) ties.push_back(ci);
+                    }
                 }
                 if (pick < 0) pick = ties[py_choice(gpy, (int)ties.size())];
                 cur = pick;
@@ -376,6 +426,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 if (rc != IPP_OK) return rc;
                 const double t_spin = now_us();
                 for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int*>(h_flag) != seq; ++spins) {
+                    if (complete_some()) continue;                                  // useful work while the device runs
                     if ((spins & 0xffff) == 0xffff && now_us() - t_spin > 5e6) {          // 5 s: something is wrong on the device
                         IPP_CUDA(cudaStreamSynchronize(stream));
                         if (*reinterpret_cast<volatile unsigned int*>(h_flag) == seq) break;
