@@ -406,7 +406,7 @@ def main():
                 'per_level_calls_reward_evals_per_s': p_['reward_evals_per_s'],
                 'cpu_reward_evals_per_s': c_['reward_evals_per_s'], 'cpu_rollouts_per_s': c_['rollouts_per_s'],
                 'same_root_visit_counts': g_['root_visits'] == c_['root_visits'] == p_['root_visits'],
-                'note': 'one device call per rollout (ipp_rollout_rewards) vs one reward + two add_data per level'}
+                'note': 'native DPW search (ipp_tree_search_dpw: walk + random streams in native code, one device pass per rollout) vs the Python tree with one reward + two add_data per level; CPU = the oracle planner'}
         except Exception as e:      # measurement extra only
             extras['mcts_N900_dpw_ucb'] = {'error': repr(e)}
         # max-value sampling (BASELINE config 4): F=1000 shared features x S=100 samples on a 2^20-point grid
