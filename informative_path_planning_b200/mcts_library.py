@@ -452,6 +452,7 @@ class cMCTS(object):
         return None
 
     NATIVE_SEARCH = True       # dpw tree + Dubins generator + a fused reward: run the whole search in libipp_b200.so
+    native_searches = 0        # how many searches (all instances) went through ipp_tree_search_dpw
 
     def search(self, t, param, budget=None):
         """Build the tree and run `budget` rollouts (reference :681-695); returns the root's children."""
@@ -467,6 +468,7 @@ class cMCTS(object):
         self.native_search_used = False
         if self.NATIVE_SEARCH and tree_cls is Tree and self._search_native(t, budget):
             self.native_search_used = True
+            cMCTS.native_searches += 1
             return self.tree.root.children
         for _ in range(budget):
             self.tree.get_next_leaf(copy.copy(self.GP))

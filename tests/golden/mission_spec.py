@@ -21,6 +21,10 @@ MISSIONS = {   # name: (f_rew, nonmyopic, tree_type, path_generator, obstacle wo
     'myopic_mes_fan': ('mes', False, 'dpw', 'default', 'free', 4, 0, 0),
     'nonmyopic_mean_dpw': ('mean', True, 'dpw', 'default', 'free', 4, 25, 3),
     'nonmyopic_mean_belief_dubins': ('mean', True, 'belief', 'dubins', 'channel', 3, 20, 3),
+    # dpw tree over Dubins candidates: the configurations the native tree search (csrc/tree.cu) takes over
+    'nonmyopic_mean_dpw_dubins': ('mean', True, 'dpw', 'dubins', 'free', 4, 60, 4),
+    'nonmyopic_mes_dpw_dubins_blocks': ('mes', True, 'dpw', 'dubins', 'block', 3, 40, 3),
+    'nonmyopic_ei_dpw_dubins_channel': ('exp_improve', True, 'dpw', 'dubins', 'channel', 3, 40, 3),
 }
 
 

@@ -271,11 +271,13 @@ def test_evaluation_batched_sweep_equals_per_path_calls(pkg, tmp_path):
 
 # ------------------------------------------------------------------ whole missions of the reference's Robot
 @pytest.mark.parametrize('name', ['myopic_mean_fan', 'myopic_mean_dubins_blocks', 'myopic_mes_fan', 'nonmyopic_mean_dpw',
-                                  'nonmyopic_mean_belief_dubins'])
+                                  'nonmyopic_mean_belief_dubins', 'nonmyopic_mean_dpw_dubins',
+                                  'nonmyopic_mes_dpw_dubins_blocks', 'nonmyopic_ei_dpw_dubins_channel'])
 def test_robot_mission_reproduces_reference_run(pkg, name, tmp_path, monkeypatch):
     """robot_library.Robot.planner + evaluation_library.Evaluation on the device against the SAME seeded mission run by
     the reference's own Robot / Evaluation source (tests/golden/missions.npz): the pose after every step, every
-    observation (so the random streams stay in lock-step), and the per-step metrics."""
+    observation (so the random streams stay in lock-step), and the per-step metrics.  The dpw + Dubins missions run
+    through the native tree search (csrc/tree.cu), which therefore reproduces the reference's own tree code as well."""
     import os
     import sys
     from conftest import GOLDEN, load_golden
@@ -285,8 +287,10 @@ def test_robot_mission_reproduces_reference_run(pkg, name, tmp_path, monkeypatch
     from informative_path_planning_b200 import obstacles as ob
     from informative_path_planning_b200.evaluation_library import Evaluation
     from informative_path_planning_b200.robot_library import Robot
+    from informative_path_planning_b200 import mcts_library as mc
     g = load_golden('missions')
     spec = ms.MISSIONS[name]
+    native_before = mc.cMCTS.native_searches
     monkeypatch.chdir(tmp_path)                                   # planner writes ./figures/<f_rew>/robot_model.csv
     e = Evaluation(ms.mission_world(pkg.OnlineGPModel), spec[0])
     np.random.seed(11)
@@ -308,6 +312,8 @@ def test_robot_mission_reproduces_reference_run(pkg, name, tmp_path, monkeypatch
     got = np.array([[float(e.metrics[n][t]) for n in ms.MISSION_METRICS] for t in range(spec[5])])
     np.testing.assert_allclose(got, g[name + '_metrics'], rtol=2e-5, atol=1e-5)
     assert os.path.exists(os.path.join('figures', spec[0], 'robot_model.csv'))
+    native_expected = spec[5] if (spec[1] and spec[2] == 'dpw' and spec[3] == 'dubins') else 0
+    assert mc.cMCTS.native_searches - native_before == native_expected
     x1, x2, mean_grid, var_grid = r.visualize_world_model(screen=False)
     assert mean_grid.shape == (100, 100) and np.isfinite(mean_grid).all() and (var_grid > 0).all()
     if spec[0] == 'mean':
