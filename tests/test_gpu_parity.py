@@ -1012,3 +1012,34 @@ def test_native_tree_search_steps_aside_when_not_covered(pkg):
         with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
             out = planner.choose_trajectory(t=2)
         assert not planner.native_search_used and len(out) == 8
+
+
+@pytest.mark.parametrize('horizon,step,depth,budget,expect_native', [
+    (1.5, 0.5, 8, 600, True),       # deep tree, many revisits: progressive widening and UCT ties well exercised
+    (3.0, 0.25, 9, 40, True),       # 12-13 points per path x 9 levels > 96: the copy + synchronise form of the rollout pass
+    (3.0, 0.25, 12, 30, False)])    # > 128 points in one rollout: the native search steps aside, the Python tree replays
+def test_native_tree_search_long_rollouts_and_fallbacks(pkg, horizon, step, depth, budget, expect_native):
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200 import obstacles as ob
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    aq = pkg.aq_library
+    w = ob.BugTrap(list(RANGES), (3., 3.), 2., 0.5, 2., 'left')
+    rng = np.random.default_rng(5)
+    X, z = world(rng, 200, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    res = {}
+    for native in (True, False):
+        pg = Dubins_Path_Generator(11, horizon, 0.05, step, RANGES, w)
+        np.random.seed(3); random.seed(4)
+        planner = mc.cMCTS(budget, m, (8.9, 1.2, 2.2), depth, pg, aq.mean_UCB, 'mean', 9, tree_type='dpw')
+        planner.NATIVE_SEARCH = native
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            out = planner.choose_trajectory(t=9)
+        assert planner.native_search_used == (native and expect_native)
+        kids = planner.tree.root.children
+        res[native] = ([c.nqueries for c in kids], [c.reward for c in kids], out[0], out[2], random.random(),
+                       np.random.standard_normal(2))
+    a, b = res[True], res[False]
+    assert a[0] == b[0] and sum(a[0]) == budget and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+    assert a[4] == b[4] and np.array_equal(a[5], b[5])
