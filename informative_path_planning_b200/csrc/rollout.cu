@@ -324,38 +324,51 @@ __device__ __forceinline__ double warp_dot(const double* __restrict__ a, const d
     return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
-// C0[a][b] for the M (M + 1) / 2 pairs b <= a, then mean0[m] = sum_n Kxt[m][n] alpha[n] for M more "pairs": one warp per
-// dot product of length N, fixed summation order.
+// C0[a][b] for the M (M + 1) / 2 pairs b <= a, then mean0[m] = sum_n Kxt[m][n] alpha[n] for M more "pairs".  Each dot
+// product of length N is split over the 4 warps of a quad (contiguous quarters, combined in a fixed order), two dot
+// products per block: with one warp per dot product only ~30 SMs had work at M = 20.
 __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const double* __restrict__ pts,
                                                           const double* __restrict__ T1, const double* __restrict__ Kxt,
                                                           int64_t ldk, int N, int M, double* __restrict__ cov, int64_t ldc,
                                                           const double* __restrict__ alpha, double* __restrict__ mean0) {
-    const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    __shared__ double part[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 2 + (warp >> 2), seg = warp & 3;
     const int pairs = M * (M + 1) / 2;
-    if (pair >= pairs + M) return;
-    if (pair >= pairs) {
-        const int mi = pair - pairs;
-        double s = warp_dot(Kxt + (int64_t)mi * ldk, alpha, N, lane);
+    const bool live = pair < pairs + M;
+    int a = 0, b = 0;
+    const double* u = nullptr;
+    const double* v = nullptr;
+    if (live) {
+        if (pair >= pairs) {
+            u = Kxt + (int64_t)(pair - pairs) * ldk;
+            v = alpha;
+        } else {
+            a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);       // pair = a (a + 1) / 2 + b, b <= a
+            while (a * (a + 1) / 2 > pair) --a;
+            while ((a + 1) * (a + 2) / 2 <= pair) ++a;
+            b = pair - a * (a + 1) / 2;
+            u = T1 + (int64_t)a * ldk;
+            v = Kxt + (int64_t)b * ldk;
+        }
+        const int quarter = (((N + 3) / 4) + 31) / 32 * 32;        // multiple of 32: every warp keeps lane-strided loads
+        const int lo = seg * quarter, hi = (lo + quarter) < N ? (lo + quarter) : N;
+        double s = (lo < hi) ? warp_dot(u + lo, v + lo, hi - lo, lane) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) mean0[mi] = s;
-        return;
+        if (lane == 0) part[warp] = s;
     }
-    int a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);           // pair = a (a + 1) / 2 + b, b <= a
-    while (a * (a + 1) / 2 > pair) --a;
-    while ((a + 1) * (a + 2) / 2 <= pair) ++a;
-    const int b = pair - a * (a + 1) / 2;
-    const double* t = T1 + (int64_t)a * ldk;
-    const double* kx = Kxt + (int64_t)b * ldk;
-    double s = warp_dot(t, kx, N, lane);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-        const double kqq = (D == 2) ? rbf_eval<2>(k, pts + 2 * a, pts + 2 * b) : rbf_eval<3>(k, pts + 3 * a, pts + 3 * b);
-        const double v = kqq - s;
-        cov[(int64_t)a * ldc + b] = v;
-        cov[(int64_t)b * ldc + a] = v;
+    __syncthreads();
+    if (live && seg == 0 && lane == 0) {
+        const double s = (part[warp] + part[warp + 1]) + (part[warp + 2] + part[warp + 3]);
+        if (pair >= pairs) {
+            mean0[pair - pairs] = s;
+        } else {
+            const double kqq = (D == 2) ? rbf_eval<2>(k, pts + 2 * a, pts + 2 * b) : rbf_eval<3>(k, pts + 3 * a, pts + 3 * b);
+            const double val = kqq - s;
+            cov[(int64_t)a * ldc + b] = val;
+            cov[(int64_t)b * ldc + a] = val;
+        }
     }
 }
 
@@ -429,7 +442,7 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
             winv, ldw, (int)N, Kxt, ldk, M, T1);
         IPP_LAUNCH_CHECK();
         const int pairs = M * (M + 1) / 2 + M;                  // covariance pairs + the M mean dot products
-        rollout_cov_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
+        rollout_cov_kernel<<<(unsigned)((pairs + 1) / 2), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
                                                                           (int)N, M, cov0, ldc, alpha, mean0);
         IPP_LAUNCH_CHECK();
     }
