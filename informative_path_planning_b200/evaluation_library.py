@@ -233,8 +233,8 @@ class Evaluation:
         time steps; cumulative sums where the reference accumulates).  No figures are drawn."""
         m = self.metrics
 
-        def col(name):
-            return np.array(list(m[name].values()), dtype=float)
+        def col(name):       # entries are floats, numpy scalars or length-1 arrays (MES max-value samples): one number per step
+            return np.array([float(np.asarray(v, dtype=float).reshape(-1)[0]) for v in m[name].values()], dtype=float)
 
         out_dir = os.path.join(directory, str(self.reward_function))
         if not os.path.exists(out_dir):

@@ -259,7 +259,8 @@ def test_evaluation_batched_sweep_equals_per_path_calls(pkg, tmp_path):
     for t in range(3):
         np.random.seed(t)
         e.update_metrics(t, m, paths, sel, value=0.5 * t, max_loc=g['max_loc'], max_val=float(g['max_val']),
-                         params=[7.0, (1.0, 2.0), [1.0, 2.0, 3.0], [(0, 1), (2, 3), (4, 5)]], dist=float(t))
+                         params=[7.0, (1.0, 2.0), None if t == 0 else np.array([[1.0], [2.0], [3.0]]),     # MES max-value samples: (nK, 1)
+                                 [(0, 1), (2, 3), (4, 5)]], dist=float(t))
     out = e.plot_metrics(str(tmp_path))
     rows = np.loadtxt(out + '/metrics.csv')
     assert rows.shape == (21, 3)
