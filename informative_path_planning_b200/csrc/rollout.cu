@@ -15,7 +15,10 @@
 //   A = C[B,B] + (diag_add / reps[l]) I = L L^T;  H = C[:,B] L^-T;  u = L^-1 (y_B - m_B);  m += H u;  C -= H H^T
 // (the same block appended reps[l] times = one conditioning with the noise divided by reps[l]).  One CTA, everything
 // in shared memory.
+#include <stdlib.h>
+
 #include "internal.cuh"
+#include "dgemm_dmma.cuh"
 
 namespace ipp {
 
@@ -309,6 +312,95 @@ __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const doub
     }
 }
 
+// ---- the same pass on the FP64 tensor pipe.  ncu of the SIMT version at N = 4096 (profiles/r1j_ncu_full_rollout_tw.csv):
+// 90 us, FP64 pipe 41 % busy with 8 warps per SM, DRAM at 19 % -- bound by FP64 FMA issue, not by the 134 MB of W^-1.
+// DMMA.8x8x4 does the same multiply-adds at the tensor rate and takes BOTH operands straight from global memory:
+//   block = 16 rows of W^-1 (2 DMMA row tiles), 8 warps = 8 contiguous slices of the j range (split-K inside the block)
+//   warp, per 32 j: A = W^-1[16 rows][32 j], B = Kxt[<= 32 points][32 j], 8 k-steps x (2 x 4) DMMA tiles
+//   k permutation: thread t (= lane % 4) of a quad supplies j = j0 + 8 t + s in k-step s for A and for B alike, so
+//   every thread reads 8 CONTIGUOUS doubles per row / point (four 16-byte loads) and nothing is staged in shared memory
+// The 8 partial 16 x 32 tiles are summed through shared memory in a fixed order.
+constexpr int TD_ROWS = 16, TD_WARPS = 8, TD_PTS = 32;
+
+__device__ __forceinline__ void td_load8(double (&dst)[8], const double* __restrict__ row, int j, int N) {
+    if (j + 8 <= N) {
+        const double2* p = reinterpret_cast<const double2*>(row + j);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 v = __ldg(p + q);
+            dst[2 * q] = v.x;
+            dst[2 * q + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = (j + q < N) ? __ldg(row + j + q) : 0.0;     // pad columns are not initialised
+    }
+}
+
+__global__ void __launch_bounds__(32 * TD_WARPS, 2) rollout_tw_dmma_kernel(const double* __restrict__ W, int64_t ldw, int N,
+                                                                           const double* __restrict__ Kxt, int64_t ldk,
+                                                                           int M, double* __restrict__ T1) {
+    __shared__ double part[TD_WARPS][TD_ROWS][TD_PTS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int n0 = blockIdx.x * TD_ROWS;
+    const int slice = (((N + TD_WARPS - 1) / TD_WARPS) + 31) / 32 * 32;
+    const int j_lo = warp * slice, j_hi = (j_lo + slice) < N ? (j_lo + slice) : N;
+    const int r0 = (n0 + g) < N ? (n0 + g) : (N - 1), r1 = (n0 + 8 + g) < N ? (n0 + 8 + g) : (N - 1);
+    const double* w0 = W + (int64_t)r0 * ldw;
+    const double* w1 = W + (int64_t)r1 * ldw;
+    for (int m0 = 0; m0 < M; m0 += TD_PTS) {
+        const int mm = (M - m0) < TD_PTS ? (M - m0) : TD_PTS;
+        const int ntiles = (mm + 7) >> 3;
+        const double* kx[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int pnt = m0 + nt * 8 + g;
+            kx[nt] = Kxt + (int64_t)(pnt < M ? pnt : (M - 1)) * ldk;
+        }
+        double c[2][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+        for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
+            const int j = j0 + 8 * t;
+            double a0[8], a1[8];
+            td_load8(a0, w0, j, N);
+            td_load8(a1, w1, j, N);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                if (nt < ntiles) {
+                    double b[8];
+                    td_load8(b, kx[nt], j, N);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        dmma884(c[0][nt][0], c[0][nt][1], a0[ks], b[ks]);
+                        dmma884(c[1][nt][0], c[1][nt][1], a1[ks], b[ks]);
+                    }
+                }
+        }
+        // C fragment: row g (+ 8 mt), columns (points) 2 t, 2 t + 1 of tile nt
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                part[warp][mt * 8 + g][nt * 8 + 2 * t] = c[mt][nt][0];
+                part[warp][mt * 8 + g][nt * 8 + 2 * t + 1] = c[mt][nt][1];
+            }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < TD_ROWS * TD_PTS; idx += 32 * TD_WARPS) {
+            const int pnt = idx / TD_ROWS, row = idx % TD_ROWS;            // consecutive threads -> consecutive n: coalesced
+            if (pnt < mm && n0 + row < N) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < TD_WARPS; ++w) sum += part[w][row][pnt];
+                T1[(int64_t)(m0 + pnt) * ldk + n0 + row] = sum;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // One lane's share of a length-N dot product with 8 independent accumulators: 16 loads in flight per lane instead of a
 // dependent load -> fma chain (one L2 round trip per 32 elements: 34 us for the covariance pass at N = 4096).
 __device__ __forceinline__ double warp_dot(const double* __restrict__ a, const double* __restrict__ b, int N, int lane) {
@@ -370,6 +462,12 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
             cov[(int64_t)b * ldc + a] = val;
         }
     }
+}
+
+// IPP_ROLLOUT_TW=simt selects the SIMT pass (A/B measurements); the tensor pass is the default
+static bool tw_use_dmma() {
+    static const int use = [] { const char* e = getenv("IPP_ROLLOUT_TW"); return (e && e[0] == 's') ? 0 : 1; }();
+    return use != 0;
 }
 
 static size_t rollout_smem(int M) {
@@ -436,10 +534,15 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
             else rollout_rbf_kernel<3><<<nb, 256, 0, stream>>>(kd, X, (int)N, pts, M, Kxt, ldk);
         }
         IPP_LAUNCH_CHECK();
-        IPP_OPT_IN_SMEM(rollout_tw_kernel, TW_SMEM);
-        constexpr int rows_per_block = TW_ROWS_PER_BLOCK;
-        rollout_tw_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 32 * TW_WARPS, TW_SMEM, stream>>>(
-            winv, ldw, (int)N, Kxt, ldk, M, T1);
+        if (tw_use_dmma()) {
+            rollout_tw_dmma_kernel<<<(unsigned)((N + TD_ROWS - 1) / TD_ROWS), 32 * TD_WARPS, 0, stream>>>(
+                winv, ldw, (int)N, Kxt, ldk, M, T1);
+        } else {
+            IPP_OPT_IN_SMEM(rollout_tw_kernel, TW_SMEM);
+            constexpr int rows_per_block = TW_ROWS_PER_BLOCK;
+            rollout_tw_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 32 * TW_WARPS, TW_SMEM, stream>>>(
+                winv, ldw, (int)N, Kxt, ldk, M, T1);
+        }
         IPP_LAUNCH_CHECK();
         const int pairs = M * (M + 1) / 2 + M;                  // covariance pairs + the M mean dot products
         rollout_cov_kernel<<<(unsigned)((pairs + 1) / 2), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
