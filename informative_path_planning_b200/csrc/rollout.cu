@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, 1) rollout_tw_kernel(const doub
 //   k permutation: thread t (= lane % 4) of a quad supplies j = j0 + 8 t + s in k-step s for A and for B alike, so
 //   every thread reads 8 CONTIGUOUS doubles per row / point (four 16-byte loads) and nothing is staged in shared memory
 // The 8 partial 16 x 32 tiles are summed through shared memory in a fixed order.
-constexpr int TD_ROWS = 16, TD_WARPS = 8, TD_PTS = 32;
+constexpr int TD_ROWS = 16, TD_WARPS = 8, TD_PTS = 32, TD_PREFETCH = 128;
 
 __device__ __forceinline__ void td_load8(double (&dst)[8], const double* __restrict__ row, int j, int N) {
     if (j + 8 <= N) {
@@ -367,6 +367,10 @@ __global__ void __launch_bounds__(32 * TD_WARPS, 2) rollout_tw_dmma_kernel(const
             double a0[8], a1[8];
             td_load8(a0, w0, j, N);
             td_load8(a1, w1, j, N);
+            if (j0 + TD_PREFETCH < j_hi) {        // W^-1 is the only HBM stream: pull the lines of a later chunk into L2 now
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + j + TD_PREFETCH));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w1 + j + TD_PREFETCH));
+            }
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
                 if (nt < ntiles) {
