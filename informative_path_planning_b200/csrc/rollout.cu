@@ -120,7 +120,64 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
         // ---- condition (m, C) on the block observation; only rows >= b0 are read later.  Appending the SAME noisy
         // block r times (the reference's double add_data, Q4) is one conditioning on that observation with the noise
         // divided by r: r independent readings that all equal y are one reading of y with variance diag_add / r.
-        if (p.reps[l] > 0) {
+        if (p.reps[l] > 0 && kb <= 4) {
+            // Blocks of up to 4 points (the usual candidate path: horizon / sample step = 3-4 samples): EVERY thread
+            // factors the 4 x 4 block redundantly in registers (identity-padded, fully unrolled) and substitutes its own
+            // row and the residual -- two barrier-separated phases per level instead of 3 kb + 3.  ncu of the generic sweep
+            // below at M = 20: 20 us, barrier stalls 6.5 per issued instruction (profiles/r1j_ncu_full_rollout_condition.csv).
+            const double dadd = p.diag_add / (double)p.reps[l];
+            const int R = M - b0;
+            __syncthreads();
+            double Lf[4][4], rd[4], u[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b)
+                    Lf[a][b] = (a < kb) ? C[(b0 + a) * ldc + b0 + b] + (a == b ? dadd : 0.0) : (a == b ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double d = Lf[j][j];
+                if (!(d > 0.0)) { if (tid == 0) s_bad = l + 1; d = 1.0; }
+                const double r = rsqrt(d);
+                rd[j] = r;
+#pragma unroll
+                for (int i = j + 1; i < 4; ++i) Lf[i][j] *= r;
+#pragma unroll
+                for (int i = j + 1; i < 4; ++i)
+#pragma unroll
+                    for (int c = j + 1; c <= i; ++c) Lf[i][c] = fma(-Lf[i][j], Lf[c][j], Lf[i][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {                     // u = L^-1 (y_B - m_B), in every thread
+                double v = (a < kb) ? p.zobs[b0 + a] - m[b0 + a] : 0.0;
+#pragma unroll
+                for (int c = 0; c < a; ++c) v = fma(-Lf[a][c], u[c], v);
+                u[a] = v * rd[a];
+            }
+            const int i = b0 + tid;                           // this thread's point (M <= 128 < RO_THREADS: at most one)
+            double dm = 0.0;
+            if (i < M) {
+                double h[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    double v = (a < kb) ? C[i * ldc + b0 + a] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < a; ++c) v = fma(-Lf[a][c], h[c], v);
+                    h[a] = v * rd[a];
+                    H[i * HL + a] = h[a];
+                    dm = fma(h[a], u[a], dm);
+                }
+            }
+            __syncthreads();                                  // H complete; everybody is done reading m[B] and C[:, B]
+            if (i < M) m[i] += dm;
+            for (int idx = tid; idx < R * R; idx += RO_THREADS) {
+                const int ii = b0 + idx / R, jj = b0 + idx % R;
+                double sacc = 0.0;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) sacc = fma(H[ii * HL + a], H[jj * HL + a], sacc);
+                C[ii * ldc + jj] -= sacc;
+            }
+        } else if (p.reps[l] > 0) {
             // Right-looking elimination of the panel [C[b0:, B] + dadd I ; (y_B - m_B)^T] by all threads: after column a,
             // H[i][a] = (L^-1 C[B, i])_a for every remaining point i and H[M][a] = u_a = (L^-1 (y_B - m_B))_a -- the
             // Cholesky factor of the block, the forward substitutions of every row and of the residual in one sweep
