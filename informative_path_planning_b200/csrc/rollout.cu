@@ -62,8 +62,13 @@ struct RolloutArgs {
     unsigned int done_seq;
 };
 
+// Kernels 2-4 of a rollout are launched with programmatic stream serialisation: their blocks are scheduled while the
+// previous kernel still runs and wait here until it has completed and its writes are visible (a no-op otherwise).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(RolloutArgs p) {
     extern __shared__ __align__(16) double sm[];
+    grid_dependency_wait();
     const int M = p.M, ldc = M + 1;
     double* C = sm;                              // [M][M+1]
     double* m = C + (size_t)M * ldc;             // [M]
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(32 * TD_WARPS, 2) rollout_tw_dmma_kernel(const
                                                                            const double* __restrict__ Kxt, int64_t ldk,
                                                                            int M, double* __restrict__ T1) {
     __shared__ double part[TD_WARPS][TD_ROWS][TD_PTS + 1];
+    grid_dependency_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int n0 = blockIdx.x * TD_ROWS;
     const int slice = (((N + TD_WARPS - 1) / TD_WARPS) + 31) / 32 * 32;
@@ -485,6 +491,7 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
                                                           int64_t ldk, int N, int M, double* __restrict__ cov, int64_t ldc,
                                                           const double* __restrict__ alpha, double* __restrict__ mean0) {
     __shared__ double part[8];
+    grid_dependency_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = blockIdx.x * 2 + (warp >> 2), seg = warp & 3;
     const int pairs = M * (M + 1) / 2;
@@ -529,6 +536,20 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
 static bool tw_use_dmma() {
     static const int use = [] { const char* e = getenv("IPP_ROLLOUT_TW"); return (e && e[0] == 's') ? 0 : 1; }();
     return use != 0;
+}
+
+static cudaLaunchConfig_t dependent_launch(unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                           cudaLaunchAttribute* attr) {
+    attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr->val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
 }
 
 static size_t rollout_smem(int M) {
@@ -581,6 +602,7 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
     double* cov0 = work;
     double* mean0 = cov0 + (int64_t)M * ldc;
     double* sub = mean0 + round_up(M, 2);
+    cudaLaunchAttribute pdl;
     {
         const int64_t ldk = round_up(N, 16);
         double* Kxt = sub;
@@ -596,8 +618,8 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         }
         IPP_LAUNCH_CHECK();
         if (tw_use_dmma()) {
-            rollout_tw_dmma_kernel<<<(unsigned)((N + TD_ROWS - 1) / TD_ROWS), 32 * TD_WARPS, 0, stream>>>(
-                winv, ldw, (int)N, Kxt, ldk, M, T1);
+            cudaLaunchConfig_t cfg = dependent_launch((unsigned)((N + TD_ROWS - 1) / TD_ROWS), 32 * TD_WARPS, 0, stream, &pdl);
+            IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_tw_dmma_kernel, winv, ldw, (int)N, (const double*)Kxt, ldk, M, T1));
         } else {
             IPP_OPT_IN_SMEM(rollout_tw_kernel, TW_SMEM);
             constexpr int rows_per_block = TW_ROWS_PER_BLOCK;
@@ -606,8 +628,11 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         }
         IPP_LAUNCH_CHECK();
         const int pairs = M * (M + 1) / 2 + M;                  // covariance pairs + the M mean dot products
-        rollout_cov_kernel<<<(unsigned)((pairs + 1) / 2), 256, 0, stream>>>(to_dev(*kern), kern->dim, pts, T1, Kxt, ldk,
-                                                                          (int)N, M, cov0, ldc, alpha, mean0);
+        {
+            cudaLaunchConfig_t cfg = dependent_launch((unsigned)((pairs + 1) / 2), 256, 0, stream, &pdl);
+            IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_cov_kernel, to_dev(*kern), (int)kern->dim, (const double*)pts,
+                                        (const double*)T1, (const double*)Kxt, ldk, (int)N, M, cov0, ldc, alpha, mean0));
+        }
         IPP_LAUNCH_CHECK();
     }
     p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc; p.zobs = zobs;
@@ -615,7 +640,10 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
     p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;
     p.done = done; p.done_seq = done_seq;
     IPP_OPT_IN_SMEM(rollout_condition_kernel, (int)rollout_smem(RO_MAX_POINTS));
-    rollout_condition_kernel<<<1, RO_THREADS, rollout_smem(M), stream>>>(p);
+    {
+        cudaLaunchConfig_t cfg = dependent_launch(1, RO_THREADS, rollout_smem(M), stream, &pdl);
+        IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_condition_kernel, p));
+    }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
