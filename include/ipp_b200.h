@@ -45,6 +45,8 @@ typedef struct ipp_rbf {
 #define IPP_REWARD_UCB    0   /* aq_library.py:82-114  mean_UCB                         */
 #define IPP_REWARD_EI     1   /* aq_library.py:556-582 exp_improvement                  */
 #define IPP_REWARD_MES    2   /* aq_library.py:281-337 mves                             */
+#define IPP_REWARD_NAIVE  3   /* aq_library.py:339-367 naive: host-side, ipp_tree_search_dpw only (reads no belief) */
+#define IPP_REWARD_NAIVE_VALUE 4 /* aq_library.py:369-413 naive_value: sampled functions on the device, ipp_tree_search_dpw only */
 
 /* variance formulations for ipp_gp_predict */
 #define IPP_VAR_WINV_SYM  0   /* var = v - k^T W^-1 k, W^-1 symmetric: lower tiles x2 + diagonal tiles (N^2 flops/query) */
@@ -294,7 +296,8 @@ typedef struct {
 typedef struct {
     int32_t budget;        /* rollouts */
     int32_t max_depth;     /* rollout_length */
-    int32_t kind;          /* IPP_REWARD_UCB / EI / MES */
+    int32_t kind;          /* IPP_REWARD_UCB / EI / MES; IPP_REWARD_NAIVE (no device work at all) or IPP_REWARD_NAIVE_VALUE
+                            * (one small device pass per rollout); for the last two the belief pointers may be NULL */
     int32_t frontier_size;
     int32_t keep_every;    /* 10 */
     int32_t n_obstacles;
@@ -306,6 +309,20 @@ typedef struct {
     const double* angles;             /* [frontier_size] host */
     const ipp_obstacle_box* obstacles;/* [n_obstacles] host, may be NULL */
     const double* prior_scale;        /* [IPP_APPEND_MAX_K + 1][IPP_APPEND_MAX_K] host */
+    const double* naive_locs;         /* IPP_REWARD_NAIVE: sampled maximisers [n_naive][2] host; reward_param = radius */
+    int32_t n_naive;                  /* number of sampled maxima (both naive kinds) */
+    int32_t rff_features;             /* IPP_REWARD_NAIVE_VALUE: F */
+    /* IPP_REWARD_NAIVE_VALUE: the n_naive sampled functions f_s(x) = sum_f theta[s][f] cos(W[s][f] . x + b[s][f]) (theta
+     * pre-scaled as for ipp_rff_eval_argmax), their maxima, and scratch: vals_dev / vals_host (pinned)
+     * [n_naive][IPP_ROLLOUT_MAX_POINTS] (+ n_naive doubles and n_naive int64 at the end of vals_dev for the unused
+     * arg-max outputs), rff_work = ipp_rff_workspace(F, n_naive, IPP_ROLLOUT_MAX_POINTS, 0); reward_param = tolerance */
+    const double* rff_W;              /* device [n_naive][F][D] */
+    const double* rff_b;              /* device [n_naive][F] */
+    const double* rff_theta;          /* device [n_naive][F] */
+    const double* naive_maxes;        /* host [n_naive] */
+    double* rff_vals_dev;
+    double* rff_vals_host;
+    double* rff_work;
 } ipp_tree_params;
 int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
                         const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,

@@ -17,7 +17,7 @@ IPP_MAX_DIM = 3
 IPP_APPEND_MAX_K = 32
 IPP_ROLLOUT_MAX_POINTS = 128
 IPP_ROLLOUT_MAX_LEVELS = 32
-REWARD_UCB, REWARD_EI, REWARD_MES = 0, 1, 2
+REWARD_UCB, REWARD_EI, REWARD_MES, REWARD_NAIVE, REWARD_NAIVE_VALUE = 0, 1, 2, 3, 4
 VAR_WINV_SYM, VAR_WINV_FULL, VAR_CHOL = 0, 1, 2
 
 
@@ -38,7 +38,11 @@ class IppTreeParams(ctypes.Structure):
                 ('c', ctypes.c_double), ('reward_param', ctypes.c_double), ('time', ctypes.c_double),
                 ('horizon', ctypes.c_double), ('turning_radius', ctypes.c_double), ('dense_step', ctypes.c_double),
                 ('border', ctypes.c_double), ('extent', ctypes.c_double * 4),
-                ('angles', ctypes.c_void_p), ('obstacles', ctypes.c_void_p), ('prior_scale', ctypes.c_void_p)]
+                ('angles', ctypes.c_void_p), ('obstacles', ctypes.c_void_p), ('prior_scale', ctypes.c_void_p),
+                ('naive_locs', ctypes.c_void_p), ('n_naive', ctypes.c_int32), ('rff_features', ctypes.c_int32),
+                ('rff_W', ctypes.c_void_p), ('rff_b', ctypes.c_void_p), ('rff_theta', ctypes.c_void_p),
+                ('naive_maxes', ctypes.c_void_p), ('rff_vals_dev', ctypes.c_void_p), ('rff_vals_host', ctypes.c_void_p),
+                ('rff_work', ctypes.c_void_p)]
 
 
 IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 32 + 16

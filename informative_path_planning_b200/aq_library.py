@@ -211,6 +211,31 @@ def naive_value(time, xvals, robot_model, param, FVECTOR=False):
     return f if FVECTOR else np.sum(f)
 
 
+def naive_levels(f_rew, time, level_points, robot_model, param):
+    """[naive / naive_value (time, x, robot_model, param) for x in level_points] -- the rewards of one tree-search rollout.
+    Neither reward reads the belief (naive: distances to the sampled maximisers; naive_value: the sampled functions
+    themselves), so a rollout needs none of its simulated belief updates.  naive_value evaluates each sampled function
+    ONCE on all points of the rollout (one device call per function instead of one per function and level)."""
+    if f_rew == 'naive':
+        return [naive(time, x, robot_model, param) for x in level_points]
+    max_vals, _, funcs = param[0]
+    if max_vals is None or funcs is None:
+        return [0.0 for _ in level_points]
+    queries = [_queries(time, x, robot_model)[1] for x in level_points]
+    offs = np.cumsum([0] + [q.shape[0] for q in queries])
+    allq = np.vstack(queries)
+    means = [funcs[i](allq) for i in range(max_vals.shape[0])]
+    out = []
+    for l in range(len(queries)):
+        f = np.zeros((queries[l].shape[0], 1))
+        for i in range(max_vals.shape[0]):
+            mean = means[i][offs[l]:offs[l + 1]]
+            f += (np.fabs(mean - max_vals[i][0]) <= param[1]).astype(float).reshape(f.shape)
+        f = f / float(max_vals.shape[0])
+        out.append(np.sum(f))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ batched rewards
 def flatten_paths(paths, dimension=2, time=0):
     """paths: sequence of per-path point lists/arrays (k_p, >=2) -> (queries (M, D), offsets (P+1,) int64)."""

@@ -84,6 +84,24 @@ inline double np_gauss(Mt& g, ipp_mt_state* st) {
     return f * x2;
 }
 
+// np.sum of a contiguous float64 vector (numpy's pairwise summation: < 8 elements sequentially, else 8 running sums
+// combined as a tree, remainder appended; blocks of 128 are not reached by a path's <= 32 points)
+inline double np_pairwise_sum(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
 // ---- candidate paths of one pose: Path_Generator.generate_frontier_points (paths_library.py:44-83) + buffered_paths
 struct PathSet {
     std::vector<int32_t> goal;       // goal index of each kept path
@@ -227,10 +245,20 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                                    int64_t* reward_evals, int32_t* status, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(valid_params(prm), "bad tree parameters");
-    IPP_CHECK_ARG(root_pose && kern && X && alpha && winv && py_rng && np_rng && stage_host && stage_dev && work, "null pointer");
+    const bool value_reward = prm->kind == IPP_REWARD_NAIVE_VALUE;
+    const bool host_reward = prm->kind == IPP_REWARD_NAIVE || value_reward;        // rewards that read no belief
+    IPP_CHECK_ARG(root_pose && kern && py_rng && np_rng, "null pointer");
+    IPP_CHECK_ARG(host_reward || (X && alpha && winv && stage_host && stage_dev && work), "null pointer");
     IPP_CHECK_ARG(n_root && root_goal && root_visits && root_reward && reward_evals && status, "null output pointer");
-    IPP_CHECK_ARG(N >= 1 && (kern->dim == 2 || kern->dim == 3), "needs a belief with data, 2 or 3 input dimensions");
-    IPP_CHECK_ARG(prm->kind == IPP_REWARD_UCB || prm->kind == IPP_REWARD_EI || prm->kind == IPP_REWARD_MES, "unknown reward kind");
+    IPP_CHECK_ARG((host_reward || N >= 1) && (kern->dim == 2 || kern->dim == 3), "needs a belief with data, 2 or 3 input dimensions");
+    IPP_CHECK_ARG(prm->kind == IPP_REWARD_UCB || prm->kind == IPP_REWARD_EI || prm->kind == IPP_REWARD_MES || host_reward,
+                  "unknown reward kind");
+    IPP_CHECK_ARG(prm->kind != IPP_REWARD_NAIVE || (prm->naive_locs && prm->n_naive >= 1),
+                  "the naive reward needs the sampled maximisers");
+    IPP_CHECK_ARG(!value_reward || (prm->rff_W && prm->rff_b && prm->rff_theta && prm->naive_maxes && prm->rff_vals_dev &&
+                                    prm->rff_vals_host && prm->rff_work && prm->n_naive >= 1 && prm->rff_features >= 1 &&
+                                    stage_host && stage_dev),
+                  "the naive_value reward needs the sampled functions and its scratch buffers");
     const ipp_tree_params& P = *prm;
     const int D = kern->dim;
     // work on copies of the generators: they are only written back when the whole search succeeded
@@ -262,7 +290,8 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     bool zero_copy = false;
     {
         void* dp = nullptr;
-        if (cudaHostGetDevicePointer(&dp, stage_host, 0) == cudaSuccess && dp) {
+        if (host_reward) {
+        } else if (cudaHostGetDevicePointer(&dp, stage_host, 0) == cudaSuccess && dp) {
             m_out = static_cast<double*>(dp) + (h_out - stage_host);
             m_flag = reinterpret_cast<unsigned int*>(static_cast<double*>(dp) + (h_flag - stage_host));
             zero_copy = true;
@@ -272,7 +301,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     }
     static unsigned int seq_base = 0;                                            // completion words never repeat a value
     unsigned int seq = (seq_base += 1u << 20);
-    *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
+    if (!host_reward) *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
     ipp::RolloutInline inl;
 
     int max_samp = 0;
@@ -395,7 +424,65 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         walk_us += t_dev - t_walk;
         double reward = 0.0;
         const int L = (int)levels.size();
-        if (L > 0) {
+        if (L > 0 && value_reward) {
+            // naive_value (aq_library.py:369-413): share of the sampled functions whose value at the point lies within the
+            // tolerance of that function's maximum; the functions are evaluated for all points of the rollout in one pass
+            int M = 0;
+            for (const Level& lv : levels) M += lv.k;
+            if (M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }
+            int row = 0;
+            for (int l = 0; l < L; ++l) {
+                const Node& a = nodes[levels[l].node];
+                if (a.k > IPP_APPEND_MAX_K) { *status = 1; return IPP_OK; }
+                for (int i = 0; i < a.k; ++i, ++row) {
+                    h_in[(size_t)row * D] = pool[a.data + 3 * i];
+                    h_in[(size_t)row * D + 1] = pool[a.data + 3 * i + 1];
+                    if (D == 3) h_in[(size_t)row * D + 2] = P.time;
+                }
+            }
+            const int S_ = P.n_naive;
+            double* d_max = P.rff_vals_dev + (size_t)S_ * IPP_ROLLOUT_MAX_POINTS;
+            int64_t* d_arg = reinterpret_cast<int64_t*>(d_max + S_);
+            IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, stream));
+            const int rc = ipp_rff_eval_argmax(P.rff_W, P.rff_b, P.rff_theta, P.rff_features, S_, D, 0, d_in, M, P.rff_vals_dev,
+                                               d_max, d_arg, P.rff_work, stream_);
+            if (rc != IPP_OK) return rc;
+            IPP_CUDA(cudaMemcpyAsync(P.rff_vals_host, P.rff_vals_dev, sizeof(double) * (size_t)S_ * M, cudaMemcpyDeviceToHost, stream));
+            IPP_CUDA(cudaStreamSynchronize(stream));
+            row = 0;
+            for (int l = 0; l < L; ++l) {
+                const int k = nodes[levels[l].node].k;
+                double f[IPP_APPEND_MAX_K];
+                for (int i = 0; i < k; ++i) f[i] = 0.0;
+                for (int sidx = 0; sidx < S_; ++sidx)
+                    for (int i = 0; i < k; ++i)
+                        f[i] += (fabs(P.rff_vals_host[(size_t)sidx * M + row + i] - P.naive_maxes[sidx]) <= P.reward_param) ? 1.0 : 0.0;
+                for (int i = 0; i < k; ++i) f[i] = f[i] / (double)S_;
+                reward = reward + np_pairwise_sum(f, k);
+                row += k;
+            }
+            evals += L;
+        } else if (L > 0 && host_reward) {
+            // naive (aq_library.py:339-367): share of the sampled maximisers within `radius` of each point, summed over the
+            // level's points the way np.sum does (pairwise, np_pairwise_sum); no belief, no device
+            for (int l = 0; l < L; ++l) {
+                const Node& a = nodes[levels[l].node];
+                double f[IPP_APPEND_MAX_K];
+                if (a.k > IPP_APPEND_MAX_K) { *status = 1; return IPP_OK; }
+                for (int i = 0; i < a.k; ++i) f[i] = 0.0;
+                for (int sidx = 0; sidx < P.n_naive; ++sidx) {
+                    const double lx = P.naive_locs[2 * sidx], ly = P.naive_locs[2 * sidx + 1];
+                    for (int i = 0; i < a.k; ++i) {
+                        const double dx = pool[a.data + 3 * i] - lx, dy = pool[a.data + 3 * i + 1] - ly;
+                        const double dist = sqrt(dx * dx + dy * dy);
+                        f[i] += (dist <= P.reward_param) ? 1.0 : 0.0;
+                    }
+                }
+                for (int i = 0; i < a.k; ++i) f[i] = f[i] / (double)P.n_naive;
+                reward = reward + np_pairwise_sum(f, a.k);
+            }
+            evals += L;
+        } else if (L > 0) {
             int M = 0;
             for (const Level& lv : levels) M += lv.k;
             if (L > IPP_ROLLOUT_MAX_LEVELS || M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }

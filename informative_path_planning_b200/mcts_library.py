@@ -167,6 +167,9 @@ class Tree(object):
         """Reward kind + parameters when the whole rollout can be scored by one device call, else None."""
         if not self.fuse_rollouts:
             return None
+        if (_BELIEF_FREE_REWARDS.get(self.aquisition_function) == self.f_rew and isinstance(belief, GPModel)
+                and belief.model is None):
+            return 'host', None, None        # naive / naive_value never read the belief: no simulated updates needed
         fast = _FAST_REWARDS.get(self.aquisition_function)
         if fast is None or fast != self.f_rew or not isinstance(belief, GPModel):
             return None
@@ -195,6 +198,11 @@ class Tree(object):
         if not levels:
             return reward
         kind, params, maxes_d = fused
+        if kind == 'host':
+            for r in aqlib.naive_levels(self.f_rew, self.t, [x for x, _, _ in levels], belief, self.param):
+                reward = reward + r
+            self.reward_evals += len(levels)
+            return reward
         n_pts = sum(x.shape[0] for x, _, _ in levels)
         ok = (len(levels) <= aqlib.L.IPP_ROLLOUT_MAX_LEVELS and n_pts <= aqlib.L.IPP_ROLLOUT_MAX_POINTS
               and max(x.shape[0] for x, _, _ in levels) <= aqlib.L.IPP_APPEND_MAX_K)
@@ -401,6 +409,8 @@ class BeliefTree(Tree):
 
 # acquisition callables of this package that have a sync-free device form, by reward name
 _FAST_REWARDS = {aqlib.mean_UCB: 'mean', aqlib.mves: 'mes', aqlib.exp_improvement: 'exp_improve'}
+# rewards that do not depend on the belief at all (reference aq_library.py:339-413)
+_BELIEF_FREE_REWARDS = {aqlib.naive: 'naive', aqlib.naive_value: 'naive_value'}
 
 
 def exploration_constant(f_rew, tree_type):
@@ -493,6 +503,34 @@ class cMCTS(object):
         if fused is None or scale is None or belief.dimension not in (2, 3):
             return False
         kind, params, maxes_d = fused
+        naive_locs, rff = None, None
+        if kind == 'host':
+            # naive: pure geometry against the sampled maximisers, computed inside the native search (no device work at
+            # all); naive_value evaluates the sampled functions and stays with the Python tree
+            if tree.param is None or tree.param[0][0] is None:
+                return False
+            max_vals, max_locs, funcs = tree.param[0]
+            if self.f_rew == 'naive':
+                if max_locs is None:
+                    return False
+                kind, params = L.REWARD_NAIVE, [float(tree.param[1])]
+                naive_locs = np.ascontiguousarray(np.asarray(max_locs, dtype=np.float64)[:, :2])
+            else:
+                # naive_value: the sampled functions evaluated on the device for all points of a rollout in one pass
+                if (funcs is None or len(funcs) != max_vals.shape[0] or len(funcs) == 0
+                        or not all(isinstance(f, aqlib.RFFTarget) for f in funcs)
+                        or len({f.nFeatures for f in funcs}) != 1):
+                    return False
+                kind, params = L.REWARD_NAIVE_VALUE, [float(tree.param[1])]
+                S_, F_ = len(funcs), funcs[0].nFeatures
+                rff = {'W': L.to_device(np.stack([np.asarray(f.W, dtype=np.float64) for f in funcs])),
+                       'b': L.to_device(np.stack([np.asarray(f.b, dtype=np.float64).reshape(-1) for f in funcs])),
+                       'theta': L.to_device(np.stack([np.asarray(f.theta, dtype=np.float64).reshape(-1) * f.scale for f in funcs])),
+                       'maxes': np.ascontiguousarray(np.asarray(max_vals, dtype=np.float64).reshape(-1)),
+                       'vals_d': torch.empty(S_ * L.IPP_ROLLOUT_MAX_POINTS + 2 * S_ + 2, dtype=torch.float64, device=L.device()),
+                       'vals_h': torch.empty(S_ * L.IPP_ROLLOUT_MAX_POINTS, dtype=torch.float64).pin_memory(),
+                       'work': torch.empty(int(L.lib.ipp_rff_workspace(F_, S_, L.IPP_ROLLOUT_MAX_POINTS, 0)),
+                                           dtype=torch.float64, device=L.device())}
         pose = np.array([float(v) for v in self.cp], dtype=np.float64)
         if pose.shape[0] != 3:
             return False
@@ -509,6 +547,14 @@ class cMCTS(object):
         prm.angles = angles.ctypes.data
         prm.obstacles = ctypes.cast(boxes[0], ctypes.c_void_p).value if boxes[1] else None
         prm.prior_scale = scale.ctypes.data
+        if naive_locs is not None:
+            prm.naive_locs, prm.n_naive = naive_locs.ctypes.data, int(naive_locs.shape[0])
+        if rff is not None:
+            prm.n_naive, prm.rff_features = int(rff['W'].shape[0]), int(rff['W'].shape[1])
+            prm.rff_W, prm.rff_b, prm.rff_theta = rff['W'].data_ptr(), rff['b'].data_ptr(), rff['theta'].data_ptr()
+            prm.naive_maxes = rff['maxes'].ctypes.data
+            prm.rff_vals_dev, prm.rff_vals_host = rff['vals_d'].data_ptr(), rff['vals_h'].data_ptr()
+            prm.rff_work = rff['work'].data_ptr()
         dev = L.device()
         stage = _native_stage.get(dev.index)
         if stage is None:

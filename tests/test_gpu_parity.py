@@ -1043,3 +1043,41 @@ def test_native_tree_search_long_rollouts_and_fallbacks(pkg, horizon, step, dept
     a, b = res[True], res[False]
     assert a[0] == b[0] and sum(a[0]) == budget and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
     assert a[4] == b[4] and np.array_equal(a[5], b[5])
+
+
+@pytest.mark.parametrize('f_rew,tree_type', [('naive', 'dpw'), ('naive_value', 'dpw'), ('naive', 'belief'), ('naive_value', 'belief')])
+def test_naive_reward_rollouts_skip_the_belief_updates(pkg, f_rew, tree_type):
+    """naive / naive_value (aq_library.py:339-413, the rewards of the reference's current sweep, run_sim_all.sh:17) never
+    read the belief: rollouts scored without their simulated add_data calls give the same visit counts, bit-identical
+    reward sums and the same action as the reference's per-level sequence, and leave the random streams in the same
+    state."""
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    aq = pkg.aq_library
+    rng = np.random.default_rng(12)
+    X, z = world(rng, 120, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    fn = {'naive': aq.naive, 'naive_value': aq.naive_value}[f_rew]
+    radius = {'naive': 1.5, 'naive_value': 3.0}[f_rew]
+    res = {}
+    for fuse in (True, False):
+        pg = Dubins_Path_Generator(11, 1.5, 0.05, 0.5, RANGES)
+        np.random.seed(8); random.seed(9)
+        planner = mc.cMCTS(60, m, (4.4, 5.3, 1.1), 4, pg, fn, f_rew, 5, aq_param=(3, radius), tree_type=tree_type)
+        mc.Tree.FUSE_ROLLOUTS = fuse
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+                out = planner.choose_trajectory(t=5)
+        finally:
+            mc.Tree.FUSE_ROLLOUTS = True
+        kids = planner.tree.root.children
+        res[fuse] = ([c.nqueries for c in kids], [float(c.reward) for c in kids], out[0], float(out[2]), random.random(),
+                     np.random.standard_normal(2), planner.tree.reward_evals)
+        # the dpw search runs natively: naive with no device work at all, naive_value with one small pass per rollout that
+        # evaluates the sampled functions; the belief tree stays with the Python tree
+        assert planner.native_search_used == (fuse and tree_type == 'dpw')
+    a, b = res[True], res[False]
+    assert a[0] == b[0] and sum(a[0]) == 60 and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+    assert a[4] == b[4] and np.array_equal(a[5], b[5]) and a[6] == b[6]
+    assert max(a[1]) > 0                                        # some rollouts came near the sampled maxima

@@ -35,11 +35,12 @@ def run(kind, n_obs, f_rew, budget=250, depth=5, fuse=True, native=True):
         model = OnlineGPModelOracle(R, 1.0, 100.0, noise=0.5); cls = mc.cMCTSOracle
     model.add_data(X, z)
     pg = PG(15, 1.5, 0.05, 0.5, R)
-    base = {'mean': aq.mean_UCB, 'mes': aq.mves}[f_rew]
+    base = {'mean': aq.mean_UCB, 'mes': aq.mves, 'naive': aq.naive, 'naive_value': aq.naive_value}[f_rew]
+    aq_param = {'naive': (3, 1.5), 'naive_value': (3, 3.0)}.get(f_rew)
     fn = CountingFn(base) if kind == 'cpu' else base       # the device planner counts evals itself (tree.reward_evals)
     np.random.seed(5); random.seed(6)
     with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
-        m = cls(budget, model, (5.0, 5.0, 0.3), depth, pg, fn, f_rew, 3, tree_type='dpw')
+        m = cls(budget, model, (5.0, 5.0, 0.3), depth, pg, fn, f_rew, 3, aq_param=aq_param, tree_type='dpw')
         t0 = time.perf_counter(); m.choose_trajectory(t=3); dt = time.perf_counter() - t0
     nq = [c.nqueries for c in m.tree.root.children]
     n_evals = fn.n if kind == 'cpu' else m.tree.reward_evals
