@@ -268,8 +268,10 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
 /* ---- a12 / 8f rank 1: one whole planning step of the DPW tree search on the host side of the library -- the walk,
  *      the progressive widening, the Dubins candidate sets, the simulated observations and the random draws of
  *      Tree.get_next_leaf / leaf_helper / get_next_child (mcts_library.py:347-455) in native code, with ONE
- *      ipp_rollout_rewards launch sequence + one stream synchronisation per rollout.  Replaces the Python interpreter on
- *      the per-rollout critical path; the search it performs is the SAME search: both random streams the reference
+ *      ipp_rollout_rewards launch sequence per rollout: the rollout's points travel by value in the kernel parameters,
+ *      the rewards are written straight into the pinned stage buffer and the host polls a completion word (no copy and
+ *      no driver synchronisation; rollouts with more than 96 points use copies + a stream synchronisation).  Replaces the
+ *      Python interpreter on the per-rollout critical path; the search it performs is the SAME search: both random streams the reference
  *      consumes are continued bit for bit --
  *        py_rng: CPython's `random` Mersenne Twister (random.getstate(): 624 words + index); random.choice(seq) is
  *                seq[_randbelow(len(seq))], getrandbits(bit_length(n)) = genrand_uint32() >> (32 - k) redrawn while >= n;
@@ -279,7 +281,9 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
  *      Simulated observations are prior draws z_i = gauss_i * prior_scale[k][i] (np.random.multivariate_normal(0,
  *      variance I_k), mcts_library.py:418-422, whose SVD transform of a scaled identity is a constant diagonal).
  *      Candidate paths: frontier goals pose + horizon (cos, sin)(heading + angles[i]) (paths_library.py:44-83) joined by
- *      shortest Dubins curves, sampled and trimmed as ipp_dubins_path_set does.
+ *      shortest Dubins curves, sampled and trimmed as ipp_dubins_path_set does -- one goal at a time on the walk, the
+ *      remaining goals of a node while the host waits for the device (same children, same order, same selection).
+ *      Single-threaded per process (the reference planner is: SURVEY 8b), one search at a time.
  *      status[0]: 0 = done; 1 = a rollout could not be scored in one call (block not positive definite, or more than
  *      IPP_ROLLOUT_MAX_POINTS / LEVELS) -- nothing is written back and the caller must run its own search from the
  *      unchanged random states.  root_goal / root_visits / root_reward [frontier_size + 1]: the root's action children in
