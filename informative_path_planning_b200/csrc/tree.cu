@@ -189,6 +189,39 @@ bool valid_params(const ipp_tree_params* p) {
            p->n_obstacles <= IPP_MAX_OBSTACLES && (p->n_obstacles == 0 || p->obstacles);
 }
 
+// naive_value: the n_naive sampled functions at the M points of one rollout.  One block; a warp per (function, point)
+// pair, lanes striding the F features (the grid evaluator of rff.cu maps one THREAD to a point, which is the right
+// shape for 10^5 grid points and a 30 us serial loop for 20).  Points arrive by value, values go straight to pinned
+// host memory, `done` is set to `seq` once they are visible there.
+__global__ void __launch_bounds__(1024) rff_points_kernel(const double* __restrict__ W, const double* __restrict__ b,
+                                                          const double* __restrict__ theta, int F, int S, int D,
+                                                          const __grid_constant__ ipp::RolloutInline pp, int M,
+                                                          double* __restrict__ vals, unsigned int* done, unsigned int seq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int pair = warp; pair < S * M; pair += nwarps) {
+        const int sidx = pair / M, m = pair % M;
+        const double* w = W + (size_t)sidx * F * D;
+        double x[3] = {pp.v[m * D], pp.v[m * D + 1], D == 3 ? pp.v[m * D + 2] : 0.0};
+        double acc = 0.0;
+        for (int f = lane; f < F; f += 32) {
+            double arg = b[(size_t)sidx * F + f];
+            for (int d = 0; d < D; ++d) arg = fma(w[(size_t)f * D + d], x[d], arg);
+            acc = fma(theta[(size_t)sidx * F + f], cos(arg), acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            vals[(size_t)sidx * M + m] = acc;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(done) = seq;
+    }
+}
+
 double g_walk_us = 0.0, g_device_us = 0.0;      // host-side split of the last search (ipp_tree_last_timing)
 inline double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -290,7 +323,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     bool zero_copy = false;
     {
         void* dp = nullptr;
-        if (host_reward) {
+        if (host_reward && !value_reward) {
         } else if (cudaHostGetDevicePointer(&dp, stage_host, 0) == cudaSuccess && dp) {
             m_out = static_cast<double*>(dp) + (h_out - stage_host);
             m_flag = reinterpret_cast<unsigned int*>(static_cast<double*>(dp) + (h_flag - stage_host));
@@ -299,9 +332,15 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             cudaGetLastError();                                                  // clear the sticky "not mapped" error
         }
     }
+    double* m_vals = nullptr;                                                    // naive_value: the pinned value buffer as the device sees it
+    if (value_reward && zero_copy) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, prm->rff_vals_host, 0) == cudaSuccess && dp) m_vals = static_cast<double*>(dp);
+        else cudaGetLastError();
+    }
     static unsigned int seq_base = 0;                                            // completion words never repeat a value
     unsigned int seq = (seq_base += 1u << 20);
-    if (!host_reward) *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
+    if (!host_reward || value_reward) *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
     ipp::RolloutInline inl;
 
     int max_samp = 0;
@@ -441,14 +480,33 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 }
             }
             const int S_ = P.n_naive;
-            double* d_max = P.rff_vals_dev + (size_t)S_ * IPP_ROLLOUT_MAX_POINTS;
-            int64_t* d_arg = reinterpret_cast<int64_t*>(d_max + S_);
-            IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, stream));
-            const int rc = ipp_rff_eval_argmax(P.rff_W, P.rff_b, P.rff_theta, P.rff_features, S_, D, 0, d_in, M, P.rff_vals_dev,
-                                               d_max, d_arg, P.rff_work, stream_);
-            if (rc != IPP_OK) return rc;
-            IPP_CUDA(cudaMemcpyAsync(P.rff_vals_host, P.rff_vals_dev, sizeof(double) * (size_t)S_ * M, cudaMemcpyDeviceToHost, stream));
-            IPP_CUDA(cudaStreamSynchronize(stream));
+            if (zero_copy && m_vals && M <= ipp::RO_INLINE_POINTS) {
+                memcpy(inl.v, h_in, sizeof(double) * (size_t)M * D);
+                ++seq;
+                rff_points_kernel<<<1, 1024, 0, stream>>>(P.rff_W, P.rff_b, P.rff_theta, P.rff_features, S_, D, inl, M, m_vals,
+                                                          m_flag, seq);
+                IPP_LAUNCH_CHECK();
+                const double t_spin = now_us();
+                for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int*>(h_flag) != seq; ++spins) {
+                    if (complete_some()) continue;
+                    if ((spins & 0xffff) == 0xffff && now_us() - t_spin > 5e6) {
+                        IPP_CUDA(cudaStreamSynchronize(stream));
+                        if (*reinterpret_cast<volatile unsigned int*>(h_flag) == seq) break;
+                        ::ipp::set_error("%s: rollout %d never completed", __func__, it);
+                        return IPP_E_CUDA;
+                    }
+                }
+                __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            } else {
+                double* d_max = P.rff_vals_dev + (size_t)S_ * IPP_ROLLOUT_MAX_POINTS;
+                int64_t* d_arg = reinterpret_cast<int64_t*>(d_max + S_);
+                IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, stream));
+                const int rc = ipp_rff_eval_argmax(P.rff_W, P.rff_b, P.rff_theta, P.rff_features, S_, D, 0, d_in, M,
+                                                   P.rff_vals_dev, d_max, d_arg, P.rff_work, stream_);
+                if (rc != IPP_OK) return rc;
+                IPP_CUDA(cudaMemcpyAsync(P.rff_vals_host, P.rff_vals_dev, sizeof(double) * (size_t)S_ * M, cudaMemcpyDeviceToHost, stream));
+                IPP_CUDA(cudaStreamSynchronize(stream));
+            }
             row = 0;
             for (int l = 0; l < L; ++l) {
                 const int k = nodes[levels[l].node].k;
