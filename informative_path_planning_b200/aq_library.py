@@ -424,6 +424,30 @@ def rff_theta_batch_device(Z_d, N, zvals, noise_var, eps):
     return Theta[:, :S].cpu().numpy()
 
 
+def rff_theta_ul(Z_d, N, zvals, noise_var, eps, z_d=None):
+    """One posterior weight draw of the N >= F branch (reference aq_library.py:195-200):
+    Sigma = (Z Z^T / s2 + I)^-1, m = Sigma Z z / s2, theta = m + chol(Sigma) eps -- without forming Sigma or factoring it.
+    With the UL factorisation A = Z Z^T / s2 + I = U U^T (U upper triangular: the Cholesky factor of A with rows and
+    columns reversed, reversed back), Sigma = U^-T U^-1 and U^-T is lower triangular with a positive diagonal, i.e.
+    chol(Sigma) = U^-T exactly.  So m and chol(Sigma) eps are three triangular solves.  The N-dependent work (the F x F x N
+    product and Z z) runs on the device; the F x F factorisation and the solves are host LAPACK, as in the reference.
+    eps: (F, 1).  Returns theta (F, 1)."""
+    import scipy.linalg
+    F = eps.shape[0]
+    A_d = _gemm_nt(Z_d, Z_d, F, F, N, alpha=1.0 / noise_var)
+    zrow = torch.zeros((1, Z_d.stride(0)), dtype=torch.float64, device=Z_d.device)
+    zrow[0, :N] = z_d.reshape(-1)[:N] if z_d is not None else L.to_device(np.asarray(zvals, dtype=float).reshape(-1))
+    Zz_d = _gemm_nt(Z_d, zrow, F, 1, N)
+    host = torch.cat([A_d[:, :F].reshape(-1), Zz_d[:, 0]]).cpu().numpy()          # one transfer, one synchronisation
+    A = host[:F * F].reshape(F, F) + np.eye(F)
+    rhs = host[F * F:] / noise_var
+    U = np.linalg.cholesky(A[::-1, ::-1])[::-1, ::-1]                              # A = U U^T
+    w = scipy.linalg.solve_triangular(U, rhs, lower=False, check_finite=False)
+    m = scipy.linalg.solve_triangular(U.T, w, lower=True, check_finite=False)
+    y = scipy.linalg.solve_triangular(U.T, np.asarray(eps, dtype=float).reshape(-1), lower=True, check_finite=False)
+    return (m + y).reshape(F, 1)
+
+
 def global_maximization(target, target_vector_n, target_grad, target_vector_gradient_n, ranges, guesses, visualize,
                         filename, obstacles, f_rew, time=None, guesses_d=None):
     """reference aq_library.py:444-553 without the plotting; the grid stage (:475-485) runs on the device
@@ -495,11 +519,13 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
         ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
         W = np.random.normal(loc=0.0, scale=np.sqrt(1. / ls), size=(nFeatures, d))
         b = 2 * np.pi * np.random.uniform(low=0.0, high=1.0, size=(nFeatures, 1))
-        Z_d = rff_features_device(W, b, robot_model._X_d, variance, nFeatures)
+        W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))           # uploaded once: features now, the sampled function later
+        Z_d = rff_features_device(W_d, b_d, robot_model._X_d, variance, nFeatures)
         eps = np.random.normal(loc=0.0, scale=1.0, size=(nFeatures, 1))
         try:
-            if N_obs >= nFeatures:      # F x F inverse + Cholesky on the device (:195-200); Z never leaves it
-                theta = rff_theta_batch_device(Z_d, N_obs, robot_model.zvals, robot_model.noise, eps)
+            if N_obs >= nFeatures:      # (:195-200) F x F x N product on the device, UL factor + three solves on the host
+                theta = rff_theta_ul(Z_d, N_obs, robot_model.zvals, robot_model.noise, eps,
+                                     z_d=getattr(robot_model, '_z_d', None))
             else:                       # N x N eigendecomposition (:177-187): small dense LAPACK on the host
                 Z = np.ascontiguousarray(Z_d[:, :N_obs].cpu().numpy())
                 theta = _rff_theta(Z, robot_model.zvals, robot_model.noise, eps, nFeatures)
@@ -507,6 +533,7 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
             delete_locs.append(i)
             continue
         target = RFFTarget(variance, nFeatures, W, theta, b)
+        target._dev = (W_d, b_d, L.to_device(theta.reshape(-1) * target.scale))
         target_vector_n = lambda x, tg=target: -tg.scalar(x)
         target_vector_gradient_n = lambda x, tg=target: -np.asarray(tg.gradient(x).reshape(d, ))
         status = False
