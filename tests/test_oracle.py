@@ -256,3 +256,50 @@ def test_evaluation_metrics_match_reference(rf):
     for name, want in zip(g['names'], g['metrics_' + rf]):
         np.testing.assert_allclose(got[str(name)], want, rtol=1e-7, atol=1e-9, err_msg=str(name))
     np.testing.assert_allclose(np.array(e.inst_regret(3, paths, sel, m), dtype=float), g['regret_' + rf], rtol=1e-8)
+
+
+@pytest.mark.parametrize('name', ['myopic_mean_fan', 'myopic_mes_fan', 'nonmyopic_mean_dpw', 'myopic_mean_dubins_blocks'])
+def test_oracle_missions_match_reference_runs(name):
+    """The oracle stack end to end (RobotOracle.planner over OnlineGPModelOracle, aq_oracle, mcts_oracle and
+    EvaluationOracle) against whole seeded missions of the reference's own Robot + Evaluation source
+    (tests/golden/missions.npz): pose after every step, every observation, the prediction-dependent metrics."""
+    import sys
+    from conftest import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import mission_spec as ms
+    from oracle.evaluation_oracle import EvaluationOracle
+    from oracle.robot_oracle import RobotOracle
+    g = load_golden('missions')
+    f_rew, nonmyopic, tree_type, gen, obstacle_kind, T, budget, rl = ms.MISSIONS[name]
+    ev = EvaluationOracle(ms.mission_world(OnlineGPModelOracle), f_rew)
+    if gen == 'default':
+        pg = mo.PathGeneratorOracle(15, 1.5, 0.05, 0.5, RANGES)
+    else:       # the `dubins` C library is absent: the package's closed-form generator, Python trimming loop (no native code)
+        from informative_path_planning_b200 import obstacles as ob
+        from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+        pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES, ms.mission_obstacles(ob, obstacle_kind))
+        pg.use_native = False
+    rows, locs = [], []
+
+    def record(t, robot_model, all_paths, selected_path, value, max_loc, max_val, dist, current_max):
+        m = ev.step_metrics(t, robot_model, all_paths, selected_path, max_loc, max_val)
+        m.update(aquisition_function=value, current_highest_obs=current_max, distance_traveled=dist)
+        rows.append([float(m[n]) for n in ms.MISSION_METRICS])
+
+    np.random.seed(11)
+    random.seed(12)
+    r = RobotOracle(ms.mission_sample_world, (5.0, 5.0, 0.0), RANGES, 1.0, 100.0, 0.5, pg, f_rew, nonmyopic, budget, rl,
+                    tree_type, evaluation=record, prior_dataset=ms.mission_prior())
+    orig = r.collect_observations
+
+    def spy(xobs):
+        orig(xobs)
+        locs.append(np.array(xobs[-1], dtype=float))
+    r.collect_observations = spy
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+        r.planner(T=T)
+    np.testing.assert_allclose(np.array(locs), g[name + '_locs'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.GP.xvals, g[name + '_X'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.GP.zvals, g[name + '_z'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(np.array(rows), g[name + '_metrics'], rtol=1e-6, atol=1e-7)
