@@ -24,8 +24,8 @@ def _world(kind):
 
 
 @pytest.mark.parametrize('world_kind,pose,budget,depth,horizon,step', [
-    ('free', (5.2, 4.6, 0.7), 400, 5, 1.5, 0.5), ('block', (5.0, 5.0, 0.0), 300, 4, 1.5, 0.5),
-    ('trap', (8.9, 1.2, 2.2), 500, 7, 1.5, 0.5), ('free', (0.6, 9.4, -2.0), 250, 5, 3.0, 0.25)])
+    ('free', (5.2, 4.6, 0.7), 250, 5, 1.5, 0.5), ('block', (5.0, 5.0, 0.0), 200, 4, 1.5, 0.5),
+    ('trap', (8.9, 1.2, 2.2), 300, 7, 1.5, 0.5), ('free', (0.6, 9.4, -2.0), 120, 5, 3.0, 0.25)])
 def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, depth, horizon, step):
     from informative_path_planning_b200 import _lib as L
     from informative_path_planning_b200 import mcts_library as mc
