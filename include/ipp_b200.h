@@ -336,6 +336,9 @@ int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
                         double* stage_host, double* stage_dev, double* work,
                         int32_t* n_root, int32_t* root_goal, int64_t* root_visits, double* root_reward,
                         int64_t* reward_evals, int32_t* status, void* stream);
+/* sizeof of the structs that cross this ABI, in declaration order: ipp_rbf, ipp_obstacle_box, ipp_mt_state,
+ * ipp_tree_params -- lets a binding verify its own struct definitions against the library it loaded */
+int ipp_abi_struct_sizes(int32_t out[4]);
 /* where the last ipp_tree_search_dpw spent its wall time: the tree walk (selection, candidate paths, draws) and the
  * device pass (staging + launches + synchronisation), microseconds summed over the rollouts */
 int ipp_tree_last_timing(double* walk_us, double* device_us);

@@ -128,6 +128,7 @@ SIGNATURES = {
     'ipp_tree_search_dpw': (_INT, [ctypes.POINTER(IppTreeParams), _P, _RBF, _P, _I64, _P, _P, _I64, _D, _D, _P, _I64,
                                    ctypes.POINTER(IppMtState), ctypes.POINTER(IppMtState), _P, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _P]),
+    'ipp_abi_struct_sizes': (_INT, [_P]),
     'ipp_tree_last_timing': (_INT, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'ipp_rng_py_choices': (_INT, [ctypes.POINTER(IppMtState), _P, _INT, _P]),
     'ipp_rng_np_normals': (_INT, [ctypes.POINTER(IppMtState), _INT, _P]),
@@ -150,6 +151,22 @@ def _load():
 
 
 lib = _load()
+
+
+def _check_struct_sizes():
+    """The ctypes mirrors above against sizeof() in the library that was actually loaded (a stale .so or an edited
+    header would otherwise corrupt memory silently)."""
+    from .obstacles import IppObstacleBox
+    out = (ctypes.c_int32 * 4)()
+    if lib.ipp_abi_struct_sizes(out) != 0:
+        raise ImportError('libipp_b200: ipp_abi_struct_sizes failed')
+    want = [ctypes.sizeof(IppRbf), ctypes.sizeof(IppObstacleBox), ctypes.sizeof(IppMtState), ctypes.sizeof(IppTreeParams)]
+    if list(out) != want:
+        raise ImportError('libipp_b200.so and its Python binding disagree on struct sizes (library %s, binding %s): '
+                          'rebuild with __graft_entry__.build()' % (list(out), want))
+
+
+_check_struct_sizes()
 
 
 def check(rc):

@@ -229,6 +229,15 @@ inline double now_us() {
 
 }  // namespace
 
+extern "C" int ipp_abi_struct_sizes(int32_t out[4]) {
+    IPP_CHECK_ARG(out, "null pointer");
+    out[0] = (int32_t)sizeof(ipp_rbf);
+    out[1] = (int32_t)sizeof(ipp_obstacle_box);
+    out[2] = (int32_t)sizeof(ipp_mt_state);
+    out[3] = (int32_t)sizeof(ipp_tree_params);
+    return IPP_OK;
+}
+
 extern "C" int ipp_tree_last_timing(double* walk_us, double* device_us) {
     IPP_CHECK_ARG(walk_us && device_us, "null pointer");
     *walk_us = g_walk_us;

@@ -37,7 +37,14 @@ def test_python_binding_covers_the_header():
 
 def test_struct_layout_matches_header():
     from informative_path_planning_b200 import _lib
+    from informative_path_planning_b200.obstacles import IppObstacleBox
     assert ctypes.sizeof(_lib.IppRbf) == 40          # int32 + pad, double, double[3]
+    sizes = (ctypes.c_int32 * 4)()
+    assert _lib.lib.ipp_abi_struct_sizes(sizes) == 0
+    assert list(sizes) == [ctypes.sizeof(_lib.IppRbf), ctypes.sizeof(IppObstacleBox), ctypes.sizeof(_lib.IppMtState),
+                           ctypes.sizeof(_lib.IppTreeParams)]
+    assert _lib.IPP_TREE_STAGE_DOUBLES == (_lib.IPP_ROLLOUT_MAX_POINTS * (_lib.IPP_MAX_DIM + 1)
+                                           + _lib.IPP_ROLLOUT_MAX_LEVELS + 16)
     k = _lib.make_rbf(2, 100.0, 1.0)
     assert (k.dim, k.variance, k.inv_lengthscale[0], k.inv_lengthscale[1], k.inv_lengthscale[2]) == (2, 100.0, 1.0, 1.0, 0.0)
     k3 = _lib.make_rbf(3, 4.0, (2.0, 4.0, 8.0))
