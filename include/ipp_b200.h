@@ -281,7 +281,7 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
  *      Simulated observations are prior draws z_i = gauss_i * prior_scale[k][i] (np.random.multivariate_normal(0,
  *      variance I_k), mcts_library.py:418-422, whose SVD transform of a scaled identity is a constant diagonal).
  *      Candidate paths: frontier goals pose + horizon (cos, sin)(heading + angles[i]) (paths_library.py:44-83) joined by
- *      shortest Dubins curves, sampled and trimmed as ipp_dubins_path_set does -- one goal at a time on the walk, the
+ *      shortest Dubins curves, sampled and trimmed as ipp_dubins_path_set does (or by the straight fan, `generator`) -- one goal at a time on the walk, the
  *      remaining goals of a node while the host waits for the device (same children, same order, same selection).
  *      Single-threaded per process (the reference planner is: SURVEY 8b), one search at a time.
  *      status[0]: 0 = done; 1 = a rollout could not be scored in one call (block not positive definite, or more than
@@ -327,6 +327,11 @@ typedef struct {
     double* rff_vals_dev;
     double* rff_vals_host;
     double* rff_work;
+    /* candidate generator: 0 = Dubins_Path_Generator (paths_library.py:141-189), 1 = the straight fan of Path_Generator
+     * (:85-105: round(distance / sample_step) points every sample_step along the goal heading; no trimming) */
+    int32_t generator;
+    int32_t reserved;
+    double sample_step;
 } ipp_tree_params;
 int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
                         const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,

@@ -140,6 +140,21 @@ int frontier_goals(const ipp_tree_params& p, const double* cp, double* goals) {
 // kept samples of the path pose -> goal (0 = dropped); samp[max_samp][3]
 inline int goal_path(const ipp_tree_params& p, const double* cp, const double* goal, double* samp, int max_samp,
                      int max_dense) {
+    if (p.generator == 1) {
+        // Path_Generator.make_sample_paths (paths_library.py:85-105): numpy scalar arithmetic restated (x ** 2 is pow(x, 2),
+        // round() is round-half-even); a path exists as soon as it has one point
+        const double distance = sqrt(pow(cp[0] - goal[0], 2.0) + pow(cp[1] - goal[1], 2.0));
+        const int n = (int)nearbyint(distance / p.sample_step);
+        if (n < 1) return 0;
+        if (n > max_samp) return -1;
+        for (int j = 0; j < n; ++j) {
+            const double step = (double)(j + 1) * p.sample_step;
+            samp[3 * j] = cp[0] + step * cos(goal[2]);
+            samp[3 * j + 1] = cp[1] + step * sin(goal[2]);
+            samp[3 * j + 2] = goal[2];
+        }
+        return n;
+    }
     int dn = 0;
     const int n = dubins_one(cp, goal, p.turning_radius, p.dense_step, p.keep_every, p.extent, p.border, p.obstacles,
                              p.n_obstacles, samp, max_samp, nullptr, max_dense, &dn, nullptr);
@@ -156,7 +171,7 @@ void build_path_set(const ipp_tree_params& p, const double* cp, PathSet& out) {
     std::vector<double> tmp((size_t)max_samp * 3);
     for (int gi = 0; gi < G; ++gi) {
         const int n = goal_path(p, cp, &goals[3 * gi], tmp.data(), max_samp, max_dense);
-        if (n == 0) continue;
+        if (n <= 0) continue;
         out.goal.push_back(gi);
         out.count.push_back(n);
         out.samp.insert(out.samp.end(), tmp.begin(), tmp.end());
@@ -185,6 +200,7 @@ struct Node {
 
 bool valid_params(const ipp_tree_params* p) {
     return p && p->angles && p->prior_scale && p->budget >= 0 && p->max_depth >= 1 && p->frontier_size >= 1 &&
+           (p->generator == 0 || (p->generator == 1 && p->sample_step > 0)) &&
            p->keep_every >= 1 && p->turning_radius > 0 && p->dense_step > 0 && p->n_obstacles >= 0 &&
            p->n_obstacles <= IPP_MAX_OBSTACLES && (p->n_obstacles == 0 || p->obstacles);
 }
@@ -356,6 +372,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     const int max_dense = path_limits(P, &max_samp);
     std::vector<double> tmp_path((size_t)max_samp * 3);
     std::vector<int> incomplete;                                                  // belief nodes with goals still to try
+    bool overflow = false;
     // try the next goal of belief node b; true when it produced an action child
     auto expand_one = [&](int b) -> bool {
         const int gi = nodes[b].g_next++;
@@ -363,7 +380,8 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         memcpy(pose, nodes[b].pose, sizeof(pose));
         memcpy(goal, &pool[nodes[b].goals + 3 * (size_t)gi], sizeof(goal));
         const int n = goal_path(P, pose, goal, tmp_path.data(), max_samp, max_dense);
-        if (n == 0) return false;
+        if (n < 0) overflow = true;                                               // more samples than the buffers hold
+        if (n <= 0) return false;
         Node a;
         a.action = true;
         a.depth = nodes[b].depth;
@@ -467,6 +485,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 cur = child;
             }
         }
+        if (overflow) { *status = 1; return IPP_OK; }
         // ---- settle: all rewards of the rollout in one device pass
         const double t_dev = now_us();
         walk_us += t_dev - t_walk;

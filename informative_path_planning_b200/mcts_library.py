@@ -461,7 +461,7 @@ class cMCTS(object):
             return ((self.max_val, self.max_locs, self.target), self.aq_param[1])
         return None
 
-    NATIVE_SEARCH = True       # dpw tree + Dubins generator + a fused reward: run the whole search in libipp_b200.so
+    NATIVE_SEARCH = True       # dpw tree + Dubins / straight-fan generator + a fused reward: the whole search in libipp_b200.so
     native_searches = 0        # how many searches (all instances) went through ipp_tree_search_dpw
 
     def search(self, t, param, budget=None):
@@ -490,13 +490,19 @@ class cMCTS(object):
         Returns False -- with nothing consumed from the random streams -- when the configuration is not covered
         (other generators / rewards, no data yet) or a rollout needs the per-level fallback."""
         import ctypes
-        from .paths_library import Dubins_Path_Generator
+        from .paths_library import Dubins_Path_Generator, Path_Generator
         L = aqlib.L
         pg, belief, tree = self.path_generator, self.GP, self.tree
-        if type(pg) is not Dubins_Path_Generator or not pg.use_native or not isinstance(belief, GPModel):
+        if not isinstance(belief, GPModel):
             return False
-        boxes = pg._obstacle_boxes()
-        if boxes is None or boxes[1] > 16:
+        if type(pg) is Dubins_Path_Generator and pg.use_native:
+            generator = 0
+            boxes = pg._obstacle_boxes()
+            if boxes is None or boxes[1] > 16:
+                return False
+        elif type(pg) is Path_Generator:
+            generator, boxes = 1, (None, 0)          # the straight fan (reference :85-105) looks at no obstacle
+        else:
             return False
         fused = tree._fused_kind(belief)
         scale = _prior_scale_table(belief.variance)
@@ -543,6 +549,7 @@ class cMCTS(object):
         prm.time = float(t)
         prm.horizon, prm.turning_radius = float(pg.hl), float(pg.tr)
         prm.dense_step, prm.border = float(pg.ss / 10), float(3 * pg.tr)
+        prm.generator, prm.sample_step = generator, float(pg.ss)
         prm.extent[:] = [float(e) for e in pg.extent]
         prm.angles = angles.ctypes.data
         prm.obstacles = ctypes.cast(boxes[0], ctypes.c_void_p).value if boxes[1] else None
@@ -583,7 +590,7 @@ class cMCTS(object):
             return False
         L.set_py_rng_state(py_state, py_extra)
         L.set_np_rng_state(np_state)
-        paths, dense_paths = pg.get_path_set_lazy(self.cp)
+        paths, dense_paths = pg.get_path_set_lazy(self.cp) if generator == 0 else pg.get_path_set(self.cp)
         keys = list(paths.keys())
         n = int(n_root[0])
         if keys != [int(g) for g in root_goal[:n]]:

@@ -995,7 +995,8 @@ def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n
 
 
 def test_native_tree_search_steps_aside_when_not_covered(pkg):
-    """Straight-fan generator, belief tree, no data yet: the interpreter keeps the search (and the native path says so)."""
+    """Belief tree, no data yet, a generator subclass the library does not know: the interpreter keeps the search (and the
+    native path says so); the plain straight fan with a dpw tree is covered natively."""
     from informative_path_planning_b200 import mcts_library as mc
     from informative_path_planning_b200.paths_library import Dubins_Path_Generator, Path_Generator
     aq = pkg.aq_library
@@ -1004,14 +1005,17 @@ def test_native_tree_search_steps_aside_when_not_covered(pkg):
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
     empty = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
     m.add_data(X, z)
-    cases = [(m, Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw'), (m, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'belief'),
-             (empty, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw')]
-    for model, pg, tree_type in cases:
+    class MyFan(Path_Generator):                 # user subclass: may override anything, so it stays with the Python tree
+        pass
+    cases = [(m, MyFan(8, 1.5, 0.05, 0.5, RANGES), 'dpw', False), (m, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'belief', False),
+             (empty, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw', False),
+             (m, Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw', True)]
+    for model, pg, tree_type, native in cases:
         np.random.seed(1); random.seed(2)
         planner = mc.cMCTS(12, model, (5.0, 5.0, 0.2), 3, pg, aq.mean_UCB, 'mean', 2, tree_type=tree_type)
         with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
             out = planner.choose_trajectory(t=2)
-        assert not planner.native_search_used and len(out) == 8
+        assert planner.native_search_used == native and len(out) == 8
 
 
 @pytest.mark.parametrize('horizon,step,depth,budget,expect_native', [

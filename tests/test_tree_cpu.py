@@ -25,12 +25,13 @@ def _world(kind):
 
 @pytest.mark.parametrize('world_kind,pose,budget,depth,horizon,step', [
     ('free', (5.2, 4.6, 0.7), 250, 5, 1.5, 0.5), ('block', (5.0, 5.0, 0.0), 200, 4, 1.5, 0.5),
-    ('trap', (8.9, 1.2, 2.2), 300, 7, 1.5, 0.5), ('free', (0.6, 9.4, -2.0), 120, 5, 3.0, 0.25)])
+    ('trap', (8.9, 1.2, 2.2), 300, 7, 1.5, 0.5), ('free', (0.6, 9.4, -2.0), 120, 5, 3.0, 0.25),
+    ('fan', (5.2, 4.6, 0.7), 250, 5, 1.5, 0.5), ('fan', (9.3, 0.8, 2.9), 200, 6, 1.7, 0.4)])
 def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, depth, horizon, step):
     from informative_path_planning_b200 import _lib as L
     from informative_path_planning_b200 import mcts_library as mc
     from informative_path_planning_b200.obstacles import box_array
-    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator, Path_Generator
     from oracle import aq_oracle
     from oracle.gpmodel_oracle import OnlineGPModelOracle
     rng = np.random.default_rng(7)
@@ -41,10 +42,11 @@ def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, 
     max_locs = np.array([[6.1, 5.2], [4.0, 6.4], [7.7, 2.1]])
     radius = 1.5
     param = ((np.array([[20.], [21.], [19.]]), max_locs, None), radius)
-    world = _world(world_kind)
+    fan = world_kind == 'fan'                                       # the straight fan of Path_Generator instead of Dubins curves
+    world = None if fan else _world(world_kind)
 
     # ---- Python tree (reference per-level sequence on the CPU oracle belief)
-    pg = Dubins_Path_Generator(15, horizon, 0.05, step, RANGES, world)
+    pg = (Path_Generator if fan else Dubins_Path_Generator)(15, horizon, 0.05, step, RANGES, world)
     np.random.seed(31); random.seed(32)
     np.random.standard_normal(1)                                   # leave a cached Gaussian behind
     planner = mc.cMCTS(budget, belief, pose, depth, pg, aq_oracle.naive, 'naive', 4, aq_param=(3, radius), tree_type='dpw')
@@ -64,6 +66,7 @@ def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, 
     prm.frontier_size, prm.keep_every, prm.n_obstacles = 15, 10, nb
     prm.c, prm.reward_param, prm.time = float(planner.c), radius, 4.0
     prm.horizon, prm.turning_radius, prm.dense_step, prm.border = horizon, 0.05, float(step / 10), float(3 * 0.05)
+    prm.generator, prm.sample_step = (1 if fan else 0), float(step)
     prm.extent[:] = list(RANGES)
     prm.angles, prm.prior_scale = angles.ctypes.data, scale.ctypes.data
     prm.obstacles = ctypes.cast(boxes, vp).value if nb else None
