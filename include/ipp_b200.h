@@ -265,7 +265,8 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
                             const ipp_obstacle_box* obstacles_host, int n_obstacles,
                             double* samp, int32_t* counts, int max_samp, double* end_pose, void* stream);
 
-/* ---- a12 / 8f rank 1: one whole planning step of the DPW tree search on the host side of the library -- the walk,
+/* ---- a12 / 8f rank 1: one whole planning step of the tree search (DPW Tree, or BeliefTree: `tree_type`) on the host side
+ *      of the library -- the walk,
  *      the progressive widening, the Dubins candidate sets, the simulated observations and the random draws of
  *      Tree.get_next_leaf / leaf_helper / get_next_child (mcts_library.py:347-455) in native code, with ONE
  *      ipp_rollout_rewards launch sequence per rollout: the rollout's points travel by value in the kernel parameters,
@@ -330,8 +331,13 @@ typedef struct {
     /* candidate generator: 0 = Dubins_Path_Generator (paths_library.py:141-189), 1 = the straight fan of Path_Generator
      * (:85-105: round(distance / sample_step) points every sample_step along the goal heading; no trimming) */
     int32_t generator;
-    int32_t reserved;
+    /* 0 = Tree (DPW, mcts_library.py:314-488); 1 = BeliefTree (:491-632): MLE (zero) observations, a new belief child per
+     * traversal, UCB1 selection, and a uniformly random rollout (np.random.randint) below the first unvisited action */
+    int32_t tree_type;
     double sample_step;
+    /* BeliefTree: log_table[n] = np.log(float(n)) for n = 0 .. budget as the CALLER's numpy computes it (its SIMD log need
+     * not agree with libm in the last bit; taking the caller's values keeps the UCB1 scores the interpreter's) */
+    const double* log_table;
 } ipp_tree_params;
 int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
                         const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,

@@ -42,8 +42,8 @@ class IppTreeParams(ctypes.Structure):
                 ('naive_locs', ctypes.c_void_p), ('n_naive', ctypes.c_int32), ('rff_features', ctypes.c_int32),
                 ('rff_W', ctypes.c_void_p), ('rff_b', ctypes.c_void_p), ('rff_theta', ctypes.c_void_p),
                 ('naive_maxes', ctypes.c_void_p), ('rff_vals_dev', ctypes.c_void_p), ('rff_vals_host', ctypes.c_void_p),
-                ('rff_work', ctypes.c_void_p), ('generator', ctypes.c_int32), ('reserved', ctypes.c_int32),
-                ('sample_step', ctypes.c_double)]
+                ('rff_work', ctypes.c_void_p), ('generator', ctypes.c_int32), ('tree_type', ctypes.c_int32),
+                ('sample_step', ctypes.c_double), ('log_table', ctypes.c_void_p)]
 
 
 IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 32 + 16

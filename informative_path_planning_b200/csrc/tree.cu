@@ -84,6 +84,18 @@ inline double np_gauss(Mt& g, ipp_mt_state* st) {
     return f * x2;
 }
 
+// np.random.randint(0, high) of the legacy global RandomState (int64 path, range < 2^32): masked rejection over 32-bit
+// draws; a one-value range consumes nothing
+inline int np_randint(Mt& g, int high) {
+    const uint32_t rng = (uint32_t)(high - 1);
+    if (rng == 0) return 0;
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t val;
+    do { val = g.next() & mask; } while (val > rng);
+    return (int)val;
+}
+
 // np.sum of a contiguous float64 vector (numpy's pairwise summation: < 8 elements sequentially, else 8 running sums
 // combined as a tree, remainder appended; blocks of 128 are not reached by a path's <= 32 points)
 inline double np_pairwise_sum(const double* a, int n) {
@@ -200,6 +212,7 @@ struct Node {
 
 bool valid_params(const ipp_tree_params* p) {
     return p && p->angles && p->prior_scale && p->budget >= 0 && p->max_depth >= 1 && p->frontier_size >= 1 &&
+           (p->tree_type == 0 || (p->tree_type == 1 && p->log_table)) &&
            (p->generator == 0 || (p->generator == 1 && p->sample_step > 0)) &&
            p->keep_every >= 1 && p->turning_radius > 0 && p->dense_step > 0 && p->n_obstacles >= 0 &&
            p->n_obstacles <= IPP_MAX_OBSTACLES && (p->n_obstacles == 0 || p->obstacles);
@@ -330,7 +343,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     nodes.emplace_back();
     memcpy(nodes[0].pose, root_pose, sizeof(double) * 3);
 
-    struct Level { int node; size_t z; int k; int reps; };
+    struct Level { size_t data; size_t z; int k; int reps; };      // pool offsets of the points [k][3] and the observation [k]
     std::vector<Level> levels;
     std::vector<int> ties;
     int64_t evals = 0;
@@ -408,6 +421,38 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         return false;
     };
 
+    const bool belief_tree = P.tree_type == 1;
+    const size_t z_zero = pool.size();                                            // BeliefTree: MLE observation of a belief without a GPy model = zeros
+    pool.resize(pool.size() + IPP_APPEND_MAX_K, 0.0);
+    PathSet ps;
+    std::vector<std::pair<size_t, int>> acts;
+    // BeliefTree.random_rollouts (mcts_library.py:499-525) from belief node b: uniformly random actions (np.random.randint,
+    // whose upper bound excludes the last action, Q12) down to the horizon, each recorded as a level with a zero observation
+    auto random_rollouts = [&](int b) {
+        int cur_depth = nodes[b].depth;
+        acts.clear();
+        for (int ci : nodes[b].children) acts.push_back({nodes[ci].data, nodes[ci].k});
+        while (cur_depth <= P.max_depth) {
+            const int n_act = (int)acts.size();
+            if (n_act <= 1) return;
+            const int a = np_randint(gnp, n_act - 1);
+            if (acts[a].second > IPP_APPEND_MAX_K) { overflow = true; return; }
+            levels.push_back({acts[a].first, z_zero, acts[a].second, 2});
+            double pose[3];
+            memcpy(pose, &pool[acts[a].first + 3 * (size_t)(acts[a].second - 1)], sizeof(pose));
+            ++cur_depth;
+            if (cur_depth > P.max_depth) return;
+            build_path_set(P, pose, ps);
+            acts.clear();
+            for (size_t i = 0; i < ps.goal.size(); ++i) {
+                const size_t off = pool.size();
+                const double* sp = &ps.samp[i * (size_t)ps.max_samp * 3];
+                pool.insert(pool.end(), sp, sp + 3 * ps.count[i]);
+                acts.push_back({off, ps.count[i]});
+            }
+        }
+    };
+
     double walk_us = 0.0, device_us = 0.0;
     for (int it = 0; it < P.budget; ++it) {
         const double t_walk = now_us();
@@ -434,15 +479,25 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 while (pick < 0 && nodes[cur].g_next < nodes[cur].n_goals)
                     if (expand_one(cur)) pick = nodes[cur].children.back();
                 if (pick < 0 && nodes[cur].children.empty()) break;                // no feasible action: python children None
+                if (pick >= 0 && belief_tree) {
+                    // BeliefTree.leaf_helper (:540-547): an unvisited action ends the tree walk; the rest of the horizon is a
+                    // random rollout from THIS belief node (it needs the node's complete action set), the leaf is the action
+                    while (nodes[cur].g_next < nodes[cur].n_goals) expand_one(cur);
+                    random_rollouts(cur);
+                    cur = pick;
+                    break;
+                }
                 if (pick < 0) {
-                    // DPW-UCT over all children, exact-equality ties -> random.choice
+                    // DPW-UCT (Tree) or UCB1 (BeliefTree :624-632) over all children, exact-equality ties -> random.choice
                     const Node& b = nodes[cur];
                     const double e_d = 0.5 * (1.0 - (3.0 / (10.0 * (P.max_depth - b.depth))));
                     double top = 0.0;
                     ties.clear();
                     for (int ci : b.children) {
                         const Node& ch = nodes[ci];
-                        const double v = ch.reward / (double)ch.nq + P.c * sqrt(pow((double)b.nq, e_d) / (double)ch.nq);
+                        const double v = belief_tree
+                            ? ch.reward / (double)ch.nq + P.c * sqrt(2.0 * P.log_table[b.nq] / (double)ch.nq)
+                            : ch.reward / (double)ch.nq + P.c * sqrt(pow((double)b.nq, e_d) / (double)ch.nq);
                         if (ties.empty() || v > top) { top = v; ties.clear(); ties.push_back(ci); }
                         else if (v == top) ties.push_back(ci);
                     }
@@ -453,6 +508,23 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 // _record_action: re-use a child (progressive widening) or simulate a new observation
                 Node& a = nodes[cur];
                 int child = -1;
+                if (belief_tree) {
+                    // BeliefTree (:549-562): every traversal of an action creates a new belief child with the MLE observation
+                    if (a.k > IPP_APPEND_MAX_K) { *status = 1; return IPP_OK; }
+                    Node bnode;
+                    bnode.depth = a.depth + 1;
+                    bnode.parent = cur;
+                    bnode.k = a.k;
+                    bnode.data = z_zero;
+                    memcpy(bnode.pose, a.end, sizeof(double) * 3);
+                    child = (int)nodes.size();
+                    levels.push_back({a.data, z_zero, a.k, 2});
+                    nodes.push_back(bnode);                                        // may move `a`: not used below
+                    nodes[cur].children.push_back(child);
+                    nodes[cur].has_children = true;
+                    cur = child;
+                    continue;
+                }
                 if (a.has_children) {
                     const double al = 3.0 / (10.0 * (P.max_depth - a.depth) - 3.0);
                     const int nchild = (int)a.children.size();
@@ -463,7 +535,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                         ties.clear();
                         for (int ci : a.children) if (nodes[ci].nq == fewest) ties.push_back(ci);
                         child = ties[py_choice(gpy, (int)ties.size())];
-                        levels.push_back({cur, nodes[child].data, a.k, 1});
+                        levels.push_back({a.data, nodes[child].data, a.k, 1});
                     }
                 }
                 if (child < 0) {
@@ -477,7 +549,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                     const double* sc = P.prior_scale + (size_t)a.k * IPP_APPEND_MAX_K;
                     for (int i = 0; i < a.k; ++i) pool.push_back(np_gauss(gnp, &np) * sc[i]);
                     child = (int)nodes.size();
-                    levels.push_back({cur, bnode.data, a.k, 2});
+                    levels.push_back({a.data, bnode.data, a.k, 2});
                     nodes.push_back(bnode);                                        // may move `a`: not used below
                     nodes[cur].children.push_back(child);
                     nodes[cur].has_children = true;
@@ -499,7 +571,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             if (M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }
             int row = 0;
             for (int l = 0; l < L; ++l) {
-                const Node& a = nodes[levels[l].node];
+                const Level& a = levels[l];
                 if (a.k > IPP_APPEND_MAX_K) { *status = 1; return IPP_OK; }
                 for (int i = 0; i < a.k; ++i, ++row) {
                     h_in[(size_t)row * D] = pool[a.data + 3 * i];
@@ -537,7 +609,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             }
             row = 0;
             for (int l = 0; l < L; ++l) {
-                const int k = nodes[levels[l].node].k;
+                const int k = levels[l].k;
                 double f[IPP_APPEND_MAX_K];
                 for (int i = 0; i < k; ++i) f[i] = 0.0;
                 for (int sidx = 0; sidx < S_; ++sidx)
@@ -552,7 +624,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             // naive (aq_library.py:339-367): share of the sampled maximisers within `radius` of each point, summed over the
             // level's points the way np.sum does (pairwise, np_pairwise_sum); no belief, no device
             for (int l = 0; l < L; ++l) {
-                const Node& a = nodes[levels[l].node];
+                const Level& a = levels[l];
                 double f[IPP_APPEND_MAX_K];
                 if (a.k > IPP_APPEND_MAX_K) { *status = 1; return IPP_OK; }
                 for (int i = 0; i < a.k; ++i) f[i] = 0.0;
@@ -577,7 +649,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             double* in = fast ? inl.v : h_in;
             int row = 0;
             for (int l = 0; l < L; ++l) {
-                const Node& a = nodes[levels[l].node];
+                const Level& a = levels[l];
                 offsets[l] = row;
                 reps[l] = levels[l].reps;
                 for (int i = 0; i < a.k; ++i, ++row) {

@@ -461,7 +461,7 @@ class cMCTS(object):
             return ((self.max_val, self.max_locs, self.target), self.aq_param[1])
         return None
 
-    NATIVE_SEARCH = True       # dpw tree + Dubins / straight-fan generator + a fused reward: the whole search in libipp_b200.so
+    NATIVE_SEARCH = True       # dpw or belief tree + Dubins / straight-fan generator + a fused reward: the whole search in libipp_b200.so
     native_searches = 0        # how many searches (all instances) went through ipp_tree_search_dpw
 
     def search(self, t, param, budget=None):
@@ -476,7 +476,7 @@ class cMCTS(object):
                              depth=self.rl, param=param, c=self.c)
         budget = self.comp_budget if budget is None else budget
         self.native_search_used = False
-        if self.NATIVE_SEARCH and tree_cls is Tree and self._search_native(t, budget):
+        if self.NATIVE_SEARCH and self._search_native(t, budget):
             self.native_search_used = True
             cMCTS.native_searches += 1
             return self.tree.root.children
@@ -550,6 +550,12 @@ class cMCTS(object):
         prm.horizon, prm.turning_radius = float(pg.hl), float(pg.tr)
         prm.dense_step, prm.border = float(pg.ss / 10), float(3 * pg.tr)
         prm.generator, prm.sample_step = generator, float(pg.ss)
+        log_table = None
+        if isinstance(tree, BeliefTree):
+            # UCB1 uses np.log of the parent's visit count: hand the interpreter's own values over (numpy's SIMD log need
+            # not agree with libm in the last bit), computed the way the Python tree computes them: one scalar at a time
+            log_table = np.array([0.0] + [np.log(float(n)) for n in range(1, int(budget) + 2)], dtype=np.float64)
+            prm.tree_type, prm.log_table = 1, log_table.ctypes.data
         prm.extent[:] = [float(e) for e in pg.extent]
         prm.angles = angles.ctypes.data
         prm.obstacles = ctypes.cast(boxes[0], ctypes.c_void_p).value if boxes[1] else None

@@ -953,10 +953,11 @@ def test_train_and_load_kernel(pkg, tmp_path):
         m2.load_kernel(str(tmp_path / 'missing.npy'))
 
 
+@pytest.mark.parametrize('tree_type', ['dpw', 'belief'])
 @pytest.mark.parametrize('f_rew,world_kind,n_obs,budget,depth', [
     ('mean', 'free', 40, 120, 5), ('mean', 'block', 300, 250, 5), ('mes', 'free', 150, 250, 5),
     ('exp_improve', 'channel', 90, 150, 4), ('mean', 'free', 1200, 60, 3)])
-def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n_obs, budget, depth):
+def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n_obs, budget, depth, tree_type):
     """ipp_tree_search_dpw (the whole DPW search in native code) against the Python Tree on the same seeds: identical
     visit counts, bit-identical reward sums, the same chosen action -- and the interpreter's two random streams are left
     exactly where the Python search leaves them."""
@@ -978,7 +979,7 @@ def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n
         np.random.seed(21); random.seed(22)
         np.random.standard_normal(1)                             # leave a cached Gaussian in numpy's state
         planner = mc.cMCTS(budget, m, (5.2, 4.6, 0.7), depth, pg, fn, f_rew, 6,
-                           aq_param=float(np.max(z)) if f_rew == 'exp_improve' else None, tree_type='dpw')
+                           aq_param=float(np.max(z)) if f_rew == 'exp_improve' else None, tree_type=tree_type)
         planner.NATIVE_SEARCH = native
         with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
             out = planner.choose_trajectory(t=6)
@@ -995,8 +996,8 @@ def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n
 
 
 def test_native_tree_search_steps_aside_when_not_covered(pkg):
-    """Belief tree, no data yet, a generator subclass the library does not know: the interpreter keeps the search (and the
-    native path says so); the plain straight fan with a dpw tree is covered natively."""
+    """No data yet, or a generator subclass the library does not know: the interpreter keeps the search (and the native
+    path says so); the plain generators with dpw and belief trees are covered natively."""
     from informative_path_planning_b200 import mcts_library as mc
     from informative_path_planning_b200.paths_library import Dubins_Path_Generator, Path_Generator
     aq = pkg.aq_library
@@ -1007,7 +1008,7 @@ def test_native_tree_search_steps_aside_when_not_covered(pkg):
     m.add_data(X, z)
     class MyFan(Path_Generator):                 # user subclass: may override anything, so it stays with the Python tree
         pass
-    cases = [(m, MyFan(8, 1.5, 0.05, 0.5, RANGES), 'dpw', False), (m, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'belief', False),
+    cases = [(m, MyFan(8, 1.5, 0.05, 0.5, RANGES), 'dpw', False), (m, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'belief', True),
              (empty, Dubins_Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw', False),
              (m, Path_Generator(8, 1.5, 0.05, 0.5, RANGES), 'dpw', True)]
     for model, pg, tree_type, native in cases:
@@ -1078,9 +1079,9 @@ def test_naive_reward_rollouts_skip_the_belief_updates(pkg, f_rew, tree_type):
         kids = planner.tree.root.children
         res[fuse] = ([c.nqueries for c in kids], [float(c.reward) for c in kids], out[0], float(out[2]), random.random(),
                      np.random.standard_normal(2), planner.tree.reward_evals)
-        # the dpw search runs natively: naive with no device work at all, naive_value with one small pass per rollout that
-        # evaluates the sampled functions; the belief tree stays with the Python tree
-        assert planner.native_search_used == (fuse and tree_type == 'dpw')
+        # the search runs natively (dpw and belief trees): naive with no device work at all, naive_value with one small pass
+        # per rollout that evaluates the sampled functions
+        assert planner.native_search_used == fuse
     a, b = res[True], res[False]
     assert a[0] == b[0] and sum(a[0]) == 60 and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
     assert a[4] == b[4] and np.array_equal(a[5], b[5]) and a[6] == b[6]

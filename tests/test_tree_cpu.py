@@ -23,11 +23,12 @@ def _world(kind):
             'trap': ob.BugTrap(ext, (3., 3.), 2., 0.5, 2., 'left')}[kind]
 
 
+@pytest.mark.parametrize('tree_type', ['dpw', 'belief'])
 @pytest.mark.parametrize('world_kind,pose,budget,depth,horizon,step', [
     ('free', (5.2, 4.6, 0.7), 250, 5, 1.5, 0.5), ('block', (5.0, 5.0, 0.0), 200, 4, 1.5, 0.5),
     ('trap', (8.9, 1.2, 2.2), 300, 7, 1.5, 0.5), ('free', (0.6, 9.4, -2.0), 120, 5, 3.0, 0.25),
     ('fan', (5.2, 4.6, 0.7), 250, 5, 1.5, 0.5), ('fan', (9.3, 0.8, 2.9), 200, 6, 1.7, 0.4)])
-def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, depth, horizon, step):
+def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, depth, horizon, step, tree_type):
     from informative_path_planning_b200 import _lib as L
     from informative_path_planning_b200 import mcts_library as mc
     from informative_path_planning_b200.obstacles import box_array
@@ -49,7 +50,7 @@ def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, 
     pg = (Path_Generator if fan else Dubins_Path_Generator)(15, horizon, 0.05, step, RANGES, world)
     np.random.seed(31); random.seed(32)
     np.random.standard_normal(1)                                   # leave a cached Gaussian behind
-    planner = mc.cMCTS(budget, belief, pose, depth, pg, aq_oracle.naive, 'naive', 4, aq_param=(3, radius), tree_type='dpw')
+    planner = mc.cMCTS(budget, belief, pose, depth, pg, aq_oracle.naive, 'naive', 4, aq_param=(3, radius), tree_type=tree_type)
     with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
         kids = planner.search(4, param)
     assert not planner.native_search_used
@@ -67,6 +68,9 @@ def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, 
     prm.c, prm.reward_param, prm.time = float(planner.c), radius, 4.0
     prm.horizon, prm.turning_radius, prm.dense_step, prm.border = horizon, 0.05, float(step / 10), float(3 * 0.05)
     prm.generator, prm.sample_step = (1 if fan else 0), float(step)
+    log_table = np.array([0.0] + [np.log(float(n)) for n in range(1, budget + 2)])
+    if tree_type == 'belief':
+        prm.tree_type, prm.log_table = 1, log_table.ctypes.data
     prm.extent[:] = list(RANGES)
     prm.angles, prm.prior_scale = angles.ctypes.data, scale.ctypes.data
     prm.obstacles = ctypes.cast(boxes, vp).value if nb else None
