@@ -1086,3 +1086,31 @@ def test_naive_reward_rollouts_skip_the_belief_updates(pkg, f_rew, tree_type):
     assert a[0] == b[0] and sum(a[0]) == 60 and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
     assert a[4] == b[4] and np.array_equal(a[5], b[5]) and a[6] == b[6]
     assert max(a[1]) > 0                                        # some rollouts came near the sampled maxima
+
+
+@pytest.mark.parametrize('tree_type,f_rew', [('dpw', 'mean'), ('belief', 'mean'), ('dpw', 'mes')])
+def test_native_tree_search_space_time_belief(pkg, tree_type, f_rew):
+    """D = 3 (space-time ARD kernel): the rollout's query points carry the planning time as third column
+    (aq_library.py:43-44); native search == Python tree, bit for bit, as in two dimensions."""
+    from informative_path_planning_b200 import mcts_library as mc
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    aq = pkg.aq_library
+    rng = np.random.default_rng(44)
+    X = np.hstack([rng.uniform(0, 10, (160, 2)), rng.integers(0, 12, (160, 1)).astype(float)])
+    z = 6 * np.sin(0.8 * X[:, :1]) * np.cos(0.5 * X[:, 1:2]) + 0.3 * X[:, 2:3] + rng.normal(0, 0.7, (160, 1))
+    m = pkg.OnlineGPModel(RANGES, (1.0, 1.0, 6.0), 100.0, noise=0.5, dimension=3)
+    m.add_data(X, z)
+    fn = {'mean': aq.mean_UCB, 'mes': aq.mves}[f_rew]
+    res = {}
+    for native in (True, False):
+        pg = Dubins_Path_Generator(11, 1.5, 0.05, 0.5, RANGES)
+        np.random.seed(14); random.seed(15)
+        planner = mc.cMCTS(80, m, (4.1, 5.7, 2.0), 4, pg, fn, f_rew, 7, tree_type=tree_type)
+        planner.NATIVE_SEARCH = native
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            out = planner.choose_trajectory(t=7)
+        assert planner.native_search_used == native
+        kids = planner.tree.root.children
+        res[native] = ([c.nqueries for c in kids], [c.reward for c in kids], out[0], random.random(), np.random.standard_normal(2))
+    a, b = res[True], res[False]
+    assert a[0] == b[0] and sum(a[0]) == 80 and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and np.array_equal(a[4], b[4])
