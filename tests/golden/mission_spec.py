@@ -25,6 +25,13 @@ MISSIONS = {   # name: (f_rew, nonmyopic, tree_type, path_generator, obstacle wo
     'nonmyopic_mean_dpw_dubins': ('mean', True, 'dpw', 'dubins', 'free', 4, 60, 4),
     'nonmyopic_mes_dpw_dubins_blocks': ('mes', True, 'dpw', 'dubins', 'block', 3, 40, 3),
     'nonmyopic_ei_dpw_dubins_channel': ('exp_improve', True, 'dpw', 'dubins', 'channel', 3, 40, 3),
+    # the remaining rewards: information gain (Schur form, batched), expected improvement, and the heuristic rewards of the
+    # reference's current sweep (run_sim_all.sh:17), whose rollouts skip the belief updates here
+    'myopic_info_gain_fan': ('info_gain', False, 'dpw', 'default', 'free', 4, 0, 0),
+    'myopic_ei_dubins': ('exp_improve', False, 'dpw', 'dubins', 'free', 5, 0, 0),
+    'myopic_naive_dubins': ('naive', False, 'dpw', 'dubins', 'free', 4, 0, 0),
+    'nonmyopic_naive_dpw_dubins': ('naive', True, 'dpw', 'dubins', 'block', 3, 40, 3),
+    'nonmyopic_naive_value_dpw_dubins': ('naive_value', True, 'dpw', 'dubins', 'free', 3, 40, 3),
 }
 
 

@@ -273,7 +273,9 @@ def test_evaluation_batched_sweep_equals_per_path_calls(pkg, tmp_path):
 # ------------------------------------------------------------------ whole missions of the reference's Robot
 @pytest.mark.parametrize('name', ['myopic_mean_fan', 'myopic_mean_dubins_blocks', 'myopic_mes_fan', 'nonmyopic_mean_dpw',
                                   'nonmyopic_mean_belief_dubins', 'nonmyopic_mean_dpw_dubins',
-                                  'nonmyopic_mes_dpw_dubins_blocks', 'nonmyopic_ei_dpw_dubins_channel'])
+                                  'nonmyopic_mes_dpw_dubins_blocks', 'nonmyopic_ei_dpw_dubins_channel',
+                                  'myopic_info_gain_fan', 'myopic_ei_dubins', 'myopic_naive_dubins',
+                                  'nonmyopic_naive_dpw_dubins', 'nonmyopic_naive_value_dpw_dubins'])
 def test_robot_mission_reproduces_reference_run(pkg, name, tmp_path, monkeypatch):
     """robot_library.Robot.planner + evaluation_library.Evaluation on the device against the SAME seeded mission run by
     the reference's own Robot / Evaluation source (tests/golden/missions.npz): the pose after every step, every
