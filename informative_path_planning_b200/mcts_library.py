@@ -485,10 +485,12 @@ class cMCTS(object):
         return self.tree.root.children
 
     def _search_native(self, t, budget):
-        """The same search by ipp_tree_search_dpw (csrc/tree.cu): walk, widening, candidate paths, simulated
-        observations and both random streams in native code, one device pass + one synchronisation per rollout.
-        Returns False -- with nothing consumed from the random streams -- when the configuration is not covered
-        (other generators / rewards, no data yet) or a rollout needs the per-level fallback."""
+        """The same search by ipp_tree_search_dpw (csrc/tree.cu): walk, widening (Tree) or random rollouts (BeliefTree),
+        candidate paths (Dubins or straight fan), simulated observations and both random streams in native code; per
+        rollout one device pass for UCB / EI / MES (points by value, rewards to pinned memory, polled completion), one
+        small kernel for naive_value, nothing at all for naive.  Returns False -- with nothing consumed from the random
+        streams -- when the configuration is not covered (generator subclasses, other rewards, no data yet) or a rollout
+        needs the per-level fallback."""
         import ctypes
         from .paths_library import Dubins_Path_Generator, Path_Generator
         L = aqlib.L
