@@ -24,9 +24,9 @@ class EvaluationOracle(object):
             self.max_loc = world.models[0].xvals[np.argmax(world.models[0].zvals), 0:-1]
             self.max_val = np.max(world.models[0].zvals)
         self.reward_function = reward_function
-        self.f_rew = {'hotspot_info': self.hotspot_info_reward, 'mean': self.mean_reward,      # :82-99
+        self.f_rew = {'hotspot_info': self.hotspot_info_reward, 'mean': self.mean_reward,      # :82-105
                       'info_gain': self.info_gain_reward, 'mes': self.mean_reward,
-                      'exp_improve': self.mean_reward}[reward_function]
+                      'exp_improve': self.mean_reward, 'naive': None, 'naive_value': None}[reward_function]
 
     def _world_predict(self, time, x1, x2):
         if self.world.dim == 2:
@@ -107,9 +107,12 @@ class EvaluationOracle(object):
         m['simple_regret'] = self.simple_regret(selected_path)
         m['sample_regret_loc'], m['sample_regret_val'] = self.sample_regret(robot_model)
         m['max_loc_error'], m['max_val_error'] = self.max_error(max_loc, max_val)
-        m['instant_regret'], _, _ = self.inst_regret(t, all_paths, selected_path, robot_model)
-        m['max_val_regret'], m['mes_reward_robot'], m['mes_reward_omni'] = self.inst_regret(
-            t, all_paths, selected_path, robot_model, param='info_regret')
+        if self.reward_function in ('naive', 'naive_value'):                                    # :280-284
+            m['instant_regret'] = m['max_val_regret'] = m['mes_reward_robot'] = m['mes_reward_omni'] = -1.
+        else:
+            m['instant_regret'], _, _ = self.inst_regret(t, all_paths, selected_path, robot_model)
+            m['max_val_regret'], m['mes_reward_robot'], m['mes_reward_omni'] = self.inst_regret(
+                t, all_paths, selected_path, robot_model, param='info_regret')
         m['info_gain_reward'] = self.info_gain_reward(t, selected_path, robot_model)
         m['MSE'] = self.MSE(t, robot_model, NTEST=200)
         m['hotspot_error'] = self.hotspot_error(t, robot_model, NTEST=200, NHS=100)

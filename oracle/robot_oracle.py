@@ -24,7 +24,12 @@ class RobotOracle(object):
         self.max_locs = self.max_val = self.target = None
         self.aquisition_function = {'hotspot_info': aqlib.hotspot_info_UCB, 'mean': aqlib.mean_UCB,       # :93-113
                                     'info_gain': aqlib.info_gain, 'mes': aqlib.mves,
-                                    'exp_improve': aqlib.exp_improvement}[f_rew]
+                                    'exp_improve': aqlib.exp_improvement, 'naive': aqlib.naive,
+                                    'naive_value': aqlib.naive_value}[f_rew]
+        if f_rew == 'naive':                                                                                # :105-112
+            self.sample_num, self.sample_radius = 3, 1.5
+        elif f_rew == 'naive_value':
+            self.sample_num, self.sample_radius = 3, 3.0
         self.GP = OnlineGPModelOracle(ranges=extent, lengthscale=init_lengthscale, variance=init_variance, noise=noise,
                                       dimension=dimension)                                                  # :119
         if prior_dataset is not None:                                                                       # :138-139
@@ -37,6 +42,10 @@ class RobotOracle(object):
         param = None
         if self.f_rew == 'mes':
             self.max_val, self.max_locs, self.target = aqlib.sample_max_vals(self.GP, t=t)
+        elif self.f_rew in ('naive', 'naive_value'):                                                        # :168-170
+            self.max_val, self.max_locs, self.target = aqlib.sample_max_vals(self.GP, t=t, f_rew=self.f_rew,
+                                                                             nK=int(self.sample_num))
+            param = ((self.max_val, self.max_locs, self.target), self.sample_radius)
         self.predict_max(t=t)
         paths, true_paths = self.path_generator.get_path_set(self.loc)
         for path, points in paths.items():
@@ -77,7 +86,10 @@ class RobotOracle(object):
             if not self.nonmyopic:
                 sampling_path, best_path, best_val, all_paths, all_values, max_locs = self.choose_trajectory(t=t)
             else:
-                param = self.current_max if self.f_rew == 'exp_improve' else None
+                if self.f_rew in ('naive', 'naive_value'):                                                  # :278-285
+                    param = (self.sample_num, self.sample_radius)
+                else:
+                    param = self.current_max if self.f_rew == 'exp_improve' else None
                 mcts = mctslib.cMCTSOracle(self.comp_budget, self.GP, self.loc, self.roll_length, self.path_generator,
                                            self.aquisition_function, self.f_rew, t, aq_param=param, tree_type=self.tree_type)
                 (sampling_path, best_path, best_val, all_paths, all_values, self.max_locs, self.max_val,
