@@ -103,3 +103,51 @@ def test_native_search_equals_python_tree_on_the_host(world_kind, pose, budget, 
     paths, _ = pg.get_path_set(pose)
     assert goal[:n].tolist() == list(paths.keys())
     assert max(got[0]) > min(got[0])                               # a non-trivial search: the visits concentrated somewhere
+
+
+def test_native_search_rejects_bad_arguments():
+    """Error behaviour of the C ABI: status code + ipp_last_error(), nothing touched."""
+    from informative_path_planning_b200 import _lib as L
+    from informative_path_planning_b200 import mcts_library as mc
+    vp = ctypes.c_void_p
+    angles = np.ascontiguousarray(np.linspace(-2.35, 2.35, 15))
+    scale = mc._prior_scale_table(100.0)
+    locs = np.array([[6.1, 5.2]])
+
+    def params(**kw):
+        prm = L.IppTreeParams()
+        prm.budget, prm.max_depth, prm.kind = 10, 3, L.REWARD_NAIVE
+        prm.frontier_size, prm.keep_every, prm.n_obstacles = 15, 10, 0
+        prm.c, prm.reward_param = 1.0, 1.5
+        prm.horizon, prm.turning_radius, prm.dense_step, prm.border = 1.5, 0.05, 0.05, 0.15
+        prm.extent[:] = list(RANGES)
+        prm.angles, prm.prior_scale = angles.ctypes.data, scale.ctypes.data
+        prm.naive_locs, prm.n_naive = locs.ctypes.data, 1
+        for k, v in kw.items():
+            setattr(prm, k, v)
+        return prm
+
+    def call(prm, kern=None):
+        kern = L.make_rbf(2, 100.0, 1.0) if kern is None else kern
+        random.seed(1); np.random.seed(1)
+        py_state, _ = L.py_rng_state()
+        np_state = L.np_rng_state()
+        before = (bytes(py_state.key), py_state.pos, bytes(np_state.key), np_state.pos)
+        outs = [np.zeros(16, dtype=dt) for dt in (np.int32, np.int32, np.int64, np.float64, np.int64, np.int32)]
+        pose = np.array([5.0, 5.0, 0.3])
+        rc = L.lib.ipp_tree_search_dpw(ctypes.byref(prm), pose.ctypes.data_as(vp), ctypes.byref(kern), None, 0, None, None, 0,
+                                       0.5, 0.5, None, 0, ctypes.byref(py_state), ctypes.byref(np_state), None, None, None,
+                                       *[o.ctypes.data_as(vp) for o in outs], None)
+        after = (bytes(py_state.key), py_state.pos, bytes(np_state.key), np_state.pos)
+        return rc, L.lib.ipp_last_error().decode(), before == after, outs
+
+    rc, msg, untouched, outs = call(params())
+    assert rc == 0 and not untouched and int(outs[2][:outs[0][0]].sum()) == 10            # the good call works, host only
+    for bad in (params(kind=7), params(n_naive=0), params(generator=1, sample_step=0.0), params(tree_type=1),
+                params(frontier_size=0), params(n_obstacles=3), params(turning_radius=0.0)):
+        rc, msg, untouched, _ = call(bad)
+        assert rc != 0 and 'ipp_tree_search_dpw' in msg and untouched
+    rc, msg, untouched, _ = call(params(kind=L.REWARD_UCB))                                # device reward without a belief
+    assert rc != 0 and untouched
+    with pytest.raises(L.IppError):
+        L.check(rc)
