@@ -151,3 +151,35 @@ def test_native_search_rejects_bad_arguments():
     assert rc != 0 and untouched
     with pytest.raises(L.IppError):
         L.check(rc)
+
+
+def test_native_search_steps_aside_without_consuming_the_streams():
+    """A rollout the one-pass scoring cannot take (here: 36 sample points on one path, the block limit is 32) makes the
+    call report status 1 and leave both random streams exactly as they were, so the caller's own search starts from the
+    same state."""
+    from informative_path_planning_b200 import _lib as L
+    from informative_path_planning_b200 import mcts_library as mc
+    vp = ctypes.c_void_p
+    angles = np.ascontiguousarray(np.linspace(-2.35, 2.35, 9))
+    scale = mc._prior_scale_table(100.0)
+    locs = np.array([[6.1, 5.2], [3.0, 4.0]])
+    prm = L.IppTreeParams()
+    prm.budget, prm.max_depth, prm.kind = 20, 3, L.REWARD_NAIVE
+    prm.frontier_size, prm.keep_every, prm.n_obstacles = 9, 10, 0
+    prm.c, prm.reward_param = 1.0, 1.5
+    prm.horizon, prm.turning_radius, prm.dense_step, prm.border = 9.0, 0.05, 0.025, 0.15      # 9.0 / 0.25 = 36 samples
+    prm.extent[:] = [0., 40., 0., 40.]
+    prm.angles, prm.prior_scale = angles.ctypes.data, scale.ctypes.data
+    prm.naive_locs, prm.n_naive = locs.ctypes.data, 2
+    kern = L.make_rbf(2, 100.0, 1.0)
+    random.seed(3); np.random.seed(4)
+    py_state, _ = L.py_rng_state()
+    np_state = L.np_rng_state()
+    before = (bytes(py_state.key), py_state.pos, bytes(np_state.key), np_state.pos, np_state.has_gauss)
+    outs = [np.zeros(16, dtype=dt) for dt in (np.int32, np.int32, np.int64, np.float64, np.int64, np.int32)]
+    pose = np.array([20.0, 20.0, 0.3])
+    L.check(L.lib.ipp_tree_search_dpw(ctypes.byref(prm), pose.ctypes.data_as(vp), ctypes.byref(kern), None, 0, None, None, 0,
+                                      0.5, 0.5, None, 0, ctypes.byref(py_state), ctypes.byref(np_state), None, None, None,
+                                      *[o.ctypes.data_as(vp) for o in outs], None))
+    assert outs[5][0] == 1                                            # status: not done here
+    assert before == (bytes(py_state.key), py_state.pos, bytes(np_state.key), np_state.pos, np_state.has_gauss)
