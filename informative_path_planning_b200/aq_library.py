@@ -150,22 +150,68 @@ def _logdet_small_device(robot_model, queries, scale_variance):
     return float(scal[0].item())
 
 
+IG_KMAX = 32          # csrc/infogain.cu: longest path the one-warp-per-path Schur kernel factors in shared memory
+
+
+def _info_gain_long_path(robot_model, xq):
+    """logdet S for one path of more than IG_KMAX points (the reference takes any length, aq_library.py:55-70): the same
+    Schur block S = I + K2(q,q) - K2(q,X) (I + vK)^-1 K2(X,q), assembled with the FP64 GEMM and factored by the blocked
+    device Cholesky."""
+    kern2, binv, ld, _ = robot_model._info_gain_state()
+    k, N, dev = xq.shape[0], robot_model.n_obs, xq.device
+    ldn = L.round_up(N, 16)
+    Ct = torch.zeros((k, ldn), dtype=torch.float64, device=dev)
+    L.check(L.lib.ipp_rbf_cross(ctypes.byref(kern2), L.ptr(xq), k, L.ptr(robot_model._X_d), N, L.ptr(Ct), ldn, L.stream_ptr()))
+    G = torch.empty((k, ldn), dtype=torch.float64, device=dev)
+    L.check(L.lib.ipp_dgemm_nt(k, N, N, 1.0, L.ptr(Ct), ldn, L.ptr(binv), ld, 0.0, L.ptr(G), ldn, None, 0, L.stream_ptr()))
+    lds = L.round_up(k, 2)
+    S = torch.empty((k, lds), dtype=torch.float64, device=dev)
+    L.check(L.lib.ipp_rbf_cross(ctypes.byref(kern2), L.ptr(xq), k, L.ptr(xq), k, L.ptr(S), lds, L.stream_ptr()))
+    S[:, :k] += torch.eye(k, dtype=torch.float64, device=dev)
+    L.check(L.lib.ipp_dgemm_nt(k, k, N, -1.0, L.ptr(G), ldn, L.ptr(Ct), ldn, 1.0, L.ptr(S), lds, None, 0, L.stream_ptr()))
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = L.workspace(L.lib.ipp_potrf_workspace(k), slot='potrf')
+    L.check(L.lib.ipp_potrf_lower(L.ptr(S), k, lds, L.ptr(scal), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('info_gain: Schur block not positive definite')
+    return float(scal[0].item())
+
+
 def info_gain_paths(robot_model, queries, offsets):
     """2*pi*e * (logdet(I + v K([X; q_p])) - logdet(I + v K(X))) for every path p, as one device pass
-    (Schur-complement form of reference aq_library.py:55-70)."""
+    (Schur-complement form of reference aq_library.py:55-70); paths longer than IG_KMAX points one by one through
+    _info_gain_long_path."""
     kern2, binv, ld, _ = robot_model._info_gain_state()
     xq = L.to_device(queries)
-    M, N = xq.shape[0], robot_model.n_obs
-    offs = torch.as_tensor(np.asarray(offsets, dtype=np.int64)).to(xq.device)
-    P = offs.shape[0] - 1
-    out = torch.empty(P, dtype=torch.float64, device=xq.device)
+    N = robot_model.n_obs
+    offsets = np.asarray(offsets, dtype=np.int64)
+    P = offsets.shape[0] - 1
+    lengths = np.diff(offsets)
+    long_paths = np.nonzero(lengths > IG_KMAX)[0]
+    result = np.empty(P)
+    short = np.nonzero(lengths <= IG_KMAX)[0]
+    if long_paths.size:
+        for p in long_paths:
+            result[p] = _info_gain_long_path(robot_model, xq[offsets[p]:offsets[p + 1]].contiguous())
+        if short.size == 0:
+            return _TWO_PI_E * result
+        keep = np.concatenate([np.arange(offsets[p], offsets[p + 1]) for p in short])
+        xq_s = xq[torch.as_tensor(keep, device=xq.device)].contiguous()
+        offs_s = np.concatenate([[0], np.cumsum(lengths[short])])
+    else:
+        xq_s, offs_s = xq, offsets
+    M, Ps = xq_s.shape[0], offs_s.shape[0] - 1
+    offs = torch.as_tensor(np.asarray(offs_s, dtype=np.int64)).to(xq.device)
+    out = torch.empty(Ps, dtype=torch.float64, device=xq.device)
     info = torch.zeros(1, dtype=torch.int32, device=xq.device)
     work = L.workspace(L.lib.ipp_info_gain_workspace(N, M))
-    L.check(L.lib.ipp_info_gain_paths(ctypes.byref(kern2), L.ptr(robot_model._X_d), N, L.ptr(binv), ld, L.ptr(xq),
-                                      L.ptr(offs), P, M, L.ptr(out), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    L.check(L.lib.ipp_info_gain_paths(ctypes.byref(kern2), L.ptr(robot_model._X_d), N, L.ptr(binv), ld, L.ptr(xq_s),
+                                      L.ptr(offs), Ps, M, L.ptr(out), L.ptr(info), L.ptr(work), L.stream_ptr()))
     if int(info.item()) != 0:
-        raise np.linalg.LinAlgError('info_gain: Schur block not positive definite (or path longer than 32 points)')
-    return _TWO_PI_E * out.cpu().numpy()
+        raise np.linalg.LinAlgError('info_gain: Schur block not positive definite')
+    result[short] = out.cpu().numpy()
+    return _TWO_PI_E * result
 
 
 def info_gain(time, xvals, robot_model, param=None):
@@ -179,7 +225,12 @@ def info_gain(time, xvals, robot_model, param=None):
 
 
 def hotspot_info_UCB(time, xvals, robot_model, param=None):
-    """reference aq_library.py:117-135 (LAMBDA = 1)"""
+    """reference aq_library.py:117-135 (LAMBDA = 1).  The reference calls predict_value itself (not mean_UCB), so with
+    no data it sees the prior (zeros, variance * ones): info_gain + sqrt(beta_t) * k * variance, not mean_UCB's 1.0."""
+    if robot_model.xvals is None:
+        k = np.array(xvals, dtype=float).shape[0]
+        v = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+        return info_gain(time, xvals, robot_model) + 0.0 + np.sqrt(ucb_beta(time)) * np.sum(np.fabs(np.ones((k, 1)) * v))
     return info_gain(time, xvals, robot_model) + mean_UCB(time, xvals, robot_model)
 
 
@@ -264,9 +315,7 @@ def reward_paths(f_rew, time, paths, robot_model, param=None, offsets=None):
         if f_rew in ('mean',):
             return np.ones(P)
         if f_rew in ('info_gain', 'hotspot_info', 'exp_improve'):
-            fn = {'info_gain': info_gain, 'exp_improve': exp_improvement}.get(f_rew)
-            if fn is None:
-                raise ValueError('hotspot_info needs observations (the reference fails here too)')
+            fn = {'info_gain': info_gain, 'exp_improve': exp_improvement, 'hotspot_info': hotspot_info_UCB}[f_rew]
             return np.array([fn(time, queries[offsets[p]:offsets[p + 1]], robot_model, param) for p in range(P)])
     if f_rew == 'mes' and param[0] is None:
         return np.ones(P)

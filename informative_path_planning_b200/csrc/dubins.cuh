@@ -1,6 +1,7 @@
 // Dubins closed forms + the trimming loop of Dubins_Path_Generator.buffered_paths (reference paths_library.py:147-175),
 // shared by the host path-set generator / device batch kernel (paths.cu) and the native tree search (tree.cu).
-// Classical six-word closed form (LSL, RSR, LSR, RSL, RLR, LRL; Shkel & Lumelsky 2001).
+// Classical six-word closed form (Shkel & Lumelsky 2001) as the `dubins` C library behind paths_library.py:151-152 states
+// it (oracle/dubins_oracle.py restates the library function by function; tests/test_dubins.py pins both).
 #pragma once
 #include <math.h>
 #include "internal.cuh"
@@ -21,28 +22,33 @@ __host__ __device__ inline Word make_word(int k0, int k1, int k2, double a, doub
     return w;
 }
 
+// The six words in the order of the `dubins` C library's DubinsPathType enum (LSL, LSR, RSL, RSR, RLR, LRL): the library
+// keeps a word only when it is STRICTLY shorter than the best so far, so this order is the tie-break.
 __host__ __device__ inline void all_words(double alpha, double beta, double d, Word out[6]) {
     const double sa = sin(alpha), sb = sin(beta), ca = cos(alpha), cb = cos(beta), cab = cos(alpha - beta);
+    const double d_sq = d * d;
     for (int i = 0; i < 6; ++i) out[i].ok = false;
-    double p2, tmp, p, t;
-    p2 = 2 + d * d - 2 * cab + 2 * d * (sa - sb);                                   // LSL
+    double p2, tmp, p, t, phi;
+    p2 = 2 + d_sq - (2 * cab) + (2 * d * (sa - sb));                                // LSL
     if (p2 >= 0) { tmp = atan2(cb - ca, d + sa - sb);
-        out[0] = make_word(0, 1, 0, mod2pi(-alpha + tmp), sqrt(p2), mod2pi(beta - tmp)); }
-    p2 = 2 + d * d - 2 * cab + 2 * d * (sb - sa);                                   // RSR
-    if (p2 >= 0) { tmp = atan2(ca - cb, d - sa + sb);
-        out[1] = make_word(2, 1, 2, mod2pi(alpha - tmp), sqrt(p2), mod2pi(-beta + tmp)); }
-    p2 = -2 + d * d + 2 * cab + 2 * d * (sa + sb);                                  // LSR
+        out[0] = make_word(0, 1, 0, mod2pi(tmp - alpha), sqrt(p2), mod2pi(beta - tmp)); }
+    p2 = -2 + d_sq + (2 * cab) + (2 * d * (sa + sb));                               // LSR
     if (p2 >= 0) { p = sqrt(p2); tmp = atan2(-ca - cb, d + sa + sb) - atan2(-2.0, p);
-        out[2] = make_word(0, 1, 2, mod2pi(-alpha + tmp), p, mod2pi(-mod2pi(beta) + tmp)); }
-    p2 = d * d - 2 + 2 * cab - 2 * d * (sa + sb);                                   // RSL
+        out[1] = make_word(0, 1, 2, mod2pi(tmp - alpha), p, mod2pi(tmp - mod2pi(beta))); }
+    p2 = -2 + d_sq + (2 * cab) - (2 * d * (sa + sb));                               // RSL
     if (p2 >= 0) { p = sqrt(p2); tmp = atan2(ca + cb, d - sa - sb) - atan2(2.0, p);
-        out[3] = make_word(2, 1, 0, mod2pi(alpha - tmp), p, mod2pi(beta - tmp)); }
-    tmp = (6.0 - d * d + 2 * cab + 2 * d * (sa - sb)) / 8.0;                        // RLR
-    if (fabs(tmp) <= 1) { p = mod2pi(TWO_PI - acos(tmp)); t = mod2pi(alpha - atan2(ca - cb, d - sa + sb) + p / 2.0);
-        out[4] = make_word(2, 0, 2, t, p, mod2pi(alpha - beta - t + p)); }
-    tmp = (6.0 - d * d + 2 * cab + 2 * d * (sb - sa)) / 8.0;                        // LRL
-    if (fabs(tmp) <= 1) { p = mod2pi(TWO_PI - acos(tmp)); t = mod2pi(-alpha - atan2(ca - cb, d + sa - sb) + p / 2.0);
-        out[5] = make_word(0, 2, 0, t, p, mod2pi(mod2pi(beta) - alpha - t + p)); }
+        out[2] = make_word(2, 1, 0, mod2pi(alpha - tmp), p, mod2pi(beta - tmp)); }
+    p2 = 2 + d_sq - (2 * cab) + (2 * d * (sb - sa));                                // RSR
+    if (p2 >= 0) { tmp = atan2(ca - cb, d - sa + sb);
+        out[3] = make_word(2, 1, 2, mod2pi(alpha - tmp), sqrt(p2), mod2pi(tmp - beta)); }
+    tmp = (6.0 - d_sq + 2 * cab + 2 * d * (sa - sb)) / 8.0;                         // RLR
+    if (fabs(tmp) <= 1) { phi = atan2(ca - cb, d - sa + sb); p = mod2pi(TWO_PI - acos(tmp));
+        t = mod2pi(alpha - phi + mod2pi(p / 2.0));
+        out[4] = make_word(2, 0, 2, t, p, mod2pi(alpha - beta - t + mod2pi(p))); }
+    tmp = (6.0 - d_sq + 2 * cab + 2 * d * (sb - sa)) / 8.0;                         // LRL
+    if (fabs(tmp) <= 1) { phi = atan2(ca - cb, d + sa - sb); p = mod2pi(TWO_PI - acos(tmp));
+        t = mod2pi(-alpha - phi + p / 2.0);
+        out[5] = make_word(0, 2, 0, t, p, mod2pi(mod2pi(beta) - alpha - t + mod2pi(p))); }
 }
 
 __host__ __device__ inline void segment(double& x, double& y, double& th, double len, int kind) {
@@ -75,8 +81,8 @@ __host__ __device__ inline int dubins_one(const double* pose, const double* q1, 
                                    const double* extent, double border, const ipp_obstacle_box* obs, int n_obs,
                                    double* sg, int max_samp, double* dg, int max_dense, int* dense_n, double* end) {
     const double dx = q1[0] - pose[0], dy = q1[1] - pose[1];
-    const double D = hypot(dx, dy), d = D / rho;
-    const double theta = D > 0 ? mod2pi(atan2(dy, dx)) : 0.0;
+    const double D = sqrt(dx * dx + dy * dy), d = D / rho;      // the library's own expression (not hypot)
+    const double theta = d > 0 ? mod2pi(atan2(dy, dx)) : 0.0;
     const double alpha = mod2pi(pose[2] - theta), beta = mod2pi(q1[2] - theta);
     Word w[6];
     all_words(alpha, beta, d, w);
@@ -115,12 +121,11 @@ __host__ __device__ inline int dubins_one(const double* pose, const double* q1, 
     for (int si = 0; nd < max_dense; si += stride, nd += stride - 1) {
         if (si) for (int a = 0; a < stride; ++a) s += dense_step;
         if (!(s < total)) break;
-        double rem = s / rho;
-        int k = 0;
-        while (k < 2 && !(rem < wb.len[k])) { rem -= (wb.len[k] < 0 ? 0 : wb.len[k]); ++k; }
+        // dubins_path_sample: the piece is chosen by t' < p1, t' < p1 + p2; the offset into it is t', t' - p1, t' - p1 - p2
+        const double tp = s / rho;
+        const int k = tp < wb.len[0] ? 0 : (tp < (wb.len[0] + wb.len[1]) ? 1 : 2);
+        const double use = k == 0 ? tp : (k == 1 ? tp - wb.len[0] : tp - wb.len[0] - wb.len[1]);
         double x = sx[k], y = sy[k], th = sth[k];
-        double use = rem < wb.len[k] ? rem : wb.len[k];
-        if (use < 0) use = 0;
         segment(x, y, th, use, wb.kinds[k]);
         const double cx = x * rho + pose[0], cy = y * rho + pose[1];
         if (!(cx > extent[0] && cx < extent[1] && cy > extent[2] && cy < extent[3])) break;

@@ -23,7 +23,10 @@ __global__ void __launch_bounds__(32) info_gain_schur_kernel(RbfDev kern, const 
     const int k = (int)(offsets[p + 1] - b);
     const int lane = threadIdx.x;
     if (k <= 0) { if (lane == 0) logdet_out[p] = 0.0; return; }
-    if (k > IG_KMAX) { if (lane == 0) { logdet_out[p] = nan(""); if (info) atomicMax(info, -1 - 0); } return; }
+    if (k > IG_KMAX) {          // the caller routes such paths through the blocked factorisation; reaching here is an error
+        if (lane == 0) { logdet_out[p] = nan(""); if (info) atomicMax(info, 0x7fffffff); }
+        return;
+    }
     for (int r = 0; r < k; ++r) {
         for (int c = 0; c <= r; ++c) {
             double s = 0.0;

@@ -154,9 +154,9 @@ inline int goal_path(const ipp_tree_params& p, const double* cp, const double* g
                      int max_dense) {
     if (p.generator == 1) {
         // Path_Generator.make_sample_paths (paths_library.py:85-105): numpy scalar arithmetic restated (x ** 2 is pow(x, 2),
-        // round() is round-half-even); a path exists as soon as it has one point
+        // round() is Python 2's: C round(), halves away from zero); a path exists as soon as it has one point
         const double distance = sqrt(pow(cp[0] - goal[0], 2.0) + pow(cp[1] - goal[1], 2.0));
-        const int n = (int)nearbyint(distance / p.sample_step);
+        const int n = (int)round(distance / p.sample_step);
         if (n < 1) return 0;
         if (n > max_samp) return -1;
         for (int j = 0; j < n; ++j) {

@@ -486,11 +486,17 @@ class GPModel(object):
         self._z_d = torch.empty(N, dtype=torch.float64, device=dev)
         self._alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
         self._winv_d = torch.empty((N, self._ld), dtype=torch.float64, device=dev)
-        if self._linv_d is not None or type(self) is GPModel:
+        # rank-independent choice (the source rank allocates L^-1 exactly for these models, see _factor's callers)
+        if type(self) is GPModel or getattr(self, 'update_legacy', False):
             self._linv_d = torch.empty((N, self._ld), dtype=torch.float64, device=dev)
             self.model = _LegacyModelHandle(self)
+        else:
+            self._linv_d = None
         self._ig = None
         self._K = None
+        self._tf32 = None          # tensor-mode operands were cut for the previous N
+        self._i8 = None
+        self._pending_info = []
 
     # info_gain support: (I + v K)^-1 and its log-determinant, cached per data version
     def _info_gain_state(self):

@@ -158,8 +158,11 @@ def mcts_root_parallel(mcts, t, seed=None):
     np.random.seed((seed + 7919 * (rank + 1)) % (2 ** 32))
     random.seed(seed + 7919 * (rank + 1))
     lo, hi = shard_bounds(mcts.comp_budget, rank, size)
-    children = mcts.search(t, param, budget=hi - lo)
-    stats = torch.tensor([[float(c.nqueries), float(c.reward)] for c in children], dtype=torch.float64, device=dev)
+    # every rank runs at least one rollout (comp_budget < world_size would leave a rank without root children), and a
+    # rank whose search produced no children (no feasible action from the root pose) still reaches the collectives
+    children = mcts.search(t, param, budget=max(1, hi - lo)) or []
+    stats = torch.tensor([[float(c.nqueries), float(c.reward)] for c in children], dtype=torch.float64,
+                         device=dev).reshape(-1, 2)
     count = torch.tensor([stats.shape[0]], dtype=torch.int64, device=dev)
     lo_c, hi_c = count.clone(), count.clone()
     dist.all_reduce(lo_c, op=dist.ReduceOp.MIN)
@@ -167,6 +170,8 @@ def mcts_root_parallel(mcts, t, seed=None):
     if int(lo_c.item()) != int(hi_c.item()):
         raise RuntimeError('root actions differ across ranks (%d vs %d): the belief or the path generator is not '
                            'replicated' % (int(lo_c.item()), int(hi_c.item())))
+    if not children:
+        raise RuntimeError('no feasible action from the root pose (every rank agrees)')
     mcts.local_root_stats = stats.cpu().numpy().copy()
     dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     stats = stats.cpu().numpy()

@@ -17,6 +17,15 @@ import numpy as np
 from .obstacles import FreeWorld, box_array  # noqa: F401  (FreeWorld re-exported: reference paths_library uses obs.FreeWorld)
 
 
+def py2_round(x):
+    """int(round(x)) as the reference's Python 2 computes it (C round(): halves away from zero; Python 3 and numpy round
+    halves to even) -- the sample count of a straight path differs when distance / sample_step lands on x.5."""
+    x = float(x)
+    f = np.floor(abs(x))
+    r = f + 1.0 if abs(x) - f >= 0.5 else f
+    return int(-r if x < 0 else r)
+
+
 class LazyPath(object):
     """A dense path that is only materialised on demand.  The tree search only ever looks at dense_path[-1] (the pose
     of the next belief node) for all but the chosen action, so the ~30-100 dense configurations per candidate path per
@@ -93,7 +102,7 @@ class Path_Generator(object):
         for i, goal in enumerate(self.goals):
             g = np.array(goal)
             distance = np.sqrt((cp[0] - g[0]) ** 2 + (cp[1] - g[1]) ** 2)
-            for j in range(int(round(distance / self.ss))):
+            for j in range(py2_round(distance / self.ss)):
                 step = (j + 1) * self.ss
                 coords.setdefault(i, []).append((cp[0] + step * np.cos(g[2]), cp[1] + step * np.sin(g[2]), g[2]))
         self.samples = coords
@@ -128,89 +137,92 @@ def _mod2pi(t):
 
 
 def _dubins_words(alpha, beta, d):
+    """The six words in the order of the `dubins` C library's DubinsPathType enum (LSL, LSR, RSL, RSR, RLR, LRL): the
+    order is the tie-break, because the library keeps a word only when it is strictly shorter than the best so far."""
     sa, sb, ca, cb, cab = math.sin(alpha), math.sin(beta), math.cos(alpha), math.cos(beta), math.cos(alpha - beta)
+    d_sq = d * d
     out = []
-    # LSL
-    p2 = 2 + d * d - 2 * cab + 2 * d * (sa - sb)
+    p2 = 2 + d_sq - (2 * cab) + (2 * d * (sa - sb))                      # LSL
     if p2 >= 0:
         tmp = math.atan2(cb - ca, d + sa - sb)
-        out.append(('LSL', _mod2pi(-alpha + tmp), math.sqrt(p2), _mod2pi(beta - tmp)))
-    # RSR
-    p2 = 2 + d * d - 2 * cab + 2 * d * (sb - sa)
-    if p2 >= 0:
-        tmp = math.atan2(ca - cb, d - sa + sb)
-        out.append(('RSR', _mod2pi(alpha - tmp), math.sqrt(p2), _mod2pi(-beta + tmp)))
-    # LSR
-    p2 = -2 + d * d + 2 * cab + 2 * d * (sa + sb)
+        out.append(('LSL', _mod2pi(tmp - alpha), math.sqrt(p2), _mod2pi(beta - tmp)))
+    p2 = -2 + d_sq + (2 * cab) + (2 * d * (sa + sb))                     # LSR
     if p2 >= 0:
         p = math.sqrt(p2)
         tmp = math.atan2(-ca - cb, d + sa + sb) - math.atan2(-2.0, p)
-        out.append(('LSR', _mod2pi(-alpha + tmp), p, _mod2pi(-_mod2pi(beta) + tmp)))
-    # RSL
-    p2 = d * d - 2 + 2 * cab - 2 * d * (sa + sb)
+        out.append(('LSR', _mod2pi(tmp - alpha), p, _mod2pi(tmp - _mod2pi(beta))))
+    p2 = -2 + d_sq + (2 * cab) - (2 * d * (sa + sb))                     # RSL
     if p2 >= 0:
         p = math.sqrt(p2)
         tmp = math.atan2(ca + cb, d - sa - sb) - math.atan2(2.0, p)
         out.append(('RSL', _mod2pi(alpha - tmp), p, _mod2pi(beta - tmp)))
-    # RLR
-    tmp = (6.0 - d * d + 2 * cab + 2 * d * (sa - sb)) / 8.0
+    p2 = 2 + d_sq - (2 * cab) + (2 * d * (sb - sa))                      # RSR
+    if p2 >= 0:
+        tmp = math.atan2(ca - cb, d - sa + sb)
+        out.append(('RSR', _mod2pi(alpha - tmp), math.sqrt(p2), _mod2pi(tmp - beta)))
+    tmp = (6.0 - d_sq + 2 * cab + 2 * d * (sa - sb)) / 8.0               # RLR
     if abs(tmp) <= 1:
+        phi = math.atan2(ca - cb, d - sa + sb)
         p = _mod2pi(2 * math.pi - math.acos(tmp))
-        t = _mod2pi(alpha - math.atan2(ca - cb, d - sa + sb) + p / 2.0)
-        out.append(('RLR', t, p, _mod2pi(alpha - beta - t + p)))
-    # LRL
-    tmp = (6.0 - d * d + 2 * cab + 2 * d * (sb - sa)) / 8.0
+        t = _mod2pi(alpha - phi + _mod2pi(p / 2.0))
+        out.append(('RLR', t, p, _mod2pi(alpha - beta - t + _mod2pi(p))))
+    tmp = (6.0 - d_sq + 2 * cab + 2 * d * (sb - sa)) / 8.0               # LRL
     if abs(tmp) <= 1:
+        phi = math.atan2(ca - cb, d + sa - sb)
         p = _mod2pi(2 * math.pi - math.acos(tmp))
-        t = _mod2pi(-alpha - math.atan2(ca - cb, d + sa - sb) + p / 2.0)
-        out.append(('LRL', t, p, _mod2pi(_mod2pi(beta) - alpha - t + p)))
+        t = _mod2pi(-alpha - phi + p / 2.0)
+        out.append(('LRL', t, p, _mod2pi(_mod2pi(beta) - alpha - t + _mod2pi(p))))
     return out
 
 
 def dubins_shortest_path(q0, q1, rho):
-    """Shortest Dubins word between poses q0 and q1 = (x, y, heading); returns (word, (t, p, q)) in units of rho."""
+    """Shortest Dubins word between poses q0 and q1 = (x, y, heading); returns (word, (t, p, q)) in units of rho.
+    Restates the `dubins` library's dubins_shortest_path (the call at reference paths_library.py:151): first word of the
+    enum order with the strictly smallest cost."""
     dx, dy = q1[0] - q0[0], q1[1] - q0[1]
-    D = math.hypot(dx, dy)
+    D = math.sqrt(dx * dx + dy * dy)
     d = D / rho
-    theta = _mod2pi(math.atan2(dy, dx)) if D > 0 else 0.0
+    theta = _mod2pi(math.atan2(dy, dx)) if d > 0 else 0.0
     alpha, beta = _mod2pi(q0[2] - theta), _mod2pi(q1[2] - theta)
-    best = min(_dubins_words(alpha, beta, d), key=lambda w: w[1] + w[2] + w[3])
+    best, best_cost = None, float('inf')
+    for w in _dubins_words(alpha, beta, d):
+        cost = w[1] + w[2] + w[3]
+        if cost < best_cost:
+            best, best_cost = w, cost
     return best[0], best[1:]
 
 
-def _segment(q, length, kind):
-    x, y, th = q
-    if kind == 'L':
-        return (x + math.sin(th + length) - math.sin(th), y - math.cos(th + length) + math.cos(th), th + length)
-    if kind == 'R':
-        return (x - math.sin(th - length) + math.sin(th), y + math.cos(th - length) - math.cos(th), th - length)
-    return (x + math.cos(th) * length, y + math.sin(th) * length, th)
-
-
 def _segment_vec(x, y, th, length, kind):
+    """The library's dubins_segment, vectorised over `length`: offsets first, start configuration added last."""
+    st, ct = np.sin(th), np.cos(th)
     if kind == 'L':
-        return x + np.sin(th + length) - np.sin(th), y - np.cos(th + length) + np.cos(th), th + length
+        return (np.sin(th + length) - st) + x, (-np.cos(th + length) + ct) + y, length + th
     if kind == 'R':
-        return x - np.sin(th - length) + np.sin(th), y + np.cos(th - length) - np.cos(th), th - length
-    return x + np.cos(th) * length, y + np.sin(th) * length, th
+        return (-np.sin(th - length) + st) + x, (np.cos(th - length) - ct) + y, -length + th
+    return ct * length + x, st * length + y, th + 0.0 * length
 
 
 def dubins_sample_many(q0, word, params, rho, step):
-    """Configurations every `step` along the path (the `dubins` package's sample_many), vectorised over the
-    arc-length samples: returns an (n, 3) array of (x, y, heading)."""
-    total = sum(params) * rho
+    """Configurations every `step` along the path (the `dubins` package's sample_many, reference paths_library.py:152),
+    vectorised over the arc-length samples: returns an (n, 3) array of (x, y, heading).  Like the library: x = 0;
+    while x < length: sample(x); x += step -- the accumulated rounding decides whether the end point is sampled -- and
+    each sample picks its piece by `t' < p1`, `t' < p1 + p2`."""
+    total = (params[0] + params[1] + params[2]) * rho
     n = int(math.ceil(total / step)) + 2 if total > 0 else 0
-    # x += step while x < length, as the library does: the accumulated rounding decides whether the end point is sampled
     s = np.concatenate([[0.0], np.cumsum(np.full(max(n - 1, 0), float(step)))])[:n]
     s = s[s < total]
-    rem = s / rho
-    x = np.zeros_like(rem)
-    y = np.zeros_like(rem)
-    th = np.full_like(rem, q0[2])
-    for seg_len, kind in zip(params, word):
-        use = np.clip(rem, 0.0, seg_len)
-        x, y, th = _segment_vec(x, y, th, use, kind)
-        rem = rem - use
+    tp = s / rho
+    p1, p2 = params[0], params[1]
+    z = np.zeros(1)
+    x1, y1, th1 = _segment_vec(z, z, z + q0[2], z + p1, word[0])
+    x2, y2, th2 = _segment_vec(x1, y1, th1, z + p2, word[1])
+    first, second = tp < p1, tp < (p1 + p2)
+    xa, ya, tha = _segment_vec(0.0, 0.0, q0[2], tp, word[0])
+    xb, yb, thb = _segment_vec(x1[0], y1[0], th1[0], tp - p1, word[1])
+    xc, yc, thc = _segment_vec(x2[0], y2[0], th2[0], tp - p1 - p2, word[2])
+    x = np.where(first, xa, np.where(second, xb, xc))
+    y = np.where(first, ya, np.where(second, yb, yc))
+    th = np.where(first, tha, np.where(second, thb, thc))
     out = np.empty((s.shape[0], 3))
     out[:, 0] = x * rho + q0[0]
     out[:, 1] = y * rho + q0[1]

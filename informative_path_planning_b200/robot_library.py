@@ -199,7 +199,7 @@ class Robot(object):
                 raise ValueError('Only 2D or 3D worlds supported!')
             self.collect_observations(xlocs)
 
-            if t < T / 3 and self.learn_params:
+            if t < T // 3 and self.learn_params:      # reference :328 is Python 2: T/3 on ints floors
                 self.GP.train_kernel()
             self.trajectory.append(best_path)
             self.loc = sampling_path[-1]

@@ -13,6 +13,14 @@ import numpy as np
 from . import aq_oracle as aq
 
 
+def _py2_round(x):
+    """int(round(x)) under the reference's Python 2 (halves away from zero; Python 3 rounds halves to even)."""
+    x = float(x)
+    f = np.floor(abs(x))
+    r = f + 1.0 if abs(x) - f >= 0.5 else f
+    return int(-r if x < 0 else r)
+
+
 class PathGeneratorOracle(object):
     """paths_library.py:18-117 (frontier fan of straight segments)."""
 
@@ -47,7 +55,7 @@ class PathGeneratorOracle(object):
         for i, goal in enumerate(self.goals):
             g = np.array(goal)
             distance = np.sqrt((cp[0] - g[0]) ** 2 + (cp[1] - g[1]) ** 2)
-            samples = int(round(distance / self.ss))
+            samples = _py2_round(distance / self.ss)
             for j in range(0, samples):
                 x = cp[0] + ((j + 1) * self.ss) * np.cos(g[2])
                 y = cp[1] + ((j + 1) * self.ss) * np.sin(g[2])
@@ -59,6 +67,53 @@ class PathGeneratorOracle(object):
         self.cp = current_pose
         self.generate_frontier_points()
         return self.make_sample_paths()
+
+
+class _FreeWorldOracle(object):                             # obstacles.py FreeWorld: nothing is an obstacle
+    def in_obstacle(self, point, buff=0.0):
+        return False
+
+
+class DubinsPathGeneratorOracle(PathGeneratorOracle):
+    """paths_library.py:141-189 over oracle/dubins_oracle.py (the restated `dubins` library): dense configurations every
+    ss / 10 cut at the first one outside the open extent or inside an obstacle, every 10th kept, then the reference's
+    border / obstacle trimming loop with its `ttemp[0:m-1]` slice (negative-index quirk included) and its try/except."""
+
+    def __init__(self, frontier_size, horizon_length, turning_radius, sample_step, extent, obstacle_world=None):
+        PathGeneratorOracle.__init__(self, frontier_size, horizon_length, turning_radius, sample_step, extent)
+        self.obstacle_world = _FreeWorldOracle() if obstacle_world is None else obstacle_world
+
+    def buffered_paths(self):                                # :147-175
+        from . import dubins_oracle
+        sampling_path, true_path = {}, {}
+        for i, goal in enumerate(self.goals):
+            word, params = dubins_oracle.shortest_path(self.cp, goal, self.tr)
+            fconfig, _ = dubins_oracle.sample_many(self.cp, word, params, self.tr, self.ss / 10)
+            ftemp = []
+            for c in fconfig:
+                if c[0] > self.extent[0] and c[0] < self.extent[1] and c[1] > self.extent[2] and c[1] < self.extent[3] \
+                        and not self.obstacle_world.in_obstacle((c[0], c[1]), buff=0.0):
+                    ftemp.append(c)
+                else:
+                    break
+            try:
+                ttemp = ftemp[0::10]
+                for m, c in enumerate(ttemp):
+                    if c[0] <= self.extent[0] + 3 * self.tr or c[0] >= self.extent[1] - 3 * self.tr or \
+                            c[1] <= self.extent[2] + 3 * self.tr or c[1] >= self.extent[3] - 3 * self.tr or \
+                            self.obstacle_world.in_obstacle((c[0], c[1]), buff=3 * self.tr):
+                        ttemp = ttemp[0:m - 1]
+                if len(ttemp) >= 2:
+                    sampling_path[i] = ttemp
+                    true_path[i] = ftemp[0:ftemp.index(ttemp[-1]) + 1]
+            except Exception:
+                pass
+        return sampling_path, true_path
+
+    def make_sample_paths(self):                             # :178-189
+        coords, true_coords = self.buffered_paths()
+        self.samples = coords
+        return coords, true_coords
 
 
 class Node(object):                                          # :277-312

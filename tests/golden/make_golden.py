@@ -15,9 +15,24 @@ import sys
 
 import numpy as np
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
+SRC = os.path.dirname(os.path.abspath(__file__))
+HERE = os.environ.get('IPP_GOLDEN_OUT') or SRC          # IPP_GOLDEN_OUT: write elsewhere (reproducibility checks)
+sys.path.insert(0, SRC)
+sys.path.insert(0, os.path.dirname(os.path.dirname(SRC)))
 import ref_loader  # noqa: E402
+
+
+class _DubinsPath(object):
+    """The two calls the reference makes on the absent `dubins` package (paths_library.py:151-152), served by
+    oracle/dubins_oracle.py -- the restated library, pinned by tests/test_dubins.py; no product code is involved."""
+
+    def __init__(self, q0, q1, rho):
+        from oracle import dubins_oracle
+        self._do, self.q0, self.rho = dubins_oracle, q0, rho
+        self.word, self.params = dubins_oracle.shortest_path(q0, q1, rho)
+
+    def sample_many(self, step):
+        return self._do.sample_many(self.q0, self.word, self.params, self.rho, step)
 
 RANGES = (0., 10., 0., 10.)
 
@@ -233,8 +248,8 @@ def case_evaluation(gp, aq, pl, ev):
 def case_obstacles(ob, pl):
     """obstacles.py in_obstacle predicates (:58-75, :145-163, :189-193) on random points and buffers -- including points
     placed exactly on the (buffered) edges -- and Dubins_Path_Generator.buffered_paths (paths_library.py:147-175)
-    in a block world.  `dubins` is absent: the reference loop runs on the restated closed-form solver through a small
-    adapter with the dubins package's two calls."""
+    in a block world.  `dubins` is absent: the reference loop runs on the restated library (oracle/dubins_oracle.py)
+    through an adapter with the dubins package's two calls."""
     rng = np.random.default_rng(9)
     ext = [0., 10., 0., 10.]
     with quiet():
@@ -253,19 +268,8 @@ def case_obstacles(ob, pl):
         out[name] = np.array([[bool(w.in_obstacle((p[0], p[1]), buff=b)) for p in pts] for b in buffs])
 
     import types
-    from informative_path_planning_b200 import paths_library as mine      # closed-form solver only (host numpy)
-
-    class _Path(object):
-        def __init__(self, q0, q1, rho):
-            self.q0, self.rho = q0, rho
-            self.word, self.params = mine.dubins_shortest_path(q0, q1, rho)
-
-        def sample_many(self, step):
-            cfg = mine.dubins_sample_many(self.q0, self.word, self.params, self.rho, step)
-            return [tuple(c) for c in cfg.tolist()], None
-
     saved = pl.dubins
-    pl.dubins = types.SimpleNamespace(shortest_path=_Path)
+    pl.dubins = types.SimpleNamespace(shortest_path=_DubinsPath)
     try:
         poses = [(1.2, 1.0, 0.3), (4.6, 2.4, 1.9), (5.2, 5.1, 2.6), (8.6, 8.2, 4.0), (2.2, 6.0, 1.2), (6.0, 3.3, 5.5)]
         out['poses'] = np.array(poses)
@@ -300,19 +304,8 @@ def case_missions(gp, pl, ob, ev, rb):
     solver adapter), free and obstacle worlds.  Recorded: the pose after every step, the final belief data, the
     per-step metrics."""
     import types
-    from informative_path_planning_b200 import paths_library as mine
-
-    class _Path(object):
-        def __init__(self, q0, q1, rho):
-            self.q0, self.rho = q0, rho
-            self.word, self.params = mine.dubins_shortest_path(q0, q1, rho)
-
-        def sample_many(self, step):
-            cfg = mine.dubins_sample_many(self.q0, self.word, self.params, self.rho, step)
-            return [tuple(c) for c in cfg.tolist()], None
-
     saved = pl.dubins
-    pl.dubins = types.SimpleNamespace(shortest_path=_Path)
+    pl.dubins = types.SimpleNamespace(shortest_path=_DubinsPath)
     out = {}
     try:
         for name, spec in MISSIONS.items():
@@ -341,6 +334,27 @@ def case_missions(gp, pl, ob, ev, rb):
     np.savez_compressed(os.path.join(HERE, 'missions.npz'), **out)
 
 
+def case_environment(en):
+    """Environment.__init__ / sample_value of the reference source (envmodel_library.py:27-260): the prior draw at the
+    first grid point, the joint NUM_PTS^2 - 1 posterior sample, the regenerate-until-the-maximum-is-inside loop (seeds
+    advance inside it), and one scalar noise draw per sample_value batch (Q9)."""
+    out = {}
+    cases = [(0, 12), (1, 12), (2, 12), (0, 20)]
+    out['cases'] = np.array(cases)
+    q = np.random.default_rng(21).uniform(0, 10, (9, 2))
+    out['q'] = q
+    for seed, npts in cases:
+        with quiet():
+            e = en.Environment(RANGES, npts, 100.0, 1.0, noise=0.5, visualize=False, seed=seed, dim=2)
+        tag = 's%d_n%d_' % (seed, npts)
+        out[tag + 'X'], out[tag + 'z'] = e.GP.xvals, e.GP.zvals
+        out[tag + 'max_loc'], out[tag + 'max_val'] = np.asarray(e.max_loc, dtype=float), np.asarray(e.max_val, dtype=float)
+        np.random.seed(100 + seed)
+        out[tag + 'sample'] = e.sample_value(q)
+        out[tag + 'after'] = np.array([np.random.random()])         # the random stream position after the call
+    np.savez_compressed(os.path.join(HERE, 'environment.npz'), **out)
+
+
 def main():
     import tempfile
     os.chdir(tempfile.mkdtemp())          # the reference's visualize=True branches mkdir ./figures
@@ -359,6 +373,7 @@ def main():
     case_myopic(gp, aq, pl)
     case_evaluation(gp, aq, pl, ref_loader.load('evaluation_library'))
     case_obstacles(ref_loader.load('obstacles'), pl)
+    case_environment(ref_loader.load('envmodel_library'))
     case_missions(gp, pl, ref_loader.load('obstacles'), ref_loader.load('evaluation_library'), ref_loader.load('robot_library'))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):

@@ -15,16 +15,22 @@ What it does, and nothing more:
     image: ``GPy`` -> oracle.gpy_restated (restated published algorithm),
     ``sets``/``IPython``/``matplotlib``/``shapely``/``dubins``/``sklearn`` -> inert
     placeholders (plotting / geometry the hot path never reaches in the golden cases);
-  * ``exec``s the transformed text into a fresh module object.
+  * restores the two Python-2 SEMANTICS the arithmetic depends on: ``a / b`` on two integers floors (an AST pass turns
+    every ``/`` into ``_py2_div(a, b)``: robot_library.py:328 ``t < T/3``), and the builtin ``round`` rounds halves away
+    from zero and returns a float (paths_library.py:92 ``int(round(distance/self.ss))``);
+  * ``exec``s the transformed module into a fresh module object.
 
 The arithmetic that produces the golden vectors is therefore the reference's own
 numpy code (OnlineGPModel.update_model / predict_value, the aq_library rewards,
 Tree.leaf_helper ...), line for line.
 """
+import ast
 import os
 import re
 import sys
 import types
+
+import numpy as np
 
 REF_ROOT = os.environ.get('IPP_REFERENCE_ROOT', '/root/reference')
 
@@ -47,6 +53,46 @@ def py2_to_py3(src):
             line = _KEYS_RE.sub(r'list(\1.keys())', line)
         out.append(line)
     return '\n'.join(out)
+
+
+def _is_int(x):
+    return (isinstance(x, (int, np.integer)) and not isinstance(x, bool)) or \
+        (isinstance(x, np.ndarray) and x.dtype.kind in 'iu')
+
+
+def _py2_div(a, b):
+    """Python 2 `/` without `from __future__ import division` (no reference module imports it): floor division when
+    both operands are integers (Python ints, numpy integer scalars or integer arrays), true division otherwise."""
+    if _is_int(a) and _is_int(b):
+        return a // b
+    return a / b
+
+
+def _py2_round(x, ndigits=0):
+    """Python 2 builtin round: a float, halves away from zero (C round())."""
+    x = float(x)
+    m = 10.0 ** ndigits
+    y = abs(x) * m
+    f = float(np.floor(y))
+    r = f + 1.0 if y - f >= 0.5 else f
+    return (-r if x < 0 else r) / m
+
+
+class _Py2Division(ast.NodeTransformer):
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Div):
+            return ast.copy_location(ast.Call(func=ast.Name(id='_py2_div', ctx=ast.Load()),
+                                              args=[node.left, node.right], keywords=[]), node)
+        return node
+
+    def visit_AugAssign(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Div):
+            load = ast.parse(ast.unparse(node.target), mode='eval').body
+            call = ast.Call(func=ast.Name(id='_py2_div', ctx=ast.Load()), args=[load, node.value], keywords=[])
+            return ast.copy_location(ast.Assign(targets=[node.target], value=call), node)
+        return node
 
 
 class _Inert(types.ModuleType):
@@ -112,9 +158,12 @@ def load(modname):
     path = os.path.join(REF_ROOT, modname + '.py')
     with open(path) as f:
         src = f.read()
-    code = compile(py2_to_py3(src), path, 'exec')
+    tree = ast.fix_missing_locations(_Py2Division().visit(ast.parse(py2_to_py3(src), path)))
+    code = compile(tree, path, 'exec')
     mod = types.ModuleType(modname)
     mod.__file__ = path
+    mod.__dict__['_py2_div'] = _py2_div
+    mod.__dict__['round'] = _py2_round
     sys.modules[modname] = mod
     _loaded[modname] = mod
     # dependencies first (reference modules import each other by bare name)

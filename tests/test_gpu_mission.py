@@ -185,6 +185,28 @@ def test_environment_world_matches_oracle_built_world(pkg):
     assert np.ptp(a - mean) < 1e-9                                   # one scalar noise value for all seven points
 
 
+def test_environment_world_matches_reference_worlds(pkg):
+    """The device-backed Environment against the worlds the REFERENCE's own Environment source drew
+    (tests/golden/environment.npz; envmodel_library.py:27-260 executed by tests/golden/make_golden.py: seeds 0-2 at
+    NUM_PTS 12, seed 0 at NUM_PTS 20 -- the 399-dimensional multivariate_normal draw and the regenerate-until-inside
+    loop).  Tolerance: the joint draw is L ~ SVD(posterior covariance) applied to the same normals, so a 1e-10 change
+    of the covariance moves the sample continuously, not bitwise: 1e-5 relative + 1e-4 absolute on values of order 10."""
+    from conftest import load_golden
+    from informative_path_planning_b200.envmodel_library import Environment
+    g = load_golden('environment')
+    ranges = (0., 10., 0., 10.)
+    for seed, npts in g['cases']:
+        tag = 's%d_n%d_' % (seed, npts)
+        e = Environment(ranges, int(npts), 100.0, 1.0, noise=0.5, seed=int(seed), dim=2)
+        np.testing.assert_array_equal(e.GP.xvals, g[tag + 'X'])
+        np.testing.assert_allclose(e.GP.zvals, g[tag + 'z'], rtol=1e-5, atol=1e-4)
+        np.testing.assert_array_equal(np.asarray(e.max_loc, dtype=float), g[tag + 'max_loc'])
+        np.testing.assert_allclose(np.asarray(e.max_val, dtype=float), g[tag + 'max_val'], rtol=1e-5, atol=1e-4)
+        np.random.seed(100 + int(seed))
+        np.testing.assert_allclose(e.sample_value(g['q']), g[tag + 'sample'], rtol=1e-5, atol=1e-4)
+        assert np.random.random() == g[tag + 'after'][0]          # same number of regenerations, same draws consumed
+
+
 def test_predict_max_matches_reference_loop(pkg):
     """Robot.predict_max (robot_library.py:222-254): arg-max of the posterior mean over the 100 x 100 grid."""
     from informative_path_planning_b200 import mcts_library as mc

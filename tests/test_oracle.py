@@ -277,11 +277,10 @@ def test_oracle_missions_match_reference_runs(name):
     ev = EvaluationOracle(ms.mission_world(OnlineGPModelOracle), f_rew)
     if gen == 'default':
         pg = mo.PathGeneratorOracle(15, 1.5, 0.05, 0.5, RANGES)
-    else:       # the `dubins` C library is absent: the package's closed-form generator, Python trimming loop (no native code)
+    else:       # the `dubins` C library is absent: the oracle's restatement of it + the reference's trimming loop; the
+        # obstacle predicates are the package's host-side boxes, pinned on their own by tests/golden/obstacles.npz
         from informative_path_planning_b200 import obstacles as ob
-        from informative_path_planning_b200.paths_library import Dubins_Path_Generator
-        pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES, ms.mission_obstacles(ob, obstacle_kind))
-        pg.use_native = False
+        pg = mo.DubinsPathGeneratorOracle(15, 1.5, 0.05, 0.5, RANGES, ms.mission_obstacles(ob, obstacle_kind))
     rows, locs = [], []
 
     def record(t, robot_model, all_paths, selected_path, value, max_loc, max_val, dist, current_max):
@@ -305,3 +304,23 @@ def test_oracle_missions_match_reference_runs(name):
     np.testing.assert_allclose(r.GP.xvals, g[name + '_X'], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(r.GP.zvals, g[name + '_z'], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(np.array(rows), g[name + '_metrics'], rtol=1e-6, atol=1e-7)
+
+
+def test_environment_matches_reference_worlds():
+    """The oracle GPModel under the package's Environment loop reproduces the worlds the reference's own Environment source
+    drew (tests/golden/environment.npz: envmodel_library.py:27-260 run through ref_loader; seeds 0-2 at NUM_PTS 12, seed 0
+    at NUM_PTS 20): grid, values, maximum, sample_value and the position of the random stream afterwards -- i.e. the
+    rejection loop consumed the same seeds and draws."""
+    from informative_path_planning_b200.envmodel_library import Environment
+    from oracle.gpmodel_oracle import GPModelOracle
+    g = load_golden('environment')
+    for seed, npts in g['cases']:
+        tag = 's%d_n%d_' % (seed, npts)
+        e = Environment(RANGES, int(npts), 100.0, 1.0, noise=0.5, seed=int(seed), dim=2, gp_cls=GPModelOracle)
+        np.testing.assert_array_equal(e.GP.xvals, g[tag + 'X'])
+        np.testing.assert_allclose(e.GP.zvals, g[tag + 'z'], rtol=1e-9, atol=1e-9)
+        np.testing.assert_array_equal(np.asarray(e.max_loc, dtype=float), g[tag + 'max_loc'])
+        np.testing.assert_allclose(np.asarray(e.max_val, dtype=float), g[tag + 'max_val'], rtol=1e-9)
+        np.random.seed(100 + int(seed))
+        np.testing.assert_allclose(e.sample_value(g['q']), g[tag + 'sample'], rtol=1e-8, atol=1e-8)
+        assert np.random.random() == g[tag + 'after'][0]
