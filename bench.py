@@ -1,25 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- GP posterior mean+var queries/sec at N=4k observations (BASELINE.json metric).
+"""bench.py -- GP posterior mean+var queries/sec at N=4k observations; MCTS reward evals/sec (BASELINE.json metric).
 
-Workload (named in config.workload): BASELINE config 3 at N = 4096 observations x M = 2^20 query
-points per GPU, 10x10 Gaussian world, RBF l=1, variance 100, noise 0.5, FP64.  One "step" = one
-pass of the hot path (cross-covariance, posterior mean, posterior variance) over the M queries.
+Workload (named in config.workload): BASELINE config 3 at N = 4096 observations x M = 2^20 query points per GPU, 10x10
+Gaussian world (RFF draw from the GP prior, RBF l=1, variance 100, noise 0.5), FP64.  One "step" = a new block of k=4
+observations arrives on rank 0, is replicated to every rank (NCCL broadcast of the block at N > 1) and block-appended
+to a fork of the belief (north_star: "replicated ... on each new observation"), then the hot path (cross-covariance,
+posterior mean, posterior variance) answers the M queries of every rank against the updated belief.
 
-  value      whole-job queries/s with the queries resident in HBM (device-timed, max over ranks)
-  e2e        the same metric through the drop-in API OnlineGPModel.predict_value(numpy) ->
-             numpy: pinned host buffers, H2D + D2H inside the timed region
-  roofline   the fused DMMA variance kernel: executed flops / its CUDA-event time, against the FP64
-             DGEMM rate of this GPU measured in the same run (cuBLAS via torch.matmul) -- the driver's
-             MEASURED_PEAKS.json holds only HBM and bf16 figures, so the FP64 denominator is
-             measured here by the same method (best of 5, CUDA events) and reported beside it
+  value      whole-job queries/s with the queries resident in HBM (device-timed, max over ranks; weak scaling)
+  e2e        the same step through the drop-in API: parallel.add_data_replicated(numpy) + OnlineGPModel.predict_value(numpy)
+             -> numpy: pinned host buffers, H2D + D2H inside the timed region
+  roofline   the fused DMMA variance kernel: executed flops / its CUDA-event time, against the FP64 DGEMM rate of this GPU
+             measured in the same run (cuBLAS via torch.matmul) -- the driver's MEASURED_PEAKS.json holds only HBM and bf16
+             figures, so the FP64 denominator is measured here by the same method (best of 5, CUDA events)
   cpu_baseline  the oracle (numpy -> BLAS, all host threads) on a bounded sample of the same queries
 
-`--impl reference` times the reference's CPU path (the numpy oracle port: the reference is Python 2 +
-GPy and cannot run here) on the same config / metric.
+Second half of the metric and the multi-GPU rows, as TOP-LEVEL keys of the same JSON line (all device- or loop-timed in
+this run, every N):
+  mcts_*       dpw tree search, horizon 5, 250 rollouts, Dubins fan, N=900 observations (BASELINE config 2 shape): reward
+               evals/s and rollouts/s over the rollout loop -- the loop the reference itself times and prints
+               (mcts_library.py:689-700) -- for UCB and MES, the CPU oracle planner beside it (N=1 only) and whether the root
+               visit counts agree; at N > 1 the search is root-parallel (250 rollouts per rank, one all_reduce)
+  config5_*    BASELINE config 5, STRONG scaling: 65536 candidate Dubins paths x 20 samples generated on the device, N=4096,
+               whole paths sharded across the ranks, rewards returned by one NCCL all_gather
+  replicate_*  one k=4 observation block replicated at N=4096: 'recompute' (broadcast the block, every rank appends)
+               vs 'broadcast' (rank 0 appends, W^-1 and alpha are broadcast over NVLink), with the NCCL bytes
 
-Multi-GPU (`torchrun ... bench.py --gpus N`): queries shard across ranks with no data-path collective
-(weak scaling: every rank owns M queries against the replicated belief); barrier + synchronize on both
-sides of the timed region, max over ranks.
+`--impl reference` times the reference's CPU path (the numpy oracle port: the reference is Python 2 + GPy and cannot
+run here) on the same config / metric.
 """
 import argparse
 import ctypes
@@ -52,11 +60,22 @@ UNIT = 'queries/s'
 
 
 def make_world(seed, n):
+    """Synthetic Gaussian-environment data: X ~ U([0,10]^2), z = a draw from the GP prior (RBF l=1,
+    variance 100) through F=2000 random Fourier features (envmodel_library.py:172-187 restated for N > 2k) + N(0, noise)."""
     rng = np.random.default_rng(seed)
     X = rng.uniform(0, 10, (n, 2))
-    # a draw-like smooth field + sensor noise (synthetic Gaussian-environment data)
-    z = 10.0 * np.sin(0.7 * X[:, :1]) * np.cos(0.5 * X[:, 1:2]) + 3.0 * np.cos(1.3 * X[:, :1] + 0.4 * X[:, 1:2])
+    F = 2000
+    W = rng.normal(0.0, 1.0, (F, 2))                   # spectral density of the RBF kernel with lengthscale 1
+    b = rng.uniform(0.0, 2.0 * np.pi, (F, 1))
+    theta = rng.normal(0.0, 1.0, (F, 1))
+    z = (np.sqrt(2.0 * 100.0 / F) * (theta.T @ np.cos(W @ X.T + b))).T
     return X, z + rng.normal(0, np.sqrt(NOISE), (n, 1))
+
+
+def new_block(seed, k=4):
+    """The k new observations of one step (a path's worth of samples, as Robot.collect_observations appends them)."""
+    rng = np.random.default_rng(seed)
+    return rng.uniform(1, 9, (k, 2)), rng.normal(0, 10.0, (k, 1))
 
 
 def flops_per_query(n, mode='sym'):
@@ -171,11 +190,145 @@ def run_reference(args, rank):
                                'sample of %d of the 2^20 queries' % sample, 'n_obs': N_OBS, 'queries_per_step': sample},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d queries per step, numpy/BLAS port of gpmodel_library.py:303-328 (reference is '
-                                   'Python 2 + GPy: not runnable in this image)' % sample},
+                                   'Python 2 + GPy: not runnable in this image); the per-step block append of the GPU arm '
+                                   '(gpmodel_library.py:230-279, O(N^2 k) + two N x N copies on the CPU) is left out of the CPU '
+                                   'step, which favours the CPU figure' % sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def device_timed(fn, steps, barrier, reduce_max):
+    """ms per call of fn(), CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return reduce_max(e0.elapsed_time(e1)) / steps
+
+
+def bench_config5(L, aq, parallel, model, rank, world, barrier, reduce_max, steps=3):
+    """BASELINE config 5 (strong scaling): 65536 (pose, goal) pairs -> Dubins curves generated on the device (~20 samples
+    per path: goal 10.0 ahead in a 40 x 40 world, sample step 0.5) -> UCB rewards against the replicated N=4096 belief ->
+    one NCCL all_gather of the per-path rewards.  Whole paths are sharded: rank r owns pairs [lo, hi)."""
+    import torch
+    import torch.distributed as dist
+    from informative_path_planning_b200.paths_library import dubins_paths_device, ragged_points
+    P = 65536
+    ext = (0., 40., 0., 40.)
+    rng = np.random.default_rng(55)
+    poses = np.column_stack([rng.uniform(12, 28, P), rng.uniform(12, 28, P), rng.uniform(-np.pi, np.pi, P)])
+    ang = poses[:, 2] + rng.uniform(-1.0, 1.0, P)
+    goals = np.column_stack([poses[:, 0] + 10.0 * np.cos(ang), poses[:, 1] + 10.0 * np.sin(ang), ang])
+    # the belief's observations live in [0, 10]^2; the candidate poses are mapped into it (x / 4) when scored, so the
+    # posterior is the benchmark belief's and the path geometry (rho 0.5, 20 samples) is config 5's
+    lo, hi = parallel.shard_bounds(P, rank, world)
+    poses_d, goals_d = L.to_device(poses[lo:hi]), L.to_device(goals[lo:hi])
+    sqb = [float(np.sqrt(aq.ucb_beta(10)))]
+    width = parallel.shard_bounds(P, 0, world)[1]
+    info = {}
+
+    def step():
+        samp, counts, _ = dubins_paths_device(poses_d, goals_d, 0.5, 0.5, ext, max_samples=24)
+        pts, offs, kept = ragged_points(samp, counts)
+        rew, _ = model.reward_paths_device(L.REWARD_UCB, pts * 0.25, offs, params=sqb)
+        full = torch.full((width,), float('nan'), dtype=torch.float64, device=rew.device)     # dropped paths stay NaN
+        full[kept] = rew
+        if world > 1:
+            out = torch.empty(world * width, dtype=torch.float64, device=rew.device)
+            dist.all_gather_into_tensor(out, full)
+            full = out
+        info['points'], info['kept'], info['finite'] = int(pts.shape[0]), int(kept.numel()), int(torch.isfinite(full).sum())
+        return full
+
+    step()
+    ms = device_timed(step, steps, barrier, reduce_max)
+    t = torch.tensor([float(info['points']), float(info['kept'])], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    kept_total = int(t[1].item())
+    return {'config5_reward_evals_per_s': kept_total / (ms / 1e3), 'config5_ms_per_step': ms, 'config5_scaling': 'strong',
+            'config5_paths': kept_total, 'config5_points': int(t[0].item()),
+            'config5_allgather_bytes_per_rank_per_step': int(8 * width * (world - 1)) if world > 1 else 0,
+            'config5_finite_rewards': info['finite'],
+            'config5_workload': '65536 (pose, goal) pairs -> device-generated Dubins paths (~20 samples each), N=4096 FP64, '
+                                'UCB; whole paths sharded over %d GPU(s), rewards all-gathered; device-timed, max over ranks' % world}
+
+
+def bench_replicate(parallel, model, rank, world, barrier, reduce_max):
+    """One k=4 observation block replicated onto the N=4096 belief, both modes of parallel.add_data_replicated."""
+    import copy
+    import torch
+    out = {}
+    xb, zb = new_block(900)
+    for mode in ('recompute', 'broadcast'):
+        def one():
+            f = copy.copy(model)
+            parallel.add_data_replicated(f, xb if rank == 0 else None, zb if rank == 0 else None, mode=mode)
+        one()
+        torch.cuda.synchronize()
+        out['replicate_%s_ms' % mode] = min(device_timed(one, 1, barrier, reduce_max) for _ in range(3))
+    n = N_OBS + 4
+    ld = (n + 15) // 16 * 16
+    out['replicate_recompute_nccl_bytes'] = int(4 * 3 * 8) if world > 1 else 0
+    out['replicate_broadcast_nccl_bytes'] = int(8 * (n * ld + n * 2 + n + n)) if world > 1 else 0   # W^-1, X, z, alpha
+    return out
+
+
+def bench_tree_search(parallel, rank, world, barrier, with_cpu):
+    """dpw tree search at N=900 (BASELINE config 2 shape).  N=1: cMCTS.choose_trajectory; N>1: root-parallel, 250
+    rollouts per rank.  Rates are over the rollout loop (the reference's own timed region, mcts_library.py:689-700)."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_mcts as bm
+    out = {'mcts_workload': 'dpw tree, horizon 5, 250 rollouts%s, 15-goal Dubins fan, N=900 observations, one planning step; '
+                            'rates over the rollout loop (reference mcts_library.py:689-700), best of 3'
+                            % (' per rank (root-parallel, one all_reduce of the root statistics)' if world > 1 else '')}
+    if world == 1:
+        for f_rew, tag in (('mean', 'mcts'), ('mes', 'mcts_mes')):
+            bm.run('gpu', 900, f_rew, budget=20)
+            g = min((bm.run('gpu', 900, f_rew) for _ in range(3)), key=lambda r: r['loop_seconds'])
+            out[tag + '_reward_evals_per_s'] = g['loop_reward_evals_per_s']
+            out[tag + '_rollouts_per_s'] = g['loop_rollouts_per_s']
+            out[tag + '_planning_step_ms'] = 1e3 * g['seconds']
+            if f_rew == 'mean':
+                visits = g['root_visits']
+        if with_cpu:
+            c = bm.run('cpu', 900, 'mean')
+            out['mcts_cpu_reward_evals_per_s'] = c['loop_reward_evals_per_s']
+            out['mcts_cpu_rollouts_per_s'] = c['loop_rollouts_per_s']
+            out['mcts_same_root_visit_counts'] = bool(visits == c['root_visits'])
+        return out
+    from informative_path_planning_b200 import aq_library as aq, gpmodel_library as gp, mcts_library as mc
+    from informative_path_planning_b200.paths_library import Dubins_Path_Generator
+    X, z = bm.world(900)
+    model = gp.OnlineGPModel(bm.R, 1.0, 100.0, noise=0.5)
+    parallel.add_data_replicated(model, X if rank == 0 else None, z if rank == 0 else None)
+    pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, bm.R)
+    for f_rew, tag, fn in (('mean', 'mcts', aq.mean_UCB), ('mes', 'mcts_mes', aq.mves)):
+        best = None
+        for rep in range(4):                                   # first repetition = warm-up
+            planner = mc.cMCTS(250 * world, model, (5.0, 5.0, 0.3), 5, pg, fn, f_rew, 3, tree_type='dpw')
+            barrier()
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+                parallel.mcts_root_parallel(planner, 3, seed=100 + rep)
+            t = torch.tensor([planner.rollout_seconds, float(planner.tree.reward_evals)], dtype=torch.float64, device='cuda')
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            if rep > 0 and (best is None or float(tmax[0]) < best[0]):
+                best = (float(tmax[0]), float(t[1]))
+        out[tag + '_rollouts_per_s'] = 250 * world / best[0]
+        out[tag + '_reward_evals_per_s'] = best[1] / best[0]
+    return out
 
 
 def main():
@@ -199,6 +352,7 @@ def main():
         run_reference(args, rank)
         return
 
+    import copy
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -211,25 +365,34 @@ def main():
 
     M = args.queries
     X, z = make_world(0, N_OBS)
+    # the standing belief holds N - 4 observations; every step appends the block that brings it to N = 4096
+    K_NEW = 4
     model = gp.OnlineGPModel(RANGES, 1.0, 100.0, noise=NOISE)
-    if world > 1:
-        parallel.add_data_replicated(model, X if rank == 0 else None, z if rank == 0 else None)
-    else:
-        model.add_data(X, z)
+    parallel.add_data_replicated(model, X[:N_OBS - K_NEW] if rank == 0 else None, z[:N_OBS - K_NEW] if rank == 0 else None)
+    xb, zb = (X[N_OBS - K_NEW:], z[N_OBS - K_NEW:]) if rank == 0 else (None, None)
     rng = np.random.default_rng(1000 + rank)
     xq_host = torch.from_numpy(rng.uniform(0, 10, (M, 2))).pin_memory()
     xq = xq_host.cuda()
-    kernels_per_step = 3 * ((M + 32767) // 32768)
+    APPEND_LAUNCHES = 8                                 # 2 cross-covariances, V = PQ, Gram, Schur inverse, U / VM, W' update, alpha
+    kernels_per_step = APPEND_LAUNCHES + 3 * ((M + 32767) // 32768)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     model.predict_precision = args.precision        # also steers predict_value (the e2e leg)
 
     def step():
-        return model.predict_device(xq)
+        belief = copy.copy(model)                   # O(1) fork: the device state of a belief is immutable
+        parallel.add_data_replicated(belief, xb, zb)   # N > 1: NCCL broadcast of the block, then every rank appends it
+        return belief.predict_device(xq)
 
     for _ in range(args.warmup):
         step()
@@ -249,26 +412,41 @@ def main():
     L.check(L.lib.ipp_profile_read(ctypes.byref(tot_ms), ctypes.byref(launches)))
     L.check(L.lib.ipp_profile_enable(0))
     clocks = sampler.stop()
-    t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = reduce_max(ms_total) / args.steps
     value = world * M / (ms_step / 1e3)
 
     # ---- end to end through the drop-in API (numpy in, numpy out; pinned host buffers)
     xq_np = xq_host.numpy()
+
+    def e2e_step():
+        belief = copy.copy(model)
+        parallel.add_data_replicated(belief, xb, zb)
+        return belief.predict_value(xq_np)
+
     for _ in range(2):
-        model.predict_value(xq_np)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
-        mu_h, var_h = model.predict_value(xq_np)
+        mu_h, var_h = e2e_step()
     torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * M * e2e_steps / float(dt.item())
+    e2e_value = world * M * e2e_steps / reduce_max(time.perf_counter() - t0)
+
+    # ---- the multi-GPU rows and the tree search, every N (collectives inside: all ranks take part)
+    multi = {}
+    if not args.no_extras:
+        model = copy.copy(model)
+        parallel.add_data_replicated(model, xb, zb)          # the N = 4096 belief itself, for the rows below
+        model.predict_precision = 'fp64'
+        for name, fn in (('config5', lambda: bench_config5(L, aq, parallel, model, rank, world, barrier, reduce_max)),
+                         ('replicate', lambda: bench_replicate(parallel, model, rank, world, barrier, reduce_max)),
+                         ('mcts', lambda: bench_tree_search(parallel, rank, world, barrier, with_cpu=(world == 1)))):
+            try:                                    # measurement rows never take the headline down: a failure that every
+                multi.update(fn())                  # rank sees alike (the likely kind) is recorded and the run goes on
+            except Exception as e:
+                multi[name + '_error'] = repr(e)
+        model.predict_precision = args.precision
 
     if rank != 0:
         if world > 1:
@@ -329,17 +507,23 @@ def main():
                  % args.precision[-1],
         'data': 'synthetic',
         'config': {'workload': 'gp_predict N=4096 obs x M=2^20 queries per GPU (BASELINE config 3 at N=4k), %s, 10x10 '
-                               'world RBF l=1 var=100 noise=0.5' % ('FP64' if fp64 else 'sliced INT8 (%s)' % args.precision),
-                   'n_obs': N_OBS, 'queries_per_gpu': M,
+                               'Gaussian world (RFF draw from the GP prior, F=2000) RBF l=1 var=100 noise=0.5; every step first '
+                               'replicates a new block of 4 observations (4092 -> 4096; NCCL broadcast at N>1 + block append on '
+                               'every rank), then answers the queries'
+                               % ('FP64' if fp64 else 'sliced INT8 (%s)' % args.precision),
+                   'n_obs': N_OBS, 'queries_per_gpu': M, 'new_observations_per_step': 4,
+                   'nccl_bytes_per_step': int(4 * 3 * 8 + 2 * 32) if world > 1 else 0,
                    'variance_form': 'W^-1 symmetric-half (IPP_VAR_WINV_SYM)' if fp64 else 'Cholesky form |L^-1 k|^2 (%s)' % args.precision,
                    'l2': 'no flush: per step the kernels stream the 134 MB W^-1 and a 1.07 GB cross-covariance '
                          'scratch, both larger than the 126 MB L2',
                    'parallelism': 'queries sharded, belief replicated (dp%d)' % world},
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(M * 2 * 8), 'd2h_bytes_per_step': int(M * 2 * 8)},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(M * 2 * 8 + 4 * 3 * 8),
+                'd2h_bytes_per_step': int(M * 2 * 8)},
         'gpu_launches': int(kernels_per_step * args.steps),
         'clocks': clocks,
         'roofline': roofline,
     }
+    line.update(multi)                              # mcts_*, config5_*, replicate_*: top-level scalars
 
     model.predict_precision = 'fp64'                # the extras below name their precision explicitly
     ms_fp64 = ms_step if fp64 else None
@@ -391,24 +575,17 @@ def main():
             extras['reward_evals_per_s_ucb_i8x6'] = repr(e)
         model.predict_precision = 'fp64'
         extras['reward_workload'] = '%d paths x %d points, N=4096 (BASELINE config 5 shape on 1 GPU)' % (P, k)
-        # tree search (BASELINE config 2 shape): dpw, horizon 5, 250 rollouts, Dubins fan, N=900 observations;
-        # GPU-backed planner vs the CPU oracle planner on the same seeds (identical visit counts expected)
+        # the reference's own call pattern on the device (one reward + two add_data per level, Python tree), for scale
         try:
             sys.path.insert(0, os.path.join(ROOT, 'tools'))
             import bench_mcts
-            bench_mcts.run('gpu', 900, 'mean', budget=20)
-            g_ = min((bench_mcts.run('gpu', 900, 'mean') for _ in range(3)), key=lambda r: r['seconds'])   # best of 3 (host jitter)
             bench_mcts.run('gpu', 900, 'mean', budget=20, fuse=False)
             p_ = bench_mcts.run('gpu', 900, 'mean', fuse=False)
-            c_ = bench_mcts.run('cpu', 900, 'mean')
-            extras['mcts_N900_dpw_ucb'] = {
-                'reward_evals_per_s': g_['reward_evals_per_s'], 'rollouts_per_s': g_['rollouts_per_s'],
-                'per_level_calls_reward_evals_per_s': p_['reward_evals_per_s'],
-                'cpu_reward_evals_per_s': c_['reward_evals_per_s'], 'cpu_rollouts_per_s': c_['rollouts_per_s'],
-                'same_root_visit_counts': g_['root_visits'] == c_['root_visits'] == p_['root_visits'],
-                'note': 'native DPW search (ipp_tree_search_dpw: walk + random streams in native code, one device pass per rollout) vs the Python tree with one reward + two add_data per level; CPU = the oracle planner'}
+            extras['mcts_N900_dpw_ucb_per_level_calls'] = {
+                'reward_evals_per_s': p_['loop_reward_evals_per_s'], 'rollouts_per_s': p_['loop_rollouts_per_s'],
+                'note': 'Python tree, one reward + two add_data device calls per level (the reference call pattern)'}
         except Exception as e:      # measurement extra only
-            extras['mcts_N900_dpw_ucb'] = {'error': repr(e)}
+            extras['mcts_N900_dpw_ucb_per_level_calls'] = {'error': repr(e)}
         # max-value sampling (BASELINE config 4): F=1000 shared features x S=100 samples on a 2^20-point grid
         try:
             F_, S_, G_ = 1000, 100, 1 << 20
@@ -571,6 +748,18 @@ def main():
             except Exception as e:
                 extras[prec + '_N4096'] = {'error': repr(e)}
         line['extra'] = extras
+        # the other BASELINE configs as top-level scalars (the driver's record keeps top-level keys only)
+        def lift(dst, src, key):
+            v = extras.get(src, {})
+            if isinstance(v, dict) and isinstance(v.get(key), (int, float)):
+                line[dst] = v[key]
+        lift('config4_grid_stage_ms', 'rff_F1000_S100_G2^20', 'ms')
+        lift('config4_end_to_end_ms', 'rff_F1000_S100_G2^20', 'end_to_end_ms_incl_features_and_100_weight_draws')
+        for prec in ('i8x7', 'i8x6', 'i8x5'):
+            lift('config3_%s_queries_per_s' % prec, prec + '_N4096', 'queries_per_s')
+            lift('config3_%s_var_rel_err_max_vs_fp64' % prec, prec + '_N4096', 'var_rel_err_max')
+            lift('config3_%s_frac_of_cublas_int8' % prec, prec + '_N4096', 'frac_of_cublas_int8')
+        lift('config5_dubins_generation_ms', 'dubins_on_device_N4096', 'path_generation_ms')
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

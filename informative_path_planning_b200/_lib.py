@@ -138,11 +138,41 @@ SIGNATURES = {
 }
 
 
+def source_hash():
+    """SHA-256 over the files the library is built from, in the Makefile's order (csrc/Makefile: HASHED)."""
+    import glob
+    import hashlib
+    csrc = os.path.join(_HERE, 'csrc')
+    files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(csrc, '*.cu')) + glob.glob(os.path.join(csrc, '*.cuh')))
+    paths = [os.path.join(csrc, f) for f in files] + [os.path.join(csrc, 'Makefile'),
+                                                     os.path.join(_HERE, '..', 'include', 'ipp_b200.h')]
+    h = hashlib.sha256()
+    for path in paths:
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _check_source_stamp():
+    """Refuse a library that was not built from the sources beside it (the .so is git-ignored and travels as a built
+    artefact: a stale one would otherwise ship silently).  Skipped for an explicit IPP_B200_LIB override."""
+    if os.environ.get('IPP_B200_LIB'):
+        return
+    stamp = LIB_PATH + '.srchash'
+    built = open(stamp).read().strip() if os.path.exists(stamp) else None
+    if built != source_hash():
+        raise ImportError(
+            'informative_path_planning_b200: %s was not built from the current csrc/*.cu, *.cuh, Makefile and '
+            'include/ipp_b200.h (%s). Rebuild it with `python -c \'import __graft_entry__ as g; g.build()\'`.'
+            % (LIB_PATH, 'no source stamp beside it' if built is None else 'source stamp differs'))
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "informative_path_planning_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    _check_source_stamp()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly

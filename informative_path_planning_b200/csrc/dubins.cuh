@@ -1,7 +1,7 @@
 // Dubins closed forms + the trimming loop of Dubins_Path_Generator.buffered_paths (reference paths_library.py:147-175),
 // shared by the host path-set generator / device batch kernel (paths.cu) and the native tree search (tree.cu).
 // Classical six-word closed form (Shkel & Lumelsky 2001) as the `dubins` C library behind paths_library.py:151-152 states
-// it (oracle/dubins_oracle.py restates the library function by function; tests/test_dubins.py pins both).
+// it, word by word and in its enum order (pinned by tests/test_dubins.py against an independent geometric construction).
 #pragma once
 #include <math.h>
 #include "internal.cuh"

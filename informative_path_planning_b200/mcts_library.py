@@ -30,6 +30,7 @@ ONE call of aq_library.reward_paths instead of one predict per path (robot_libra
 """
 import copy
 import random
+import time
 
 import numpy as np
 import torch
@@ -476,12 +477,16 @@ class cMCTS(object):
                              depth=self.rl, param=param, c=self.c)
         budget = self.comp_budget if budget is None else budget
         self.native_search_used = False
+        # the reference's own performance figure brackets exactly this loop (:689-700, "Rollouts completed in ...s")
+        time_start = time.time()
         if self.NATIVE_SEARCH and self._search_native(t, budget):
             self.native_search_used = True
             cMCTS.native_searches += 1
-            return self.tree.root.children
-        for _ in range(budget):
-            self.tree.get_next_leaf(copy.copy(self.GP))
+        else:
+            for _ in range(budget):
+                self.tree.get_next_leaf(copy.copy(self.GP))
+        self.rollout_seconds = time.time() - time_start
+        self.rollouts = budget
         return self.tree.root.children
 
     def _search_native(self, t, budget):

@@ -7,6 +7,7 @@ consumed in the reference's order so seeded runs select the same actions.
 """
 import copy
 import random
+import time
 
 import numpy as np
 
@@ -316,8 +317,10 @@ class cMCTSOracle(object):                                   # :636-713
             raise ValueError('Tree type must be one of either \'dpw\' or \'belief\'')
         self.tree = cls(self.f_rew, self.aquisition_function, self.GP, self.cp, self.path_generator, t,
                         depth=self.rl, param=param, c=self.c)
+        time_start = time.time()                             # :689: the reference's "Rollouts completed in ...s"
         for _ in range(self.comp_budget):                    # :692-698
             self.tree.get_next_leaf(copy.copy(self.GP))
+        self.rollout_seconds = time.time() - time_start
         top = max(n.nqueries for n in self.tree.root.children)
         best = random.choice([n for n in self.tree.root.children if n.nqueries == top])     # :707
         all_vals = {i: c.reward / float(c.nqueries) for i, c in enumerate(self.tree.root.children)}

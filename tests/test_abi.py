@@ -278,3 +278,16 @@ def test_native_tree_path_sets_equal_the_generators():
             assert list(paths.keys()) == goal[:n[0]].tolist(), pose
             for i, key in enumerate(paths):
                 assert np.array_equal(np.array(paths[key]), samp[i, :cnt[i]]), (pose, key)
+
+
+def test_stale_library_is_refused(monkeypatch):
+    """The built library carries a stamp of the sources it was built from (csrc/Makefile); _lib refuses to load one whose
+    stamp does not match the sources beside it."""
+    import pytest
+    from informative_path_planning_b200 import _lib as L
+    monkeypatch.delenv('IPP_B200_LIB', raising=False)
+    L._check_source_stamp()                                   # the library in the tree is current
+    assert open(L.LIB_PATH + '.srchash').read().strip() == L.source_hash()
+    monkeypatch.setattr(L, 'source_hash', lambda: 'edited-after-the-build')
+    with pytest.raises(ImportError, match='was not built from the current'):
+        L._check_source_stamp()

@@ -44,8 +44,12 @@ def run(kind, n_obs, f_rew, budget=250, depth=5, fuse=True, native=True):
         t0 = time.perf_counter(); m.choose_trajectory(t=3); dt = time.perf_counter() - t0
     nq = [c.nqueries for c in m.tree.root.children]
     n_evals = fn.n if kind == 'cpu' else m.tree.reward_evals
+    # `seconds` = the whole planning step (choose_trajectory: max-value sampling for MES, tree, rollouts, path set);
+    # `loop_seconds` = the rollout loop alone, what the reference itself times and prints (mcts_library.py:689-700)
+    loop = float(getattr(m, 'rollout_seconds', dt))
     return {'kind': kind if kind == 'cpu' else (('gpu_native' if native else 'gpu_fused') if fuse else 'gpu_per_level'), 'n_obs': n_obs, 'f_rew': f_rew,
             'seconds': dt, 'rollouts_per_s': budget / dt, 'reward_evals': n_evals, 'reward_evals_per_s': n_evals / dt,
+            'loop_seconds': loop, 'loop_rollouts_per_s': budget / loop, 'loop_reward_evals_per_s': n_evals / loop,
             'root_visits': nq}
 
 if __name__ == '__main__':
