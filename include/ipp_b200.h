@@ -47,6 +47,11 @@ typedef struct ipp_rbf {
 #define IPP_REWARD_MES    2   /* aq_library.py:281-337 mves                             */
 #define IPP_REWARD_NAIVE  3   /* aq_library.py:339-367 naive: host-side, ipp_tree_search_dpw only (reads no belief) */
 #define IPP_REWARD_NAIVE_VALUE 4 /* aq_library.py:369-413 naive_value: sampled functions on the device, ipp_tree_search_dpw only */
+#define IPP_REWARD_INFO   5   /* aq_library.py:34-80 info_gain, ipp_rollout_rewards / ipp_tree_search_dpw only.  The caller passes
+                               * the INFORMATION-GAIN belief instead of the regression belief: kern = RBF with variance v^2,
+                               * winv = (I + v K(X,X))^-1 (ipp_gp_factor(kern_v2, diag_add = 1)), diag_add = 1, noise_pred = 0,
+                               * params_host[0] = 2 pi e; level l's reward is params[0] * logdet(I + Cov(q_l | earlier levels)),
+                               * the Schur form of logdet(I + vK([X; q])) - logdet(I + vK(X)).  At most 32 points per rollout. */
 
 /* variance formulations for ipp_gp_predict */
 #define IPP_VAR_WINV_SYM  0   /* var = v - k^T W^-1 k, W^-1 symmetric: lower tiles x2 + diagonal tiles (N^2 flops/query) */
@@ -190,6 +195,13 @@ int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const d
                         const double* pts, const double* zobs, const int32_t* offsets_host,
                         const int32_t* reps_host, int L, double* reward, int32_t* info,
                         double* work, void* stream);
+/* diagnostics: 1 = the whole rollout in one launch (default for <= 64 points; only the lower tiles of winv are read),
+ * 0 = the four-kernel sequence; any other value leaves the mode alone.  Returns the mode before the call. */
+int ipp_rollout_mode(int fused);
+/* diagnostics: SM clocks of the finishing CTA of the last one-launch rollout: [0..3] time in {its tiles, the hand-over,
+ * the sum of the partials + C0, the conditioning}; [4..10] the tile phase in detail; [16..26] clock at the start of the
+ * conditioning, of each level, of the scoring and at the end */
+int ipp_rollout_debug_clocks(int64_t out[32]);
 
 /* ---- a11: random-Fourier-feature function samples on a grid + per-sample arg-max
  *      (general_target aq_library.py:138-139 and the grid stage of global_maximization :475-479).
@@ -353,6 +365,8 @@ int ipp_abi_struct_sizes(int32_t out[4]);
 /* where the last ipp_tree_search_dpw spent its wall time: the tree walk (selection, candidate paths, draws) and the
  * device pass (staging + launches + synchronisation), microseconds summed over the rollouts */
 int ipp_tree_last_timing(double* walk_us, double* device_us);
+/* of device_us: host time inside the kernel-launch calls themselves */
+int ipp_tree_last_launch_us(double* launch_us);
 /* test hooks for the two generators (host only, no device): out[i] = random.choice(range(ns[i])) /
  * out[i] = np.random.standard_normal() continued from the given state, which is advanced. */
 int ipp_rng_py_choices(ipp_mt_state* py_rng, const int32_t* ns, int count, int32_t* out);

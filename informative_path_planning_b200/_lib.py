@@ -17,7 +17,8 @@ IPP_MAX_DIM = 3
 IPP_APPEND_MAX_K = 32
 IPP_ROLLOUT_MAX_POINTS = 128
 IPP_ROLLOUT_MAX_LEVELS = 32
-REWARD_UCB, REWARD_EI, REWARD_MES, REWARD_NAIVE, REWARD_NAIVE_VALUE = 0, 1, 2, 3, 4
+REWARD_UCB, REWARD_EI, REWARD_MES, REWARD_NAIVE, REWARD_NAIVE_VALUE, REWARD_INFO = 0, 1, 2, 3, 4, 5
+IPP_ROLLOUT_INFO_MAX_POINTS = 32
 VAR_WINV_SYM, VAR_WINV_FULL, VAR_CHOL = 0, 1, 2
 
 
@@ -117,6 +118,8 @@ SIGNATURES = {
     'ipp_rollout_workspace': (_I64, [_I64, _I64]),
     'ipp_rollout_rewards': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _D, _D, _INT, _P, _INT, _P, _I64, _P, _P, _P, _P, _INT, _P, _P,
                                    _P, _P]),
+    'ipp_rollout_mode': (_INT, [_INT]),
+    'ipp_rollout_debug_clocks': (_INT, [_P]),
     'ipp_rff_workspace': (_I64, [_I64, _I64, _I64, _INT]),
     'ipp_rff_eval_argmax': (_INT, [_P, _P, _P, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
@@ -131,6 +134,7 @@ SIGNATURES = {
                                    _P, _P]),
     'ipp_abi_struct_sizes': (_INT, [_P]),
     'ipp_tree_last_timing': (_INT, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    'ipp_tree_last_launch_us': (_INT, [ctypes.POINTER(ctypes.c_double)]),
     'ipp_rng_py_choices': (_INT, [ctypes.POINTER(IppMtState), _P, _INT, _P]),
     'ipp_rng_np_normals': (_INT, [ctypes.POINTER(IppMtState), _INT, _P]),
     'ipp_tree_path_set': (_INT, [ctypes.POINTER(IppTreeParams), _P, _P, _P, _P, _P, _INT]),

@@ -14,67 +14,130 @@
 namespace ipp {
 
 constexpr int NB = 64;
-constexpr int DIAG_SMEM = 2 * NB * (NB + 1) * 8;
+constexpr int DIAG_LD = NB + 1;
+constexpr int DIAG_SMEM = (2 * NB * DIAG_LD + 32 * 33 + NB) * 8;
 
 // Cholesky of the jb x jb lower block at A (leading dimension lda) + its inverse into dinv[64][64].
+//
+// r1 version: 3 barriers, a division per column entry and two integer divisions per updated element for each of the 64
+// pivots, then 64 threads each running a serial O(n^2) substitution -- 100 us per block, 40 % of a refresh at N = 4096
+// (profiles/r2a_launches_factor_4096.csv).  Now:
+//   * one barrier per pivot.  Four threads own a row (columns k = j + 1 + part, + 4, ...); every thread takes the pivot
+//     d = a[j][j] and forms r = 1 / sqrt(d) itself, scales its own a[i][j] and applies  a[i][k] -= (a[i][j] r) (a[k][j] r)
+//     from the UNSCALED column still in shared memory; the scaled column goes to a second array, so nothing has to be
+//     re-read after a barrier;
+//   * the triangular inverse by recursive doubling with all 256 threads: the eight 8 x 8 diagonal blocks by substitution
+//     in registers (reciprocal pivots already known), then Linv21 = -Linv22 (L21 Linv11) for block sizes 8, 16, 32.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t lda, int jb,
                                                          double* __restrict__ dinv, double* logdet,
                                                          int32_t* info, int j0) {
     extern __shared__ double sm[];
-    double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
-    double (*li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+    double (*a)[DIAG_LD] = reinterpret_cast<double (*)[DIAG_LD]>(sm);                      // working copy, later L^-1
+    double (*l)[DIAG_LD] = reinterpret_cast<double (*)[DIAG_LD]>(sm + NB * DIAG_LD);       // the factor
+    double (*tmp)[33] = reinterpret_cast<double (*)[33]>(sm + 2 * NB * DIAG_LD);           // L21 Linv11
+    double* rinv = sm + 2 * NB * DIAG_LD + 32 * 33;                                       // 1 / L[j][j]
     __shared__ int bad;
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+    for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
         double v = (r == c) ? 1.0 : 0.0;
         if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
         a[r][c] = v;
-        li[r][c] = 0.0;
+        l[r][c] = (r == c && r >= jb) ? 1.0 : 0.0;
     }
+    if (tid < NB) rinv[tid] = 1.0;
     if (tid == 0) bad = 0;
     __syncthreads();
+    const int row = tid >> 2, part = tid & 3;
     for (int j = 0; j < jb; ++j) {
-        if (tid == 0) {
-            double d = a[j][j];
-            if (!(d > 0.0)) {            // also catches NaN, like LAPACK's dpotrf
-                if (bad == 0) bad = j + 1;
-                d = 1.0;
-            }
-            a[j][j] = sqrt(d);
+        double d = a[j][j];
+        if (!(d > 0.0)) {                // also catches NaN, like LAPACK's dpotrf
+            if (tid == 0 && bad == 0) bad = j + 1;
+            d = 1.0;
         }
-        __syncthreads();
-        const double djj = a[j][j];
-        if (tid > j && tid < jb) a[tid][j] /= djj;
-        __syncthreads();
-        const int w = jb - j - 1;
-        for (int idx = tid; idx < w * w; idx += blockDim.x) {
-            const int i = j + 1 + idx / w, k = j + 1 + idx % w;
-            if (k <= i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+        const double r = rsqrt(d);
+        if (tid == 0) { l[j][j] = d * r; rinv[j] = r; }
+        if (row > j && row < jb) {
+            const double c = a[row][j] * r;
+            if (part == 0) l[row][j] = c;
+            // four elements per pass, all loads before the first store (the compiler cannot prove that the stores to
+            // a[row][.] do not alias the column reads, and would otherwise serialise load -> fma -> store per element)
+            for (int k = j + 1 + part; k <= row; k += 16) {
+                double col[4], old[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + 4 * u;
+                    col[u] = kk <= row ? a[kk][j] : 0.0;
+                    old[u] = kk <= row ? a[row][kk] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + 4 * u;
+                    if (kk <= row) a[row][kk] = fma(-c, col[u] * r, old[u]);
+                }
+            }
         }
         __syncthreads();
     }
-    // triangular inverse: thread c solves L x = e_c by forward substitution
-    if (tid < jb) {
-        const int c = tid;
-        li[c][c] = 1.0 / a[c][c];
-        for (int i = c + 1; i < jb; ++i) {
-            double s = 0.0;
-            for (int k = c; k < i; ++k) s = fma(a[i][k], li[k][c], s);
-            li[i][c] = -s / a[i][i];
+    // ---- L^-1 into `a`.  8 x 8 diagonal blocks: thread (block, column) substitutes in registers
+    for (int idx = tid; idx < NB * NB; idx += 256) a[idx >> 6][idx & 63] = 0.0;
+    __syncthreads();
+    if (tid < NB) {
+        const int b8 = (tid >> 3) * 8, c = tid & 7;
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < i) sacc = fma(l[b8 + i][b8 + k], (k >= c) ? x[k] : 0.0, sacc);
+            x[i] = (i < c) ? 0.0 : ((i == c) ? rinv[b8 + i] : -sacc * rinv[b8 + i]);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[b8 + i][b8 + c] = x[i];
     }
     __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-        const int r = idx >> 6, c = idx & 63;
-        if (r < jb && c <= r) A[(int64_t)r * lda + c] = a[r][c];
-        dinv[idx] = (r < jb && c <= r) ? li[r][c] : 0.0;
+    // ---- doubling: blocks of size s -> 2 s.  Pair p: rows R0 = 2 s p + s .. + s, columns C0 = 2 s p .. + s
+#pragma unroll 1
+    for (int s = 8, sh = 3; s < NB; s <<= 1, ++sh) {
+        const int outs = 32 * s;                         // (NB / 2 s) pairs x s x s
+        for (int idx = tid; idx < outs; idx += 256) {    // tmp = L21 Linv11
+            const int p = idx >> (2 * sh), rr = (idx >> sh) & (s - 1), cc = idx & (s - 1);
+            const int R0 = 2 * s * p + s, C0 = 2 * s * p;
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = cc & ~1; k < s; k += 2) {       // Linv11 is lower triangular: rows k >= cc only
+                s0 = fma(l[R0 + rr][C0 + k], a[C0 + k][C0 + cc], s0);
+                s1 = fma(l[R0 + rr][C0 + k + 1], a[C0 + k + 1][C0 + cc], s1);
+            }
+            tmp[(p << sh) + rr][cc] = s0 + s1;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < outs; idx += 256) {    // Linv21 = -Linv22 tmp
+            const int p = idx >> (2 * sh), rr = (idx >> sh) & (s - 1), cc = idx & (s - 1);
+            const int R0 = 2 * s * p + s, C0 = 2 * s * p;
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = 0; k <= (rr | 1); k += 2) {     // Linv22 is lower triangular: columns k <= rr only
+                s0 = fma(a[R0 + rr][R0 + k], tmp[(p << sh) + k][cc], s0);
+                s1 = fma(a[R0 + rr][R0 + k + 1], tmp[(p << sh) + k + 1][cc], s1);
+            }
+            a[R0 + rr][C0 + cc] = -(s0 + s1);
+        }
+        __syncthreads();
     }
-    if (tid == 0) {
-        double s = 0.0;
-        for (int j = 0; j < jb; ++j) s += log(a[j][j]);
-        if (logdet) *logdet += 2.0 * s;
-        if (bad && info && *info == 0) *info = j0 + bad;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r < jb && c <= r) A[(int64_t)r * lda + c] = l[r][c];
+        dinv[idx] = (r < jb && c <= r) ? a[r][c] : 0.0;
+    }
+    if (tid < 32) {
+        double sacc = 0.0;
+        for (int j = tid; j < jb; j += 32) sacc += log(l[j][j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (tid == 0) {
+            if (logdet) *logdet += 2.0 * sacc;
+            if (bad && info && *info == 0) *info = j0 + bad;
+        }
     }
 }
 

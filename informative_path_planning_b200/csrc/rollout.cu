@@ -66,20 +66,15 @@ struct RolloutArgs {
 // previous kernel still runs and wait here until it has completed and its writes are visible (a no-op otherwise).
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-__global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(RolloutArgs p) {
-    extern __shared__ __align__(16) double sm[];
-    grid_dependency_wait();
+// Level-by-level rewards and conditioning of the small joint Gaussian (m, C) over the rollout's M points, by one CTA of
+// RO_THREADS threads.  C [M][M+1], m [M], H [(M+1)][RO_MAX_BLOCK+1], red [2 * RO_THREADS / 32] live in shared memory and
+// are already filled (C, m) when this is called; zobs may be shared or global.  Ends by publishing rewards, info and the
+// completion word.
+__device__ __forceinline__ void ro_condition(const RolloutArgs& p, const double* zobs, double* C, double* m, double* H,
+                                             double* red, int& s_bad) {
     const int M = p.M, ldc = M + 1;
-    double* C = sm;                              // [M][M+1]
-    double* m = C + (size_t)M * ldc;             // [M]
-    double* H = m + M;                           // [M + 1][RO_MAX_BLOCK + 1]; row M = the block's residual y_B - m_B
-    double* red = H + (size_t)(M + 1) * (RO_MAX_BLOCK + 1);   // [RO_THREADS / 32][2]
-    __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int HL = RO_MAX_BLOCK + 1;
-
-    for (int idx = tid; idx < M * M; idx += RO_THREADS) C[(idx / M) * ldc + idx % M] = p.cov0[(int64_t)(idx / M) * p.ldc + idx % M];
-    for (int i = tid; i < M; i += RO_THREADS) m[i] = p.mean0[i];
     if (tid == 0) s_bad = 0;
     __syncthreads();
 
@@ -154,7 +149,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {                     // u = L^-1 (y_B - m_B), in every thread
-                double v = (a < kb) ? p.zobs[b0 + a] - m[b0 + a] : 0.0;
+                double v = (a < kb) ? zobs[b0 + a] - m[b0 + a] : 0.0;
 #pragma unroll
                 for (int c = 0; c < a; ++c) v = fma(-Lf[a][c], u[c], v);
                 u[a] = v * rd[a];
@@ -194,7 +189,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
                 const int i = idx / kb, a = idx % kb;
                 H[(b0 + i) * HL + a] = C[(b0 + i) * ldc + b0 + a] + (i == a ? dadd : 0.0);
             }
-            if (tid < kb) H[M * HL + tid] = p.zobs[b0 + tid] - m[b0 + tid];
+            if (tid < kb) H[M * HL + tid] = zobs[b0 + tid] - m[b0 + tid];
             __syncthreads();
             for (int a = 0; a < kb; ++a) {
                 const double piv = H[(b0 + a) * HL + a];
@@ -233,6 +228,21 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(Rollou
             *reinterpret_cast<volatile unsigned int*>(p.done) = p.done_seq;
         }
     }
+}
+
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_condition_kernel(RolloutArgs p) {
+    extern __shared__ __align__(16) double sm[];
+    grid_dependency_wait();
+    const int M = p.M, ldc = M + 1;
+    double* C = sm;                              // [M][M+1]
+    double* m = C + (size_t)M * ldc;             // [M]
+    double* H = m + M;                           // [M + 1][RO_MAX_BLOCK + 1]; row M = the block's residual y_B - m_B
+    double* red = H + (size_t)(M + 1) * (RO_MAX_BLOCK + 1);   // [RO_THREADS / 32][2]
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < M * M; idx += RO_THREADS) C[(idx / M) * ldc + idx % M] = p.cov0[(int64_t)(idx / M) * p.ldc + idx % M];
+    for (int i = tid; i < M; i += RO_THREADS) m[i] = p.mean0[i];
+    ro_condition(p, p.zobs, C, m, H, red, s_bad);
 }
 
 // ---- base posterior over the rollout's M <= 128 points.  A 128-row DMMA tile would be > 80 % padding here and only
@@ -532,6 +542,30 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
     }
 }
 
+}  // namespace ipp
+
+#include "rollout_fused.cuh"
+
+namespace ipp {
+
+// IPP_ROLLOUT_FUSED=0 / ipp_rollout_mode(0) select the four-kernel sequence (A/B measurements and cross-checks; it is
+// always used for more than 32 points)
+static int g_rollout_fused = -1;
+static bool rollout_use_fused() {
+    if (g_rollout_fused < 0) { const char* e = getenv("IPP_ROLLOUT_FUSED"); g_rollout_fused = (e && e[0] == '0') ? 0 : 1; }
+    return g_rollout_fused != 0;
+}
+
+template <int D, int NT>
+static int rollout_fused_launch(const RolloutFusedArgs& fa, const RolloutInline* inl, int grid, cudaStream_t stream) {
+    constexpr int bytes = rf_smem_doubles<NT>() * (int)sizeof(double);
+    IPP_OPT_IN_SMEM((rollout_fused_kernel<D, NT>), bytes);
+    static const RolloutInline none = {};
+    rollout_fused_kernel<D, NT><<<grid, RF_THREADS, bytes, stream>>>(fa, inl ? *inl : none);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
 // IPP_ROLLOUT_TW=simt selects the SIMT pass (A/B measurements); the tensor pass is the default
 static bool tw_use_dmma() {
     static const int use = [] { const char* e = getenv("IPP_ROLLOUT_TW"); return (e && e[0] == 's') ? 0 : 1; }();
@@ -560,10 +594,15 @@ static size_t rollout_smem(int M) {
 
 using namespace ipp;
 
+static int rf_ntiles(int M) { return M <= 16 ? 2 : (M <= 24 ? 3 : 4); }     // P = 8 NT padded points of the fused kernel
+
 extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
     if (M <= 0) return 16;
     const int64_t ldc = round_up(M, 2);
-    return 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
+    const int64_t four_kernels = 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
+    const int64_t Mf = M < 32 ? M : 32;
+    const int64_t fused = (int64_t)ipp::sm_count() * (Mf * (Mf + 1) / 2 + Mf) + 16;    // one partial per CTA, <= 1 CTA per SM
+    return four_kernels > fused ? four_kernels : fused;
 }
 
 namespace ipp {
@@ -580,7 +619,8 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
                    unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream) {
     IPP_CHECK_ARG(kern && pts && zobs && offsets_host && reps_host && reward && info && work, "null pointer");
     IPP_CHECK_ARG(L >= 1 && L <= RO_MAX_LEVELS, "1 <= levels <= IPP_ROLLOUT_MAX_LEVELS");
-    IPP_CHECK_ARG(kind == IPP_REWARD_UCB || kind == IPP_REWARD_EI || kind == IPP_REWARD_MES, "unknown reward kind");
+    IPP_CHECK_ARG(kind == IPP_REWARD_UCB || kind == IPP_REWARD_EI || kind == IPP_REWARD_MES || kind == IPP_REWARD_INFO,
+                  "unknown reward kind");
     IPP_CHECK_ARG(N >= 1 && X && alpha && winv, "needs a belief with data (the reference's no-data early-outs stay with the caller)");
     const int M = offsets_host[L];
     IPP_CHECK_ARG(offsets_host[0] == 0 && M >= 1 && M <= RO_MAX_POINTS, "1 <= points <= IPP_ROLLOUT_MAX_POINTS");
@@ -598,6 +638,32 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
     if (kind == IPP_REWARD_MES) IPP_CHECK_ARG(maxes_dev && S >= 1, "MES needs the sampled maxima");
     else { IPP_CHECK_ARG(params_host && n_params >= 1, "need params[0]"); p.p0 = params_host[0]; }
 
+    p.M = M; p.L = L; p.kind = kind; p.maxes = maxes_dev; p.S = (int)S;
+    p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;
+    p.done = done; p.done_seq = done_seq;
+    p.mean0 = nullptr; p.cov0 = nullptr; p.ldc = 0; p.zobs = zobs;
+    if (rollout_use_fused() && M <= 32 && (kern->dim == 2 || kern->dim == 3)) {
+        static unsigned int seq = 0;                      // a fresh ticket slot per launch (a slot is zero again when its launch ends)
+        RolloutFusedArgs fa;
+        fa.kern = to_dev(*kern);
+        fa.X = X; fa.alpha = alpha; fa.W = winv; fa.ldw = ldw; fa.N = (int)N;
+        fa.pts = pts; fa.zobs = zobs; fa.use_inline = inline_pts ? 1 : 0;
+        fa.part = work;
+        fa.slot = (int)(__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % RF_SLOTS);
+        fa.T = (int)((N + RF_B - 1) / RF_B);
+        fa.tiles = fa.T * (fa.T + 1) / 2;
+        fa.r = p;
+        // small beliefs: a CTA per tpc tiles (IPP_ROLLOUT_TPC, default 1: shortest tile phase); large ones: one CTA per SM
+        static const int tpc = [] { const char* e = getenv("IPP_ROLLOUT_TPC"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();
+        int grid = (fa.tiles + tpc - 1) / tpc;
+        if (grid > sm_count()) grid = sm_count();
+        const int nt = rf_ntiles(M);
+        const bool d2 = kern->dim == 2;
+        if (nt == 2) return d2 ? rollout_fused_launch<2, 2>(fa, inline_pts, grid, stream) : rollout_fused_launch<3, 2>(fa, inline_pts, grid, stream);
+        if (nt == 3) return d2 ? rollout_fused_launch<2, 3>(fa, inline_pts, grid, stream) : rollout_fused_launch<3, 3>(fa, inline_pts, grid, stream);
+        return d2 ? rollout_fused_launch<2, 4>(fa, inline_pts, grid, stream) : rollout_fused_launch<3, 4>(fa, inline_pts, grid, stream);
+    }
+    IPP_CHECK_ARG(kind != IPP_REWARD_INFO, "information-gain rollouts take at most 32 points (one-launch form only)");
     const int64_t ldc = round_up(M, 2);
     double* cov0 = work;
     double* mean0 = cov0 + (int64_t)M * ldc;
@@ -635,10 +701,7 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         }
         IPP_LAUNCH_CHECK();
     }
-    p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc; p.zobs = zobs;
-    p.M = M; p.L = L; p.kind = kind; p.maxes = maxes_dev; p.S = (int)S;
-    p.noise_pred = noise_pred; p.diag_add = diag_add; p.reward = reward; p.info = info;
-    p.done = done; p.done_seq = done_seq;
+    p.mean0 = mean0; p.cov0 = cov0; p.ldc = ldc;
     IPP_OPT_IN_SMEM(rollout_condition_kernel, (int)rollout_smem(RO_MAX_POINTS));
     {
         cudaLaunchConfig_t cfg = dependent_launch(1, RO_THREADS, rollout_smem(M), stream, &pdl);
@@ -649,6 +712,20 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
 }
 
 }  // namespace ipp
+
+extern "C" int ipp_rollout_debug_clocks(int64_t out[32]) {
+    long long v[32];
+    IPP_CUDA(cudaDeviceSynchronize());
+    IPP_CUDA(cudaMemcpyFromSymbol(v, ipp::g_rf_clock, sizeof(v)));
+    for (int i = 0; i < 32; ++i) out[i] = v[i];
+    return IPP_OK;
+}
+
+extern "C" int ipp_rollout_mode(int fused) {
+    const int before = ipp::rollout_use_fused() ? 1 : 0;
+    if (fused == 0 || fused == 1) ipp::g_rollout_fused = fused;
+    return before;
+}
 
 extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,
                                    const double* winv, int64_t ldw, double noise_pred, double diag_add,

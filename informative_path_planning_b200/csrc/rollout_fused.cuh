@@ -1,0 +1,519 @@
+// The whole rollout in ONE launch (included by rollout.cu after RolloutArgs, td_load8 and the reward closed forms).
+//
+// The four-kernel sequence costs ~35 us per rollout at N = 900, nearly all of it launch and hand-off latency
+// (profiles/r1j_launches_mcts_native_900_final.csv), and its W^-1 pass reads the full symmetric matrix.  Here
+//   * only the lower 64 x 64 tiles of W^-1 are read.  With W = Ls + Dg + Ls^T (strictly-lower tiles, diagonal tiles) and
+//     K = the cross-covariance rows of the rollout's points,
+//         K W K^T = A + A^T,     A = sum_{J} ( sum_{I > J} K_I W_IJ + 1/2 K_J W_JJ ) K_J^T = sum_J U_J K_J^T;
+//   * the tiles of the lower triangle, in column-major order, are cut into contiguous runs, one per CTA.  While a CTA
+//     stays in tile column J its 8 warps keep U_J (P x 64, 8 columns per warp) in DMMA accumulators:
+//         U_J[a][j] += sum_{i in I} K[a][i] W[i][j]       A operand = K_I from a fragment-ordered shared-memory image the
+//                                                          CTA computes itself (1/2 folded in on the diagonal tile),
+//                                                          B operand = W^-1 straight from global memory, one tile ahead
+//     and when the column ends the accumulator fragments ARE the A operand of the second contraction (k permutation:
+//     thread t of a quad owns columns 2t, 2t+1 in both), so  A += U_J K_J^T  needs no shared-memory round trip;
+//   * on the diagonal tile the CTA also adds K_J alpha_J to its partial mean;
+//   * every CTA stores its partial (A + A^T lower triangle and the mean: M (M + 1) / 2 + M doubles), the last one to finish
+//     (a ticket counter) sums the partials in CTA order -- a fixed order, so the result does not depend on timing --,
+//     forms C0 = Kqq - (A + A^T) and m0, and runs the level-by-level conditioning in the same launch;
+//   * the rewards are not evaluated inside the sequential conditioning: each level's predictive moments are snapshot when
+//     the level is reached and all levels are scored in parallel (one warp per level) at the end.
+#pragma once
+
+namespace ipp {
+
+constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8, RF_SLOTS = 256;
+__device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
+__device__ long long g_rf_clock[32];                     // SM clocks of the finishing CTA per phase (ipp_rollout_debug_clocks)
+
+struct RolloutFusedArgs {
+    RbfDev kern;
+    const double* X; const double* alpha; const double* W; int64_t ldw; int N;
+    const double* pts; const double* zobs;               // device copies (used when use_inline == 0)
+    int use_inline;
+    double* part;                                        // [gridDim.x][V], V = M (M + 1) / 2 + M
+    int slot, tiles, T;
+    RolloutArgs r;
+};
+
+// exp(x), x <= 0, branch-free (several calls interleave in one thread): Cody-Waite reduction by ln 2 and the degree-13
+// Taylor polynomial on |f| <= ln 2 / 2 (truncation 4e-18 relative), result scaled by 2^n through the exponent bits.
+__device__ __forceinline__ double rf_exp_neg(double x) {
+    const double xc = x < -700.0 ? -700.0 : x;
+    const double tt = fma(xc, 1.4426950408889634074, 6755399441055744.0);     // n = rint(x log2 e) in the low word
+    const int n = __double2loint(tt);
+    const double nf = tt - 6755399441055744.0;
+    double f = fma(nf, -6.93147180369123816490e-01, xc);
+    f = fma(nf, -1.90821492927058770002e-10, f);
+    double p = 1.6059043836821613e-10;                                        // 1/13!
+    p = fma(p, f, 2.08767569878681e-09);
+    p = fma(p, f, 2.505210838544172e-08);
+    p = fma(p, f, 2.755731922398589e-07);
+    p = fma(p, f, 2.7557319223985893e-06);
+    p = fma(p, f, 2.48015873015873e-05);
+    p = fma(p, f, 1.984126984126984e-04);
+    p = fma(p, f, 1.388888888888889e-03);
+    p = fma(p, f, 8.333333333333333e-03);
+    p = fma(p, f, 4.1666666666666664e-02);
+    p = fma(p, f, 1.6666666666666666e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));   // p in [0.70, 1.42]
+    return x < -700.0 ? 0.0 : r;
+}
+
+template <int D>
+__device__ __forceinline__ double rf_rbf(const RbfDev& k, const double* a, const double* b) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double u = (a[d] - b[d]) * k.il[d];
+        r2 = fma(u, u, r2);
+    }
+    return k.variance * rf_exp_neg(-0.5 * r2);
+}
+
+template <int NT>
+constexpr int rf_smem_doubles() {
+    constexpr int P = 8 * NT;
+    //      points  K_I images (2)    K_J image + plain copy   mean  obs
+    return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + 8;
+}
+
+// Conditioning with the rewards deferred: same arithmetic per level as ro_condition (rollout.cu), but a level only
+// snapshots (mean, variance + noise) of its points; all levels are scored afterwards, one warp per level.
+// kind == IPP_REWARD_INFO: the operand is the information-gain belief ((I + vK)^-1, kernel variance v^2, diag_add = 1,
+// see ipp_b200.h); a level's reward is p0 * logdet(I + C[B, B]) of its block under the conditioned covariance
+// (aq_library.py:55-70 in Schur form), so the level snapshots that block (into Cs, same positions) instead of moments.
+__device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double* zobs, double* C, double* m, double* H,
+                                             double* snap_m, double* snap_v, double* Cs, int& s_bad) {
+    const int M = p.M, ldc = M + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int HL = RO_MAX_BLOCK + 1;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    if (tid == 0) g_rf_clock[16] = clock64();
+    for (int l = 0; l < p.L; ++l) {
+        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
+        if (tid == 0 && l < 8) g_rf_clock[17 + l] = clock64();
+        if (p.kind == IPP_REWARD_INFO) {
+            for (int idx = tid; idx < kb * kb; idx += RF_THREADS) {
+                const int a = b0 + idx / kb, b = b0 + idx % kb;
+                Cs[a * ldc + b] = C[a * ldc + b] + (a == b ? 1.0 : 0.0);
+            }
+        } else if (tid < kb) {
+            snap_m[b0 + tid] = m[b0 + tid];
+            snap_v[b0 + tid] = C[(b0 + tid) * ldc + b0 + tid] + p.noise_pred;
+        }
+        if (l == p.L - 1) break;                  // the last level's observation is never looked at again
+        if (p.reps[l] > 0 && kb <= 4) {
+            // every thread factors the (identity-padded) 4 x 4 block redundantly in registers and substitutes its own row
+            const double dadd = p.diag_add / (double)p.reps[l];
+            const int R = M - b0;
+            __syncthreads();
+            double Lf[4][4], rd[4], u[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b)
+                    Lf[a][b] = (a < kb) ? C[(b0 + a) * ldc + b0 + b] + (a == b ? dadd : 0.0) : (a == b ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double d = Lf[j][j];
+                if (!(d > 0.0)) { if (tid == 0) s_bad = l + 1; d = 1.0; }
+                const double r = rsqrt(d);
+                rd[j] = r;
+#pragma unroll
+                for (int i = j + 1; i < 4; ++i) Lf[i][j] *= r;
+#pragma unroll
+                for (int i = j + 1; i < 4; ++i)
+#pragma unroll
+                    for (int c = j + 1; c <= i; ++c) Lf[i][c] = fma(-Lf[i][j], Lf[c][j], Lf[i][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double v = (a < kb) ? zobs[b0 + a] - m[b0 + a] : 0.0;
+#pragma unroll
+                for (int c = 0; c < a; ++c) v = fma(-Lf[a][c], u[c], v);
+                u[a] = v * rd[a];
+            }
+            const int i = b0 + tid;               // this thread's point (M <= 32 < RF_THREADS: at most one)
+            double dm = 0.0;
+            if (i < M) {
+                double h[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    double v = (a < kb) ? C[i * ldc + b0 + a] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < a; ++c) v = fma(-Lf[a][c], h[c], v);
+                    h[a] = v * rd[a];
+                    H[i * HL + a] = h[a];
+                    dm = fma(h[a], u[a], dm);
+                }
+            }
+            __syncthreads();
+            if (i < M) m[i] += dm;
+            // C -= H H^T on the rows / columns that are still ahead: thread -> (ii, jj) without a division (R <= 32)
+            for (int ii = b0 + warp; ii < M; ii += RF_WARPS) {
+                const int jj = b0 + lane;
+                if (lane < R) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) sacc = fma(H[ii * HL + a], H[jj * HL + a], sacc);
+                    C[ii * ldc + jj] -= sacc;
+                }
+            }
+        } else if (p.reps[l] > 0) {
+            const double dadd = p.diag_add / (double)p.reps[l];
+            const int R = M - b0;
+            __syncthreads();
+            for (int idx = tid; idx < R * kb; idx += RF_THREADS) {
+                const int i = idx / kb, a = idx % kb;
+                H[(b0 + i) * HL + a] = C[(b0 + i) * ldc + b0 + a] + (i == a ? dadd : 0.0);
+            }
+            if (tid < kb) H[M * HL + tid] = zobs[b0 + tid] - m[b0 + tid];
+            __syncthreads();
+            for (int a = 0; a < kb; ++a) {
+                const double piv = H[(b0 + a) * HL + a];
+                __syncthreads();
+                if (!(piv > 0.0) && tid == 0) s_bad = l + 1;
+                const double d = piv > 0.0 ? rsqrt(piv) : 1.0;
+                for (int i = b0 + tid; i <= M; i += RF_THREADS)
+                    H[i * HL + a] = (i < b0 + a) ? 0.0 : H[i * HL + a] * d;
+                __syncthreads();
+                const int rest = kb - a - 1;
+                for (int idx = tid; idx < (R + 1) * rest; idx += RF_THREADS) {
+                    const int i = b0 + idx / rest, c = a + 1 + idx % rest;
+                    H[i * HL + c] = fma(-H[i * HL + a], H[(b0 + c) * HL + a], H[i * HL + c]);
+                }
+                __syncthreads();
+            }
+            for (int i = b0 + tid; i < M; i += RF_THREADS) {
+                double dm = 0.0;
+                for (int a = 0; a < kb; ++a) dm = fma(H[i * HL + a], H[M * HL + a], dm);
+                m[i] += dm;
+            }
+            for (int ii = b0 + warp; ii < M; ii += RF_WARPS) {
+                const int jj = b0 + lane;
+                if (lane < R) {
+                    double s = 0.0;
+                    for (int a = 0; a < kb; ++a) s = fma(H[ii * HL + a], H[jj * HL + a], s);
+                    C[ii * ldc + jj] -= s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) g_rf_clock[25] = clock64();
+    // ---- all levels scored in parallel: warp w takes levels w, w + 8, ...
+    for (int l = warp; l < p.L; l += RF_WARPS) {
+        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
+        double s0 = 0.0, s1 = 0.0;
+        if (p.kind == IPP_REWARD_INFO) {                  // in-place Cholesky of the kb x kb block, lane = row
+            double* a = Cs + b0 * ldc + b0;
+            int bad = 0;
+            for (int j = 0; j < kb; ++j) {
+                if (lane == 0) {
+                    double d = a[j * ldc + j];
+                    if (!(d > 0.0)) { bad = 1; d = 1.0; }
+                    a[j * ldc + j] = sqrt(d);
+                }
+                __syncwarp();
+                if (lane > j && lane < kb) a[lane * ldc + j] /= a[j * ldc + j];
+                __syncwarp();
+                if (lane > j && lane < kb)
+                    for (int c = j + 1; c <= lane; ++c) a[lane * ldc + c] = fma(-a[lane * ldc + j], a[c * ldc + j], a[lane * ldc + c]);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                double sacc = 0.0;
+                for (int j = 0; j < kb; ++j) sacc += log(a[j * ldc + j]);
+                p.reward[l] = p.p0 * 2.0 * sacc;
+                if (bad) s_bad = l + 1;
+            }
+            continue;
+        }
+        if (p.kind == IPP_REWARD_MES) {
+            for (int idx = lane; idx < kb * p.S; idx += 32) {
+                const int qi = b0 + idx / p.S;
+                s0 += ro_mes_utility(p.maxes[idx % p.S], snap_m[qi], snap_v[qi]);
+            }
+        } else {
+            for (int qi = b0 + lane; qi < b0 + kb; qi += 32) {
+                s0 += (p.kind == IPP_REWARD_EI) ? (snap_m[qi] - p.p0) : snap_m[qi];
+                s1 += fabs(snap_v[qi]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane == 0) {
+            double r;
+            if (p.kind == IPP_REWARD_UCB) {
+                r = s0 + p.p0 * s1;
+            } else if (p.kind == IPP_REWARD_EI) {
+                const double z = s0 / s1;
+                const double big_phi = 0.5 * (1.0 + erf(z / 1.41421356237309504880));
+                const double small_phi = 1.0 / 2.50662827463100050242 * exp(-(z * z) / 2.0);
+                r = s0 * big_phi + s1 * small_phi;
+            } else {
+                r = 2.0 * s0 / (double)p.S;
+            }
+            p.reward[l] = r;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        g_rf_clock[26] = clock64();
+        *p.info = s_bad;
+        if (p.done) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(p.done) = p.done_seq;
+        }
+    }
+}
+
+template <int D, int NT>
+__global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __grid_constant__ RolloutFusedArgs q,
+                                                                     const __grid_constant__ RolloutInline pp) {
+    constexpr int P = 8 * NT;
+    extern __shared__ __align__(16) double sm[];
+    double* s_pts = sm;                                  // [P][3]
+    double* s_ki = s_pts + P * 3;                        // [2][P * 64] fragment-ordered K[a][i] (A operand), i in tile row I
+    double* s_kj = s_ki + 2 * P * RF_B;                  // [P * 64]    fragment-ordered K[b][j] (B operand of the fold), column J
+    double* s_kp = s_kj + P * RF_B;                      // [P][64]     the same, plain (mean on the diagonal tile)
+    double* s_m0 = s_kp + P * RF_B;                      // [P]
+    double* s_z = s_m0 + P;                              // [P]         observations
+    __shared__ int s_last, s_bad;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int M = q.r.M, N = q.N, T = q.T;
+    const long long clk0 = clock64();
+
+    for (int i = tid; i < M * D; i += RF_THREADS) s_pts[i] = q.use_inline ? pp.v[i] : q.pts[i];
+    if (tid < P) s_m0[tid] = 0.0;
+    __syncthreads();
+
+    const int G = gridDim.x;
+    const int k0 = (int)(((int64_t)blockIdx.x * q.tiles) / G), k1 = (int)(((int64_t)(blockIdx.x + 1) * q.tiles) / G);
+    // column-major walk over the lower triangle: column J holds tiles (I = J .. T - 1, J)
+    int J = 0, I = 0;
+    {
+        int rest = k0;
+        while (rest >= T - J) { rest -= T - J; ++J; }
+        I = J + rest;
+    }
+    // B operand of the first contraction, one tile: thread (g, t) of warp w supplies W[I 64 + 32 c + 8 t + s][J 64 + 8 w + g]
+    auto load_w = [&](double (&wv)[2][8], int I_, int J_) {
+        const int col = J_ * RF_B + warp * 8 + g;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int row = I_ * RF_B + 32 * c + 8 * t + s;
+                wv[c][s] = (row < N && col < N) ? __ldg(q.W + (int64_t)row * q.ldw + col) : 0.0;
+            }
+    };
+    // K[a][x_n] for the 64 observations n of block blk, all P rows: thread -> one observation, rows tid / 64 + 4 r
+    auto gen_k = [&](int blk, double scale, double* frag_a, double* frag_b, double* plain) {
+        const int jj = tid & (RF_B - 1);
+        const int n = blk * RF_B + jj;
+        double x[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = n < N ? q.X[(int64_t)n * D + d] : 0.0;
+        const int a0 = tid / RF_B;
+        double v[2 * NT];
+#pragma unroll
+        for (int r = 0; r < 2 * NT; ++r) {
+            const int a = a0 + 4 * r;
+            v[r] = (a < M && n < N) ? rf_rbf<D>(q.kern, s_pts + a * D, x) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 2 * NT; ++r) {
+            const int a = a0 + 4 * r;
+            if (frag_a)     // element (a, ii = 32 c + 8 tt + 2 qq + e) -> ((((mt 2 + c) 4 + qq) 32 + 4 g' + tt) 2 + e
+                frag_a[((((a >> 3) * 2 + (jj >> 5)) * 4 + ((jj >> 1) & 3)) * 32 + 4 * (a & 7) + ((jj >> 3) & 3)) * 2 + (jj & 1)] = scale * v[r];
+            if (frag_b) {   // element (b, jj = 8 w + 2 tt + e) -> (((nt 8 + w) 32 + 4 g' + tt) 2 + e
+                frag_b[(((a >> 3) * 8 + (jj >> 3)) * 32 + 4 * (a & 7) + ((jj >> 1) & 3)) * 2 + (jj & 1)] = v[r];
+                plain[a * RF_B + jj] = v[r];
+            }
+        }
+    };
+    double U[NT][2], Z[NT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        U[mt][0] = U[mt][1] = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) Z[mt][nt][0] = Z[mt][nt][1] = 0.0;
+    }
+    auto fold = [&]() {                                   // A += U_J K_J^T straight from the accumulator fragments
+        const double2* kb = reinterpret_cast<const double2*>(s_kj);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double2 b = kb[(nt * 8 + warp) * 32 + lane];
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) {
+                dmma884(Z[mt][nt][0], Z[mt][nt][1], U[mt][0], b.x);
+                dmma884(Z[mt][nt][0], Z[mt][nt][1], U[mt][1], b.y);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) U[mt][0] = U[mt][1] = 0.0;
+    };
+
+    int curJ = -1, buf = 0;
+    double w_cur[2][8], w_nxt[2][8];
+    long long tk[6] = {0, 0, 0, 0, 0, 0};
+    tk[0] = clock64();
+    if (k0 < k1) load_w(w_nxt, I, J);
+    for (int k = k0; k < k1; ++k) {
+        if (J != curJ) {
+            if (curJ >= 0) {
+                fold();
+                __syncthreads();                          // everybody is done with the old column's image
+            }
+            curJ = J;
+            gen_k(J, 1.0, nullptr, s_kj, s_kp);
+        }
+        if (k == k0) tk[1] = clock64();
+        gen_k(I, I == J ? 0.5 : 1.0, s_ki + buf * P * RF_B, nullptr, nullptr);
+        if (k == k0) tk[2] = clock64();
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int s = 0; s < 8; ++s) w_cur[c][s] = w_nxt[c][s];
+        int In = I + 1, Jn = J;
+        if (In == T) { ++Jn; In = Jn; }
+        if (k + 1 < k1) load_w(w_nxt, In, Jn);
+        __syncthreads();
+        if (k == k0) tk[3] = clock64();
+        if (I == J) {                                     // partial mean: K_J alpha_J, 8 lanes per point
+            for (int idx = tid; idx < P * 8; idx += RF_THREADS) {
+                const int a = idx >> 3, seg = idx & 7;
+                double sacc = 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int n = J * RF_B + seg * 8 + u;
+                    sacc = fma(s_kp[a * RF_B + seg * 8 + u], n < N ? q.alpha[n] : 0.0, sacc);
+                }
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+                if (seg == 0) s_m0[a] += sacc;
+            }
+        }
+        const double2* ka = reinterpret_cast<const double2*>(s_ki + buf * P * RF_B);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            double a[NT][8];
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const double2 v = ka[((mt * 2 + c) * 4 + qq) * 32 + lane];
+                    a[mt][2 * qq] = v.x;
+                    a[mt][2 * qq + 1] = v.y;
+                }
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) dmma884(U[mt][0], U[mt][1], a[mt][s], w_cur[c][s]);
+        }
+        buf ^= 1;
+        I = In; J = Jn;
+        if (k == k0) tk[4] = clock64();
+    }
+    fold();
+    __syncthreads();
+    tk[5] = clock64();
+
+    // ---- A summed over the 8 warps (fixed order), symmetrised, and handed over together with the partial mean
+    double* s_z8 = s_ki;                                  // [8][P * P], over the dead images (4 P 64 >= 8 P P for P <= 32)
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            s_z8[warp * P * P + (mt * 8 + g) * P + nt * 8 + 2 * t] = Z[mt][nt][0];
+            s_z8[warp * P * P + (mt * 8 + g) * P + nt * 8 + 2 * t + 1] = Z[mt][nt][1];
+        }
+    __syncthreads();
+    const int V = M * (M + 1) / 2 + M;
+    double* mine = q.part + (size_t)blockIdx.x * V;
+    for (int a = warp; a < M; a += RF_WARPS)              // pairs b <= a: lane = b (M <= 32)
+        if (lane <= a) {
+            double s_ab = 0.0, s_ba = 0.0;
+#pragma unroll
+            for (int w = 0; w < RF_WARPS; ++w) {
+                s_ab += s_z8[w * P * P + a * P + lane];
+                s_ba += s_z8[w * P * P + lane * P + a];
+            }
+            mine[a * (a + 1) / 2 + lane] = s_ab + s_ba;
+        }
+    if (tid < M) mine[M * (M + 1) / 2 + tid] = s_m0[tid];
+    const long long clk1 = clock64();
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int old = atomicAdd(&g_rf_ticket[q.slot], 1u);
+        s_last = (old == (unsigned int)(G - 1));
+        if (s_last) g_rf_ticket[q.slot] = 0u;             // everybody has arrived: the slot is free again
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long clk2 = clock64();
+
+    // ---- the last CTA: partials summed in CTA order (16 loads in flight per thread), C0 and m0, conditioning
+    const int ldc = M + 1;
+    double* C = s_ki;
+    double* m = C + (size_t)M * ldc;
+    double* H = m + M;
+    double* snap_m = H + (size_t)(M + 1) * (RO_MAX_BLOCK + 1);
+    double* snap_v = snap_m + M;
+    double* Cs = snap_v + M;                              // [M][M+1] (information gain: the levels' blocks)
+    __syncthreads();                                      // s_z8 (same memory as C) has been consumed by everybody
+    for (int v = tid; v < V; v += RF_THREADS) {
+        const double* src = q.part + v;
+        double acc[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[u] = 0.0;
+        int c = 0;
+        for (; c + 16 <= G; c += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc[u] += __ldcg(src + (size_t)(c + u) * V);
+        }
+        for (; c < G; ++c) acc[0] += __ldcg(src + (size_t)c * V);
+        double tot = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tot += acc[u];
+        if (v < M * (M + 1) / 2) {
+            int a = (int)((sqrt(8.0 * v + 1.0) - 1.0) * 0.5);
+            while (a * (a + 1) / 2 > v) --a;
+            while ((a + 1) * (a + 2) / 2 <= v) ++a;
+            const int b = v - a * (a + 1) / 2;
+            const double val = rf_rbf<D>(q.kern, s_pts + a * D, s_pts + b * D) - tot;
+            C[a * ldc + b] = val;
+            C[b * ldc + a] = val;
+        } else {
+            m[v - M * (M + 1) / 2] = tot;
+        }
+    }
+    for (int i = tid; i < M; i += RF_THREADS) s_z[i] = q.use_inline ? pp.v[M * D + i] : q.zobs[i];
+    const long long clk3 = clock64();
+    rf_condition(q.r, s_z, C, m, H, snap_m, snap_v, Cs, s_bad);
+    if (tid == 0) {
+        g_rf_clock[0] = clk1 - clk0; g_rf_clock[1] = clk2 - clk1; g_rf_clock[2] = clk3 - clk2; g_rf_clock[3] = clock64() - clk3;
+        g_rf_clock[4] = tk[0] - clk0;     // points + setup
+        g_rf_clock[5] = tk[1] - tk[0];    // first W loads issued + column image
+        g_rf_clock[6] = tk[2] - tk[1];    // row image
+        g_rf_clock[7] = tk[3] - tk[2];    // barrier (W loads of the next tile issued)
+        g_rf_clock[8] = tk[4] - tk[3];    // mean + first contraction
+        g_rf_clock[9] = tk[5] - tk[4];    // remaining tiles + fold
+        g_rf_clock[10] = clk1 - tk[5];    // 8-warp sum + partial store
+    }
+}
+
+}  // namespace ipp

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(1024) rff_points_kernel(const double* __restri
 }
 
 double g_walk_us = 0.0, g_device_us = 0.0;      // host-side split of the last search (ipp_tree_last_timing)
+double g_launch_us = 0.0;                       // of g_device_us: time inside the launch calls themselves
 inline double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -264,6 +265,12 @@ extern "C" int ipp_abi_struct_sizes(int32_t out[4]) {
     out[1] = (int32_t)sizeof(ipp_obstacle_box);
     out[2] = (int32_t)sizeof(ipp_mt_state);
     out[3] = (int32_t)sizeof(ipp_tree_params);
+    return IPP_OK;
+}
+
+extern "C" int ipp_tree_last_launch_us(double* launch_us) {
+    IPP_CHECK_ARG(launch_us, "null pointer");
+    *launch_us = g_launch_us;
     return IPP_OK;
 }
 
@@ -322,8 +329,8 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     IPP_CHECK_ARG(host_reward || (X && alpha && winv && stage_host && stage_dev && work), "null pointer");
     IPP_CHECK_ARG(n_root && root_goal && root_visits && root_reward && reward_evals && status, "null output pointer");
     IPP_CHECK_ARG((host_reward || N >= 1) && (kern->dim == 2 || kern->dim == 3), "needs a belief with data, 2 or 3 input dimensions");
-    IPP_CHECK_ARG(prm->kind == IPP_REWARD_UCB || prm->kind == IPP_REWARD_EI || prm->kind == IPP_REWARD_MES || host_reward,
-                  "unknown reward kind");
+    IPP_CHECK_ARG(prm->kind == IPP_REWARD_UCB || prm->kind == IPP_REWARD_EI || prm->kind == IPP_REWARD_MES ||
+                  prm->kind == IPP_REWARD_INFO || host_reward, "unknown reward kind");
     IPP_CHECK_ARG(prm->kind != IPP_REWARD_NAIVE || (prm->naive_locs && prm->n_naive >= 1),
                   "the naive reward needs the sampled maximisers");
     IPP_CHECK_ARG(!value_reward || (prm->rff_W && prm->rff_b && prm->rff_theta && prm->naive_maxes && prm->rff_vals_dev &&
@@ -453,7 +460,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         }
     };
 
-    double walk_us = 0.0, device_us = 0.0;
+    double walk_us = 0.0, device_us = 0.0, launch_us = 0.0;
     for (int it = 0; it < P.budget; ++it) {
         const double t_walk = now_us();
         // ---- leaf_helper: walk down, recording the (points, observation, appends) of every action step
@@ -644,6 +651,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             int M = 0;
             for (const Level& lv : levels) M += lv.k;
             if (L > IPP_ROLLOUT_MAX_LEVELS || M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }
+            if (P.kind == IPP_REWARD_INFO && M > 32) { *status = 1; return IPP_OK; }     // one-launch form only (ipp_b200.h)
             int32_t offsets[IPP_ROLLOUT_MAX_LEVELS + 1], reps[IPP_ROLLOUT_MAX_LEVELS];
             const bool fast = zero_copy && M <= ipp::RO_INLINE_POINTS;
             double* in = fast ? inl.v : h_in;
@@ -665,11 +673,13 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 // points by value in the kernel parameters, rewards + info written straight into the pinned buffer, completion
                 // word polled by this thread: no copies and no driver synchronisation on the rollout's critical path
                 ++seq;
+                const double t_launch = now_us();
                 const int rc = ipp::rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
                                                    maxes_dev, S, d_in, d_in + (size_t)M * D, &inl, offsets, reps, L, m_out,
                                                    reinterpret_cast<int32_t*>(m_out + L), m_flag, seq, work, stream);
                 if (rc != IPP_OK) return rc;
                 const double t_spin = now_us();
+                launch_us += t_spin - t_launch;
                 for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int*>(h_flag) != seq; ++spins) {
                     if (complete_some()) continue;                                  // useful work while the device runs
                     if ((spins & 0xffff) == 0xffff && now_us() - t_spin > 5e6) {          // 5 s: something is wrong on the device
@@ -713,6 +723,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     *reward_evals = evals;
     g_walk_us = walk_us;
     g_device_us = device_us;
+    g_launch_us = launch_us;
     *py_rng = py;
     *np_rng = np;
     return IPP_OK;

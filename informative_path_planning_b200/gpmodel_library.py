@@ -440,7 +440,14 @@ class GPModel(object):
         """Every reward of one tree-search rollout in ONE device call (ipp_rollout_rewards): `levels` is the
         rollout's list of (query points (k_l, D), simulated observations (k_l, 1), times the block is appended
         afterwards).  This belief is the base and is not modified.  Returns (rewards ndarray [L], info int);
-        info != 0 means a block was not positive definite and the caller must replay through add_data."""
+        info != 0 means a block was not positive definite and the caller must replay through add_data.
+        kind REWARD_INFO (info_gain, reference aq_library.py:34-80): the call runs on the information-gain belief
+        ((I + vK)^-1 with the variance-squared kernel, unit noise: _info_gain_state) and scales by 2 pi e."""
+        if kind == L.REWARD_INFO:
+            kern_c, mat, ldm, _ = self._info_gain_state()
+            noise_pred, diag_add, params = 0.0, 1.0, [_TWO_PI_E]
+        else:
+            kern_c, mat, ldm, noise_pred, diag_add = self.kern._c, self._winv_d, self._ld, self._noise_var(), self._diag_add()
         D = self.dimension
         L_ = len(levels)
         offsets = (ctypes.c_int32 * (L_ + 1))()
@@ -460,8 +467,8 @@ class GPModel(object):
         par = (ctypes.c_double * 1)(float(params[0]) if params is not None else 0.0)
         S = 0 if maxes_d is None else int(maxes_d.numel())
         base = buf.data_ptr()
-        L.check(L.lib.ipp_rollout_rewards(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                          L.ptr(self._winv_d), self._ld, self._noise_var(), self._diag_add(), kind,
+        L.check(L.lib.ipp_rollout_rewards(ctypes.byref(kern_c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
+                                          L.ptr(mat), ldm, noise_pred, diag_add, kind,
                                           par, 1, L.ptr(maxes_d), S, ctypes.c_void_p(base),
                                           ctypes.c_void_p(base + 8 * M * D), offsets, reps, L_,
                                           L.ptr(out), ctypes.c_void_p(out.data_ptr() + 8 * L_), L.ptr(work),

@@ -171,6 +171,13 @@ class Tree(object):
         if (_BELIEF_FREE_REWARDS.get(self.aquisition_function) == self.f_rew and isinstance(belief, GPModel)
                 and belief.model is None):
             return 'host', None, None        # naive / naive_value never read the belief: no simulated updates needed
+        info = _INFO_REWARDS.get(self.aquisition_function)
+        if info is not None and info == self.f_rew and isinstance(belief, GPModel):
+            if belief.model is not None or belief.xvals is None or belief._winv_d is None:
+                return None
+            if info == 'info_gain':
+                return aqlib.L.REWARD_INFO, None, None
+            return 'hotspot', [np.sqrt(aqlib.ucb_beta(self.t))], None        # info_gain + mean_UCB, two device passes
         fast = _FAST_REWARDS.get(self.aquisition_function)
         if fast is None or fast != self.f_rew or not isinstance(belief, GPModel):
             return None
@@ -207,9 +214,16 @@ class Tree(object):
         n_pts = sum(x.shape[0] for x, _, _ in levels)
         ok = (len(levels) <= aqlib.L.IPP_ROLLOUT_MAX_LEVELS and n_pts <= aqlib.L.IPP_ROLLOUT_MAX_POINTS
               and max(x.shape[0] for x, _, _ in levels) <= aqlib.L.IPP_APPEND_MAX_K)
+        if kind in (aqlib.L.REWARD_INFO, 'hotspot'):
+            ok = ok and n_pts <= aqlib.L.IPP_ROLLOUT_INFO_MAX_POINTS
         if ok:
             queries = [(aqlib._queries(self.t, x, belief)[1], z, r) for x, z, r in levels]
-            vals, info = belief.rollout_rewards(kind, queries, params=params, maxes_d=maxes_d)
+            if kind == 'hotspot':                 # hotspot_info_UCB = info_gain + mean_UCB (aq_library.hotspot_info_UCB)
+                ig, info = belief.rollout_rewards(aqlib.L.REWARD_INFO, queries)
+                ucb, info2 = belief.rollout_rewards(aqlib.L.REWARD_UCB, queries, params=params)
+                vals, info = ig + ucb, (info or info2)
+            else:
+                vals, info = belief.rollout_rewards(kind, queries, params=params, maxes_d=maxes_d)
             ok = info == 0
             if ok:
                 self.reward_evals += len(levels)
@@ -410,6 +424,8 @@ class BeliefTree(Tree):
 
 # acquisition callables of this package that have a sync-free device form, by reward name
 _FAST_REWARDS = {aqlib.mean_UCB: 'mean', aqlib.mves: 'mes', aqlib.exp_improvement: 'exp_improve'}
+# information-gain rewards (reference aq_library.py:34-80, :117-135): fused rollouts on the information-gain belief
+_INFO_REWARDS = {aqlib.info_gain: 'info_gain', aqlib.hotspot_info_UCB: 'hotspot_info'}
 # rewards that do not depend on the belief at all (reference aq_library.py:339-413)
 _BELIEF_FREE_REWARDS = {aqlib.naive: 'naive', aqlib.naive_value: 'naive_value'}
 
@@ -516,6 +532,12 @@ class cMCTS(object):
         if fused is None or scale is None or belief.dimension not in (2, 3):
             return False
         kind, params, maxes_d = fused
+        if kind == 'hotspot':
+            return False                              # two beliefs per rollout: the Python tree with fused rollouts
+        operand = (belief.kern._c, belief._winv_d, belief._ld, belief._noise_var(), belief._diag_add())
+        if kind == L.REWARD_INFO:                     # the search runs on the information-gain belief (ipp_b200.h)
+            kern2, binv, ldb, _ = belief._info_gain_state()
+            operand, params = (kern2, binv, ldb, 0.0, 1.0), [2 * np.pi * np.e]
         naive_locs, rff = None, None
         if kind == 'host':
             # naive: pure geometry against the sampled maximisers, computed inside the native search (no device work at
@@ -594,8 +616,8 @@ class cMCTS(object):
         vp = ctypes.c_void_p
         S = 0 if maxes_d is None else int(maxes_d.numel())
         L.check(L.lib.ipp_tree_search_dpw(
-            ctypes.byref(prm), pose.ctypes.data_as(vp), ctypes.byref(belief.kern._c), L.ptr(belief._X_d), N,
-            L.ptr(belief._alpha_d), L.ptr(belief._winv_d), belief._ld, belief._noise_var(), belief._diag_add(),
+            ctypes.byref(prm), pose.ctypes.data_as(vp), ctypes.byref(operand[0]), L.ptr(belief._X_d), N,
+            L.ptr(belief._alpha_d), L.ptr(operand[1]), operand[2], operand[3], operand[4],
             L.ptr(maxes_d), S, ctypes.byref(py_state), ctypes.byref(np_state), L.ptr(stage[0]), L.ptr(stage[1]),
             L.ptr(work), n_root.ctypes.data_as(vp), root_goal.ctypes.data_as(vp), root_visits.ctypes.data_as(vp),
             root_reward.ctypes.data_as(vp), evals.ctypes.data_as(vp), status.ctypes.data_as(vp), L.stream_ptr()))

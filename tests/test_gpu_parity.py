@@ -631,7 +631,91 @@ def test_rollout_rewards_match_sequential_appends(pkg, f_rew, noise):
     np.testing.assert_allclose(got, np.array(scratch, dtype=float), **tol)
 
 
-@pytest.mark.parametrize('f_rew,tree_type', [('mean', 'dpw'), ('mes', 'dpw'), ('exp_improve', 'dpw'), ('mean', 'belief'), ('mes', 'belief')])
+@pytest.mark.parametrize('n_obs,sizes', [(40, [4, 4, 4, 4, 4]), (300, [3, 1, 5, 4]), (1000, [4, 4, 4]), (64, [8, 8, 8, 8])])
+def test_info_gain_rollouts_match_sequential_appends(pkg, n_obs, sizes):
+    """info_gain (reference aq_library.py:34-80) for every level of a rollout in one device pass on the information-gain
+    belief -- (I + vK)^-1, variance-squared kernel, unit noise; a block appended twice = unit noise / 2 -- against the
+    reference's sequence through the ORACLE (two (N+k)^3 slogdets per level, add_data once or twice in between) and
+    through this package's per-call info_gain on a fork of the device belief."""
+    aqo, gpo, _ = _oracle()
+    aq, L = pkg.aq_library, pkg._lib
+    rng = np.random.default_rng(77 + n_obs)
+    X, z = world(rng, n_obs, 0.5)
+    d = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    d.add_data(X, z); o.add_data(X, z)
+    levels = []
+    start = rng.uniform(2, 8, 2)
+    for k in sizes:
+        pts = start + np.cumsum(rng.normal(0, 0.4, (k, 2)), axis=0)
+        start = pts[-1]
+        levels.append((pts, rng.normal(0, 10.0, (k, 1)), int(rng.integers(1, 3))))
+    got, info = d.rollout_rewards(L.REWARD_INFO, levels)
+    assert info == 0 and d.n_obs == n_obs
+    fork = copy.copy(d)
+    for l, (pts, zo, r) in enumerate(levels):
+        want_o = aqo.info_gain(3, pts, o)
+        want_d = aq.info_gain(time=3, xvals=pts, robot_model=fork)
+        # the reference's own difference of two log-determinants of (N+k)-dimensional matrices carries ~1e-10 * |logdet|
+        np.testing.assert_allclose(got[l], want_o, rtol=1e-6, atol=1e-5)
+        # I + vK has entries up to 1e4 against a unit diagonal (condition ~1e4 N): two FP64 routes to the same Schur block
+        # -- conditioning here, a refresh of the extended belief there -- agree to ~cond * eps
+        np.testing.assert_allclose(got[l], want_d, rtol=5e-6, atol=1e-6)
+        for _ in range(r):
+            fork.add_data(pts, zo); o.add_data(pts, zo)
+
+
+@pytest.mark.parametrize('n_obs', [1, 63, 64, 65, 150, 900, 1500])
+@pytest.mark.parametrize('sizes', [[4, 4, 4, 4, 4], [3], [8, 8, 8, 6], [12, 12, 12, 12, 2], [1, 1, 1]])
+def test_fused_rollout_kernel_equals_the_four_kernel_sequence(pkg, n_obs, sizes):
+    """The one-launch rollout (lower tiles of W^-1 only, per-CTA partials summed in CTA order by the last CTA, conditioning
+    in the same launch) against the four-kernel sequence it replaces, for ragged N (tile edges 64), 20 / 3 / 30 / 50 points
+    (the three padded widths of the kernel), UCB, EI and MES; identical from one call to the next (fixed summation order);
+    and both against a from-scratch oracle belief."""
+    aqo, gpo, _ = _oracle()
+    aq, L = pkg.aq_library, pkg._lib
+    rng = np.random.default_rng(1000 + n_obs + len(sizes))
+    X, z = world(rng, n_obs, 0.5)
+    d = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    d.add_data(X, z)
+    levels = []
+    start = rng.uniform(2, 8, 2)
+    for k in sizes:
+        pts = start + np.cumsum(rng.normal(0, 0.3, (k, 2)), axis=0)
+        start = pts[-1]
+        levels.append((pts, rng.normal(0, 10.0, (k, 1)), int(rng.integers(1, 3))))
+    maxes = np.array([28.0, 33.0, 41.0])
+    cases = [(L.REWARD_UCB, [np.sqrt(aq.ucb_beta(5))], None), (L.REWARD_EI, [float(z.max())], None),
+             (L.REWARD_MES, None, L.to_device(maxes))]
+    before = L.lib.ipp_rollout_mode(1)
+    try:
+        for kind, params, maxes_d in cases:
+            L.lib.ipp_rollout_mode(1)
+            fused, info = d.rollout_rewards(kind, levels, params=params, maxes_d=maxes_d)
+            again, _ = d.rollout_rewards(kind, levels, params=params, maxes_d=maxes_d)
+            L.lib.ipp_rollout_mode(0)
+            four, info4 = d.rollout_rewards(kind, levels, params=params, maxes_d=maxes_d)
+            assert info == 0 and info4 == 0
+            np.testing.assert_array_equal(fused, again)
+            # both are FP64 sums of N^2 terms of magnitude ~1e4 in different orders: ~1e-9 absolute round-off each
+            np.testing.assert_allclose(fused, four, rtol=1e-7, atol=1e-7)
+    finally:
+        L.lib.ipp_rollout_mode(before)
+    # UCB against the oracle refreshed from scratch at every level
+    L.lib.ipp_rollout_mode(1)
+    got, _ = d.rollout_rewards(L.REWARD_UCB, levels, params=[np.sqrt(aq.ucb_beta(5))])
+    L.lib.ipp_rollout_mode(before)
+    Xa, za = X, z
+    for l, (pts, zo, r) in enumerate(levels):
+        o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+        o.add_data(Xa, za)
+        np.testing.assert_allclose(got[l], aqo.mean_UCB(5, pts, o), rtol=1e-7, atol=1e-6)
+        for _ in range(r):
+            Xa, za = np.vstack([Xa, pts]), np.vstack([za, zo])
+
+
+@pytest.mark.parametrize('f_rew,tree_type', [('mean', 'dpw'), ('mes', 'dpw'), ('exp_improve', 'dpw'), ('mean', 'belief'), ('mes', 'belief'),
+                                             ('info_gain', 'dpw'), ('hotspot_info', 'dpw'), ('info_gain', 'belief')])
 def test_mcts_fused_rollouts_same_choices_as_per_level_path(pkg, f_rew, tree_type):
     """One device call per rollout vs one reward + two add_data per level: same random streams, same tree, same
     visit counts and action; average rewards equal to round-off."""
@@ -643,7 +727,8 @@ def test_mcts_fused_rollouts_same_choices_as_per_level_path(pkg, f_rew, tree_typ
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
     m.add_data(X, z)
     pg = Path_Generator(8, 1.5, 0.05, 0.5, RANGES)
-    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement}[f_rew]
+    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement, 'info_gain': aq.info_gain,
+          'hotspot_info': aq.hotspot_info_UCB}[f_rew]
     aq_param = float(np.max(z)) if f_rew == 'exp_improve' else None
     out = {}
     for fuse in (True, False):
@@ -659,7 +744,8 @@ def test_mcts_fused_rollouts_same_choices_as_per_level_path(pkg, f_rew, tree_typ
                      [c.reward / c.nqueries for c in mcts.tree.root.children])
     assert out[True][0] == out[False][0]
     np.testing.assert_array_equal(out[True][1], out[False][1])
-    np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-8)
+    # information gain: the per-level path refreshes (I + vK)^-1 of the extended belief (condition ~1e4 N), see above
+    np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-6 if 'info' in f_rew else 1e-8)
     assert m.n_obs == 120
 
 
@@ -956,7 +1042,8 @@ def test_train_and_load_kernel(pkg, tmp_path):
 @pytest.mark.parametrize('tree_type', ['dpw', 'belief'])
 @pytest.mark.parametrize('f_rew,world_kind,n_obs,budget,depth', [
     ('mean', 'free', 40, 120, 5), ('mean', 'block', 300, 250, 5), ('mes', 'free', 150, 250, 5),
-    ('exp_improve', 'channel', 90, 150, 4), ('mean', 'free', 1200, 60, 3)])
+    ('exp_improve', 'channel', 90, 150, 4), ('mean', 'free', 1200, 60, 3), ('info_gain', 'free', 200, 120, 5),
+    ('info_gain', 'block', 700, 80, 4)])
 def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n_obs, budget, depth, tree_type):
     """ipp_tree_search_dpw (the whole DPW search in native code) against the Python Tree on the same seeds: identical
     visit counts, bit-identical reward sums, the same chosen action -- and the interpreter's two random streams are left
@@ -972,7 +1059,7 @@ def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n
     X, z = world(rng, n_obs, 0.5)
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
     m.add_data(X, z)
-    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement}[f_rew]
+    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement, 'info_gain': aq.info_gain}[f_rew]
     res = {}
     for native in (True, False):
         pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES, w)

@@ -260,7 +260,8 @@ def test_evaluation_metrics_match_reference(rf):
 
 @pytest.mark.parametrize('name', ['myopic_mean_fan', 'myopic_mes_fan', 'nonmyopic_mean_dpw', 'myopic_mean_dubins_blocks',
                                   'myopic_info_gain_fan', 'myopic_ei_dubins', 'myopic_naive_dubins',
-                                  'nonmyopic_naive_dpw_dubins'])
+                                  'nonmyopic_naive_dpw_dubins', 'nonmyopic_info_gain_dpw_dubins',
+                                  'nonmyopic_hotspot_dpw_dubins'])
 def test_oracle_missions_match_reference_runs(name):
     """The oracle stack end to end (RobotOracle.planner over OnlineGPModelOracle, aq_oracle, mcts_oracle and
     EvaluationOracle) against whole seeded missions of the reference's own Robot + Evaluation source
