@@ -303,7 +303,7 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
  *      creation order (goal index, visit count, reward sum); n_root[0] of them.  reward_evals[0]: path rewards scored.
  *      stage_host: PINNED host scratch, stage_dev: device scratch, each >= IPP_TREE_STAGE_DOUBLES doubles;
  *      work: ipp_rollout_workspace(N, IPP_ROLLOUT_MAX_POINTS) doubles on the device. */
-#define IPP_TREE_STAGE_DOUBLES (IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1) + IPP_ROLLOUT_MAX_LEVELS + 16)
+#define IPP_TREE_STAGE_DOUBLES (IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1) + 3 * IPP_ROLLOUT_MAX_LEVELS + 32)
 typedef struct {
     uint32_t key[624];
     int32_t pos;

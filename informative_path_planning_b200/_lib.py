@@ -47,7 +47,7 @@ class IppTreeParams(ctypes.Structure):
                 ('sample_step', ctypes.c_double), ('log_table', ctypes.c_void_p)]
 
 
-IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 32 + 16
+IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 3 * 32 + 32
 
 
 def py_rng_state():

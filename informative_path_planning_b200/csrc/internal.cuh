@@ -133,6 +133,10 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
                    int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
                    double* pts, double* zobs, const RolloutInline* inline_pts, const int32_t* offsets_host,
                    const int32_t* reps_host, int L, double* reward, int32_t* info,
-                   unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream);
+                   unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream,
+                   double* tagged_out, unsigned long long tag, bool* used_tagged);
+// tagged_out != NULL (host-mapped, 16-byte aligned, 2 (L + 1) doubles) and tag != 0: when the one-launch form runs, the
+// results are written there as {value, tag} records -- L rewards, then info -- and *used_tagged is set; `done` is then not
+// signalled.  Tags must never repeat for a given buffer.
 
 }  // namespace ipp

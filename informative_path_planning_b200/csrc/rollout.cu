@@ -16,6 +16,7 @@
 // (the same block appended reps[l] times = one conditioning with the noise divided by reps[l]).  One CTA, everything
 // in shared memory.
 #include <stdlib.h>
+#include <string.h>
 
 #include "internal.cuh"
 #include "dgemm_dmma.cuh"
@@ -560,8 +561,9 @@ template <int D, int NT>
 static int rollout_fused_launch(const RolloutFusedArgs& fa, const RolloutInline* inl, int grid, cudaStream_t stream) {
     constexpr int bytes = rf_smem_doubles<NT>() * (int)sizeof(double);
     IPP_OPT_IN_SMEM((rollout_fused_kernel<D, NT>), bytes);
-    static const RolloutInline none = {};
-    rollout_fused_kernel<D, NT><<<grid, RF_THREADS, bytes, stream>>>(fa, inl ? *inl : none);
+    RolloutInlineSmall small;
+    if (inl) memcpy(small.v, inl->v, sizeof(double) * (size_t)fa.r.M * (D + 1));      // [M][D] points, then [M] observations
+    rollout_fused_kernel<D, NT><<<grid, RF_THREADS, bytes, stream>>>(fa, small);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -616,8 +618,10 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
                    int kind, const double* params_host, int n_params, const double* maxes_dev, int64_t S,
                    double* pts, double* zobs, const RolloutInline* inline_pts, const int32_t* offsets_host,
                    const int32_t* reps_host, int L, double* reward, int32_t* info,
-                   unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream) {
+                   unsigned int* done, unsigned int done_seq, double* work, cudaStream_t stream,
+                   double* tagged_out, unsigned long long tag, bool* used_tagged) {
     IPP_CHECK_ARG(kern && pts && zobs && offsets_host && reps_host && reward && info && work, "null pointer");
+    if (used_tagged) *used_tagged = false;
     IPP_CHECK_ARG(L >= 1 && L <= RO_MAX_LEVELS, "1 <= levels <= IPP_ROLLOUT_MAX_LEVELS");
     IPP_CHECK_ARG(kind == IPP_REWARD_UCB || kind == IPP_REWARD_EI || kind == IPP_REWARD_MES || kind == IPP_REWARD_INFO,
                   "unknown reward kind");
@@ -650,9 +654,18 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         fa.pts = pts; fa.zobs = zobs; fa.use_inline = inline_pts ? 1 : 0;
         fa.part = work;
         fa.slot = (int)(__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % RF_SLOTS);
+        fa.tag = 0;
+        if (tagged_out && tag) {                          // results as self-validating records, no completion word
+            fa.tag = tag;
+            p.reward = tagged_out;
+        }
         fa.T = (int)((N + RF_B - 1) / RF_B);
         fa.tiles = fa.T * (fa.T + 1) / 2;
         fa.r = p;
+        fa.warp_cond = 1;
+        for (int l = 0; l < L; ++l)
+            if (offsets_host[l + 1] - offsets_host[l] > 4) fa.warp_cond = 0;
+        if (used_tagged) *used_tagged = fa.tag != 0;
         // small beliefs: a CTA per tpc tiles (IPP_ROLLOUT_TPC, default 1: shortest tile phase); large ones: one CTA per SM
         static const int tpc = [] { const char* e = getenv("IPP_ROLLOUT_TPC"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();
         int grid = (fa.tiles + tpc - 1) / tpc;
@@ -735,5 +748,5 @@ extern "C" int ipp_rollout_rewards(const ipp_rbf* kern, const double* X, int64_t
                                    double* work, void* stream_) {
     return rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, kind, params_host, n_params, maxes_dev, S,
                           const_cast<double*>(pts), const_cast<double*>(zobs), nullptr, offsets_host, reps_host, L,
-                          reward, info, nullptr, 0u, work, static_cast<cudaStream_t>(stream_));
+                          reward, info, nullptr, 0u, work, static_cast<cudaStream_t>(stream_), nullptr, 0ull, nullptr);
 }

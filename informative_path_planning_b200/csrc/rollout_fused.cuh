@@ -26,6 +26,17 @@ constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8, RF_SLOTS = 256;
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
 __device__ long long g_rf_clock[32];                     // SM clocks of the finishing CTA per phase (ipp_rollout_debug_clocks)
 
+// The rollout's points and observations by value: [M][D] points, then [M] observations (M <= 32 in this kernel: 1 KB of
+// kernel parameters instead of the 3 KB RolloutInline of the four-kernel form).
+struct RolloutInlineSmall { double v[32 * (IPP_MAX_DIM + 1)]; };
+
+// A result the host can validate without a fence: value and tag travel in ONE 16-byte store, so a reader that sees the
+// tag sees the value (the four-kernel form orders plain stores before a completion word with __threadfence_system, a
+// PCIe round trip of ~3.5k SM clocks at the end of every rollout).
+__device__ __forceinline__ void rf_publish(double* rec, int slot, double value, unsigned long long tag) {
+    *reinterpret_cast<double2*>(rec + 2 * slot) = make_double2(value, __longlong_as_double((long long)tag));
+}
+
 struct RolloutFusedArgs {
     RbfDev kern;
     const double* X; const double* alpha; const double* W; int64_t ldw; int N;
@@ -33,6 +44,8 @@ struct RolloutFusedArgs {
     int use_inline;
     double* part;                                        // [gridDim.x][V], V = M (M + 1) / 2 + M
     int slot, tiles, T;
+    int warp_cond;                                       // every level has <= 4 points: single-warp conditioning
+    unsigned long long tag;                              // != 0: r.reward holds 16-byte {value, tag} records, L rewards then info
     RolloutArgs r;
 };
 
@@ -81,13 +94,201 @@ constexpr int rf_smem_doubles() {
     return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + 8;
 }
 
+// All levels scored in parallel from the snapshots: warp w takes levels w, w + 8, ...  Called by every thread after a
+// barrier that made the snapshots visible.
+__device__ __forceinline__ void rf_score(const RolloutArgs& p, const double* snap_m, const double* snap_v, double* Cs,
+                                         int& s_bad, unsigned long long tag) {
+    const int M = p.M, ldc = M + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) g_rf_clock[25] = clock64();
+    for (int l = warp; l < p.L; l += RF_WARPS) {
+        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
+        double s0 = 0.0, s1 = 0.0;
+        if (p.kind == IPP_REWARD_INFO) {                  // in-place Cholesky of the kb x kb block, lane = row
+            double* a = Cs + b0 * ldc + b0;
+            int bad = 0;
+            for (int j = 0; j < kb; ++j) {
+                if (lane == 0) {
+                    double d = a[j * ldc + j];
+                    if (!(d > 0.0)) { bad = 1; d = 1.0; }
+                    a[j * ldc + j] = sqrt(d);
+                }
+                __syncwarp();
+                if (lane > j && lane < kb) a[lane * ldc + j] /= a[j * ldc + j];
+                __syncwarp();
+                if (lane > j && lane < kb)
+                    for (int c = j + 1; c <= lane; ++c) a[lane * ldc + c] = fma(-a[lane * ldc + j], a[c * ldc + j], a[lane * ldc + c]);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                double sacc = 0.0;
+                for (int j = 0; j < kb; ++j) sacc += log(a[j * ldc + j]);
+                if (tag) rf_publish(p.reward, l, p.p0 * 2.0 * sacc, tag);
+                else p.reward[l] = p.p0 * 2.0 * sacc;
+                if (bad) s_bad = l + 1;
+            }
+            continue;
+        }
+        if (p.kind == IPP_REWARD_MES) {
+            for (int idx = lane; idx < kb * p.S; idx += 32) {
+                const int qi = b0 + idx / p.S;
+                s0 += ro_mes_utility(p.maxes[idx % p.S], snap_m[qi], snap_v[qi]);
+            }
+        } else {
+            for (int qi = b0 + lane; qi < b0 + kb; qi += 32) {
+                s0 += (p.kind == IPP_REWARD_EI) ? (snap_m[qi] - p.p0) : snap_m[qi];
+                s1 += fabs(snap_v[qi]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane == 0) {
+            double r;
+            if (p.kind == IPP_REWARD_UCB) {
+                r = s0 + p.p0 * s1;
+            } else if (p.kind == IPP_REWARD_EI) {
+                const double z = s0 / s1;
+                const double big_phi = 0.5 * (1.0 + erf(z / 1.41421356237309504880));
+                const double small_phi = 1.0 / 2.50662827463100050242 * exp(-(z * z) / 2.0);
+                r = s0 * big_phi + s1 * small_phi;
+            } else {
+                r = 2.0 * s0 / (double)p.S;
+            }
+            if (tag) rf_publish(p.reward, l, r, tag);
+            else p.reward[l] = r;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        g_rf_clock[26] = clock64();
+        if (tag) {
+            rf_publish(p.reward, p.L, (double)s_bad, tag);
+        } else {
+            *p.info = s_bad;
+            if (p.done) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(p.done) = p.done_seq;
+            }
+        }
+    }
+}
+
+// The usual rollout -- every level a block of <= 4 points, <= 32 points in all -- conditioned by ONE warp, lane = point,
+// in left-looking form: nothing is written back into the covariance.  At level l a lane assembles the couplings of its
+// point with the level's block under the conditioned covariance from the prior block and the panels H_l' of the earlier
+// levels (c = C0[i][B] - sum_l' H_l'[i] H_l'[B]^T), the 4 x 4 pivot block is gathered from its owner lanes by shuffles,
+// factored redundantly in registers (branch-free, so the substitutions overlap the rsqrt latencies), and the lane's own
+// panel row h = L^-1 c, mean m += h . u and H_l[i] = h follow.  Per level: one __syncwarp instead of three block barriers
+// and an M x M read-modify-write pass (8.2k -> ~3k SM clocks for five levels of four points).
+__device__ __forceinline__ void rf_condition_warp(const RolloutArgs& p, const double* zobs, const double* C0, const double* m0,
+                                                  double* Hs /* [L][4][32] */, double* snap_m, double* snap_v, double* Cs,
+                                                  int& s_bad) {
+    const int M = p.M, ldc = M + 1, lane = threadIdx.x & 31;
+    const bool live = lane < M;
+    const int row = live ? lane : 0;
+    double mi = live ? m0[row] : 0.0;
+    const double zi = live ? zobs[row] : 0.0;
+    int bad = 0;
+    for (int l = 0; l < p.L; ++l) {
+        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
+        if (lane == 0 && l < 8) g_rf_clock[17 + l] = clock64();
+        int col[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) col[a] = (b0 + a) < M ? (b0 + a) : (M - 1);
+        double c[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) c[a] = C0[row * ldc + col[a]];
+        for (int lp = 0; lp < l; ++lp) {
+            const double* hp = Hs + lp * 128;
+            double own[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) own[cc] = hp[cc * 32 + lane];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) c[a] = fma(-own[cc], hp[cc * 32 + col[a]], c[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) c[a] = (live && a < kb) ? c[a] : 0.0;
+        // the pivot block: entry (a, b) = coupling b of the lane that owns point b0 + a
+        const double dadd = p.reps[l] > 0 ? p.diag_add / (double)p.reps[l] : 0.0;
+        double Lf[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) {
+                const double v = __shfl_sync(0xffffffffu, c[b], col[a]);
+                Lf[a][b] = (a < kb) ? v : (a == b ? 1.0 : 0.0);
+            }
+        // snapshot of the level's predictive moments (or of its block, for the information gain)
+        if (p.kind == IPP_REWARD_INFO) {
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b <= a; ++b)
+                        if (a < kb) Cs[(b0 + a) * ldc + b0 + b] = Lf[a][b] + (a == b ? 1.0 : 0.0);
+            }
+        } else if (lane >= b0 && lane < b0 + kb) {
+            const int o = lane - b0;
+            snap_m[lane] = mi;
+            snap_v[lane] = (o == 0 ? c[0] : (o == 1 ? c[1] : (o == 2 ? c[2] : c[3]))) + p.noise_pred;
+        }
+        if (l == p.L - 1) break;                  // the last level's observation is never looked at again
+        double rd[4], u[4], h[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            if (a < kb) Lf[a][a] += dadd;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ok = Lf[j][j] > 0.0;
+            bad = (!ok && bad == 0) ? (l + 1) : bad;
+            const double r = rsqrt(ok ? Lf[j][j] : 1.0);
+            rd[j] = r;
+#pragma unroll
+            for (int i = j + 1; i < 4; ++i) Lf[i][j] *= r;
+#pragma unroll
+            for (int i = j + 1; i < 4; ++i)
+#pragma unroll
+                for (int cc = j + 1; cc <= i; ++cc) Lf[i][cc] = fma(-Lf[i][j], Lf[cc][j], Lf[i][cc]);
+        }
+        const double resid = zi - mi;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double v = __shfl_sync(0xffffffffu, resid, col[a]);
+            v = (a < kb) ? v : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < a; ++cc) v = fma(-Lf[a][cc], u[cc], v);
+            u[a] = v * rd[a];
+        }
+        double dm = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double v = c[a];
+#pragma unroll
+            for (int cc = 0; cc < a; ++cc) v = fma(-Lf[a][cc], h[cc], v);
+            h[a] = p.reps[l] > 0 ? v * rd[a] : 0.0;   // reps == 0: the block is scored but never appended
+            dm = fma(h[a], u[a], dm);
+        }
+        mi += dm;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) Hs[l * 128 + cc * 32 + lane] = h[cc];
+        __syncwarp();
+    }
+    if (lane == 0 && bad) s_bad = bad;
+}
+
 // Conditioning with the rewards deferred: same arithmetic per level as ro_condition (rollout.cu), but a level only
 // snapshots (mean, variance + noise) of its points; all levels are scored afterwards, one warp per level.
 // kind == IPP_REWARD_INFO: the operand is the information-gain belief ((I + vK)^-1, kernel variance v^2, diag_add = 1,
 // see ipp_b200.h); a level's reward is p0 * logdet(I + C[B, B]) of its block under the conditioned covariance
 // (aq_library.py:55-70 in Schur form), so the level snapshots that block (into Cs, same positions) instead of moments.
 __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double* zobs, double* C, double* m, double* H,
-                                             double* snap_m, double* snap_v, double* Cs, int& s_bad) {
+                                             double* snap_m, double* snap_v, double* Cs, int& s_bad,
+                                             unsigned long long tag) {
     const int M = p.M, ldc = M + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int HL = RO_MAX_BLOCK + 1;
@@ -206,80 +407,12 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
         __syncthreads();
     }
     __syncthreads();
-    if (tid == 0) g_rf_clock[25] = clock64();
-    // ---- all levels scored in parallel: warp w takes levels w, w + 8, ...
-    for (int l = warp; l < p.L; l += RF_WARPS) {
-        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
-        double s0 = 0.0, s1 = 0.0;
-        if (p.kind == IPP_REWARD_INFO) {                  // in-place Cholesky of the kb x kb block, lane = row
-            double* a = Cs + b0 * ldc + b0;
-            int bad = 0;
-            for (int j = 0; j < kb; ++j) {
-                if (lane == 0) {
-                    double d = a[j * ldc + j];
-                    if (!(d > 0.0)) { bad = 1; d = 1.0; }
-                    a[j * ldc + j] = sqrt(d);
-                }
-                __syncwarp();
-                if (lane > j && lane < kb) a[lane * ldc + j] /= a[j * ldc + j];
-                __syncwarp();
-                if (lane > j && lane < kb)
-                    for (int c = j + 1; c <= lane; ++c) a[lane * ldc + c] = fma(-a[lane * ldc + j], a[c * ldc + j], a[lane * ldc + c]);
-                __syncwarp();
-            }
-            if (lane == 0) {
-                double sacc = 0.0;
-                for (int j = 0; j < kb; ++j) sacc += log(a[j * ldc + j]);
-                p.reward[l] = p.p0 * 2.0 * sacc;
-                if (bad) s_bad = l + 1;
-            }
-            continue;
-        }
-        if (p.kind == IPP_REWARD_MES) {
-            for (int idx = lane; idx < kb * p.S; idx += 32) {
-                const int qi = b0 + idx / p.S;
-                s0 += ro_mes_utility(p.maxes[idx % p.S], snap_m[qi], snap_v[qi]);
-            }
-        } else {
-            for (int qi = b0 + lane; qi < b0 + kb; qi += 32) {
-                s0 += (p.kind == IPP_REWARD_EI) ? (snap_m[qi] - p.p0) : snap_m[qi];
-                s1 += fabs(snap_v[qi]);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        }
-        if (lane == 0) {
-            double r;
-            if (p.kind == IPP_REWARD_UCB) {
-                r = s0 + p.p0 * s1;
-            } else if (p.kind == IPP_REWARD_EI) {
-                const double z = s0 / s1;
-                const double big_phi = 0.5 * (1.0 + erf(z / 1.41421356237309504880));
-                const double small_phi = 1.0 / 2.50662827463100050242 * exp(-(z * z) / 2.0);
-                r = s0 * big_phi + s1 * small_phi;
-            } else {
-                r = 2.0 * s0 / (double)p.S;
-            }
-            p.reward[l] = r;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        g_rf_clock[26] = clock64();
-        *p.info = s_bad;
-        if (p.done) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned int*>(p.done) = p.done_seq;
-        }
-    }
+    rf_score(p, snap_m, snap_v, Cs, s_bad, tag);
 }
 
 template <int D, int NT>
 __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __grid_constant__ RolloutFusedArgs q,
-                                                                     const __grid_constant__ RolloutInline pp) {
+                                                                     const __grid_constant__ RolloutInlineSmall pp) {
     constexpr int P = 8 * NT;
     extern __shared__ __align__(16) double sm[];
     double* s_pts = sm;                                  // [P][3]
@@ -298,7 +431,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     __syncthreads();
 
     const int G = gridDim.x;
-    const int k0 = (int)(((int64_t)blockIdx.x * q.tiles) / G), k1 = (int)(((int64_t)(blockIdx.x + 1) * q.tiles) / G);
+    const int k0 = (int)((blockIdx.x * (unsigned)q.tiles) / (unsigned)G);                  // tiles * SMs < 2^31
+    const int k1 = (int)(((blockIdx.x + 1u) * (unsigned)q.tiles) / (unsigned)G);
     // column-major walk over the lower triangle: column J holds tiles (I = J .. T - 1, J)
     int J = 0, I = 0;
     {
@@ -328,8 +462,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         double v[2 * NT];
 #pragma unroll
         for (int r = 0; r < 2 * NT; ++r) {
-            const int a = a0 + 4 * r;
-            v[r] = (a < M && n < N) ? rf_rbf<D>(q.kern, s_pts + a * D, x) : 0.0;
+            const int a = a0 + 4 * r;                     // a0 is the same for the whole warp: the skip is a real branch
+            v[r] = 0.0;
+            if (a < M) v[r] = n < N ? rf_rbf<D>(q.kern, s_pts + a * D, x) : 0.0;
         }
 #pragma unroll
         for (int r = 0; r < 2 * NT; ++r) {
@@ -471,24 +606,28 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     double* C = s_ki;
     double* m = C + (size_t)M * ldc;
     double* H = m + M;
-    double* snap_m = H + (size_t)(M + 1) * (RO_MAX_BLOCK + 1);
+    const int h_doubles = (M + 1) * (RO_MAX_BLOCK + 1) > q.r.L * 128 ? (M + 1) * (RO_MAX_BLOCK + 1) : q.r.L * 128;
+    double* snap_m = H + h_doubles;
     double* snap_v = snap_m + M;
     double* Cs = snap_v + M;                              // [M][M+1] (information gain: the levels' blocks)
     __syncthreads();                                      // s_z8 (same memory as C) has been consumed by everybody
     for (int v = tid; v < V; v += RF_THREADS) {
         const double* src = q.part + v;
-        double acc[16];
+        double acc[32];                                   // 32 independent loads in flight: the sum is L2-latency bound
 #pragma unroll
-        for (int u = 0; u < 16; ++u) acc[u] = 0.0;
+        for (int u = 0; u < 32; ++u) acc[u] = 0.0;
         int c = 0;
-        for (; c + 16 <= G; c += 16) {
+        for (; c + 32 <= G; c += 32) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) acc[u] += __ldcg(src + (size_t)(c + u) * V);
+            for (int u = 0; u < 32; ++u) acc[u] += __ldcg(src + (size_t)(c + u) * V);
         }
-        for (; c < G; ++c) acc[0] += __ldcg(src + (size_t)c * V);
+        if (c < G) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc[u] += (c + u < G) ? __ldcg(src + (size_t)(c + u) * V) : 0.0;
+        }
         double tot = 0.0;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) tot += acc[u];
+        for (int u = 0; u < 32; ++u) tot += acc[u];
         if (v < M * (M + 1) / 2) {
             int a = (int)((sqrt(8.0 * v + 1.0) - 1.0) * 0.5);
             while (a * (a + 1) / 2 > v) --a;
@@ -503,7 +642,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     }
     for (int i = tid; i < M; i += RF_THREADS) s_z[i] = q.use_inline ? pp.v[M * D + i] : q.zobs[i];
     const long long clk3 = clock64();
-    rf_condition(q.r, s_z, C, m, H, snap_m, snap_v, Cs, s_bad);
+    if (q.warp_cond) {                                    // every level <= 4 points: one warp, left-looking
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        if (tid == 0) g_rf_clock[16] = clock64();
+        if (warp == 0) rf_condition_warp(q.r, s_z, C, m, H /* panels [L][4][32] */, snap_m, snap_v, Cs, s_bad);
+        __syncthreads();
+        rf_score(q.r, snap_m, snap_v, Cs, s_bad, q.tag);
+    } else {
+        rf_condition(q.r, s_z, C, m, H, snap_m, snap_v, Cs, s_bad, q.tag);
+    }
     if (tid == 0) {
         g_rf_clock[0] = clk1 - clk0; g_rf_clock[1] = clk2 - clk1; g_rf_clock[2] = clk3 - clk2; g_rf_clock[3] = clock64() - clk3;
         g_rf_clock[4] = tk[0] - clk0;     // points + setup

@@ -363,7 +363,9 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     // zero-copy form: the pinned staging buffer as the device sees it (same memory; unified addressing normally makes
     // the two pointers equal).  If the buffer is not mapped, the copy + synchronise form below is used instead.
     double* h_flag = h_out + IPP_ROLLOUT_MAX_LEVELS + 8;
+    double* h_rec = h_out + IPP_ROLLOUT_MAX_LEVELS + 16;                          // [L + 1] {value, tag} records (16-byte aligned)
     double* m_out = nullptr;
+    double* m_rec = nullptr;
     unsigned int* m_flag = nullptr;
     bool zero_copy = false;
     {
@@ -372,6 +374,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
         } else if (cudaHostGetDevicePointer(&dp, stage_host, 0) == cudaSuccess && dp) {
             m_out = static_cast<double*>(dp) + (h_out - stage_host);
             m_flag = reinterpret_cast<unsigned int*>(static_cast<double*>(dp) + (h_flag - stage_host));
+            m_rec = static_cast<double*>(dp) + (h_rec - stage_host);
             zero_copy = true;
         } else {
             cudaGetLastError();                                                  // clear the sticky "not mapped" error
@@ -385,7 +388,10 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     }
     static unsigned int seq_base = 0;                                            // completion words never repeat a value
     unsigned int seq = (seq_base += 1u << 20);
-    if (!host_reward || value_reward) *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
+    if (!host_reward || value_reward) {
+        *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
+        memset(h_rec, 0, sizeof(double) * 2 * (IPP_ROLLOUT_MAX_LEVELS + 1));     // no stale record can carry a live tag
+    }
     ipp::RolloutInline inl;
 
     int max_samp = 0;
@@ -674,27 +680,45 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
                 // word polled by this thread: no copies and no driver synchronisation on the rollout's critical path
                 ++seq;
                 const double t_launch = now_us();
+                bool tagged = false;
+                static unsigned long long tag_counter = 0;                          // 64 bits: a tag never repeats
+                const unsigned long long tag64 = ++tag_counter;
                 const int rc = ipp::rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
                                                    maxes_dev, S, d_in, d_in + (size_t)M * D, &inl, offsets, reps, L, m_out,
-                                                   reinterpret_cast<int32_t*>(m_out + L), m_flag, seq, work, stream);
+                                                   reinterpret_cast<int32_t*>(m_out + L), m_flag, seq, work, stream,
+                                                   (reinterpret_cast<uintptr_t>(m_rec) % 16 == 0) ? m_rec : nullptr, tag64, &tagged);
                 if (rc != IPP_OK) return rc;
                 const double t_spin = now_us();
                 launch_us += t_spin - t_launch;
-                for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int*>(h_flag) != seq; ++spins) {
+                // done = the completion word (four-kernel form) or, for the one-launch form, every {value, tag} record
+                // carrying this rollout's tag: each record is one 16-byte store, so a visible tag means a visible value
+                auto done = [&]() {
+                    if (!tagged) return *reinterpret_cast<volatile unsigned int*>(h_flag) == seq;
+                    const volatile unsigned long long* tags = reinterpret_cast<const volatile unsigned long long*>(h_rec);
+                    for (int l = L; l >= 0; --l)
+                        if (tags[2 * l + 1] != tag64) return false;
+                    return true;
+                };
+                for (unsigned spins = 0; !done(); ++spins) {
                     if (complete_some()) continue;                                  // useful work while the device runs
                     if ((spins & 0xffff) == 0xffff && now_us() - t_spin > 5e6) {          // 5 s: something is wrong on the device
                         IPP_CUDA(cudaStreamSynchronize(stream));
-                        if (*reinterpret_cast<volatile unsigned int*>(h_flag) == seq) break;
+                        if (done()) break;
                         ::ipp::set_error("%s: rollout %d never completed", __func__, it);
                         return IPP_E_CUDA;
                     }
                 }
                 __atomic_thread_fence(__ATOMIC_ACQUIRE);
+                if (tagged) {                                                       // unpack into the plain layout read below
+                    for (int l = 0; l < L; ++l) h_out[l] = h_rec[2 * l];
+                    const int32_t bad = (int32_t)h_rec[2 * L];
+                    memcpy(h_out + L, &bad, sizeof(int32_t));
+                }
             } else {
                 IPP_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (size_t)M * (D + 1), cudaMemcpyHostToDevice, stream));
                 const int rc = ipp::rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, P.kind, params_host, 1,
                                                    maxes_dev, S, d_in, d_in + (size_t)M * D, nullptr, offsets, reps, L, d_out,
-                                                   reinterpret_cast<int32_t*>(d_out + L), nullptr, 0u, work, stream);
+                                                   reinterpret_cast<int32_t*>(d_out + L), nullptr, 0u, work, stream, nullptr, 0ull, nullptr);
                 if (rc != IPP_OK) return rc;
                 IPP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * (size_t)(L + 1), cudaMemcpyDeviceToHost, stream));
                 IPP_CUDA(cudaStreamSynchronize(stream));

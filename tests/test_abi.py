@@ -43,8 +43,13 @@ def test_struct_layout_matches_header():
     assert _lib.lib.ipp_abi_struct_sizes(sizes) == 0
     assert list(sizes) == [ctypes.sizeof(_lib.IppRbf), ctypes.sizeof(IppObstacleBox), ctypes.sizeof(_lib.IppMtState),
                            ctypes.sizeof(_lib.IppTreeParams)]
-    assert _lib.IPP_TREE_STAGE_DOUBLES == (_lib.IPP_ROLLOUT_MAX_POINTS * (_lib.IPP_MAX_DIM + 1)
-                                           + _lib.IPP_ROLLOUT_MAX_LEVELS + 16)
+    # the staging size is the header's own expression, evaluated with the binding's constants
+    import re
+    hdr = open(os.path.join(ROOT, 'include', 'ipp_b200.h')).read()
+    expr = re.search(r'#define IPP_TREE_STAGE_DOUBLES \((.*)\)\s*$', hdr, re.M).group(1)
+    assert _lib.IPP_TREE_STAGE_DOUBLES == eval(expr, {'IPP_ROLLOUT_MAX_POINTS': _lib.IPP_ROLLOUT_MAX_POINTS,
+                                                      'IPP_MAX_DIM': _lib.IPP_MAX_DIM,
+                                                      'IPP_ROLLOUT_MAX_LEVELS': _lib.IPP_ROLLOUT_MAX_LEVELS})
     k = _lib.make_rbf(2, 100.0, 1.0)
     assert (k.dim, k.variance, k.inv_lengthscale[0], k.inv_lengthscale[1], k.inv_lengthscale[2]) == (2, 100.0, 1.0, 1.0, 0.0)
     k3 = _lib.make_rbf(3, 4.0, (2.0, 4.0, 8.0))
