@@ -22,10 +22,10 @@ constexpr int DIAG_SMEM = (2 * NB * DIAG_LD + 32 * 33 + NB) * 8;
 // r1 version: 3 barriers, a division per column entry and two integer divisions per updated element for each of the 64
 // pivots, then 64 threads each running a serial O(n^2) substitution -- 100 us per block, 40 % of a refresh at N = 4096
 // (profiles/r2a_launches_factor_4096.csv).  Now:
-//   * one barrier per pivot.  Four threads own a row (columns k = j + 1 + part, + 4, ...); every thread takes the pivot
-//     d = a[j][j] and forms r = 1 / sqrt(d) itself, scales its own a[i][j] and applies  a[i][k] -= (a[i][j] r) (a[k][j] r)
-//     from the UNSCALED column still in shared memory; the scaled column goes to a second array, so nothing has to be
-//     re-read after a barrier;
+//   * one barrier per pivot.  16 x 16 threads own the elements cyclically; every thread takes the pivot d = a[j][j] and
+//     forms r = 1 / sqrt(d) itself (rsqrt_fast: four dependent operations after the hardware approximation), scales the
+//     column entries of its rows and columns and applies  a[i][k] -= (a[i][j] r) (a[k][j] r)  from the UNSCALED column still
+//     in shared memory; the scaled column goes to a second array, so nothing has to be re-read after a barrier;
 //   * the triangular inverse by recursive doubling with all 256 threads: the eight 8 x 8 diagonal blocks by substitution
 //     in registers (reciprocal pivots already known), then Linv21 = -Linv22 (L21 Linv11) for block sizes 8, 16, 32.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t lda, int jb,
@@ -48,35 +48,46 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     if (tid < NB) rinv[tid] = 1.0;
     if (tid == 0) bad = 0;
     __syncthreads();
-    const int row = tid >> 2, part = tid & 3;
+    // 16 x 16 threads, cyclic in both directions: thread (ty, tx) owns the elements (ty + 16 i, tx + 16 m) -- the trailing
+    // block shrinks towards the bottom-right corner and a cyclic layout keeps every thread busy until the end
+    const int ty = tid >> 4, tx = tid & 15;
     for (int j = 0; j < jb; ++j) {
         double d = a[j][j];
         if (!(d > 0.0)) {                // also catches NaN, like LAPACK's dpotrf
             if (tid == 0 && bad == 0) bad = j + 1;
             d = 1.0;
         }
-        const double r = rsqrt(d);
+        const double r = rsqrt_fast(d);
         if (tid == 0) { l[j][j] = d * r; rinv[j] = r; }
-        if (row > j && row < jb) {
-            const double c = a[row][j] * r;
-            if (part == 0) l[row][j] = c;
-            // four elements per pass, all loads before the first store (the compiler cannot prove that the stores to
-            // a[row][.] do not alias the column reads, and would otherwise serialise load -> fma -> store per element)
-            for (int k = j + 1 + part; k <= row; k += 16) {
-                double col[4], old[4];
+        double cr[4], cc[4], old[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int kk = k + 4 * u;
-                    col[u] = kk <= row ? a[kk][j] : 0.0;
-                    old[u] = kk <= row ? a[row][kk] : 0.0;
-                }
+        for (int i = 0; i < 4; ++i) {
+            const int row = ty + 16 * i, col = tx + 16 * i;
+            cr[i] = (row > j && row < jb) ? a[row][j] * r : 0.0;     // the UNSCALED column is still in place: no barrier
+            cc[i] = (col > j && col < jb) ? a[col][j] * r : 0.0;     // between scaling it and using it
+        }
+        // all loads before the first store (the compiler cannot prove that the stores do not alias the later loads)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int kk = k + 4 * u;
-                    if (kk <= row) a[row][kk] = fma(-c, col[u] * r, old[u]);
-                }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int row = ty + 16 * i, col = tx + 16 * m;
+                old[i][m] = (col > j && col <= row && row < jb) ? a[row][col] : 0.0;
+            }
+        if (tx == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = ty + 16 * i;
+                if (row > j && row < jb) l[row][j] = cr[i];
             }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int row = ty + 16 * i, col = tx + 16 * m;
+                if (col > j && col <= row && row < jb) a[row][col] = fma(-cr[i], cc[m], old[i][m]);
+            }
         __syncthreads();
     }
     // ---- L^-1 into `a`.  8 x 8 diagonal blocks: thread (block, column) substitutes in registers

@@ -124,6 +124,20 @@ __device__ __forceinline__ double rbf_eval_fast(const RbfDev& k, const double* a
 }
 
 
+// 1 / sqrt(d), d > 0 and normal, to ~1 ulp in four dependent FP64 operations after the hardware approximation
+// (MUFU.RSQ64H, 2^-22.9): one third-order step  y' = y (1 + e/2 + 3 e^2 / 8),  e = 1 - d y^2, leaves e^3 ~ 2^-68.
+// libdevice's rsqrt() is ~20 dependent instructions; on the pivot chains of the small Cholesky factorisations
+// (rollout conditioning, diagonal blocks of the refresh) that latency is the critical path.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
+
 // ---- rollout.cu <-> tree.cu: one rollout's launch sequence with the points passed by value and a host-visible
 // completion word (see rollout_launch in rollout.cu)
 constexpr int RO_INLINE_POINTS = 96;                                          // 96 * 4 doubles = 3 KB of kernel parameters

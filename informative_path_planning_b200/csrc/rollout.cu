@@ -602,9 +602,7 @@ extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
     if (M <= 0) return 16;
     const int64_t ldc = round_up(M, 2);
     const int64_t four_kernels = 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
-    const int64_t Mf = M < 32 ? M : 32;
-    const int64_t fused = (int64_t)ipp::sm_count() * (Mf * (Mf + 1) / 2 + Mf) + 16;    // one partial per CTA, <= 1 CTA per SM
-    return four_kernels > fused ? four_kernels : fused;
+    return four_kernels;                // the one-launch form (<= 32 points) keeps its partial sums in library-owned accumulators
 }
 
 namespace ipp {
@@ -652,7 +650,6 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         fa.kern = to_dev(*kern);
         fa.X = X; fa.alpha = alpha; fa.W = winv; fa.ldw = ldw; fa.N = (int)N;
         fa.pts = pts; fa.zobs = zobs; fa.use_inline = inline_pts ? 1 : 0;
-        fa.part = work;
         fa.slot = (int)(__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % RF_SLOTS);
         fa.tag = 0;
         if (tagged_out && tag) {                          // results as self-validating records, no completion word
@@ -662,9 +659,6 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         fa.T = (int)((N + RF_B - 1) / RF_B);
         fa.tiles = fa.T * (fa.T + 1) / 2;
         fa.r = p;
-        fa.warp_cond = 1;
-        for (int l = 0; l < L; ++l)
-            if (offsets_host[l + 1] - offsets_host[l] > 4) fa.warp_cond = 0;
         if (used_tagged) *used_tagged = fa.tag != 0;
         // small beliefs: a CTA per tpc tiles (IPP_ROLLOUT_TPC, default 1: shortest tile phase); large ones: one CTA per SM
         static const int tpc = [] { const char* e = getenv("IPP_ROLLOUT_TPC"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();

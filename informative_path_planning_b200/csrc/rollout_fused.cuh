@@ -13,18 +13,46 @@
 //     and when the column ends the accumulator fragments ARE the A operand of the second contraction (k permutation:
 //     thread t of a quad owns columns 2t, 2t+1 in both), so  A += U_J K_J^T  needs no shared-memory round trip;
 //   * on the diagonal tile the CTA also adds K_J alpha_J to its partial mean;
-//   * every CTA stores its partial (A + A^T lower triangle and the mean: M (M + 1) / 2 + M doubles), the last one to finish
-//     (a ticket counter) sums the partials in CTA order -- a fixed order, so the result does not depend on timing --,
-//     forms C0 = Kqq - (A + A^T) and m0, and runs the level-by-level conditioning in the same launch;
+//   * every CTA adds its partial (A + A^T lower triangle and the mean: M (M + 1) / 2 + M numbers) into 128-bit fixed-point
+//     accumulators -- exact integer sums, so the result does not depend on the order of arrival --; the last CTA to
+//     finish (a ticket counter) reads the totals, forms C0 = Kqq - (A + A^T) and m0, and runs the level-by-level
+//     conditioning in the same launch;
 //   * the rewards are not evaluated inside the sequential conditioning: each level's predictive moments are snapshot when
 //     the level is reached and all levels are scored in parallel (one warp per level) at the end.
 #pragma once
 
 namespace ipp {
 
-constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8, RF_SLOTS = 256;
+constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8;
+constexpr int RF_SLOTS = 16;                            // rollouts in flight per device (each launch takes the next slot)
+constexpr int RF_VMAX = 32 * 33 / 2 + 32;               // partial sums per rollout: A + A^T lower triangle and the mean, M <= 32
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
+// The CTAs' partial sums meet in FIXED-POINT accumulators (units of 2^-70): integer addition is associative, so the total
+// is exact and independent of the order in which the CTAs arrive -- deterministic like a fixed-order sum, but the
+// finishing CTA reads V numbers instead of V x (number of CTAs) (7.5k -> ~2k SM clocks at N = 900, 120 CTAs).  A value is
+// cut into three 42-bit limbs held in 64-bit words: 22 bits of headroom per word absorb the carries of up to 2^21 CTAs,
+// so every add is a fire-and-forget reduction (no returned value to wait for); the finishing CTA propagates the carries.
+// Zero at load, put back to zero by the finishing CTA.  g_rf_nonfinite: some partial was NaN / Inf / out of range.
+__device__ long long g_rf_acc[RF_SLOTS][3 * RF_VMAX];
 __device__ long long g_rf_clock[32];                     // SM clocks of the finishing CTA per phase (ipp_rollout_debug_clocks)
+__device__ unsigned int g_rf_nonfinite[RF_SLOTS];
+
+__device__ __forceinline__ void rf_accumulate(long long* acc, double x) {
+    const double y = x * 0x1p70;                         // exact: |x| < 2^56
+    const double h2 = floor(y * 0x1p-84);                // signed top limb
+    const double r1 = fma(-h2, 0x1p84, y);               // in [0, 2^84), exact
+    const double h1 = floor(r1 * 0x1p-42);
+    const double h0 = fma(-h1, 0x1p42, r1);              // in [0, 2^42)
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__double2ll_rz(h0));
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 1), (unsigned long long)__double2ll_rz(h1));
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2), (unsigned long long)__double2ll_rz(h2));
+}
+__device__ __forceinline__ double rf_total(long long l0, long long l1, long long l2) {
+    l1 += l0 >> 42;  l0 &= (1ll << 42) - 1;              // carries upwards (arithmetic shifts: limbs may be negative)
+    l2 += l1 >> 42;  l1 &= (1ll << 42) - 1;
+    // l2 2^84 + l1 2^42 + l0: the two low limbs are < 2^42 and exact in double; one rounding per addition
+    return fma((double)l2, 0x1p84, fma((double)l1, 0x1p42, (double)l0)) * 0x1p-70;
+}
 
 // The rollout's points and observations by value: [M][D] points, then [M] observations (M <= 32 in this kernel: 1 KB of
 // kernel parameters instead of the 3 KB RolloutInline of the four-kernel form).
@@ -42,9 +70,7 @@ struct RolloutFusedArgs {
     const double* X; const double* alpha; const double* W; int64_t ldw; int N;
     const double* pts; const double* zobs;               // device copies (used when use_inline == 0)
     int use_inline;
-    double* part;                                        // [gridDim.x][V], V = M (M + 1) / 2 + M
     int slot, tiles, T;
-    int warp_cond;                                       // every level has <= 4 points: single-warp conditioning
     unsigned long long tag;                              // != 0: r.reward holds 16-byte {value, tag} records, L rewards then info
     RolloutArgs r;
 };
@@ -176,111 +202,6 @@ __device__ __forceinline__ void rf_score(const RolloutArgs& p, const double* sna
     }
 }
 
-// The usual rollout -- every level a block of <= 4 points, <= 32 points in all -- conditioned by ONE warp, lane = point,
-// in left-looking form: nothing is written back into the covariance.  At level l a lane assembles the couplings of its
-// point with the level's block under the conditioned covariance from the prior block and the panels H_l' of the earlier
-// levels (c = C0[i][B] - sum_l' H_l'[i] H_l'[B]^T), the 4 x 4 pivot block is gathered from its owner lanes by shuffles,
-// factored redundantly in registers (branch-free, so the substitutions overlap the rsqrt latencies), and the lane's own
-// panel row h = L^-1 c, mean m += h . u and H_l[i] = h follow.  Per level: one __syncwarp instead of three block barriers
-// and an M x M read-modify-write pass (8.2k -> ~3k SM clocks for five levels of four points).
-__device__ __forceinline__ void rf_condition_warp(const RolloutArgs& p, const double* zobs, const double* C0, const double* m0,
-                                                  double* Hs /* [L][4][32] */, double* snap_m, double* snap_v, double* Cs,
-                                                  int& s_bad) {
-    const int M = p.M, ldc = M + 1, lane = threadIdx.x & 31;
-    const bool live = lane < M;
-    const int row = live ? lane : 0;
-    double mi = live ? m0[row] : 0.0;
-    const double zi = live ? zobs[row] : 0.0;
-    int bad = 0;
-    for (int l = 0; l < p.L; ++l) {
-        const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
-        if (lane == 0 && l < 8) g_rf_clock[17 + l] = clock64();
-        int col[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) col[a] = (b0 + a) < M ? (b0 + a) : (M - 1);
-        double c[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) c[a] = C0[row * ldc + col[a]];
-        for (int lp = 0; lp < l; ++lp) {
-            const double* hp = Hs + lp * 128;
-            double own[4];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) own[cc] = hp[cc * 32 + lane];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) c[a] = fma(-own[cc], hp[cc * 32 + col[a]], c[a]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) c[a] = (live && a < kb) ? c[a] : 0.0;
-        // the pivot block: entry (a, b) = coupling b of the lane that owns point b0 + a
-        const double dadd = p.reps[l] > 0 ? p.diag_add / (double)p.reps[l] : 0.0;
-        double Lf[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                const double v = __shfl_sync(0xffffffffu, c[b], col[a]);
-                Lf[a][b] = (a < kb) ? v : (a == b ? 1.0 : 0.0);
-            }
-        // snapshot of the level's predictive moments (or of its block, for the information gain)
-        if (p.kind == IPP_REWARD_INFO) {
-            if (lane == 0) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b <= a; ++b)
-                        if (a < kb) Cs[(b0 + a) * ldc + b0 + b] = Lf[a][b] + (a == b ? 1.0 : 0.0);
-            }
-        } else if (lane >= b0 && lane < b0 + kb) {
-            const int o = lane - b0;
-            snap_m[lane] = mi;
-            snap_v[lane] = (o == 0 ? c[0] : (o == 1 ? c[1] : (o == 2 ? c[2] : c[3]))) + p.noise_pred;
-        }
-        if (l == p.L - 1) break;                  // the last level's observation is never looked at again
-        double rd[4], u[4], h[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-            if (a < kb) Lf[a][a] += dadd;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool ok = Lf[j][j] > 0.0;
-            bad = (!ok && bad == 0) ? (l + 1) : bad;
-            const double r = rsqrt(ok ? Lf[j][j] : 1.0);
-            rd[j] = r;
-#pragma unroll
-            for (int i = j + 1; i < 4; ++i) Lf[i][j] *= r;
-#pragma unroll
-            for (int i = j + 1; i < 4; ++i)
-#pragma unroll
-                for (int cc = j + 1; cc <= i; ++cc) Lf[i][cc] = fma(-Lf[i][j], Lf[cc][j], Lf[i][cc]);
-        }
-        const double resid = zi - mi;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            double v = __shfl_sync(0xffffffffu, resid, col[a]);
-            v = (a < kb) ? v : 0.0;
-#pragma unroll
-            for (int cc = 0; cc < a; ++cc) v = fma(-Lf[a][cc], u[cc], v);
-            u[a] = v * rd[a];
-        }
-        double dm = 0.0;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            double v = c[a];
-#pragma unroll
-            for (int cc = 0; cc < a; ++cc) v = fma(-Lf[a][cc], h[cc], v);
-            h[a] = p.reps[l] > 0 ? v * rd[a] : 0.0;   // reps == 0: the block is scored but never appended
-            dm = fma(h[a], u[a], dm);
-        }
-        mi += dm;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) Hs[l * 128 + cc * 32 + lane] = h[cc];
-        __syncwarp();
-    }
-    if (lane == 0 && bad) s_bad = bad;
-}
-
 // Conditioning with the rewards deferred: same arithmetic per level as ro_condition (rollout.cu), but a level only
 // snapshots (mean, variance + noise) of its points; all levels are scored afterwards, one warp per level.
 // kind == IPP_REWARD_INFO: the operand is the information-gain belief ((I + vK)^-1, kernel variance v^2, diag_add = 1,
@@ -314,6 +235,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
             const int R = M - b0;
             __syncthreads();
             double Lf[4][4], rd[4], u[4];
+            int bad = 0;
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -321,9 +243,9 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                     Lf[a][b] = (a < kb) ? C[(b0 + a) * ldc + b0 + b] + (a == b ? dadd : 0.0) : (a == b ? 1.0 : 0.0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                double d = Lf[j][j];
-                if (!(d > 0.0)) { if (tid == 0) s_bad = l + 1; d = 1.0; }
-                const double r = rsqrt(d);
+                const bool ok = Lf[j][j] > 0.0;       // branch-free: the substitutions below overlap the pivot chain
+                bad = (!ok && bad == 0) ? (l + 1) : bad;
+                const double r = rsqrt_fast(ok ? Lf[j][j] : 1.0);
                 rd[j] = r;
 #pragma unroll
                 for (int i = j + 1; i < 4; ++i) Lf[i][j] *= r;
@@ -339,6 +261,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                 for (int c = 0; c < a; ++c) v = fma(-Lf[a][c], u[c], v);
                 u[a] = v * rd[a];
             }
+            if (bad && tid == 0) s_bad = bad;
             const int i = b0 + tid;               // this thread's point (M <= 32 < RF_THREADS: at most one)
             double dm = 0.0;
             if (i < M) {
@@ -379,7 +302,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                 const double piv = H[(b0 + a) * HL + a];
                 __syncthreads();
                 if (!(piv > 0.0) && tid == 0) s_bad = l + 1;
-                const double d = piv > 0.0 ? rsqrt(piv) : 1.0;
+                const double d = piv > 0.0 ? rsqrt_fast(piv) : 1.0;
                 for (int i = b0 + tid; i <= M; i += RF_THREADS)
                     H[i * HL + a] = (i < b0 + a) ? 0.0 : H[i * HL + a] * d;
                 __syncthreads();
@@ -576,7 +499,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         }
     __syncthreads();
     const int V = M * (M + 1) / 2 + M;
-    double* mine = q.part + (size_t)blockIdx.x * V;
+    long long* acc = g_rf_acc[q.slot];
+    bool finite = true;
     for (int a = warp; a < M; a += RF_WARPS)              // pairs b <= a: lane = b (M <= 32)
         if (lane <= a) {
             double s_ab = 0.0, s_ba = 0.0;
@@ -585,9 +509,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
                 s_ab += s_z8[w * P * P + a * P + lane];
                 s_ba += s_z8[w * P * P + lane * P + a];
             }
-            mine[a * (a + 1) / 2 + lane] = s_ab + s_ba;
+            const double v = s_ab + s_ba;
+            finite = finite && (fabs(v) < 0x1p56);        // also false for NaN
+            rf_accumulate(acc + 3 * (a * (a + 1) / 2 + lane), finite ? v : 0.0);
         }
-    if (tid < M) mine[M * (M + 1) / 2 + tid] = s_m0[tid];
+    if (tid < M) {
+        const double v = s_m0[tid];
+        finite = finite && (fabs(v) < 0x1p56);
+        rf_accumulate(acc + 3 * (M * (M + 1) / 2 + tid), finite ? v : 0.0);
+    }
+    if (!finite) atomicOr(&g_rf_nonfinite[q.slot], 1u);
     const long long clk1 = clock64();
     __threadfence();
     __syncthreads();
@@ -606,28 +537,15 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     double* C = s_ki;
     double* m = C + (size_t)M * ldc;
     double* H = m + M;
-    const int h_doubles = (M + 1) * (RO_MAX_BLOCK + 1) > q.r.L * 128 ? (M + 1) * (RO_MAX_BLOCK + 1) : q.r.L * 128;
-    double* snap_m = H + h_doubles;
+    double* snap_m = H + (size_t)(M + 1) * (RO_MAX_BLOCK + 1);
     double* snap_v = snap_m + M;
     double* Cs = snap_v + M;                              // [M][M+1] (information gain: the levels' blocks)
     __syncthreads();                                      // s_z8 (same memory as C) has been consumed by everybody
+    const bool poisoned = __ldcg(&g_rf_nonfinite[q.slot]) != 0u;
     for (int v = tid; v < V; v += RF_THREADS) {
-        const double* src = q.part + v;
-        double acc[32];                                   // 32 independent loads in flight: the sum is L2-latency bound
-#pragma unroll
-        for (int u = 0; u < 32; ++u) acc[u] = 0.0;
-        int c = 0;
-        for (; c + 32 <= G; c += 32) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) acc[u] += __ldcg(src + (size_t)(c + u) * V);
-        }
-        if (c < G) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) acc[u] += (c + u < G) ? __ldcg(src + (size_t)(c + u) * V) : 0.0;
-        }
-        double tot = 0.0;
-#pragma unroll
-        for (int u = 0; u < 32; ++u) tot += acc[u];
+        const long long l0 = __ldcg(acc + 3 * v), l1 = __ldcg(acc + 3 * v + 1), l2 = __ldcg(acc + 3 * v + 2);
+        acc[3 * v] = acc[3 * v + 1] = acc[3 * v + 2] = 0ll;        // the slot is clean for its next rollout
+        const double tot = poisoned ? nan("") : rf_total(l0, l1, l2);
         if (v < M * (M + 1) / 2) {
             int a = (int)((sqrt(8.0 * v + 1.0) - 1.0) * 0.5);
             while (a * (a + 1) / 2 > v) --a;
@@ -641,17 +559,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         }
     }
     for (int i = tid; i < M; i += RF_THREADS) s_z[i] = q.use_inline ? pp.v[M * D + i] : q.zobs[i];
+    __syncthreads();
+    if (tid == 0 && poisoned) g_rf_nonfinite[q.slot] = 0u;
     const long long clk3 = clock64();
-    if (q.warp_cond) {                                    // every level <= 4 points: one warp, left-looking
-        if (tid == 0) s_bad = 0;
-        __syncthreads();
-        if (tid == 0) g_rf_clock[16] = clock64();
-        if (warp == 0) rf_condition_warp(q.r, s_z, C, m, H /* panels [L][4][32] */, snap_m, snap_v, Cs, s_bad);
-        __syncthreads();
-        rf_score(q.r, snap_m, snap_v, Cs, s_bad, q.tag);
-    } else {
-        rf_condition(q.r, s_z, C, m, H, snap_m, snap_v, Cs, s_bad, q.tag);
-    }
+    rf_condition(q.r, s_z, C, m, H, snap_m, snap_v, Cs, s_bad, q.tag);
     if (tid == 0) {
         g_rf_clock[0] = clk1 - clk0; g_rf_clock[1] = clk2 - clk1; g_rf_clock[2] = clk3 - clk2; g_rf_clock[3] = clock64() - clk3;
         g_rf_clock[4] = tk[0] - clk0;     // points + setup
