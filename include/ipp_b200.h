@@ -228,6 +228,8 @@ int ipp_dgemm_nt(int64_t M, int64_t N, int64_t K, double alpha, const double* A,
  * logdet = 2 sum log diag; info as above */
 int64_t ipp_potrf_workspace(int64_t N);
 int ipp_potrf_lower(double* A, int64_t N, int64_t lda, double* logdet, int32_t* info, double* work, void* stream);
+/* diagnostics: SM clocks the last 64 x 64 diagonal block spent in {load, pivots, triangular inverse, store} */
+int ipp_potrf_debug_clocks(int64_t out[4]);
 /* per-path log det of the k_p x k_p Schur blocks S_p = I + v Kqq_p - v^2 C_p^T Binv C_p  (info_gain) */
 int64_t ipp_info_gain_workspace(int64_t N, int64_t M);
 int ipp_info_gain_paths(const ipp_rbf* kern_v2 /* RBF with variance = v^2 */, const double* X, int64_t N,

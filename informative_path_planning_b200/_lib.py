@@ -125,6 +125,7 @@ SIGNATURES = {
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
     'ipp_dgemm_nt': (_INT, [_I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, _P, _I64, _P]),
     'ipp_potrf_workspace': (_I64, [_I64]),
+    'ipp_potrf_debug_clocks': (_INT, [_P]),
     'ipp_potrf_lower': (_INT, [_P, _I64, _I64, _P, _P, _P, _P]),
     'ipp_info_gain_workspace': (_I64, [_I64, _I64]),
     'ipp_dubins_path_set': (_INT, [_P, _P, _INT, _D, _D, _INT, _P, _D, _P, _INT, _P, _P, _INT, _P, _P, _INT]),

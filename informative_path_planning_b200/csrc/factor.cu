@@ -16,6 +16,7 @@ namespace ipp {
 constexpr int NB = 64;
 constexpr int DIAG_LD = NB + 1;
 constexpr int DIAG_SMEM = (2 * NB * DIAG_LD + 32 * 33 + NB) * 8;
+__device__ long long g_potrf_clock[4];       // SM clocks of the last diagonal block: load, pivots, inverse, store (diagnostics)
 
 // Cholesky of the jb x jb lower block at A (leading dimension lda) + its inverse into dinv[64][64].
 //
@@ -28,7 +29,7 @@ constexpr int DIAG_SMEM = (2 * NB * DIAG_LD + 32 * 33 + NB) * 8;
 //     in shared memory; the scaled column goes to a second array, so nothing has to be re-read after a barrier;
 //   * the triangular inverse by recursive doubling with all 256 threads: the eight 8 x 8 diagonal blocks by substitution
 //     in registers (reciprocal pivots already known), then Linv21 = -Linv22 (L21 Linv11) for block sizes 8, 16, 32.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t lda, int jb,
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t lda, int jb,
                                                          double* __restrict__ dinv, double* logdet,
                                                          int32_t* info, int j0) {
     extern __shared__ double sm[];
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     double* rinv = sm + 2 * NB * DIAG_LD + 32 * 33;                                       // 1 / L[j][j]
     __shared__ int bad;
     const int tid = threadIdx.x;
+    const long long t0 = clock64();
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
         double v = (r == c) ? 1.0 : 0.0;
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     // 16 x 16 threads, cyclic in both directions: thread (ty, tx) owns the elements (ty + 16 i, tx + 16 m) -- the trailing
     // block shrinks towards the bottom-right corner and a cyclic layout keeps every thread busy until the end
     const int ty = tid >> 4, tx = tid & 15;
+    const long long t1 = clock64();
     for (int j = 0; j < jb; ++j) {
         double d = a[j][j];
         if (!(d > 0.0)) {                // also catches NaN, like LAPACK's dpotrf
@@ -59,9 +62,15 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
         }
         const double r = rsqrt_fast(d);
         if (tid == 0) { l[j][j] = d * r; rinv[j] = r; }
+        // element blocks (i, m) = rows ty + 16 i, columns tx + 16 m.  Blocks that lie entirely at or before the pivot
+        // (16 i + 15 <= j, 16 m + 15 <= j) and above the diagonal (m > i) are skipped with conditions that depend on j
+        // only -- the same for every thread, so they are real branches, not predicated-off instructions: without them
+        // the late pivots issue as many instructions as the first (measured 711 clocks per pivot)
+        const int first = (j + 1) >> 4;
         double cr[4], cc[4], old[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            if (i < first) continue;
             const int row = ty + 16 * i, col = tx + 16 * i;
             cr[i] = (row > j && row < jb) ? a[row][j] * r : 0.0;     // the UNSCALED column is still in place: no barrier
             cc[i] = (col > j && col < jb) ? a[col][j] * r : 0.0;     // between scaling it and using it
@@ -70,7 +79,8 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m <= i; ++m) {
+                if (m < first) continue;
                 const int row = ty + 16 * i, col = tx + 16 * m;
                 old[i][m] = (col > j && col <= row && row < jb) ? a[row][col] : 0.0;
             }
@@ -78,19 +88,21 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = ty + 16 * i;
-                if (row > j && row < jb) l[row][j] = cr[i];
+                if (i >= first && row > j && row < jb) l[row][j] = cr[i];
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m <= i; ++m) {
+                if (m < first) continue;
                 const int row = ty + 16 * i, col = tx + 16 * m;
                 if (col > j && col <= row && row < jb) a[row][col] = fma(-cr[i], cc[m], old[i][m]);
             }
         __syncthreads();
     }
     // ---- L^-1 into `a`.  8 x 8 diagonal blocks: thread (block, column) substitutes in registers
+    const long long t2 = clock64();
     for (int idx = tid; idx < NB * NB; idx += 256) a[idx >> 6][idx & 63] = 0.0;
     __syncthreads();
     if (tid < NB) {
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
             const int p = idx >> (2 * sh), rr = (idx >> sh) & (s - 1), cc = idx & (s - 1);
             const int R0 = 2 * s * p + s, C0 = 2 * s * p;
             double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
             for (int k = cc & ~1; k < s; k += 2) {       // Linv11 is lower triangular: rows k >= cc only
                 s0 = fma(l[R0 + rr][C0 + k], a[C0 + k][C0 + cc], s0);
                 s1 = fma(l[R0 + rr][C0 + k + 1], a[C0 + k + 1][C0 + cc], s1);
@@ -127,6 +140,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
             const int p = idx >> (2 * sh), rr = (idx >> sh) & (s - 1), cc = idx & (s - 1);
             const int R0 = 2 * s * p + s, C0 = 2 * s * p;
             double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
             for (int k = 0; k <= (rr | 1); k += 2) {     // Linv22 is lower triangular: columns k <= rr only
                 s0 = fma(a[R0 + rr][R0 + k], tmp[(p << sh) + k][cc], s0);
                 s1 = fma(a[R0 + rr][R0 + k + 1], tmp[(p << sh) + k + 1][cc], s1);
@@ -135,6 +149,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
         }
         __syncthreads();
     }
+    const long long t3 = clock64();
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
         if (r < jb && c <= r) A[(int64_t)r * lda + c] = l[r][c];
@@ -148,6 +163,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
         if (tid == 0) {
             if (logdet) *logdet += 2.0 * sacc;
             if (bad && info && *info == 0) *info = j0 + bad;
+            g_potrf_clock[0] = t1 - t0; g_potrf_clock[1] = t2 - t1; g_potrf_clock[2] = t3 - t2; g_potrf_clock[3] = clock64() - t3;
         }
     }
 }
@@ -206,6 +222,14 @@ __global__ void place_diag_inverse_kernel(const double* __restrict__ dinv, int64
 
 using namespace ipp;
 
+extern "C" int ipp_potrf_debug_clocks(int64_t out[4]) {
+    long long v[4];
+    IPP_CUDA(cudaDeviceSynchronize());
+    IPP_CUDA(cudaMemcpyFromSymbol(v, ipp::g_potrf_clock, sizeof(v)));
+    for (int i = 0; i < 4; ++i) out[i] = v[i];
+    return IPP_OK;
+}
+
 extern "C" int64_t ipp_potrf_workspace(int64_t N) { return ((N + NB - 1) / NB + 1) * NB * NB + 16; }
 
 extern "C" int ipp_potrf_lower(double* A, int64_t N, int64_t lda, double* logdet, int32_t* info, double* work,
@@ -231,21 +255,34 @@ static int pdinv_device(double* Lf, int64_t N, int64_t lda, double* winv, double
     IPP_CUDA(cudaMemsetAsync(U, 0, sizeof(double) * N * ld, s));
     place_diag_inverse_kernel<<<(unsigned)((N + NB - 1) / NB), 256, 0, s>>>(dinv, N, Linv, ldl, U, ld);
     IPP_LAUNCH_CHECK();
+    // Doubling: at block size b the pairs (rows r0 + b .., columns r0 ..), r0 = 0, 2b, 4b, ... are independent.  All FULL
+    // pairs of a level go out as one batched launch per product (the r1 version launched every pair on its own: 126
+    // launches at N = 4096, most of them far too small to fill the GPU, 4.9 of the 12.9 ms of a refresh); a ragged last
+    // pair (N not a multiple of 2b) follows on its own.  Tt holds (L21 Linv11)^T of pair r0 in its rows r0 .. r0 + b.
     for (int64_t b = NB; b < N; b *= 2) {
-        for (int64_t r0 = 0; r0 + b < N; r0 += 2 * b) {
-            const int64_t b2 = (N - r0 - b) < b ? (N - r0 - b) : b;
+        const int64_t pairs = (N - b + 2 * b - 1) / (2 * b);            // r0 + b < N
+        const int64_t last_r0 = (pairs - 1) * 2 * b;
+        const int64_t last_b2 = (N - last_r0 - b) < b ? (N - last_r0 - b) : b;
+        const int64_t full = last_b2 == b ? pairs : pairs - 1;
+        for (int part = 0; part < 2; ++part) {
+            const int64_t r0 = part == 0 ? 0 : last_r0;
+            const int64_t nb = part == 0 ? full : (full < pairs ? 1 : 0);
+            const int64_t b2 = part == 0 ? b : last_b2;
+            if (nb <= 0) continue;
             GemmArgs g{};                               // Tt = (L21 * Linv11)^T  [b][b2]
             g.A = Lf + (r0 + b) * lda + r0; g.lda = lda;
             g.B = U + r0 * ld + r0; g.ldb = ld;
-            g.C = nullptr; g.Ct = Tt; g.ldct = ld;
+            g.C = nullptr; g.Ct = Tt + r0 * ld; g.ldct = ld;
             g.M = (int)b2; g.N = (int)b; g.K = (int)b; g.alpha = 1.0; g.beta = 0.0;
+            g.batch = (int)nb; g.sA = 2 * b * lda + 2 * b; g.sB = 2 * b * ld + 2 * b; g.sC = 0; g.sCt = 2 * b * ld;
             IPP_TRY(launch_gemm(g, s));
             GemmArgs h{};                               // Linv21 = -Linv22 * T, and its transpose into U
             h.A = Linv + (r0 + b) * ldl + (r0 + b); h.lda = ldl;
-            h.B = Tt; h.ldb = ld;
+            h.B = Tt + r0 * ld; h.ldb = ld;
             h.C = Linv + (r0 + b) * ldl + r0; h.ldc = ldl;
             h.Ct = U + r0 * ld + (r0 + b); h.ldct = ld;
             h.M = (int)b2; h.N = (int)b; h.K = (int)b2; h.alpha = -1.0; h.beta = 0.0;
+            h.batch = (int)nb; h.sA = 2 * b * ldl + 2 * b; h.sB = 2 * b * ld; h.sC = 2 * b * ldl + 2 * b; h.sCt = 2 * b * ld + 2 * b;
             IPP_TRY(launch_gemm(h, s));
         }
     }

@@ -7,6 +7,12 @@ namespace ipp {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (blockIdx.z) {                                    // batched: the same shape on operands a fixed stride apart
+        p.A += (int64_t)blockIdx.z * p.sA;
+        p.B += (int64_t)blockIdx.z * p.sB;
+        if (p.C) p.C += (int64_t)blockIdx.z * p.sC;
+        if (p.Ct) p.Ct += (int64_t)blockIdx.z * p.sCt;
+    }
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if (p.lower_only && n0 >= m0 + BM) return;
     const uint32_t smem_base = smem_u32(smem_raw);
@@ -64,7 +70,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
                   "C must be 16-byte aligned with even ldc");
     IPP_CHECK_ARG(g.C != nullptr || g.beta == 0.0, "beta != 0 needs C");
     IPP_OPT_IN_SMEM(dgemm_nt_kernel, GEMM_SMEM);
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, 1);
+    IPP_CHECK_ARG(g.batch <= 1 || (g.sA % 2 == 0 && g.sB % 2 == 0 && g.sC % 2 == 0), "batch strides must keep 16-byte alignment");
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch > 1 ? g.batch : 1);
     dgemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g);
     IPP_LAUNCH_CHECK();
     return IPP_OK;

@@ -50,6 +50,8 @@ struct GemmArgs {
     int lower_only;      // skip output tiles that lie strictly above the block diagonal
     int k_from_max;      // contraction starts at max(m0, n0) (product of two upper-triangular-stored factors)
     int k_to_min;        // contraction ends at min(m0, n0) + tile (product with lower-triangular operands)
+    int batch;           // > 1: blockIdx.z = problem index; operand / result z starts sA, sB, sC, sCt elements further on
+    int64_t sA, sB, sC, sCt;
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 

@@ -602,7 +602,9 @@ extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
     if (M <= 0) return 16;
     const int64_t ldc = round_up(M, 2);
     const int64_t four_kernels = 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
-    return four_kernels;                // the one-launch form (<= 32 points) keeps its partial sums in library-owned accumulators
+    const int64_t Mf = M < 32 ? M : 32;
+    const int64_t fused = (int64_t)ipp::sm_count() * (Mf * (Mf + 1) / 2 + Mf) + 16;    // one partial per CTA, <= 1 CTA per SM
+    return four_kernels > fused ? four_kernels : fused;
 }
 
 namespace ipp {
@@ -650,6 +652,7 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         fa.kern = to_dev(*kern);
         fa.X = X; fa.alpha = alpha; fa.W = winv; fa.ldw = ldw; fa.N = (int)N;
         fa.pts = pts; fa.zobs = zobs; fa.use_inline = inline_pts ? 1 : 0;
+        fa.part = work;
         fa.slot = (int)(__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % RF_SLOTS);
         fa.tag = 0;
         if (tagged_out && tag) {                          // results as self-validating records, no completion word

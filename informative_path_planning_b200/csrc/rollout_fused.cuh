@@ -13,10 +13,9 @@
 //     and when the column ends the accumulator fragments ARE the A operand of the second contraction (k permutation:
 //     thread t of a quad owns columns 2t, 2t+1 in both), so  A += U_J K_J^T  needs no shared-memory round trip;
 //   * on the diagonal tile the CTA also adds K_J alpha_J to its partial mean;
-//   * every CTA adds its partial (A + A^T lower triangle and the mean: M (M + 1) / 2 + M numbers) into 128-bit fixed-point
-//     accumulators -- exact integer sums, so the result does not depend on the order of arrival --; the last CTA to
-//     finish (a ticket counter) reads the totals, forms C0 = Kqq - (A + A^T) and m0, and runs the level-by-level
-//     conditioning in the same launch;
+//   * every CTA stores its partial (A + A^T lower triangle and the mean: M (M + 1) / 2 + M doubles), the last one to finish
+//     (a ticket counter) sums the partials in CTA order -- a fixed order, so the result does not depend on timing --,
+//     forms C0 = Kqq - (A + A^T) and m0, and runs the level-by-level conditioning in the same launch;
 //   * the rewards are not evaluated inside the sequential conditioning: each level's predictive moments are snapshot when
 //     the level is reached and all levels are scored in parallel (one warp per level) at the end.
 #pragma once
@@ -24,35 +23,9 @@
 namespace ipp {
 
 constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8;
-constexpr int RF_SLOTS = 16;                            // rollouts in flight per device (each launch takes the next slot)
-constexpr int RF_VMAX = 32 * 33 / 2 + 32;               // partial sums per rollout: A + A^T lower triangle and the mean, M <= 32
+constexpr int RF_SLOTS = 256;                           // ticket counters; each launch takes the next one
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
-// The CTAs' partial sums meet in FIXED-POINT accumulators (units of 2^-70): integer addition is associative, so the total
-// is exact and independent of the order in which the CTAs arrive -- deterministic like a fixed-order sum, but the
-// finishing CTA reads V numbers instead of V x (number of CTAs) (7.5k -> ~2k SM clocks at N = 900, 120 CTAs).  A value is
-// cut into three 42-bit limbs held in 64-bit words: 22 bits of headroom per word absorb the carries of up to 2^21 CTAs,
-// so every add is a fire-and-forget reduction (no returned value to wait for); the finishing CTA propagates the carries.
-// Zero at load, put back to zero by the finishing CTA.  g_rf_nonfinite: some partial was NaN / Inf / out of range.
-__device__ long long g_rf_acc[RF_SLOTS][3 * RF_VMAX];
 __device__ long long g_rf_clock[32];                     // SM clocks of the finishing CTA per phase (ipp_rollout_debug_clocks)
-__device__ unsigned int g_rf_nonfinite[RF_SLOTS];
-
-__device__ __forceinline__ void rf_accumulate(long long* acc, double x) {
-    const double y = x * 0x1p70;                         // exact: |x| < 2^56
-    const double h2 = floor(y * 0x1p-84);                // signed top limb
-    const double r1 = fma(-h2, 0x1p84, y);               // in [0, 2^84), exact
-    const double h1 = floor(r1 * 0x1p-42);
-    const double h0 = fma(-h1, 0x1p42, r1);              // in [0, 2^42)
-    atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__double2ll_rz(h0));
-    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 1), (unsigned long long)__double2ll_rz(h1));
-    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2), (unsigned long long)__double2ll_rz(h2));
-}
-__device__ __forceinline__ double rf_total(long long l0, long long l1, long long l2) {
-    l1 += l0 >> 42;  l0 &= (1ll << 42) - 1;              // carries upwards (arithmetic shifts: limbs may be negative)
-    l2 += l1 >> 42;  l1 &= (1ll << 42) - 1;
-    // l2 2^84 + l1 2^42 + l0: the two low limbs are < 2^42 and exact in double; one rounding per addition
-    return fma((double)l2, 0x1p84, fma((double)l1, 0x1p42, (double)l0)) * 0x1p-70;
-}
 
 // The rollout's points and observations by value: [M][D] points, then [M] observations (M <= 32 in this kernel: 1 KB of
 // kernel parameters instead of the 3 KB RolloutInline of the four-kernel form).
@@ -70,6 +43,7 @@ struct RolloutFusedArgs {
     const double* X; const double* alpha; const double* W; int64_t ldw; int N;
     const double* pts; const double* zobs;               // device copies (used when use_inline == 0)
     int use_inline;
+    double* part;                                        // [gridDim.x][V], V = M (M + 1) / 2 + M
     int slot, tiles, T;
     unsigned long long tag;                              // != 0: r.reward holds 16-byte {value, tag} records, L rewards then info
     RolloutArgs r;
@@ -230,10 +204,11 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
         }
         if (l == p.L - 1) break;                  // the last level's observation is never looked at again
         if (p.reps[l] > 0 && kb <= 4) {
-            // every thread factors the (identity-padded) 4 x 4 block redundantly in registers and substitutes its own row
+            // every thread factors the (identity-padded) 4 x 4 block redundantly in registers and substitutes its own row.
+            // Only the points AFTER this block are ever looked at again: rows / columns >= b1.  (No barrier here: the
+            // snapshot above only reads what the barrier that ended the previous level made final.)
             const double dadd = p.diag_add / (double)p.reps[l];
-            const int R = M - b0;
-            __syncthreads();
+            const int b1 = b0 + kb, R = M - b1;
             double Lf[4][4], rd[4], u[4];
             int bad = 0;
 #pragma unroll
@@ -262,7 +237,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                 u[a] = v * rd[a];
             }
             if (bad && tid == 0) s_bad = bad;
-            const int i = b0 + tid;               // this thread's point (M <= 32 < RF_THREADS: at most one)
+            const int i = b1 + tid;               // this thread's point (M <= 32 < RF_THREADS: at most one)
             double dm = 0.0;
             if (i < M) {
                 double h[4];
@@ -278,14 +253,25 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
             }
             __syncthreads();
             if (i < M) m[i] += dm;
-            // C -= H H^T on the rows / columns that are still ahead: thread -> (ii, jj) without a division (R <= 32)
-            for (int ii = b0 + warp; ii < M; ii += RF_WARPS) {
-                const int jj = b0 + lane;
-                if (lane < R) {
+            // C -= H H^T on the rows / columns that are still ahead.  R <= 16 (the usual case): 16 threads per row, all rows
+            // in one pass; else a warp per row
+            if (R <= 16) {
+                const int ii = b1 + (tid >> 4), jj = b1 + (tid & 15);
+                if (ii < M && jj < M) {
                     double sacc = 0.0;
 #pragma unroll
                     for (int a = 0; a < 4; ++a) sacc = fma(H[ii * HL + a], H[jj * HL + a], sacc);
                     C[ii * ldc + jj] -= sacc;
+                }
+            } else {
+                for (int ii = b1 + warp; ii < M; ii += RF_WARPS) {
+                    const int jj = b1 + lane;
+                    if (lane < R) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) sacc = fma(H[ii * HL + a], H[jj * HL + a], sacc);
+                        C[ii * ldc + jj] -= sacc;
+                    }
                 }
             }
         } else if (p.reps[l] > 0) {
@@ -349,7 +335,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     const int M = q.r.M, N = q.N, T = q.T;
     const long long clk0 = clock64();
 
-    for (int i = tid; i < M * D; i += RF_THREADS) s_pts[i] = q.use_inline ? pp.v[i] : q.pts[i];
+    if (q.use_inline) {          // parameter space is constant memory: every thread reads the SAME word (a broadcast;
+        for (int i = 0; i < M * D; ++i) {                 // thread-dependent indices would be replayed address by address)
+            const double v = pp.v[i];
+            if (tid == (i & (RF_THREADS - 1))) s_pts[i] = v;
+        }
+    } else {
+        for (int i = tid; i < M * D; i += RF_THREADS) s_pts[i] = q.pts[i];
+    }
     if (tid < P) s_m0[tid] = 0.0;
     __syncthreads();
 
@@ -389,14 +382,18 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
             v[r] = 0.0;
             if (a < M) v[r] = n < N ? rf_rbf<D>(q.kern, s_pts + a * D, x) : 0.0;
         }
+        // element (a, jj) with a = a0 + 4 r, i.e. a >> 3 = r >> 1 and a & 7 = a0 + 4 (r & 1): everything that depends on
+        // the thread is hoisted, what depends on r is a compile-time constant of the unrolled loop
+        //   A operand image: ((((a>>3) 2 + c) 4 + qq) 32 + 4 (a&7) + tt) 2 + e,  jj = 32 c + 8 tt + 2 qq + e
+        //   B operand image: (((a>>3) 8 + w) 32 + 4 (a&7) + tt') 2 + e,          jj = 8 w + 2 tt' + e
+        const int ta = ((((jj >> 5) * 4 + ((jj >> 1) & 3)) * 32 + 4 * a0 + ((jj >> 3) & 3)) * 2) + (jj & 1);
+        const int tb = (((jj >> 3) * 32 + 4 * a0 + ((jj >> 1) & 3)) * 2) + (jj & 1);
 #pragma unroll
         for (int r = 0; r < 2 * NT; ++r) {
-            const int a = a0 + 4 * r;
-            if (frag_a)     // element (a, ii = 32 c + 8 tt + 2 qq + e) -> ((((mt 2 + c) 4 + qq) 32 + 4 g' + tt) 2 + e
-                frag_a[((((a >> 3) * 2 + (jj >> 5)) * 4 + ((jj >> 1) & 3)) * 32 + 4 * (a & 7) + ((jj >> 3) & 3)) * 2 + (jj & 1)] = scale * v[r];
-            if (frag_b) {   // element (b, jj = 8 w + 2 tt + e) -> (((nt 8 + w) 32 + 4 g' + tt) 2 + e
-                frag_b[(((a >> 3) * 8 + (jj >> 3)) * 32 + 4 * (a & 7) + ((jj >> 1) & 3)) * 2 + (jj & 1)] = v[r];
-                plain[a * RF_B + jj] = v[r];
+            if (frag_a) frag_a[ta + (r >> 1) * 512 + (r & 1) * 32] = scale * v[r];
+            if (frag_b) {
+                frag_b[tb + (r >> 1) * 512 + (r & 1) * 32] = v[r];
+                plain[(a0 + 4 * r) * RF_B + jj] = v[r];
             }
         }
     };
@@ -499,8 +496,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         }
     __syncthreads();
     const int V = M * (M + 1) / 2 + M;
-    long long* acc = g_rf_acc[q.slot];
-    bool finite = true;
+    double* mine = q.part + (size_t)blockIdx.x * V;
     for (int a = warp; a < M; a += RF_WARPS)              // pairs b <= a: lane = b (M <= 32)
         if (lane <= a) {
             double s_ab = 0.0, s_ba = 0.0;
@@ -509,16 +505,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
                 s_ab += s_z8[w * P * P + a * P + lane];
                 s_ba += s_z8[w * P * P + lane * P + a];
             }
-            const double v = s_ab + s_ba;
-            finite = finite && (fabs(v) < 0x1p56);        // also false for NaN
-            rf_accumulate(acc + 3 * (a * (a + 1) / 2 + lane), finite ? v : 0.0);
+            mine[a * (a + 1) / 2 + lane] = s_ab + s_ba;
         }
-    if (tid < M) {
-        const double v = s_m0[tid];
-        finite = finite && (fabs(v) < 0x1p56);
-        rf_accumulate(acc + 3 * (M * (M + 1) / 2 + tid), finite ? v : 0.0);
-    }
-    if (!finite) atomicOr(&g_rf_nonfinite[q.slot], 1u);
+    if (tid < M) mine[M * (M + 1) / 2 + tid] = s_m0[tid];
     const long long clk1 = clock64();
     __threadfence();
     __syncthreads();
@@ -541,11 +530,28 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     double* snap_v = snap_m + M;
     double* Cs = snap_v + M;                              // [M][M+1] (information gain: the levels' blocks)
     __syncthreads();                                      // s_z8 (same memory as C) has been consumed by everybody
-    const bool poisoned = __ldcg(&g_rf_nonfinite[q.slot]) != 0u;
     for (int v = tid; v < V; v += RF_THREADS) {
-        const long long l0 = __ldcg(acc + 3 * v), l1 = __ldcg(acc + 3 * v + 1), l2 = __ldcg(acc + 3 * v + 2);
-        acc[3 * v] = acc[3 * v + 1] = acc[3 * v + 2] = 0ll;        // the slot is clean for its next rollout
-        const double tot = poisoned ? nan("") : rf_total(l0, l1, l2);
+        // fixed order over the CTAs -- the result does not depend on their timing --, 32 independent loads in flight.
+        // (Tried: exact 128-bit fixed-point accumulators fed by atomics, so that only V numbers are read here: the
+        // atomics of ~120 CTAs on the same V addresses cost more than this sum saves, profiles/r2g_*.)
+        const double* src = q.part + v;
+        double acc[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) acc[u] = 0.0;
+        int c = 0;
+        for (; c + 32 <= G; c += 32) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc[u] += __ldcg(src + (size_t)(c + u) * V);
+        }
+        if (c < G) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc[u] += (c + u < G) ? __ldcg(src + (size_t)(c + u) * V) : 0.0;
+        }
+#pragma unroll
+        for (int w = 16; w > 0; w >>= 1)                  // pairwise: five dependent additions instead of 31
+#pragma unroll
+            for (int u = 0; u < w; ++u) acc[u] += acc[u + w];
+        const double tot = acc[0];
         if (v < M * (M + 1) / 2) {
             int a = (int)((sqrt(8.0 * v + 1.0) - 1.0) * 0.5);
             while (a * (a + 1) / 2 > v) --a;
@@ -558,9 +564,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
             m[v - M * (M + 1) / 2] = tot;
         }
     }
-    for (int i = tid; i < M; i += RF_THREADS) s_z[i] = q.use_inline ? pp.v[M * D + i] : q.zobs[i];
-    __syncthreads();
-    if (tid == 0 && poisoned) g_rf_nonfinite[q.slot] = 0u;
+    if (q.use_inline) {
+        for (int i = 0; i < M; ++i) {
+            const double v = pp.v[M * D + i];
+            if (tid == i) s_z[i] = v;
+        }
+    } else {
+        for (int i = tid; i < M; i += RF_THREADS) s_z[i] = q.zobs[i];
+    }
     const long long clk3 = clock64();
     rf_condition(q.r, s_z, C, m, H, snap_m, snap_v, Cs, s_bad, q.tag);
     if (tid == 0) {

@@ -71,6 +71,10 @@ def main():
         m, rng = model(4096)
         for _ in range(reps):
             m._factor(want_linv=False)
+        import ctypes
+        clk = np.zeros(4, dtype=np.int64)
+        L.check(L.lib.ipp_potrf_debug_clocks(clk.ctypes.data_as(ctypes.c_void_p)))
+        print('last diagonal block, SM clocks: load %d, pivots %d, inverse %d, store %d' % tuple(clk))
     else:
         raise SystemExit('unknown target ' + target)
     torch.cuda.synchronize()
