@@ -563,8 +563,37 @@ static int rollout_fused_launch(const RolloutFusedArgs& fa, const RolloutInline*
     IPP_OPT_IN_SMEM((rollout_fused_kernel<D, NT>), bytes);
     RolloutInlineSmall small;
     if (inl) memcpy(small.v, inl->v, sizeof(double) * (size_t)fa.r.M * (D + 1));      // [M][D] points, then [M] observations
-    rollout_fused_kernel<D, NT><<<grid, RF_THREADS, bytes, stream>>>(fa, small);
-    IPP_LAUNCH_CHECK();
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = RF_CLUSTER;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(RF_THREADS);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = stream;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    // clusters of RF_CLUSTER CTAs only while all of them are resident at once (fewer whole clusters than single CTAs fit:
+    // each needs RF_CLUSTER free SMs in one GPC); otherwise every CTA is its own cluster
+    static int max_clusters[64];                          // per device; 0 = not asked yet
+    int dev = 0;
+    IPP_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
+        cfg.gridDim = dim3((unsigned)(sm_count() / RF_CLUSTER * RF_CLUSTER));
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, rollout_fused_kernel<D, NT>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = -1; }
+        max_clusters[dev] = n;
+    }
+    const int fit = (dev >= 0 && dev < 64) ? max_clusters[dev] : -1;
+    int g = grid;
+    if (fit > 0 && (grid + RF_CLUSTER - 1) / RF_CLUSTER <= fit) {
+        g = (grid + RF_CLUSTER - 1) / RF_CLUSTER * RF_CLUSTER;         // whole clusters; surplus CTAs get no tiles
+    } else {
+        attr.val.clusterDim.x = 1;
+    }
+    cfg.gridDim = dim3((unsigned)g);
+    IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_fused_kernel<D, NT>, fa, small));
     return IPP_OK;
 }
 

@@ -19,10 +19,14 @@
 //   * the rewards are not evaluated inside the sequential conditioning: each level's predictive moments are snapshot when
 //     the level is reached and all levels are scored in parallel (one warp per level) at the end.
 #pragma once
+#include <cooperative_groups.h>
 
 namespace ipp {
 
+namespace cg = cooperative_groups;
+
 constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8;
+constexpr int RF_CLUSTER = 4;                           // CTAs per thread-block cluster: their partials meet in shared memory
 constexpr int RF_SLOTS = 256;                           // ticket counters; each launch takes the next one
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
 __device__ long long g_rf_clock[32];                     // SM clocks of the finishing CTA per phase (ipp_rollout_debug_clocks)
@@ -43,7 +47,7 @@ struct RolloutFusedArgs {
     const double* X; const double* alpha; const double* W; int64_t ldw; int N;
     const double* pts; const double* zobs;               // device copies (used when use_inline == 0)
     int use_inline;
-    double* part;                                        // [gridDim.x][V], V = M (M + 1) / 2 + M
+    double* part;                                        // [clusters][V], V = M (M + 1) / 2 + M
     int slot, tiles, T;
     unsigned long long tag;                              // != 0: r.reward holds 16-byte {value, tag} records, L rewards then info
     RolloutArgs r;
@@ -90,8 +94,8 @@ __device__ __forceinline__ double rf_rbf(const RbfDev& k, const double* a, const
 template <int NT>
 constexpr int rf_smem_doubles() {
     constexpr int P = 8 * NT;
-    //      points  K_I images (2)    K_J image + plain copy   mean  obs
-    return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + 8;
+    //      points  K_I images (2)    K_J image + plain copy   mean  obs   this CTA's partial (read by its cluster leader)
+    return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + (P * (P + 1) / 2 + P) + 8;
 }
 
 // All levels scored in parallel from the snapshots: warp w takes levels w, w + 8, ...  Called by every thread after a
@@ -330,6 +334,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     double* s_kp = s_kj + P * RF_B;                      // [P][64]     the same, plain (mean on the diagonal tile)
     double* s_m0 = s_kp + P * RF_B;                      // [P]
     double* s_z = s_m0 + P;                              // [P]         observations
+    double* s_part = s_z + P;                            // [V]         this CTA's partial: A + A^T lower triangle, then the mean
     __shared__ int s_last, s_bad;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int M = q.r.M, N = q.N, T = q.T;
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         I = In; J = Jn;
         if (k == k0) tk[4] = clock64();
     }
-    fold();
+    if (k0 < k1) fold();                                  // (a CTA without tiles only pads its cluster: its partial is zero)
     __syncthreads();
     tk[5] = clock64();
 
@@ -496,7 +501,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         }
     __syncthreads();
     const int V = M * (M + 1) / 2 + M;
-    double* mine = q.part + (size_t)blockIdx.x * V;
     for (int a = warp; a < M; a += RF_WARPS)              // pairs b <= a: lane = b (M <= 32)
         if (lane <= a) {
             double s_ab = 0.0, s_ba = 0.0;
@@ -505,15 +509,35 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
                 s_ab += s_z8[w * P * P + a * P + lane];
                 s_ba += s_z8[w * P * P + lane * P + a];
             }
-            mine[a * (a + 1) / 2 + lane] = s_ab + s_ba;
+            s_part[a * (a + 1) / 2 + lane] = s_ab + s_ba;
         }
-    if (tid < M) mine[M * (M + 1) / 2 + tid] = s_m0[tid];
+    if (tid < M) s_part[M * (M + 1) / 2 + tid] = s_m0[tid];
+    // ---- the RF_CLUSTER partials of a thread-block cluster meet in its leader through distributed shared memory (fixed
+    // rank order): the finishing CTA then reads a quarter of the partials.  That read is one SM pulling V x (number of
+    // partials) doubles through its L2 port and was the longest single step of a rollout at N = 900 (7.5k SM clocks).
+    // (Large beliefs are launched with clusters of ONE CTA: whole clusters need RF_CLUSTER free SMs in one GPC, fewer of
+    // them are co-resident than single CTAs, and there the partial sum is a small part of the rollout.)
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int crank = cluster.block_rank(), csize = cluster.num_blocks();
+    if (csize > 1) cluster.sync();
+    else __syncthreads();                                 // s_part complete before anybody sums it
+    if (crank == 0) {
+        double* mine = q.part + (size_t)(blockIdx.x / csize) * V;
+        for (int v = tid; v < V; v += RF_THREADS) {
+            double tot = s_part[v];
+            for (unsigned int r = 1; r < csize; ++r) tot += cluster.map_shared_rank(s_part, r)[v];
+            mine[v] = tot;
+        }
+    }
+    if (csize > 1) cluster.sync();                        // the members' shared memory stays alive until the leader has read it
+    if (crank != 0) return;
+    const int GC = G / (int)csize;                        // partials = clusters
     const long long clk1 = clock64();
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned int old = atomicAdd(&g_rf_ticket[q.slot], 1u);
-        s_last = (old == (unsigned int)(G - 1));
+        s_last = (old == (unsigned int)(GC - 1));
         if (s_last) g_rf_ticket[q.slot] = 0u;             // everybody has arrived: the slot is free again
     }
     __syncthreads();
@@ -531,7 +555,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     double* Cs = snap_v + M;                              // [M][M+1] (information gain: the levels' blocks)
     __syncthreads();                                      // s_z8 (same memory as C) has been consumed by everybody
     for (int v = tid; v < V; v += RF_THREADS) {
-        // fixed order over the CTAs -- the result does not depend on their timing --, 32 independent loads in flight.
+        // fixed order over the clusters -- the result does not depend on their timing --, 32 independent loads in flight.
         // (Tried: exact 128-bit fixed-point accumulators fed by atomics, so that only V numbers are read here: the
         // atomics of ~120 CTAs on the same V addresses cost more than this sum saves, profiles/r2g_*.)
         const double* src = q.part + v;
@@ -539,13 +563,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
 #pragma unroll
         for (int u = 0; u < 32; ++u) acc[u] = 0.0;
         int c = 0;
-        for (; c + 32 <= G; c += 32) {
+        for (; c + 32 <= GC; c += 32) {
 #pragma unroll
             for (int u = 0; u < 32; ++u) acc[u] += __ldcg(src + (size_t)(c + u) * V);
         }
-        if (c < G) {
+        if (c < GC) {
 #pragma unroll
-            for (int u = 0; u < 32; ++u) acc[u] += (c + u < G) ? __ldcg(src + (size_t)(c + u) * V) : 0.0;
+            for (int u = 0; u < 32; ++u) acc[u] += (c + u < GC) ? __ldcg(src + (size_t)(c + u) * V) : 0.0;
         }
 #pragma unroll
         for (int w = 16; w > 0; w >>= 1)                  // pairwise: five dependent additions instead of 31

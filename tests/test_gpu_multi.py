@@ -50,6 +50,14 @@ def _worker(rank, size, port, tmp):
         out[mode + '_mu'], out[mode + '_var'] = mu, var
         out[mode + '_ucb'] = parallel.reward_paths_sharded(m, 'mean', 5, pts, offs)
         out[mode + '_mes'] = parallel.reward_paths_sharded(m, 'mes', 5, pts, offs, param=(np.array([[20.], [25.]]), None, None))
+        # a tensor-mode predict caches operands cut for the current N; the next replicated append must drop them on EVERY
+        # rank (the non-source ranks of 'broadcast' mode go through attach_state_shell) -- ADVICE r1
+        m.predict_precision = 'i8x6'
+        parallel.predict_sharded(m, q)
+        parallel.add_data_replicated(m, q[:7] if rank == 0 else None, np.ones((7, 1)) if rank == 0 else None, mode=mode)
+        out[mode + '_i8_mu'], out[mode + '_i8_var'] = parallel.predict_sharded(m, q)
+        m.predict_precision = 'fp64'
+        out[mode + '_i8_ref_var'] = parallel.predict_sharded(m, q)[1]
     # root-parallel tree search (config 2 sharding): replicated belief, budget split, one all_reduce of root statistics
     import contextlib
     import io
@@ -95,6 +103,7 @@ def test_two_ranks_match_one_gpu(tmp_path):
         np.testing.assert_array_equal(r0[mode + '_var'], var)
         np.testing.assert_allclose(r0[mode + '_ucb'], ucb, rtol=1e-12)
         np.testing.assert_allclose(r0[mode + '_mes'], mes, rtol=1e-12)
+        np.testing.assert_allclose(r0[mode + '_i8_var'], r0[mode + '_i8_ref_var'], rtol=1e-6)    # operands of the NEW belief
     for f_rew in ('mean', 'mes'):
         l0, l1 = np.load(tmp_path / ('mcts_%s_local0.npy' % f_rew)), np.load(tmp_path / ('mcts_%s_local1.npy' % f_rew))
         g = r0['mcts_' + f_rew + '_global']

@@ -665,7 +665,7 @@ def test_info_gain_rollouts_match_sequential_appends(pkg, n_obs, sizes):
             fork.add_data(pts, zo); o.add_data(pts, zo)
 
 
-@pytest.mark.parametrize('n_obs', [1, 63, 64, 65, 150, 900, 1500])
+@pytest.mark.parametrize('n_obs', [1, 63, 64, 65, 150, 900, 1500, 2500])
 @pytest.mark.parametrize('sizes', [[4, 4, 4, 4, 4], [3], [8, 8, 8, 6], [12, 12, 12, 12, 2], [1, 1, 1]])
 def test_fused_rollout_kernel_equals_the_four_kernel_sequence(pkg, n_obs, sizes):
     """The one-launch rollout (lower tiles of W^-1 only, per-CTA partials summed in CTA order by the last CTA, conditioning
@@ -1201,3 +1201,56 @@ def test_native_tree_search_space_time_belief(pkg, tree_type, f_rew):
         res[native] = ([c.nqueries for c in kids], [c.reward for c in kids], out[0], random.random(), np.random.standard_normal(2))
     a, b = res[True], res[False]
     assert a[0] == b[0] and sum(a[0]) == 80 and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and np.array_equal(a[4], b[4])
+
+
+def test_attach_state_shell_drops_tensor_mode_operands(pkg):
+    """parallel.add_data_replicated(mode='broadcast') adopts a refreshed state on the non-source ranks through
+    attach_state_shell: operands cut for the previous N by an earlier 'i8x6' predict must not survive, and an
+    update_legacy model gets its L^-1 buffer from a rank-independent rule.  Single process: the shell is filled by copy."""
+    rng = np.random.default_rng(12)
+    X, z = world(rng, 200, 0.5)
+    src = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    dst = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    for m in (src, dst):
+        m.add_data(X[:150], z[:150])
+        m.predict_precision = 'i8x6'
+    q = rng.uniform(0, 10, (300, 2))
+    dst.predict_value(q)                                    # caches int8 slices of L^-1 for N = 150
+    assert dst._i8
+    src.add_data(X[150:], z[150:])
+    dst.attach_state_shell(X[150:], z[150:])
+    assert dst._i8 is None and dst._tf32 is None and dst._pending_info == []
+    assert len(src.state_tensors()) == len(dst.state_tensors())
+    for a, b in zip(src.state_tensors(), dst.state_tensors()):
+        b.copy_(a)                                          # what the NCCL broadcast does
+    np.testing.assert_array_equal(dst.predict_value(q)[1], src.predict_value(q)[1])
+    leg_src = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5, update_legacy=True)
+    leg_dst = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5, update_legacy=True)
+    leg_src.add_data(X[:50], z[:50])
+    leg_dst.attach_state_shell(X[:50], z[:50])              # first add: the source allocated L^-1, so must the shell
+    assert len(leg_src.state_tensors()) == len(leg_dst.state_tensors())
+
+
+def test_info_gain_of_paths_longer_than_the_batched_kernel_takes(pkg):
+    """info_gain handles a path of any length (reference aq_library.py:34-80); the one-warp-per-path Schur kernel factors
+    at most 32 points in shared memory, longer paths go through the blocked GEMM + Cholesky route (they used
+    to come back as NaN without an error).  Mixed batch: 5, 40 and 70 points."""
+    aqo, gpo, _ = _oracle()
+    aq = pkg.aq_library
+    rng = np.random.default_rng(3)
+    X, z = world(rng, 120, 0.5)
+    d = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    o = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    d.add_data(X, z); o.add_data(X, z)
+    paths = [rng.uniform(0.5, 9.5, (k, 2)) for k in (5, 40, 70, 3)]
+    got = aq.reward_paths('info_gain', 2, paths, d)
+    want = np.array([aqo.info_gain(2, p, o) for p in paths])
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(aq.info_gain(time=2, xvals=paths[1], robot_model=d), want[1], rtol=1e-6, atol=1e-5)
+    # hotspot_info with no data: info_gain's prior branch + sqrt(beta) * k * variance (the reference calls predict_value)
+    empty = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    oe = gpo.OnlineGPModelOracle(RANGES, 1.0, 100.0, noise=0.5)
+    np.testing.assert_allclose(aq.hotspot_info_UCB(time=2, xvals=paths[0], robot_model=empty),
+                               aqo.hotspot_info_UCB(2, paths[0], oe), rtol=1e-9)
+    np.testing.assert_allclose(aq.reward_paths('hotspot_info', 2, paths[:1], empty)[0], aqo.hotspot_info_UCB(2, paths[0], oe), rtol=1e-9)
