@@ -650,52 +650,9 @@ def main():
                 'note': 'shortest Dubins curves (goal 3.0 ahead, rho 0.3, samples every 0.5, border-trimmed), FP64 rewards'}
         except Exception as e:
             extras['dubins_on_device_N4096'] = {'error': repr(e)}
-        # BASELINE config 3, second arm: 3xTF32 mode (tcgen05 kind::tf32, Cholesky form) on the same belief / queries
-        try:
-            mu64, var64 = model.predict_device(xq)
-            model.predict_device(xq, precision='tf32x3')
-            torch.cuda.synchronize()
-            L.check(L.lib.ipp_profile_enable(1))
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record()
-            for _ in range(3):
-                mu32, var32 = model.predict_device(xq, precision='tf32x3')
-            r1.record()
-            torch.cuda.synchronize()
-            k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
-            L.check(L.lib.ipp_profile_read(ctypes.byref(k_ms), ctypes.byref(k_n)))
-            L.check(L.lib.ipp_profile_enable(0))
-            ms32 = r0.elapsed_time(r1) / 3
-            torch.backends.cuda.matmul.allow_tf32 = True
-            a32 = torch.randn(8192, 8192, device='cuda'); b32 = torch.randn(8192, 8192, device='cuda')
-            best32 = None
-            for i in range(6):
-                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s0.record(); torch.matmul(a32, b32); s1.record(); torch.cuda.synchronize()
-                if i:
-                    best32 = s0.elapsed_time(s1) if best32 is None else min(best32, s0.elapsed_time(s1))
-            torch.backends.cuda.matmul.allow_tf32 = False
-            del a32, b32
-            tf32_peak = 2.0 * 8192 ** 3 / (best32 / 1e3) / 1e12
-            T_ = (N_OBS + 127) // 128
-            flops32 = 3 * 2.0 * 128 * 128 * T_ * (T_ + 1) / 2 * min(M, 32768)
-            kern_tf = flops32 / (k_ms.value / max(1, k_n.value) / 1e3) / 1e12
-            err = (var32 - var64).abs()
-            extras['tf32x3_N4096'] = {
-                'queries_per_s': M / (ms32 / 1e3), 'ms_per_step': ms32, 'speedup_vs_fp64_mode': (ms_fp64 / ms32) if ms_fp64 else None,
-                'acc_kblocks': int(model.tf32_acc_kblocks),
-                'kernel': 'predict_var_tf32_kernel (tcgen05.mma kind::tf32, TMA, TMEM; 3 products per MAC executed)',
-                'kernel_ms': k_ms.value / max(1, k_n.value), 'kernel_tflops_executed': kern_tf,
-                'cublas_tf32_tflops_measured': tf32_peak, 'frac_of_cublas_tf32': kern_tf / tf32_peak,
-                'mean_max_abs_diff_vs_fp64': float((mu32 - mu64).abs().max()),
-                'var_rel_err_max': float((err / var64).max()), 'var_rel_err_median': float((err / var64).median()),
-                'var_err_over_prior_variance_max': float(err.max()) / 100.0,
-                'note': 'misses the 1e-4 relative-variance target (SURVEY.md H1): reported beside, never instead of, the FP64 mode'}
-        except Exception as e:
-            extras['tf32x3_N4096'] = {'error': repr(e)}
         # BASELINE config 3, tensor arms on the INT8 tensor cores (tcgen05 kind::i8, exact INT32 accumulation, FP64 level
         # combine): 'i8x6' = six 7-bit slices per operand, 21 products -- FP64-grade (inside the FP64 mode's 1e-6 parity
-        # tolerance); 'i8x5' = five slices, 15 products on wider tiles -- ~4e-6, faster than and 200x more accurate than 3xTF32
+        # tolerance); 'i8x5' = five slices, 15 products on wider tiles -- ~4e-6: the split tensor mode of config 3 (the 3xTF32 arm of round 1 missed its 1e-4 tolerance and was removed)
         try:
             a8 = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
             b8 = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
@@ -743,8 +700,8 @@ def main():
                                 'precision solve where the FP64 DMMA mode is 2e-9 (profiles/r1i_check_large_N4096.json)',
                              6: 'FP64-grade: 42-bit operands; passes the FP64 mode parity tests '
                                 '(tests/test_gpu_parity.py::test_predict_i8x6_mode_is_fp64_grade); headline stays FP64 DMMA',
-                             5: 'fast tensor mode: 35-bit operands; the reduced-precision arm that replaces 3xTF32 (faster and '
-                                '~200x more accurate)'}[ns]}
+                             5: 'fast tensor mode: 35-bit operands; the split-precision arm of config 3 (faster and ~200x more '
+                                'accurate than the 3xTF32 arm of round 1, which was removed)'}[ns]}
             except Exception as e:
                 extras[prec + '_N4096'] = {'error': repr(e)}
         line['extra'] = extras

@@ -103,9 +103,6 @@ SIGNATURES = {
     'ipp_gp_append': (_INT, [_RBF, _P, _P, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _P, _P, _P]),
     'ipp_gp_predict_workspace': (_I64, [_I64, _I64]),
     'ipp_gp_predict': (_INT, [_RBF, _P, _I64, _P, _P, _I64, _INT, _D, _P, _I64, _P, _P, _P, _P]),
-    'ipp_tf32_split': (_INT, [_P, _I64, _I64, _I64, _P, _P, _I64, _P]),
-    'ipp_gp_predict_tf32_workspace': (_I64, [_I64, _I64]),
-    'ipp_gp_predict_tf32': (_INT, [_RBF, _P, _I64, _P, _P, _P, _I64, _INT, _D, _P, _I64, _P, _P, _P, _P]),
     'ipp_i8_slice_bytes': (_I64, [_I64, _I64, _INT]),
     'ipp_i8_slice': (_INT, [_P, _I64, _I64, _I64, _D, _INT, _P, _P]),
     'ipp_gp_predict_i8_workspace': (_I64, [_I64, _I64]),

@@ -46,7 +46,7 @@ int launch_gemv(const double* A, int64_t lda, int64_t rows, int64_t cols, const 
     return IPP_OK;
 }
 
-// Optional CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_tf32 (the fused variance
+// Optional CUDA-event timing of the dominant kernel of ipp_gp_predict / ipp_gp_predict_i8 (the fused variance
 // kernels), recorded on the launching stream.  Used by bench.py for the roofline figure; off by default.
 constexpr int PROFILE_MAX = 8192;
 static bool g_profile = false;

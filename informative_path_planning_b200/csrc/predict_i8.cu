@@ -13,7 +13,7 @@
 // tolerance with a wide margin (numpy emulation with exact integers agrees: 2.0e-8).
 //
 // Kernel: 128 x 64 tiles (6 levels x 64 columns of TMEM), 3 x 72 KB stages, 42 MMAs (128 x 64 x 32) per stage issued by
-// one thread, persistent warp-specialised CTA as in predict_tf32.cu.  Lower-triangular Linv: n-tile I contracts
+// one thread, persistent warp-specialised CTA.  Lower-triangular Linv: n-tile I contracts
 // k < 64 (I + 1).
 // Operand layout: the generators write the planes ALREADY in the shared-memory image of a stage -- tile-major
 // [row tile][k-block of 64][plane][rows][64 B] with the SWIZZLE_64B chunk permutation applied (16-byte chunk c of row r

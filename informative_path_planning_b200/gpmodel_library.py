@@ -125,10 +125,8 @@ class GPModel(object):
         self._linv_d = None        # [N][ld] L^-1 (GPy-form models only)
         self._ld = 0
         self._ig = None            # cached (binv, logdet_before) for info_gain
-        self._tf32 = None          # cached (linv_hi, linv_lo, ld) float32 split of L^-1 for the 3xTF32 predict
         self._i8 = None            # cached (planes, ld, scale) int8 slices of L^-1 for the sliced-INT8 predict
-        self.predict_precision = 'fp64'   # 'tf32x3': batched predicts run on the tcgen05 path (see predict_device)
-        self.tf32_acc_kblocks = 1         # tensor-core accumulation chunk of the 3xTF32 path (1 = most accurate)
+        self.predict_precision = 'fp64'   # 'i8x7' / 'i8x6' / 'i8x5': batched predicts run on the tcgen05 INT8 path (see predict_device)
         # Rollout forks may defer the "is the Schur block positive definite" read-back (a device->host
         # sync per append) to one check per rollout: see defer_checks() / check_pending().
         self._defer = False
@@ -176,7 +174,6 @@ class GPModel(object):
         self._winv_d, self._linv_d, self._alpha_d, self._ld = winv, linv, alpha, ld
         self._logdet = scal
         self._ig = None
-        self._tf32 = None
         self._i8 = None
 
     def _predict_core(self, xq_d, include_noise, mode, mat):
@@ -377,46 +374,20 @@ class GPModel(object):
                                         L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
         return mean, var
 
-    def _tf32_operand(self):
-        """(hi, lo, ld): float32 split of L^-1 of the current belief, built on first use after every refresh /
-        append."""
-        if self._tf32 is None:
-            N, dev = self.n_obs, L.device()
-            linv, lda = self._linv_for_tensor_modes()
-            ldl = L.round_up(N, 32)
-            hi = torch.empty((N, ldl), dtype=torch.float32, device=dev)
-            lo = torch.empty((N, ldl), dtype=torch.float32, device=dev)
-            L.check(L.lib.ipp_tf32_split(L.ptr(linv), N, N, lda, L.ptr(hi), L.ptr(lo), ldl, L.stream_ptr()))
-            self._tf32 = (hi, lo, ldl)
-        return self._tf32
-
-    def _predict_tf32(self, xq_d, include_noise):
-        M, N = xq_d.shape[0], self.n_obs
-        hi, lo, ldl = self._tf32_operand()
-        mean = torch.empty(M, dtype=torch.float64, device=xq_d.device)
-        var = torch.empty(M, dtype=torch.float64, device=xq_d.device)
-        work = L.workspace(L.lib.ipp_gp_predict_tf32_workspace(N, M), slot='tf32')
-        L.check(L.lib.ipp_gp_predict_tf32(ctypes.byref(self.kern._c), L.ptr(self._X_d), N, L.ptr(self._alpha_d),
-                                          L.ptr(hi), L.ptr(lo), ldl, int(self.tf32_acc_kblocks),
-                                          self._noise_var() if include_noise else 0.0,
-                                          L.ptr(xq_d), M, L.ptr(mean), L.ptr(var), L.ptr(work), L.stream_ptr()))
-        return mean, var
-
     def predict_device(self, xq_d, include_noise=True, precision=None):
         """(M, D) float64 CUDA tensor -> (mean[M], var[M]) CUDA tensors; no host transfer.
         precision: 'fp64' (FP64 DMMA), 'i8x6' (tcgen05 kind::i8 on six 7-bit slices per operand, exact integer
         accumulation: FP64-grade, ~4e-8 relative variance error), 'i8x7' (seven slices, 28 products: ~3e-10, below the
-        FP64 DMMA mode's own round-off against an extended-precision solve), 'i8x5' (five slices, 15 products on wider tiles:
-        ~2e-6, faster) or 'tf32x3' (tcgen05 kind::tf32, split operands, ~2e-4); default = the model's .predict_precision.  Small batches always use the FP64 path (bandwidth-bound)."""
+        FP64 DMMA mode's own round-off against an extended-precision solve) or 'i8x5' (five slices, 15 products on wider
+        tiles: ~2e-6, the fast split mode); default = the model's .predict_precision.  Small batches always use the FP64
+        path (bandwidth-bound)."""
         if self.n_obs == 0:
             M = xq_d.shape[0]
             return (torch.zeros(M, dtype=torch.float64, device=xq_d.device),
                     torch.full((M,), float(self.variance), dtype=torch.float64, device=xq_d.device))
         precision = self.predict_precision if precision is None else precision
-        if precision not in ('fp64', 'tf32x3', 'i8x7', 'i8x6', 'i8x5'):
-            raise ValueError("precision must be 'fp64', 'i8x7', 'i8x6', 'i8x5' or 'tf32x3'")
-        if precision == 'tf32x3' and xq_d.shape[0] > 64:
-            return self._predict_tf32(xq_d.contiguous(), include_noise)
+        if precision not in ('fp64', 'i8x7', 'i8x6', 'i8x5'):
+            raise ValueError("precision must be 'fp64', 'i8x7', 'i8x6' or 'i8x5'")
         if precision in ('i8x7', 'i8x6', 'i8x5') and xq_d.shape[0] > 64:
             return self._predict_i8(xq_d.contiguous(), include_noise, ns=int(precision[-1]))
         mode, mat = self._var_operand()
@@ -501,8 +472,7 @@ class GPModel(object):
             self._linv_d = None
         self._ig = None
         self._K = None
-        self._tf32 = None          # tensor-mode operands were cut for the previous N
-        self._i8 = None
+        self._i8 = None            # tensor-mode operands were cut for the previous N
         self._pending_info = []
 
     # info_gain support: (I + v K)^-1 and its log-determinant, cached per data version
@@ -576,7 +546,6 @@ class OnlineGPModel(GPModel):
             done += kb
         self._X_d, self._z_d, self._winv_d, self._alpha_d, self._ld = X_all, z_all, winv, alpha, ld
         self._ig = None
-        self._tf32 = None
         self._i8 = None
         self._linv_d = None
 

@@ -441,13 +441,11 @@ def test_full_size_properties(pkg):
     mu_o, var_o = o.predict_value(xq[:512].cpu().numpy())
     np.testing.assert_allclose(mean[:512].cpu().numpy().reshape(-1, 1), mu_o, rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(var[:512].cpu().numpy().reshape(-1, 1), var_o, rtol=RTOL)
-    # (6) the tensor modes at full size: sliced INT8 inside the FP64 tolerance on every query, 3xTF32 inside its bound
+    # (6) the tensor mode at full size: sliced INT8 inside the FP64 tolerance on every query
     mean8, var8 = m.predict_device(xq, precision='i8x6')
     torch.testing.assert_close(mean8, mean, rtol=1e-9, atol=1e-9)
     torch.testing.assert_close(var8, var, rtol=2e-7, atol=0)
     np.testing.assert_allclose(var8[:512].cpu().numpy().reshape(-1, 1), var_o, rtol=RTOL)
-    mean32, var32 = m.predict_device(xq, precision='tf32x3')
-    assert float(((var32 - var).abs() / var).max()) < 2e-3 and float((mean32 - mean).abs().max()) < 1e-6
 
 
 # ------------------------------------------------------------------ more edge cases
@@ -494,7 +492,7 @@ def test_space_time_kernel_d3(pkg):
         d.predict_value(q[:, :2])
     # the tensor modes carry D = 3 too (their cross-covariance generators are templated on the dimension)
     mu_o, var_o = o.predict_value(q)
-    for prec, tol in (('i8x7', RTOL), ('i8x6', RTOL), ('tf32x3', 2e-3)):
+    for prec, tol in (('i8x7', RTOL), ('i8x6', RTOL), ('i8x5', 1e-4)):
         d.predict_precision = prec
         mu_t, var_t = d.predict_value(q)
         np.testing.assert_allclose(mu_t, mu_o, rtol=RTOL, atol=1e-7)
@@ -749,33 +747,6 @@ def test_mcts_fused_rollouts_same_choices_as_per_level_path(pkg, f_rew, tree_typ
     assert m.n_obs == 120
 
 
-@pytest.mark.parametrize('N,M', [(9, 70), (333, 130), (1000, 5000), (2048, 33000)])
-def test_predict_tf32x3_mode_against_fp64_mode(pkg, N, M):
-    """3xTF32 mode (tcgen05 kind::tf32, Cholesky form, split operands) against the FP64 mode on the same belief.
-    The mean is computed in FP64 in both.  The variance carries the FP32 representation error of the operands
-    amplified by the cancellation variance - |Linv k|^2: bounded here relative to the PRIOR
-    variance (1e-5 * variance) and, at noise 0.5, to 2e-3 of the posterior variance (typically ~5e-5)."""
-    rng = np.random.default_rng(N)
-    X, z = world(rng, N, 0.5)
-    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
-    m.add_data(X, z)
-    q = rng.uniform(0, 10, (M, 2))
-    mu64, var64 = m.predict_value(q)
-    m.predict_precision = 'tf32x3'
-    mu32, var32 = m.predict_value(q)
-    np.testing.assert_allclose(mu32, mu64, rtol=1e-8, atol=1e-7)      # same FP64 accumulation; exp to 2^-36 instead of < 1 ulp
-    err = np.abs(var32 - var64)
-    assert err.max() <= 1e-5 * 100.0, err.max()
-    assert (err / var64).max() <= 2e-3, (err / var64).max()
-    assert np.median(err / var64) <= 2e-4
-    # appended data invalidates the split operand
-    m.add_data(np.array([[5.0, 5.0], [2.5, 7.5]]), np.array([[1.0], [2.0]]))
-    v_a = m.predict_value(q[:200])[1]
-    m.predict_precision = 'fp64'
-    v_b = m.predict_value(q[:200])[1]
-    assert np.abs(v_a - v_b).max() <= 1e-3
-
-
 def _device_vs_host_paths(world_obj, seed, n_poses=60):
     from informative_path_planning_b200.paths_library import Dubins_Path_Generator, dubins_paths_device
     rng = np.random.default_rng(seed)
@@ -904,8 +875,8 @@ def test_predict_i8x5_mode(pkg, N, M):
 
 @pytest.mark.parametrize('variance,lengthscale,noise', [(1.0, 0.5, 0.01), (1000.0, 2.0, 5.0), (7.3, 1.3, 0.2), (100.0, 1.0, 0.5)])
 def test_precision_modes_across_hyperparameters(pkg, variance, lengthscale, noise):
-    """The fixed-point scales of the INT8 modes (power of two >= variance, power of two >= max |L^-1|) and the TF32
-    split must follow the kernel hyper-parameters: every mode against the oracle on non-default worlds."""
+    """The fixed-point scales of the INT8 modes (power of two >= variance, power of two >= max |L^-1|)
+    must follow the kernel hyper-parameters: every mode against the oracle on non-default worlds."""
     _, gpo, _ = _oracle()
     rng = np.random.default_rng(int(variance * 10) + 3)
     N, M = 500, 700
@@ -916,7 +887,7 @@ def test_precision_modes_across_hyperparameters(pkg, variance, lengthscale, nois
     d.add_data(X, z); o.add_data(X, z)
     q = rng.uniform(0, 10, (M, 2))
     mu_o, var_o = o.predict_value(q)
-    for prec, tol in (('fp64', RTOL), ('i8x7', RTOL), ('i8x6', RTOL), ('i8x5', 1e-4), ('tf32x3', 5e-3)):
+    for prec, tol in (('fp64', RTOL), ('i8x7', RTOL), ('i8x6', RTOL), ('i8x5', 1e-4)):
         d.predict_precision = prec
         mu, var = d.predict_value(q)
         np.testing.assert_allclose(mu, mu_o, rtol=RTOL, atol=1e-7 * np.sqrt(variance), err_msg=prec)
@@ -1219,7 +1190,7 @@ def test_attach_state_shell_drops_tensor_mode_operands(pkg):
     assert dst._i8
     src.add_data(X[150:], z[150:])
     dst.attach_state_shell(X[150:], z[150:])
-    assert dst._i8 is None and dst._tf32 is None and dst._pending_info == []
+    assert dst._i8 is None and dst._pending_info == []
     assert len(src.state_tensors()) == len(dst.state_tensors())
     for a, b in zip(src.state_tensors(), dst.state_tensors()):
         b.copy_(a)                                          # what the NCCL broadcast does

@@ -17,7 +17,7 @@ q = rng.uniform(0, 10, (4096, 2))
 mu_o, var_o = o.predict_value(q[:512])
 out = {'N': N, 'factor_device_s': t_dev, 'factor_cpu_s': t_cpu}
 res = {}
-for prec in ('fp64', 'i8x7', 'i8x6', 'i8x5', 'tf32x3'):
+for prec in ('fp64', 'i8x7', 'i8x6', 'i8x5'):
     d.predict_precision = prec
     mu, var = d.predict_value(q)
     res[prec] = var
