@@ -16,6 +16,12 @@
  *     allocates nothing (callers own all workspace; sizes come from ipp_*_workspace);
  *   - return value 0 = ok, otherwise an IPP_E_* code; ipp_last_error() gives the text
  *     (thread-local).  No torch or C++ types cross this boundary.
+ *
+ * Multi-GPU: this library is single-device on purpose.  The collectives of the sharded path (broadcast of
+ * a new observation block or of the refreshed state, all-gather of per-path rewards, all-reduce of root statistics) are
+ * torch.distributed / NCCL calls in the Python host layer (informative_path_planning_b200/parallel.py), as the north star
+ * prescribes ("host code stays Python"); the survey's proposed ipp_comm_broadcast_state / ipp_comm_allgather_rewards entry
+ * points are therefore NOT part of this ABI.  Every rank owns one device and calls the functions below on it.
  */
 #ifndef IPP_B200_H
 #define IPP_B200_H
