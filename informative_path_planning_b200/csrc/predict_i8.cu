@@ -277,13 +277,17 @@ __global__ void i8_slice_kernel(const double* __restrict__ A, int64_t rows, int6
 // value is cut into plain base-128 digits in [0, 127] with integer shifts (the signed round-to-nearest slicing of
 // slice_signed costs as many FP64-pipe instructions as the exp itself).  A warp owns QPW queries; lane l handles observations
 // 4 l .. 4 l + 3 of every 128-block so that each plane store is a packed 32-bit word (128 B per warp and plane).
+// queries per warp: every observation (x, alpha: three loads) is reused by I8_QPW queries.  With 2 the kernel sat on the loads
+// (ncu r2a: long-scoreboard 5.0 stalls per issue, FP64 pipe 37 %, 1.4 TB/s of plane stores)
+constexpr int I8_QPW = 4;
+
 template <int D, int I_NS>
 __global__ void __launch_bounds__(256) rbf_queries_i8_kernel(RbfDev k, const double* __restrict__ X, int64_t N,
                                                              const double* __restrict__ alpha,
                                                              const double* __restrict__ Xq, int64_t M, double inv_scale,
                                                              int8_t* __restrict__ tiles, int64_t KB,
                                                              double* __restrict__ mean) {
-    constexpr int QPW = 2;
+    constexpr int QPW = I8_QPW;
     const int lane = threadIdx.x & 31;
     const int64_t m0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * QPW;
     if (m0 >= M) return;
@@ -403,7 +407,7 @@ static int predict_i8_impl(const ipp_rbf* kern, const double* X, int64_t N, cons
     const int grid = sm_count();
     for (int64_t s = 0; s < M; s += mc_max) {
         const int64_t mc = (M - s) < mc_max ? (M - s) : mc_max;
-        const unsigned qblocks = (unsigned)((mc + 15) / 16);
+        const unsigned qblocks = (unsigned)((mc + 8 * I8_QPW - 1) / (8 * I8_QPW));
         if (kern->dim == 2)
             rbf_queries_i8_kernel<2, NS><<<qblocks, 256, 0, stream>>>(kd, X, N, alpha, Xq + s * 2, mc, 1.0 / sa, tiles, KB, mean + s);
         else

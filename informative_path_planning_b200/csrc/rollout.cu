@@ -551,28 +551,33 @@ namespace ipp {
 
 // IPP_ROLLOUT_FUSED=0 / ipp_rollout_mode(0) select the four-kernel sequence (A/B measurements and cross-checks; it is
 // always used for more than 32 points)
+static int64_t rf_part_doubles() { return (int64_t)sm_count() * (32 * 33 / 2 + 32 + 2) / 2 * 2; }   // partials, even count
 static int g_rollout_fused = -1;
 static bool rollout_use_fused() {
     if (g_rollout_fused < 0) { const char* e = getenv("IPP_ROLLOUT_FUSED"); g_rollout_fused = (e && e[0] == '0') ? 0 : 1; }
     return g_rollout_fused != 0;
 }
 
-template <int D, int NT>
-static int rollout_fused_launch(const RolloutFusedArgs& fa, const RolloutInline* inl, int grid, cudaStream_t stream) {
-    constexpr int bytes = rf_smem_doubles<NT>() * (int)sizeof(double);
-    IPP_OPT_IN_SMEM((rollout_fused_kernel<D, NT>), bytes);
+constexpr int RF_STREAM_MIN_N = 2048;       // from here on the images come from a pre-pass and W^-1 arrives by cp.async
+
+template <int D, int NT, bool STREAM>
+static int rollout_fused_launch(const RolloutFusedArgs& fa_in, const RolloutInline* inl, const double* pts_dev, double* img,
+                                int grid, cudaStream_t stream) {
+    constexpr int bytes = rf_smem_doubles<NT, STREAM>() * (int)sizeof(double);
+    IPP_OPT_IN_SMEM((rollout_fused_kernel<D, NT, STREAM>), bytes);
+    RolloutFusedArgs fa = fa_in;
     RolloutInlineSmall small;
     if (inl) memcpy(small.v, inl->v, sizeof(double) * (size_t)fa.r.M * (D + 1));      // [M][D] points, then [M] observations
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = RF_CLUSTER;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = RF_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(RF_THREADS);
     cfg.dynamicSmemBytes = bytes;
     cfg.stream = stream;
-    cfg.attrs = &attr;
+    cfg.attrs = attr;
     cfg.numAttrs = 1;
     // clusters of RF_CLUSTER CTAs only while all of them are resident at once (fewer whole clusters than single CTAs fit:
     // each needs RF_CLUSTER free SMs in one GPC); otherwise every CTA is its own cluster
@@ -582,7 +587,7 @@ static int rollout_fused_launch(const RolloutFusedArgs& fa, const RolloutInline*
     if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
         cfg.gridDim = dim3((unsigned)(sm_count() / RF_CLUSTER * RF_CLUSTER));
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, rollout_fused_kernel<D, NT>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = -1; }
+        if (cudaOccupancyMaxActiveClusters(&n, rollout_fused_kernel<D, NT, STREAM>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = -1; }
         max_clusters[dev] = n;
     }
     const int fit = (dev >= 0 && dev < 64) ? max_clusters[dev] : -1;
@@ -590,11 +595,26 @@ static int rollout_fused_launch(const RolloutFusedArgs& fa, const RolloutInline*
     if (fit > 0 && (grid + RF_CLUSTER - 1) / RF_CLUSTER <= fit) {
         g = (grid + RF_CLUSTER - 1) / RF_CLUSTER * RF_CLUSTER;         // whole clusters; surplus CTAs get no tiles
     } else {
-        attr.val.clusterDim.x = 1;
+        attr[0].val.clusterDim.x = 1;
     }
     cfg.gridDim = dim3((unsigned)g);
-    IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_fused_kernel<D, NT>, fa, small));
+    if (STREAM) {
+        fa.img = img;
+        rollout_images_kernel<D, NT><<<(unsigned)fa.T, RF_THREADS, 0, stream>>>(fa.kern, fa.X, fa.N, pts_dev, inl ? 1 : 0, fa.r.M, small, img);
+        IPP_LAUNCH_CHECK();
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // scheduled while the pre-pass runs; waits for
+        attr[1].val.programmaticStreamSerializationAllowed = 1;                // it in griddepcontrol.wait
+        cfg.numAttrs = 2;
+    }
+    IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_fused_kernel<D, NT, STREAM>, fa, small));
     return IPP_OK;
+}
+
+template <int D, int NT>
+static int rollout_fused_dispatch(const RolloutFusedArgs& fa, const RolloutInline* inl, const double* pts_dev, double* img,
+                                  int grid, cudaStream_t stream) {
+    if (fa.N >= RF_STREAM_MIN_N) return rollout_fused_launch<D, NT, true>(fa, inl, pts_dev, img, grid, stream);
+    return rollout_fused_launch<D, NT, false>(fa, inl, pts_dev, img, grid, stream);
 }
 
 // IPP_ROLLOUT_TW=simt selects the SIMT pass (A/B measurements); the tensor pass is the default
@@ -631,8 +651,9 @@ extern "C" int64_t ipp_rollout_workspace(int64_t N, int64_t M) {
     if (M <= 0) return 16;
     const int64_t ldc = round_up(M, 2);
     const int64_t four_kernels = 2 * M * round_up(N, 16) + M * ldc + round_up(M, 2) + 16;
-    const int64_t Mf = M < 32 ? M : 32;
-    const int64_t fused = (int64_t)ipp::sm_count() * (Mf * (Mf + 1) / 2 + Mf) + 16;    // one partial per CTA, <= 1 CTA per SM
+    // one-launch form: one partial per cluster, and for N >= RF_STREAM_MIN_N four P x 64 images per 64-block of observations
+    const int64_t T = (N + 63) / 64, P = 8 * rf_ntiles((int)(M < 32 ? M : 32));
+    const int64_t fused = ipp::rf_part_doubles() + (N >= ipp::RF_STREAM_MIN_N ? T * 4 * P * 64 : 0) + 16;
     return four_kernels > fused ? four_kernels : fused;
 }
 
@@ -698,9 +719,11 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         if (grid > sm_count()) grid = sm_count();
         const int nt = rf_ntiles(M);
         const bool d2 = kern->dim == 2;
-        if (nt == 2) return d2 ? rollout_fused_launch<2, 2>(fa, inline_pts, grid, stream) : rollout_fused_launch<3, 2>(fa, inline_pts, grid, stream);
-        if (nt == 3) return d2 ? rollout_fused_launch<2, 3>(fa, inline_pts, grid, stream) : rollout_fused_launch<3, 3>(fa, inline_pts, grid, stream);
-        return d2 ? rollout_fused_launch<2, 4>(fa, inline_pts, grid, stream) : rollout_fused_launch<3, 4>(fa, inline_pts, grid, stream);
+        fa.img = nullptr;
+        double* img = work + rf_part_doubles();            // the streaming form's images, behind the partials
+        if (nt == 2) return d2 ? rollout_fused_dispatch<2, 2>(fa, inline_pts, pts, img, grid, stream) : rollout_fused_dispatch<3, 2>(fa, inline_pts, pts, img, grid, stream);
+        if (nt == 3) return d2 ? rollout_fused_dispatch<2, 3>(fa, inline_pts, pts, img, grid, stream) : rollout_fused_dispatch<3, 3>(fa, inline_pts, pts, img, grid, stream);
+        return d2 ? rollout_fused_dispatch<2, 4>(fa, inline_pts, pts, img, grid, stream) : rollout_fused_dispatch<3, 4>(fa, inline_pts, pts, img, grid, stream);
     }
     IPP_CHECK_ARG(kind != IPP_REWARD_INFO, "information-gain rollouts take at most 32 points (one-launch form only)");
     const int64_t ldc = round_up(M, 2);

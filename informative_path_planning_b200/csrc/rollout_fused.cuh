@@ -26,6 +26,7 @@ namespace ipp {
 namespace cg = cooperative_groups;
 
 constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8;
+constexpr int RF_STAGES = 3;                            // streaming form: tiles in flight per CTA (HBM latency x bandwidth)
 constexpr int RF_CLUSTER = 4;                           // CTAs per thread-block cluster: their partials meet in shared memory
 constexpr int RF_SLOTS = 256;                           // ticket counters; each launch takes the next one
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
@@ -48,6 +49,7 @@ struct RolloutFusedArgs {
     const double* pts; const double* zobs;               // device copies (used when use_inline == 0)
     int use_inline;
     double* part;                                        // [clusters][V], V = M (M + 1) / 2 + M
+    const double* img;                                   // streaming form: [T][4][P * 64] cross-covariance images (pre-pass)
     int slot, tiles, T;
     unsigned long long tag;                              // != 0: r.reward holds 16-byte {value, tag} records, L rewards then info
     RolloutArgs r;
@@ -91,9 +93,12 @@ __device__ __forceinline__ double rf_rbf(const RbfDev& k, const double* a, const
     return k.variance * rf_exp_neg(-0.5 * r2);
 }
 
-template <int NT>
+template <int NT, bool STREAM>
 constexpr int rf_smem_doubles() {
     constexpr int P = 8 * NT;
+    if (STREAM)     // RF_STAGES x (A image + 64 x 64 tile of W^-1) ring fed by cp.async; V rounded up (16-byte alignment)
+        return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + ((P * (P + 1) / 2 + P + 1) & ~1) +
+               RF_STAGES * (RF_B * RF_B + P * RF_B) + 8;
     //      points  K_I images (2)    K_J image + plain copy   mean  obs   this CTA's partial (read by its cluster leader)
     return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + (P * (P + 1) / 2 + P) + 8;
 }
@@ -323,7 +328,53 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
     rf_score(p, snap_m, snap_v, Cs, s_bad, tag);
 }
 
+// The cross-covariance images of the streaming form, one CTA per 64-block of observations: A operand (fragment order),
+// the same scaled by 1/2 (diagonal tiles), B operand of the fold (fragment order), plain copy (mean).
 template <int D, int NT>
+__global__ void __launch_bounds__(RF_THREADS) rollout_images_kernel(RbfDev kern, const double* __restrict__ X, int N,
+                                                                    const double* __restrict__ pts, int use_inline, int M,
+                                                                    const __grid_constant__ RolloutInlineSmall pp,
+                                                                    double* __restrict__ img) {
+    constexpr int P = 8 * NT;
+    __shared__ double s_pts[P * 3];
+    const int tid = threadIdx.x;
+    if (use_inline) {
+        for (int i = 0; i < M * D; ++i) {
+            const double v = pp.v[i];
+            if (tid == (i & (RF_THREADS - 1))) s_pts[i] = v;
+        }
+    } else {
+        for (int i = tid; i < M * D; i += RF_THREADS) s_pts[i] = pts[i];
+    }
+    __syncthreads();
+    const int jj = tid & (RF_B - 1), a0 = tid / RF_B;
+    const int n = blockIdx.x * RF_B + jj;
+    double x[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = n < N ? X[(int64_t)n * D + d] : 0.0;
+    double* out = img + (size_t)blockIdx.x * 4 * P * RF_B;
+    const int ta = ((((jj >> 5) * 4 + ((jj >> 1) & 3)) * 32 + 4 * a0 + ((jj >> 3) & 3)) * 2) + (jj & 1);      // see gen_k below
+    const int tb = (((jj >> 3) * 32 + 4 * a0 + ((jj >> 1) & 3)) * 2) + (jj & 1);
+#pragma unroll
+    for (int r = 0; r < 2 * NT; ++r) {
+        const int a = a0 + 4 * r;
+        double v = 0.0;
+        if (a < M) v = n < N ? rf_rbf<D>(kern, s_pts + a * D, x) : 0.0;
+        out[ta + (r >> 1) * 512 + (r & 1) * 32] = v;
+        out[P * RF_B + ta + (r >> 1) * 512 + (r & 1) * 32] = 0.5 * v;
+        out[2 * P * RF_B + tb + (r >> 1) * 512 + (r & 1) * 32] = v;
+        out[3 * P * RF_B + a * RF_B + jj] = v;
+    }
+}
+
+__device__ __forceinline__ void rf_cp16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+
+// STREAM: large beliefs.  The images come from rollout_images_kernel (computed once instead of once per tile: at N = 4096
+// a tile cost 6.1k SM clocks of which the tensor pipe needs 1.5k -- the FP64 exp of the images and the register-staged,
+// 8-byte loads of W^-1 made up the rest) and, like the 64 x 64 tiles of W^-1, arrive by cp.async one tile ahead.
+template <int D, int NT, bool STREAM>
 __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __grid_constant__ RolloutFusedArgs q,
                                                                      const __grid_constant__ RolloutInlineSmall pp) {
     constexpr int P = 8 * NT;
@@ -428,6 +479,119 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     double w_cur[2][8], w_nxt[2][8];
     long long tk[6] = {0, 0, 0, 0, 0, 0};
     tk[0] = clock64();
+    if constexpr (STREAM) {
+        constexpr int VP = (P * (P + 1) / 2 + P + 1) & ~1;
+        constexpr int STG = RF_B * RF_B + P * RF_B;       // one stage: the tile of W^-1 (16-byte chunks XOR-swizzled by bit
+        double* s_ring = s_part + VP;                     // 3 of the row), then the A image of its row block
+        const uint32_t ring_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_ring));
+        const uint32_t c_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_kj));
+        // thread -> 16-byte chunk c = tid & 31 of rows (tid >> 5) + 8 u: bit 3 of the row is u & 1
+        const int cw = tid & 31, rw = tid >> 5;
+        const uint32_t dst_even = (uint32_t)((rw * RF_B + (cw << 1)) * 8), dst_odd = (uint32_t)((rw * RF_B + ((cw ^ 4) << 1)) * 8);
+        auto issue_tile = [&](int slot, int I_, int J_) { // tile (I_, J_) of W^-1 and the A image of block I_: one group
+            const uint32_t base = ring_base + (uint32_t)(slot * STG * 8);
+            if ((I_ + 1) * RF_B <= N) {                   // interior tile (J_ <= I_): no bounds, one pointer bump per chunk
+                const double* src = q.W + (int64_t)(I_ * RF_B + rw) * q.ldw + J_ * RF_B + 2 * cw;
+#pragma unroll
+                for (int u = 0; u < (RF_B * RF_B / 2) / RF_THREADS; ++u)
+                    rf_cp16(base + ((u & 1) ? dst_odd : dst_even) + (uint32_t)(u * 8 * RF_B * 8), src + (int64_t)u * 8 * q.ldw, 16);
+            } else
+#pragma unroll
+            for (int u = 0; u < (RF_B * RF_B / 2) / RF_THREADS; ++u) {
+                const int id = tid + RF_THREADS * u, r = id >> 5, c = id & 31;
+                const int row = I_ * RF_B + r, col = J_ * RF_B + 2 * c;
+                const int bytes = row < N ? (col + 1 < N ? 16 : (col < N ? 8 : 0)) : 0;       // zero-fill beyond N
+                const double* src = q.W + (bytes ? (int64_t)row * q.ldw + col : 0);
+                rf_cp16(base + (uint32_t)((r * RF_B + ((c ^ (((r >> 3) & 1) << 2)) << 1)) * 8), src, bytes);
+            }
+            const double* a_src = q.img + ((size_t)I_ * 4 + (I_ == J_ ? 1 : 0)) * (P * RF_B);
+            for (int id = tid; id < P * RF_B / 2; id += RF_THREADS)
+                rf_cp16(base + (uint32_t)((RF_B * RF_B + 2 * id) * 8), a_src + 2 * id, 16);
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        auto issue_column = [&](int J_) {                 // B image + plain copy of block J_ (adjacent in both places)
+            const double* c_src = q.img + ((size_t)J_ * 4 + 2) * (P * RF_B);
+            for (int id = tid; id < P * RF_B; id += RF_THREADS) rf_cp16(c_base + (uint32_t)(2 * id * 8), c_src + 2 * id, 16);
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        auto next_tile = [&](int& I_, int& J_) { if (++I_ == T) { ++J_; I_ = J_; } };
+        grid_dependency_wait();                           // the images are the pre-pass kernel's output
+        tk[1] = clock64();                                // (diagnostics: tk[2..4] accumulate issue / wait / contraction clocks)
+        int Ia = I, Ja = J, ka = k0;                      // the next tile to ask for
+        for (; ka < k1 && ka < k0 + RF_STAGES - 1; ++ka) { issue_tile(ka - k0, Ia, Ja); next_tile(Ia, Ja); }
+        for (int k = k0; k < k1; ++k) {
+            const long long c0 = clock64();
+            const bool new_col = J != curJ;
+            if (new_col) {
+                if (curJ >= 0) {
+                    fold();
+                    __syncthreads();                      // everybody is done with the old column's image
+                }
+                curJ = J;
+                issue_column(J);
+            }
+            const bool issued_now = ka < k1;
+            if (issued_now) { issue_tile((ka - k0) % RF_STAGES, Ia, Ja); next_tile(Ia, Ja); ++ka; }
+            // groups younger than tile k's: the tiles k + 1 .. ka - 1.  At a column change the column's images were
+            // committed just before the tile issued in this iteration (if any): everything but that one is waited for
+            const long long c1 = clock64();
+            const int younger = ka - 1 - k;
+            if (new_col) {
+                if (issued_now) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
+            } else if (younger <= 0) {
+                asm volatile("cp.async.wait_group 0;\n" ::);
+            } else if (younger == 1) {
+                asm volatile("cp.async.wait_group 1;\n" ::);
+            } else {
+                asm volatile("cp.async.wait_group 2;\n" ::);
+            }
+            __syncthreads();
+            const long long c2 = clock64();
+            if (I == J) {                                 // partial mean: K_J alpha_J, 8 lanes per point
+                for (int idx = tid; idx < P * 8; idx += RF_THREADS) {
+                    const int a = idx >> 3, seg = idx & 7;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int n = J * RF_B + seg * 8 + u;
+                        sacc = fma(s_kp[a * RF_B + seg * 8 + u], n < N ? q.alpha[n] : 0.0, sacc);
+                    }
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+                    if (seg == 0) s_m0[a] += sacc;
+                }
+            }
+            // B operand: W[32 c + 8 t + s][8 w + g] from the swizzled tile; bit 3 of the row is t & 1 for every (c, s)
+            const int col = 8 * warp + g;
+            const double* st = s_ring + ((k - k0) % RF_STAGES) * STG;
+            const double* wt = st + 8 * t * RF_B + ((((col >> 1) ^ ((t & 1) << 2)) << 1) + (col & 1));
+            const double2* ka2 = reinterpret_cast<const double2*>(st + RF_B * RF_B);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                double a[NT][8], wv[8];
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) wv[s8] = wt[(32 * c + s8) * RF_B];
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const double2 v = ka2[((mt * 2 + c) * 4 + qq) * 32 + lane];
+                        a[mt][2 * qq] = v.x;
+                        a[mt][2 * qq + 1] = v.y;
+                    }
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8)
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt) dmma884(U[mt][0], U[mt][1], a[mt][s8], wv[s8]);
+            }
+            __syncthreads();                              // this stage is free for the tile RF_STAGES further on
+            next_tile(I, J);
+            const long long c3 = clock64();
+            tk[2] += c1 - c0; tk[3] += c2 - c1; tk[4] += c3 - c2;
+        }
+        tk[2] += tk[1]; tk[3] += tk[2]; tk[4] += tk[3];   // so that the differences printed below are the three sums
+    } else {
     if (k0 < k1) load_w(w_nxt, I, J);
     for (int k = k0; k < k1; ++k) {
         if (J != curJ) {
@@ -485,6 +649,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         buf ^= 1;
         I = In; J = Jn;
         if (k == k0) tk[4] = clock64();
+    }
     }
     if (k0 < k1) fold();                                  // (a CTA without tiles only pads its cluster: its partial is zero)
     __syncthreads();
