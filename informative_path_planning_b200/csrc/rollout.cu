@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(256) rollout_cov_kernel(RbfDev k, int D, const
 
 }  // namespace ipp
 
+#include "tc05.cuh"
 #include "rollout_fused.cuh"
 
 namespace ipp {
@@ -558,7 +559,29 @@ static bool rollout_use_fused() {
     return g_rollout_fused != 0;
 }
 
-constexpr int RF_STREAM_MIN_N = 2048;       // from here on the images come from a pre-pass and W^-1 arrives by cp.async
+constexpr int RF_STREAM_MIN_N = 2048;       // from here on the images come from a pre-pass and W^-1 arrives by bulk copies
+
+// W^-1 ([N][ldw] doubles) as a tensor map for the streaming form: boxes of 16 columns x 64 rows (one panel of a staged
+// tile), 128-byte swizzle, rows / columns beyond N read as zeros.  Encoding costs ~1 us on the host; the search asks for
+// the same belief hundreds of times in a row, so the last one is kept.
+static int rollout_w_map(CUtensorMap* out, const double* W, int64_t N, int64_t ldw) {
+    static thread_local struct { const double* W; int64_t N, ldw; CUtensorMap map; } last = {nullptr, 0, 0, {}};
+    if (last.W != W || last.N != N || last.ldw != ldw) {
+        EncodeTiledFn fn = encode_tiled_fn();
+        if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IPP_E_CUDA; }
+        const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)N};
+        const cuuint64_t strides[1] = {(cuuint64_t)ldw * sizeof(double)};
+        const cuuint32_t box[2] = {16u, (cuuint32_t)RF_B};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = fn(&last.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(W), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { last.W = nullptr; set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return IPP_E_CUDA; }
+        last.W = W; last.N = N; last.ldw = ldw;
+    }
+    *out = last.map;
+    return IPP_OK;
+}
 
 template <int D, int NT, bool STREAM>
 static int rollout_fused_launch(const RolloutFusedArgs& fa_in, const RolloutInline* inl, const double* pts_dev, double* img,
@@ -574,7 +597,7 @@ static int rollout_fused_launch(const RolloutFusedArgs& fa_in, const RolloutInli
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(RF_THREADS);
+    cfg.blockDim = dim3(STREAM ? RF_THREADS + 32 : RF_THREADS);      // streaming form: + the warp that feeds the ring
     cfg.dynamicSmemBytes = bytes;
     cfg.stream = stream;
     cfg.attrs = attr;
@@ -598,15 +621,19 @@ static int rollout_fused_launch(const RolloutFusedArgs& fa_in, const RolloutInli
         attr[0].val.clusterDim.x = 1;
     }
     cfg.gridDim = dim3((unsigned)g);
+    alignas(64) CUtensorMap wmap;
+    memset(&wmap, 0, sizeof(wmap));
     if (STREAM) {
+        const int rc = rollout_w_map(&wmap, fa.W, fa.N, fa.ldw);
+        if (rc != IPP_OK) return rc;
         fa.img = img;
-        rollout_images_kernel<D, NT><<<(unsigned)fa.T, RF_THREADS, 0, stream>>>(fa.kern, fa.X, fa.N, pts_dev, inl ? 1 : 0, fa.r.M, small, img);
+        rollout_images_kernel<D, NT><<<(unsigned)fa.T, RF_THREADS, 0, stream>>>(fa.kern, fa.X, fa.N, fa.alpha, pts_dev, inl ? 1 : 0, fa.r.M, small, img);
         IPP_LAUNCH_CHECK();
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // scheduled while the pre-pass runs; waits for
         attr[1].val.programmaticStreamSerializationAllowed = 1;                // it in griddepcontrol.wait
         cfg.numAttrs = 2;
     }
-    IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_fused_kernel<D, NT, STREAM>, fa, small));
+    IPP_CUDA(cudaLaunchKernelEx(&cfg, rollout_fused_kernel<D, NT, STREAM>, fa, small, wmap));
     return IPP_OK;
 }
 

@@ -26,7 +26,9 @@ namespace ipp {
 namespace cg = cooperative_groups;
 
 constexpr int RF_B = 64, RF_THREADS = 256, RF_WARPS = 8;
-constexpr int RF_STAGES = 3;                            // streaming form: tiles in flight per CTA (HBM latency x bandwidth)
+constexpr int RF_STAGES = 4;                            // streaming form: ring of tile stages per CTA
+constexpr int RF_AHEAD = 2;                             // ... of which this many are requested ahead of the tile being contracted
+constexpr int RF_TILE = RF_B * RF_B;                    // a staged tile of W^-1: four 16-column panels [64 rows][128 B], TMA 128-byte swizzle
 constexpr int RF_CLUSTER = 4;                           // CTAs per thread-block cluster: their partials meet in shared memory
 constexpr int RF_SLOTS = 256;                           // ticket counters; each launch takes the next one
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
@@ -96,11 +98,18 @@ __device__ __forceinline__ double rf_rbf(const RbfDev& k, const double* a, const
 template <int NT, bool STREAM>
 constexpr int rf_smem_doubles() {
     constexpr int P = 8 * NT;
-    if (STREAM)     // RF_STAGES x (A image + 64 x 64 tile of W^-1) ring fed by cp.async; V rounded up (16-byte alignment)
-        return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + ((P * (P + 1) / 2 + P + 1) & ~1) +
-               RF_STAGES * (RF_B * RF_B + P * RF_B) + 8;
+    if (STREAM)     // points, K_J image, mean, obs, partial (V rounded up: 16-byte alignment), then the ring of RF_STAGES x
+        return P * 3 + P * RF_B + P + P + ((P * (P + 1) / 2 + P + 1) & ~1) +      // (tile of W^-1 + A image) fed by bulk copies
+               RF_STAGES * (RF_TILE + P * RF_B) + 128 + 8;                        // (+ 1 KB: the ring starts on a 1024-byte boundary)
     //      points  K_I images (2)    K_J image + plain copy   mean  obs   this CTA's partial (read by its cluster leader)
     return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + (P * (P + 1) / 2 + P) + 8;
+}
+
+// Thread index as the code below the tile loop sees it.  The streaming form runs a ninth warp that only feeds the ring;
+// its threads get indices no strided loop or guard ever reaches (tid >= 2^20, warp >= 2^15), so outside the tile loop they
+// just keep the block-wide barriers company.
+__device__ __forceinline__ int rf_tid() {
+    return threadIdx.x < RF_THREADS ? (int)threadIdx.x : (1 << 20) + (int)(threadIdx.x & 31);
 }
 
 // All levels scored in parallel from the snapshots: warp w takes levels w, w + 8, ...  Called by every thread after a
@@ -108,7 +117,7 @@ constexpr int rf_smem_doubles() {
 __device__ __forceinline__ void rf_score(const RolloutArgs& p, const double* snap_m, const double* snap_v, double* Cs,
                                          int& s_bad, unsigned long long tag) {
     const int M = p.M, ldc = M + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = rf_tid(), lane = tid & 31, warp = tid >> 5;
     if (tid == 0) g_rf_clock[25] = clock64();
     for (int l = warp; l < p.L; l += RF_WARPS) {
         const int b0 = p.offsets[l], kb = p.offsets[l + 1] - b0;
@@ -194,7 +203,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                                              double* snap_m, double* snap_v, double* Cs, int& s_bad,
                                              unsigned long long tag) {
     const int M = p.M, ldc = M + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = rf_tid(), lane = tid & 31, warp = tid >> 5;
     constexpr int HL = RO_MAX_BLOCK + 1;
     if (tid == 0) s_bad = 0;
     __syncthreads();
@@ -328,16 +337,20 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
     rf_score(p, snap_m, snap_v, Cs, s_bad, tag);
 }
 
-// The cross-covariance images of the streaming form, one CTA per 64-block of observations: A operand (fragment order),
-// the same scaled by 1/2 (diagonal tiles), B operand of the fold (fragment order), plain copy (mean).
+// The cross-covariance images of the streaming form, one CTA per 64-block of observations (four slots of P x 64 doubles):
+// slot 0 the image in fragment order (A operand of the first contraction, B operand of the fold), slot 1 the same scaled
+// by 1/2 (diagonal tiles), and -- in the first P doubles of slot 3 -- the block's share of the prior mean,
+// K[a][block] . alpha[block] (fixed summation order).
 template <int D, int NT>
 __global__ void __launch_bounds__(RF_THREADS) rollout_images_kernel(RbfDev kern, const double* __restrict__ X, int N,
+                                                                    const double* __restrict__ alpha,
                                                                     const double* __restrict__ pts, int use_inline, int M,
                                                                     const __grid_constant__ RolloutInlineSmall pp,
                                                                     double* __restrict__ img) {
     constexpr int P = 8 * NT;
     __shared__ double s_pts[P * 3];
-    const int tid = threadIdx.x;
+    __shared__ double s_red[RF_WARPS][2 * NT];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (use_inline) {
         for (int i = 0; i < M * D; ++i) {
             const double v = pp.v[i];
@@ -352,9 +365,12 @@ __global__ void __launch_bounds__(RF_THREADS) rollout_images_kernel(RbfDev kern,
     double x[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) x[d] = n < N ? X[(int64_t)n * D + d] : 0.0;
+    const double al = n < N ? alpha[n] : 0.0;
     double* out = img + (size_t)blockIdx.x * 4 * P * RF_B;
-    const int ta = ((((jj >> 5) * 4 + ((jj >> 1) & 3)) * 32 + 4 * a0 + ((jj >> 3) & 3)) * 2) + (jj & 1);      // see gen_k below
-    const int tb = (((jj >> 3) * 32 + 4 * a0 + ((jj >> 1) & 3)) * 2) + (jj & 1);
+    // element (a, i) at (((a >> 3) 8 + (i >> 3)) 32 + 4 (a & 7) + ((i >> 1) & 3)) 2 + (i & 1): as the A operand of the first
+    // contraction one 16-byte load per lane feeds the two k-steps that contract i = 8 h + 2 t and 8 h + 2 t + 1 (t = lane & 3);
+    // the same order is the B operand of the fold (gen_k below), so slot 0 serves both
+    const int ta = ((((jj >> 3) * 32) + 4 * a0 + ((jj >> 1) & 3)) * 2) + (jj & 1);
 #pragma unroll
     for (int r = 0; r < 2 * NT; ++r) {
         const int a = a0 + 4 * r;
@@ -362,32 +378,43 @@ __global__ void __launch_bounds__(RF_THREADS) rollout_images_kernel(RbfDev kern,
         if (a < M) v = n < N ? rf_rbf<D>(kern, s_pts + a * D, x) : 0.0;
         out[ta + (r >> 1) * 512 + (r & 1) * 32] = v;
         out[P * RF_B + ta + (r >> 1) * 512 + (r & 1) * 32] = 0.5 * v;
-        out[2 * P * RF_B + tb + (r >> 1) * 512 + (r & 1) * 32] = v;
-        out[3 * P * RF_B + a * RF_B + jj] = v;
+        double sacc = v * al;                             // point a lives in warps 2 a0 (jj < 32) and 2 a0 + 1
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) s_red[warp][r] = sacc;
     }
-}
-
-__device__ __forceinline__ void rf_cp16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+    __syncthreads();
+    if (tid < P) out[3 * P * RF_B + tid] = s_red[2 * (tid & 3)][tid >> 2] + s_red[2 * (tid & 3) + 1][tid >> 2];
 }
 
 // STREAM: large beliefs.  The images come from rollout_images_kernel (computed once instead of once per tile: at N = 4096
 // a tile cost 6.1k SM clocks of which the tensor pipe needs 1.5k -- the FP64 exp of the images and the register-staged,
-// 8-byte loads of W^-1 made up the rest) and, like the 64 x 64 tiles of W^-1, arrive by cp.async one tile ahead.
+// 8-byte loads of W^-1 made up the rest).  Tiles of W^-1 and the A images arrive through a ring of RF_STAGES stages filled
+// by the TMA engine at the request of a ninth warp and handed over with mbarriers -- full: the bytes, empty: 8 arrivals --
+// so the tile loop has no block-wide barrier: the two contracting warps of an SM sub-partition drift apart and one's
+// operand reads run under the other's DMMAs.
 template <int D, int NT, bool STREAM>
-__global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __grid_constant__ RolloutFusedArgs q,
-                                                                     const __grid_constant__ RolloutInlineSmall pp) {
+__global__ void __launch_bounds__(STREAM ? RF_THREADS + 32 : RF_THREADS, 1) rollout_fused_kernel(const __grid_constant__ RolloutFusedArgs q,
+                                                                     const __grid_constant__ RolloutInlineSmall pp,
+                                                                     const __grid_constant__ CUtensorMap wmap) {
     constexpr int P = 8 * NT;
     extern __shared__ __align__(16) double sm[];
+    constexpr int VP = (P * (P + 1) / 2 + P + 1) & ~1;
     double* s_pts = sm;                                  // [P][3]
-    double* s_ki = s_pts + P * 3;                        // [2][P * 64] fragment-ordered K[a][i] (A operand), i in tile row I
-    double* s_kj = s_ki + 2 * P * RF_B;                  // [P * 64]    fragment-ordered K[b][j] (B operand of the fold), column J
-    double* s_kp = s_kj + P * RF_B;                      // [P][64]     the same, plain (mean on the diagonal tile)
-    double* s_m0 = s_kp + P * RF_B;                      // [P]
+    // one-shot form: [2][P * 64] fragment-ordered K[a][i] (A operand), i in tile row I; streaming form: the ring (after the
+    // fixed part).  Either way the memory the hand-over and the conditioning reuse once the tile loop is over.
+    double* s_ki = STREAM ? s_pts + P * 3 + P * RF_B + 2 * P + VP : s_pts + P * 3;
+    double* s_kj = STREAM ? s_pts + P * 3 : s_ki + 2 * P * RF_B;      // [P * 64] fragment-ordered K[b][j] (B operand of the fold), column J
+    double* s_kp = s_kj + P * RF_B;                      // [P][64]     the same, plain (one-shot form: mean on the diagonal tile)
+    double* s_m0 = STREAM ? s_kj + P * RF_B : s_kp + P * RF_B;        // [P]
     double* s_z = s_m0 + P;                              // [P]         observations
     double* s_part = s_z + P;                            // [V]         this CTA's partial: A + A^T lower triangle, then the mean
     __shared__ int s_last, s_bad;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    __shared__ unsigned int s_colcnt;
+    __shared__ __align__(8) unsigned long long s_bar[2 * RF_STAGES + 1];      // full[], empty[], column image
+    const bool producer = STREAM && threadIdx.x >= RF_THREADS;       // the warp that feeds the ring (see rf_tid)
+    const int tid = rf_tid();
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int M = q.r.M, N = q.N, T = q.T;
     const long long clk0 = clock64();
 
@@ -406,12 +433,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     const int k0 = (int)((blockIdx.x * (unsigned)q.tiles) / (unsigned)G);                  // tiles * SMs < 2^31
     const int k1 = (int)(((blockIdx.x + 1u) * (unsigned)q.tiles) / (unsigned)G);
     // column-major walk over the lower triangle: column J holds tiles (I = J .. T - 1, J)
-    int J = 0, I = 0;
-    {
-        int rest = k0;
-        while (rest >= T - J) { rest -= T - J; ++J; }
-        I = J + rest;
-    }
+    // (tiles ahead of column J: J T - J (J - 1) / 2; the square root lands within one column, the loops settle it)
+    int J = (int)(0.5 * ((double)(2 * T + 1) - sqrt((double)(2 * T + 1) * (double)(2 * T + 1) - 8.0 * (double)k0)));
+    J = J < 0 ? 0 : (J > T - 1 ? T - 1 : J);
+    while (J > 0 && J * T - J * (J - 1) / 2 > k0) --J;
+    while (J < T - 1 && (J + 1) * T - (J + 1) * J / 2 <= k0) ++J;
+    int I = J + (k0 - (J * T - J * (J - 1) / 2));
     // B operand of the first contraction, one tile: thread (g, t) of warp w supplies W[I 64 + 32 c + 8 t + s][J 64 + 8 w + g]
     auto load_w = [&](double (&wv)[2][8], int I_, int J_) {
         const int col = J_ * RF_B + warp * 8 + g;
@@ -453,15 +480,23 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
             }
         }
     };
-    double U[NT][2], Z[NT][NT][2];
+    double U[NT][2], U2[NT][2], Z[NT][NT][2];          // (U2: the streaming form's second accumulator set, odd k-steps)
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt) {
         U[mt][0] = U[mt][1] = 0.0;
+        U2[mt][0] = U2[mt][1] = 0.0;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) Z[mt][nt][0] = Z[mt][nt][1] = 0.0;
     }
     auto fold = [&]() {                                   // A += U_J K_J^T straight from the accumulator fragments
         const double2* kb = reinterpret_cast<const double2*>(s_kj);
+        if constexpr (STREAM) {
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) {
+                U[mt][0] += U2[mt][0]; U[mt][1] += U2[mt][1];
+                U2[mt][0] = U2[mt][1] = 0.0;
+            }
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const double2 b = kb[(nt * 8 + warp) * 32 + lane];
@@ -480,117 +515,133 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
     long long tk[6] = {0, 0, 0, 0, 0, 0};
     tk[0] = clock64();
     if constexpr (STREAM) {
-        constexpr int VP = (P * (P + 1) / 2 + P + 1) & ~1;
-        constexpr int STG = RF_B * RF_B + P * RF_B;       // one stage: the tile of W^-1 (16-byte chunks XOR-swizzled by bit
-        double* s_ring = s_part + VP;                     // 3 of the row), then the A image of its row block
-        const uint32_t ring_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_ring));
-        const uint32_t c_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_kj));
-        // thread -> 16-byte chunk c = tid & 31 of rows (tid >> 5) + 8 u: bit 3 of the row is u & 1
-        const int cw = tid & 31, rw = tid >> 5;
-        const uint32_t dst_even = (uint32_t)((rw * RF_B + (cw << 1)) * 8), dst_odd = (uint32_t)((rw * RF_B + ((cw ^ 4) << 1)) * 8);
-        auto issue_tile = [&](int slot, int I_, int J_) { // tile (I_, J_) of W^-1 and the A image of block I_: one group
-            const uint32_t base = ring_base + (uint32_t)(slot * STG * 8);
-            if ((I_ + 1) * RF_B <= N) {                   // interior tile (J_ <= I_): no bounds, one pointer bump per chunk
-                const double* src = q.W + (int64_t)(I_ * RF_B + rw) * q.ldw + J_ * RF_B + 2 * cw;
-#pragma unroll
-                for (int u = 0; u < (RF_B * RF_B / 2) / RF_THREADS; ++u)
-                    rf_cp16(base + ((u & 1) ? dst_odd : dst_even) + (uint32_t)(u * 8 * RF_B * 8), src + (int64_t)u * 8 * q.ldw, 16);
-            } else
-#pragma unroll
-            for (int u = 0; u < (RF_B * RF_B / 2) / RF_THREADS; ++u) {
-                const int id = tid + RF_THREADS * u, r = id >> 5, c = id & 31;
-                const int row = I_ * RF_B + r, col = J_ * RF_B + 2 * c;
-                const int bytes = row < N ? (col + 1 < N ? 16 : (col < N ? 8 : 0)) : 0;       // zero-fill beyond N
-                const double* src = q.W + (bytes ? (int64_t)row * q.ldw + col : 0);
-                rf_cp16(base + (uint32_t)((r * RF_B + ((c ^ (((r >> 3) & 1) << 2)) << 1)) * 8), src, bytes);
-            }
-            const double* a_src = q.img + ((size_t)I_ * 4 + (I_ == J_ ? 1 : 0)) * (P * RF_B);
-            for (int id = tid; id < P * RF_B / 2; id += RF_THREADS)
-                rf_cp16(base + (uint32_t)((RF_B * RF_B + 2 * id) * 8), a_src + 2 * id, 16);
-            asm volatile("cp.async.commit_group;\n" ::);
-        };
-        auto issue_column = [&](int J_) {                 // B image + plain copy of block J_ (adjacent in both places)
-            const double* c_src = q.img + ((size_t)J_ * 4 + 2) * (P * RF_B);
-            for (int id = tid; id < P * RF_B; id += RF_THREADS) rf_cp16(c_base + (uint32_t)(2 * id * 8), c_src + 2 * id, 16);
-            asm volatile("cp.async.commit_group;\n" ::);
+        // one stage: the tile of W^-1 as four panels of 16 observations i -- [64 rows j][128 B], 16-byte chunk c of row j at
+        // c ^ (j & 7) (the TMA engine's 128-byte swizzle) --, then the A image of block I.  W^-1 is symmetric: the tile is
+        // fetched from the mirrored position (rows J, columns I), so that a lane's two k-steps are ONE 16-byte load and
+        // the 8 rows x 4 chunks of a warp's load spread over all banks.
+        constexpr int STG = RF_TILE + P * RF_B;
+        const uint32_t ring0 = (smem_addr(s_ki) + 1023u) & ~1023u;
+        const uint32_t bar0 = smem_addr(s_bar);
+        const uint32_t col_bar = bar0 + 8 * 2 * RF_STAGES;
+        if (tid == 0) {
+            for (int i = 0; i < RF_STAGES; ++i) { mbar_init(bar0 + 8 * i, 1); mbar_init(bar0 + 8 * (RF_STAGES + i), RF_WARPS); }
+            mbar_init(col_bar, 1);
+            s_colcnt = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const int cnt = k1 - k0;
+        auto issue_column = [&](int J_) {                 // the image of block J_ as the fold's B operand (one thread)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(col_bar, P * RF_B * 8);
+            bulk_load(smem_addr(s_kj), q.img + (size_t)J_ * 4 * (P * RF_B), P * RF_B * 8, col_bar);
         };
         auto next_tile = [&](int& I_, int& J_) { if (++I_ == T) { ++J_; I_ = J_; } };
-        grid_dependency_wait();                           // the images are the pre-pass kernel's output
-        tk[1] = clock64();                                // (diagnostics: tk[2..4] accumulate issue / wait / contraction clocks)
-        int Ia = I, Ja = J, ka = k0;                      // the next tile to ask for
-        for (; ka < k1 && ka < k0 + RF_STAGES - 1; ++ka) { issue_tile(ka - k0, Ia, Ja); next_tile(Ia, Ja); }
-        for (int k = k0; k < k1; ++k) {
+        if (producer) {
+            // The ninth warp feeds the ring: local tile number n -> stage n % RF_STAGES, asked for again once all eight
+            // contracting warps have let go of it.  Per tile four tensor copies (one 16-column panel each; rows / columns
+            // beyond N arrive as zeros) and one bulk copy (the A image).  A copy instruction holds its thread until the TMA
+            // engine takes it (~600 clocks per tile when the contracting warps issued them themselves), hence a warp of its
+            // own.  The panels do not depend on the pre-pass: the first RF_STAGES tiles' go out before griddepcontrol.wait.
+            auto issue_panels = [&](int n, int I_, int J_) {
+                const int sg = n % RF_STAGES;
+                const uint32_t full = bar0 + 8 * sg;
+                mbar_expect_tx(full, (RF_TILE + P * RF_B) * 8);
+#pragma unroll
+                for (int pnl = 0; pnl < 4; ++pnl)
+                    tma_load_2d(ring0 + (uint32_t)(sg * STG * 8 + pnl * RF_B * 16 * 8), &wmap, I_ * RF_B + 16 * pnl, J_ * RF_B, full);
+            };
+            auto issue_image = [&](int n, int I_, int J_) {
+                const int sg = n % RF_STAGES;
+                bulk_load(ring0 + (uint32_t)((sg * STG + RF_TILE) * 8), q.img + ((size_t)I_ * 4 + (I_ == J_ ? 1 : 0)) * (P * RF_B),
+                          P * RF_B * 8, bar0 + 8 * sg);
+            };
+            const bool leader = elect_one();
+            int Ia = I, Ja = J, na = 0;
+            for (; na < cnt && na < RF_STAGES; ++na) { if (leader) issue_panels(na, Ia, Ja); next_tile(Ia, Ja); }
+            grid_dependency_wait();                       // the images are the pre-pass kernel's output
+            if (leader) {
+                int Ib = I, Jb = J;
+                for (int nb = 0; nb < na; ++nb) { issue_image(nb, Ib, Jb); next_tile(Ib, Jb); }
+                if (cnt > 0) issue_column(J);
+            }
+            for (; na < cnt; ++na) {
+                mbar_wait(bar0 + 8 * (RF_STAGES + na % RF_STAGES), (uint32_t)((na / RF_STAGES - 1) & 1));
+                if (leader) { issue_panels(na, Ia, Ja); issue_image(na, Ia, Ja); }
+                next_tile(Ia, Ja);
+            }
+        } else {
+        grid_dependency_wait();
+        tk[1] = clock64();                                // (diagnostics: tk[2..4] accumulate column / wait / contraction clocks)
+        uint32_t col_phase = 0;
+        for (int n = 0; n < cnt; ++n) {
             const long long c0 = clock64();
-            const bool new_col = J != curJ;
-            if (new_col) {
+            if (J != curJ) {
                 if (curJ >= 0) {
+                    mbar_wait(col_bar, col_phase);
+                    col_phase ^= 1u;
                     fold();
-                    __syncthreads();                      // everybody is done with the old column's image
+                    __syncwarp();
+                    if (lane == 0) {                      // the last warp to let go of the old column's image asks for the new one
+                        __threadfence_block();
+                        const unsigned int old = atomicAdd(&s_colcnt, 1u);
+                        if ((old & (RF_WARPS - 1)) == RF_WARPS - 1) { __threadfence_block(); issue_column(J); }
+                    }
+                    __syncwarp();
                 }
                 curJ = J;
-                issue_column(J);
             }
-            const bool issued_now = ka < k1;
-            if (issued_now) { issue_tile((ka - k0) % RF_STAGES, Ia, Ja); next_tile(Ia, Ja); ++ka; }
-            // groups younger than tile k's: the tiles k + 1 .. ka - 1.  At a column change the column's images were
-            // committed just before the tile issued in this iteration (if any): everything but that one is waited for
             const long long c1 = clock64();
-            const int younger = ka - 1 - k;
-            if (new_col) {
-                if (issued_now) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
-            } else if (younger <= 0) {
-                asm volatile("cp.async.wait_group 0;\n" ::);
-            } else if (younger == 1) {
-                asm volatile("cp.async.wait_group 1;\n" ::);
-            } else {
-                asm volatile("cp.async.wait_group 2;\n" ::);
-            }
-            __syncthreads();
+            mbar_wait(bar0 + 8 * (n % RF_STAGES), (uint32_t)((n / RF_STAGES) & 1));
             const long long c2 = clock64();
-            if (I == J) {                                 // partial mean: K_J alpha_J, 8 lanes per point
-                for (int idx = tid; idx < P * 8; idx += RF_THREADS) {
-                    const int a = idx >> 3, seg = idx & 7;
-                    double sacc = 0.0;
+            if (I == J && tid < P) s_m0[tid] += __ldcg(q.img + ((size_t)J * 4 + 3) * (P * RF_B) + tid);      // K_J alpha_J (pre-pass)
+            // B operand of k-step (p, h, e): W[i = 16 p + 8 h + 2 t + e][j = 8 w + g] = mirrored tile row 8 w + g, chunk 4 h + t
+            const uint32_t wrow = ring0 + (uint32_t)((n % RF_STAGES) * STG * 8 + (8 * warp + g) * 128);
+            // (odd rows load their two chunks in the other order, so that the two rows of a quarter-warp never meet in a bank)
+            const bool odd = (g & 1) != 0;
+            const uint32_t wc0 = (uint32_t)((((odd ? 4 : 0) + t) ^ g) << 4), wc1 = (uint32_t)((((odd ? 0 : 4) + t) ^ g) << 4);
+            const uint32_t img0 = ring0 + (uint32_t)(((n % RF_STAGES) * STG + RF_TILE) * 8 + lane * 16);
+            // (the loads are asm volatile like the DMMAs: source order is issue order, so panel pnl + 1 is asked for before
+            // the sixteen-clock-apart DMMAs of panel pnl are issued)
+            double2 la[2], lb[2], a0[2][NT], a1[2][NT];
+            auto load_panel = [&](int pnl, int bf) {
+                la[bf] = lds128(wrow + pnl * (RF_B * 16 * 8) + wc0);
+                lb[bf] = lds128(wrow + pnl * (RF_B * 16 * 8) + wc1);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int n = J * RF_B + seg * 8 + u;
-                        sacc = fma(s_kp[a * RF_B + seg * 8 + u], n < N ? q.alpha[n] : 0.0, sacc);
-                    }
-                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-                    if (seg == 0) s_m0[a] += sacc;
+                for (int mt = 0; mt < NT; ++mt) {
+                    a0[bf][mt] = lds128(img0 + (uint32_t)(((mt * 8 + 2 * pnl) * 32) * 16));
+                    a1[bf][mt] = lds128(img0 + (uint32_t)(((mt * 8 + 2 * pnl + 1) * 32) * 16));
                 }
+            };
+            load_panel(0, 0);
+#pragma unroll
+            for (int pnl = 0; pnl < 4; ++pnl) {
+                const int bf = pnl & 1;
+                if (pnl + 1 < 4) load_panel(pnl + 1, bf ^ 1);
+                const double2 w0 = odd ? lb[bf] : la[bf], w1 = odd ? la[bf] : lb[bf];
+                // two accumulator sets: a DMMA waits ~110 clocks for the one before it on the same accumulator, and NT chains
+                // per warp (two warps per tensor pipe) leave the pipe idle 1 clock in 8
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) dmma884(U[mt][0], U[mt][1], a0[bf][mt].x, w0.x);
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) dmma884(U2[mt][0], U2[mt][1], a0[bf][mt].y, w0.y);
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) dmma884(U[mt][0], U[mt][1], a1[bf][mt].x, w1.x);
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) dmma884(U2[mt][0], U2[mt][1], a1[bf][mt].y, w1.y);
             }
-            // B operand: W[32 c + 8 t + s][8 w + g] from the swizzled tile; bit 3 of the row is t & 1 for every (c, s)
-            const int col = 8 * warp + g;
-            const double* st = s_ring + ((k - k0) % RF_STAGES) * STG;
-            const double* wt = st + 8 * t * RF_B + ((((col >> 1) ^ ((t & 1) << 2)) << 1) + (col & 1));
-            const double2* ka2 = reinterpret_cast<const double2*>(st + RF_B * RF_B);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                double a[NT][8], wv[8];
-#pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8) wv[s8] = wt[(32 * c + s8) * RF_B];
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const double2 v = ka2[((mt * 2 + c) * 4 + qq) * 32 + lane];
-                        a[mt][2 * qq] = v.x;
-                        a[mt][2 * qq + 1] = v.y;
-                    }
-#pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8)
-#pragma unroll
-                    for (int mt = 0; mt < NT; ++mt) dmma884(U[mt][0], U[mt][1], a[mt][s8], wv[s8]);
-            }
-            __syncthreads();                              // this stage is free for the tile RF_STAGES further on
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (RF_STAGES + n % RF_STAGES));      // this warp is done with the stage
             next_tile(I, J);
             const long long c3 = clock64();
             tk[2] += c1 - c0; tk[3] += c2 - c1; tk[4] += c3 - c2;
         }
+        if (cnt > 0) {
+            mbar_wait(col_bar, col_phase);
+            fold();
+        }
         tk[2] += tk[1]; tk[3] += tk[2]; tk[4] += tk[3];   // so that the differences printed below are the three sums
+        }
     } else {
     if (k0 < k1) load_w(w_nxt, I, J);
     for (int k = k0; k < k1; ++k) {
@@ -651,12 +702,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const __gr
         if (k == k0) tk[4] = clock64();
     }
     }
-    if (k0 < k1) fold();                                  // (a CTA without tiles only pads its cluster: its partial is zero)
+    if (!STREAM && k0 < k1) fold();                       // (a CTA without tiles only pads its cluster: its partial is zero)
     __syncthreads();
     tk[5] = clock64();
 
     // ---- A summed over the 8 warps (fixed order), symmetrised, and handed over together with the partial mean
     double* s_z8 = s_ki;                                  // [8][P * P], over the dead images (4 P 64 >= 8 P P for P <= 32)
+    if (!producer)
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
