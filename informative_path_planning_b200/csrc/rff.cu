@@ -14,6 +14,34 @@
 
 namespace ipp {
 
+// cos(x) in ~14 FP64 instructions, branch-free for |x| < 8e5 (phases here are W . x + b with |x| <= a few tens): Cody-Waite
+// reduction by pi/2 in three pieces (the first two have 33 significant bits, so their products with k < 2^20 are exact),
+// then the fdlibm kernel polynomials on |r| <= pi/4 (< 1 ulp), sine or cosine by the parity of the quadrant with the
+// coefficients selected instead of branching.  libdevice's cos() costs ~2.5x as many FP64-pipe slots -- the pipe the
+// DMMAs of the grid stage share -- and made the feature pass compute-bound (3 ms for 2^20 x 1000 features against 1.3 ms
+// for writing them).
+__device__ __forceinline__ double cos_fast(double x) {
+    if (!(fabs(x) < 8.0e5)) return cos(x);
+    const double kf = fma(x, 0.63661977236758134308, 6755399441055744.0);     // k = rint(x 2 / pi) in the low word
+    const int k = __double2loint(kf);
+    const double kd = kf - 6755399441055744.0;
+    double r = fma(kd, -1.57079632673412561417e+00, x);
+    r = fma(kd, -6.07710050630396597660e-11, r);
+    r = fma(kd, -2.02226624879595063154e-21, r);
+    const bool odd = (k & 1) != 0;                        // quadrant 0: cos r, 1: -sin r, 2: -cos r, 3: sin r
+    const double z = r * r;
+    double p = odd ? 1.58969099521155010221e-10 : -1.13596475577881948265e-11;
+    p = fma(p, z, odd ? -2.50507602534068634195e-08 : 2.08757232129817482790e-09);
+    p = fma(p, z, odd ? 2.75573137070700676789e-06 : -2.75573143513906633035e-07);
+    p = fma(p, z, odd ? -1.98412698298579493134e-04 : 2.48015872894767294178e-05);
+    p = fma(p, z, odd ? 8.33333333332248946124e-03 : -1.38888888888741095749e-03);
+    p = fma(p, z, odd ? -1.66666666666666324348e-01 : 4.16666666666666019037e-02);
+    const double u = (odd ? r : z) * z;                   // r^3 or r^4
+    const double base = odd ? r : fma(-0.5, z, 1.0);
+    const double v = fma(u, p, base);
+    return ((k + 1) & 2) ? -v : v;
+}
+
 template <int D, int SC>
 __global__ void __launch_bounds__(256) rff_eval_kernel(const double* __restrict__ W, const double* __restrict__ b,
                                                        const double* __restrict__ theta, int F, int S, int shared_w,
@@ -37,7 +65,7 @@ __global__ void __launch_bounds__(256) rff_eval_kernel(const double* __restrict_
                 double ph = b[f];
 #pragma unroll
                 for (int d = 0; d < D; ++d) ph = fma(W[f * D + d], x[d], ph);
-                const double c = cos(ph);
+                const double c = cos_fast(ph);
 #pragma unroll
                 for (int j = 0; j < SC; ++j)
                     if (s0 + j < S) acc[j] = fma(theta[(int64_t)(s0 + j) * F + f], c, acc[j]);
@@ -54,7 +82,7 @@ __global__ void __launch_bounds__(256) rff_eval_kernel(const double* __restrict_
                         double ph = bs[f];
 #pragma unroll
                         for (int d = 0; d < D; ++d) ph = fma(Ws[f * D + d], x[d], ph);
-                        a = fma(ts[f], cos(ph), a);
+                        a = fma(ts[f], cos_fast(ph), a);
                     }
                     acc[j] = a;
                 }
@@ -160,7 +188,7 @@ __global__ void __launch_bounds__(256) rff_phi_kernel(const double* __restrict__
             double ph = bf;
 #pragma unroll
             for (int d = 0; d < D; ++d) ph = fma(w[d], sx[r][d], ph);
-            Phi[(int64_t)(r0 + r) * ldf + f] = cos(ph);
+            Phi[(int64_t)(r0 + r) * ldf + f] = cos_fast(ph);
         }
     }
 }
@@ -179,47 +207,105 @@ struct RffGemmArgs {
     int nparts, part0;                           // this chunk's m-tiles write columns part0 + blockIdx.x
 };
 
+// Phi (128 grid points) x Theta^T (up to 8 NB samples) with the per-sample arg-max in the epilogue.  The eight warps split
+// the 128 rows (16 each) and every warp spans ALL sample columns, so the tile is 8 NB wide instead of a multiple of 128:
+// S = 100 (config 4) runs as NB = 13 -- 104 columns, 4 % of the DMMAs on padding where the 128-wide tile spent 22 %.
+// Pipeline, swizzle and k-permutation are dgemm_dmma.cuh's (3 stages x (A 32 KB + B 32 KB), B rows >= S zero-filled).
+template <int NB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGemmArgs p) {
+    static_assert(GEMM_THREADS == 256 && NB >= 1 && NB <= 16, "eight warps, at most 128 sample columns per tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_val[Cfg::WARPS_M][BN];
-    __shared__ int s_row[Cfg::WARPS_M][BN];
+    __shared__ double s_val[8][BN];
+    __shared__ int s_row[8][BN];
     const uint32_t smem_base = smem_u32(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wmi = warp / Cfg::WARPS_N;
-    const int wm0 = wmi * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
+    const int wm0 = 16 * warp;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
-    double acc[MI][NI][2];
+    double acc[2][NB][2];
 #pragma unroll
-    for (int i = 0; i < MI; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    gemm_mainloop(smem_base, p.Phi, p.ldf, m0, p.Gc, p.Th, p.ldf, n0, p.S, 0, p.F, acc, tid, wm0, wn0, g, t);
+        for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    {
+        const int KT = (p.F + BK - 1) / BK;
+        TileLoader la, lb;
+        la.init(p.Phi, p.ldf, m0, p.Gc, tid);
+        lb.init(p.Th, p.ldf, n0, p.S, tid);
+        const bool late_loader = (warp & 4) != 0;         // see gemm_mainloop: the two warps of a sub-partition prefetch in turn
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < KT) {
+                la.load(smem_base + s * STAGE_BYTES, s * BK, p.F);
+                lb.load(smem_base + s * STAGE_BYTES + TILE_BYTES, s * BK, p.F);
+            }
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < KT; ++kt) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            const int nk = kt + STAGES - 1;
+            const uint32_t nst = smem_base + (nk % STAGES) * STAGE_BYTES;
+            const uint32_t sA = smem_base + (kt % STAGES) * STAGE_BYTES, sB = sA + TILE_BYTES;
+            if (!late_loader) {
+                if (nk < KT) { la.load(nst, nk * BK, p.F); lb.load(nst + TILE_BYTES, nk * BK, p.F); }
+                cp_async_commit();
+            }
+#pragma unroll
+            for (int kg = 0; kg < BK / 8; ++kg) {
+                if (kg == BK / 16 && late_loader) {
+                    if (nk < KT) { la.load(nst, nk * BK, p.F); lb.load(nst + TILE_BYTES, nk * BK, p.F); }
+                    cp_async_commit();
+                }
+                const uint32_t chunk = (uint32_t)(((4 * kg + t) ^ ((g & 1) << 2)) << 4);
+                constexpr int JG = NB > 13 ? NB / 2 : NB;       // B fragments held at a time (registers: 128 accumulators at NB = 16)
+                double2 a[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = lds128(sA + (wm0 + 8 * i + g) * ROW_BYTES + chunk);
+#pragma unroll
+                for (int j0 = 0; j0 < NB; j0 += JG) {
+                    double2 b[JG];
+#pragma unroll
+                    for (int j = 0; j < JG; ++j) b[j] = lds128(sB + (8 * (j0 + j) + g) * ROW_BYTES + chunk);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < JG; ++j) dmma884(acc[i][j0 + j][0], acc[i][j0 + j][1], a[i].x, b[j].x);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < JG; ++j) dmma884(acc[i][j0 + j][0], acc[i][j0 + j][1], a[i].y, b[j].y);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
 
     if (p.values) {
 #pragma unroll
-        for (int i = 0; i < MI; ++i) {
+        for (int i = 0; i < 2; ++i) {
             const int row = m0 + wm0 + 8 * i + g;
             if (row >= p.Gc) continue;
 #pragma unroll
-            for (int j = 0; j < NI; ++j)
+            for (int j = 0; j < NB; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int col = n0 + wn0 + 8 * j + 2 * t + e;
+                    const int col = n0 + 8 * j + 2 * t + e;
                     if (col < p.S) p.values[(int64_t)col * p.G + p.g0 + row] = acc[i][j][e];
                 }
         }
     }
     // per sample column: (max, first row attaining it) over the tile's 128 grid points
 #pragma unroll
-    for (int j = 0; j < NI; ++j)
+    for (int j = 0; j < NB; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             double v = -INFINITY;
             int row = 0x7fffffff;
 #pragma unroll
-            for (int i = 0; i < MI; ++i) {          // rows ascend with i: strict > keeps the first maximum
+            for (int i = 0; i < 2; ++i) {              // rows ascend with i: strict > keeps the first maximum
                 const int r = m0 + wm0 + 8 * i + g;
                 if (r < p.Gc && acc[i][j][e] > v) { v = acc[i][j][e]; row = r; }
             }
@@ -230,21 +316,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGem
                 if (ov > v || (ov == v && orow < row)) { v = ov; row = orow; }
             }
             if (g == 0) {
-                s_val[wmi][wn0 + 8 * j + 2 * t + e] = v;
-                s_row[wmi][wn0 + 8 * j + 2 * t + e] = row;
+                s_val[warp][8 * j + 2 * t + e] = v;
+                s_row[warp][8 * j + 2 * t + e] = row;
             }
         }
     __syncthreads();
-    if (tid < BN && n0 + tid < p.S) {
+    if (tid < 8 * NB && n0 + tid < p.S) {
         double v = s_val[0][tid];
         int row = s_row[0][tid];
 #pragma unroll
-        for (int w = 1; w < Cfg::WARPS_M; ++w)
+        for (int w = 1; w < 8; ++w)
             if (s_val[w][tid] > v || (s_val[w][tid] == v && s_row[w][tid] < row)) { v = s_val[w][tid]; row = s_row[w][tid]; }
         const int64_t slot = (int64_t)(n0 + tid) * p.nparts + p.part0 + blockIdx.x;
         p.part_val[slot] = v;
         p.part_idx[slot] = (row == 0x7fffffff) ? INT64_MAX : p.g0 + row;
     }
+}
+
+template <int NB>
+static int rff_gemm_launch(const RffGemmArgs& p, dim3 tiles, cudaStream_t s) {
+    IPP_OPT_IN_SMEM(rff_gemm_argmax_kernel<NB>, GEMM_SMEM);
+    rff_gemm_argmax_kernel<NB><<<tiles, GEMM_THREADS, GEMM_SMEM, s>>>(p);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
 }
 
 static int64_t rff_chunk_rows(int64_t G) { return G < RFF_CHUNK ? round_up(G, BM) : RFF_CHUNK; }
@@ -269,7 +363,6 @@ extern "C" int ipp_rff_eval_argmax(const double* W, const double* b, const doubl
     IPP_CHECK_ARG(F >= 1 && S >= 1 && G >= 1 && F < (1 << 30) && S < (1 << 30), "bad shape");
     IPP_CHECK_ARG(D == 2 || D == 3, "dimension must be 2 or 3");
     if (rff_use_gemm(S, shared_w)) {
-        IPP_OPT_IN_SMEM(rff_gemm_argmax_kernel, GEMM_SMEM);
         const int64_t ldf = round_up(F, 16), gc_max = rff_chunk_rows(G);
         const int nparts = (int)((G + BM - 1) / BM);
         double* Phi = work;
@@ -290,8 +383,10 @@ extern "C" int ipp_rff_eval_argmax(const double* W, const double* b, const doubl
             p.part_val = part_val; p.part_idx = part_idx;
             p.nparts = nparts; p.part0 = (int)(g0 / BM);
             dim3 tiles((gc + BM - 1) / BM, (unsigned)((S + BN - 1) / BN));
-            rff_gemm_argmax_kernel<<<tiles, GEMM_THREADS, GEMM_SMEM, s>>>(p);
-            IPP_LAUNCH_CHECK();
+            const int nb = S > BN ? 16 : (int)((S + 7) / 8);              // tile width: 8 nb sample columns
+            const int rc = nb <= 4 ? rff_gemm_launch<4>(p, tiles, s) : nb <= 8 ? rff_gemm_launch<8>(p, tiles, s)
+                         : nb <= 13 ? rff_gemm_launch<13>(p, tiles, s) : rff_gemm_launch<16>(p, tiles, s);
+            if (rc != IPP_OK) return rc;
         }
         rff_argmax_finalize_kernel<<<(unsigned)S, 256, 0, s>>>(part_val, part_idx, nparts, max_val, arg_max);
         IPP_LAUNCH_CHECK();
