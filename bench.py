@@ -20,7 +20,8 @@ this run, every N):
   mcts_*       dpw tree search, horizon 5, 250 rollouts, Dubins fan, N=900 observations (BASELINE config 2 shape): reward
                evals/s and rollouts/s over the rollout loop -- the loop the reference itself times and prints
                (mcts_library.py:689-700) -- for UCB and MES, the CPU oracle planner beside it (N=1 only) and whether the root
-               visit counts agree; at N > 1 the search is root-parallel (250 rollouts per rank, one all_reduce)
+               visit counts agree; at N > 1 the search is root-parallel (250 rollouts per rank, one all_reduce);
+               mcts_n4096_* (N=1): the same search over a belief of N=4096 observations, the size the metric is quoted on
   config5_*    BASELINE config 5, STRONG scaling: 65536 candidate Dubins paths x 20 samples generated on the device, N=4096,
                whole paths sharded across the ranks, rewards returned by one NCCL all_gather
   replicate_*  one k=4 observation block replicated at N=4096: 'recompute' (broadcast the block, every rank appends)
@@ -301,6 +302,12 @@ def bench_tree_search(parallel, rank, world, barrier, with_cpu):
             out[tag + '_planning_step_ms'] = 1e3 * g['seconds']
             if f_rew == 'mean':
                 visits = g['root_visits']
+        # the same search over the belief size the metric is quoted on (N = 4096: the streaming form of the rollout kernel)
+        bm.run('gpu', 4096, 'mean', budget=20)
+        g = min((bm.run('gpu', 4096, 'mean') for _ in range(3)), key=lambda r: r['loop_seconds'])
+        out['mcts_n4096_reward_evals_per_s'] = g['loop_reward_evals_per_s']
+        out['mcts_n4096_rollouts_per_s'] = g['loop_rollouts_per_s']
+        out['mcts_n4096_planning_step_ms'] = 1e3 * g['seconds']
         if with_cpu:
             c = bm.run('cpu', 900, 'mean')
             out['mcts_cpu_reward_evals_per_s'] = c['loop_reward_evals_per_s']

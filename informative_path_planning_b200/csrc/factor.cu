@@ -10,160 +10,142 @@
 // and W^-1 = U U^T is a lower-tile GEMM whose contraction starts at max(m0, n0), mirrored on store.
 #include "internal.cuh"
 #include "dgemm_dmma.cuh"
+#include <type_traits>
+#include <utility>
 
 namespace ipp {
 
 constexpr int NB = 64;
 constexpr int DIAG_LD = NB + 1;
-constexpr int DIAG_SMEM = (2 * NB * DIAG_LD + 32 * 33 + NB) * 8;
-__device__ long long g_potrf_clock[4];       // SM clocks of the last diagonal block: load, pivots, inverse, store (diagnostics)
+__device__ long long g_potrf_clock[4];       // SM clocks of the last diagonal block: load, pivots + inverse, -, store (diagnostics)
 
 // Cholesky of the jb x jb lower block at A (leading dimension lda) + its inverse into dinv[64][64].
 //
-// r1 version: 3 barriers, a division per column entry and two integer divisions per updated element for each of the 64
-// pivots, then 64 threads each running a serial O(n^2) substitution -- 100 us per block, 40 % of a refresh at N = 4096
-// (profiles/r2a_launches_factor_4096.csv).  Now:
-//   * one barrier per pivot.  16 x 16 threads own the elements cyclically; every thread takes the pivot d = a[j][j] and
-//     forms r = 1 / sqrt(d) itself (rsqrt_fast: four dependent operations after the hardware approximation), scales the
-//     column entries of its rows and columns and applies  a[i][k] -= (a[i][j] r) (a[k][j] r)  from the UNSCALED column still
-//     in shared memory; the scaled column goes to a second array, so nothing has to be re-read after a barrier;
-//   * the triangular inverse by recursive doubling with all 256 threads: the eight 8 x 8 diagonal blocks by substitution
-//     in registers (reciprocal pivots already known), then Linv21 = -Linv22 (L21 Linv11) for block sizes 8, 16, 32.
+// r1: 3 barriers, a division per column entry and two integer divisions per updated element for each of the 64 pivots,
+// then 64 threads each running a serial O(n^2) substitution -- 100 us per block.  r2a: one barrier per pivot, the block
+// updated in shared memory by 16 x 16 threads, inverse by recursive doubling -- 44 us (757 clocks per pivot against ~200 of
+// dependency chain: every pivot re-read and re-wrote its thread's 16 elements through shared memory).  Now the block
+// LIVES IN REGISTERS: warp w owns the columns w, w + 8, ... and lane l the rows l, l + 32 of each (16 elements per thread),
+// the pivot loop is unrolled by column slot so every register index is a constant, and per pivot
+//   * the owning warp takes the pivot from the lane that holds row j (one shuffle), forms r = 1 / sqrt(d) (rsqrt_fast),
+//     scales its column and puts the 64 scaled entries (+ r) into shared memory -- the only thing that ever goes there;
+//   * one barrier (the column buffer is double-buffered);
+//   * every thread reads the two entries of its rows and the (at most eight) entries of its columns and applies the
+//     rank-1 update to its registers;
+//   * the INVERSE rides along: with B = I at the start, row j of L^-1 is B[j][:] r and B[i][:] -= l_ij (row j) for i > j
+//     -- the same rank-1 pattern; row j of a warp's columns sits in one lane, so it is broadcast by shuffles, no barrier.
+//     (The r2a version ran the inverse as a second phase, recursive doubling through shared memory.)
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t lda, int jb,
                                                          double* __restrict__ dinv, double* logdet,
                                                          int32_t* info, int j0) {
-    extern __shared__ double sm[];
-    double (*a)[DIAG_LD] = reinterpret_cast<double (*)[DIAG_LD]>(sm);                      // working copy, later L^-1
-    double (*l)[DIAG_LD] = reinterpret_cast<double (*)[DIAG_LD]>(sm + NB * DIAG_LD);       // the factor
-    double (*tmp)[33] = reinterpret_cast<double (*)[33]>(sm + 2 * NB * DIAG_LD);           // L21 Linv11
-    double* rinv = sm + 2 * NB * DIAG_LD + 32 * 33;                                       // 1 / L[j][j]
+    __shared__ double tile[NB][DIAG_LD];          // staging: A on the way in, L and L^-1 on the way out (coalesced I/O)
+    __shared__ double colbuf[2][NB];              // the scaled column of the current pivot
+    __shared__ double rbuf[NB], dbuf[NB];         // 1 / l_jj, l_jj
     __shared__ int bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t0 = clock64();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 6, c = idx & 63;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
-        a[r][c] = v;
-        l[r][c] = (r == c && r >= jb) ? 1.0 : 0.0;
+    {
+        double v[16];                             // all sixteen loads of a thread in flight before the first store
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int r = (tid >> 6) + 4 * u, c = tid & 63;
+            v[u] = (r == c) ? 1.0 : 0.0;          // rows / columns beyond jb: identity
+            if (r < jb && c <= r) v[u] = A[(int64_t)r * lda + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tile[(tid >> 6) + 4 * u][tid & 63] = v[u];
     }
-    if (tid < NB) rinv[tid] = 1.0;
     if (tid == 0) bad = 0;
     __syncthreads();
-    // 16 x 16 threads, cyclic in both directions: thread (ty, tx) owns the elements (ty + 16 i, tx + 16 m) -- the trailing
-    // block shrinks towards the bottom-right corner and a cyclic layout keeps every thread busy until the end
-    const int ty = tid >> 4, tx = tid & 15;
+    double a[2][8], B[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            a[i][m] = tile[lane + 32 * i][warp + 8 * m];
+            B[i][m] = (lane + 32 * i == warp + 8 * m) ? 1.0 : 0.0;
+        }
     const long long t1 = clock64();
-    for (int j = 0; j < jb; ++j) {
-        double d = a[j][j];
-        if (!(d > 0.0)) {                // also catches NaN, like LAPACK's dpotrf
-            if (tid == 0 && bad == 0) bad = j + 1;
-            d = 1.0;
-        }
-        const double r = rsqrt_fast(d);
-        if (tid == 0) { l[j][j] = d * r; rinv[j] = r; }
-        // element blocks (i, m) = rows ty + 16 i, columns tx + 16 m.  Blocks that lie entirely at or before the pivot
-        // (16 i + 15 <= j, 16 m + 15 <= j) and above the diagonal (m > i) are skipped with conditions that depend on j
-        // only -- the same for every thread, so they are real branches, not predicated-off instructions: without them
-        // the late pivots issue as many instructions as the first (measured 711 clocks per pivot)
-        const int first = (j + 1) >> 4;
-        double cr[4], cc[4], old[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (i < first) continue;
-            const int row = ty + 16 * i, col = tx + 16 * i;
-            cr[i] = (row > j && row < jb) ? a[row][j] * r : 0.0;     // the UNSCALED column is still in place: no barrier
-            cc[i] = (col > j && col < jb) ? a[col][j] * r : 0.0;     // between scaling it and using it
-        }
-        // all loads before the first store (the compiler cannot prove that the stores do not alias the later loads)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int m = 0; m <= i; ++m) {
-                if (m < first) continue;
-                const int row = ty + 16 * i, col = tx + 16 * m;
-                old[i][m] = (col > j && col <= row && row < jb) ? a[row][col] : 0.0;
-            }
-        if (tx == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = ty + 16 * i;
-                if (i >= first && row > j && row < jb) l[row][j] = cr[i];
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int m = 0; m <= i; ++m) {
-                if (m < first) continue;
-                const int row = ty + 16 * i, col = tx + 16 * m;
-                if (col > j && col <= row && row < jb) a[row][col] = fma(-cr[i], cc[m], old[i][m]);
-            }
-        __syncthreads();
-    }
-    // ---- L^-1 into `a`.  8 x 8 diagonal blocks: thread (block, column) substitutes in registers
-    const long long t2 = clock64();
-    for (int idx = tid; idx < NB * NB; idx += 256) a[idx >> 6][idx & 63] = 0.0;
-    __syncthreads();
-    if (tid < NB) {
-        const int b8 = (tid >> 3) * 8, c = tid & 7;
-        double x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < i) sacc = fma(l[b8 + i][b8 + k], (k >= c) ? x[k] : 0.0, sacc);
-            x[i] = (i < c) ? 0.0 : ((i == c) ? rinv[b8 + i] : -sacc * rinv[b8 + i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[b8 + i][b8 + c] = x[i];
-    }
-    __syncthreads();
-    // ---- doubling: blocks of size s -> 2 s.  Pair p: rows R0 = 2 s p + s .. + s, columns C0 = 2 s p .. + s
+    // The eight pivots j = 8 MJ + w8 of column slot MJ share one copy of the code (register indices depend on MJ only;
+    // a fully unrolled loop -- 64 copies, ~160 KB of instructions -- ran at 470-520 clocks per pivot, bound by
+    // instruction fetch: no line was ever executed twice).
+    auto slot = [&](auto mjc) {
+        constexpr int MJ = decltype(mjc)::value, IJ = MJ >> 2;
 #pragma unroll 1
-    for (int s = 8, sh = 3; s < NB; s <<= 1, ++sh) {
-        const int outs = 32 * s;                         // (NB / 2 s) pairs x s x s
-        for (int idx = tid; idx < outs; idx += 256) {    // tmp = L21 Linv11
-            const int p = idx >> (2 * sh), rr = (idx >> sh) & (s - 1), cc = idx & (s - 1);
-            const int R0 = 2 * s * p + s, C0 = 2 * s * p;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-            for (int k = cc & ~1; k < s; k += 2) {       // Linv11 is lower triangular: rows k >= cc only
-                s0 = fma(l[R0 + rr][C0 + k], a[C0 + k][C0 + cc], s0);
-                s1 = fma(l[R0 + rr][C0 + k + 1], a[C0 + k + 1][C0 + cc], s1);
+        for (int w8 = 0; w8 < 8; ++w8) {
+            const int j = 8 * MJ + w8, lj = j & 31;
+            if (warp == w8) {       // the owning warp takes d from the lane that holds row j, scales its column, publishes it
+                const double d0 = __shfl_sync(0xffffffffu, a[IJ][MJ], lj);
+                const bool ok = d0 > 0.0;                           // also catches NaN, like LAPACK's dpotrf
+                const double d = ok ? d0 : 1.0;
+                const double r = rsqrt_fast(d);
+                if (!ok && lane == 0 && bad == 0) bad = j + 1;
+#pragma unroll
+                for (int i = IJ; i < 2; ++i) {                      // (row slot 0 lies above the pivots of slots 4 .. 7)
+                    const int row = lane + 32 * i;
+                    const double v = row > j ? a[i][MJ] * r : (row == j ? d * r : 0.0);
+                    a[i][MJ] = v;
+                    colbuf[j & 1][row] = v;
+                }
+                if (lane == 0) { rbuf[j] = r; dbuf[j] = d * r; }
             }
-            tmp[(p << sh) + rr][cc] = s0 + s1;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < outs; idx += 256) {    // Linv21 = -Linv22 tmp
-            const int p = idx >> (2 * sh), rr = (idx >> sh) & (s - 1), cc = idx & (s - 1);
-            const int R0 = 2 * s * p + s, C0 = 2 * s * p;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-            for (int k = 0; k <= (rr | 1); k += 2) {     // Linv22 is lower triangular: columns k <= rr only
-                s0 = fma(a[R0 + rr][R0 + k], tmp[(p << sh) + k][cc], s0);
-                s1 = fma(a[R0 + rr][R0 + k + 1], tmp[(p << sh) + k + 1][cc], s1);
+            __syncthreads();
+            const double r = rbuf[j];
+            double lr[2] = {0.0, 0.0};
+#pragma unroll
+            for (int i = IJ; i < 2; ++i) lr[i] = (lane + 32 * i > j) ? colbuf[j & 1][lane + 32 * i] : 0.0;
+#pragma unroll
+            for (int m = MJ; m < 8; ++m) {                          // trailing update: columns c > j of this warp
+                const int c = warp + 8 * m;
+                if (c > j) {
+                    const double lc = colbuf[j & 1][c];
+#pragma unroll
+                    for (int i = IJ; i < 2; ++i) a[i][m] = fma(-lr[i], lc, a[i][m]);
+                }
             }
-            a[R0 + rr][C0 + cc] = -(s0 + s1);
+#pragma unroll
+            for (int m = 0; m <= MJ; ++m) {                         // inverse: row j becomes final, the rows below take their update
+                const int c = warp + 8 * m;
+                if (c <= j) {
+                    const double x = __shfl_sync(0xffffffffu, B[IJ][m], lj) * r;
+#pragma unroll
+                    for (int i = IJ; i < 2; ++i) B[i][m] = (lane + 32 * i == j) ? x : fma(-lr[i], x, B[i][m]);
+                }
+            }
         }
-        __syncthreads();
-    }
-    const long long t3 = clock64();
+    };
+    [&]<int... Ms>(std::integer_sequence<int, Ms...>) { (slot(std::integral_constant<int, Ms>{}), ...); }(std::make_integer_sequence<int, 8>{});
+    const long long t2 = clock64();
+    __syncthreads();
+    // ---- out: the factor into A (lower triangle of the jb x jb block), its inverse into dinv (zeros elsewhere)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) tile[lane + 32 * i][warp + 8 * m] = a[i][m];
+    __syncthreads();
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
-        if (r < jb && c <= r) A[(int64_t)r * lda + c] = l[r][c];
-        dinv[idx] = (r < jb && c <= r) ? a[r][c] : 0.0;
+        if (r < jb && c <= r) A[(int64_t)r * lda + c] = tile[r][c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) tile[lane + 32 * i][warp + 8 * m] = B[i][m];
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        dinv[idx] = (r < jb && c <= r) ? tile[r][c] : 0.0;
     }
     if (tid < 32) {
         double sacc = 0.0;
-        for (int j = tid; j < jb; j += 32) sacc += log(l[j][j]);
+        for (int j = tid; j < jb; j += 32) sacc += log(dbuf[j]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
         if (tid == 0) {
             if (logdet) *logdet += 2.0 * sacc;
             if (bad && info && *info == 0) *info = j0 + bad;
-            g_potrf_clock[0] = t1 - t0; g_potrf_clock[1] = t2 - t1; g_potrf_clock[2] = t3 - t2; g_potrf_clock[3] = clock64() - t3;
+            g_potrf_clock[0] = t1 - t0; g_potrf_clock[1] = t2 - t1; g_potrf_clock[2] = 0; g_potrf_clock[3] = clock64() - t2;
         }
     }
 }
@@ -174,14 +156,13 @@ __global__ void init_factor_scalars_kernel(double* logdet, int32_t* info) {
 }
 
 int potrf_lower(double* A, int64_t N, int64_t lda, double* dinv, double* logdet, int32_t* info, cudaStream_t s) {
-    IPP_OPT_IN_SMEM(potrf_diag_kernel, DIAG_SMEM);
     init_factor_scalars_kernel<<<1, 1, 0, s>>>(logdet, info);
     IPP_LAUNCH_CHECK();
     for (int64_t j0 = 0, blk = 0; j0 < N; j0 += NB, ++blk) {
         const int jb = (int)((N - j0) < NB ? (N - j0) : NB);
         double* Ajj = A + j0 * lda + j0;
         double* D = dinv + blk * NB * NB;
-        potrf_diag_kernel<<<1, 256, DIAG_SMEM, s>>>(Ajj, lda, jb, D, logdet, info, (int)j0);
+        potrf_diag_kernel<<<1, 256, 0, s>>>(Ajj, lda, jb, D, logdet, info, (int)j0);
         IPP_LAUNCH_CHECK();
         const int64_t rows = N - j0 - jb;
         if (rows <= 0) break;
