@@ -59,6 +59,11 @@ typedef struct ipp_rbf {
                                * params_host[0] = 2 pi e; level l's reward is params[0] * logdet(I + Cov(q_l | earlier levels)),
                                * the Schur form of logdet(I + vK([X; q])) - logdet(I + vK(X)).  At most 32 points per rollout. */
 
+#define IPP_REWARD_HOTSPOT 6  /* aq_library.py:117-135 hotspot_info_UCB = info_gain + mean_UCB, ipp_tree_search_dpw only: two device
+                               * passes per rollout over the same points -- IPP_REWARD_UCB on the regression belief (the function's
+                               * belief arguments, reward_param = sqrt(beta_t)) and IPP_REWARD_INFO on the information-gain belief
+                               * (ipp_tree_params.info_*) -- summed level by level.  At most 32 points per rollout. */
+
 /* variance formulations for ipp_gp_predict */
 #define IPP_VAR_WINV_SYM  0   /* var = v - k^T W^-1 k, W^-1 symmetric: lower tiles x2 + diagonal tiles (N^2 flops/query) */
 #define IPP_VAR_WINV_FULL 1   /* var = v - sum((W^-T Kx) * Kx): every tile, the reference's literal formula (2 N^2)     */
@@ -212,6 +217,18 @@ int ipp_rff_eval_argmax(const double* W, const double* b, const double* theta, i
 /* feature matrix Z[F][ldz] = scale * cos(W X^T + b) (aq_library.py:171) */
 int ipp_rff_features(const double* W, const double* b, int64_t F, int D, const double* X, int64_t N,
                      double scale, double* Z, int64_t ldz, void* stream);
+/* posterior weight draw of the sampler's N >= F branch (aq_library.py:195-200) in one call, nothing read back:
+ *      Z = sqrt(2 v / F) cos(W X^T + b),  Sigma = (Z Z^T / s2 + I)^-1,  theta = Sigma Z z / s2 + chol(Sigma) eps.
+ *      chol(Sigma) without forming or factoring Sigma: the system is factored with the features in reverse order
+ *      (A_r = L_r L_r^T  <=>  A = U U^T, U upper triangular, chol(Sigma) = U^-T exactly), so
+ *      theta_r = A_r^-1 (Z_r z) / s2 + L_r^-T eps_r: one ipp_pdinv-class factorisation and two products.
+ *      W [F][D], b [F], X [N][D], z [N], eps [F] (the reference's standard-normal draw), theta [F] out: all device;
+ *      info: 0, or != 0 when Z Z^T / s2 + I is not positive definite (np.linalg.LinAlgError in the reference);
+ *      work: ipp_rff_theta_workspace(F, N) doubles. */
+int64_t ipp_rff_theta_workspace(int64_t F, int64_t N);
+int ipp_rff_theta_draw(const double* W, const double* b, int64_t F, int D, const double* X, const double* z,
+                       int64_t N, double variance, double noise_var, const double* eps, double* theta,
+                       int32_t* info, double* work, void* stream);
 
 /* ---- building blocks exposed for tests and for info_gain (aq_library.py:34-80, Schur form):
  *      C[M][ldc] (and/or Ct[N][ldct]) = alpha * A[M][K] * B[N][K]^T + beta * C      (FP64 DMMA) */
@@ -299,7 +316,7 @@ int ipp_dubins_paths_device(const double* poses, const double* goals, int64_t P,
  *      creation order (goal index, visit count, reward sum); n_root[0] of them.  reward_evals[0]: path rewards scored.
  *      stage_host: PINNED host scratch, stage_dev: device scratch, each >= IPP_TREE_STAGE_DOUBLES doubles;
  *      work: ipp_rollout_workspace(N, IPP_ROLLOUT_MAX_POINTS) doubles on the device. */
-#define IPP_TREE_STAGE_DOUBLES (IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1) + 3 * IPP_ROLLOUT_MAX_LEVELS + 32)
+#define IPP_TREE_STAGE_DOUBLES (IPP_ROLLOUT_MAX_POINTS * (IPP_MAX_DIM + 1) + 6 * IPP_ROLLOUT_MAX_LEVELS + 32)
 typedef struct {
     uint32_t key[624];
     int32_t pos;
@@ -309,7 +326,7 @@ typedef struct {
 typedef struct {
     int32_t budget;        /* rollouts */
     int32_t max_depth;     /* rollout_length */
-    int32_t kind;          /* IPP_REWARD_UCB / EI / MES; IPP_REWARD_NAIVE (no device work at all) or IPP_REWARD_NAIVE_VALUE
+    int32_t kind;          /* IPP_REWARD_UCB / EI / MES / INFO / HOTSPOT; IPP_REWARD_NAIVE (no device work at all) or IPP_REWARD_NAIVE_VALUE
                             * (one small device pass per rollout); for the last two the belief pointers may be NULL */
     int32_t frontier_size;
     int32_t keep_every;    /* 10 */
@@ -346,6 +363,12 @@ typedef struct {
     /* BeliefTree: log_table[n] = np.log(float(n)) for n = 0 .. budget as the CALLER's numpy computes it (its SIMD log need
      * not agree with libm in the last bit; taking the caller's values keeps the UCB1 scores the interpreter's) */
     const double* log_table;
+    /* IPP_REWARD_HOTSPOT: the information-gain belief over the same observations X (see IPP_REWARD_INFO): its kernel
+     * (variance v^2), (I + v K)^-1 [N][info_ldw] on the device, and the scale 2 pi e */
+    const ipp_rbf* info_kern;
+    const double* info_winv;
+    int64_t info_ldw;
+    double info_param;
 } ipp_tree_params;
 int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* root_pose,
                         const ipp_rbf* kern, const double* X, int64_t N, const double* alpha,

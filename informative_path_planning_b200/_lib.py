@@ -17,7 +17,7 @@ IPP_MAX_DIM = 3
 IPP_APPEND_MAX_K = 32
 IPP_ROLLOUT_MAX_POINTS = 128
 IPP_ROLLOUT_MAX_LEVELS = 32
-REWARD_UCB, REWARD_EI, REWARD_MES, REWARD_NAIVE, REWARD_NAIVE_VALUE, REWARD_INFO = 0, 1, 2, 3, 4, 5
+REWARD_UCB, REWARD_EI, REWARD_MES, REWARD_NAIVE, REWARD_NAIVE_VALUE, REWARD_INFO, REWARD_HOTSPOT = 0, 1, 2, 3, 4, 5, 6
 IPP_ROLLOUT_INFO_MAX_POINTS = 32
 VAR_WINV_SYM, VAR_WINV_FULL, VAR_CHOL = 0, 1, 2
 
@@ -44,10 +44,12 @@ class IppTreeParams(ctypes.Structure):
                 ('rff_W', ctypes.c_void_p), ('rff_b', ctypes.c_void_p), ('rff_theta', ctypes.c_void_p),
                 ('naive_maxes', ctypes.c_void_p), ('rff_vals_dev', ctypes.c_void_p), ('rff_vals_host', ctypes.c_void_p),
                 ('rff_work', ctypes.c_void_p), ('generator', ctypes.c_int32), ('tree_type', ctypes.c_int32),
-                ('sample_step', ctypes.c_double), ('log_table', ctypes.c_void_p)]
+                ('sample_step', ctypes.c_double), ('log_table', ctypes.c_void_p),
+                ('info_kern', ctypes.c_void_p), ('info_winv', ctypes.c_void_p), ('info_ldw', ctypes.c_int64),
+                ('info_param', ctypes.c_double)]
 
 
-IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 3 * 32 + 32
+IPP_TREE_STAGE_DOUBLES = 128 * (IPP_MAX_DIM + 1) + 6 * 32 + 32
 
 
 def py_rng_state():
@@ -120,6 +122,8 @@ SIGNATURES = {
     'ipp_rff_workspace': (_I64, [_I64, _I64, _I64, _INT]),
     'ipp_rff_eval_argmax': (_INT, [_P, _P, _P, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
+    'ipp_rff_theta_workspace': (_I64, [_I64, _I64]),
+    'ipp_rff_theta_draw': (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _D, _D, _P, _P, _P, _P, _P]),
     'ipp_dgemm_nt': (_INT, [_I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, _P, _I64, _P]),
     'ipp_potrf_workspace': (_I64, [_I64]),
     'ipp_potrf_debug_clocks': (_INT, [_P]),

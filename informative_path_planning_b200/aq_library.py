@@ -499,37 +499,74 @@ def rff_theta_ul(Z_d, N, zvals, noise_var, eps, z_d=None):
     return (m + y).reshape(F, 1)
 
 
+def rff_theta_device(robot_model, W_d, b_d, eps_d, variance, nFeatures):
+    """One posterior weight draw of the N >= F branch (reference aq_library.py:195-200) entirely on the device, nothing
+    read back:  Sigma = (Z Z^T / s2 + I)^-1,  theta = Sigma Z z / s2 + chol(Sigma) eps  (ipp_rff_theta_draw: the system
+    is factored with the features in reverse order, which makes chol(Sigma) a by-product of the factorisation of A --
+    rff_theta_ul does the same with host LAPACK).
+    W_d (F, D), b_d (F), eps_d (F): device tensors.  Nothing here synchronises with the host.
+    Returns (theta [F], info [1] int32: != 0 when A is not positive definite), both on the device."""
+    F = int(nFeatures)
+    N = robot_model.xvals.shape[0]
+    dev = robot_model._X_d.device
+    z_d = getattr(robot_model, '_z_d', None)
+    if z_d is None:
+        z_d = L.to_device(np.asarray(robot_model.zvals, dtype=float).reshape(-1))
+    theta = torch.empty(F, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = L.workspace(L.lib.ipp_rff_theta_workspace(F, N), slot='rff_theta')
+    W_d, b_d, eps_d = W_d.contiguous(), b_d.reshape(-1).contiguous(), eps_d.reshape(-1).contiguous()
+    L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, int(W_d.shape[1]), L.ptr(robot_model._X_d), L.ptr(z_d), N,
+                                     float(variance), float(robot_model.noise), L.ptr(eps_d), L.ptr(theta), L.ptr(info),
+                                     L.ptr(work), L.stream_ptr()))
+    return theta, info
+
+
+def _grid_stage_device(target, guesses_d, dim, time, ax, gridSize=300):
+    """Grid stage of global_maximization (reference aq_library.py:455-479) for an RFFTarget, enqueued only: the 300 x 300
+    meshgrid (+ the data points as extra guesses when dim == 2) is assembled on the device from the 600 drawn coordinates
+    (ax = [x1; x2] on the device; torch indexing = plumbing); row g = (x1[g % 300], x2[g // 300]) as np.meshgrid 'xy'
+    ravels.  Returns (values, argmax)."""
+    G0 = gridSize * gridSize
+    cols = [ax[:gridSize].repeat(gridSize), ax[gridSize:].repeat_interleave(gridSize)]
+    if dim != 2:
+        cols.append(torch.full((G0,), float(time), dtype=torch.float64, device=ax.device))
+    grid_d = torch.stack(cols, dim=1)
+    if dim == 2:
+        grid_d = torch.cat([grid_d, guesses_d[:, :2]], dim=0)
+    vals, _, am = target.eval_device(grid_d.contiguous(), want_values=True)
+    return vals, am
+
+
 def global_maximization(target, target_vector_n, target_grad, target_vector_gradient_n, ranges, guesses, visualize,
-                        filename, obstacles, f_rew, time=None, guesses_d=None):
+                        filename, obstacles, f_rew, time=None, guesses_d=None, staged=None):
     """reference aq_library.py:444-553 without the plotting; the grid stage (:475-485) runs on the device
-    when `target` is an RFFTarget."""
+    when `target` is an RFFTarget.  `staged` = (x1, x2, values, argmax index, argmax index over the mesh points alone): the
+    grid draws were already made (in the reference's order) and the grid stage already ran (sample_max_vals' pipelined form)."""
     gridSize = 300
     bb = ((ranges[1] - ranges[0]) * 0.10, (ranges[3] - ranges[2]) * 0.10)
     ranges = (ranges[0] + bb[0], ranges[1] - bb[0], ranges[2] + bb[1], ranges[3] - bb[1])
     dim = guesses.shape[1]
-    x1 = np.random.uniform(ranges[0], ranges[1], size=gridSize)
-    x2 = np.random.uniform(ranges[2], ranges[3], size=gridSize)
+    am_mesh = None
+    if staged is not None:
+        x1, x2, vals, am_index, am_mesh = staged
+    else:
+        x1 = np.random.uniform(ranges[0], ranges[1], size=gridSize)
+        x2 = np.random.uniform(ranges[2], ranges[3], size=gridSize)
     if isinstance(target, RFFTarget):
-        # the 300 x 300 meshgrid (+ the data points as extra guesses when dim == 2) is assembled on the device from the
-        # 600 drawn coordinates (torch indexing = plumbing); row g = (x1[g % 300], x2[g // 300]) as np.meshgrid 'xy' ravels
-        ax = L.to_device(np.concatenate([x1, x2]))
         G0 = gridSize * gridSize
-        cols = [ax[:gridSize].repeat(gridSize), ax[gridSize:].repeat_interleave(gridSize)]
-        if dim != 2:
-            cols.append(torch.full((G0,), float(time), dtype=torch.float64, device=ax.device))
-        grid_d = torch.stack(cols, dim=1)
-        guesses_d = guesses_d if guesses_d is not None else L.to_device(guesses)
-        if dim == 2:
-            grid_d = torch.cat([grid_d, guesses_d[:, :2]], dim=0)
-        vals, _, am = target.eval_device(grid_d.contiguous(), want_values=True)
+        if staged is None:
+            guesses_d = guesses_d if guesses_d is not None else L.to_device(guesses)
+            vals, am = _grid_stage_device(target, guesses_d, dim, time, L.to_device(np.concatenate([x1, x2])), gridSize)
+            am_index = int(am.item())
 
         def point(g):
             if g < G0:
                 return np.array([x1[g % gridSize], x2[g // gridSize]] + ([float(time)] if dim != 2 else []))
             return np.asarray(guesses[g - G0, :], dtype=float)
-        start = point(int(am.item()))
+        start = point(am_index)
         if start[0] < ranges[0] or start[0] > ranges[1] or start[1] < ranges[2] or start[1] > ranges[3]:
-            start = point(int(torch.argmax(vals[:G0]).item()))
+            start = point(am_mesh if am_mesh is not None else int(torch.argmax(vals[:G0]).item()))
     else:
         x1, x2 = np.meshgrid(x1, x2, sparse=False, indexing='xy')
         if dim == 2:
@@ -553,9 +590,42 @@ def global_maximization(target, target_vector_n, target_grad, target_vector_grad
     return res['x'], -res['fun'], res['jac'], True
 
 
+PIPELINE_MAX_VALUE_SAMPLES = True
+_mv_buffers = {}
+
+
+def _mv_stage(i, n_up, n_down):
+    """Pinned staging of pipelined sample i on the current device: (upload buffer, download buffer), reused from call to
+    call (pinning a fresh buffer costs more than the whole sample).  The upload buffer is only handed out again once the
+    copy that last read it has run (_mv_guard's event)."""
+    key = (L.device().index, i, n_up, n_down)
+    st = _mv_buffers.get(key)
+    if st is None:
+        st = _mv_buffers[key] = {'up': torch.empty(n_up, dtype=torch.float64).pin_memory(),
+                                 'down': torch.empty(n_down, dtype=torch.float64).pin_memory(), 'event': None, 'key': key}
+    if st['event'] is not None:
+        st['event'].synchronize()
+    _mv_buffers['last', L.device().index, i] = st
+    return st['up'], st['down']
+
+
+def _mv_guard(i):
+    st = _mv_buffers['last', L.device().index, i]
+    st['event'] = torch.cuda.Event()
+    st['event'].record()
+
+
 def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstacles=None, f_rew='mes'):
     """reference aq_library.py:141-279.  Random draws come from the global np.random in the reference's
-    order (W, b, eps, then the grid draws of each optimisation attempt)."""
+    order (W, b, eps, then the grid draws of each optimisation attempt).
+
+    Pipelined form (N >= F, the usual case): the reference's samples only interact through the random stream, and the
+    stream's order is known as long as every weight draw succeeds and every optimisation succeeds at its FIRST attempt.
+    So all draws of all nK samples are made up front in exactly that order, the device work of every sample (features,
+    F x F x N product, factorisation, weight draw, 300 x 300 grid stage, arg-max) is enqueued without a single
+    synchronisation, and the host then polishes sample i with SLSQP while the device is still busy with i + 1.  If a
+    sample does break the assumption (not positive definite, or SLSQP fails and the reference would redraw the grid), the
+    stream is put back to where the reference's would be at that point and the rest runs one sample at a time."""
     _require_model(robot_model)
     if robot_model.xvals is None:
         return None, None, None
@@ -566,42 +636,121 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
     delete_locs = []
     variance = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
     N_obs = robot_model.xvals.shape[0]
-    for i in range(nK):
-        ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
+    ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
+    gridSize = 300
+    rg = robot_model.ranges
+    bb = ((rg[1] - rg[0]) * 0.10, (rg[3] - rg[2]) * 0.10)
+    inner = (rg[0] + bb[0], rg[1] - bb[0], rg[2] + bb[1], rg[3] - bb[1])
+
+    def draw_weights():
         W = np.random.normal(loc=0.0, scale=np.sqrt(1. / ls), size=(nFeatures, d))
         b = 2 * np.pi * np.random.uniform(low=0.0, high=1.0, size=(nFeatures, 1))
-        W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))           # uploaded once: features now, the sampled function later
-        Z_d = rff_features_device(W_d, b_d, robot_model._X_d, variance, nFeatures)
         eps = np.random.normal(loc=0.0, scale=1.0, size=(nFeatures, 1))
-        try:
-            if N_obs >= nFeatures:      # (:195-200) F x F x N product on the device, UL factor + three solves on the host
-                theta = rff_theta_ul(Z_d, N_obs, robot_model.zvals, robot_model.noise, eps,
-                                     z_d=getattr(robot_model, '_z_d', None))
-            else:                       # N x N eigendecomposition (:177-187): small dense LAPACK on the host
-                Z = np.ascontiguousarray(Z_d[:, :N_obs].cpu().numpy())
-                theta = _rff_theta(Z, robot_model.zvals, robot_model.noise, eps, nFeatures)
-        except Exception:
-            delete_locs.append(i)
-            continue
+        return W, b, eps
+
+    def make_target(W, b, theta, W_d, b_d, theta_d):
         target = RFFTarget(variance, nFeatures, W, theta, b)
-        target._dev = (W_d, b_d, L.to_device(theta.reshape(-1) * target.scale))
+        target._dev = (W_d, b_d, theta_d if theta_d is not None else L.to_device(theta.reshape(-1) * target.scale))
+        return target
+
+    def polish(i, target, staged=None, count=0):
+        """The optimisation attempts of sample i (reference :237-262); `staged` serves the first one."""
         target_vector_n = lambda x, tg=target: -tg.scalar(x)
         target_vector_gradient_n = lambda x, tg=target: -np.asarray(tg.gradient(x).reshape(d, ))
         status = False
-        count = 0
         while status is False and count < 5:
             maxima, max_val, _, status = global_maximization(target, target_vector_n, target.gradient,
                                                              target_vector_gradient_n, robot_model.ranges,
                                                              robot_model.xvals, visualize, 't%s.nK%s' % (t, i),
                                                              obstacles, f_rew=f_rew, time=t,
-                                                             guesses_d=robot_model._X_d)
+                                                             guesses_d=robot_model._X_d, staged=staged)
+            staged = None
             count += 1
         if status is False:
             delete_locs.append(i)
-            continue
+            return
         samples[i] = np.array(max_val).reshape((1, 1))
         funcs.append(target)
         locs[i, :] = maxima.reshape((1, d))
+
+    def one_sample(i):
+        """Sample i start to finish, one synchronisation per stage (the reference's own order of events)."""
+        W, b, eps = draw_weights()
+        W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))           # uploaded once: features now, the sampled function later
+        try:
+            if N_obs >= nFeatures:      # (:195-200) on the device
+                theta_d, info = rff_theta_device(robot_model, W_d, b_d, L.to_device(eps.reshape(-1)), variance, nFeatures)
+                if int(info.item()) != 0:
+                    raise np.linalg.LinAlgError('Z Z^T / noise + I is not positive definite')
+                theta = theta_d.cpu().numpy().reshape(nFeatures, 1)
+            else:                       # N x N eigendecomposition (:177-187): small dense LAPACK on the host
+                Z_d = rff_features_device(W_d, b_d, robot_model._X_d, variance, nFeatures)
+                Z = np.ascontiguousarray(Z_d[:, :N_obs].cpu().numpy())
+                theta = _rff_theta(Z, robot_model.zvals, robot_model.noise, eps, nFeatures)
+        except Exception:
+            delete_locs.append(i)
+            return
+        polish(i, make_target(W, b, theta, W_d, b_d, None))
+
+    first = 0
+    if PIPELINE_MAX_VALUE_SAMPLES and N_obs >= nFeatures and nK > 1:
+        scale = np.sqrt(2.0 * variance / nFeatures)
+        staged = []
+        for i in range(nK):             # every draw of every sample, in the reference's order; device work enqueued only
+            W, b, eps = draw_weights()
+            mid_state = np.random.get_state()
+            x1 = np.random.uniform(inner[0], inner[1], size=gridSize)
+            x2 = np.random.uniform(inner[2], inner[3], size=gridSize)
+            end_state = np.random.get_state()
+            # one pinned buffer up (W, b, eps, x1, x2), one down (theta, arg-max, info): no pageable copy, which would
+            # wait for everything enqueued so far
+            up, host = _mv_stage(i, nFeatures * (d + 2) + 2 * gridSize, nFeatures + 3)
+            up_np = up.numpy()
+            up_np[:nFeatures * d] = W.reshape(-1)
+            up_np[nFeatures * d:nFeatures * (d + 1)] = b.reshape(-1)
+            up_np[nFeatures * (d + 1):nFeatures * (d + 2)] = eps.reshape(-1)
+            up_np[nFeatures * (d + 2):nFeatures * (d + 2) + gridSize] = x1
+            up_np[nFeatures * (d + 2) + gridSize:] = x2
+            dev_in = up.to(robot_model._X_d.device, non_blocking=True)
+            _mv_guard(i)
+            W_d = dev_in[:nFeatures * d].view(nFeatures, d)
+            b_d = dev_in[nFeatures * d:nFeatures * (d + 1)]
+            theta_d, info = rff_theta_device(robot_model, W_d, b_d, dev_in[nFeatures * (d + 1):nFeatures * (d + 2)],
+                                             variance, nFeatures)
+            target = make_target(W, b, None, W_d, b_d, theta_d * scale)
+            vals, am = _grid_stage_device(target, robot_model._X_d, d, t, dev_in[nFeatures * (d + 2):], gridSize)
+            am_mesh = torch.argmax(vals[:gridSize * gridSize]).reshape(1)        # (:481-485: the fall-back start point)
+            host.copy_(torch.cat([theta_d, am.to(torch.float64), info.to(torch.float64), am_mesh.to(torch.float64)]),
+                       non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            staged.append((target, x1, x2, vals, host, ev, mid_state, end_state))
+        for i, (target, x1, x2, vals, host, ev, mid_state, end_state) in enumerate(staged):
+            first = i + 1
+            ev.synchronize()
+            h = host.numpy()
+            if int(h[nFeatures + 1]) != 0:          # the weight draw failed: the reference never drew this sample's grid
+                delete_locs.append(i)
+                np.random.set_state(mid_state)
+                break
+            target.theta = h[:nFeatures].reshape(nFeatures, 1).copy()
+            before = len(delete_locs), len(funcs)
+            target_vector_n = lambda x, tg=target: -tg.scalar(x)
+            target_vector_gradient_n = lambda x, tg=target: -np.asarray(tg.gradient(x).reshape(d, ))
+            maxima, max_val, _, status = global_maximization(target, target_vector_n, target.gradient,
+                                                             target_vector_gradient_n, robot_model.ranges,
+                                                             robot_model.xvals, visualize, 't%s.nK%s' % (t, i), obstacles,
+                                                             f_rew=f_rew, time=t, guesses_d=robot_model._X_d,
+                                                             staged=(x1, x2, vals, int(h[nFeatures]), int(h[nFeatures + 2])))
+            if status is False:                     # the reference redraws the grid from here: later draws were speculative
+                np.random.set_state(end_state)
+                polish(i, target, count=1)
+                break
+            samples[i] = np.array(max_val).reshape((1, 1))
+            funcs.append(target)
+            locs[i, :] = maxima.reshape((1, d))
+    for i in range(first, nK):
+        one_sample(i)
     samples = np.delete(samples, delete_locs, axis=0)
     locs = np.delete(locs, delete_locs, axis=0)
     if len(delete_locs) == nK:

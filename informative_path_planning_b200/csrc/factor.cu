@@ -221,8 +221,8 @@ extern "C" int ipp_potrf_lower(double* A, int64_t N, int64_t lda, double* logdet
 }
 
 // pdinv of a dense SPD matrix already in device memory (lower triangle read, A overwritten by its factor)
-static int pdinv_device(double* Lf, int64_t N, int64_t lda, double* winv, double* linv, int64_t ldw,
-                        double* logdet, int32_t* info, double* work, cudaStream_t s) {
+int ipp::pdinv_device(double* Lf, int64_t N, int64_t lda, double* winv, double* linv, int64_t ldw,
+                      double* logdet, int32_t* info, double* work, cudaStream_t s) {
     const int64_t ld = round_up(N, 16);
     double* U = work;                     // Linv^T
     double* Tt = U + N * ld;              // scratch for (L21 Linv11)^T

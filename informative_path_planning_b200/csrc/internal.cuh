@@ -64,6 +64,10 @@ int launch_rbf_queries(const ipp_rbf& k, const double* X, int64_t N, const doubl
 int launch_gemv(const double* A, int64_t lda, int64_t rows, int64_t cols, const double* x, double* y, cudaStream_t s);
 int potrf_lower(double* A, int64_t N, int64_t lda, double* dinv /* [ceil(N/64)][64*64] */, double* logdet,
                 int32_t* info, cudaStream_t s);
+// pdinv of a dense SPD matrix in device memory (factor.cu): winv = A^-1, linv (may be NULL) = chol(A)^-1; A is overwritten
+// by its factor; work: ipp_pdinv_workspace(N) doubles
+int pdinv_device(double* A, int64_t N, int64_t lda, double* winv, double* linv, int64_t ldw,
+                 double* logdet, int32_t* info, double* work, cudaStream_t s);
 
 struct RbfDev {
     int dim;

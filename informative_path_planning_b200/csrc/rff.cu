@@ -147,17 +147,50 @@ __global__ void __launch_bounds__(256) rff_argmax_finalize_kernel(const double* 
     if (threadIdx.x == 0) { max_val[s] = sv[0]; arg_max[s] = si[0]; }
 }
 
+// Z[row][n] = scale cos(W_f . x_n + b_f), row = f, or F - 1 - f with `reverse` (the weight draw factors the REVERSED system)
 template <int D>
 __global__ void rff_features_kernel(const double* __restrict__ W, const double* __restrict__ b, int64_t F,
                                     const double* __restrict__ X, int64_t N, double scale, double* __restrict__ Z,
-                                    int64_t ldz) {
+                                    int64_t ldz, int reverse) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t f = blockIdx.y;
     if (n >= N) return;
     double ph = b[f];
 #pragma unroll
     for (int d = 0; d < D; ++d) ph = fma(W[f * D + d], X[n * D + d], ph);
-    Z[f * ldz + n] = scale * cos(ph);
+    Z[(reverse ? F - 1 - f : f) * ldz + n] = scale * cos(ph);
+}
+
+// A[i][j] = sum_p part[p][i][j] + (i == j): the split-K partial products of Z Z^T / s2, summed in a fixed order
+__global__ void rff_sum_partials_kernel(const double* __restrict__ part, int nparts, int64_t F, int64_t ld, double* __restrict__ A) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= F * ld) return;
+    const int64_t i = idx / ld, j = idx % ld;
+    double acc = 0.0;
+    for (int p = 0; p < nparts; ++p) acc += part[(int64_t)p * F * ld + idx];
+    A[idx] = (j < F) ? acc + (i == j ? 1.0 : 0.0) : 0.0;
+}
+
+// theta[F - 1 - i] = (Sigma_r rhs_r)[i] / s2 + (L_r^-T eps_r)[i],  eps_r[k] = eps[F - 1 - k];  one block per i
+__global__ void __launch_bounds__(128) rff_theta_combine_kernel(const double* __restrict__ Sigma, const double* __restrict__ Linv,
+                                                               int64_t ld, int F, const double* __restrict__ rhs,
+                                                               const double* __restrict__ eps, double inv_s2,
+                                                               double* __restrict__ theta) {
+    __shared__ double sm[4], sy[4];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    double m = 0.0, y = 0.0;
+    for (int k = tid; k < F; k += 128) {
+        m = fma(Sigma[(int64_t)i * ld + k], rhs[k], m);
+        if (k >= i) y = fma(Linv[(int64_t)k * ld + i], eps[F - 1 - k], y);       // L_r^-1 is lower triangular
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+        y += __shfl_xor_sync(0xffffffffu, y, o);
+    }
+    if ((tid & 31) == 0) { sm[tid >> 5] = m; sy[tid >> 5] = y; }
+    __syncthreads();
+    if (tid == 0) theta[F - 1 - i] = ((sm[0] + sm[1]) + (sm[2] + sm[3])) * inv_s2 + ((sy[0] + sy[1]) + (sy[2] + sy[3]));
 }
 
 // ---- shared-feature GEMM path -------------------------------------------------------------------
@@ -414,8 +447,52 @@ extern "C" int ipp_rff_features(const double* W, const double* b, int64_t F, int
     IPP_CHECK_ARG(W && b && X && Z && F >= 1 && N >= 1 && ldz >= N && F <= 65535, "bad arguments");
     IPP_CHECK_ARG(D == 2 || D == 3, "dimension must be 2 or 3");
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)F);
-    if (D == 2) rff_features_kernel<2><<<grid, 256, 0, s>>>(W, b, F, X, N, scale, Z, ldz);
-    else rff_features_kernel<3><<<grid, 256, 0, s>>>(W, b, F, X, N, scale, Z, ldz);
+    if (D == 2) rff_features_kernel<2><<<grid, 256, 0, s>>>(W, b, F, X, N, scale, Z, ldz, 0);
+    else rff_features_kernel<3><<<grid, 256, 0, s>>>(W, b, F, X, N, scale, Z, ldz, 0);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+// ---- posterior weight draw (N >= F branch of the reference's sampler) in one call
+constexpr int64_t RFF_THETA_KSPLIT = 512;         // observations per partial product of Z Z^T: F x F x N has few output tiles
+static int64_t rff_theta_nparts(int64_t N) { return (N + RFF_THETA_KSPLIT - 1) / RFF_THETA_KSPLIT; }
+
+extern "C" int64_t ipp_rff_theta_workspace(int64_t F, int64_t N) {
+    if (F <= 0 || N <= 0) return 16;
+    const int64_t ld = round_up(F, 16), ldz = rff_theta_nparts(N) * RFF_THETA_KSPLIT;
+    return F * ldz + rff_theta_nparts(N) * F * ld + 3 * F * ld + round_up(F, 2) + ipp_pdinv_workspace(F) + 64;
+}
+
+extern "C" int ipp_rff_theta_draw(const double* W, const double* b, int64_t F, int D, const double* X, const double* z,
+                                  int64_t N, double variance, double noise_var, const double* eps, double* theta,
+                                  int32_t* info, double* work, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(W && b && X && z && eps && theta && info && work, "null pointer");
+    IPP_CHECK_ARG(F >= 1 && F <= 65535 && N >= 1 && (D == 2 || D == 3) && noise_var > 0.0 && variance > 0.0, "bad arguments");
+    const int64_t ld = round_up(F, 16), nparts = rff_theta_nparts(N), ldz = nparts * RFF_THETA_KSPLIT;
+    double* Zr = work;                          // [F][ldz] reversed features, zero beyond N
+    double* part = Zr + F * ldz;                // [nparts][F][ld]
+    double* A = part + nparts * F * ld;         // [F][ld]   Z_r Z_r^T / s2 + I, then its Cholesky factor
+    double* Sigma = A + F * ld;                 // [F][ld]   A_r^-1
+    double* Linv = Sigma + F * ld;              // [F][ld]   L_r^-1
+    double* rhs = Linv + F * ld;                // [F]       Z_r z
+    double* pwork = rhs + round_up(F, 2);
+    IPP_CUDA(cudaMemsetAsync(Zr, 0, sizeof(double) * F * ldz, s));
+    const double scale = sqrt(2.0 * variance / (double)F);
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)F);
+    if (D == 2) rff_features_kernel<2><<<grid, 256, 0, s>>>(W, b, F, X, N, scale, Zr, ldz, 1);
+    else rff_features_kernel<3><<<grid, 256, 0, s>>>(W, b, F, X, N, scale, Zr, ldz, 1);
+    IPP_LAUNCH_CHECK();
+    GemmArgs g{};                               // part[p] = Z_r[:, p-th slice] Z_r[:, p-th slice]^T / s2
+    g.A = Zr; g.lda = ldz; g.B = Zr; g.ldb = ldz; g.C = part; g.ldc = ld;
+    g.M = (int)F; g.N = (int)F; g.K = (int)RFF_THETA_KSPLIT; g.alpha = 1.0 / noise_var; g.beta = 0.0;
+    g.batch = (int)nparts; g.sA = RFF_THETA_KSPLIT; g.sB = RFF_THETA_KSPLIT; g.sC = F * ld;
+    IPP_TRY(launch_gemm(g, s));
+    rff_sum_partials_kernel<<<(unsigned)((F * ld + 255) / 256), 256, 0, s>>>(part, (int)nparts, F, ld, A);
+    IPP_LAUNCH_CHECK();
+    IPP_TRY(launch_gemv(Zr, ldz, F, N, z, rhs, s));
+    IPP_TRY(pdinv_device(A, F, ld, Sigma, Linv, ld, nullptr, info, pwork, s));
+    rff_theta_combine_kernel<<<(unsigned)F, 128, 0, s>>>(Sigma, Linv, ld, (int)F, rhs, eps, 1.0 / noise_var, theta);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

@@ -329,8 +329,11 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     IPP_CHECK_ARG(host_reward || (X && alpha && winv && stage_host && stage_dev && work), "null pointer");
     IPP_CHECK_ARG(n_root && root_goal && root_visits && root_reward && reward_evals && status, "null output pointer");
     IPP_CHECK_ARG((host_reward || N >= 1) && (kern->dim == 2 || kern->dim == 3), "needs a belief with data, 2 or 3 input dimensions");
+    const bool hotspot = prm->kind == IPP_REWARD_HOTSPOT;
     IPP_CHECK_ARG(prm->kind == IPP_REWARD_UCB || prm->kind == IPP_REWARD_EI || prm->kind == IPP_REWARD_MES ||
-                  prm->kind == IPP_REWARD_INFO || host_reward, "unknown reward kind");
+                  prm->kind == IPP_REWARD_INFO || hotspot || host_reward, "unknown reward kind");
+    IPP_CHECK_ARG(!hotspot || (prm->info_kern && prm->info_winv && prm->info_ldw >= N && prm->info_kern->dim == kern->dim),
+                  "the hotspot reward needs the information-gain belief over the same observations");
     IPP_CHECK_ARG(prm->kind != IPP_REWARD_NAIVE || (prm->naive_locs && prm->n_naive >= 1),
                   "the naive reward needs the sampled maximisers");
     IPP_CHECK_ARG(!value_reward || (prm->rff_W && prm->rff_b && prm->rff_theta && prm->naive_maxes && prm->rff_vals_dev &&
@@ -364,8 +367,10 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     // the two pointers equal).  If the buffer is not mapped, the copy + synchronise form below is used instead.
     double* h_flag = h_out + IPP_ROLLOUT_MAX_LEVELS + 8;
     double* h_rec = h_out + IPP_ROLLOUT_MAX_LEVELS + 16;                          // [L + 1] {value, tag} records (16-byte aligned)
+    double* h_rec2 = h_rec + 2 * (IPP_ROLLOUT_MAX_LEVELS + 1);                    // hotspot: the information-gain pass's records
     double* m_out = nullptr;
     double* m_rec = nullptr;
+    double* m_rec2 = nullptr;
     unsigned int* m_flag = nullptr;
     bool zero_copy = false;
     {
@@ -375,6 +380,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             m_out = static_cast<double*>(dp) + (h_out - stage_host);
             m_flag = reinterpret_cast<unsigned int*>(static_cast<double*>(dp) + (h_flag - stage_host));
             m_rec = static_cast<double*>(dp) + (h_rec - stage_host);
+            m_rec2 = static_cast<double*>(dp) + (h_rec2 - stage_host);
             zero_copy = true;
         } else {
             cudaGetLastError();                                                  // clear the sticky "not mapped" error
@@ -390,7 +396,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
     unsigned int seq = (seq_base += 1u << 20);
     if (!host_reward || value_reward) {
         *reinterpret_cast<volatile unsigned int*>(h_flag) = seq;
-        memset(h_rec, 0, sizeof(double) * 2 * (IPP_ROLLOUT_MAX_LEVELS + 1));     // no stale record can carry a live tag
+        memset(h_rec, 0, sizeof(double) * 4 * (IPP_ROLLOUT_MAX_LEVELS + 1));     // no stale record can carry a live tag
     }
     ipp::RolloutInline inl;
 
@@ -657,7 +663,7 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             int M = 0;
             for (const Level& lv : levels) M += lv.k;
             if (L > IPP_ROLLOUT_MAX_LEVELS || M > IPP_ROLLOUT_MAX_POINTS) { *status = 1; return IPP_OK; }
-            if (P.kind == IPP_REWARD_INFO && M > 32) { *status = 1; return IPP_OK; }     // one-launch form only (ipp_b200.h)
+            if ((P.kind == IPP_REWARD_INFO || hotspot) && M > 32) { *status = 1; return IPP_OK; }     // one-launch form only (ipp_b200.h)
             int32_t offsets[IPP_ROLLOUT_MAX_LEVELS + 1], reps[IPP_ROLLOUT_MAX_LEVELS];
             const bool fast = zero_copy && M <= ipp::RO_INLINE_POINTS;
             double* in = fast ? inl.v : h_in;
@@ -675,7 +681,52 @@ extern "C" int ipp_tree_search_dpw(const ipp_tree_params* prm, const double* roo
             }
             offsets[L] = M;
             int32_t info;
-            if (fast) {
+            if (hotspot) {
+                // hotspot_info_UCB = info_gain + mean_UCB (aq_library.py:117-135): two one-launch passes over the same
+                // points, back to back on the stream -- UCB on the regression belief, information gain on (I + vK)^-1 --
+                // each publishing its own tagged records; the sum per level is formed here, in the order ig + ucb
+                if (!fast || reinterpret_cast<uintptr_t>(m_rec) % 16 != 0) { *status = 1; return IPP_OK; }
+                const double t_launch = now_us();
+                static unsigned long long hs_tag_counter = 1ull << 62;              // disjoint from the single-pass tags
+                const unsigned long long tag_u = ++hs_tag_counter, tag_i = ++hs_tag_counter;
+                bool tagged_u = false, tagged_i = false;
+                const double info_params[1] = {P.info_param};
+                int rc = ipp::rollout_launch(kern, X, N, alpha, winv, ldw, noise_pred, diag_add, IPP_REWARD_UCB, params_host, 1,
+                                             nullptr, 0, d_in, d_in + (size_t)M * D, &inl, offsets, reps, L, m_out,
+                                             reinterpret_cast<int32_t*>(m_out + L), m_flag, seq, work, stream, m_rec, tag_u, &tagged_u);
+                if (rc != IPP_OK) return rc;
+                rc = ipp::rollout_launch(P.info_kern, X, N, alpha, P.info_winv, P.info_ldw, 0.0, 1.0, IPP_REWARD_INFO, info_params, 1,
+                                         nullptr, 0, d_in, d_in + (size_t)M * D, &inl, offsets, reps, L, m_out,
+                                         reinterpret_cast<int32_t*>(m_out + L), m_flag, seq, work, stream, m_rec2, tag_i, &tagged_i);
+                if (rc != IPP_OK) return rc;
+                if (!tagged_u || !tagged_i) {                                       // (the four-kernel form has no information-gain pass)
+                    IPP_CUDA(cudaStreamSynchronize(stream));
+                    *status = 1;
+                    return IPP_OK;
+                }
+                const double t_spin = now_us();
+                launch_us += t_spin - t_launch;
+                auto done = [&]() {
+                    const volatile unsigned long long* tu = reinterpret_cast<const volatile unsigned long long*>(h_rec);
+                    const volatile unsigned long long* ti = reinterpret_cast<const volatile unsigned long long*>(h_rec2);
+                    for (int l = L; l >= 0; --l)
+                        if (ti[2 * l + 1] != tag_i || tu[2 * l + 1] != tag_u) return false;
+                    return true;
+                };
+                for (unsigned spins = 0; !done(); ++spins) {
+                    if (complete_some()) continue;
+                    if ((spins & 0xffff) == 0xffff && now_us() - t_spin > 5e6) {
+                        IPP_CUDA(cudaStreamSynchronize(stream));
+                        if (done()) break;
+                        ::ipp::set_error("%s: rollout %d never completed", __func__, it);
+                        return IPP_E_CUDA;
+                    }
+                }
+                __atomic_thread_fence(__ATOMIC_ACQUIRE);
+                for (int l = 0; l < L; ++l) h_out[l] = h_rec2[2 * l] + h_rec[2 * l];
+                const int32_t bad = ((int32_t)h_rec[2 * L] != 0 || (int32_t)h_rec2[2 * L] != 0) ? 1 : 0;
+                memcpy(h_out + L, &bad, sizeof(int32_t));
+            } else if (fast) {
                 // points by value in the kernel parameters, rewards + info written straight into the pinned buffer, completion
                 // word polled by this thread: no copies and no driver synchronisation on the rollout's critical path
                 ++seq;

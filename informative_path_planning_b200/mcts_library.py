@@ -532,9 +532,11 @@ class cMCTS(object):
         if fused is None or scale is None or belief.dimension not in (2, 3):
             return False
         kind, params, maxes_d = fused
-        if kind == 'hotspot':
-            return False                              # two beliefs per rollout: the Python tree with fused rollouts
         operand = (belief.kern._c, belief._winv_d, belief._ld, belief._noise_var(), belief._diag_add())
+        hotspot = None
+        if kind == 'hotspot':                         # two passes per rollout: UCB on this belief, information gain on (I + vK)^-1
+            hotspot = belief._info_gain_state()
+            kind = L.REWARD_HOTSPOT
         if kind == L.REWARD_INFO:                     # the search runs on the information-gain belief (ipp_b200.h)
             kern2, binv, ldb, _ = belief._info_gain_state()
             operand, params = (kern2, binv, ldb, 0.0, 1.0), [2 * np.pi * np.e]
@@ -589,6 +591,9 @@ class cMCTS(object):
         prm.angles = angles.ctypes.data
         prm.obstacles = ctypes.cast(boxes[0], ctypes.c_void_p).value if boxes[1] else None
         prm.prior_scale = scale.ctypes.data
+        if hotspot is not None:
+            prm.info_kern = ctypes.cast(ctypes.pointer(hotspot[0]), ctypes.c_void_p).value
+            prm.info_winv, prm.info_ldw, prm.info_param = hotspot[1].data_ptr(), int(hotspot[2]), float(2 * np.pi * np.e)
         if naive_locs is not None:
             prm.naive_locs, prm.n_naive = naive_locs.ctypes.data, int(naive_locs.shape[0])
         if rff is not None:

@@ -33,7 +33,7 @@ MISSIONS = {   # name: (f_rew, nonmyopic, tree_type, path_generator, obstacle wo
     'nonmyopic_naive_dpw_dubins': ('naive', True, 'dpw', 'dubins', 'block', 3, 40, 3),
     'nonmyopic_naive_value_dpw_dubins': ('naive_value', True, 'dpw', 'dubins', 'free', 3, 40, 3),
     # information gain inside the tree search (robot_library.py:95-100 accepts it with nonmyopic=True): rollouts on the
-    # information-gain belief, natively for the dpw tree; hotspot_info (= info_gain + UCB) through the Python tree
+    # information-gain belief, natively for the dpw tree; hotspot_info (= info_gain + UCB): two passes per rollout, natively too
     'nonmyopic_info_gain_dpw_dubins': ('info_gain', True, 'dpw', 'dubins', 'free', 3, 40, 3),
     'nonmyopic_hotspot_dpw_dubins': ('hotspot_info', True, 'dpw', 'dubins', 'block', 3, 30, 3),
 }

@@ -338,9 +338,9 @@ def test_robot_mission_reproduces_reference_run(pkg, name, tmp_path, monkeypatch
     got = np.array([[float(e.metrics[n][t]) for n in ms.MISSION_METRICS] for t in range(spec[5])])
     np.testing.assert_allclose(got, g[name + '_metrics'], rtol=2e-5, atol=1e-5)
     assert os.path.exists(os.path.join('figures', spec[0], 'robot_model.csv'))
-    # every tree search of these missions runs natively (dpw and belief trees, both generators), except hotspot_info,
-    # whose rollouts need two beliefs (Python tree, two fused device passes per rollout)
-    native_expected = spec[5] if (spec[1] and spec[0] != 'hotspot_info') else 0
+    # every tree search of these missions runs natively (dpw and belief trees, both generators, all rewards: hotspot_info
+    # as two device passes per rollout, UCB on the regression belief + information gain on (I + vK)^-1)
+    native_expected = spec[5] if spec[1] else 0
     assert mc.cMCTS.native_searches - native_before == native_expected
     x1, x2, mean_grid, var_grid = r.visualize_world_model(screen=False)
     assert mean_grid.shape == (100, 100) and np.isfinite(mean_grid).all() and (var_grid > 0).all()

@@ -1017,7 +1017,7 @@ def test_train_and_load_kernel(pkg, tmp_path):
 @pytest.mark.parametrize('f_rew,world_kind,n_obs,budget,depth', [
     ('mean', 'free', 40, 120, 5), ('mean', 'block', 300, 250, 5), ('mes', 'free', 150, 250, 5),
     ('exp_improve', 'channel', 90, 150, 4), ('mean', 'free', 1200, 60, 3), ('info_gain', 'free', 200, 120, 5),
-    ('info_gain', 'block', 700, 80, 4)])
+    ('info_gain', 'block', 700, 80, 4), ('hotspot_info', 'free', 150, 120, 5), ('hotspot_info', 'block', 500, 80, 4)])
 def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n_obs, budget, depth, tree_type):
     """ipp_tree_search_dpw (the whole DPW search in native code) against the Python Tree on the same seeds: identical
     visit counts, bit-identical reward sums, the same chosen action -- and the interpreter's two random streams are left
@@ -1033,7 +1033,8 @@ def test_native_tree_search_is_the_interpreters_search(pkg, f_rew, world_kind, n
     X, z = world(rng, n_obs, 0.5)
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
     m.add_data(X, z)
-    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement, 'info_gain': aq.info_gain}[f_rew]
+    fn = {'mean': aq.mean_UCB, 'mes': aq.mves, 'exp_improve': aq.exp_improvement, 'info_gain': aq.info_gain,
+          'hotspot_info': aq.hotspot_info_UCB}[f_rew]
     res = {}
     for native in (True, False):
         pg = Dubins_Path_Generator(15, 1.5, 0.05, 0.5, RANGES, w)

@@ -35,7 +35,8 @@ def run(kind, n_obs, f_rew, budget=250, depth=5, fuse=True, native=True):
         model = OnlineGPModelOracle(R, 1.0, 100.0, noise=0.5); cls = mc.cMCTSOracle
     model.add_data(X, z)
     pg = PG(15, 1.5, 0.05, 0.5, R)
-    base = {'mean': aq.mean_UCB, 'mes': aq.mves, 'naive': aq.naive, 'naive_value': aq.naive_value}[f_rew]
+    base = {'mean': aq.mean_UCB, 'mes': aq.mves, 'naive': aq.naive, 'naive_value': aq.naive_value,
+            'info_gain': aq.info_gain, 'hotspot_info': aq.hotspot_info_UCB}[f_rew]
     aq_param = {'naive': (3, 1.5), 'naive_value': (3, 3.0)}.get(f_rew)
     fn = CountingFn(base) if kind == 'cpu' else base       # the device planner counts evals itself (tree.reward_evals)
     np.random.seed(5); random.seed(6)
