@@ -237,6 +237,45 @@ def test_sample_max_vals_golden(pkg, tag):
     np.testing.assert_allclose(fvals, g[tag + '_fvals'], rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize('fail_calls', [(), (0,), (1,), (2, 3), (0, 1, 2, 3, 4)])
+def test_sample_max_vals_pipelined_equals_one_at_a_time(pkg, monkeypatch, fail_calls):
+    """The pipelined sampler (all draws up front, device work of every sample enqueued, SLSQP of sample i under the device
+    work of i + 1) against the one-sample-at-a-time order of the reference: same maxima, same locations, same sampled
+    functions, and the global numpy stream left in the same state -- also when optimisation attempts FAIL (the reference
+    then redraws the grid, which shifts every later draw: the speculative draws are taken back)."""
+    import scipy.optimize
+    aq = pkg.aq_library
+    rng = np.random.default_rng(5)
+    X, z = world(rng, 260, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X, z)
+    real = scipy.optimize.minimize
+    res = {}
+    for pipelined in (True, False):
+        calls = {'n': 0}
+
+        def flaky(*a, **kw):
+            out = real(*a, **kw)
+            if calls['n'] in fail_calls:
+                out['success'] = False
+            calls['n'] += 1
+            return out
+        monkeypatch.setattr(scipy.optimize, 'minimize', flaky)
+        monkeypatch.setattr(aq, 'PIPELINE_MAX_VALUE_SAMPLES', pipelined)
+        np.random.seed(404)
+        samples, locs, funcs = aq.sample_max_vals(m, t=2, nK=4, nFeatures=200)
+        probe = rng.uniform(1, 9, (5, 2)) if not res else res[True][4]
+        res[pipelined] = (samples, locs, [f(probe) for f in funcs], np.random.standard_normal(4), probe, calls['n'])
+    a, b = res[True], res[False]
+    assert a[5] == b[5]                                                  # the same number of optimisation attempts
+    np.testing.assert_array_equal(a[3], b[3])                            # the stream ends in the same place
+    assert a[0].shape == b[0].shape and len(a[2]) == len(b[2])
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-9)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-7, atol=1e-7)
+    for fa, fb in zip(a[2], b[2]):
+        np.testing.assert_allclose(fa, fb, rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.parametrize('tag,f_rew,tree_type', [('dpw_mean', 'mean', 'dpw'), ('dpw_mes', 'mes', 'dpw'),
                                                  ('belief_mean', 'mean', 'belief'), ('dpw_ei', 'exp_improve', 'dpw')])
 def test_mcts_action_selection_golden(pkg, tag, f_rew, tree_type):
