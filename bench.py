@@ -601,14 +601,22 @@ def main():
             g1 = r4.uniform(1, 9, 1024); g2 = r4.uniform(1, 9, 1024)
             gx, gy = np.meshgrid(g1, g2)
             grid_d = L.to_device(np.vstack([gx.ravel(), gy.ravel()]).T)
-            aq.rff_eval_argmax_shared(W4, b4, T4, 100.0, grid_d)
-            torch.cuda.synchronize()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record()
-            aq.rff_eval_argmax_shared(W4, b4, T4, 100.0, grid_d)
-            r1.record()
-            torch.cuda.synchronize()
-            ms4 = r0.elapsed_time(r1)
+            # the grid is a meshgrid (as the reference's global_maximization builds it): the factored form of the features;
+            # the general-grid path (one cos per feature value) is timed beside it
+            xs_d, ys_d = L.to_device(g1), L.to_device(g2)
+
+            def timed(fn):
+                fn()
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                out = fn()
+                r1.record()
+                torch.cuda.synchronize()
+                return r0.elapsed_time(r1), out
+            ms4_general, (mx_g, am_g) = timed(lambda: aq.rff_eval_argmax_shared(W4, b4, T4, 100.0, grid_d))
+            ms4, (mx_m, am_m) = timed(lambda: aq.rff_eval_argmax_mesh(W4, b4, T4, 100.0, xs_d, ys_d))
+            same4 = bool(torch.equal(am_g, am_m))
             gs = 1 << 15
             sub = np.vstack([gx.ravel(), gy.ravel()]).T[:gs]
             t0 = time.perf_counter()
@@ -617,13 +625,14 @@ def main():
             dt4 = time.perf_counter() - t0
             # the whole of config 4: features of the N=4096 observations, 100 posterior weight draws (shared F x F inverse +
             # Cholesky on the device), evaluation on the 2^20-point grid, per-sample arg-max
-            aq.sample_max_vals_shared(model, grid_d, nK=S_, nFeatures=F_, rng=np.random.default_rng(1))
+            aq.sample_max_vals_shared(model, (xs_d, ys_d), nK=S_, nFeatures=F_, rng=np.random.default_rng(1))
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            aq.sample_max_vals_shared(model, grid_d, nK=S_, nFeatures=F_, rng=np.random.default_rng(1))
+            aq.sample_max_vals_shared(model, (xs_d, ys_d), nK=S_, nFeatures=F_, rng=np.random.default_rng(1))
             torch.cuda.synchronize()
             ms4_all = 1e3 * (time.perf_counter() - t0)
-            extras['rff_F1000_S100_G2^20'] = {'ms': ms4, 'grid_points_per_s': G_ / (ms4 / 1e3),
+            extras['rff_F1000_S100_G2^20'] = {'ms': ms4, 'general_grid_ms': ms4_general, 'same_argmax_as_general_grid': same4,
+                                              'grid_points_per_s': G_ / (ms4 / 1e3),
                                               'cpu_grid_points_per_s': gs / dt4, 'cpu_sample': '%d grid points, numpy' % gs,
                                               'end_to_end_ms_incl_features_and_100_weight_draws': ms4_all}
         except Exception as e:
@@ -718,6 +727,7 @@ def main():
             if isinstance(v, dict) and isinstance(v.get(key), (int, float)):
                 line[dst] = v[key]
         lift('config4_grid_stage_ms', 'rff_F1000_S100_G2^20', 'ms')
+        lift('config4_grid_stage_general_grid_ms', 'rff_F1000_S100_G2^20', 'general_grid_ms')
         lift('config4_end_to_end_ms', 'rff_F1000_S100_G2^20', 'end_to_end_ms_incl_features_and_100_weight_draws')
         for prec in ('i8x7', 'i8x6', 'i8x5'):
             lift('config3_%s_queries_per_s' % prec, prec + '_N4096', 'queries_per_s')

@@ -214,6 +214,15 @@ int64_t ipp_rff_workspace(int64_t F, int64_t S, int64_t G, int shared_w);
 int ipp_rff_eval_argmax(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
                         int shared_w, const double* grid, int64_t G, double* values,
                         double* max_val, int64_t* arg_max, double* work, void* stream);
+/* the same with shared features (S >= 8) on a MESHGRID -- grid point g = j * nx + i is (xs[i], ys[j] [, tval]), i.e.
+ *      np.meshgrid(xs, ys, indexing='xy') ravelled, the grid global_maximization builds (aq_library.py:455-466):
+ *      cos(a_i + c_j) = cos a_i cos c_j - sin a_i sin c_j turns nx * ny * F cosines into (nx + ny) * F sincos and two
+ *      multiplies per feature value.  xs [nx], ys [ny]: device; arg_max[s] = first g attaining the maximum;
+ *      work: ipp_rff_mesh_workspace(F, S, nx, ny) doubles. */
+int64_t ipp_rff_mesh_workspace(int64_t F, int64_t S, int64_t nx, int64_t ny);
+int ipp_rff_eval_argmax_mesh(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
+                             const double* xs, int64_t nx, const double* ys, int64_t ny, double tval,
+                             double* values, double* max_val, int64_t* arg_max, double* work, void* stream);
 /* feature matrix Z[F][ldz] = scale * cos(W X^T + b) (aq_library.py:171) */
 int ipp_rff_features(const double* W, const double* b, int64_t F, int D, const double* X, int64_t N,
                      double scale, double* Z, int64_t ldz, void* stream);

@@ -121,6 +121,8 @@ SIGNATURES = {
     'ipp_rollout_debug_clocks': (_INT, [_P]),
     'ipp_rff_workspace': (_I64, [_I64, _I64, _I64, _INT]),
     'ipp_rff_eval_argmax': (_INT, [_P, _P, _P, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
+    'ipp_rff_mesh_workspace': (_I64, [_I64, _I64, _I64, _I64]),
+    'ipp_rff_eval_argmax_mesh': (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _I64, _D, _P, _P, _P, _P, _P]),
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
     'ipp_rff_theta_workspace': (_I64, [_I64, _I64]),
     'ipp_rff_theta_draw': (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _D, _D, _P, _P, _P, _P, _P]),

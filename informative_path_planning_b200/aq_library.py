@@ -759,11 +759,30 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
     return samples, locs, funcs
 
 
+def rff_eval_argmax_mesh(W, b, Theta, variance, xs_d, ys_d, tval=0.0):
+    """rff_eval_argmax_shared on the meshgrid of xs and ys (grid point g = j * nx + i is (xs[i], ys[j] [, tval]), i.e.
+    np.meshgrid(xs, ys, indexing='xy') ravelled -- the grid of the reference's global_maximization, aq_library.py:455-466):
+    the features factor as cos a_i cos c_j - sin a_i sin c_j (ipp_rff_eval_argmax_mesh).  Needs >= 8 samples."""
+    F, D = W.shape
+    S = Theta.shape[1]
+    nx, ny = int(xs_d.numel()), int(ys_d.numel())
+    scale = np.sqrt(2.0 * variance / F)
+    th_d = L.to_device(np.ascontiguousarray(Theta.T) * scale)            # [S][F]
+    mx = torch.empty(S, dtype=torch.float64, device=xs_d.device)
+    am = torch.empty(S, dtype=torch.int64, device=xs_d.device)
+    work = L.workspace(L.lib.ipp_rff_mesh_workspace(F, S, nx, ny), slot='rff')
+    W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))     # keep both alive until the launch is enqueued
+    L.check(L.lib.ipp_rff_eval_argmax_mesh(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, D, L.ptr(xs_d), nx, L.ptr(ys_d), ny,
+                                           float(tval), None, L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
+    return mx, am
+
+
 def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
     """Batched max-value sampling with ONE feature set shared by all nK posterior samples:
     phi(grid) is evaluated once per grid point and contracted against all nK weight vectors in the same
     kernel, followed by the per-sample arg-max.  Statistically the reference's sampler with a different
     RNG stream; used for BASELINE config 4 (F=1000, S=100, 1M-point grid).
+    `grid`: (G, D) points, or a tuple (xs, ys) standing for their meshgrid (2-D beliefs; the factored form of the features).
     Returns (max_vals (nK,1), max_locs (nK,D), (W, b, Theta))."""
     _require_model(robot_model)
     rng = np.random.default_rng() if rng is None else rng
@@ -781,6 +800,12 @@ def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
         Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
         Theta = np.hstack([_rff_theta(Z, robot_model.zvals, robot_model.noise, eps[:, s:s + 1], nFeatures)
                            for s in range(nK)])                                # (F, nK)
+    if isinstance(grid, tuple):                                  # (xs, ys): the meshgrid of two coordinate vectors, never built
+        xs_d, ys_d = (g if isinstance(g, torch.Tensor) else L.to_device(g) for g in grid)
+        mx, am = rff_eval_argmax_mesh(W, b, Theta, variance, xs_d, ys_d)
+        nx = int(xs_d.numel())
+        locs = torch.stack([xs_d[am % nx], ys_d[am // nx]], dim=1).cpu().numpy()
+        return mx.cpu().numpy().reshape(-1, 1), locs, (W, b, Theta)
     grid_d = grid if isinstance(grid, torch.Tensor) else L.to_device(grid)
     mx, am = rff_eval_argmax_shared(W, b, Theta, variance, grid_d)
     locs = grid_d[am].cpu().numpy()

@@ -226,6 +226,67 @@ __global__ void __launch_bounds__(256) rff_phi_kernel(const double* __restrict__
     }
 }
 
+// ---- meshgrid form: grid point g = j nx + i is (xs[i], ys[j]) -- np.meshgrid(xs, ys, indexing='xy') ravelled, the grid
+// of the reference's global_maximization (aq_library.py:455-466).  cos(a_i + c_j) = cos a_i cos c_j - sin a_i sin c_j with
+// a_i = W_f0 xs_i + b_f and c_j = W_f1 ys_j (+ W_f2 t): (nx + ny) F sincos instead of nx ny F cos.  The non-tensor FP64
+// rate of this GPU is 16 lanes per clock and SM (measured: the feature pass of a 2^20 x 1000 grid, 14 FP64 instructions
+// per cos, took the 3.2 ms that rate predicts -- while a pure-write kernel reaches 7.2 TB/s, profiles/r3g_write_bw.log);
+// two multiplies per feature value leave the pass bound by writing Phi.
+template <int D>
+__global__ void rff_mesh_tables_kernel(const double* __restrict__ W, const double* __restrict__ b, int F,
+                                       const double* __restrict__ xs, int nx, const double* __restrict__ ys, int ny,
+                                       double tval, double* __restrict__ TC, double* __restrict__ TS, int64_t ldf) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)(nx + ny) * ldf) return;
+    const int r = (int)(idx / ldf), f = (int)(idx % ldf);
+    if (f >= F) { TC[idx] = 0.0; TS[idx] = 0.0; return; }
+    double ph;
+    if (r < nx) ph = fma(W[f * D], xs[r], b[f]);
+    else {
+        ph = W[f * D + 1] * ys[r - nx];
+        if (D == 3) ph = fma(W[f * D + 2], tval, ph);
+    }
+    double sn, cs;
+    sincos(ph, &sn, &cs);
+    TC[(int64_t)r * ldf + f] = cs;
+    TS[(int64_t)r * ldf + f] = sn;
+}
+
+// Phi rows g0 .. g0 + Gc of the mesh.  A block owns a patch of 8 x-coordinates x 8 mesh rows: a thread keeps the eight
+// (cos a_i, sin a_i) of its two features in registers and walks the eight rows, so a feature value costs half a table
+// load (a block of 16 consecutive grid points re-read both x tables for every value: 2 loads per value, and the pass
+// ran at the rate L2 delivers them, 122 us per 37 888-row chunk -- no faster than the cosine version; patches: 88 us;
+// 16-byte loads and stores: 64 us = 4.8 TB/s written).
+__global__ void __launch_bounds__(256) rff_phi_mesh_kernel(const double* __restrict__ TC, const double* __restrict__ TS, int F,
+                                                           int nx, int64_t g0, int Gc, double* __restrict__ Phi, int64_t ldf) {
+    const int i0 = blockIdx.x * 8;
+    const int64_t j0 = g0 / nx + (int64_t)blockIdx.y * 8;
+    for (int f = 2 * threadIdx.x; f < F; f += 512) {                  // two features per thread: 16-byte loads and stores
+        double2 ca[8], sa[8];                                         // (ldf is even and the tables are zero beyond F)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool in = i0 + u < nx;
+            ca[u] = in ? *reinterpret_cast<const double2*>(TC + (int64_t)(i0 + u) * ldf + f) : make_double2(0.0, 0.0);
+            sa[u] = in ? *reinterpret_cast<const double2*>(TS + (int64_t)(i0 + u) * ldf + f) : make_double2(0.0, 0.0);
+        }
+#pragma unroll 2
+        for (int v = 0; v < 8; ++v) {
+            const int64_t j = j0 + v;
+            const int64_t row0 = j * nx + i0 - g0;                     // row of (i0, j) inside this chunk (may be outside it)
+            if (row0 + 8 <= 0 || row0 >= Gc) continue;
+            const double2 cb = *reinterpret_cast<const double2*>(TC + (nx + j) * ldf + f);
+            const double2 sb = *reinterpret_cast<const double2*>(TS + (nx + j) * ldf + f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t row = row0 + u;
+                if (i0 + u < nx && row >= 0 && row < Gc)
+                    *reinterpret_cast<double2*>(Phi + row * ldf + f) =
+                        make_double2(fma(ca[u].x, cb.x, -(sa[u].x * sb.x)), fma(ca[u].y, cb.y, -(sa[u].y * sb.y)));
+            }
+        }
+    }
+}
+
 __global__ void rff_pad_theta_kernel(const double* __restrict__ theta, int S, int F, double* __restrict__ out, int64_t ldf) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)S * F) out[(i / F) * ldf + i % F] = theta[i];
@@ -388,6 +449,74 @@ extern "C" int64_t ipp_rff_workspace(int64_t F, int64_t S, int64_t G, int shared
     return rff_chunk_rows(G) * ldf + S * ldf + 2 * S * ((G + BM - 1) / BM) + 16;
 }
 
+extern "C" int64_t ipp_rff_mesh_workspace(int64_t F, int64_t S, int64_t nx, int64_t ny) {
+    if (F <= 0 || S <= 0 || nx <= 0 || ny <= 0) return 16;
+    return ipp_rff_workspace(F, S, nx * ny, 1) + 2 * (nx + ny) * round_up(F, 16);
+}
+
+namespace ipp {
+
+// Shared-feature grid stage: Phi chunk by chunk (general grid: one cos per value; mesh: from the two tables), contraction
+// with the arg-max in its epilogue, final reduction over the row tiles.
+static int rff_gemm_path(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
+                         const double* grid, const double* TC, const double* TS, int nx, int64_t G, double* values,
+                         double* max_val, int64_t* arg_max, double* work, cudaStream_t s) {
+    const int64_t ldf = round_up(F, 16), gc_max = rff_chunk_rows(G);
+    const int nparts = (int)((G + BM - 1) / BM);
+    double* Phi = work;
+    double* Th = Phi + gc_max * ldf;
+    double* part_val = Th + S * ldf;
+    int64_t* part_idx = reinterpret_cast<int64_t*>(part_val + (int64_t)S * nparts);
+    rff_pad_theta_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, s>>>(theta, (int)S, (int)F, Th, ldf);
+    IPP_LAUNCH_CHECK();
+    // (Tried: the feature pass of chunk c + 1 on a helper stream beside the contraction of chunk c, two Phi buffers.  No
+    // overlap at all -- the contraction's CTA holds 238 x 256 of the SM's 65 536 registers, so no second block fits.)
+    for (int64_t g0 = 0; g0 < G; g0 += gc_max) {
+        const int gc = (int)((G - g0) < gc_max ? (G - g0) : gc_max);
+        if (TC) {
+            const int64_t nj = (g0 + gc - 1) / nx - g0 / nx + 1;           // mesh rows this chunk touches
+            rff_phi_mesh_kernel<<<dim3((unsigned)((nx + 7) / 8), (unsigned)((nj + 7) / 8)), 256, 0, s>>>(TC, TS, (int)F, nx, g0, gc, Phi, ldf);
+        }
+        else if (D == 2) rff_phi_kernel<2><<<(gc + 15) / 16, 256, 0, s>>>(W, b, (int)F, grid, g0, gc, Phi, ldf);
+        else rff_phi_kernel<3><<<(gc + 15) / 16, 256, 0, s>>>(W, b, (int)F, grid, g0, gc, Phi, ldf);
+        IPP_LAUNCH_CHECK();
+        RffGemmArgs p;
+        p.Phi = Phi; p.ldf = ldf; p.Gc = gc;
+        p.Th = Th; p.S = (int)S; p.F = (int)F;
+        p.g0 = g0; p.G = G; p.values = values;
+        p.part_val = part_val; p.part_idx = part_idx;
+        p.nparts = nparts; p.part0 = (int)(g0 / BM);
+        dim3 tiles((gc + BM - 1) / BM, (unsigned)((S + BN - 1) / BN));
+        const int nb = S > BN ? 16 : (int)((S + 7) / 8);              // tile width: 8 nb sample columns
+        const int rc = nb <= 4 ? rff_gemm_launch<4>(p, tiles, s) : nb <= 8 ? rff_gemm_launch<8>(p, tiles, s)
+                     : nb <= 13 ? rff_gemm_launch<13>(p, tiles, s) : rff_gemm_launch<16>(p, tiles, s);
+        if (rc != IPP_OK) return rc;
+    }
+    rff_argmax_finalize_kernel<<<(unsigned)S, 256, 0, s>>>(part_val, part_idx, nparts, max_val, arg_max);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+}  // namespace ipp
+
+extern "C" int ipp_rff_eval_argmax_mesh(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
+                                        const double* xs, int64_t nx, const double* ys, int64_t ny, double tval,
+                                        double* values, double* max_val, int64_t* arg_max, double* work, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    IPP_CHECK_ARG(W && b && theta && xs && ys && max_val && arg_max && work, "null pointer");
+    IPP_CHECK_ARG(F >= 1 && F < (1 << 30) && S >= RFF_GEMM_MIN_S && S < (1 << 30), "shared features, at least 8 samples");
+    IPP_CHECK_ARG(nx >= 1 && ny >= 1 && nx < (1 << 30) && ny < (1 << 30), "bad mesh");
+    IPP_CHECK_ARG(D == 2 || D == 3, "dimension must be 2 or 3");
+    const int64_t ldf = round_up(F, 16), G = nx * ny;
+    double* TC = work + ipp_rff_workspace(F, S, G, 1);
+    double* TS = TC + (nx + ny) * ldf;
+    const unsigned nb = (unsigned)(((nx + ny) * ldf + 255) / 256);
+    if (D == 2) rff_mesh_tables_kernel<2><<<nb, 256, 0, s>>>(W, b, (int)F, xs, (int)nx, ys, (int)ny, tval, TC, TS, ldf);
+    else rff_mesh_tables_kernel<3><<<nb, 256, 0, s>>>(W, b, (int)F, xs, (int)nx, ys, (int)ny, tval, TC, TS, ldf);
+    IPP_LAUNCH_CHECK();
+    return rff_gemm_path(W, b, theta, F, S, D, nullptr, TC, TS, (int)nx, G, values, max_val, arg_max, work, s);
+}
+
 extern "C" int ipp_rff_eval_argmax(const double* W, const double* b, const double* theta, int64_t F, int64_t S, int D,
                                    int shared_w, const double* grid, int64_t G, double* values,
                                    double* max_val, int64_t* arg_max, double* work, void* stream_) {
@@ -395,36 +524,8 @@ extern "C" int ipp_rff_eval_argmax(const double* W, const double* b, const doubl
     IPP_CHECK_ARG(W && b && theta && grid && max_val && arg_max && work, "null pointer");
     IPP_CHECK_ARG(F >= 1 && S >= 1 && G >= 1 && F < (1 << 30) && S < (1 << 30), "bad shape");
     IPP_CHECK_ARG(D == 2 || D == 3, "dimension must be 2 or 3");
-    if (rff_use_gemm(S, shared_w)) {
-        const int64_t ldf = round_up(F, 16), gc_max = rff_chunk_rows(G);
-        const int nparts = (int)((G + BM - 1) / BM);
-        double* Phi = work;
-        double* Th = Phi + gc_max * ldf;
-        double* part_val = Th + S * ldf;
-        int64_t* part_idx = reinterpret_cast<int64_t*>(part_val + (int64_t)S * nparts);
-        rff_pad_theta_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, s>>>(theta, (int)S, (int)F, Th, ldf);
-        IPP_LAUNCH_CHECK();
-        for (int64_t g0 = 0; g0 < G; g0 += gc_max) {
-            const int gc = (int)((G - g0) < gc_max ? (G - g0) : gc_max);
-            if (D == 2) rff_phi_kernel<2><<<(gc + 15) / 16, 256, 0, s>>>(W, b, (int)F, grid, g0, gc, Phi, ldf);
-            else rff_phi_kernel<3><<<(gc + 15) / 16, 256, 0, s>>>(W, b, (int)F, grid, g0, gc, Phi, ldf);
-            IPP_LAUNCH_CHECK();
-            RffGemmArgs p;
-            p.Phi = Phi; p.ldf = ldf; p.Gc = gc;
-            p.Th = Th; p.S = (int)S; p.F = (int)F;
-            p.g0 = g0; p.G = G; p.values = values;
-            p.part_val = part_val; p.part_idx = part_idx;
-            p.nparts = nparts; p.part0 = (int)(g0 / BM);
-            dim3 tiles((gc + BM - 1) / BM, (unsigned)((S + BN - 1) / BN));
-            const int nb = S > BN ? 16 : (int)((S + 7) / 8);              // tile width: 8 nb sample columns
-            const int rc = nb <= 4 ? rff_gemm_launch<4>(p, tiles, s) : nb <= 8 ? rff_gemm_launch<8>(p, tiles, s)
-                         : nb <= 13 ? rff_gemm_launch<13>(p, tiles, s) : rff_gemm_launch<16>(p, tiles, s);
-            if (rc != IPP_OK) return rc;
-        }
-        rff_argmax_finalize_kernel<<<(unsigned)S, 256, 0, s>>>(part_val, part_idx, nparts, max_val, arg_max);
-        IPP_LAUNCH_CHECK();
-        return IPP_OK;
-    }
+    if (rff_use_gemm(S, shared_w))
+        return rff_gemm_path(W, b, theta, F, S, D, grid, nullptr, nullptr, 0, G, values, max_val, arg_max, work, s);
     const int nblocks = (int)((G + 255) / 256);
     double* part_val = work;
     int64_t* part_idx = reinterpret_cast<int64_t*>(work + (int64_t)S * nblocks);

@@ -608,6 +608,43 @@ def test_rff_shared_gemm_path_values_and_argmax(pkg, F, S, G):
     np.testing.assert_allclose(vals.cpu().numpy(), want, rtol=1e-10, atol=1e-9)
 
 
+@pytest.mark.parametrize('F,S,nx,ny,D', [(101, 40, 150, 97, 2), (200, 8, 300, 300, 2), (64, 100, 33, 500, 3), (1000, 100, 64, 70, 2)])
+def test_rff_mesh_form_equals_the_general_grid(pkg, F, S, nx, ny, D):
+    """ipp_rff_eval_argmax_mesh (features factored over the two mesh coordinates) against numpy on the explicit
+    np.meshgrid(..., indexing='xy') grid of the reference's global_maximization (aq_library.py:455-466) and against the
+    general-grid device path: same arg-max, maxima and values to round-off; grid rows that straddle mesh rows, a grid
+    spanning several Phi chunks, and the space-time kernel's constant third coordinate."""
+    L = pkg._lib
+    rng = np.random.default_rng(F + S + nx)
+    W, b, th = rng.normal(size=(F, D)), rng.uniform(0, 6.28, F), rng.normal(size=(S, F))
+    xs, ys, tval = rng.uniform(1, 9, nx), rng.uniform(1, 9, ny), 3.0
+    gx, gy = np.meshgrid(xs, ys, sparse=False, indexing='xy')
+    cols = [gx.ravel(), gy.ravel()] + ([tval * np.ones(nx * ny)] if D == 3 else [])
+    grid = np.vstack(cols).T
+    want = th @ np.cos(W @ grid.T + b[:, None])
+    W_d, b_d, th_d, xs_d, ys_d = (L.to_device(a) for a in (W, b, th, xs, ys))
+    G = nx * ny
+    vals = torch.empty((S, G), dtype=torch.float64, device='cuda')
+    mx = torch.empty(S, dtype=torch.float64, device='cuda')
+    am = torch.empty(S, dtype=torch.int64, device='cuda')
+    work = torch.empty(L.lib.ipp_rff_mesh_workspace(F, S, nx, ny), dtype=torch.float64, device='cuda')
+    for v in (vals, None):
+        mx.zero_(); am.zero_()
+        L.check(L.lib.ipp_rff_eval_argmax_mesh(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, D, L.ptr(xs_d), nx, L.ptr(ys_d), ny,
+                                               tval, L.ptr(v), L.ptr(mx), L.ptr(am), L.ptr(work), L.stream_ptr()))
+        np.testing.assert_array_equal(am.cpu().numpy(), want.argmax(1))
+        np.testing.assert_allclose(mx.cpu().numpy(), want.max(1), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(vals.cpu().numpy(), want, rtol=1e-10, atol=1e-9)
+    mx2 = torch.empty(S, dtype=torch.float64, device='cuda')
+    am2 = torch.empty(S, dtype=torch.int64, device='cuda')
+    g_d = L.to_device(grid)
+    work2 = torch.empty(L.lib.ipp_rff_workspace(F, S, G, 1), dtype=torch.float64, device='cuda')
+    L.check(L.lib.ipp_rff_eval_argmax(L.ptr(W_d), L.ptr(b_d), L.ptr(th_d), F, S, D, 1, L.ptr(g_d), G, None, L.ptr(mx2),
+                                      L.ptr(am2), L.ptr(work2), L.stream_ptr()))
+    assert torch.equal(am, am2)
+    torch.testing.assert_close(mx, mx2, rtol=1e-12, atol=1e-11)
+
+
 @pytest.mark.parametrize('f_rew', ['mean', 'exp_improve', 'mes'])
 @pytest.mark.parametrize('noise', [0.5, 1e-4])
 def test_rollout_rewards_match_sequential_appends(pkg, f_rew, noise):

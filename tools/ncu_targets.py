@@ -49,6 +49,13 @@ def main():
         grid_d = L.to_device(np.vstack([gx.ravel(), gy.ravel()]).T)
         for _ in range(reps):
             aq.rff_eval_argmax_shared(W4, b4, T4, 100.0, grid_d)
+    elif target == 'rffmesh':
+        r4 = np.random.default_rng(4)
+        F_, S_ = 1000, 100
+        W4 = r4.normal(size=(F_, 2)); b4 = 2 * np.pi * r4.uniform(size=(F_, 1)); T4 = r4.normal(size=(F_, S_))
+        xs_d, ys_d = L.to_device(r4.uniform(1, 9, 1024)), L.to_device(r4.uniform(1, 9, 1024))
+        for _ in range(reps):
+            aq.rff_eval_argmax_mesh(W4, b4, T4, 100.0, xs_d, ys_d)
     elif target == 'append':
         import copy
         m, rng = model(4096)
