@@ -293,6 +293,7 @@ __global__ void rff_pad_theta_kernel(const double* __restrict__ theta, int S, in
 }
 
 struct RffGemmArgs {
+    const double* TC; const double* TS; int nx;  // mesh form (MESH kernels): the two tables; Phi is never materialised
     const double* Phi; int64_t ldf; int Gc;      // A operand: [Gc][ldf]
     const double* Th; int S; int F;              // B operand: [S][ldf]
     int64_t g0, G;                               // global index of the chunk's first grid point, total grid size
@@ -305,7 +306,17 @@ struct RffGemmArgs {
 // the 128 rows (16 each) and every warp spans ALL sample columns, so the tile is 8 NB wide instead of a multiple of 128:
 // S = 100 (config 4) runs as NB = 13 -- 104 columns, 4 % of the DMMAs on padding where the 128-wide tile spent 22 %.
 // Pipeline, swizzle and k-permutation are dgemm_dmma.cuh's (3 stages x (A 32 KB + B 32 KB), B rows >= S zero-filled).
-template <int NB>
+//
+// MESH: the A operand is formed at fragment-load time from the two tables of the meshgrid form,
+//     Phi[(i, j)][f] = C[i][f] C[nx + j][f] - S[i][f] S[nx + j][f],
+// so Phi never exists in memory: per k-step a stage holds the tile's 128 rows of C[i] and of S[i] (L2-resident tables;
+// tile row r is mesh column (g0 + r) % nx), the <= RFF_MESH_JT mesh rows the tile touches, and the Theta tile (two
+// stages of 96 KB + 4 KB).  In the 8 x 1 warp layout no warp shares an A fragment with another, so every value is formed
+// exactly once: 8 non-tensor FP64 instructions per k-group and warp beside 52 DMMAs (the pipe they share: + 8 %).
+constexpr int RFF_MESH_JT = 4;                   // mesh rows a 128-point tile may touch (nx >= 64)
+constexpr int RFF_MESH_TB = RFF_MESH_JT * 2 * BK * 8;                          // bytes: [jrel][cos | sin][BK]
+constexpr int RFF_MESH_STAGE = 3 * TILE_BYTES + RFF_MESH_TB;
+template <int NB, bool MESH>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGemmArgs p) {
     static_assert(GEMM_THREADS == 256 && NB >= 1 && NB <= 16, "eight warps, at most 128 sample columns per tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -322,7 +333,92 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGem
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    {
+    if constexpr (MESH) {
+        const int KT = (p.F + BK - 1) / BK;
+        TileLoader lb;
+        lb.init(p.Th, p.ldf, n0, p.S, tid);
+        // loader side: thread (row group r0, chunk column ch) fetches chunk ch of the C and S rows of tile rows r0 + 16 u
+        const int ch = tid % CHUNKS_PER_ROW, r0 = tid / CHUNKS_PER_ROW;
+        const uint32_t ldst = (uint32_t)(r0 * ROW_BYTES + ((ch ^ ((r0 & 1) << 2)) << 4));
+        const int64_t gfirst = p.g0 + m0;
+        const int64_t jfirst = gfirst / p.nx;
+        int icol[LOADS_PER_THREAD];              // mesh column of the thread's u-th row, -1 beyond the grid
+#pragma unroll
+        for (int u = 0; u < LOADS_PER_THREAD; ++u) {
+            const int r = r0 + RSTEP * u;
+            icol[u] = (m0 + r < p.Gc) ? (int)((gfirst + r) % p.nx) : -1;
+        }
+        auto load_stage = [&](uint32_t st, int k0) {
+            const int rem = p.F - (k0 + 2 * ch);
+            const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+#pragma unroll
+            for (int u = 0; u < LOADS_PER_THREAD; ++u) {
+                const bool ok = icol[u] >= 0 && bytes > 0;
+                const int64_t off = ok ? (int64_t)icol[u] * p.ldf + k0 + 2 * ch : 0;
+                cp_async16(st + ldst + u * (RSTEP * ROW_BYTES), p.TC + off, ok ? bytes : 0);
+                cp_async16(st + TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), p.TS + off, ok ? bytes : 0);
+            }
+            lb.load(st + 2 * TILE_BYTES, k0, p.F);
+            if (tid < RFF_MESH_JT * 2 * (BK / 2)) {      // the mesh rows: [jrel][cos | sin][BK], 16 bytes per thread
+                const int c2 = tid % (BK / 2), cs = (tid / (BK / 2)) & 1, jr = tid / BK;
+                const int remj = p.F - (k0 + 2 * c2);
+                const int bj = remj >= 2 ? 16 : (remj == 1 ? 8 : 0);
+                const int64_t jrow = jfirst + jr;
+                const bool okj = bj > 0 && jrow * p.nx < p.G;
+                const double* src = (cs ? p.TS : p.TC) + (okj ? (p.nx + jrow) * p.ldf + k0 + 2 * c2 : 0);
+                cp_async16(st + 3 * TILE_BYTES + (uint32_t)(((jr * 2 + cs) * BK + 2 * c2) * 8), src, okj ? bj : 0);
+            }
+        };
+        // consumer side: the two fragment rows of this lane and the mesh row each belongs to
+        uint32_t jofs[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int64_t gg = gfirst + wm0 + 8 * i + g;
+            const int64_t jr = gg / p.nx - jfirst;
+            jofs[i] = (uint32_t)((jr < RFF_MESH_JT ? jr : 0) * 2 * BK * 8);
+        }
+        load_stage(smem_base, 0);
+        cp_async_commit();
+        for (int kt = 0; kt < KT; ++kt) {
+            cp_async_wait<0>();
+            __syncthreads();                              // stage kt & 1 landed; everybody is done with stage (kt + 1) & 1
+            if (kt + 1 < KT) load_stage(smem_base + ((kt + 1) & 1) * RFF_MESH_STAGE, (kt + 1) * BK);
+            cp_async_commit();
+            const uint32_t sC = smem_base + (kt & 1) * RFF_MESH_STAGE, sS = sC + TILE_BYTES, sB = sC + 2 * TILE_BYTES;
+            const uint32_t sT = sC + 3 * TILE_BYTES;
+#pragma unroll
+            for (int kg = 0; kg < BK / 8; ++kg) {
+                const uint32_t chunk = (uint32_t)(((4 * kg + t) ^ ((g & 1) << 2)) << 4);
+                const uint32_t kofs = (uint32_t)((8 * kg + 2 * t) * 8);
+                constexpr int JG = NB > 13 ? NB / 2 : NB;
+                double2 a[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double2 ac = lds128(sC + (wm0 + 8 * i + g) * ROW_BYTES + chunk);
+                    const double2 as = lds128(sS + (wm0 + 8 * i + g) * ROW_BYTES + chunk);
+                    const double2 cb = lds128(sT + jofs[i] + kofs), sb = lds128(sT + jofs[i] + BK * 8 + kofs);
+                    a[i].x = fma(ac.x, cb.x, -(as.x * sb.x));
+                    a[i].y = fma(ac.y, cb.y, -(as.y * sb.y));
+                }
+#pragma unroll
+                for (int j0 = 0; j0 < NB; j0 += JG) {
+                    double2 b[JG];
+#pragma unroll
+                    for (int j = 0; j < JG; ++j) b[j] = lds128(sB + (8 * (j0 + j) + g) * ROW_BYTES + chunk);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < JG; ++j) dmma884(acc[i][j0 + j][0], acc[i][j0 + j][1], a[i].x, b[j].x);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < JG; ++j) dmma884(acc[i][j0 + j][0], acc[i][j0 + j][1], a[i].y, b[j].y);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    } else {
         const int KT = (p.F + BK - 1) / BK;
         TileLoader la, lb;
         la.init(p.Phi, p.ldf, m0, p.Gc, tid);
@@ -427,12 +523,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGem
     }
 }
 
-template <int NB>
+template <int NB, bool MESH>
 static int rff_gemm_launch(const RffGemmArgs& p, dim3 tiles, cudaStream_t s) {
-    IPP_OPT_IN_SMEM(rff_gemm_argmax_kernel<NB>, GEMM_SMEM);
-    rff_gemm_argmax_kernel<NB><<<tiles, GEMM_THREADS, GEMM_SMEM, s>>>(p);
+    constexpr int bytes = MESH ? 2 * RFF_MESH_STAGE : GEMM_SMEM;
+    IPP_OPT_IN_SMEM((rff_gemm_argmax_kernel<NB, MESH>), bytes);
+    rff_gemm_argmax_kernel<NB, MESH><<<tiles, GEMM_THREADS, bytes, s>>>(p);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
+}
+template <bool MESH>
+static int rff_gemm_dispatch(const RffGemmArgs& p, dim3 tiles, cudaStream_t s) {
+    const int nb = p.S > BN ? 16 : (p.S + 7) / 8;                   // tile width: 8 nb sample columns
+    return nb <= 4 ? rff_gemm_launch<4, MESH>(p, tiles, s) : nb <= 8 ? rff_gemm_launch<8, MESH>(p, tiles, s)
+         : nb <= 13 ? rff_gemm_launch<13, MESH>(p, tiles, s) : rff_gemm_launch<16, MESH>(p, tiles, s);
+}
+// IPP_RFF_MESH_FUSED=0: the mesh form with a separate feature pass (A/B measurements)
+static bool rff_mesh_fused() {
+    static const int use = [] { const char* e = getenv("IPP_RFF_MESH_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
+    return use != 0;
 }
 
 static int64_t rff_chunk_rows(int64_t G) { return G < RFF_CHUNK ? round_up(G, BM) : RFF_CHUNK; }
@@ -469,6 +577,20 @@ static int rff_gemm_path(const double* W, const double* b, const double* theta, 
     int64_t* part_idx = reinterpret_cast<int64_t*>(part_val + (int64_t)S * nparts);
     rff_pad_theta_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, s>>>(theta, (int)S, (int)F, Th, ldf);
     IPP_LAUNCH_CHECK();
+    if (TC && rff_mesh_fused() && (BM + nx - 2) / nx + 1 <= RFF_MESH_JT && G < (1LL << 31)) {
+        RffGemmArgs p;                              // one launch over the whole grid: Phi formed in the A fragments
+        p.TC = TC; p.TS = TS; p.nx = nx;
+        p.Phi = nullptr; p.ldf = ldf; p.Gc = (int)G;
+        p.Th = Th; p.S = (int)S; p.F = (int)F;
+        p.g0 = 0; p.G = G; p.values = values;
+        p.part_val = part_val; p.part_idx = part_idx;
+        p.nparts = nparts; p.part0 = 0;
+        dim3 tiles((unsigned)((G + BM - 1) / BM), (unsigned)((S + BN - 1) / BN));
+        IPP_TRY(rff_gemm_dispatch<true>(p, tiles, s));
+        rff_argmax_finalize_kernel<<<(unsigned)S, 256, 0, s>>>(part_val, part_idx, nparts, max_val, arg_max);
+        IPP_LAUNCH_CHECK();
+        return IPP_OK;
+    }
     // (Tried: the feature pass of chunk c + 1 on a helper stream beside the contraction of chunk c, two Phi buffers.  No
     // overlap at all -- the contraction's CTA holds 238 x 256 of the SM's 65 536 registers, so no second block fits.)
     for (int64_t g0 = 0; g0 < G; g0 += gc_max) {
@@ -481,16 +603,14 @@ static int rff_gemm_path(const double* W, const double* b, const double* theta, 
         else rff_phi_kernel<3><<<(gc + 15) / 16, 256, 0, s>>>(W, b, (int)F, grid, g0, gc, Phi, ldf);
         IPP_LAUNCH_CHECK();
         RffGemmArgs p;
+        p.TC = nullptr; p.TS = nullptr; p.nx = 0;
         p.Phi = Phi; p.ldf = ldf; p.Gc = gc;
         p.Th = Th; p.S = (int)S; p.F = (int)F;
         p.g0 = g0; p.G = G; p.values = values;
         p.part_val = part_val; p.part_idx = part_idx;
         p.nparts = nparts; p.part0 = (int)(g0 / BM);
         dim3 tiles((gc + BM - 1) / BM, (unsigned)((S + BN - 1) / BN));
-        const int nb = S > BN ? 16 : (int)((S + 7) / 8);              // tile width: 8 nb sample columns
-        const int rc = nb <= 4 ? rff_gemm_launch<4>(p, tiles, s) : nb <= 8 ? rff_gemm_launch<8>(p, tiles, s)
-                     : nb <= 13 ? rff_gemm_launch<13>(p, tiles, s) : rff_gemm_launch<16>(p, tiles, s);
-        if (rc != IPP_OK) return rc;
+        IPP_TRY(rff_gemm_dispatch<false>(p, tiles, s));
     }
     rff_argmax_finalize_kernel<<<(unsigned)S, 256, 0, s>>>(part_val, part_idx, nparts, max_val, arg_max);
     IPP_LAUNCH_CHECK();
