@@ -539,6 +539,37 @@ def test_space_time_kernel_d3(pkg):
     d.predict_precision = 'fp64'
 
 
+@pytest.mark.parametrize('n_obs', [700, 2100, 2176])
+def test_fused_rollout_kernel_space_time(pkg, n_obs):
+    """The one-launch rollout with the 3-D space-time kernel: one-shot form (N = 700) and streaming form (N >= 2048: tiles
+    of W^-1 by tensor-map TMA, ragged and whole last row block) against the four-kernel sequence, and information gain."""
+    L = pkg._lib
+    rng = np.random.default_rng(n_obs)
+    X = np.hstack([rng.uniform(0, 10, (n_obs, 2)), rng.integers(0, 20, (n_obs, 1)).astype(float)])
+    z = 10 * np.sin(0.7 * X[:, :1]) * np.cos(0.5 * X[:, 1:2]) + rng.normal(0, 0.7, (n_obs, 1))
+    d = pkg.OnlineGPModel(RANGES, (1.0, 1.0, 8.0), 100.0, noise=0.5, dimension=3)
+    d.add_data(X, z)
+    levels = []
+    start = rng.uniform(2, 8, 2)
+    for k in (4, 4, 3, 5):
+        pts2 = start + np.cumsum(rng.normal(0, 0.3, (k, 2)), axis=0)
+        start = pts2[-1]
+        levels.append((np.hstack([pts2, np.full((k, 1), 12.0)]), rng.normal(0, 10.0, (k, 1)), int(rng.integers(1, 3))))
+    before = L.lib.ipp_rollout_mode(1)
+    try:
+        fused, info = d.rollout_rewards(L.REWARD_UCB, levels, params=[2.5])
+        again, _ = d.rollout_rewards(L.REWARD_UCB, levels, params=[2.5])
+        ig, info_ig = d.rollout_rewards(L.REWARD_INFO, levels)
+        L.lib.ipp_rollout_mode(0)
+        four, info4 = d.rollout_rewards(L.REWARD_UCB, levels, params=[2.5])
+    finally:
+        L.lib.ipp_rollout_mode(before)
+    assert info == 0 and info4 == 0 and info_ig == 0
+    np.testing.assert_array_equal(fused, again)
+    np.testing.assert_allclose(fused, four, rtol=1e-7, atol=1e-7)
+    assert np.all(np.isfinite(ig)) and np.all(ig > 0)
+
+
 def test_linalg_error_on_indefinite_append(pkg):
     """A Schur block that is not positive definite even with GPy's jitter ladder raises LinAlgError."""
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=-60.0)           # negative 'noise' makes K + noise I indefinite
@@ -742,7 +773,7 @@ def test_info_gain_rollouts_match_sequential_appends(pkg, n_obs, sizes):
             fork.add_data(pts, zo); o.add_data(pts, zo)
 
 
-@pytest.mark.parametrize('n_obs', [1, 63, 64, 65, 150, 900, 1500, 2500])
+@pytest.mark.parametrize('n_obs', [1, 63, 64, 65, 150, 900, 1500, 2048, 2500, 4100])
 @pytest.mark.parametrize('sizes', [[4, 4, 4, 4, 4], [3], [8, 8, 8, 6], [12, 12, 12, 12, 2], [1, 1, 1]])
 def test_fused_rollout_kernel_equals_the_four_kernel_sequence(pkg, n_obs, sizes):
     """The one-launch rollout (lower tiles of W^-1 only, per-CTA partials summed in CTA order by the last CTA, conditioning
