@@ -615,7 +615,7 @@ static int rollout_fused_launch(const RolloutFusedArgs& fa_in, const RolloutInli
     }
     const int fit = (dev >= 0 && dev < 64) ? max_clusters[dev] : -1;
     int g = grid;
-    if (fit > 0 && (grid + RF_CLUSTER - 1) / RF_CLUSTER <= fit) {
+    if (!STREAM && fit > 0 && (grid + RF_CLUSTER - 1) / RF_CLUSTER <= fit) {
         g = (grid + RF_CLUSTER - 1) / RF_CLUSTER * RF_CLUSTER;         // whole clusters; surplus CTAs get no tiles
     } else {
         attr[0].val.clusterDim.x = 1;

@@ -101,8 +101,8 @@ constexpr int rf_smem_doubles() {
     if (STREAM)     // points, K_J image, mean, obs, partial (V rounded up: 16-byte alignment), then the ring of RF_STAGES x
         return P * 3 + P * RF_B + P + P + ((P * (P + 1) / 2 + P + 1) & ~1) +      // (tile of W^-1 + A image) fed by bulk copies
                RF_STAGES * (RF_TILE + P * RF_B) + 128 + 8;                        // (+ 1 KB: the ring starts on a 1024-byte boundary)
-    //      points  K_I images (2)    K_J image + plain copy   mean  obs   this CTA's partial (read by its cluster leader)
-    return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + (P * (P + 1) / 2 + P) + 8;
+    //      points  K_I images (2)    K_J image + plain copy   mean  obs   this CTA's partial + the (RF_CLUSTER - 1) its cluster mates push
+    return P * 3 + 2 * P * RF_B + 2 * P * RF_B + P + P + RF_CLUSTER * ((P * (P + 1) / 2 + P + 1) & ~1) + 8;
 }
 
 // Thread index as the code below the tile loop sees it.  The streaming form runs a ninth warp that only feeds the ring;
@@ -417,6 +417,11 @@ __global__ void __launch_bounds__(STREAM ? RF_THREADS + 32 : RF_THREADS, 1) roll
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int M = q.r.M, N = q.N, T = q.T;
     const long long clk0 = clock64();
+    // cluster mates store into the leader's shared memory at the end: a (split) cluster barrier first makes sure every CTA
+    // of the cluster has started -- arrive here, wait just before the stores, by which time it has long completed
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int crank = cluster.block_rank(), csize = cluster.num_blocks();
+    if (!STREAM && csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
     if (q.use_inline) {          // parameter space is constant memory: every thread reads the SAME word (a broadcast;
         for (int i = 0; i < M * D; ++i) {                 // thread-dependent indices would be replayed address by address)
@@ -729,25 +734,39 @@ __global__ void __launch_bounds__(STREAM ? RF_THREADS + 32 : RF_THREADS, 1) roll
             s_part[a * (a + 1) / 2 + lane] = s_ab + s_ba;
         }
     if (tid < M) s_part[M * (M + 1) / 2 + tid] = s_m0[tid];
-    // ---- the RF_CLUSTER partials of a thread-block cluster meet in its leader through distributed shared memory (fixed
-    // rank order): the finishing CTA then reads a quarter of the partials.  That read is one SM pulling V x (number of
-    // partials) doubles through its L2 port and was the longest single step of a rollout at N = 900 (7.5k SM clocks).
+    // ---- the RF_CLUSTER partials of a thread-block cluster meet in its leader through distributed shared memory: the
+    // finishing CTA then reads a quarter of the partials.  That read is one SM pulling V x (number of partials) doubles
+    // through its L2 port and was the longest single step of a rollout at N = 900 (7.5k SM clocks).  The mates PUSH: each
+    // stores its partial into its own slot of the leader's shared memory, arrives at the cluster barrier (release) and is
+    // done; only the leader waits (acquire) and adds the slots in rank order.  (First version: the leader pulled the mates'
+    // partials -- a second cluster barrier had to keep their shared memory alive, and the remote loads were a round trip.)
     // (Large beliefs are launched with clusters of ONE CTA: whole clusters need RF_CLUSTER free SMs in one GPC, fewer of
     // them are co-resident than single CTAs, and there the partial sum is a small part of the rollout.)
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned int crank = cluster.block_rank(), csize = cluster.num_blocks();
-    if (csize > 1) cluster.sync();
-    else __syncthreads();                                 // s_part complete before anybody sums it
-    if (crank == 0) {
-        double* mine = q.part + (size_t)(blockIdx.x / csize) * V;
-        for (int v = tid; v < V; v += RF_THREADS) {
-            double tot = s_part[v];
-            for (unsigned int r = 1; r < csize; ++r) tot += cluster.map_shared_rank(s_part, r)[v];
-            mine[v] = tot;
+    __syncthreads();                                      // s_part complete
+    if (csize > 1) {
+        if constexpr (!STREAM) {
+            double* s_gather = s_part + VP;               // [RF_CLUSTER - 1][VP], the leader's copy is the one written
+            asm volatile("barrier.cluster.wait.aligned;" ::: "memory");      // (the start-up barrier)
+            if (crank != 0) {
+                double* dst = cluster.map_shared_rank(s_gather, 0) + (size_t)(crank - 1) * VP;
+                for (int v = tid; v < V; v += RF_THREADS) dst[v] = s_part[v];
+            }
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            if (crank != 0) return;
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            double* mine = q.part + (size_t)(blockIdx.x / csize) * V;
+            for (int v = tid; v < V; v += RF_THREADS) {
+                double tot = s_part[v];
+                for (unsigned int r = 1; r < csize; ++r) tot += s_gather[(size_t)(r - 1) * VP + v];
+                mine[v] = tot;
+            }
+        } else {
+            __trap();                                     // the streaming form is launched with clusters of one CTA
         }
+    } else {
+        double* mine = q.part + (size_t)blockIdx.x * V;
+        for (int v = tid; v < V; v += RF_THREADS) mine[v] = s_part[v];
     }
-    if (csize > 1) cluster.sync();                        // the members' shared memory stays alive until the leader has read it
-    if (crank != 0) return;
     const int GC = G / (int)csize;                        // partials = clusters
     const long long clk1 = clock64();
     __threadfence();
