@@ -352,9 +352,12 @@ __global__ void __launch_bounds__(RF_THREADS) rollout_images_kernel(RbfDev kern,
     __shared__ double s_red[RF_WARPS][2 * NT];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (use_inline) {
-        for (int i = 0; i < M * D; ++i) {
-            const double v = pp.v[i];
-            if (tid == (i & (RF_THREADS - 1))) s_pts[i] = v;
+#pragma unroll
+        for (int i = 0; i < P * D; ++i) {                // fully unrolled: the constant-bank loads issue back to back
+            if (i < M * D) {
+                const double v = pp.v[i];
+                if (tid == i) s_pts[i] = v;
+            }
         }
     } else {
         for (int i = tid; i < M * D; i += RF_THREADS) s_pts[i] = pts[i];
@@ -424,9 +427,12 @@ __global__ void __launch_bounds__(STREAM ? RF_THREADS + 32 : RF_THREADS, 1) roll
     if (!STREAM && csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
     if (q.use_inline) {          // parameter space is constant memory: every thread reads the SAME word (a broadcast;
-        for (int i = 0; i < M * D; ++i) {                 // thread-dependent indices would be replayed address by address)
-            const double v = pp.v[i];
-            if (tid == (i & (RF_THREADS - 1))) s_pts[i] = v;
+#pragma unroll                   // thread-dependent indices would be replayed address by address).  Fully unrolled: the
+        for (int i = 0; i < P * D; ++i) {                 // loads have constant addresses and issue back to back (a rolled
+            if (i < M * D) {                              // loop paid one load latency per point coordinate: ~1.5k clocks)
+                const double v = pp.v[i];
+                if (tid == i) s_pts[i] = v;
+            }
         }
     } else {
         for (int i = tid; i < M * D; i += RF_THREADS) s_pts[i] = q.pts[i];

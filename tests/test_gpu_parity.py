@@ -639,6 +639,32 @@ def test_rff_shared_gemm_path_values_and_argmax(pkg, F, S, G):
     np.testing.assert_allclose(vals.cpu().numpy(), want, rtol=1e-10, atol=1e-9)
 
 
+@pytest.mark.parametrize('F,N,D', [(200, 260, 2), (64, 64, 2), (130, 1500, 3), (200, 4096, 2)])
+def test_rff_theta_draw_against_the_reference_formula(pkg, F, N, D):
+    """ipp_rff_theta_draw (one device call: features, split-K product, factorisation of the reversed system, both products)
+    against the reference's N >= F lines (aq_library.py:195-200) in numpy: Sigma = inv(Z Z^T / s2 + I),
+    theta = Sigma Z z / s2 + cholesky(Sigma) eps."""
+    L = pkg._lib
+    rng = np.random.default_rng(F + N)
+    X = rng.uniform(0, 10, (N, D))
+    z = rng.normal(0, 10, N)
+    W = rng.normal(0, 1.0, (F, D))
+    b = 2 * np.pi * rng.uniform(size=F)
+    eps = rng.normal(size=F)
+    variance, s2 = 100.0, 0.5
+    Z = np.sqrt(2 * variance / F) * np.cos(W @ X.T + b[:, None])
+    Sigma = np.linalg.inv(Z @ Z.T / s2 + np.eye(F))
+    want = Sigma @ Z @ z / s2 + np.linalg.cholesky(Sigma) @ eps
+    W_d, b_d, X_d, z_d, eps_d = (L.to_device(a) for a in (W, b, X, z, eps))
+    theta = torch.empty(F, dtype=torch.float64, device='cuda')
+    info = torch.zeros(1, dtype=torch.int32, device='cuda')
+    work = torch.empty(L.lib.ipp_rff_theta_workspace(F, N), dtype=torch.float64, device='cuda')
+    L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, D, L.ptr(X_d), L.ptr(z_d), N, variance, s2, L.ptr(eps_d),
+                                     L.ptr(theta), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    assert int(info.item()) == 0
+    np.testing.assert_allclose(theta.cpu().numpy(), want, rtol=1e-8, atol=1e-9)
+
+
 @pytest.mark.parametrize('F,S,nx,ny,D', [(101, 40, 150, 97, 2), (200, 8, 300, 300, 2), (64, 100, 33, 500, 3), (1000, 100, 64, 70, 2)])
 def test_rff_mesh_form_equals_the_general_grid(pkg, F, S, nx, ny, D):
     """ipp_rff_eval_argmax_mesh (features factored over the two mesh coordinates) against numpy on the explicit
