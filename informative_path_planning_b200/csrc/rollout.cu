@@ -552,7 +552,9 @@ namespace ipp {
 
 // IPP_ROLLOUT_FUSED=0 / ipp_rollout_mode(0) select the four-kernel sequence (A/B measurements and cross-checks; it is
 // always used for more than 32 points)
-static int64_t rf_part_doubles() { return (int64_t)sm_count() * (32 * 33 / 2 + 32 + 2) / 2 * 2; }   // partials, even count
+static int64_t rf_part_doubles() {      // partials (one per CTA or cluster) + the streaming form's group sums, even count
+    return ((int64_t)sm_count() + RF_MAX_GROUPS) * (32 * 33 / 2 + 32 + 2) / 2 * 2;
+}
 static int g_rollout_fused = -1;
 static bool rollout_use_fused() {
     if (g_rollout_fused < 0) { const char* e = getenv("IPP_ROLLOUT_FUSED"); g_rollout_fused = (e && e[0] == '0') ? 0 : 1; }
@@ -730,6 +732,7 @@ int rollout_launch(const ipp_rbf* kern, const double* X, int64_t N, const double
         fa.X = X; fa.alpha = alpha; fa.W = winv; fa.ldw = ldw; fa.N = (int)N;
         fa.pts = pts; fa.zobs = zobs; fa.use_inline = inline_pts ? 1 : 0;
         fa.part = work;
+        fa.part2 = work + (int64_t)sm_count() * (32 * 33 / 2 + 32 + 2);
         fa.slot = (int)(__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % RF_SLOTS);
         fa.tag = 0;
         if (tagged_out && tag) {                          // results as self-validating records, no completion word

@@ -32,6 +32,8 @@ constexpr int RF_TILE = RF_B * RF_B;                    // a staged tile of W^-1
 constexpr int RF_CLUSTER = 4;                           // CTAs per thread-block cluster: their partials meet in shared memory
 constexpr int RF_SLOTS = 256;                           // ticket counters; each launch takes the next one
 __device__ unsigned int g_rf_ticket[RF_SLOTS];          // zero at load; the last CTA of a launch puts its slot back to zero
+constexpr int RF_GROUP = 8, RF_MAX_GROUPS = 32;         // streaming form: partials are first summed in groups of RF_GROUP CTAs
+__device__ unsigned int g_rf_ticket2[RF_SLOTS][RF_MAX_GROUPS];
 __device__ long long g_rf_clock[32];                     // SM clocks of the finishing CTA per phase (ipp_rollout_debug_clocks)
 
 // The rollout's points and observations by value: [M][D] points, then [M] observations (M <= 32 in this kernel: 1 KB of
@@ -51,6 +53,7 @@ struct RolloutFusedArgs {
     const double* pts; const double* zobs;               // device copies (used when use_inline == 0)
     int use_inline;
     double* part;                                        // [clusters][V], V = M (M + 1) / 2 + M
+    double* part2;                                       // [RF_MAX_GROUPS][V]: group sums (streaming form)
     const double* img;                                   // streaming form: [T][4][P * 64] cross-covariance images (pre-pass)
     int slot, tiles, T;
     unsigned long long tag;                              // != 0: r.reward holds 16-byte {value, tag} records, L rewards then info
@@ -773,8 +776,37 @@ __global__ void __launch_bounds__(STREAM ? RF_THREADS + 32 : RF_THREADS, 1) roll
         double* mine = q.part + (size_t)blockIdx.x * V;
         for (int v = tid; v < V; v += RF_THREADS) mine[v] = s_part[v];
     }
-    const int GC = G / (int)csize;                        // partials = clusters
+    int GC = G / (int)csize;                              // partials = clusters
+    const double* fin = q.part;                           // what the last CTA adds up: GC partials of V numbers
     const long long clk1 = clock64();
+    if constexpr (STREAM) {
+        // Large beliefs run one partial per SM: the finishing CTA pulling 148 x V doubles through its L2 port was 9k of
+        // the kernel's 62k clocks at N = 4096.  Two levels, both in a fixed order: the last CTA of every group of RF_GROUP
+        // (a ticket per group) adds its group's partials, and the last group to finish adds the group sums.
+        if (GC > 2 * RF_GROUP && GC <= RF_GROUP * RF_MAX_GROUPS) {
+            const int grp = blockIdx.x / RF_GROUP, ngroups = (GC + RF_GROUP - 1) / RF_GROUP;
+            const int gsize = (GC - grp * RF_GROUP) < RF_GROUP ? (GC - grp * RF_GROUP) : RF_GROUP;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int old = atomicAdd(&g_rf_ticket2[q.slot][grp], 1u);
+                s_last = (old == (unsigned int)(gsize - 1));
+                if (s_last) g_rf_ticket2[q.slot][grp] = 0u;
+            }
+            __syncthreads();
+            if (!s_last) return;
+            __threadfence();
+            for (int v = tid; v < V; v += RF_THREADS) {
+                const double* src = q.part + (size_t)grp * RF_GROUP * V + v;
+                double acc[RF_GROUP];
+#pragma unroll
+                for (int u = 0; u < RF_GROUP; ++u) acc[u] = (u < gsize) ? __ldcg(src + (size_t)u * V) : 0.0;
+                q.part2[(size_t)grp * V + v] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            }
+            fin = q.part2;
+            GC = ngroups;
+        }
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -800,7 +832,7 @@ __global__ void __launch_bounds__(STREAM ? RF_THREADS + 32 : RF_THREADS, 1) roll
         // fixed order over the clusters -- the result does not depend on their timing --, 32 independent loads in flight.
         // (Tried: exact 128-bit fixed-point accumulators fed by atomics, so that only V numbers are read here: the
         // atomics of ~120 CTAs on the same V addresses cost more than this sum saves, profiles/r2g_*.)
-        const double* src = q.part + v;
+        const double* src = fin + v;
         double acc[32];
 #pragma unroll
         for (int u = 0; u < 32; ++u) acc[u] = 0.0;

@@ -1,0 +1,7 @@
+#!/bin/bash
+# round 2, call 3s: streaming rollout kernel, partials summed in two levels -- parity, clocks
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "rollout or mcts or tree" > gpurun_out/r3s_pytest.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r3s_pytest.log
+for n in 2048 4096; do timeout 300 python tools/mcts_split_n.py $n > gpurun_out/r3s_split_$n.log 2>&1; tail -4 gpurun_out/r3s_split_$n.log; done
