@@ -225,11 +225,17 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
         }
         if (l == p.L - 1) break;                  // the last level's observation is never looked at again
         if (p.reps[l] > 0 && kb <= 4) {
-            // every thread factors the (identity-padded) 4 x 4 block redundantly in registers and substitutes its own row.
+            // every thread of the FIRST warp factors the (identity-padded) 4 x 4 block redundantly in registers and
+            // substitutes its own row (M <= 32: one warp has a lane for every point).  The other warps skip all of it:
+            // non-tensor FP64 issues at four lanes per clock and sub-partition here, so the seven warps that computed
+            // the factorisation for nothing were not free -- warp 4 shares warp 0's pipe.
             // Only the points AFTER this block are ever looked at again: rows / columns >= b1.  (No barrier here: the
             // snapshot above only reads what the barrier that ended the previous level made final.)
             const double dadd = p.diag_add / (double)p.reps[l];
             const int b1 = b0 + kb, R = M - b1;
+            const int i = b1 + tid;               // this thread's point (M <= 32 < RF_THREADS: at most one)
+            double dm = 0.0;
+            if (warp == 0) {
             double Lf[4][4], rd[4], u[4];
             int bad = 0;
 #pragma unroll
@@ -258,8 +264,6 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                 u[a] = v * rd[a];
             }
             if (bad && tid == 0) s_bad = bad;
-            const int i = b1 + tid;               // this thread's point (M <= 32 < RF_THREADS: at most one)
-            double dm = 0.0;
             if (i < M) {
                 double h[4];
 #pragma unroll
@@ -271,6 +275,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
                     H[i * HL + a] = h[a];
                     dm = fma(h[a], u[a], dm);
                 }
+            }
             }
             __syncthreads();
             if (i < M) m[i] += dm;

@@ -16,3 +16,4 @@ print('N=%d %s: %.0f rollouts/s, step %.1f ms = walk %.1f + device %.1f (launch 
     n, f_rew, r['rollouts_per_s'], r['seconds'] * 1e3, w.value / 1e3, d.value / 1e3, lu.value / 1e3))
 print('  phases: tiles %d, hand-over %d, sum + C0 %d, conditioning %d' % tuple(clk[:4]))
 print('  tile phase detail [4..10]:', [int(v) for v in clk[4:11]])
+print('  conditioning detail: start-to-level clocks', [int(clk[17 + i] - clk[16]) for i in range(5)], 'scoring', int(clk[26] - clk[25]), 'levels-to-scoring', int(clk[25] - clk[16]))
