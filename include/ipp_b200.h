@@ -231,12 +231,13 @@ int ipp_rff_features(const double* W, const double* b, int64_t F, int D, const d
  *      chol(Sigma) without forming or factoring Sigma: the system is factored with the features in reverse order
  *      (A_r = L_r L_r^T  <=>  A = U U^T, U upper triangular, chol(Sigma) = U^-T exactly), so
  *      theta_r = A_r^-1 (Z_r z) / s2 + L_r^-T eps_r: one ipp_pdinv-class factorisation and two products.
- *      W [F][D], b [F], X [N][D], z [N], eps [F] (the reference's standard-normal draw), theta [F] out: all device;
- *      info: 0, or != 0 when Z Z^T / s2 + I is not positive definite (np.linalg.LinAlgError in the reference);
- *      work: ipp_rff_theta_workspace(F, N) doubles. */
-int64_t ipp_rff_theta_workspace(int64_t F, int64_t N);
+ *      W [F][D], b [F], X [N][D], z [N], eps [S][F] (the reference's standard-normal draws; S = 1 in its own sampler, S
+ *      draws sharing one feature set -- and hence one factorisation -- in the shared-feature sampler), theta [S][F] out:
+ *      all device; info: 0, or != 0 when Z Z^T / s2 + I is not positive definite (np.linalg.LinAlgError in the reference);
+ *      work: ipp_rff_theta_workspace(F, N, S) doubles. */
+int64_t ipp_rff_theta_workspace(int64_t F, int64_t N, int64_t S);
 int ipp_rff_theta_draw(const double* W, const double* b, int64_t F, int D, const double* X, const double* z,
-                       int64_t N, double variance, double noise_var, const double* eps, double* theta,
+                       int64_t N, double variance, double noise_var, const double* eps, int64_t S, double* theta,
                        int32_t* info, double* work, void* stream);
 
 /* ---- building blocks exposed for tests and for info_gain (aq_library.py:34-80, Schur form):

@@ -124,8 +124,8 @@ SIGNATURES = {
     'ipp_rff_mesh_workspace': (_I64, [_I64, _I64, _I64, _I64]),
     'ipp_rff_eval_argmax_mesh': (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _I64, _D, _P, _P, _P, _P, _P]),
     'ipp_rff_features': (_INT, [_P, _P, _I64, _INT, _P, _I64, _D, _P, _I64, _P]),
-    'ipp_rff_theta_workspace': (_I64, [_I64, _I64]),
-    'ipp_rff_theta_draw': (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _D, _D, _P, _P, _P, _P, _P]),
+    'ipp_rff_theta_workspace': (_I64, [_I64, _I64, _I64]),
+    'ipp_rff_theta_draw': (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _D, _D, _P, _I64, _P, _P, _P, _P]),
     'ipp_dgemm_nt': (_INT, [_I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, _P, _I64, _P]),
     'ipp_potrf_workspace': (_I64, [_I64]),
     'ipp_potrf_debug_clocks': (_INT, [_P]),

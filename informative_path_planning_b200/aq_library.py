@@ -437,42 +437,29 @@ def _gemm_nt(A, B, M, N, K, alpha=1.0, C=None, beta=0.0):
     return C
 
 
-def rff_theta_batch_device(Z_d, N, zvals, noise_var, eps):
-    """All S posterior weight draws of the N >= F branch (reference aq_library.py:195-200) in one device pass:
-    Sigma = (Z Z^T / s2 + I)^-1, m = Sigma Z z / s2, Theta[:, s] = m + chol(Sigma) eps[:, s].  The reference redoes the
-    F x F inverse and Cholesky for every sample although only eps changes; here they are shared (FP64 DMMA GEMMs,
-    ipp_pdinv, ipp_potrf_lower).  eps: (F, S) numpy.  Returns Theta as a (F, S) numpy array."""
+def rff_theta_batch_device(robot_model, W, b, eps, variance):
+    """All S posterior weight draws of the N >= F branch (reference aq_library.py:195-200) for ONE feature set in one device
+    call (ipp_rff_theta_draw with S draws): Sigma = (Z Z^T / s2 + I)^-1, m = Sigma Z z / s2, Theta[:, s] = m +
+    chol(Sigma) eps[:, s].  The reference redoes the F x F inverse and Cholesky for every sample although only eps
+    changes; here one factorisation of the reversed system serves all of them (chol(Sigma) = U^-T, see ipp_b200.h).
+    eps: (F, S) numpy.  Returns Theta as a device tensor [S][F] (unscaled)."""
     F, S = eps.shape
-    dev = Z_d.device
-    ld = L.round_up(F, 16)
-    A = torch.zeros((F, ld), dtype=torch.float64, device=dev)
-    _gemm_nt(Z_d, Z_d, F, F, N, alpha=1.0 / noise_var, C=A)
-    A.diagonal().add_(1.0)                                     # + I (plumbing: F adds)
-    Sigma = torch.zeros((F, ld), dtype=torch.float64, device=dev)
-    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    N = robot_model.xvals.shape[0]
+    dev = robot_model._X_d.device
+    z_d = getattr(robot_model, '_z_d', None)
+    if z_d is None:
+        z_d = L.to_device(np.asarray(robot_model.zvals, dtype=float).reshape(-1))
+    W_d, b_d = L.to_device(W), L.to_device(b.reshape(-1))
+    eps_d = L.to_device(np.ascontiguousarray(eps.T))           # [S][F]
+    theta = torch.empty((S, F), dtype=torch.float64, device=dev)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
-    work = L.workspace(L.lib.ipp_pdinv_workspace(F), slot='pdinv')
-    L.check(L.lib.ipp_pdinv(L.ptr(A), F, ld, L.ptr(Sigma), None, ld, L.ptr(scal), L.ptr(info), L.ptr(work), L.stream_ptr()))
+    work = L.workspace(L.lib.ipp_rff_theta_workspace(F, N, S), slot='rff_theta')
+    L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, int(W_d.shape[1]), L.ptr(robot_model._X_d), L.ptr(z_d), N,
+                                     float(variance), float(robot_model.noise), L.ptr(eps_d), S, L.ptr(theta), L.ptr(info),
+                                     L.ptr(work), L.stream_ptr()))
     if int(info.item()) != 0:
         raise np.linalg.LinAlgError('Z Z^T / noise + I is not positive definite')
-    zrow = torch.zeros((1, Z_d.stride(0)), dtype=torch.float64, device=dev)
-    zrow[0, :N] = L.to_device(np.asarray(zvals, dtype=float).reshape(-1))
-    Zz = _gemm_nt(Z_d, zrow, F, 1, N)                           # (F, 2): column 0 = Z z
-    zz_row = torch.zeros((1, ld), dtype=torch.float64, device=dev)
-    zz_row[0, :F] = Zz[:, 0]
-    m = _gemm_nt(Sigma, zz_row, F, 1, F, alpha=1.0 / noise_var)  # (F, 2): column 0 = Sigma Z z / s2
-    Cf = Sigma.clone()
-    work = L.workspace(L.lib.ipp_potrf_workspace(F), slot='potrf')
-    L.check(L.lib.ipp_potrf_lower(L.ptr(Cf), F, ld, L.ptr(scal), L.ptr(info), L.ptr(work), L.stream_ptr()))
-    if int(info.item()) != 0:
-        raise np.linalg.LinAlgError('posterior weight covariance is not positive definite')
-    Cf[:, :F].tril_()                                           # entries above the diagonal are factorisation scratch
-    Et = torch.zeros((S, ld), dtype=torch.float64, device=dev)
-    Et[:, :F] = L.to_device(np.ascontiguousarray(eps.T))
-    Theta = torch.zeros((F, L.round_up(S, 2)), dtype=torch.float64, device=dev)
-    Theta[:, :S] = m[:, :1]                                     # broadcast m, then += chol(Sigma) eps
-    _gemm_nt(Cf, Et, F, S, F, C=Theta, beta=1.0)
-    return Theta[:, :S].cpu().numpy()
+    return theta
 
 
 def rff_theta_ul(Z_d, N, zvals, noise_var, eps, z_d=None):
@@ -514,10 +501,10 @@ def rff_theta_device(robot_model, W_d, b_d, eps_d, variance, nFeatures):
         z_d = L.to_device(np.asarray(robot_model.zvals, dtype=float).reshape(-1))
     theta = torch.empty(F, dtype=torch.float64, device=dev)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
-    work = L.workspace(L.lib.ipp_rff_theta_workspace(F, N), slot='rff_theta')
+    work = L.workspace(L.lib.ipp_rff_theta_workspace(F, N, 1), slot='rff_theta')
     W_d, b_d, eps_d = W_d.contiguous(), b_d.reshape(-1).contiguous(), eps_d.reshape(-1).contiguous()
     L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, int(W_d.shape[1]), L.ptr(robot_model._X_d), L.ptr(z_d), N,
-                                     float(variance), float(robot_model.noise), L.ptr(eps_d), L.ptr(theta), L.ptr(info),
+                                     float(variance), float(robot_model.noise), L.ptr(eps_d), 1, L.ptr(theta), L.ptr(info),
                                      L.ptr(work), L.stream_ptr()))
     return theta, info
 
@@ -759,15 +746,20 @@ def sample_max_vals(robot_model, t, nK=3, nFeatures=200, visualize=False, obstac
     return samples, locs, funcs
 
 
+def _theta_rows(Theta, scale):
+    """[S][F] device operand of the grid stage from Theta: (F, S) numpy or an [S][F] device tensor (unscaled)."""
+    if isinstance(Theta, torch.Tensor):
+        return (Theta * scale).contiguous(), int(Theta.shape[0])
+    return L.to_device(np.ascontiguousarray(Theta.T) * scale), int(Theta.shape[1])
+
+
 def rff_eval_argmax_mesh(W, b, Theta, variance, xs_d, ys_d, tval=0.0):
     """rff_eval_argmax_shared on the meshgrid of xs and ys (grid point g = j * nx + i is (xs[i], ys[j] [, tval]), i.e.
     np.meshgrid(xs, ys, indexing='xy') ravelled -- the grid of the reference's global_maximization, aq_library.py:455-466):
     the features factor as cos a_i cos c_j - sin a_i sin c_j (ipp_rff_eval_argmax_mesh).  Needs >= 8 samples."""
     F, D = W.shape
-    S = Theta.shape[1]
     nx, ny = int(xs_d.numel()), int(ys_d.numel())
-    scale = np.sqrt(2.0 * variance / F)
-    th_d = L.to_device(np.ascontiguousarray(Theta.T) * scale)            # [S][F]
+    th_d, S = _theta_rows(Theta, np.sqrt(2.0 * variance / F))           # [S][F]
     mx = torch.empty(S, dtype=torch.float64, device=xs_d.device)
     am = torch.empty(S, dtype=torch.int64, device=xs_d.device)
     work = L.workspace(L.lib.ipp_rff_mesh_workspace(F, S, nx, ny), slot='rff')
@@ -794,8 +786,7 @@ def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
     N = robot_model.xvals.shape[0]
     eps = np.hstack([rng.normal(size=(nFeatures, 1)) for _ in range(nK)])      # same draws, same order as one-by-one
     if N >= nFeatures:
-        Z_d = rff_features_device(W, b, robot_model._X_d, variance, nFeatures)
-        Theta = rff_theta_batch_device(Z_d, N, robot_model.zvals, float(robot_model.noise), eps)
+        Theta = rff_theta_batch_device(robot_model, W, b, eps, variance)       # [S][F] on the device: stays there for the grid stage
     else:
         Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
         Theta = np.hstack([_rff_theta(Z, robot_model.zvals, robot_model.noise, eps[:, s:s + 1], nFeatures)
@@ -804,21 +795,21 @@ def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
         xs_d, ys_d = (g if isinstance(g, torch.Tensor) else L.to_device(g) for g in grid)
         mx, am = rff_eval_argmax_mesh(W, b, Theta, variance, xs_d, ys_d)
         nx = int(xs_d.numel())
-        locs = torch.stack([xs_d[am % nx], ys_d[am // nx]], dim=1).cpu().numpy()
-        return mx.cpu().numpy().reshape(-1, 1), locs, (W, b, Theta)
-    grid_d = grid if isinstance(grid, torch.Tensor) else L.to_device(grid)
-    mx, am = rff_eval_argmax_shared(W, b, Theta, variance, grid_d)
-    locs = grid_d[am].cpu().numpy()
-    return mx.cpu().numpy().reshape(-1, 1), locs, (W, b, Theta)
+        locs_d = torch.stack([xs_d[am % nx], ys_d[am // nx]], dim=1)
+    else:
+        grid_d = grid if isinstance(grid, torch.Tensor) else L.to_device(grid)
+        mx, am = rff_eval_argmax_shared(W, b, Theta, variance, grid_d)
+        locs_d = grid_d[am]
+    if isinstance(Theta, torch.Tensor):
+        Theta = np.ascontiguousarray(Theta.cpu().numpy().T)        # (F, nK), the layout the host-side branch returns
+    return mx.cpu().numpy().reshape(-1, 1), locs_d.cpu().numpy(), (W, b, Theta)
 
 
 def rff_eval_argmax_shared(W, b, Theta, variance, grid_d):
     """max_g / argmax_g of f_s(x_g) for all samples s with shared features; device tensors out."""
     F, D = W.shape
-    S = Theta.shape[1]
     G = grid_d.shape[0]
-    scale = np.sqrt(2.0 * variance / F)
-    th_d = L.to_device(np.ascontiguousarray(Theta.T) * scale)            # [S][F]
+    th_d, S = _theta_rows(Theta, np.sqrt(2.0 * variance / F))           # [S][F]
     mx = torch.empty(S, dtype=torch.float64, device=grid_d.device)
     am = torch.empty(S, dtype=torch.int64, device=grid_d.device)
     work = L.workspace(L.lib.ipp_rff_workspace(F, S, G, 1), slot='rff')

@@ -678,18 +678,36 @@ extern "C" int ipp_rff_features(const double* W, const double* b, int64_t F, int
 constexpr int64_t RFF_THETA_KSPLIT = 512;         // observations per partial product of Z Z^T: F x F x N has few output tiles
 static int64_t rff_theta_nparts(int64_t N) { return (N + RFF_THETA_KSPLIT - 1) / RFF_THETA_KSPLIT; }
 
-extern "C" int64_t ipp_rff_theta_workspace(int64_t F, int64_t N) {
-    if (F <= 0 || N <= 0) return 16;
+// eps_r[s][k] = eps[s][F - 1 - k] (zero beyond F): the draws in the order of the reversed system
+__global__ void rff_reverse_rows_kernel(const double* __restrict__ eps, int64_t S, int64_t F, int64_t ld, double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * ld) return;
+    const int64_t sidx = idx / ld, k = idx % ld;
+    out[idx] = k < F ? eps[sidx * F + (F - 1 - k)] : 0.0;
+}
+
+// theta[s][F - 1 - i] = m[i] / s2 + Y[s][i]
+__global__ void rff_theta_assemble_kernel(const double* __restrict__ m, const double* __restrict__ Y, int64_t S, int64_t F,
+                                          int64_t ld, double inv_s2, double* __restrict__ theta) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * F) return;
+    const int64_t sidx = idx / F, i = idx % F;
+    theta[sidx * F + (F - 1 - i)] = fma(m[i], inv_s2, Y[sidx * ld + i]);
+}
+
+extern "C" int64_t ipp_rff_theta_workspace(int64_t F, int64_t N, int64_t S) {
+    if (F <= 0 || N <= 0 || S <= 0) return 16;
     const int64_t ld = round_up(F, 16), ldz = rff_theta_nparts(N) * RFF_THETA_KSPLIT;
-    return F * ldz + rff_theta_nparts(N) * F * ld + 3 * F * ld + round_up(F, 2) + ipp_pdinv_workspace(F) + 64;
+    return F * ldz + rff_theta_nparts(N) * F * ld + 3 * F * ld + 2 * round_up(F, 2) + 2 * S * ld + ipp_pdinv_workspace(F) + 64;
 }
 
 extern "C" int ipp_rff_theta_draw(const double* W, const double* b, int64_t F, int D, const double* X, const double* z,
-                                  int64_t N, double variance, double noise_var, const double* eps, double* theta,
+                                  int64_t N, double variance, double noise_var, const double* eps, int64_t S, double* theta,
                                   int32_t* info, double* work, void* stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     IPP_CHECK_ARG(W && b && X && z && eps && theta && info && work, "null pointer");
-    IPP_CHECK_ARG(F >= 1 && F <= 65535 && N >= 1 && (D == 2 || D == 3) && noise_var > 0.0 && variance > 0.0, "bad arguments");
+    IPP_CHECK_ARG(F >= 1 && F <= 65535 && N >= 1 && S >= 1 && S < (1 << 30) && (D == 2 || D == 3) && noise_var > 0.0 &&
+                  variance > 0.0, "bad arguments");
     const int64_t ld = round_up(F, 16), nparts = rff_theta_nparts(N), ldz = nparts * RFF_THETA_KSPLIT;
     double* Zr = work;                          // [F][ldz] reversed features, zero beyond N
     double* part = Zr + F * ldz;                // [nparts][F][ld]
@@ -697,7 +715,10 @@ extern "C" int ipp_rff_theta_draw(const double* W, const double* b, int64_t F, i
     double* Sigma = A + F * ld;                 // [F][ld]   A_r^-1
     double* Linv = Sigma + F * ld;              // [F][ld]   L_r^-1
     double* rhs = Linv + F * ld;                // [F]       Z_r z
-    double* pwork = rhs + round_up(F, 2);
+    double* mvec = rhs + round_up(F, 2);        // [F]       A_r^-1 Z_r z        (S > 1)
+    double* EpsR = mvec + round_up(F, 2);       // [S][ld]   the draws, reversed  (S > 1)
+    double* Y = EpsR + S * ld;                  // [S][ld]   L_r^-T eps_r         (S > 1)
+    double* pwork = Y + S * ld;
     IPP_CUDA(cudaMemsetAsync(Zr, 0, sizeof(double) * F * ldz, s));
     const double scale = sqrt(2.0 * variance / (double)F);
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)F);
@@ -713,7 +734,21 @@ extern "C" int ipp_rff_theta_draw(const double* W, const double* b, int64_t F, i
     IPP_LAUNCH_CHECK();
     IPP_TRY(launch_gemv(Zr, ldz, F, N, z, rhs, s));
     IPP_TRY(pdinv_device(A, F, ld, Sigma, Linv, ld, nullptr, info, pwork, s));
-    rff_theta_combine_kernel<<<(unsigned)F, 128, 0, s>>>(Sigma, Linv, ld, (int)F, rhs, eps, 1.0 / noise_var, theta);
+    if (S == 1) {
+        rff_theta_combine_kernel<<<(unsigned)F, 128, 0, s>>>(Sigma, Linv, ld, (int)F, rhs, eps, 1.0 / noise_var, theta);
+        IPP_LAUNCH_CHECK();
+        return IPP_OK;
+    }
+    // S draws share the factorisation: Y = Eps_r U^T with U = L_r^-T, which pdinv_device leaves at the head of its workspace
+    const double* U = pwork;
+    IPP_TRY(launch_gemv(Sigma, ld, F, F, rhs, mvec, s));
+    rff_reverse_rows_kernel<<<(unsigned)((S * ld + 255) / 256), 256, 0, s>>>(eps, S, F, ld, EpsR);
+    IPP_LAUNCH_CHECK();
+    GemmArgs y{};
+    y.A = EpsR; y.lda = ld; y.B = U; y.ldb = ld; y.C = Y; y.ldc = ld;
+    y.M = (int)S; y.N = (int)F; y.K = (int)F; y.alpha = 1.0; y.beta = 0.0;
+    IPP_TRY(launch_gemm(y, s));
+    rff_theta_assemble_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, s>>>(mvec, Y, S, F, ld, 1.0 / noise_var, theta);
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

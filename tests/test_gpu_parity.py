@@ -658,11 +658,22 @@ def test_rff_theta_draw_against_the_reference_formula(pkg, F, N, D):
     W_d, b_d, X_d, z_d, eps_d = (L.to_device(a) for a in (W, b, X, z, eps))
     theta = torch.empty(F, dtype=torch.float64, device='cuda')
     info = torch.zeros(1, dtype=torch.int32, device='cuda')
-    work = torch.empty(L.lib.ipp_rff_theta_workspace(F, N), dtype=torch.float64, device='cuda')
-    L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, D, L.ptr(X_d), L.ptr(z_d), N, variance, s2, L.ptr(eps_d),
+    work = torch.empty(L.lib.ipp_rff_theta_workspace(F, N, 1), dtype=torch.float64, device='cuda')
+    L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, D, L.ptr(X_d), L.ptr(z_d), N, variance, s2, L.ptr(eps_d), 1,
                                      L.ptr(theta), L.ptr(info), L.ptr(work), L.stream_ptr()))
     assert int(info.item()) == 0
     np.testing.assert_allclose(theta.cpu().numpy(), want, rtol=1e-8, atol=1e-9)
+    # several draws against one factorisation
+    S = 5
+    epsS = rng.normal(size=(S, F))
+    wantS = (Sigma @ Z @ z / s2)[None, :] + epsS @ np.linalg.cholesky(Sigma).T
+    epsS_d = L.to_device(epsS)
+    thetaS = torch.empty((S, F), dtype=torch.float64, device='cuda')
+    workS = torch.empty(L.lib.ipp_rff_theta_workspace(F, N, S), dtype=torch.float64, device='cuda')
+    L.check(L.lib.ipp_rff_theta_draw(L.ptr(W_d), L.ptr(b_d), F, D, L.ptr(X_d), L.ptr(z_d), N, variance, s2, L.ptr(epsS_d), S,
+                                     L.ptr(thetaS), L.ptr(info), L.ptr(workS), L.stream_ptr()))
+    assert int(info.item()) == 0
+    np.testing.assert_allclose(thetaS.cpu().numpy(), wantS, rtol=1e-8, atol=1e-9)
 
 
 @pytest.mark.parametrize('F,S,nx,ny,D', [(101, 40, 150, 97, 2), (200, 8, 300, 300, 2), (64, 100, 33, 500, 3), (1000, 100, 64, 70, 2)])
@@ -1041,15 +1052,25 @@ def test_rff_theta_batch_on_device_matches_reference_formula(pkg):
     m.add_data(X, z)
     W = rng.normal(size=(F, 2)); b = 2 * np.pi * rng.uniform(size=(F, 1))
     eps = rng.normal(size=(F, S))
-    Z_d = aq.rff_features_device(W, b, m._X_d, 100.0, F)
-    got = aq.rff_theta_batch_device(Z_d, N, z, 0.5, eps)
+    got = aq.rff_theta_batch_device(m, W, b, eps, 100.0)         # [S][F] device tensor
     Z = aq.rff_features(W, b, m._X_d, 100.0, F)
     want = np.hstack([aq._rff_theta(Z, z, 0.5, eps[:, s:s + 1], F) for s in range(S)])
-    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(got.cpu().numpy().T, want, rtol=1e-8, atol=1e-9)
     grid = rng.uniform(1, 9, (5000, 2))
-    mx, locs, _ = aq.sample_max_vals_shared(m, grid, nK=6, nFeatures=F, rng=np.random.default_rng(5))
-    assert mx.shape == (6, 1) and locs.shape == (6, 2) and np.all(np.isfinite(mx))
+    mx, locs, (W6, b6, Th6) = aq.sample_max_vals_shared(m, grid, nK=6, nFeatures=F, rng=np.random.default_rng(5))
+    assert mx.shape == (6, 1) and locs.shape == (6, 2) and np.all(np.isfinite(mx)) and Th6.shape == (F, 6)
     assert np.all(mx.ravel() > z.max() - 15.0)                 # sampled maxima sit near / above the observed maximum
+    # the sampled functions it returns are the ones whose maxima it reports
+    vals = (Th6.T * np.sqrt(2 * 100.0 / F)) @ np.cos(W6 @ grid.T + b6)
+    np.testing.assert_allclose(vals.max(axis=1), mx.ravel(), rtol=1e-9)
+    # the meshgrid form of the same sampler: same draws, maxima over the mesh of two coordinate vectors
+    xs, ys = rng.uniform(1, 9, 80), rng.uniform(1, 9, 90)
+    mxm, locm, (Wm, bm, Thm) = aq.sample_max_vals_shared(m, (xs, ys), nK=12, nFeatures=F, rng=np.random.default_rng(5))
+    gx, gy = np.meshgrid(xs, ys, indexing='xy')
+    gm = np.vstack([gx.ravel(), gy.ravel()]).T
+    valm = (Thm.T * np.sqrt(2 * 100.0 / F)) @ np.cos(Wm @ gm.T + bm)
+    np.testing.assert_allclose(valm.max(axis=1), mxm.ravel(), rtol=1e-9)
+    np.testing.assert_allclose(locm, gm[valm.argmax(axis=1)], rtol=0, atol=0)
 
 
 def test_legacy_ipp_library_call_sites(pkg):
