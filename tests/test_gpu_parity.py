@@ -570,6 +570,50 @@ def test_fused_rollout_kernel_space_time(pkg, n_obs):
     assert np.all(np.isfinite(ig)) and np.all(ig > 0)
 
 
+def test_library_calls_stay_inside_their_workspaces(pkg, monkeypatch):
+    """Every scratch buffer handed to the library through _lib.workspace gets a tail of canary values behind the size the
+    library asked for (ipp_*_workspace); after a tour through the calls -- refresh, block append, predict in three modes,
+    rewards, information gain, rollouts in both forms of the one-launch kernel, both max-value samplers, the mesh grid stage
+    -- every tail must be untouched."""
+    L, aq = pkg._lib, pkg.aq_library
+    CANARY, TAIL = -7.25e77, 2048
+    handed = []
+
+    def guarded(n_doubles, slot='main'):
+        buf = torch.full((int(n_doubles) + TAIL,), CANARY, dtype=torch.float64, device=L.device())
+        handed.append((slot, int(n_doubles), buf))
+        return buf[:int(n_doubles)]
+    monkeypatch.setattr(L, 'workspace', guarded)
+    rng = np.random.default_rng(2100)
+    X, z = world(rng, 2100, 0.5)
+    m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    m.add_data(X[:2096], z[:2096])                        # refresh
+    m.add_data(X[2096:], z[2096:])                        # block append of 4
+    q = rng.uniform(0, 10, (700, 2))
+    for prec in ('fp64', 'i8x6', 'i8x5'):
+        m.predict_precision = prec
+        m.predict_value(q)
+    m.predict_precision = 'fp64'
+    paths = [rng.uniform(1, 9, (k, 2)) for k in (3, 5, 4, 40)]
+    for f_rew in ('mean', 'exp_improve', 'info_gain', 'hotspot_info'):
+        aq.reward_paths(f_rew, 3, paths, m, param=[float(z.max())] if f_rew == 'exp_improve' else None)
+    levels = [(rng.uniform(3, 7, (4, 2)), rng.normal(0, 10, (4, 1)), 1 + (i & 1)) for i in range(5)]
+    small = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=0.5)
+    small.add_data(X[:700], z[:700])
+    for model in (m, small):                              # streaming and one-shot forms of the one-launch rollout kernel
+        model.rollout_rewards(L.REWARD_UCB, levels, params=[2.0])
+        model.rollout_rewards(L.REWARD_INFO, levels)
+    np.random.seed(3)
+    aq.sample_max_vals(m, t=2, nK=3, nFeatures=200)       # pipelined sampler: one-call weight draws, grid stage
+    aq.sample_max_vals_shared(small, rng.uniform(1, 9, (5000, 2)), nK=20, nFeatures=150, rng=np.random.default_rng(1))
+    aq.sample_max_vals_shared(small, (rng.uniform(1, 9, 130), rng.uniform(1, 9, 90)), nK=20, nFeatures=150,
+                              rng=np.random.default_rng(1))
+    torch.cuda.synchronize()
+    assert len(handed) > 20
+    for slot, n, buf in handed:
+        assert bool(torch.all(buf[n:] == CANARY)), 'workspace %r (%d doubles) was overrun' % (slot, n)
+
+
 def test_linalg_error_on_indefinite_append(pkg):
     """A Schur block that is not positive definite even with GPy's jitter ladder raises LinAlgError."""
     m = pkg.OnlineGPModel(RANGES, 1.0, 100.0, noise=-60.0)           # negative 'noise' makes K + noise I indefinite
