@@ -21,7 +21,6 @@
 // 1152 64-byte tensor-map rows; with tensor maps the TMA request rate (~2.2 clk per 64-byte row) capped the kernel.
 #include "internal.cuh"
 #include "tc05.cuh"
-#include <stdlib.h>
 
 namespace ipp {
 
@@ -40,16 +39,9 @@ constexpr int I_MAX_NS = 7;
 //   <6, 64, 3>  42-bit operands, 21 products, 6 x 64 = 384 columns   ("i8x6": ~4e-8, FP64-grade: inside the 1e-6 tolerance)
 //   <5, 96, 3>  35-bit operands, 15 products, 5 x 96 = 480 columns   ("i8x5": ~4e-6; fewer products AND a wider MMA --
 //               faster and 200x more accurate than the 3xTF32 mode)
-//   <6, 64, 3, TS>  the same with the A slices staged in TENSOR MEMORY: per k-block the MMA warp first copies the NS x 2
-//               K-slices of the cross-covariance planes shared memory -> TMEM (tcgen05.cp, 128 lanes x 32 B each, columns
-//               384 .. 479 behind the accumulators), then issues the MMAs with A = [tmem]: no A reads from shared memory
-//               and no collector fills between the MMAs (the SS form spends 12 x 64 of a stage's 2110 clocks on them)
-template <int NS_, int BN_, int STAGES_, bool TS_ = false>
+template <int NS_, int BN_, int STAGES_>
 struct I8Cfg {
     static constexpr int NS = NS_, BN = BN_, STAGES = STAGES_;
-    static constexpr bool TS = TS_;
-    static constexpr int A_TMEM_COL0 = NS_ * BN_;          // TS: A slices behind the accumulator levels, 8 columns per K-slice
-    static_assert(!TS_ || NS_ * BN_ + NS_ * 16 <= 512, "TS form: accumulators + A slices must fit the 512 TMEM columns");
     static constexpr int A_PLANE = I_BM * I_BK, B_PLANE = BN_ * I_BK;
     static constexpr int A_BYTES = NS_ * A_PLANE, B_BYTES = NS_ * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -82,16 +74,6 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// A operand from tensor memory (a_tmem: 128 lanes x 8 columns = 128 rows x 32 int8)
-__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// shared memory -> tensor memory: 128 rows x 256 bits of the matrix the descriptor describes
-__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 // K-major operand plane [rows][64 B], SWIZZLE_64B: 8-row groups 512 B apart (SBO), LBO unused (1), version 1,
 // layout type 4 = SWIZZLE_64B   (cute::UMMA::SmemDescriptor)
@@ -189,25 +171,6 @@ predict_var_i8_kernel(const I8Args p) {
                         ad[i] = make_desc64(base + i * I_A_PLANE);
                         bd[i] = make_desc64(base + I_A_BYTES + i * I_B_PLANE);
                     }
-                    if constexpr (C::TS) {
-                        // A slices into tensor memory first (the tensor pipe runs copies and MMAs in issue order: the
-                        // copies of this k-block wait for the MMAs of the previous one, which read the same columns)
-#pragma unroll
-                        for (int i = 0; i < I_NS; ++i)
-#pragma unroll
-                            for (int ks = 0; ks < I_BK / 32; ++ks)
-                                tc_cp_128x256b(tmem_base + C::A_TMEM_COL0 + (i * (I_BK / 32) + ks) * 8, ad[i] + (uint64_t)(2 * ks));
-#pragma unroll
-                        for (int ks = 0; ks < I_BK / 32; ++ks)
-#pragma unroll
-                            for (int i = 0; i < I_NS; ++i)
-#pragma unroll
-                                for (int j = 0; j < I_NS - i; ++j) {
-                                    const uint32_t accumulate = (ks == 0 && i == 0) ? fresh : 1u;
-                                    tc_mma_i8_ts(tmem_base + (i + j) * I_BN, tmem_base + C::A_TMEM_COL0 + (i * (I_BK / 32) + ks) * 8,
-                                                 bd[j] + (uint64_t)(2 * ks), C::IDESC, accumulate);
-                                }
-                    } else
 #pragma unroll
                     for (int ks = 0; ks < I_BK / 32; ++ks) {             // UMMA_K = 32 int8 = 32 B: +2 in 16-B units
 #pragma unroll
@@ -489,12 +452,7 @@ extern "C" int ipp_gp_predict_i8(const ipp_rbf* kern, const double* X, int64_t N
     IPP_CHECK_ARG(N <= 37000 || n_slices < 7, "n_slices = 7 needs N <= 37000 (exact INT32 accumulation of 7 pairs per level)");
     if (n_slices == 7)
         return predict_i8_impl<I8Cfg<7, 64, 2>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
-    if (n_slices == 6) {
-        // IPP_I8_TS=1: A slices staged in tensor memory (experimental arm, A/B measurements)
-        static const int ts = [] { const char* e = getenv("IPP_I8_TS"); return (e && e[0] == '1') ? 1 : 0; }();
-        if (ts)
-            return predict_i8_impl<I8Cfg<6, 64, 3, true>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
+    if (n_slices == 6)
         return predict_i8_impl<I8Cfg<6, 64, 3>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
-    }
     return predict_i8_impl<I8Cfg<5, 96, 3>>(kern, X, N, alpha, linv_tiles, linv_scale, noise_add, Xq, M, mean, var, work, stream);
 }
