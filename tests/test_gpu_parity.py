@@ -48,8 +48,10 @@ def build_online(cls, g):
 
 
 # ------------------------------------------------------------------ building blocks
-@pytest.mark.parametrize('M,N,K', [(128, 128, 16), (257, 130, 75), (64, 64, 64), (1, 1, 1), (300, 513, 1000), (5, 7, 3)])
+@pytest.mark.parametrize('M,N,K', [(128, 128, 16), (257, 130, 75), (64, 64, 64), (1, 1, 1), (300, 513, 1000), (5, 7, 3),
+                                   (1290, 1213, 77), (1100, 900, 300)])       # the last two fill the GPU: 128 x 128 tiles
 def test_dgemm_nt_against_torch(pkg, M, N, K):
+    """Both tile sizes of the FP64 DMMA GEMM (64 x 64 tiles when 128 x 128 tiles would leave half the SMs idle)."""
     L = pkg._lib
     g = torch.Generator(device='cuda').manual_seed(M * 131 + N * 17 + K)
     lda, ldb, ldc = L.round_up(K, 2) + 2, L.round_up(K, 2), L.round_up(N, 2)
