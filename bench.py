@@ -24,6 +24,8 @@ this run, every N):
                mcts_n4096_* (N=1): the same search over a belief of N=4096 observations, the size the metric is quoted on
   config5_*    BASELINE config 5, STRONG scaling: 65536 candidate Dubins paths x 20 samples generated on the device, N=4096,
                whole paths sharded across the ranks, rewards returned by one NCCL all_gather
+  config4_sharded_*  BASELINE config 4 with the mesh rows sharded (STRONG scaling): replicated weight draws, sharded grid
+               stage, one all_gather of the 100 (max, arg-max) pairs
   replicate_*  one k=4 observation block replicated at N=4096: 'recompute' (broadcast the block, every rank appends)
                vs 'broadcast' (rank 0 appends, W^-1 and alpha are broadcast over NVLink), with the NCCL bytes
 
@@ -281,6 +283,25 @@ def bench_replicate(parallel, model, rank, world, barrier, reduce_max):
     return out
 
 
+def bench_config4_sharded(parallel, model, rank, world, barrier, reduce_max):
+    """BASELINE config 4 (F=1000 shared features, S=100 samples, 1024 x 1024 mesh, N=4096 belief) with the mesh rows sharded
+    across the ranks (STRONG scaling): every rank draws the same posterior weights from the replicated belief, evaluates
+    its rows, and the 100 (max, arg-max) pairs are gathered and reduced (parallel.sample_max_vals_shared_sharded)."""
+    import torch
+    r4 = np.random.default_rng(4)
+    xs, ys = r4.uniform(1, 9, 1024), r4.uniform(1, 9, 1024)
+
+    def one():
+        parallel.sample_max_vals_shared_sharded(model, xs, ys, nK=100, nFeatures=1000, seed=1)
+    one()
+    torch.cuda.synchronize()
+    ms = min(device_timed(one, 1, barrier, reduce_max) for _ in range(3))
+    return {'config4_sharded_end_to_end_ms': ms, 'config4_sharded_scaling': 'strong',
+            'config4_sharded_allgather_bytes_per_rank': int(2 * 100 * 8) if world > 1 else 0,
+            'config4_sharded_workload': 'F=1000, S=100, 1024 x 1024 mesh, N=4096: weight draws replicated, mesh rows sharded over '
+                                        '%d GPU(s), (max, arg-max) pairs all-gathered; device-timed, max over ranks' % world}
+
+
 def bench_tree_search(parallel, rank, world, barrier, with_cpu):
     """dpw tree search at N=900 (BASELINE config 2 shape).  N=1: cMCTS.choose_trajectory; N>1: root-parallel, 250
     rollouts per rank.  Rates are over the rollout loop (the reference's own timed region, mcts_library.py:689-700)."""
@@ -448,6 +469,7 @@ def main():
         model.predict_precision = 'fp64'
         for name, fn in (('config5', lambda: bench_config5(L, aq, parallel, model, rank, world, barrier, reduce_max)),
                          ('replicate', lambda: bench_replicate(parallel, model, rank, world, barrier, reduce_max)),
+                         ('config4_sharded', lambda: bench_config4_sharded(parallel, model, rank, world, barrier, reduce_max)),
                          ('mcts', lambda: bench_tree_search(parallel, rank, world, barrier, with_cpu=(world == 1)))):
             try:                                    # measurement rows never take the headline down: a failure that every
                 multi.update(fn())                  # rank sees alike (the likely kind) is recorded and the run goes on

@@ -769,15 +769,10 @@ def rff_eval_argmax_mesh(W, b, Theta, variance, xs_d, ys_d, tval=0.0):
     return mx, am
 
 
-def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
-    """Batched max-value sampling with ONE feature set shared by all nK posterior samples (SURVEY.md H5):
-    phi(grid) is evaluated once per grid point and contracted against all nK weight vectors in the same
-    kernel, followed by the per-sample arg-max.  Statistically the reference's sampler with a different
-    RNG stream; used for BASELINE config 4 (F=1000, S=100, 1M-point grid).
-    `grid`: (G, D) points, or a tuple (xs, ys) standing for their meshgrid (2-D beliefs; the factored form of the features).
-    Returns (max_vals (nK,1), max_locs (nK,D), (W, b, Theta))."""
-    _require_model(robot_model)
-    rng = np.random.default_rng() if rng is None else rng
+def shared_feature_draws(robot_model, nK, nFeatures, rng):
+    """One feature set (W, b) and nK posterior weight vectors for it (reference aq_library.py:156-206 with the features
+    shared by all samples): Theta is an [nK][F] device tensor when N >= F (one factorisation for all draws), else an
+    (F, nK) numpy array from the host branch."""
     d = robot_model.xvals.shape[1]
     variance = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
     ls = robot_model.lengthscale if robot_model.dimension == 2 else robot_model.lengthscale[0]
@@ -791,6 +786,20 @@ def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
         Z = rff_features(W, b, robot_model._X_d, variance, nFeatures)
         Theta = np.hstack([_rff_theta(Z, robot_model.zvals, robot_model.noise, eps[:, s:s + 1], nFeatures)
                            for s in range(nK)])                                # (F, nK)
+    return W, b, Theta
+
+
+def sample_max_vals_shared(robot_model, grid, nK=100, nFeatures=1000, rng=None):
+    """Batched max-value sampling with ONE feature set shared by all nK posterior samples (SURVEY.md H5):
+    phi(grid) is evaluated once per grid point and contracted against all nK weight vectors in the same
+    kernel, followed by the per-sample arg-max.  Statistically the reference's sampler with a different
+    RNG stream; used for BASELINE config 4 (F=1000, S=100, 1M-point grid).
+    `grid`: (G, D) points, or a tuple (xs, ys) standing for their meshgrid (2-D beliefs; the factored form of the features).
+    Returns (max_vals (nK,1), max_locs (nK,D), (W, b, Theta))."""
+    _require_model(robot_model)
+    rng = np.random.default_rng() if rng is None else rng
+    variance = float(np.asarray(robot_model.variance, dtype=float).reshape(-1)[0])
+    W, b, Theta = shared_feature_draws(robot_model, nK, nFeatures, rng)
     if isinstance(grid, tuple):                                  # (xs, ys): the meshgrid of two coordinate vectors, never built
         xs_d, ys_d = (g if isinstance(g, torch.Tensor) else L.to_device(g) for g in grid)
         mx, am = rff_eval_argmax_mesh(W, b, Theta, variance, xs_d, ys_d)

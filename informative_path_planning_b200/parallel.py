@@ -7,7 +7,8 @@ The path shards naturally: query points and whole candidate paths are independen
     N x N inverse (134 MB at N=4096) and bit-identical across ranks because every rank runs the same
     deterministic kernels on the same inputs; `mode='broadcast'` ships the factor instead;
   * queries / paths are SHARDED contiguously (never splitting a path), with no data-path collective;
-  * per-path rewards are returned with one all_gather (64k paths x 8 B: latency-bound).
+  * per-path rewards are returned with one all_gather (64k paths x 8 B: latency-bound);
+  * max-value sampling over a large grid: mesh rows sharded, the S (max, arg-max) pairs gathered and reduced.
 Collectives run on NCCL over NVLink when the tensors are CUDA tensors and on gloo for the CPU tests
 of the host-side logic (the functions below never look at the device of what they move).
 """
@@ -128,6 +129,63 @@ def reward_paths_sharded(model, f_rew, time, queries, offsets, param=None, rewar
     dev = _comm_device() if size > 1 else torch.device('cpu')
     out = gather_concat(torch.from_numpy(local).to(dev), counts)
     return out.cpu().numpy()
+
+
+def combine_sharded_argmax(max_local, arg_global_local):
+    """(max, first arg-max) over grid slices held by different ranks ("MES additionally needs the S
+    max-values: computed on sharded grid slices, then reduced over the (value, index) pairs").  max_local [S] float64 and
+    arg_global_local [S] int64 (indices into the WHOLE grid; a rank without points passes -inf / any index) on the
+    communication device.  One all_gather of 2 S numbers per rank; ties go to the smallest index, like np.argmax.
+    Returns (max [S], arg-max [S]) on every rank."""
+    rank, size = world()
+    if size == 1:
+        return max_local, arg_global_local
+    pair = torch.stack([max_local.to(torch.float64), arg_global_local.to(torch.float64)])      # indices < 2^53: exact
+    out = [torch.empty_like(pair) for _ in range(size)]
+    dist.all_gather(out, pair)
+    vals = torch.stack([o[0] for o in out])                 # [size][S]
+    idxs = torch.stack([o[1] for o in out])
+    best = vals.max(dim=0).values
+    cand = torch.where(vals == best.unsqueeze(0), idxs, torch.full_like(idxs, float('inf')))
+    return best, cand.min(dim=0).values.to(torch.int64)
+
+
+def sample_max_vals_shared_sharded(model, xs, ys, nK=100, nFeatures=1000, seed=0, eval_fn=None):
+    """Shared-feature max-value sampling (aq_library.sample_max_vals_shared, BASELINE config 4) over the meshgrid of xs and
+    ys with the MESH ROWS sharded across the ranks: every rank draws the same features and the same posterior weights
+    from the replicated belief (same seed, deterministic kernels), evaluates the nK sampled functions on its rows
+    ys[lo:hi] only, and the per-sample (max, arg-max) pairs meet in combine_sharded_argmax.
+    `eval_fn(W, b, Theta, variance, xs, ys_slice) -> (max [S], arg-max [S] within the slice's mesh)` defaults to the
+    device grid stage (injected in the CPU tests).  Returns (max_vals (nK, 1), max_locs (nK, 2), (W, b, Theta))."""
+    rank, size = world()
+    xs, ys = np.asarray(xs, dtype=np.float64).reshape(-1), np.asarray(ys, dtype=np.float64).reshape(-1)
+    nx, ny = xs.shape[0], ys.shape[0]
+    lo, hi = shard_bounds(ny, rank, size)
+    variance = float(np.asarray(model.variance, dtype=float).reshape(-1)[0])
+    if eval_fn is None:
+        from . import _lib as L
+        from . import aq_library as aq
+        W, b, Theta = aq.shared_feature_draws(model, nK, nFeatures, np.random.default_rng(seed))
+
+        def eval_fn(W_, b_, Th_, var_, xs_, ys_):
+            return aq.rff_eval_argmax_mesh(W_, b_, Th_, var_, L.to_device(xs_), L.to_device(ys_))
+    else:
+        W, b, Theta = model.shared_feature_draws(nK, nFeatures, np.random.default_rng(seed))
+    dev = _comm_device() if size > 1 else None
+    if hi > lo:
+        mx, am = eval_fn(W, b, Theta, variance, xs, ys[lo:hi])
+        mx = torch.as_tensor(mx, dtype=torch.float64)
+        am = torch.as_tensor(am, dtype=torch.int64) + lo * nx          # index into the whole mesh: g = j * nx + i
+    else:
+        mx = torch.full((nK,), -float('inf'), dtype=torch.float64)
+        am = torch.zeros(nK, dtype=torch.int64)
+    if dev is not None:
+        mx, am = mx.to(dev), am.to(dev)
+    mx, am = combine_sharded_argmax(mx, am)
+    am_h = am.cpu().numpy()
+    locs = np.column_stack([xs[am_h % nx], ys[am_h // nx]])
+    Theta_h = np.ascontiguousarray(Theta.cpu().numpy().T) if isinstance(Theta, torch.Tensor) else Theta
+    return mx.cpu().numpy().reshape(-1, 1), locs, (W, b, Theta_h)
 
 
 def mcts_root_parallel(mcts, t, seed=None):

@@ -73,6 +73,12 @@ def _worker(rank, size, port, tmp):
         np.save(os.path.join(tmp, 'mcts_%s_local%d.npy' % (f_rew, rank)), planner.local_root_stats)
         if f_rew == 'mes':
             out['mcts_mes_maxes'] = np.asarray(res[6])
+    # max-value sampling with the mesh rows sharded: same features and weights on both ranks, each rank
+    # evaluates its rows, the (max, arg-max) pairs are gathered and reduced
+    rngm = np.random.default_rng(8)
+    xs, ys = rngm.uniform(1, 9, 150), rngm.uniform(1, 9, 131)
+    mv, ml, (Wm, bm, Thm) = parallel.sample_max_vals_shared_sharded(m, xs, ys, nK=12, nFeatures=150, seed=6)
+    out['maxvals'], out['maxlocs'], out['maxvals_theta'] = mv, ml, Thm
     np.savez(os.path.join(tmp, 'rank%d.npz' % rank), **out)
     dist.destroy_process_group()
 
@@ -104,6 +110,15 @@ def test_two_ranks_match_one_gpu(tmp_path):
         np.testing.assert_allclose(r0[mode + '_ucb'], ucb, rtol=1e-12)
         np.testing.assert_allclose(r0[mode + '_mes'], mes, rtol=1e-12)
         np.testing.assert_allclose(r0[mode + '_i8_var'], r0[mode + '_i8_ref_var'], rtol=1e-6)    # operands of the NEW belief
+    # sharded max-value sampling against the one-GPU sampler on the whole mesh with the same seed (the belief the ranks hold
+    # at that point: 500 observations + the 7 appended after the tensor-mode predict)
+    m.add_data(q[:7], np.ones((7, 1)))
+    rngm = np.random.default_rng(8)
+    xs, ys = rngm.uniform(1, 9, 150), rngm.uniform(1, 9, 131)
+    mv1, ml1, (W1, b1, Th1) = aq.sample_max_vals_shared(m, (xs, ys), nK=12, nFeatures=150, rng=np.random.default_rng(6))
+    np.testing.assert_array_equal(r0['maxvals_theta'], Th1)          # deterministic weight draws on every rank
+    np.testing.assert_allclose(r0['maxvals'], mv1, rtol=1e-12)
+    np.testing.assert_array_equal(r0['maxlocs'], ml1)
     for f_rew in ('mean', 'mes'):
         l0, l1 = np.load(tmp_path / ('mcts_%s_local0.npy' % f_rew)), np.load(tmp_path / ('mcts_%s_local1.npy' % f_rew))
         g = r0['mcts_' + f_rew + '_global']

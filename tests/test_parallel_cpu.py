@@ -130,3 +130,56 @@ def test_root_parallel_tree_search_gloo(tmp_path):
         assert a[f_rew + '_value'][0] == means[best]
         np.testing.assert_allclose(a[f_rew + '_all'], means)
     assert a['mes_param'].shape == (3, 1)
+
+
+class _FakeBelief(object):
+    """Stand-in for the replicated device belief in the sharded max-value sampler: the draws only."""
+    variance = 100.0
+
+    def shared_feature_draws(self, nK, nFeatures, rng):
+        W = rng.normal(size=(nFeatures, 2))
+        b = 2 * np.pi * rng.uniform(size=(nFeatures, 1))
+        return W, b, rng.normal(size=(nFeatures, nK))
+
+
+def _numpy_grid_stage(W, b, Theta, variance, xs, ys):
+    gx, gy = np.meshgrid(xs, ys, indexing='xy')
+    grid = np.vstack([gx.ravel(), gy.ravel()]).T
+    vals = (Theta.T * np.sqrt(2 * variance / W.shape[0])) @ np.cos(W @ grid.T + b)
+    return vals.max(axis=1), vals.argmax(axis=1)
+
+
+def _maxvals_worker(rank, size, port, tmp):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    from informative_path_planning_b200 import parallel
+    rng = np.random.default_rng(9)
+    xs, ys = rng.uniform(1, 9, 23), rng.uniform(1, 9, 17)           # 17 mesh rows over 2 ranks: 9 + 8
+    mx, locs, (W, b, Theta) = parallel.sample_max_vals_shared_sharded(_FakeBelief(), xs, ys, nK=6, nFeatures=40, seed=4,
+                                                                      eval_fn=_numpy_grid_stage)
+    # ties across ranks go to the smallest global index, like np.argmax over the whole grid
+    v = torch.tensor([1.0, 5.0, 2.0]) if rank == 0 else torch.tensor([1.0, 3.0, 7.0])
+    i = torch.tensor([40, 11, 12]) if rank == 0 else torch.tensor([7, 50, 3])
+    tv, ti = parallel.combine_sharded_argmax(v.to(torch.float64), i.to(torch.int64))
+    np.savez(os.path.join(tmp, 'mv%d.npz' % rank), mx=mx, locs=locs, W=W, b=b, Theta=Theta, xs=xs, ys=ys,
+             tv=tv.numpy(), ti=ti.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_max_value_sampling_gloo(tmp_path):
+    """Mesh rows sharded over two ranks, (max, arg-max) pairs gathered and reduced: every rank ends with the maxima and
+    locations of the WHOLE mesh, ties resolved like np.argmax."""
+    port = _free_port()
+    mp.spawn(_maxvals_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / 'mv0.npz'), np.load(tmp_path / 'mv1.npz')
+    for k in ('mx', 'locs', 'W', 'b', 'Theta', 'tv', 'ti'):
+        np.testing.assert_array_equal(r0[k], r1[k])
+    want_max, want_arg = _numpy_grid_stage(r0['W'], r0['b'], r0['Theta'], 100.0, r0['xs'], r0['ys'])
+    np.testing.assert_allclose(r0['mx'].ravel(), want_max, rtol=0, atol=0)
+    nx = r0['xs'].shape[0]
+    np.testing.assert_array_equal(r0['locs'], np.column_stack([r0['xs'][want_arg % nx], r0['ys'][want_arg // nx]]))
+    np.testing.assert_array_equal(r0['tv'], [1.0, 5.0, 7.0])
+    np.testing.assert_array_equal(r0['ti'], [7, 11, 3])
