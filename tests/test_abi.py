@@ -296,3 +296,24 @@ def test_stale_library_is_refused(monkeypatch):
     monkeypatch.setattr(L, 'source_hash', lambda: 'edited-after-the-build')
     with pytest.raises(ImportError, match='was not built from the current'):
         L._check_source_stamp()
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_the_device():
+    """Argument validation of the entry points added in round 2 happens on the host: null pointers and impossible shapes
+    come back as IPP_E_INVALID with a message, on a machine without a GPU too (no launch is attempted)."""
+    import ctypes
+    from informative_path_planning_b200 import _lib as L
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)                    # never dereferenced: validation fails first
+    rc = L.lib.ipp_rff_theta_draw(null, one, 200, 2, one, one, 300, 100.0, 0.5, one, 1, one, one, one, null)
+    assert rc != 0 and b'null pointer' in L.lib.ipp_last_error()
+    rc = L.lib.ipp_rff_theta_draw(one, one, 200, 4, one, one, 300, 100.0, 0.5, one, 1, one, one, one, null)
+    assert rc != 0 and b'bad arguments' in L.lib.ipp_last_error()
+    rc = L.lib.ipp_rff_theta_draw(one, one, 200, 2, one, one, 300, 100.0, 0.0, one, 1, one, one, one, null)      # noise 0
+    assert rc != 0
+    rc = L.lib.ipp_rff_eval_argmax_mesh(one, one, one, 100, 3, 2, one, 10, one, 10, 0.0, null, one, one, one, null)   # S < 8
+    assert rc != 0 and b'at least 8 samples' in L.lib.ipp_last_error()
+    rc = L.lib.ipp_rff_eval_argmax_mesh(one, one, one, 100, 16, 2, one, 0, one, 10, 0.0, null, one, one, one, null)
+    assert rc != 0 and b'bad mesh' in L.lib.ipp_last_error()
+    assert L.lib.ipp_rff_theta_workspace(200, 300, 1) > 0 and L.lib.ipp_rff_theta_workspace(200, 300, 100) > L.lib.ipp_rff_theta_workspace(200, 300, 1)
+    assert L.lib.ipp_rff_mesh_workspace(1000, 100, 1024, 1024) > L.lib.ipp_rff_workspace(1000, 100, 1 << 20, 1)
