@@ -95,6 +95,42 @@ __device__ __forceinline__ double rbf_eval(const RbfDev& k, const double* a, con
 }
 
 
+// exp(x), x <= 0, branch-free (several calls interleave in one thread; libdevice's exp is ~2x the instructions, half of
+// them outside the FP64 pipe, with a branch per call): Cody-Waite reduction by ln 2 and the degree-13
+// Taylor polynomial on |f| <= ln 2 / 2 (truncation 4e-18 relative), result scaled by 2^n through the exponent bits.
+// The constants sit in constant memory: FP64 instructions read a constant-bank operand directly, whereas 64-bit
+// immediates are rebuilt in (uniform) registers inside the loop -- 6 extra instructions per call in rbf_queries_kernel.
+// No clamp of the argument: for x < -700 the polynomial may see garbage, the final select discards it.
+static __constant__ double EXPC[18] = {
+    1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+    2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
+    1.6666666666666666e-01, 0.5, 1.0, -700.0};
+__device__ __forceinline__ double exp_neg_exact(double x) {
+    const double tt = fma(x, EXPC[0], EXPC[1]);                               // n = rint(x log2 e) in the low word
+    const int n = __double2loint(tt);
+    const double nf = tt - EXPC[1];
+    double f = fma(nf, EXPC[2], x);
+    f = fma(nf, EXPC[3], f);
+    double p = EXPC[4];                                                       // 1/13!
+#pragma unroll
+    for (int i = 5; i <= 16; ++i) p = fma(p, f, EXPC[i]);                     // ... 1/2!, 1
+    p = fma(p, f, EXPC[16]);
+    const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));   // p in [0.70, 1.42]
+    return x < EXPC[17] ? 0.0 : r;
+}
+
+template <int D>
+__device__ __forceinline__ double rbf_eval_bf(const RbfDev& k, const double* a, const double* b) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double u = (a[d] - b[d]) * k.il[d];
+        r2 = fma(u, u, r2);
+    }
+    return k.variance * exp_neg_exact(-0.5 * r2);
+}
+
 // exp(x) for x <= 0 to ~2^-36 relative (degree-9 Taylor after Cody-Waite reduction): used by the tensor-core modes
 // (3xTF32: operands rounded to 22 bits; sliced INT8: 42-bit fixed point, tolerance 1e-6), where libdevice's < 1 ulp exp
 // (about twice the FP64-pipe instructions) buys nothing.  The FP64 DMMA mode keeps the exact exp.
