@@ -14,31 +14,39 @@
 
 namespace ipp {
 
-// cos(x) in ~14 FP64 instructions, branch-free for |x| < 8e5 (phases here are W . x + b with |x| <= a few tens): Cody-Waite
+// cos(x) in ~21 FP64 instructions, branch-free for |x| < 8e5 (phases here are W . x + b with |x| <= a few tens): Cody-Waite
 // reduction by pi/2 in three pieces (the first two have 33 significant bits, so their products with k < 2^20 are exact),
 // then the fdlibm kernel polynomials on |r| <= pi/4 (< 1 ulp), sine or cosine by the parity of the quadrant with the
 // coefficients selected instead of branching.  libdevice's cos() costs ~2.5x as many FP64-pipe slots -- the pipe the
 // DMMAs of the grid stage share -- and made the feature pass compute-bound (3 ms for 2^20 x 1000 features against 1.3 ms
 // for writing them).
+// (The constants sit in constant memory: an FP64 instruction reads a constant-bank operand directly, whereas the compiler
+// rebuilds every 64-bit immediate in registers at each use -- two moves per constant, ~56 of the 93 instructions this
+// function issued per value, which made the feature pass issue-bound: ncu r5g, issue slots 83 % busy, FP64 pipe 48 %.)
+static __constant__ double COSC[18] = {
+    0.63661977236758134308, 6755399441055744.0,
+    -1.57079632673412561417e+00, -6.07710050630396597660e-11, -2.02226624879595063154e-21,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02, 8.0e5};
 __device__ __forceinline__ double cos_fast(double x) {
-    if (!(fabs(x) < 8.0e5)) return cos(x);
-    const double kf = fma(x, 0.63661977236758134308, 6755399441055744.0);     // k = rint(x 2 / pi) in the low word
+    if (!(fabs(x) < COSC[17])) return cos(x);
+    const double kf = fma(x, COSC[0], COSC[1]);           // k = rint(x 2 / pi) in the low word
     const int k = __double2loint(kf);
-    const double kd = kf - 6755399441055744.0;
-    double r = fma(kd, -1.57079632673412561417e+00, x);
-    r = fma(kd, -6.07710050630396597660e-11, r);
-    r = fma(kd, -2.02226624879595063154e-21, r);
-    const bool odd = (k & 1) != 0;                        // quadrant 0: cos r, 1: -sin r, 2: -cos r, 3: sin r
+    const double kd = kf - COSC[1];
+    double r = fma(kd, COSC[2], x);
+    r = fma(kd, COSC[3], r);
+    r = fma(kd, COSC[4], r);
+    // quadrant 0: cos r, 1: -sin r, 2: -cos r, 3: sin r.  BOTH kernel polynomials are evaluated and the result is selected
+    // at the end (selecting every coefficient by the parity costs four integer-pipe instructions per coefficient).
     const double z = r * r;
-    double p = odd ? 1.58969099521155010221e-10 : -1.13596475577881948265e-11;
-    p = fma(p, z, odd ? -2.50507602534068634195e-08 : 2.08757232129817482790e-09);
-    p = fma(p, z, odd ? 2.75573137070700676789e-06 : -2.75573143513906633035e-07);
-    p = fma(p, z, odd ? -1.98412698298579493134e-04 : 2.48015872894767294178e-05);
-    p = fma(p, z, odd ? 8.33333333332248946124e-03 : -1.38888888888741095749e-03);
-    p = fma(p, z, odd ? -1.66666666666666324348e-01 : 4.16666666666666019037e-02);
-    const double u = (odd ? r : z) * z;                   // r^3 or r^4
-    const double base = odd ? r : fma(-0.5, z, 1.0);
-    const double v = fma(u, p, base);
+    double ps = COSC[5], pc = COSC[11];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) { ps = fma(ps, z, COSC[5 + i]); pc = fma(pc, z, COSC[11 + i]); }
+    const double vs = fma(r * z, ps, r);                  // sin r
+    const double vc = fma(z * z, pc, fma(-0.5, z, 1.0));  // cos r
+    const double v = (k & 1) ? vs : vc;
     return ((k + 1) & 2) ? -v : v;
 }
 
@@ -228,10 +236,9 @@ __global__ void __launch_bounds__(256) rff_phi_kernel(const double* __restrict__
 
 // ---- meshgrid form: grid point g = j nx + i is (xs[i], ys[j]) -- np.meshgrid(xs, ys, indexing='xy') ravelled, the grid
 // of the reference's global_maximization (aq_library.py:455-466).  cos(a_i + c_j) = cos a_i cos c_j - sin a_i sin c_j with
-// a_i = W_f0 xs_i + b_f and c_j = W_f1 ys_j (+ W_f2 t): (nx + ny) F sincos instead of nx ny F cos.  The non-tensor FP64
-// rate of this GPU is 16 lanes per clock and SM (measured: the feature pass of a 2^20 x 1000 grid, 14 FP64 instructions
-// per cos, took the 3.2 ms that rate predicts -- while a pure-write kernel reaches 7.2 TB/s, profiles/r3g_write_bw.log);
-// two multiplies per feature value leave the pass bound by writing Phi.
+// a_i = W_f0 xs_i + b_f and c_j = W_f1 ys_j (+ W_f2 t): (nx + ny) F sincos instead of nx ny F cos.  The general-grid
+// feature pass (14 FP64 instructions per cos) takes 3.2 ms for a 2^20 x 1000 grid, while a pure-write kernel reaches
+// 7.2 TB/s (profiles/r3g_write_bw.log); two multiplies per feature value leave this pass bound by writing Phi.
 template <int D>
 __global__ void rff_mesh_tables_kernel(const double* __restrict__ W, const double* __restrict__ b, int F,
                                        const double* __restrict__ xs, int nx, const double* __restrict__ ys, int ny,

@@ -227,7 +227,7 @@ __device__ __forceinline__ void rf_condition(const RolloutArgs& p, const double*
         if (p.reps[l] > 0 && kb <= 4) {
             // every thread of the FIRST warp factors the (identity-padded) 4 x 4 block redundantly in registers and
             // substitutes its own row (M <= 32: one warp has a lane for every point).  The other warps skip all of it:
-            // non-tensor FP64 issues at four lanes per clock and sub-partition here, so the seven warps that computed
+            // the FP64 pipe of a sub-partition is shared by its two warps, so the seven warps that computed
             // the factorisation for nothing were not free -- warp 4 shares warp 0's pipe.
             // Only the points AFTER this block are ever looked at again: rows / columns >= b1.  (No barrier here: the
             // snapshot above only reads what the barrier that ended the previous level made final.)
