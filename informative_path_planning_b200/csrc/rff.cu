@@ -320,6 +320,9 @@ struct RffGemmArgs {
 // tile row r is mesh column (g0 + r) % nx), the <= RFF_MESH_JT mesh rows the tile touches, and the Theta tile (two
 // stages of 96 KB + 4 KB).  In the 8 x 1 warp layout no warp shares an A fragment with another, so every value is formed
 // exactly once: 8 non-tensor FP64 instructions per k-group and warp beside 52 DMMAs (the pipe they share: + 8 %).
+#ifndef RFF_MESH_LATE_KG
+#define RFF_MESH_LATE_KG (BK / 16)
+#endif
 constexpr int RFF_MESH_JT = 4;                   // mesh rows a 128-point tile may touch (nx >= 64)
 constexpr int RFF_MESH_TB = RFF_MESH_JT * 2 * BK * 8;                          // bytes: [jrel][cos | sin][BK]
 constexpr int RFF_MESH_STAGE = 3 * TILE_BYTES + RFF_MESH_TB;
@@ -386,15 +389,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGem
         }
         load_stage(smem_base, 0);
         cp_async_commit();
+        // the two warps of a sub-partition ask for the next stage in turn (as in gemm_mainloop): the ~300 address and
+        // predicate instructions of a stage's 24 copies issue no DMMA, and with every warp running them right after the
+        // barrier the tensor pipe idled for that long in every k-step (ncu r3l: pipe 75 % busy against 89 % of the
+        // plain GEMM form, a third of the issued instructions in the loader)
+        const bool late_loader = (warp & 4) != 0;
         for (int kt = 0; kt < KT; ++kt) {
             cp_async_wait<0>();
             __syncthreads();                              // stage kt & 1 landed; everybody is done with stage (kt + 1) & 1
-            if (kt + 1 < KT) load_stage(smem_base + ((kt + 1) & 1) * RFF_MESH_STAGE, (kt + 1) * BK);
-            cp_async_commit();
+            if (!late_loader) {
+                if (kt + 1 < KT) load_stage(smem_base + ((kt + 1) & 1) * RFF_MESH_STAGE, (kt + 1) * BK);
+                cp_async_commit();
+            }
             const uint32_t sC = smem_base + (kt & 1) * RFF_MESH_STAGE, sS = sC + TILE_BYTES, sB = sC + 2 * TILE_BYTES;
             const uint32_t sT = sC + 3 * TILE_BYTES;
 #pragma unroll
             for (int kg = 0; kg < BK / 8; ++kg) {
+                if (kg == RFF_MESH_LATE_KG && late_loader) {
+                    if (kt + 1 < KT) load_stage(smem_base + ((kt + 1) & 1) * RFF_MESH_STAGE, (kt + 1) * BK);
+                    cp_async_commit();
+                }
                 const uint32_t chunk = (uint32_t)(((4 * kg + t) ^ ((g & 1) << 2)) << 4);
                 const uint32_t kofs = (uint32_t)((8 * kg + 2 * t) * 8);
                 constexpr int JG = NB > 13 ? NB / 2 : NB;
