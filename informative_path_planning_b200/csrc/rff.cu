@@ -345,38 +345,73 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rff_gemm_argmax_kernel(RffGem
         for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     if constexpr (MESH) {
         const int KT = (p.F + BK - 1) / BK;
-        TileLoader lb;
-        lb.init(p.Th, p.ldf, n0, p.S, tid);
         // loader side: thread (row group r0, chunk column ch) fetches chunk ch of the C and S rows of tile rows r0 + 16 u
         const int ch = tid % CHUNKS_PER_ROW, r0 = tid / CHUNKS_PER_ROW;
         const uint32_t ldst = (uint32_t)(r0 * ROW_BYTES + ((ch ^ ((r0 & 1) << 2)) << 4));
         const int64_t gfirst = p.g0 + m0;
         const int64_t jfirst = gfirst / p.nx;
-        int icol[LOADS_PER_THREAD];              // mesh column of the thread's u-th row, -1 beyond the grid
+        // Everything that does not depend on k, once: 32-bit element offsets of the thread's rows in the tables and in
+        // Theta (0 for a row outside the grid / beyond the samples, with its validity bit clear), so that a copy costs one
+        // 64-bit multiply-add for the address; a stage away from the ragged end of F skips the byte-count logic, and a
+        // tile whose 128 rows are all grid points (every tile of a grid that is a multiple of 128) skips the row tests.
+        int offC[LOADS_PER_THREAD], offB[LOADS_PER_THREAD];
+        unsigned vmask = 0, bmask = 0;
 #pragma unroll
         for (int u = 0; u < LOADS_PER_THREAD; ++u) {
             const int r = r0 + RSTEP * u;
-            icol[u] = (m0 + r < p.Gc) ? (int)((gfirst + r) % p.nx) : -1;
+            const bool okc = m0 + r < p.Gc, okb = n0 + r < p.S;
+            offC[u] = okc ? (int)((gfirst + r) % p.nx) * (int)p.ldf + 2 * ch : 0;
+            offB[u] = okb ? (n0 + r) * (int)p.ldf + 2 * ch : 0;
+            vmask |= (okc ? 1u : 0u) << u;
+            bmask |= (okb ? 1u : 0u) << u;
         }
+        const bool all_rows = vmask == (1u << LOADS_PER_THREAD) - 1u;
+        // the mesh rows: [jrel][cos | sin][BK], 16 bytes per thread of the first RFF_MESH_JT * BK threads
+        const bool jthread = tid < RFF_MESH_JT * 2 * (BK / 2);
+        const int c2 = tid % (BK / 2), jcs = (tid / (BK / 2)) & 1, jrl = tid / BK;
+        const bool okj = jthread && (jfirst + jrl) * p.nx < p.G;
+        const double* jsrc = (jcs ? p.TS : p.TC) + (okj ? (p.nx + jfirst + jrl) * p.ldf + 2 * c2 : 0);
+        const uint32_t jdst = (uint32_t)(3 * TILE_BYTES + ((jrl * 2 + jcs) * BK + 2 * c2) * 8);
         auto load_stage = [&](uint32_t st, int k0) {
-            const int rem = p.F - (k0 + 2 * ch);
-            const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            const double* tc = p.TC + k0;
+            const double* ts = p.TS + k0;
+            const double* th = p.Th + k0;
+            if (k0 + BK <= p.F) {                         // a whole stage: 16 bytes everywhere
+                if (all_rows) {
 #pragma unroll
-            for (int u = 0; u < LOADS_PER_THREAD; ++u) {
-                const bool ok = icol[u] >= 0 && bytes > 0;
-                const int64_t off = ok ? (int64_t)icol[u] * p.ldf + k0 + 2 * ch : 0;
-                cp_async16(st + ldst + u * (RSTEP * ROW_BYTES), p.TC + off, ok ? bytes : 0);
-                cp_async16(st + TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), p.TS + off, ok ? bytes : 0);
-            }
-            lb.load(st + 2 * TILE_BYTES, k0, p.F);
-            if (tid < RFF_MESH_JT * 2 * (BK / 2)) {      // the mesh rows: [jrel][cos | sin][BK], 16 bytes per thread
-                const int c2 = tid % (BK / 2), cs = (tid / (BK / 2)) & 1, jr = tid / BK;
-                const int remj = p.F - (k0 + 2 * c2);
-                const int bj = remj >= 2 ? 16 : (remj == 1 ? 8 : 0);
-                const int64_t jrow = jfirst + jr;
-                const bool okj = bj > 0 && jrow * p.nx < p.G;
-                const double* src = (cs ? p.TS : p.TC) + (okj ? (p.nx + jrow) * p.ldf + k0 + 2 * c2 : 0);
-                cp_async16(st + 3 * TILE_BYTES + (uint32_t)(((jr * 2 + cs) * BK + 2 * c2) * 8), src, okj ? bj : 0);
+                    for (int u = 0; u < LOADS_PER_THREAD; ++u) {
+                        cp_async16(st + ldst + u * (RSTEP * ROW_BYTES), tc + offC[u], 16);
+                        cp_async16(st + TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), ts + offC[u], 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < LOADS_PER_THREAD; ++u) {
+                        const int sz = (int)((vmask >> u) & 1u) << 4;
+                        cp_async16(st + ldst + u * (RSTEP * ROW_BYTES), tc + offC[u], sz);
+                        cp_async16(st + TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), ts + offC[u], sz);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < LOADS_PER_THREAD; ++u)
+                    if (RSTEP * u < 8 * NB)               // (rows >= 8 NB of the Theta tile are never read)
+                        cp_async16(st + 2 * TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), th + offB[u], (int)((bmask >> u) & 1u) << 4);
+                if (jthread) cp_async16(st + jdst, jsrc + k0, okj ? 16 : 0);
+            } else {                                      // the ragged last stage of F
+                const int rem = p.F - (k0 + 2 * ch);
+                const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+#pragma unroll
+                for (int u = 0; u < LOADS_PER_THREAD; ++u) {
+                    const int sz = ((vmask >> u) & 1u) ? bytes : 0;
+                    cp_async16(st + ldst + u * (RSTEP * ROW_BYTES), sz ? tc + offC[u] : p.TC, sz);
+                    cp_async16(st + TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), sz ? ts + offC[u] : p.TS, sz);
+                    const int szb = ((bmask >> u) & 1u) ? bytes : 0;
+                    cp_async16(st + 2 * TILE_BYTES + ldst + u * (RSTEP * ROW_BYTES), szb ? th + offB[u] : p.Th, szb);
+                }
+                if (jthread) {
+                    const int remj = p.F - (k0 + 2 * c2);
+                    const int bj = !okj ? 0 : remj >= 2 ? 16 : (remj == 1 ? 8 : 0);
+                    cp_async16(st + jdst, bj ? jsrc + k0 : p.TC, bj);
+                }
             }
         };
         // consumer side: the two fragment rows of this lane and the mesh row each belongs to
@@ -598,7 +633,8 @@ static int rff_gemm_path(const double* W, const double* b, const double* theta, 
     int64_t* part_idx = reinterpret_cast<int64_t*>(part_val + (int64_t)S * nparts);
     rff_pad_theta_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, s>>>(theta, (int)S, (int)F, Th, ldf);
     IPP_LAUNCH_CHECK();
-    if (TC && rff_mesh_fused() && (BM + nx - 2) / nx + 1 <= RFF_MESH_JT && G < (1LL << 31)) {
+    if (TC && rff_mesh_fused() && (BM + nx - 2) / nx + 1 <= RFF_MESH_JT && G < (1LL << 31) &&
+        (int64_t)nx * ldf < (1LL << 31) && S * ldf < (1LL << 31)) {     // (the loader keeps 32-bit row offsets)
         RffGemmArgs p;                              // one launch over the whole grid: Phi formed in the A fragments
         p.TC = TC; p.TS = TS; p.nx = nx;
         p.Phi = nullptr; p.ldf = ldf; p.Gc = (int)G;
