@@ -339,6 +339,39 @@ def test_predict_against_oracle(pkg, N, M, noise):
         np.testing.assert_allclose(var_d, var_o, rtol=RTOL, atol=1e-8)
 
 
+_RBFQ_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from informative_path_planning_b200 import gpmodel_library as gp
+from oracle import gpmodel_oracle as gpo
+R = (0., 10., 0., 10.)
+for dim, ls, N, M in ((2, 1.0, 333, 1), (2, 1.3, 70, 4097), (3, (1.0, 2.0, 5.0), 129, 35)):
+    rng = np.random.default_rng(N + M)
+    X = rng.uniform(0, 10, (N, dim)); z = rng.normal(0, 3, (N, 1)); q = rng.uniform(-1, 11, (M, dim))
+    d = gp.OnlineGPModel(R, ls, 100.0, noise=0.5, dimension=dim)
+    o = gpo.OnlineGPModelOracle(R, ls, 100.0, noise=0.5, dimension=dim)
+    d.add_data(X, z); o.add_data(X, z)
+    (md, vd), (mo, vo) = d.predict_value(q), o.predict_value(q)
+    np.testing.assert_allclose(md, mo, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(vd, vo, rtol=1e-6, atol=1e-8)
+print('ok')
+"""
+
+
+@pytest.mark.parametrize('mode', ['0', '1', '2'])
+def test_cross_covariance_kernel_forms(pkg, mode):
+    """rbf_queries_kernel: the staged form (2, the default), the global-load form with one wave (1: what beliefs too large
+    for shared memory take) and round 1's grid (0) give the oracle's posterior -- ragged sizes: one query, more queries
+    than resident warps, D = 3.  The form is chosen once per process (IPP_RBFQ_MODE), hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IPP_RBFQ_MODE=mode)
+    out = subprocess.run([sys.executable, '-c', _RBFQ_SCRIPT % root], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stdout + out.stderr
+
+
 def test_variance_formulations_agree(pkg):
     """Symmetric-half, full and Cholesky forms are the same quadratic form (well-conditioned case)."""
     L = pkg._lib
