@@ -89,6 +89,10 @@ struct TileLoader {
     uint32_t dst;          // byte offset of the thread's first chunk inside a tile
     int kcol;              // first k of the thread's chunk column
     unsigned valid;        // bit i: row r + i * RSTEP is inside the matrix
+    bool fast;             // every row of every lane of this warp is inside the matrix and the row step fits 32 bits: a
+                           // whole stage (no ragged k) then needs neither row tests nor byte counts -- 3 instructions per
+                           // copy instead of 14 (the loader's burst is the stretch of a k-step in which a warp issues no DMMA)
+    unsigned rstep32;
 
     __device__ __forceinline__ void init(const double* G, int64_t ld, int row0, int nrows, int tid) {
         const int r = tid / CHUNKS_PER_ROW, ch = tid % CHUNKS_PER_ROW;
@@ -100,8 +104,17 @@ struct TileLoader {
 #pragma unroll
         for (int i = 0; i < LOADS_PER_THREAD; ++i)
             if (row0 + r + i * RSTEP < nrows) valid |= 1u << i;
+        rstep32 = (unsigned)rstep;
+        fast = __all_sync(0xffffffffu, valid == (1u << LOADS_PER_THREAD) - 1u) && rstep * LOADS_PER_THREAD < (1LL << 31);
     }
     __device__ __forceinline__ void load(uint32_t smem_tile, int k0, int kend) const {
+        if (fast && k0 + BK <= kend) {
+            const double* src = base + k0;
+#pragma unroll
+            for (int i = 0; i < LOADS_PER_THREAD; ++i)
+                cp_async16(smem_tile + dst + i * (RSTEP * ROW_BYTES), src + (unsigned)i * rstep32, 16);
+            return;
+        }
         const int rem = kend - (k0 + kcol);
         const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
         const double* src = base + k0;
