@@ -14,7 +14,8 @@
 //   k = 8*kg + 2*t + s for quad-lane t.  A and B use the same map, so the sum is unchanged
 //   and one LDS.128 feeds two DMMA steps.
 // Measured on B200 (r1, N=4096 x 2^20 queries): BK16/4 stages 32.0 TFLOP/s -> lean loader 32.1 ->
-//   + phase-shifted prefetch 32.6 -> BK32/3 stages 33.7 (cuBLAS DGEMM 35.5, DMMA peak 37.2).
+//   + phase-shifted prefetch 32.6 -> BK32/3 stages 33.7 -> (r2) whole-stage / all-rows fast path of the loader 34.0
+//   (cuBLAS DGEMM 35.5, DMMA peak 37.2).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
