@@ -30,8 +30,7 @@ static __constant__ double COSC[18] = {
     8.33333333332248946124e-03, -1.66666666666666324348e-01,
     -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
     -1.38888888888741095749e-03, 4.16666666666666019037e-02, 8.0e5};
-__device__ __forceinline__ double cos_fast(double x) {
-    if (!(fabs(x) < COSC[17])) return cos(x);
+__device__ __forceinline__ double cos_core(double x) {   // |x| < 8e5
     const double kf = fma(x, COSC[0], COSC[1]);           // k = rint(x 2 / pi) in the low word
     const int k = __double2loint(kf);
     const double kd = kf - COSC[1];
@@ -49,6 +48,7 @@ __device__ __forceinline__ double cos_fast(double x) {
     const double v = (k & 1) ? vs : vc;
     return ((k + 1) & 2) ? -v : v;
 }
+__device__ __forceinline__ double cos_fast(double x) { return (fabs(x) < COSC[17]) ? cos_core(x) : cos(x); }
 
 template <int D, int SC>
 __global__ void __launch_bounds__(256) rff_eval_kernel(const double* __restrict__ W, const double* __restrict__ b,
@@ -218,18 +218,41 @@ __global__ void __launch_bounds__(256) rff_phi_kernel(const double* __restrict__
         sx[r][d] = (r0 + r < Gc) ? grid[(g0 + r0 + r) * D + d] : 0.0;
     }
     __syncthreads();
+    // the magnitude test of cos_fast once per (thread, feature) from the block's largest coordinates, the store pointer
+    // advanced instead of recomputed, whole blocks without row tests: ~45 instead of ~65 instructions per value
+    __shared__ double smax[D];
+    if (threadIdx.x < D) {
+        double m = 0.0;
+        for (int r = 0; r < ROWS; ++r) m = fmax(m, fabs(sx[r][threadIdx.x]));
+        smax[threadIdx.x] = m;
+    }
+    __syncthreads();
+    const int rows = (Gc - r0) < ROWS ? (Gc - r0) : ROWS;
     for (int f = threadIdx.x; f < F; f += 256) {
         double w[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) w[d] = W[f * D + d];
         const double bf = b[f];
-#pragma unroll 4
-        for (int r = 0; r < ROWS; ++r) {
-            if (r0 + r >= Gc) break;
-            double ph = bf;
+        double bound = fabs(bf);
 #pragma unroll
-            for (int d = 0; d < D; ++d) ph = fma(w[d], sx[r][d], ph);
-            Phi[(int64_t)(r0 + r) * ldf + f] = cos_fast(ph);
+        for (int d = 0; d < D; ++d) bound = fma(fabs(w[d]), smax[d], bound);
+        double* out = Phi + (int64_t)r0 * ldf + f;
+        if (bound < 7.9e5 && rows == ROWS) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                double ph = bf;
+#pragma unroll
+                for (int d = 0; d < D; ++d) ph = fma(w[d], sx[r][d], ph);
+                *out = cos_core(ph);
+                out += ldf;
+            }
+        } else {
+            for (int r = 0; r < rows; ++r) {
+                double ph = bf;
+#pragma unroll
+                for (int d = 0; d < D; ++d) ph = fma(w[d], sx[r][d], ph);
+                out[(int64_t)r * ldf] = cos_fast(ph);
+            }
         }
     }
 }
